@@ -1,0 +1,128 @@
+/* kart_b200 -- C ABI of the B200 (sm_100a) implementation of Kart's per-read hot path.
+ *
+ * Kart (hsinnan75/Kart v2.5.6) is a monolithic executable without a plugin or FFI layer; the seam this library
+ * replaces is the per-chunk body of ReadMapping(), reference src/Mapping.cpp:513-596: everything between
+ * "chunk read" (GetNextChunk, :506-510) and "format SAM" (OutputPaired/SingledAlignments, :597-599).
+ * The reference functions behind that seam (prototypes in src/structure.h:177-229):
+ *   BWT_Search (structure.h:178), IdentifySeedPairs_FastMode/_SensitiveMode (:189,:191),
+ *   GenerateAlignmentCandidateForIlluminaSeq/ForPacBioSeq (:193,:194), CheckPairedAlignmentCandidates (:182),
+ *   RescueUnpairedAlignment (:198), GenMappingReport (:192), nw_alignment (:229), and from src/Mapping.cpp
+ *   RemoveRedundantCandidates (:317), RemoveUnMatedAlignmentCandidates (:402), CheckPairedFinalAlignments (:429),
+ *   SetPairedAlignmentFlag (:73), SetSingleAlignmentFlag (:49), EvaluateMAPQ (:160).
+ *
+ * Plain C types only; no CUDA, torch or C++ types cross this boundary. All functions return 0 on success or a
+ * negative KB_E* code (kb_strerror). There is no CPU fallback: without a CUDA device every compute entry point fails.
+ * Threading: one kb_ctx_t per device and per host thread (mirrors one ReadMapping pthread, src/Mapping.cpp:716).
+ */
+#ifndef KART_B200_H
+#define KART_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kb_ctx kb_ctx_t;
+
+enum { KB_OK = 0, KB_ENODEV = -1, KB_ECUDA = -2, KB_EINVAL = -3, KB_ENOMEM = -4, KB_ENOINDEX = -5, KB_ECAPACITY = -6, KB_EOVERFLOW = -7, KB_ESTATE = -8 };
+
+/* Host view of the BWA-format index exactly as the reference loads it (src/bwt_index.cpp:16-36,103-122,148-259).
+ * Pointers are borrowed for the duration of kb_upload_index only. */
+typedef struct {
+	uint64_t primary;            /* .bwt header word 0                                    (bwt_index.cpp:114) */
+	uint64_t L2[5];              /* L2[0] = 0, L2[1..4] = .bwt header words 1..4           (:115)              */
+	uint64_t seq_len;            /* = L2[4]                                                (:117)              */
+	const uint32_t* bwt;         /* .bwt payload: interleaved Occ/BWT, 16 words / 128 rows (BWT_Index/bwtindex.c:53) */
+	uint64_t bwt_words;
+	const uint64_t* sa;          /* sampled SA with sa[0] = ~0 prepended, n_sa entries     (bwt_index.cpp:30-34) */
+	uint64_t n_sa;
+	int32_t sa_intv;             /* 32                                                                       */
+	const uint8_t* pac;          /* forward strand, 2 bit/base, l_pac/4+1 bytes            (bwt_index.cpp:156,240) */
+	int64_t l_pac;               /* GenomeSize                                                                */
+	int32_t n_chr;
+	const int64_t* chr_len;      /* bntann1_t::len per sequence, in .ann order             (:244-251)         */
+} kb_index_host_t;
+
+/* Globals of the reference that steer the hot path (src/structure.h:157-170, src/main.cpp:92-104). */
+typedef struct {
+	int32_t min_seed_len;        /* MinSeedLength; <= 0: derive from 2*l_pac as Mapping.cpp:645 does */
+	int32_t max_gaps;            /* -g   [5]    */
+	int32_t max_insert;          /* MaxInsertSize [1500] */
+	int32_t pacbio;              /* -pacbio     */
+	int32_t paired;              /* reads are (mate 1, reverse-complemented mate 2) pairs: ReadMapping's bPairEnd branch (:531) */
+	int32_t multihit;            /* -m          */
+} kb_params_t;
+
+/* One chunk of reads, structure-of-arrays. seq holds the raw read characters back to back; for paired input read 2i+1
+ * is the mate of read 2i and must already be reverse-complemented the way GetNextChunk does (src/GetData.cpp:125-135). */
+typedef struct {
+	int32_t n_reads;
+	const uint8_t* seq;
+	const uint64_t* seq_off;     /* n_reads + 1 offsets into seq */
+} kb_reads_t;
+
+/* What OutputPairedAlignments / OutputSingledAlignments (src/Mapping.cpp:177-315) need to print one read's primary line. */
+typedef struct {
+	int64_t pos;                 /* 1-based leftmost coordinate (Coordinate_t::gPos)                */
+	int64_t mate_pos;            /* RNEXT/PNEXT coordinate, or -1 when the line carries "*\t0\t0"   */
+	int32_t kind;                /* 0: unmapped line, 1: mapped line, 2: no line (score>0 but best report cleared) */
+	int32_t flag;                /* SAM flag                                                        */
+	int32_t chr;                 /* index into the .ann sequence list                               */
+	int32_t mapq;
+	int32_t score, sub_score;    /* AS / XS ; NM = rlen - score                                     */
+	int32_t tlen;
+	int32_t fwd;                 /* Coordinate_t::bDir                                              */
+	uint32_t cig_off;            /* first op in the cigar array                                     */
+	int32_t cig_len;             /* ops: len << 4 | op with BAM op numbers (M=0,I=1,D=2,S=4)        */
+} kb_aln_t;
+
+/* Per pair: contribution to the running insert-size statistic (iPaired/iDistance, src/Mapping.cpp:206-213) and the
+ * closed interval of EstDistance values for which this pair's result is provably unchanged (host-side recurrence,
+ * src/Mapping.cpp:533-540). */
+typedef struct { int32_t counted, absdist, est_lo, est_hi; } kb_pair_stat_t;
+
+/* Caller-owned result buffers (pinned memory makes the copies asynchronous, pageable works too). */
+typedef struct {
+	kb_aln_t* aln;               /* n_reads entries                                    */
+	kb_pair_stat_t* pairs;       /* n_reads/2 entries, may be NULL when not paired     */
+	uint32_t* cigar;             /* cap_cigar entries                                  */
+	uint32_t cap_cigar;
+	uint32_t n_cigar;            /* out: entries used (also set when KB_ECAPACITY is returned) */
+} kb_results_t;
+
+int  kb_init(int device, kb_ctx_t** out);
+void kb_destroy(kb_ctx_t* ctx);
+const char* kb_strerror(int code);
+const char* kb_last_error(kb_ctx_t* ctx);
+
+/* Copies the index to the device and re-blocks it (see kart_b200/csrc/kb_types.h). expand_sa != 0 additionally expands
+ * the sampled SA into a full SA on the device (values identical by construction; the .sa file format is untouched). */
+int  kb_upload_index(kb_ctx_t* ctx, const kb_index_host_t* idx, int expand_sa);
+int  kb_set_params(kb_ctx_t* ctx, const kb_params_t* p);
+int  kb_get_min_seed_len(kb_ctx_t* ctx);
+
+/* The drop-in call: host buffers in, host buffers out (H2D, all kernels, D2H). est holds one EstDistance per pair
+ * (n_reads/2 values) when paired, else it may be NULL. */
+int  kb_map_chunk(kb_ctx_t* ctx, const kb_reads_t* in, const int32_t* est, kb_results_t* out);
+
+/* The same pipeline in three steps, for callers that keep a batch resident in HBM (bench.py's device-timed `value`). */
+int  kb_stage_reads(kb_ctx_t* ctx, const kb_reads_t* in, const int32_t* est);   /* H2D */
+int  kb_run(kb_ctx_t* ctx);                                                      /* kernels only, returns after they finish */
+int  kb_fetch_results(kb_ctx_t* ctx, kb_results_t* out);                         /* D2H */
+
+/* Instrumentation. kb_stage_ms: device time (CUDA events on the context's stream) of each kernel of the last kb_run:
+ * [0] fm_seed [1] sa_locate [2] cand_pair [3] rescue [4] report [5] finalize [6] whole run. Returns entries written.
+ * kb_work: algorithmic work of the last run: [0] extension steps [1] Occ blocks touched (32-byte sectors)
+ * [2] LF steps [3] NW cells [4] seeds [5] NW calls [6] rescue attempts [7] kernels launched. */
+int  kb_stage_ms(kb_ctx_t* ctx, float* ms, int n);
+int  kb_work(kb_ctx_t* ctx, uint64_t* w, int n);
+void* kb_cuda_stream(kb_ctx_t* ctx);
+
+/* Test hook: copy an internal device array of the last run to the host. what: 0 n_seeds(i32) 1 seed_off(u32) 2 segs(KbSeg)
+ * 3 n_cands(i32) 4 cand_off(u32) 5 cands(KbCand) 6 reports(KbReport) 7 res(KbReadRes) 8 cigar(u32) 9 counters(u32[8]).
+ * Returns bytes copied (<= bytes) or a negative error. */
+int64_t kb_debug_fetch(kb_ctx_t* ctx, int what, void* dst, uint64_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,684 @@
+// Gap filling, CIGAR construction and per-read reports (one thread per read, private scratch arena in HBM).
+// Replaces: IdentifyNormalPairs src/AlignmentCandidates.cpp:420 (+ :235,:273,:323,:382), GenerateSimplePairsFromFragmentPair
+// src/KmerAnalysis.cpp:164 (+ :56,:104,:132), nw_alignment src/nw_alignment.cpp:18, GenerateNormalPairAlignment src/tools.cpp:142,
+// Process{Normal,Head,Tail}SequencePair :225,:292,:344, AddNewCigarElements :49, CheckLocalAlignmentQuality :255,
+// GenMappingReport src/AlignmentCandidates.cpp:624, CheckCoordinateValidity :582, GenCoordinateInfo :515, GenerateCIGAR :492.
+//
+// Alignments are never materialised as gapped strings: every consumer in the reference (CIGAR run-length encoding,
+// identity count, the head/tail quality test, leading/trailing gap stripping) is a function of the run list
+// (type,len) plus the number of identical aligned characters, so that is what is carried around.
+#ifndef KB_ALIGN_CUH
+#define KB_ALIGN_CUH
+#include "kb_cand.cuh"
+
+// ---- per-thread stack arena --------------------------------------------------------------------
+struct KbArena
+{
+	u8* base; u64 used, cap; bool ovf;
+	KB_HD void* alloc(u64 bytes)
+	{
+		bytes = (bytes + 15) & ~(u64)15;
+		if (used + bytes > cap) { ovf = true; return nullptr; }
+		void* p = base + used; used += bytes; return p;
+	}
+};
+
+// ---- reference text: Kart's 2G text = forward strand + reverse complement (src/bwt_index.cpp:194-213) ----
+KB_HD int kb_ref_code(const KbIndexDev& ix, i64 p)   // 0..3, or 4 outside [0,2G) (undefined behaviour in the reference)
+{
+	if (p < 0 || p >= ix.G2) return 4;
+	bool rev = p >= ix.G; i64 f = rev ? ix.G2 - 1 - p : p;
+	int c = (KB_LDG(ix.pac + (f >> 2)) >> ((~f & 3) << 1)) & 3;
+	return rev ? 3 - c : c;
+}
+KB_HD u8 kb_code_char(int c) { return c == 0 ? 'A' : (c == 1 ? 'C' : (c == 2 ? 'G' : (c == 3 ? 'T' : 'N'))); }
+
+// ---- run-list accumulator ----------------------------------------------------------------------
+enum { KB_RUN_D = 0, KB_RUN_I = 1, KB_RUN_M = 2 };   // gap in read / gap in genome / aligned column  (CheckLocalAlignmentQuality types 0,1,2)
+struct KbRuns
+{
+	u32* r; int n, cap; int ident, aligned; bool ovf;
+	KB_HD void push(int type, int len)
+	{
+		if (len <= 0) return;
+		if (n > 0 && (int)(r[n - 1] & 3) == type) { r[n - 1] += (u32)len << 2; return; }
+		if (n >= cap) { ovf = true; return; }
+		r[n++] = ((u32)len << 2) | (u32)type;
+	}
+};
+
+// ---- cigar list of one candidate (elements exactly as the reference pushes them into cigar_vec) ----
+struct KbCigar
+{
+	u32* e; int n, cap; bool ovf;
+	KB_HD void push(int len, int op) { if (n >= cap) { ovf = true; return; } e[n++] = ((u32)len << 4) | (u32)op; }
+};
+
+// ================================================================================================
+// IdentifyNormalPairs
+// ================================================================================================
+KB_HD int kb_drop_empty(KbSeg* v, int n) { int w = 0; for (int i = 0; i < n; i++) if (v[i].rlen != 0) v[w++] = v[i]; return w; }
+
+// order[] = indices of v sorted by rpos (insertion sort; lists are short)
+KB_HD void kb_order_by_rpos(const KbSeg* v, int n, i32* order)
+{
+	for (int i = 0; i < n; i++)
+	{
+		int j = i, key = v[i].rpos;
+		while (j > 0 && v[order[j - 1]].rpos > key) { order[j] = order[j - 1]; j--; }
+		order[j] = i;
+	}
+}
+
+KB_HD int kb_drop_shared_rpos(KbSeg* v, int n, i32* order)   // RemoveTandemRepeatSeeds :235
+{
+	if (n < 2) return n;
+	kb_order_by_rpos(v, n, order);
+	bool any = false;
+	for (int i = 0; i < n;)
+	{
+		int j = i + 1; while (j < n && v[order[j]].rpos == v[order[i]].rpos) j++;
+		if (j - i > 1) { any = true; for (int k = i; k < j; k++) v[order[k]].rlen = v[order[k]].glen = 0; }
+		i = j;
+	}
+	return any ? kb_drop_empty(v, n) : n;
+}
+
+KB_HD int kb_drop_translocated(KbSeg* v, int n, i32* order)   // RemoveTranslocatedSeeds :273
+{
+	if (n < 2) return n;
+	kb_order_by_rpos(v, n, order);
+	bool any = false;
+	for (int i = 0; i < n; i++)
+	{
+		if (v[order[i]].rpos == v[i].rpos) continue;
+		any = true;
+		int hi = order[i];
+		for (int j = i + 1; j <= hi; j++) if (order[j] > hi) hi = order[j];
+		int s1 = 0, s2 = 0;
+		for (int k = i; k <= hi; k++) { if (k < order[k]) s1 += v[order[k]].rlen; else s2 += v[order[k]].rlen; }
+		for (int k = i; k <= hi; k++)
+		{
+			bool kill = (s1 > s2) ? (k > order[k]) : (k < order[k]);
+			if (kill) v[order[k]].rlen = v[order[k]].glen = 0;
+		}
+		i = hi;
+	}
+	return any ? kb_drop_empty(v, n) : n;
+}
+
+KB_HD bool kb_resolve_overlap(KbSeg& a, KbSeg& b)   // CheckSeedOverlapping :323
+{
+	bool master = true; int ov;
+	if ((ov = a.rpos + a.rlen - b.rpos) > 0)
+	{
+		if (a.rlen < b.rlen) { master = false; if (a.rlen > ov) a.glen = (a.rlen -= ov); else a.rlen = a.glen = 0; }
+		else if (b.rlen > ov) { b.rpos += ov; b.gpos += ov; b.glen = (b.rlen -= ov); }
+		else b.rlen = b.glen = 0;
+	}
+	if (a.rlen > 0 && b.rlen > 0 && (ov = (int)(a.gpos + a.glen - b.gpos)) > 0)
+	{
+		if (a.glen < b.glen) { master = false; if (a.rlen > ov) a.glen = (a.rlen -= ov); else a.rlen = a.glen = 0; }
+		else if (b.rlen > ov) { b.rpos += ov; b.gpos += ov; b.glen = (b.rlen -= ov); }
+		else b.rlen = b.glen = 0;
+	}
+	return master;
+}
+
+KB_HD int kb_trim_overlaps(KbSeg* v, int n)   // CheckOverlappingSeeds :382
+{
+	if (n < 2) return n;
+	bool any = false;
+	for (int i = 0; i < n;)
+	{
+		if (v[i].rlen > 0)
+		{
+			int rEnd = v[i].rpos + v[i].rlen - 1; i64 gEnd = v[i].gpos + v[i].glen - 1;
+			for (int j = i + 1; j < n; j++)
+			{
+				if (v[j].rlen == 0) continue;
+				if (rEnd < v[j].rpos && gEnd < v[j].gpos) break;
+				if (!kb_resolve_overlap(v[i], v[j])) break;
+			}
+			if (v[i].rlen == 0)
+			{
+				any = true;
+				int p = i - 1; while (p > 0 && v[p].rlen == 0) p--;
+				i = p < 0 ? 0 : p;
+			}
+			else i++;
+		}
+		else { any = true; i++; }
+	}
+	return any ? kb_drop_empty(v, n) : n;
+}
+
+// Expands the simple pairs in `in` (n entries, (gPos,rPos)-sorted) into the full segment list written to `out`
+// (capacity >= 2n+2). glen < 0: whole read against the genome (head/tail get gLen = rLen). Returns the count.
+KB_HD int kb_fill_pairs(int rlen, int glen, KbSeg* in, int n, KbSeg* out, i32* order)
+{
+	int total = 0;
+	if (n > 1)
+	{
+		n = kb_drop_shared_rpos(in, n, order);
+		n = kb_drop_translocated(in, n, order);
+		n = kb_trim_overlaps(in, n);
+		// gap ("normal") pairs in seed order, parked behind the merge output (write index si+gi never reaches read index n+1+gi)
+		KbSeg* gaps = out + n + 1; int ng = 0;
+		for (int i = 0, j = 1; j < n; i++, j++)
+		{
+			int rg = in[j].rpos - (in[i].rpos + in[i].rlen); if (rg < 0) rg = 0;
+			int gg = (int)(in[j].gpos - (in[i].gpos + in[i].glen)); if (gg < 0) gg = 0;
+			if (rg > 0 || gg > 0)
+			{
+				KbSeg g; g.simple = 0; g.rpos = in[i].rpos + in[i].rlen; g.gpos = in[i].gpos + in[i].glen; g.rlen = rg; g.glen = gg;
+				gaps[ng++] = g;
+			}
+		}
+		// std::inplace_merge(:449) == stable merge of the two runs by (gPos,rPos)
+		int si = 0, gi = 0;
+		while (si < n && gi < ng) { if (kb_less_gpos(gaps[gi], in[si])) out[total++] = gaps[gi++]; else out[total++] = in[si++]; }
+		while (si < n) out[total++] = in[si++];
+		while (gi < ng) out[total++] = gaps[gi++];
+	}
+	else { for (int i = 0; i < n; i++) out[i] = in[i]; total = n; }
+	if (total > 0)
+	{
+		int rg = out[0].rpos > 0 ? out[0].rpos : 0;
+		int gg = glen > 0 ? (int)out[0].gpos : rg;
+		if (rg > 0 || gg > 0)
+		{
+			KbSeg h; h.simple = 0; h.rpos = 0; h.gpos = out[0].gpos - gg; if (h.gpos < 0) h.gpos = 0;
+			h.rlen = rg; h.glen = gg;
+			for (int i = total; i > 0; i--) out[i] = out[i - 1];
+			out[0] = h; total++;
+		}
+		const KbSeg t = out[total - 1];
+		rg = rlen - (t.rpos + t.rlen);
+		gg = glen > 0 ? glen - (int)(t.gpos + t.glen) : rg;
+		if (rg > 0 || gg > 0)
+		{
+			KbSeg e; e.simple = 0; e.rpos = t.rpos + t.rlen; e.gpos = t.gpos + t.glen; e.rlen = rg; e.glen = gg;
+			out[total++] = e;
+		}
+	}
+	return total;
+}
+
+// ================================================================================================
+// 8-mer partition of a fragment pair
+// ================================================================================================
+#define KB_NOKMER 0xFFFFFFFFu
+
+// w[p] = word id of the 8-mer starting at p (exactly as CreateKmerVecFromReadSeq computes it, including the
+// fresh-vs-rolled distinction for non-ACGTN characters), KB_NOKMER where the window holds a literal 'N' or runs off the end.
+KB_HD void kb_kmer_ids(int len, const u8* ch, u32* w)
+{
+	for (int i = 0; i < len; i++) w[i] = KB_NOKMER;
+	int run = 0; u32 id = 0;
+	for (int t = 0; t < len; t++)
+	{
+		u8 c = ch[t];
+		if (c == 'N') { run = 0; continue; }
+		run++;
+		if (run < 8) continue;
+		if (run == 8) { id = 0; for (int i = t - 7; i <= t; i++) id = (id << 2) + (u32)kb_nt4(ch[i]); }
+		else id = ((id & 0x3FFF) << 2) + (u32)kb_nt4(c);
+		w[t - 7] = id;
+	}
+}
+
+// Exact-match runs of common 8-mers, emitted in (PosDiff,rPos) order like GenerateSimplePairsFromCommonKmers(:132):
+// a pair (r,g) exists iff both 8-mers exist, ids are equal and |g-r| < max_shift (IdentifyCommonKmers :118).
+KB_HD int kb_kmer_pairs(const u32* w1, int len1, const u32* w2, int len2, int max_shift, int min_len, KbSeg* out, int cap, bool* ovf)
+{
+	int n = 0;
+	int n1 = len1 - 7, n2 = len2 - 7;   // number of candidate start positions
+	if (n1 <= 0 || n2 <= 0) return 0;
+	int dlo = -(n1 - 1), dhi = n2 - 1;
+	if (dlo < -(max_shift - 1)) dlo = -(max_shift - 1);
+	if (dhi > max_shift - 1) dhi = max_shift - 1;
+	for (int d = dlo; d <= dhi; d++)
+	{
+		int r0 = d < 0 ? -d : 0, r1 = n1 < n2 - d ? n1 : n2 - d;   // r in [r0, r1)
+		int run = 0;
+		for (int r = r0; r <= r1; r++)
+		{
+			bool m = r < r1 && w1[r] != KB_NOKMER && w1[r] == w2[r + d];
+			if (m) run++;
+			else if (run > 0)
+			{
+				int l = 8 + run - 1;
+				if (l >= min_len)
+				{
+					if (n < cap) { KbSeg s; s.simple = 1; s.rpos = r - run; s.gpos = (i64)(r - run + d); s.rlen = s.glen = l; out[n++] = s; }
+					else *ovf = true;
+				}
+				run = 0;
+			}
+		}
+	}
+	return n;
+}
+
+// ================================================================================================
+// Needleman-Wunsch, integer recurrence with all scores doubled (exactly equivalent to the float DP of
+// nw_alignment.cpp because every value there is a multiple of 0.5), 2-bit traceback.
+// ================================================================================================
+KB_HD void kb_nw(const u8* c1, int m, const u8* c2, int n, KbArena& ar, KbRuns& acc, unsigned long long* cells)
+{
+	*cells += (unsigned long long)m * n;
+	u64 mark = ar.used;
+	int* S = (int*)ar.alloc((u64)(n + 1) * 4);
+	int* T = (int*)ar.alloc((u64)(n + 1) * 4);
+	u8* code2 = (u8*)ar.alloc((u64)n + 1);
+	u64 stride = ((u64)n + 3) >> 2;
+	u8* tb = (u8*)ar.alloc(stride * (u64)m);
+	u32* rev = (u32*)ar.alloc((u64)(m + n) * 4);
+	if (ar.ovf) { ar.used = mark; return; }
+	const int NEG = -131072;
+	S[0] = 0; T[0] = 0;
+	for (int j = 1; j <= n; j++) { S[j] = -2 - j; T[j] = NEG; code2[j] = (u8)kb_nt4(c2[j - 1]); }
+	for (int i = 1; i <= m; i++)
+	{
+		int a = kb_nt4(c1[i - 1]);
+		int diag = S[0], left_s = -2 - i, left_r = NEG;   // S[i-1][0] ; S[i][0] ; R[i][0]
+		S[0] = left_s; T[0] = left_s;
+		u8* row = tb + stride * (u64)(i - 1);
+		u8 pack = 0;
+		for (int j = 1; j <= n; j++)
+		{
+			int r = left_r - 1 > left_s - 3 ? left_r - 1 : left_s - 3;
+			int t = T[j] - 1 > S[j] - 3 ? T[j] - 1 : S[j] - 3;
+			int d = diag + (a == code2[j] ? 3 : -3);
+			int s = d > r ? d : r; if (t > s) s = t;
+			diag = S[j]; S[j] = s; T[j] = t; left_s = s; left_r = r;
+			int bits = (s == r ? 1 : 0) | (s == t ? 2 : 0);
+			int q = (j - 1) & 3;
+			pack |= (u8)(bits << (q << 1));
+			if (q == 3 || j == n) { row[(j - 1) >> 2] = pack; pack = 0; }
+		}
+	}
+	// traceback (:59-72): gap-in-read first, then gap-in-genome, else diagonal
+	int i = m, j = n, nr = 0; int ident = 0, aligned = 0;
+	int cur = -1, len = 0;
+	while (i > 0 || j > 0)
+	{
+		int type;
+		if (i == 0) type = KB_RUN_D;
+		else if (j == 0) type = KB_RUN_I;
+		else
+		{
+			int bits = (tb[stride * (u64)(i - 1) + ((j - 1) >> 2)] >> (((j - 1) & 3) << 1)) & 3;
+			type = (bits & 1) ? KB_RUN_D : ((bits & 2) ? KB_RUN_I : KB_RUN_M);
+		}
+		if (type == KB_RUN_D) j--;
+		else if (type == KB_RUN_I) i--;
+		else { i--; j--; aligned++; if (c1[i] == c2[j]) ident++; }
+		if (type == cur) len++;
+		else { if (len > 0) rev[nr++] = ((u32)len << 2) | (u32)cur; cur = type; len = 1; }
+	}
+	if (len > 0) rev[nr++] = ((u32)len << 2) | (u32)cur;
+	for (int k = nr - 1; k >= 0; k--) acc.push((int)(rev[k] & 3), (int)(rev[k] >> 2));
+	acc.ident += ident; acc.aligned += aligned;
+	ar.used = mark;
+}
+
+// ================================================================================================
+// GenerateNormalPairAlignment: optional 8-mer partition, then NW on what is left. Appends to acc.
+// f1 = read characters [0,rl), f2 = reference characters [0,gl).
+// ================================================================================================
+struct KbFragCtx { const KbParams* pm; KbArena* ar; unsigned long long* cells; u32* nw_calls; };
+
+// work-stack entry: a sub-fragment (offsets into f1 / f2) and what to do with it
+enum { KB_W_FRAG = 0, KB_W_NW = 1, KB_W_COPY = 2, KB_W_INS = 3, KB_W_DEL = 4 };
+struct KbWork { i32 r0, rl, g0, gl, kind, pad; };
+
+// The reference recurses (tools.cpp:197, pacbio pieces > 300); here the recursion is an explicit depth-first work stack
+// so that pieces are appended to `acc` in exactly the reference's left-to-right order.
+KB_HD void kb_align_fragments(const KbFragCtx& fc, const u8* f1, int rl0, const u8* f2, int gl0, KbRuns& acc)
+{
+	KbArena& ar = *fc.ar;
+	u64 mark0 = ar.used;
+	int scap = rl0 + gl0 + 4;
+	KbWork* st = (KbWork*)ar.alloc((u64)scap * sizeof(KbWork));
+	if (st == nullptr) return;
+	int sp = 0;
+	{ KbWork w; w.r0 = 0; w.rl = rl0; w.g0 = 0; w.gl = gl0; w.kind = KB_W_FRAG; w.pad = 0; st[sp++] = w; }
+	while (sp > 0 && !ar.ovf)
+	{
+		const KbWork e = st[--sp];
+		const u8* a = f1 + e.r0; const u8* b = f2 + e.g0;
+		if (e.kind == KB_W_INS) { acc.push(KB_RUN_I, e.rl); continue; }
+		if (e.kind == KB_W_DEL) { acc.push(KB_RUN_D, e.gl); continue; }
+		if (e.kind == KB_W_COPY)
+		{
+			int id = 0; for (int t = 0; t < e.rl; t++) if (a[t] == b[t]) id++;
+			acc.push(KB_RUN_M, e.rl); acc.ident += id; acc.aligned += e.rl;
+			continue;
+		}
+		if (e.kind == KB_W_FRAG && e.rl > 30 && e.gl > 30)
+		{
+			int rl = e.rl, gl = e.gl, shift;
+			if (fc.pm->pacbio) { shift = rl > gl ? (int)(rl * 0.2) : (int)(gl * 0.2); if (shift > 50) shift = 50; }
+			else shift = fc.pm->max_gaps;
+			u64 mark = ar.used;
+			u32* w1 = (u32*)ar.alloc((u64)rl * 4); u32* w2 = (u32*)ar.alloc((u64)gl * 4);
+			int cap = ((rl < gl ? rl : gl) / 9 + 2) * (2 * shift + 1);   // exact-match runs on one diagonal start >= 9 apart
+			if (cap > rl + gl) cap = rl + gl;
+			KbSeg* raw = (KbSeg*)ar.alloc((u64)cap * sizeof(KbSeg));
+			if (ar.ovf) break;
+			kb_kmer_ids(rl, a, w1); kb_kmer_ids(gl, b, w2);
+			bool povf = false;
+			int np = kb_kmer_pairs(w1, rl, w2, gl, shift, 8, raw, cap, &povf);
+			if (povf) { ar.ovf = true; break; }
+			int tot = 0; KbSeg* part = nullptr;
+			if (np > 0)
+			{
+				kb_sort_segs<true>(raw, np);
+				part = (KbSeg*)ar.alloc((u64)(2 * np + 2) * sizeof(KbSeg));
+				i32* order = (i32*)ar.alloc((u64)np * 4);
+				if (ar.ovf) break;
+				tot = kb_fill_pairs(rl, gl, raw, np, part, order);
+			}
+			if (tot > 0)
+			{
+				if (sp + tot > scap) { ar.ovf = true; break; }
+				for (int i = tot - 1; i >= 0; i--)   // reversed, so that pops come out left to right
+				{
+					const KbSeg p = part[i];
+					if (p.rlen <= 0 && p.glen <= 0) continue;
+					KbWork w; w.r0 = e.r0 + p.rpos; w.rl = p.rlen; w.g0 = e.g0 + (i32)p.gpos; w.gl = p.glen; w.pad = 0;
+					if (p.glen == 0) w.kind = KB_W_INS;
+					else if (p.rlen == 0) w.kind = KB_W_DEL;
+					else if ((p.rlen == 1 && p.glen == 1) || p.simple) w.kind = KB_W_COPY;
+					else if (fc.pm->pacbio && (p.rlen > 300 || p.glen > 300)) w.kind = KB_W_FRAG;
+					else w.kind = KB_W_NW;
+					st[sp++] = w;
+				}
+				ar.used = mark;
+				continue;
+			}
+			ar.used = mark;
+		}
+		(*fc.nw_calls)++;
+		kb_nw(a, e.rl, b, e.gl, ar, acc, fc.cells);
+	}
+	ar.used = mark0;
+}
+
+// ================================================================================================
+// Fragment-pair processing
+// ================================================================================================
+struct KbReadCtx
+{
+	const KbIndexDev* ix; const KbParams* pm; KbArena* ar;
+	const u8* seq; int rlen;
+	unsigned long long cells; u32 nw_calls;
+};
+
+// reference characters [gpos, gpos+len) into arena memory
+KB_HD u8* kb_fetch_ref(KbReadCtx& rc, i64 gpos, int len)
+{
+	u8* f = (u8*)rc.ar->alloc((u64)(len > 0 ? len : 1));
+	if (f == nullptr) return nullptr;
+	for (int i = 0; i < len; i++) f[i] = kb_code_char(kb_ref_code(*rc.ix, gpos + i));
+	return f;
+}
+
+KB_HD int kb_mismatches(const u8* a, const u8* b, int n) { int c = 0; for (int i = 0; i < n; i++) if (a[i] != b[i]) c++; return c; }
+
+// AddNewCigarElements: run list -> cigar elements (D/I/M), returns identity count
+KB_HD int kb_push_runs(const KbRuns& acc, int first, int last, KbCigar& cg)
+{
+	for (int k = first; k < last; k++)
+	{
+		int t = (int)(acc.r[k] & 3), len = (int)(acc.r[k] >> 2);
+		cg.push(len, t == KB_RUN_D ? KB_OP_D : (t == KB_RUN_I ? KB_OP_I : KB_OP_M));
+	}
+	return acc.ident;
+}
+
+KB_HD bool kb_init_runs(KbReadCtx& rc, KbRuns& acc, int rl, int gl)
+{
+	acc.cap = rl + gl + 2; acc.n = 0; acc.ident = 0; acc.aligned = 0; acc.ovf = false;
+	acc.r = (u32*)rc.ar->alloc((u64)acc.cap * 4);
+	return acc.r != nullptr;
+}
+
+KB_HD void kb_align(KbReadCtx& rc, const u8* f1, int rl, const u8* f2, int gl, KbRuns& acc)
+{
+	KbFragCtx fc; fc.pm = rc.pm; fc.ar = rc.ar; fc.cells = &rc.cells; fc.nw_calls = &rc.nw_calls;
+	kb_align_fragments(fc, f1, rl, f2, gl, acc);
+	if (acc.ovf) rc.ar->ovf = true;
+}
+
+// quick test of tools.cpp:240/301/352: equal length, <= 2 mismatches and <= 20 %
+KB_HD bool kb_quick_match(const u8* f1, const u8* f2, int rl, int gl, int* n)
+{
+	if (rl != gl) return false;
+	*n = kb_mismatches(f1, f2, rl);
+	return *n <= 2 && *n <= (int)(rl * 0.2);
+}
+
+KB_HD int kb_do_middle(KbReadCtx& rc, KbSeg& sp, KbCigar& cg)   // ProcessNormalSequencePair :225
+{
+	if (sp.rlen == 0 || sp.glen == 0)
+	{
+		if (sp.rlen > 0) cg.push(sp.rlen, KB_OP_I); else if (sp.glen > 0) cg.push(sp.glen, KB_OP_D);
+		return 0;
+	}
+	u64 mark = rc.ar->used; int score = 0, n;
+	const u8* f1 = rc.seq + sp.rpos; u8* f2 = kb_fetch_ref(rc, sp.gpos, sp.glen);
+	if (f2 != nullptr)
+	{
+		if (kb_quick_match(f1, f2, sp.rlen, sp.glen, &n)) { cg.push(sp.rlen, KB_OP_M); score = sp.rlen - n; }
+		else
+		{
+			KbRuns acc;
+			if (kb_init_runs(rc, acc, sp.rlen, sp.glen)) { kb_align(rc, f1, sp.rlen, f2, sp.glen, acc); score = kb_push_runs(acc, 0, acc.n, cg); }
+		}
+	}
+	rc.ar->used = mark;
+	return score;
+}
+
+// CheckLocalAlignmentQuality :255 on the run list
+KB_HD bool kb_quality_ok(const KbRuns& acc)
+{
+	int mis = acc.aligned - acc.ident;
+	return !(acc.n >= 4 || (mis >= 3 && mis >= (int)(acc.aligned * 0.3)));
+}
+
+KB_HD int kb_do_head(KbReadCtx& rc, KbSeg& sp, KbCigar& cg)   // ProcessHeadSequencePair :292
+{
+	u64 mark = rc.ar->used; int score = 0, n;
+	const u8* f1 = rc.seq + sp.rpos; u8* f2 = kb_fetch_ref(rc, sp.gpos, sp.glen);
+	if (f2 != nullptr)
+	{
+		if (!rc.pm->pacbio && kb_quick_match(f1, f2, sp.rlen, sp.glen, &n)) { cg.push(sp.rlen, KB_OP_M); score = sp.rlen - n; }
+		else if (!rc.pm->pacbio && sp.rlen > 50) cg.push(sp.rlen, KB_OP_S);
+		else
+		{
+			KbRuns acc;
+			if (kb_init_runs(rc, acc, sp.rlen, sp.glen))
+			{
+				kb_align(rc, f1, sp.rlen, f2, sp.glen, acc);
+				if (!kb_quality_ok(acc)) cg.push(sp.rlen, KB_OP_S);
+				else
+				{
+					int first = 0;
+					// leading gaps in the read block shrink the genome block; then leading gaps in the genome block become a soft clip
+					if (first < acc.n && (acc.r[first] & 3) == KB_RUN_D) { int p = (int)(acc.r[first] >> 2); sp.gpos += p; sp.glen -= p; first++; }
+					if (first < acc.n && (acc.r[first] & 3) == KB_RUN_I) { int p = (int)(acc.r[first] >> 2); sp.rpos += p; sp.rlen -= p; cg.push(p, KB_OP_S); first++; }
+					score = kb_push_runs(acc, first, acc.n, cg);
+				}
+			}
+		}
+	}
+	rc.ar->used = mark;
+	return score;
+}
+
+KB_HD int kb_do_tail(KbReadCtx& rc, KbSeg& sp, KbCigar& cg)   // ProcessTailSequencePair :344
+{
+	u64 mark = rc.ar->used; int score = 0, n;
+	const u8* f1 = rc.seq + sp.rpos; u8* f2 = kb_fetch_ref(rc, sp.gpos, sp.glen);
+	if (f2 != nullptr)
+	{
+		if (!rc.pm->pacbio && kb_quick_match(f1, f2, sp.rlen, sp.glen, &n)) { cg.push(sp.rlen, KB_OP_M); score = sp.rlen - n; }
+		else if (!rc.pm->pacbio && sp.rlen > 100) cg.push(sp.rlen, KB_OP_S);
+		else
+		{
+			KbRuns acc;
+			if (kb_init_runs(rc, acc, sp.rlen, sp.glen))
+			{
+				kb_align(rc, f1, sp.rlen, f2, sp.glen, acc);
+				if (!kb_quality_ok(acc)) cg.push(sp.rlen, KB_OP_S);
+				else
+				{
+					int last = acc.n, clip = 0;
+					if (last > 0 && (acc.r[last - 1] & 3) == KB_RUN_D) { int c = (int)(acc.r[last - 1] >> 2); sp.glen -= c; last--; }
+					if (last > 0 && (acc.r[last - 1] & 3) == KB_RUN_I) { clip = (int)(acc.r[last - 1] >> 2); sp.rlen -= clip; last--; }
+					score = kb_push_runs(acc, 0, last, cg);
+					if (clip > 0) cg.push(clip, KB_OP_S);
+				}
+			}
+		}
+	}
+	rc.ar->used = mark;
+	return score;
+}
+
+// ================================================================================================
+// Reports
+// ================================================================================================
+KB_HD bool kb_same_chromosome(const KbIndexDev& ix, const KbSeg* v, int n)   // CheckCoordinateValidity :582
+{
+	i64 a = 0, b = ix.G2;
+	for (int i = 0; i < n; i++) if (v[i].glen > 0) { a = v[i].gpos; break; }
+	for (int i = n - 1; i >= 0; i--) if (v[i].glen > 0) { b = v[i].gpos + v[i].glen - 1; break; }
+	if ((a < ix.G) != (b < ix.G)) return false;
+	int ea = kb_chr_lookup(ix, a), eb = kb_chr_lookup(ix, b);
+	return ea < ix.n_ends && eb < ix.n_ends && ix.end_chr[ea] == ix.end_chr[eb];
+}
+
+// GenCoordinateInfo + GenerateCIGAR: writes the merged cigar into the global arena
+KB_HD void kb_locate_report(const KbIndexDev& ix, const KbBatchDev& bt, bool first, i64 gpos, i64 gend, KbCigar& cg, KbReport& rp)
+{
+	bool rev = gpos >= ix.G;
+	if (!rev)
+	{
+		rp.fwd = first ? 1 : 0;
+		if (ix.n_chr == 1) { rp.chr = 0; rp.pos = gpos + 1; }
+		else { int e = kb_chr_lookup(ix, gpos); rp.chr = ix.end_chr[e]; rp.pos = gpos + 1 - ix.chr_fwd[rp.chr]; }
+	}
+	else
+	{
+		rp.fwd = first ? 0 : 1;
+		if (ix.n_chr == 1) { rp.chr = 0; rp.pos = ix.G2 - gend; }
+		else { int e = kb_chr_lookup(ix, gpos); rp.pos = ix.end_key[e] - gend + 1; rp.chr = ix.end_chr[e]; }
+	}
+	// merge equal neighbours (elements are visited back to front for the reverse strand)
+	int merged = 0;
+	{
+		int prev = -1;
+		for (int k = 0; k < cg.n; k++) { int op = (int)(cg.e[rev ? cg.n - 1 - k : k] & 15); if (op != prev) { merged++; prev = op; } }
+	}
+	u32 off = KB_ATOMIC_ADD(&bt.counters[2], (u32)merged);
+	rp.cig_off = off; rp.cig_len = merged;
+	if ((u64)off + (u64)merged > (u64)bt.cap_cigar) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_CIGAR); rp.cig_len = 0; return; }
+	int w = -1, prev = -1;
+	for (int k = 0; k < cg.n; k++)
+	{
+		u32 e = cg.e[rev ? cg.n - 1 - k : k]; int op = (int)(e & 15);
+		if (op != prev) { w++; bt.cigar[off + w] = e; prev = op; }
+		else bt.cigar[off + w] += (e >> 4) << 4;
+	}
+}
+
+// GenMappingReport for one read. cands/reports are this read's slices.
+KB_HD void kb_report_read(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int r, KbArena& ar)
+{
+	KbReadRes& rd = bt.res[r];
+	KbCand* cv = bt.cands + bt.cand_off[r];
+	KbReport* rep = bt.reports + bt.cand_off[r];
+	int ncan = bt.n_cands[r];
+	bool first = pm.paired ? ((r & 1) == 0) : true;
+	KbReadCtx rc; rc.ix = &ix; rc.pm = &pm; rc.ar = &ar; rc.seq = bt.seq + bt.seq_off[r]; rc.rlen = (int)(bt.seq_off[r + 1] - bt.seq_off[r]);
+	rc.cells = 0; rc.nw_calls = 0;
+	rd.score = 0; rd.sub = 0; rd.best = 0; rd.mapq = 0; rd.rep_off = bt.cand_off[r];
+	if (ncan == 0)
+	{
+		rd.ncan = 1;
+		KbReport z; z.pos = 0; z.aln = 0; z.flag = 0; z.mate = -1; z.chr = 0; z.cig_off = 0; z.cig_len = 0; z.fwd = 1; z.pad = 0;
+		rep[0] = z;
+		return;
+	}
+	rd.ncan = ncan;
+	for (int i = 0; i < ncan; i++)
+	{
+		KbReport rp; rp.pos = 0; rp.aln = 0; rp.flag = 0; rp.mate = cv[i].mate; rp.chr = 0; rp.cig_off = 0; rp.cig_len = 0; rp.fwd = 1; rp.pad = 0;
+		rep[i] = rp;
+		if (cv[i].score == 0) continue;
+		if (pm.pacbio && rd.score > 0) { rd.sub = rd.score; continue; }
+		u64 mark = ar.used;
+		int ns = cv[i].nseg;
+		KbSeg* in = (KbSeg*)ar.alloc((u64)(ns > 0 ? ns : 1) * sizeof(KbSeg));
+		KbSeg* sv = (KbSeg*)ar.alloc((u64)(2 * ns + 2) * sizeof(KbSeg));
+		i32* order = (i32*)ar.alloc((u64)(ns > 0 ? ns : 1) * 4);
+		KbCigar cg; cg.n = 0; cg.ovf = false; cg.cap = 3 * rc.rlen + 2 * ns + 64; cg.e = (u32*)ar.alloc((u64)cg.cap * 4);
+		if (ar.ovf) { ar.used = mark; break; }
+		for (int k = 0; k < ns; k++) in[k] = bt.segs[cv[i].seg_start + k];
+		int n = kb_fill_pairs(rc.rlen, -1, in, ns, sv, order);
+		if (kb_same_chromosome(ix, sv, n))
+		{
+			for (int j = 0; j < n; j++)
+			{
+				if (sv[j].rlen == 0 && sv[j].glen == 0) continue;
+				if (sv[j].simple) { cg.push(sv[j].rlen, KB_OP_M); rp.aln += sv[j].rlen; continue; }
+				if (j == 0)
+				{
+					int s = 0;
+					if (sv[0].rlen > 3000) cg.push(sv[0].rlen, KB_OP_S);
+					else { s = kb_do_head(rc, sv[0], cg); rp.aln += s; }
+					if (s == 0) { sv[0].gpos = sv[1].gpos; sv[0].glen = 0; }
+				}
+				else if (j == n - 1)
+				{
+					int s = 0;
+					if (sv[j].rlen > 3000) cg.push(sv[j].rlen, KB_OP_S);
+					else { s = kb_do_tail(rc, sv[j], cg); rp.aln += s; }
+					if (s == 0) { sv[j].gpos = sv[j - 1].gpos + sv[j - 1].glen; sv[j].glen = 0; }
+				}
+				else rp.aln += kb_do_middle(rc, sv[j], cg);
+			}
+			if (cg.ovf) ar.ovf = true;
+			bool dead = false;
+			if (!pm.pacbio && cg.n > 1)
+			{
+				int gp = 0; for (int k = 0; k < cg.n; k++) { int op = (int)(cg.e[k] & 15); if (op == KB_OP_I || op == KB_OP_D) gp += (int)(cg.e[k] >> 4); }
+				rp.aln -= gp;
+				if (rp.aln <= 0) { rp.aln = 0; dead = true; }
+			}
+			if (!dead)
+			{
+				if (cg.n == 0) rp.aln = 0;
+				else { kb_locate_report(ix, bt, first, sv[0].gpos, sv[n - 1].gpos + sv[n - 1].glen - 1, cg, rp); if (rp.pos <= 0) rp.aln = 0; }
+				if (rp.aln > rd.score) { rd.best = i; rd.sub = rd.score; rd.score = rp.aln; }
+				else if (rp.aln == rd.score)
+				{
+					rd.sub = rd.score;
+					if (!pm.multihit && ix.chr_len[rp.chr] > ix.chr_len[rep[rd.best].chr]) rd.best = i;
+				}
+			}
+		}
+		rep[i] = rp;
+		ar.used = mark;
+		if (ar.ovf) break;
+	}
+	if (rc.cells) KB_ATOMIC_ADD(&bt.work[3], rc.cells);
+	if (rc.nw_calls) KB_ATOMIC_ADD(&bt.counters[6], rc.nw_calls);
+}
+
+#endif

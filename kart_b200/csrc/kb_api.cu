@@ -1,0 +1,420 @@
+// kart_b200: CUDA kernels (sm_100a) and the C ABI declared in include/kart_b200.h.
+// One context = one device, one stream. The pipeline of a batch is six kernels with no host round trip in between:
+//   k_fm_seed -> k_sa_locate -> k_cand_pair -> k_rescue -> k_report -> k_finalize
+// Capacities of the bump-allocated arenas are checked on the device; a batch that overflowed anything is rerun with
+// larger arenas (never silently truncated, never sent to a CPU path -- there is none).
+#ifndef KB_EMUL
+#include <cuda_runtime.h>
+#define KB_LAUNCH(kern, grid, block, stream, ...) kern<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#else   // host emulation build for the CPU-only test container (tests/emul/cuda_shim.h); never part of the product library
+#define KB_LAUNCH(kern, grid, block, stream, ...) kb_emul_launch((grid), (block), [&]() { kern(__VA_ARGS__); })
+#endif
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../include/kart_b200.h"
+#include "kb_stages.cuh"
+
+#define KB_BLOCK 128
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void kb_warp_add64(unsigned long long* dst, unsigned long long v)
+{
+#ifndef KB_EMUL
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+	if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst, v);
+#else
+	*dst += v;
+#endif
+}
+
+__global__ void __launch_bounds__(KB_BLOCK) k_fm_seed(KbIndexDev ix, KbParams pm, KbBatchDev bt)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	u32 steps = 0, blocks = 0;
+	if (r < bt.n_reads) kb_seed_read(ix, pm, bt, r, &steps, &blocks);
+	kb_warp_add64(&bt.work[0], steps); kb_warp_add64(&bt.work[1], blocks);
+}
+
+__global__ void __launch_bounds__(KB_BLOCK) k_sa_locate(KbIndexDev ix, KbBatchDev bt)
+{
+	long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	u32 lf = 0;
+	if (t < (long long)bt.n_reads * bt.max_hits) kb_locate_hit(ix, bt, (int)(t / bt.max_hits), (int)(t % bt.max_hits), &lf);
+	kb_warp_add64(&bt.work[2], lf);
+}
+
+// expands the sampled SA into a full one (upload time only)
+__global__ void k_expand_sa(KbIndexDev ix, u64* full)
+{
+	u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k > ix.seq_len) return;
+	u32 steps; full[k] = kb_sa(ix, k, &steps);
+}
+
+// re-blocks the BWA Occ/BWT interleave (16 words / 128 rows, u64 counts) into 8 words / 64 rows with u32 counts
+__global__ void k_reblock(const u32* bwt, u64 bwt_words, u64 n_new, u32* occ)
+{
+	u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n_new) return;
+	u64 ob = (j >> 1) * 16; int half = (int)(j & 1);
+	u32 cnt[4], w[8];
+	for (int c = 0; c < 4; c++) { u64 i = ob + 2 * c; cnt[c] = i < bwt_words ? bwt[i] : 0; }   // low words of the u64 counts (checked < 2^32 on the host)
+	for (int k = 0; k < 8; k++) { u64 i = ob + 8 + k; w[k] = i < bwt_words ? bwt[i] : 0; }
+	if (half)
+	{
+		kb_count32(((u64)w[0] << 32) | w[1], 32, cnt);
+		kb_count32(((u64)w[2] << 32) | w[3], 32, cnt);
+	}
+	u32* o = occ + j * 8;
+	o[0] = cnt[0]; o[1] = cnt[1]; o[2] = cnt[2]; o[3] = cnt[3];
+	for (int k = 0; k < 4; k++) o[4 + k] = w[4 * half + k];
+}
+
+__global__ void __launch_bounds__(KB_BLOCK) k_cand_pair(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_cand_pair(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x); }
+__global__ void __launch_bounds__(KB_BLOCK) k_cand_pacbio(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_cand_pacbio(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
+__global__ void __launch_bounds__(KB_BLOCK) k_rescue(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_rescue(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
+__global__ void __launch_bounds__(KB_BLOCK) k_report(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_report(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
+__global__ void __launch_bounds__(KB_BLOCK) k_finalize(KbIndexDev ix, KbParams pm, KbBatchDev bt, kb_aln_t* aln) { kb_stage_finalize(ix, pm, bt, aln, blockIdx.x * blockDim.x + threadIdx.x); }
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+template <class T>
+struct DevBuf
+{
+	T* p = nullptr; size_t n = 0;
+	cudaError_t ensure(size_t want) { if (want <= n) return cudaSuccess; if (p) cudaFree(p); p = nullptr; n = 0; cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T)); if (e == cudaSuccess) n = want; return e; }
+	void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct kb_ctx
+{
+	int device = 0; cudaStream_t stream = nullptr; std::string err;
+	bool have_index = false; KbIndexDev ix; KbParams pm;
+	DevBuf<u32> occ; DevBuf<u64> sa, sa_full; DevBuf<u8> pac, lut; DevBuf<i64> chr64; DevBuf<i32> chr32;
+	int64_t l_pac = 0;
+	// batch
+	KbBatchDev bt; bool staged = false, ran = false; int n_reads = 0; size_t seq_bytes = 0;
+	DevBuf<u8> seq, scratch; DevBuf<u64> seq_off; DevBuf<unsigned long long> work; DevBuf<i32> est, n_hits, n_seeds, n_cands, cand_cap, rescue; DevBuf<u32> seed_off, cand_off, cigar, counters;
+	DevBuf<KbHit> hits; DevBuf<KbSeg> segs; DevBuf<KbCand> cands; DevBuf<KbReport> reports; DevBuf<KbReadRes> res; DevBuf<KbPairStat> pstat; DevBuf<kb_aln_t> aln;
+	size_t cap_segs = 0, cap_cands = 0, cap_cigar = 0, scratch_per_thread = 0; int scratch_threads = 0; int max_rlen = 0;
+	double seg_factor = 32, cigar_factor = 8, scratch_factor = 1;
+	cudaEvent_t ev[8]; float stage_ms[7]; uint64_t work_host[8]; u32 counters_host[8]; int launches = 0;
+};
+
+static int fail(kb_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess)
+{
+	char buf[512];
+	if (e != cudaSuccess) snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e)); else snprintf(buf, sizeof(buf), "%s", what);
+	if (c) c->err = buf;
+	return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, e_ == cudaErrorMemoryAllocation ? KB_ENOMEM : KB_ECUDA, #call, e_); } while (0)
+
+extern "C" {
+
+const char* kb_strerror(int code)
+{
+	switch (code)
+	{
+	case KB_OK: return "ok";
+	case KB_ENODEV: return "no CUDA device (this library has no CPU path)";
+	case KB_ECUDA: return "CUDA runtime error";
+	case KB_EINVAL: return "invalid argument";
+	case KB_ENOMEM: return "out of device memory";
+	case KB_ENOINDEX: return "index not uploaded";
+	case KB_ECAPACITY: return "result buffer too small";
+	case KB_EOVERFLOW: return "device arena overflow persisted after regrowth";
+	case KB_ESTATE: return "call out of order";
+	default: return "unknown error";
+	}
+}
+
+const char* kb_last_error(kb_ctx_t* ctx) { return ctx ? ctx->err.c_str() : ""; }
+
+int kb_init(int device, kb_ctx_t** out)
+{
+	if (!out) return KB_EINVAL;
+	*out = nullptr;
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return KB_ENODEV;
+	if (device < 0 || device >= n) return KB_EINVAL;
+	kb_ctx* ctx = new kb_ctx();
+	ctx->device = device;
+	memset(&ctx->ix, 0, sizeof(ctx->ix)); memset(&ctx->bt, 0, sizeof(ctx->bt)); memset(ctx->stage_ms, 0, sizeof(ctx->stage_ms)); memset(ctx->work_host, 0, sizeof(ctx->work_host));
+	ctx->pm.min_seed = 0; ctx->pm.max_gaps = 5; ctx->pm.max_insert = 1500; ctx->pm.pacbio = 0; ctx->pm.multihit = 0; ctx->pm.paired = 0;
+	if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return KB_ECUDA; }
+	for (int i = 0; i < 8; i++) cudaEventCreate(&ctx->ev[i]);
+	*out = ctx;
+	return KB_OK;
+}
+
+void kb_destroy(kb_ctx_t* ctx)
+{
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	ctx->occ.release(); ctx->sa.release(); ctx->sa_full.release(); ctx->pac.release(); ctx->lut.release(); ctx->chr64.release(); ctx->chr32.release();
+	ctx->seq.release(); ctx->scratch.release(); ctx->seq_off.release(); ctx->work.release(); ctx->est.release(); ctx->n_hits.release(); ctx->n_seeds.release();
+	ctx->n_cands.release(); ctx->cand_cap.release(); ctx->rescue.release(); ctx->seed_off.release(); ctx->cand_off.release(); ctx->cigar.release(); ctx->counters.release();
+	ctx->hits.release(); ctx->segs.release(); ctx->cands.release(); ctx->reports.release(); ctx->res.release(); ctx->pstat.release(); ctx->aln.release();
+	for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->ev[i]);
+	cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+static int derive_min_seed(int64_t l_pac)   // src/Mapping.cpp:645
+{
+	int m; double two_g = (double)(l_pac * 2);
+	for (m = 13; m < 16; m++) if (two_g < pow(4, m)) break;
+	return m;
+}
+
+int kb_upload_index(kb_ctx_t* ctx, const kb_index_host_t* h, int expand_sa)
+{
+	if (!ctx || !h || !h->bwt || !h->sa || !h->pac || h->n_chr <= 0 || !h->chr_len || h->sa_intv <= 0 || (h->sa_intv & (h->sa_intv - 1))) return fail(ctx, KB_EINVAL, "kb_upload_index: bad index description");
+	CK(cudaSetDevice(ctx->device));
+	for (int c = 1; c <= 4; c++) if (h->L2[c] - h->L2[c - 1] >= 0xFFFFFFFFull) return fail(ctx, KB_EINVAL, "kb_upload_index: a base count exceeds 2^32-1 (u32 Occ layout)");
+	KbIndexDev& ix = ctx->ix; memset(&ix, 0, sizeof(ix));
+	ix.primary = h->primary; for (int i = 0; i < 5; i++) ix.L2[i] = h->L2[i]; ix.seq_len = h->seq_len;
+	// Occ re-blocking on the device
+	u64 n_new = (h->seq_len >> 6) + 2;
+	{
+		DevBuf<u32> raw;
+		CK(raw.ensure(h->bwt_words)); CK(ctx->occ.ensure(n_new * 8));
+		CK(cudaMemcpyAsync(raw.p, h->bwt, h->bwt_words * 4, cudaMemcpyHostToDevice, ctx->stream));
+		KB_LAUNCH(k_reblock, (unsigned)((n_new + 255) / 256), 256, ctx->stream, raw.p, h->bwt_words, n_new, ctx->occ.p);
+		CK(cudaGetLastError()); CK(cudaStreamSynchronize(ctx->stream));
+		raw.release();
+	}
+	ix.occ = ctx->occ.p; ix.n_blocks = n_new;
+	CK(ctx->sa.ensure(h->n_sa)); CK(cudaMemcpyAsync(ctx->sa.p, h->sa, h->n_sa * 8, cudaMemcpyHostToDevice, ctx->stream));
+	ix.sa = ctx->sa.p; ix.n_sa = h->n_sa; ix.sa_intv = h->sa_intv; ix.sa_full = nullptr;
+	size_t pac_bytes = (size_t)(h->l_pac / 4 + 1);
+	CK(ctx->pac.ensure(pac_bytes)); CK(cudaMemcpyAsync(ctx->pac.p, h->pac, pac_bytes, cudaMemcpyHostToDevice, ctx->stream));
+	ix.pac = ctx->pac.p; ix.G = h->l_pac; ix.G2 = h->l_pac * 2; ctx->l_pac = h->l_pac;
+	// chromosome tables: ChrLocMap (src/bwt_index.cpp:250-251) as a sorted key array
+	int nc = h->n_chr, ne = 2 * nc;
+	std::vector<i64> t64((size_t)ne + 3 * nc); std::vector<i32> t32(ne);
+	i64* key = t64.data(); i64* fwd = key + ne; i64* rev = fwd + nc; i64* len = rev + nc;
+	i64 total = 0;
+	for (int i = 0; i < nc; i++) { len[i] = h->chr_len[i]; fwd[i] = total; total += len[i]; rev[i] = ix.G2 - total; }
+	for (int i = 0; i < nc; i++) { key[i] = fwd[i] + len[i] - 1; t32[i] = i; }                       // forward ends ascend with i
+	for (int i = 0; i < nc; i++) { int c = nc - 1 - i; key[nc + i] = rev[c] + len[c] - 1; t32[nc + i] = c; }   // reverse ends ascend with descending i
+	CK(ctx->chr64.ensure(t64.size())); CK(ctx->chr32.ensure(t32.size()));
+	CK(cudaMemcpyAsync(ctx->chr64.p, t64.data(), t64.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaMemcpyAsync(ctx->chr32.p, t32.data(), t32.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+	ix.n_chr = nc; ix.n_ends = ne; ix.end_key = ctx->chr64.p; ix.chr_fwd = ctx->chr64.p + ne; ix.chr_rev = ix.chr_fwd + nc; ix.chr_len = ix.chr_rev + nc; ix.end_chr = ctx->chr32.p;
+	// MAPQ table with the reference expression (src/Mapping.cpp:172), evaluated by the host libm exactly like the reference
+	const int lut_scores = 1 << 16;
+	std::vector<u8> lut((size_t)lut_scores * 5, 0);
+	for (int s = 1; s < lut_scores; s++)
+		for (int d = 1; d <= 5 && d < s; d++)
+		{
+			int score = s, sub = s - d;
+			int q = (int)(30 * (1 - (float)(score - sub) / score) * log(score) + 0.4999);
+			lut[(size_t)s * 5 + d - 1] = (u8)(q > 60 ? 60 : (q < 0 ? 0 : q));
+		}
+	CK(ctx->lut.ensure(lut.size())); CK(cudaMemcpyAsync(ctx->lut.p, lut.data(), lut.size(), cudaMemcpyHostToDevice, ctx->stream));
+	ix.mapq_lut = ctx->lut.p; ix.mapq_lut_scores = lut_scores;
+	CK(cudaStreamSynchronize(ctx->stream));
+	if (expand_sa)
+	{
+		CK(ctx->sa_full.ensure(h->seq_len + 1));
+		KB_LAUNCH(k_expand_sa, (unsigned)((h->seq_len + 256) / 256), 256, ctx->stream, ix, ctx->sa_full.p);
+		CK(cudaGetLastError()); CK(cudaStreamSynchronize(ctx->stream));
+		ix.sa_full = ctx->sa_full.p;
+	}
+	if (ctx->pm.min_seed <= 0) ctx->pm.min_seed = derive_min_seed(h->l_pac);
+	ctx->have_index = true;
+	return KB_OK;
+}
+
+int kb_set_params(kb_ctx_t* ctx, const kb_params_t* p)
+{
+	if (!ctx || !p) return KB_EINVAL;
+	ctx->pm.max_gaps = p->max_gaps < 0 ? 0 : p->max_gaps; ctx->pm.max_insert = p->max_insert > 0 ? p->max_insert : 1500;
+	ctx->pm.pacbio = p->pacbio ? 1 : 0; ctx->pm.multihit = p->multihit ? 1 : 0; ctx->pm.paired = (p->paired && !p->pacbio) ? 1 : 0;
+	ctx->pm.min_seed = p->min_seed_len > 0 ? p->min_seed_len : (ctx->have_index ? derive_min_seed(ctx->l_pac) : 0);
+	return KB_OK;
+}
+
+int kb_get_min_seed_len(kb_ctx_t* ctx) { return ctx ? ctx->pm.min_seed : KB_EINVAL; }
+void* kb_cuda_stream(kb_ctx_t* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+static int alloc_batch(kb_ctx* ctx)
+{
+	size_t n = (size_t)ctx->n_reads; KbBatchDev& bt = ctx->bt;
+	int L = ctx->max_rlen > 0 ? ctx->max_rlen : 1;
+	int max_hits = ctx->pm.pacbio ? L / ctx->pm.min_seed + 2 : L / (ctx->pm.min_seed + 1) + 2;
+	ctx->cap_segs = (size_t)(ctx->seg_factor * (double)n) + (ctx->pm.pacbio ? (size_t)n * (size_t)(L / 8 + 64) : 0) + 65536;
+	if (ctx->cap_segs > 0xF0000000ull) ctx->cap_segs = 0xF0000000ull;
+	ctx->cap_cands = 2 * ctx->cap_segs + 2 * n + 1024;
+	if (ctx->cap_cands > 0xF0000000ull) ctx->cap_cands = 0xF0000000ull;
+	ctx->cap_cigar = (size_t)(ctx->cigar_factor * (double)n) + (ctx->pm.pacbio ? (size_t)n * (size_t)(L / 2) : 0) + 65536;
+	// per-thread scratch of the report / rescue kernels: NW traceback (2 bit / cell) dominates
+	double side = L < 3100 ? L + 64 : 3100 + 64;
+	size_t per = (size_t)(side * side / 4) + (size_t)L * 160 + (64 << 10);
+	if (ctx->pm.pacbio) per += (size_t)L * 64;
+	per = (size_t)((double)per * ctx->scratch_factor); per = (per + 255) & ~(size_t)255;
+	size_t budget = (size_t)24 << 30;
+	size_t threads = budget / per; if (threads > 148 * 1024) threads = 148 * 1024;
+	size_t need_threads = ctx->pm.paired ? n : n; if (threads > need_threads) threads = need_threads;
+	threads = (threads + KB_BLOCK - 1) / KB_BLOCK * KB_BLOCK; if (threads < KB_BLOCK) threads = KB_BLOCK;
+	ctx->scratch_per_thread = per; ctx->scratch_threads = (int)threads;
+	CK(ctx->hits.ensure(n * max_hits)); CK(ctx->n_hits.ensure(n)); CK(ctx->n_seeds.ensure(n)); CK(ctx->seed_off.ensure(n));
+	CK(ctx->segs.ensure(ctx->cap_segs)); CK(ctx->cands.ensure(ctx->cap_cands)); CK(ctx->reports.ensure(ctx->cap_cands));
+	CK(ctx->n_cands.ensure(n)); CK(ctx->cand_off.ensure(n)); CK(ctx->cand_cap.ensure(n)); CK(ctx->rescue.ensure(n / 2 + 1));
+	CK(ctx->res.ensure(n)); CK(ctx->pstat.ensure(n / 2 + 1)); CK(ctx->aln.ensure(n)); CK(ctx->cigar.ensure(ctx->cap_cigar));
+	CK(ctx->counters.ensure(8)); CK(ctx->work.ensure(4)); CK(ctx->scratch.ensure(per * threads));
+	bt.n_reads = ctx->n_reads; bt.seq = ctx->seq.p; bt.seq_off = ctx->seq_off.p; bt.est = ctx->est.p;
+	bt.hits = ctx->hits.p; bt.max_hits = max_hits; bt.n_hits = ctx->n_hits.p; bt.n_seeds = ctx->n_seeds.p; bt.seed_off = ctx->seed_off.p;
+	bt.segs = ctx->segs.p; bt.cap_segs = (u32)ctx->cap_segs; bt.cands = ctx->cands.p; bt.cap_cands = (u32)ctx->cap_cands; bt.n_cands = ctx->n_cands.p;
+	bt.cand_off = ctx->cand_off.p; bt.cand_cap = ctx->cand_cap.p; bt.rescue_list = ctx->rescue.p; bt.reports = ctx->reports.p; bt.res = ctx->res.p; bt.pstat = ctx->pstat.p;
+	bt.cigar = ctx->cigar.p; bt.cap_cigar = (u32)ctx->cap_cigar; bt.scratch = ctx->scratch.p; bt.scratch_per_thread = per; bt.scratch_threads = (int)threads;
+	bt.max_rlen = L; bt.nw_max_m = 0; bt.nw_max_n = 0; bt.seg_cap = 0; bt.kmer_cap = 0; bt.counters = ctx->counters.p; bt.work = ctx->work.p;
+	return KB_OK;
+}
+
+int kb_stage_reads(kb_ctx_t* ctx, const kb_reads_t* in, const int32_t* est)
+{
+	if (!ctx || !in || in->n_reads < 0 || (in->n_reads > 0 && (!in->seq || !in->seq_off))) return fail(ctx, KB_EINVAL, "kb_stage_reads: bad arguments");
+	if (!ctx->have_index) return fail(ctx, KB_ENOINDEX, "kb_stage_reads: no index");
+	if (ctx->pm.paired && ((in->n_reads & 1) || (in->n_reads > 0 && !est))) return fail(ctx, KB_EINVAL, "kb_stage_reads: paired chunks need an even read count and one EstDistance per pair");
+	CK(cudaSetDevice(ctx->device));
+	ctx->n_reads = in->n_reads; ctx->staged = false; ctx->ran = false;
+	size_t n = (size_t)in->n_reads;
+	ctx->seq_bytes = n ? (size_t)in->seq_off[n] : 0;
+	int L = 0; for (size_t i = 0; i < n; i++) { u64 l = in->seq_off[i + 1] - in->seq_off[i]; if (l > 0x7FFFFFF0ull) return fail(ctx, KB_EINVAL, "read too long"); if ((int)l > L) L = (int)l; }
+	ctx->max_rlen = L;
+	CK(ctx->seq.ensure(ctx->seq_bytes + 64)); CK(ctx->seq_off.ensure(n + 1)); CK(ctx->est.ensure(n / 2 + 1));
+	if (n)
+	{
+		CK(cudaMemcpyAsync(ctx->seq.p, in->seq, ctx->seq_bytes, cudaMemcpyHostToDevice, ctx->stream));
+		CK(cudaMemcpyAsync(ctx->seq_off.p, in->seq_off, (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+		if (ctx->pm.paired) CK(cudaMemcpyAsync(ctx->est.p, est, (n / 2) * 4, cudaMemcpyHostToDevice, ctx->stream));
+	}
+	ctx->staged = true;
+	return KB_OK;
+}
+
+static int launch_pipeline(kb_ctx* ctx)
+{
+	KbBatchDev& bt = ctx->bt; const KbIndexDev& ix = ctx->ix; const KbParams& pm = ctx->pm;
+	int n = ctx->n_reads; cudaStream_t s = ctx->stream;
+	CK(cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(u32), s)); CK(cudaMemsetAsync(ctx->work.p, 0, 4 * sizeof(u64), s));
+	unsigned g_reads = (unsigned)((n + KB_BLOCK - 1) / KB_BLOCK);
+	unsigned g_items = pm.paired ? (unsigned)((n / 2 + KB_BLOCK - 1) / KB_BLOCK) : g_reads;
+	unsigned g_hits = (unsigned)(((long long)n * bt.max_hits + KB_BLOCK - 1) / KB_BLOCK);
+	unsigned g_scr = (unsigned)(bt.scratch_threads / KB_BLOCK);
+	ctx->launches = 0;
+	CK(cudaEventRecord(ctx->ev[0], s));
+	KB_LAUNCH(k_fm_seed, g_reads, KB_BLOCK, s, ix, pm, bt); ctx->launches++;
+	CK(cudaEventRecord(ctx->ev[1], s));
+	KB_LAUNCH(k_sa_locate, g_hits, KB_BLOCK, s, ix, bt); ctx->launches++;
+	CK(cudaEventRecord(ctx->ev[2], s));
+	KB_LAUNCH(k_cand_pair, g_items, KB_BLOCK, s, ix, pm, bt); ctx->launches++;
+	if (pm.pacbio) { KB_LAUNCH(k_cand_pacbio, g_scr, KB_BLOCK, s, ix, pm, bt); ctx->launches++; }
+	CK(cudaEventRecord(ctx->ev[3], s));
+	if (pm.paired) { KB_LAUNCH(k_rescue, g_scr, KB_BLOCK, s, ix, pm, bt); ctx->launches++; }
+	CK(cudaEventRecord(ctx->ev[4], s));
+	KB_LAUNCH(k_report, g_scr, KB_BLOCK, s, ix, pm, bt); ctx->launches++;
+	CK(cudaEventRecord(ctx->ev[5], s));
+	KB_LAUNCH(k_finalize, g_items, KB_BLOCK, s, ix, pm, bt, ctx->aln.p); ctx->launches++;
+	CK(cudaEventRecord(ctx->ev[6], s));
+	CK(cudaGetLastError());
+	return KB_OK;
+}
+
+int kb_run(kb_ctx_t* ctx)
+{
+	if (!ctx) return KB_EINVAL;
+	if (!ctx->staged) return fail(ctx, KB_ESTATE, "kb_run: no staged reads");
+	CK(cudaSetDevice(ctx->device));
+	memset(ctx->stage_ms, 0, sizeof(ctx->stage_ms)); memset(ctx->work_host, 0, sizeof(ctx->work_host));
+	if (ctx->n_reads == 0) { ctx->ran = true; memset(ctx->counters_host, 0, sizeof(ctx->counters_host)); return KB_OK; }
+	for (int attempt = 0; attempt < 6; attempt++)
+	{
+		int rc = alloc_batch(ctx); if (rc) return rc;
+		rc = launch_pipeline(ctx); if (rc) return rc;
+		CK(cudaMemcpyAsync(ctx->counters_host, ctx->counters.p, 8 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+		unsigned long long w[4];
+		CK(cudaMemcpyAsync(w, ctx->work.p, 4 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+		u32 st = ctx->counters_host[3];
+		if (st == 0)
+		{
+			for (int i = 0; i < 6; i++) cudaEventElapsedTime(&ctx->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]);
+			cudaEventElapsedTime(&ctx->stage_ms[6], ctx->ev[0], ctx->ev[6]);
+			ctx->work_host[0] = w[0]; ctx->work_host[1] = w[1]; ctx->work_host[2] = w[2]; ctx->work_host[3] = w[3];
+			ctx->work_host[4] = ctx->counters_host[0]; ctx->work_host[5] = ctx->counters_host[6]; ctx->work_host[6] = ctx->counters_host[7]; ctx->work_host[7] = (uint64_t)ctx->launches;
+			ctx->ran = true;
+			return KB_OK;
+		}
+		// something overflowed: grow what was flagged and run the batch again
+		if (st & (KB_OVF_SEEDS | KB_OVF_CANDS | KB_OVF_HITS)) ctx->seg_factor *= 4;
+		if (st & KB_OVF_CIGAR) ctx->cigar_factor *= 4;
+		if (st & (KB_OVF_SCRATCH | KB_OVF_NW | KB_OVF_RESCUE)) ctx->scratch_factor *= 2;
+	}
+	return fail(ctx, KB_EOVERFLOW, "kb_run: arenas still overflow after regrowth");
+}
+
+int kb_fetch_results(kb_ctx_t* ctx, kb_results_t* out)
+{
+	if (!ctx || !out) return KB_EINVAL;
+	if (!ctx->ran) return fail(ctx, KB_ESTATE, "kb_fetch_results: nothing has run");
+	CK(cudaSetDevice(ctx->device));
+	size_t n = (size_t)ctx->n_reads;
+	out->n_cigar = n ? ctx->counters_host[2] : 0;
+	if (n == 0) return KB_OK;
+	if (!out->aln || (out->n_cigar > 0 && !out->cigar)) return fail(ctx, KB_EINVAL, "kb_fetch_results: missing buffers");
+	if (out->n_cigar > out->cap_cigar) return fail(ctx, KB_ECAPACITY, "kb_fetch_results: cigar buffer too small");
+	CK(cudaMemcpyAsync(out->aln, ctx->aln.p, n * sizeof(kb_aln_t), cudaMemcpyDeviceToHost, ctx->stream));
+	if (out->n_cigar) CK(cudaMemcpyAsync(out->cigar, ctx->cigar.p, (size_t)out->n_cigar * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	if (ctx->pm.paired && out->pairs) CK(cudaMemcpyAsync(out->pairs, ctx->pstat.p, (n / 2) * sizeof(kb_pair_stat_t), cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return KB_OK;
+}
+
+int kb_map_chunk(kb_ctx_t* ctx, const kb_reads_t* in, const int32_t* est, kb_results_t* out)
+{
+	int rc = kb_stage_reads(ctx, in, est); if (rc) return rc;
+	rc = kb_run(ctx); if (rc) return rc;
+	return kb_fetch_results(ctx, out);
+}
+
+int kb_stage_ms(kb_ctx_t* ctx, float* ms, int n) { if (!ctx || !ms) return KB_EINVAL; int k = n < 7 ? n : 7; for (int i = 0; i < k; i++) ms[i] = ctx->stage_ms[i]; return k; }
+int kb_work(kb_ctx_t* ctx, uint64_t* w, int n) { if (!ctx || !w) return KB_EINVAL; int k = n < 8 ? n : 8; for (int i = 0; i < k; i++) w[i] = ctx->work_host[i]; return k; }
+
+int64_t kb_debug_fetch(kb_ctx_t* ctx, int what, void* dst, uint64_t bytes)
+{
+	if (!ctx || !dst) return KB_EINVAL;
+	if (!ctx->ran) return KB_ESTATE;
+	cudaSetDevice(ctx->device);
+	size_t n = (size_t)ctx->n_reads; const void* src = nullptr; size_t have = 0;
+	switch (what)
+	{
+	case 0: src = ctx->n_seeds.p; have = n * 4; break;
+	case 1: src = ctx->seed_off.p; have = n * 4; break;
+	case 2: src = ctx->segs.p; have = (size_t)ctx->counters_host[0] * sizeof(KbSeg); break;
+	case 3: src = ctx->n_cands.p; have = n * 4; break;
+	case 4: src = ctx->cand_off.p; have = n * 4; break;
+	case 5: src = ctx->cands.p; have = (size_t)ctx->counters_host[1] * sizeof(KbCand); break;
+	case 6: src = ctx->reports.p; have = (size_t)ctx->counters_host[1] * sizeof(KbReport); break;
+	case 7: src = ctx->res.p; have = n * sizeof(KbReadRes); break;
+	case 8: src = ctx->cigar.p; have = (size_t)ctx->counters_host[2] * 4; break;
+	case 9: src = ctx->counters.p; have = 8 * 4; break;
+	default: return KB_EINVAL;
+	}
+	if (have > bytes) have = bytes;
+	if (have && cudaMemcpy(dst, src, have, cudaMemcpyDeviceToHost) != cudaSuccess) return KB_ECUDA;
+	return (int64_t)have;
+}
+
+} // extern "C"

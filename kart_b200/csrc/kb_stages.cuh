@@ -1,0 +1,170 @@
+// Per-thread bodies of the pipeline kernels (k_cand_pair, k_cand_pacbio, k_rescue, k_report, k_finalize in kb_api.cu).
+// Kept as KB_HD functions so that tests/emul can run the identical logic on the host next to the oracle.
+#ifndef KB_STAGES_CUH
+#define KB_STAGES_CUH
+#include "../../include/kart_b200.h"
+#include "kb_pair.cuh"
+
+// seeds -> sorted seeds -> candidates -> pairing (one thread per pair, or per read when not paired)
+KB_HD void kb_stage_cand_pair(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int t)
+{
+	if (pm.paired)
+	{
+		int np = bt.n_reads >> 1; if (t >= np) return;
+		int ra = 2 * t, rb = ra + 1;
+		int s1 = bt.n_seeds[ra], s2 = bt.n_seeds[rb];
+		int cap = s1 + s2 + 1;
+		u32 off = KB_ATOMIC_ADD(&bt.counters[1], (u32)(2 * cap));
+		bt.cand_off[ra] = off; bt.cand_off[rb] = off + cap; bt.cand_cap[ra] = cap; bt.cand_cap[rb] = cap;
+		bt.n_cands[ra] = 0; bt.n_cands[rb] = 0;
+		KbPairStat st; st.counted = 0; st.absdist = 0; st.est_lo = -2147483647 - 1; st.est_hi = 2147483647; bt.pstat[t] = st;
+		if ((u64)off + 2ull * cap > (u64)bt.cap_cands) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_CANDS); bt.cand_off[ra] = 0; bt.cand_off[rb] = 0; return; }
+		if (bt.counters[3] & (KB_OVF_SEEDS | KB_OVF_HITS)) return;
+		KbSeg* v1 = bt.segs + bt.seed_off[ra]; KbSeg* v2 = bt.segs + bt.seed_off[rb];
+		kb_sort_segs<false>(v1, s1); kb_sort_segs<false>(v2, s2);
+		int l1 = (int)(bt.seq_off[ra + 1] - bt.seq_off[ra]), l2 = (int)(bt.seq_off[rb + 1] - bt.seq_off[rb]);
+		KbCand* a = bt.cands + off; KbCand* b = a + cap;
+		int n1 = kb_cands_illumina(ix, pm, l1, v1, s1, bt.seed_off[ra], a, cap);
+		int n2 = kb_cands_illumina(ix, pm, l2, v2, s2, bt.seed_off[rb], b, cap);
+		bt.n_cands[ra] = n1; bt.n_cands[rb] = n2;
+		i32 lo = st.est_lo, hi = st.est_hi;
+		bool paired = kb_pair(pm, (i64)bt.est[t], a, n1, b, n2, &lo, &hi);
+		bt.pstat[t].est_lo = lo; bt.pstat[t].est_hi = hi;
+		if (paired) { kb_keep_mated(a, n1, b, n2); kb_prune(pm, a, n1); kb_prune(pm, b, n2); }
+		else if (kb_top_score(a, n1) == 0 && kb_top_score(b, n2) == 0) { kb_prune(pm, a, n1); kb_prune(pm, b, n2); }   // AlignmentRescue.cpp:89
+		else { u32 slot = KB_ATOMIC_ADD(&bt.counters[4], 1u); bt.rescue_list[slot] = t; }
+	}
+	else
+	{
+		if (t >= bt.n_reads) return;
+		int s1 = bt.n_seeds[t], cap = s1 + 1;
+		u32 off = KB_ATOMIC_ADD(&bt.counters[1], (u32)cap);
+		bt.cand_off[t] = off; bt.cand_cap[t] = cap; bt.n_cands[t] = 0;
+		if ((u64)off + (u64)cap > (u64)bt.cap_cands) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_CANDS); bt.cand_off[t] = 0; return; }
+		if (bt.counters[3] & (KB_OVF_SEEDS | KB_OVF_HITS)) return;
+		if (pm.pacbio) return;   // pacbio chaining needs scratch: done by k_cand_pacbio
+		KbSeg* v = bt.segs + bt.seed_off[t];
+		kb_sort_segs<false>(v, s1);
+		int l = (int)(bt.seq_off[t + 1] - bt.seq_off[t]);
+		KbCand* a = bt.cands + off;
+		int n = kb_cands_illumina(ix, pm, l, v, s1, bt.seed_off[t], a, cap);
+		bt.n_cands[t] = n;
+		kb_prune(pm, a, n);
+	}
+}
+
+KB_HD KbArena kb_thread_arena(const KbBatchDev& bt, int tid)
+{
+	KbArena ar; ar.base = bt.scratch + (u64)tid * bt.scratch_per_thread; ar.used = 0; ar.cap = bt.scratch_per_thread; ar.ovf = false;
+	return ar;
+}
+
+KB_HD void kb_stage_cand_pacbio(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int tid, int nth)
+{
+	if (tid >= bt.scratch_threads) return;
+	if (bt.counters[3]) return;
+	KbArena ar = kb_thread_arena(bt, tid);
+	for (int r = tid; r < bt.n_reads; r += nth)
+	{
+		int n = bt.n_seeds[r];
+		KbSeg* v = bt.segs + bt.seed_off[r];
+		kb_sort_segs<true>(v, n);
+		ar.used = 0;
+		u8* taken = (u8*)ar.alloc((u64)n + 1); KbSeg* tmp = (KbSeg*)ar.alloc((u64)(n + 1) * sizeof(KbSeg));
+		if (ar.ovf) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SCRATCH); return; }
+		KbCand* a = bt.cands + bt.cand_off[r];
+		int nc = kb_cands_pacbio(bt, v, n, taken, tmp, a, bt.cand_cap[r]);
+		bt.n_cands[r] = nc;
+		kb_prune(pm, a, nc);
+	}
+}
+
+KB_HD void kb_stage_rescue(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int tid, int nth)
+{
+	if (tid >= bt.scratch_threads) return;
+	if (bt.counters[3]) return;
+	int count = (int)bt.counters[4];
+	KbArena ar = kb_thread_arena(bt, tid);
+	u32 attempts = 0;
+	for (int k = tid; k < count; k += nth)
+	{
+		int p = bt.rescue_list[k], ra = 2 * p, rb = ra + 1;
+		KbCand* a = bt.cands + bt.cand_off[ra]; KbCand* b = bt.cands + bt.cand_off[rb];
+		int n1 = bt.n_cands[ra], n2 = bt.n_cands[rb];
+		int l1 = (int)(bt.seq_off[ra + 1] - bt.seq_off[ra]), l2 = (int)(bt.seq_off[rb + 1] - bt.seq_off[rb]);
+		int est = bt.est[p]; bool attempted = false;
+		ar.used = 0;
+		bool mated = kb_rescue_pair(ix, pm, bt, ar, est, bt.seq + bt.seq_off[ra], l1, bt.seq + bt.seq_off[rb], l2, a, &n1, bt.cand_cap[ra], b, &n2, bt.cand_cap[rb], &attempted);
+		if (ar.ovf) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SCRATCH); return; }
+		bt.n_cands[ra] = n1; bt.n_cands[rb] = n2;
+		if (attempted)
+		{
+			attempts++;
+			KbPairStat& st = bt.pstat[p];
+			if (est >= pm.max_insert) { if (st.est_lo < pm.max_insert) st.est_lo = pm.max_insert; }
+			else { st.est_lo = est; st.est_hi = est; }
+		}
+		if (mated) kb_keep_mated(a, n1, b, n2);
+		kb_prune(pm, a, n1); kb_prune(pm, b, n2);
+	}
+	if (attempts) KB_ATOMIC_ADD(&bt.counters[7], attempts);
+}
+
+KB_HD void kb_stage_report(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int tid, int nth)
+{
+	if (tid >= bt.scratch_threads) return;
+	if (bt.counters[3]) return;
+	KbArena ar = kb_thread_arena(bt, tid);
+	for (int r = tid; r < bt.n_reads; r += nth)
+	{
+		ar.used = 0;
+		kb_report_read(ix, pm, bt, r, ar);
+		if (ar.ovf) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SCRATCH); return; }
+	}
+}
+
+// what one SAM line needs (OutputPairedAlignments / OutputSingledAlignments, src/Mapping.cpp:177-315)
+KB_HD void kb_fill_aln(kb_aln_t& o, const KbReadRes& rd, const KbReport* rep, const KbReport* mate_rep, bool mate_ok, int tlen)
+{
+	o.score = rd.score; o.sub_score = rd.sub; o.mapq = rd.mapq; o.mate_pos = -1; o.tlen = 0; o.pos = 0; o.chr = 0; o.cig_off = 0; o.cig_len = 0; o.fwd = 1;
+	if (rd.score == 0) { o.kind = 0; o.flag = rep[0].flag; return; }
+	const KbReport& a = rep[rd.best];
+	if (a.aln <= 0) { o.kind = 2; o.flag = 0; return; }
+	o.kind = 1; o.flag = a.flag; o.chr = a.chr; o.pos = a.pos; o.cig_off = a.cig_off; o.cig_len = a.cig_len; o.fwd = a.fwd;
+	if (mate_ok) { o.mate_pos = mate_rep->pos; o.tlen = tlen; }
+}
+
+KB_HD void kb_stage_finalize(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, kb_aln_t* aln, int t)
+{
+	if (bt.counters[3]) return;
+	if (pm.paired)
+	{
+		if (t >= (bt.n_reads >> 1)) return;
+		kb_finalize_pair(ix, pm, bt, t);
+		int ra = 2 * t, rb = ra + 1;
+		const KbReadRes& r1 = bt.res[ra]; const KbReadRes& r2 = bt.res[rb];
+		const KbReport* p1 = bt.reports + r1.rep_off; const KbReport* p2 = bt.reports + r2.rep_off;
+		int l1 = (int)(bt.seq_off[ra + 1] - bt.seq_off[ra]), l2 = (int)(bt.seq_off[rb + 1] - bt.seq_off[rb]);
+		{   // read 1 line (:194-221)
+			const KbReport& a = p1[r1.best]; int j = a.mate; bool ok = r1.score > 0 && a.aln > 0 && j != -1 && p2[j].aln > 0;
+			int dist = ok ? (int)(p2[j].pos - a.pos + (a.fwd ? l2 : 0 - l1)) : 0;
+			kb_fill_aln(aln[ra], r1, p1, ok ? &p2[j] : nullptr, ok, dist);
+		}
+		{   // read 2 line (:242-261)
+			const KbReport& b = p2[r2.best]; int i = b.mate; bool ok = r2.score > 0 && b.aln > 0 && i != -1 && p1[i].aln > 0;
+			int dist = ok ? 0 - (int)(b.pos - p1[i].pos + (p1[i].fwd ? l2 : 0 - l1)) : 0;
+			kb_fill_aln(aln[rb], r2, p2, ok ? &p1[i] : nullptr, ok, dist);
+		}
+	}
+	else
+	{
+		if (t >= bt.n_reads) return;
+		kb_finalize_single(ix, pm, bt, t);
+		const KbReadRes& rd = bt.res[t]; const KbReport* rep = bt.reports + rd.rep_off;
+		kb_fill_aln(aln[t], rd, rep, nullptr, false, 0);
+		if (rd.score > 0 && rep[rd.best].aln != rd.score) aln[t].kind = 2;   // OutputSingledAlignments prints reports with AlnScore == score (:293)
+	}
+}
+
+
+#endif

@@ -1,0 +1,103 @@
+// Shared POD types for the kart_b200 CUDA path (host + device).
+//
+// Everything the kernels touch lives in HBM in these layouts:
+//   * FM-index: re-blocked at upload from the BWA .bwt layout (reference src/BWT_Index/bwtindex.c:53-75:
+//     64-byte blocks = 4 x u64 counts + 128 symbols) into 32-byte blocks = ONE DRAM sector per Occ query:
+//     [u32 cntA,cntC,cntG,cntT][4 x u32 = 64 symbols, 16 per word, MSB first]. Results are identical by construction.
+//   * sampled SA exactly as in .sa (every 32nd row, sa[0] = ~0), optionally expanded to a full SA.
+//   * reference: the forward strand 2-bit .pac bytes; the reverse-complement half of Kart's 2G text
+//     (src/bwt_index.cpp:194-213) is computed on the fly.
+//   * per-batch worklists: hits -> seeds -> candidates -> reports -> cigar arena (bump-allocated, capacity checked).
+#ifndef KB_TYPES_H
+#define KB_TYPES_H
+#include <stdint.h>
+
+typedef uint64_t u64;
+typedef int64_t i64;
+typedef uint32_t u32;
+typedef int32_t i32;
+typedef uint8_t u8;
+
+#if defined(__CUDACC__)
+#define KB_HD __host__ __device__ __forceinline__
+#define KB_D __device__ __forceinline__
+#else
+#define KB_HD inline
+#define KB_D inline
+#endif
+
+struct KbParams
+{
+	i32 min_seed;      // MinSeedLength, src/Mapping.cpp:645
+	i32 max_gaps;      // -g, src/main.cpp:92
+	i32 max_insert;    // MaxInsertSize 1500, src/main.cpp:96
+	i32 pacbio;        // -pacbio
+	i32 multihit;      // -m
+	i32 paired;        // reads come as (mate1, revcomp(mate2)) pairs
+};
+
+struct KbIndexDev
+{
+	u64 primary, L2[5], seq_len;
+	const uint32_t* occ;     // 8 words per 64-row block
+	u64 n_blocks;
+	const u64* sa;           // sampled SA (.sa layout), sa[0] = ~0
+	u64 n_sa;
+	i32 sa_intv;
+	const u64* sa_full;      // optional full SA (NULL when not expanded)
+	const u8* pac;           // forward strand, 2 bit / base, MSB first
+	i64 G, G2;               // GenomeSize, TwoGenomeSize
+	i32 n_chr, n_ends;
+	const i64* end_key;      // ChrLocMap keys (last coordinate of each chromosome on each strand), ascending
+	const i32* end_chr;      // ChrLocMap values
+	const i64* chr_fwd;      // Chromosome_t::FowardLocation
+	const i64* chr_rev;      // Chromosome_t::ReverseLocation
+	const i64* chr_len;
+	const u8* mapq_lut;      // [score][diff-1], diff = 1..5 ; built on the host with the reference expression
+	i32 mapq_lut_scores;
+};
+
+struct KbHit { u64 x0; u32 rpos; u32 len_freq; };                 // len << 8 | freq   (freq <= 50)
+struct KbSeg { i64 gpos; i32 rpos; i32 rlen; i32 glen; i32 simple; };
+struct KbCand { i64 diff; i32 score; i32 mate; u32 seg_start; i32 nseg; };
+struct KbReport { i64 pos; i32 aln; i32 flag; i32 mate; i32 chr; u32 cig_off; i32 cig_len; i32 fwd; i32 pad; };
+struct KbReadRes { i32 score, sub, mapq, ncan, best; u32 rep_off; };
+struct KbPairStat { i32 counted, absdist, est_lo, est_hi; };
+
+// status bits written by kernels (any non-zero value fails the batch loudly; capacities are then grown and the batch rerun)
+enum { KB_OVF_SEEDS = 1, KB_OVF_CANDS = 2, KB_OVF_CIGAR = 4, KB_OVF_SCRATCH = 8, KB_OVF_HITS = 16, KB_OVF_RESCUE = 32, KB_OVF_NW = 64 };
+
+// cigar op codes in the arena: len << 4 | op  (BAM numbering)
+enum { KB_OP_M = 0, KB_OP_I = 1, KB_OP_D = 2, KB_OP_S = 4 };
+
+// Everything one batch needs on the device. Arrays are device pointers.
+struct KbBatchDev
+{
+	i32 n_reads;
+	const u8* seq;           // concatenated read characters (mate 2 already reverse-complemented, src/GetData.cpp:125-135)
+	const u64* seq_off;      // n_reads + 1
+	const i32* est;          // per pair EstDistance (n_reads / 2 entries) when paired
+	// stage 1
+	KbHit* hits; i32 max_hits;          // [n_reads][max_hits]
+	i32* n_hits;                        // hits stored per read
+	i32* n_seeds; u32* seed_off;        // seeds per read and their offset in `segs`
+	KbSeg* segs; u32 cap_segs;
+	// stage 2
+	KbCand* cands; u32 cap_cands; i32* n_cands; u32* cand_off; i32* cand_cap;
+	i32* rescue_list;                   // pair ids that need rescue
+	// stage 3/4
+	KbReport* reports;                  // indexed like cands
+	KbReadRes* res;
+	KbPairStat* pstat;
+	u32* cigar; u32 cap_cigar;
+	// per-thread scratch for the report / rescue kernels
+	u8* scratch; u64 scratch_per_thread; i32 scratch_threads;
+	i32 max_rlen;                       // longest read in the batch
+	i32 nw_max_m, nw_max_n, seg_cap, kmer_cap;
+	// counters: [0] seeds cursor [1] cands cursor [2] cigar cursor [3] status bits [4] rescue count [5] max seeds/read
+	//           [6] nw calls [7] (unused) ; 64-bit: work[0] extension steps, work[1] occ blocks, work[2] LF steps, work[3] NW cells
+	u32* counters;
+	unsigned long long* work;
+};
+
+#endif
