@@ -210,21 +210,29 @@ KB_HD int kb_fill_pairs(int rlen, int glen, KbSeg* in, int n, KbSeg* out, i32* o
 // ================================================================================================
 #define KB_NOKMER 0xFFFFFFFFu
 
-// w[p] = word id of the 8-mer starting at p (exactly as CreateKmerVecFromReadSeq computes it, including the
-// fresh-vs-rolled distinction for non-ACGTN characters), KB_NOKMER where the window holds a literal 'N' or runs off the end.
-KB_HD void kb_kmer_ids(int len, const u8* ch, u32* w)
+// w[p] = word id CreateKmerVecFromReadSeq (KmerAnalysis.cpp:56-98) records for position p, KB_NOKMER where it records none.
+// This is a literal transcription of the reference's scan, because its bookkeeping after a literal 'N' is off by one
+// (the loop increment at :74 runs once more after the restart at :93, so the character right behind the first clean
+// window is skipped and every later 8-mer is labelled one position early); results must match that, not the intent.
+KB_HD u32 kb_fresh_kmer(const u8* s, u32 pos) { u32 id = 0; for (u32 i = pos; i < pos + 8; i++) id = (id << 2) + (u32)kb_nt4(s[i]); return id; }
+KB_HD void kb_kmer_ids(int len, const u8* s, u32* w)
 {
 	for (int i = 0; i < len; i++) w[i] = KB_NOKMER;
-	int run = 0; u32 id = 0;
-	for (int t = 0; t < len; t++)
+	u32 count = 0, head, tail = 0, n = (u32)(len < 0 ? 0 : len);
+	while (count < 8 && tail < n) { if (s[tail++] != 'N') count++; else count = 0; }
+	if (count != 8) return;
+	head = tail - 8;
+	u32 wid = kb_fresh_kmer(s, head); w[head] = wid;
+	for (head += 1; tail < n; head++, tail++)
 	{
-		u8 c = ch[t];
-		if (c == 'N') { run = 0; continue; }
-		run++;
-		if (run < 8) continue;
-		if (run == 8) { id = 0; for (int i = t - 7; i <= t; i++) id = (id << 2) + (u32)kb_nt4(ch[i]); }
-		else id = ((id & 0x3FFF) << 2) + (u32)kb_nt4(c);
-		w[t - 7] = id;
+		if (s[tail] != 'N') { wid = ((wid & 0x3FFF) << 2) + (u32)kb_nt4(s[tail]); w[head] = wid; }
+		else
+		{
+			count = 0; tail++;
+			while (count < 8 && tail < n) { if (s[tail++] != 'N') count++; else count = 0; }
+			if (count != 8) break;
+			head = tail - 8; wid = kb_fresh_kmer(s, head); w[head] = wid;
+		}
 	}
 }
 

@@ -1,0 +1,62 @@
+// Host side of kart_b200: freshly written C++ with the observable behaviour of the reference's host code
+// (CLI src/main.cpp, index loading src/bwt_index.cpp, read input src/GetData.cpp, chunk loop + SAM text src/Mapping.cpp).
+// All per-read computation goes through the C ABI in include/kart_b200.h; nothing here maps reads on the CPU.
+#ifndef KART_HOST_H
+#define KART_HOST_H
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <zlib.h>
+#include "../../include/kart_b200.h"
+
+struct HostIndex
+{
+	std::vector<uint32_t> bwt; std::vector<uint64_t> sa; std::vector<uint8_t> pac;
+	std::vector<std::string> chr_name; std::vector<int64_t> chr_len;
+	uint64_t primary = 0, L2[5] = {0, 0, 0, 0, 0}, seq_len = 0; int sa_intv = 32; int64_t l_pac = 0;
+	bool load(const std::string& prefix, std::string& err);       // bwa_idx_load + RestoreReferenceInfo
+	void describe(kb_index_host_t* out) const;
+};
+bool check_index_files(const std::string& prefix);                // CheckBWAIndexFiles, GetData.cpp:222
+
+// One batch of reads in structure-of-arrays form (what the C ABI takes) plus what SAM output needs.
+struct ReadBatch
+{
+	std::vector<uint8_t> seq;  std::vector<uint64_t> seq_off;     // mate 2 stored reverse-complemented (GetData.cpp:125-135)
+	std::vector<char> qual;                                       // same offsets as seq (mate 2 reversed), empty for FASTA
+	std::vector<char> names;   std::vector<uint32_t> name_off;
+	int n() const { return (int)seq_off.size() - 1; }
+	void clear() { seq.clear(); seq_off.assign(1, 0); qual.clear(); names.clear(); name_off.assign(1, 0); }
+};
+
+class ReadSource   // GetNextChunk / gzGetNextChunk semantics on top of zlib (which reads plain files transparently)
+{
+public:
+	bool open(const char* f1, const char* f2);
+	void close();
+	bool fastq = true;
+	// appends up to max_reads reads (always whole pairs of entries, like the reference) ; returns reads appended
+	int fill(ReadBatch& b, int max_reads, bool pair_end);
+private:
+	struct Stream { gzFile fp = nullptr; std::vector<char> buf; size_t pos = 0, end = 0; bool eof = false; std::string pending; bool has_pending = false; };
+	Stream s1, s2; bool two = false;
+	bool line(Stream& s, std::string& out);
+	bool entry(Stream& s, std::string& name, std::string& seq, std::string& qual);
+};
+
+struct RunOptions
+{
+	std::string index_prefix, out_name = "output.sam";
+	std::vector<std::string> files1, files2;
+	int threads = 4, max_gaps = 5, out_format = 0, n_gpus = 1; bool pair_flag = false, pacbio = false, multihit = false, silent = false, debug = false;
+	int batch_reads = 1 << 20; bool expand_sa = false;
+};
+
+int run_mapping(const RunOptions& opt, const HostIndex& idx);     // Mapping(), src/Mapping.cpp:639
+
+// SAM text (src/Mapping.cpp:177-315)
+void sam_header(std::string& out, const HostIndex& idx);
+void sam_read_line(std::string& out, const HostIndex& idx, const ReadBatch& b, int r, bool stored_fwd, const kb_aln_t& a, const uint32_t* cigar, bool fastq);
+
+#endif

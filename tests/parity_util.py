@@ -1,0 +1,148 @@
+"""Shared helpers for the parity tests, __graft_entry__.smoke() and bench.py's checker leg.
+
+The oracle (oracle/libkartoracle.so, and oracle/_ref/* when built) is loaded ONLY here, as the checker."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from kart_b200 import KartIndex, Mapper, binding, synth   # noqa: E402
+
+ORACLE_LIB = os.path.join(ROOT, "oracle", "libkartoracle.so")
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libkartref.so")
+REF_KART = os.path.join(ROOT, "oracle", "_ref", "kart")
+REF_BWT_INDEX = os.path.join(ROOT, "oracle", "_ref", "bwt_index")
+EMUL_LIB = os.path.join(ROOT, "tests", "emul", "libkartb200_emul.so")
+ECOLI_PREFIX = os.path.join(ROOT, "data", "_gen", "ecoli", "EcoliIdx")
+MINI_PREFIX = os.path.join(ROOT, "tests", "golden", "mini", "mini")
+GEN_DIR = os.path.join(ROOT, "data", "_gen")
+
+
+def have_ecoli() -> bool:
+    return os.path.exists(ECOLI_PREFIX + ".bwt")
+
+
+def default_prefix() -> str:
+    return ECOLI_PREFIX if have_ecoli() else MINI_PREFIX
+
+
+class Oracle:
+    """ctypes view of oracle/libkartoracle.so (prefix kor_) or oracle/_ref/libkartref.so (prefix kref_)."""
+
+    def __init__(self, prefix: str, pacbio=False, max_gaps=5, multihit=False, ref=False):
+        self.ref = ref
+        self.lib = C.CDLL(REF_LIB if ref else ORACLE_LIB)
+        self.p = "kref_" if ref else "kor_"
+        load = getattr(self.lib, self.p + "load")
+        rc = load(prefix.encode(), int(pacbio), max_gaps, int(multihit), 1) if ref else load(prefix.encode(), int(pacbio), max_gaps, int(multihit))
+        if rc != 0:
+            raise RuntimeError("oracle load failed: %d" % rc)
+        for f in ("map_pair", "map_single", "seeds", "candidates", "nw", "fragment_pairs", "normal_pairs", "process_pair"):
+            getattr(self.lib, self.p + f).restype = C.c_long
+        self.buf = C.create_string_buffer(1 << 22)
+
+    def fn(self, name):
+        return getattr(self.lib, self.p + name)
+
+    def map_pair(self, s1: bytes, s2rc: bytes, est: int, stage=False) -> str:
+        self.fn("map_pair")(s1, len(s1), s2rc, len(s2rc), int(est), int(stage), self.buf, len(self.buf))
+        return self.buf.value.decode()
+
+    def map_single(self, s: bytes) -> str:
+        self.fn("map_single")(s, len(s), self.buf, len(self.buf))
+        return self.buf.value.decode()
+
+    def seeds(self, s: bytes, sensitive=False) -> str:
+        self.fn("seeds")(s, len(s), int(sensitive), self.buf, len(self.buf))
+        return self.buf.value.decode()
+
+    def candidates(self, s: bytes) -> str:
+        self.fn("candidates")(s, len(s), self.buf, len(self.buf))
+        return self.buf.value.decode()
+
+    def nw(self, a: bytes, b: bytes):
+        o1 = C.create_string_buffer(len(a) + len(b) + 2)
+        o2 = C.create_string_buffer(len(a) + len(b) + 2)
+        self.fn("nw")(a, len(a), b, len(b), o1, o2)
+        return o1.value.decode(), o2.value.decode()
+
+    def counters(self, reset=True):
+        a = (C.c_ulonglong * 7)()
+        self.lib.kor_counters(a, int(reset))
+        return dict(zip(["searches", "ext_steps", "occ_blocks64", "locates", "lf_steps", "nw_calls", "nw_cells"], [int(x) for x in a]))
+
+
+def genome_of(idx: KartIndex):
+    """Forward strand of every sequence of the index as upper-case uint8 arrays (decoded from the 2-bit .pac)."""
+    pac = idx.pac
+    pos = np.arange(idx.l_pac, dtype=np.int64)
+    codes = (pac[pos >> 2] >> ((~pos & 3) << 1).astype(np.uint8)) & 3
+    bases = np.frombuffer(b"ACGT", dtype=np.uint8)[codes]
+    out, s = [], 0
+    for ln in idx.chr_len:
+        out.append(bases[s:s + ln])
+        s += ln
+    return out
+
+
+def interleave(r1: np.ndarray, r2: np.ndarray) -> np.ndarray:
+    """Pairs in the layout the C ABI expects: read 2i = mate 1, read 2i+1 = reverse-complemented mate 2."""
+    n, L = r1.shape
+    out = np.empty((2 * n, L), dtype=np.uint8)
+    out[0::2] = r1
+    out[1::2] = synth.revcomp_bytes(r2)
+    return out
+
+
+def make_mapper(idx: KartIndex, emul=False, expand_sa=False, **params) -> Mapper:
+    m = Mapper(lib_path=EMUL_LIB if emul else None)
+    m.upload_index(idx, expand_sa=expand_sa)
+    m.set_params(**params)
+    return m
+
+
+def compare_pairs(m: Mapper, orc: Oracle, reads: np.ndarray, est: int = 1500, show: int = 3):
+    """Maps interleaved pairs through the C ABI and checks every pair against the oracle dump. Returns #mismatches."""
+    flat, off = Mapper.pack_reads(reads)
+    aln, pairs, cig = m.map_chunk(flat, off, est)
+    st = m.dump_state()
+    bad = 0
+    for p in range(len(reads) // 2):
+        exp = orc.map_pair(reads[2 * p].tobytes(), reads[2 * p + 1].tobytes(), est)
+        got = binding.dump_read(st, 2 * p) + binding.dump_read(st, 2 * p + 1) + "P %d %d\n" % (pairs[p]["counted"], pairs[p]["absdist"])
+        if exp != got:
+            bad += 1
+            if bad <= show:
+                print("PAIR %d differs\n--- oracle\n%s--- kart_b200\n%s" % (p, exp, got))
+    return bad
+
+
+def compare_singles(m: Mapper, orc: Oracle, reads, show: int = 3):
+    flat, off = Mapper.pack_reads(reads)
+    m.map_chunk(flat, off)
+    st = m.dump_state()
+    bad = 0
+    for r in range(len(off) - 1):
+        s = flat[int(off[r]):int(off[r + 1])].tobytes()
+        exp = orc.map_single(s)
+        got = binding.dump_read(st, r)
+        if exp != got:
+            bad += 1
+            if bad <= show:
+                print("READ %d differs\n--- oracle\n%s--- kart_b200\n%s" % (r, exp, got))
+    return bad
+
+
+def smoke_check(n_pairs: int = 256):
+    idx = KartIndex(default_prefix())
+    genome = genome_of(idx)
+    r1, r2, _ = synth.simulate(genome, n_pairs, 150, 0.02, seed=11, indel=0.002)
+    reads = interleave(r1, r2)
+    m = make_mapper(idx, paired=True)
+    orc = Oracle(default_prefix())
+    return compare_pairs(m, orc, reads), n_pairs
