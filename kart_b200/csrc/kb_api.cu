@@ -78,7 +78,57 @@ __global__ void k_reblock(const u32* bwt, u64 bwt_words, u64 n_new, u32* occ)
 
 __global__ void __launch_bounds__(KB_BLOCK) k_cand_pair(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_cand_pair(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x); }
 __global__ void __launch_bounds__(KB_BLOCK) k_cand_pacbio(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_cand_pacbio(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
-__global__ void __launch_bounds__(KB_BLOCK) k_rescue(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_rescue(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
+// one thread block per unpaired pair; see kb_pair.cuh "block-cooperative rescue"
+#ifndef KB_EMUL
+__global__ void __launch_bounds__(KB_BLOCK) k_rescue(KbIndexDev ix, KbParams pm, KbBatchDev bt)
+{
+	if (bt.counters[3]) return;
+	int count = (int)bt.counters[4], tid = threadIdx.x, nth = blockDim.x;
+	KbRescueJob* j; KbArena ar = kb_job_arena(bt, blockIdx.x, &j);
+	const u64 base_used = ar.used;
+	for (int k = blockIdx.x; k < count; k += gridDim.x)
+	{
+		if (tid == 0) kb_rj_begin(pm, bt, j, ar, k);
+		__syncthreads();
+		while (true)
+		{
+			if (tid == 0 && !j->done) kb_rj_next(ix, bt, j, ar);
+			__syncthreads();
+			if (j->done) break;
+			kb_rj_window(ix, j, tid, nth); __syncthreads();
+			kb_rj_ids(j, tid, nth); __syncthreads();
+			kb_rj_pairs(j, tid, nth); __syncthreads();
+			if (tid == 0) kb_rj_cluster(pm, bt, j);
+			__syncthreads();
+		}
+		if (tid == 0) { kb_rj_end(pm, bt, j); ar.used = base_used; }
+		__syncthreads();
+	}
+}
+#else
+static void k_rescue(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulation: the same phases, barriers replaced by loops over tid
+{
+	if (blockIdx.x != 0 || threadIdx.x != 0) return;
+	if (bt.counters[3]) return;
+	int count = (int)bt.counters[4], nth = KB_BLOCK;
+	KbRescueJob* j; KbArena ar = kb_job_arena(bt, 0, &j);
+	const u64 base_used = ar.used;
+	for (int k = 0; k < count; k++)
+	{
+		kb_rj_begin(pm, bt, j, ar, k);
+		while (true)
+		{
+			if (!j->done) kb_rj_next(ix, bt, j, ar);
+			if (j->done) break;
+			for (int t = 0; t < nth; t++) kb_rj_window(ix, j, t, nth);
+			for (int t = 0; t < nth; t++) kb_rj_ids(j, t, nth);
+			for (int t = nth - 1; t >= 0; t--) kb_rj_pairs(j, t, nth);   // reversed on purpose: the result must not depend on append order
+			kb_rj_cluster(pm, bt, j);
+		}
+		kb_rj_end(pm, bt, j); ar.used = base_used;
+	}
+}
+#endif
 __global__ void __launch_bounds__(KB_BLOCK) k_report(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_report(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
 __global__ void __launch_bounds__(KB_BLOCK) k_finalize(KbIndexDev ix, KbParams pm, KbBatchDev bt, kb_aln_t* aln) { kb_stage_finalize(ix, pm, bt, aln, blockIdx.x * blockDim.x + threadIdx.x); }
 

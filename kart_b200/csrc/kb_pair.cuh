@@ -32,84 +32,185 @@ KB_HD int kb_rescue_cluster(const KbParams& pm, const KbBatchDev& bt, i64 left, 
 	return best_s;
 }
 
-// Search `mate` (length ml) in the reference window [left, left+slen) with 8-mers; exact runs >= 10 (AlignmentRescue.cpp:119-122).
-KB_HD int kb_rescue_window(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, KbArena& ar, const u32* wm, int ml, i64 left, int slen, KbCand* out)
+// ---- block-cooperative rescue ---------------------------------------------------------------------
+// One thread block per pair that failed to pair (RescueUnpairedAlignment). The block walks the anchors in the reference's
+// order; for every reference window the threads share the work: decode the window, 8-mer ids, one diagonal of the
+// (mate x window) match matrix per thread. Control flow is decided by thread 0 between barriers and published through the
+// job record, so the phases below are plain functions of (job, tid, nth) that the host-emulation build can replay.
+struct KbRescueJob
 {
-	u64 mark = ar.used; int score = 0;
-	u8* win = (u8*)ar.alloc((u64)slen);
-	u32* ww = (u32*)ar.alloc((u64)slen * 4);
-	u64 worst = (u64)((ml < slen ? ml : slen) / 9 + 2) * (u64)(ml + slen);
-	u64 room = ar.cap > ar.used ? (ar.cap - ar.used) / (2 * sizeof(KbSeg)) : 0;
-	int cap = (int)(worst < room ? worst : room);
-	KbSeg* pairs = (KbSeg*)ar.alloc((u64)(cap > 0 ? cap : 1) * sizeof(KbSeg));
-	if (!ar.ovf)
-	{
-		for (int i = 0; i < slen; i++) win[i] = kb_code_char(kb_ref_code(ix, left + i));
-		kb_kmer_ids(slen, win, ww);
-		bool povf = false;
-		int np = kb_kmer_pairs(wm, ml, ww, slen, slen, 10, pairs, cap, &povf);
-		if (povf) ar.ovf = true;
-		else score = kb_rescue_cluster(pm, bt, left, pairs, np, out);
-	}
-	ar.used = mark;
-	return score;
+	i32 p, ra, rb, n1, n2, n1o, n2o, l1, l2, est, sc1, sc2, strategy, attempted, mated;
+	i32 side, idx, thr, next_new, done, ovf, clean, slen, cap_pairs, ml;
+	u32 npairs;
+	i64 left;
+	u64 arena_used;
+	u32* wm; u8* win; u32* ww; KbSeg* pairs;
+	const u8* mate;
+};
+
+KB_HD KbArena kb_job_arena(const KbBatchDev& bt, int block, KbRescueJob** job)
+{
+	KbArena ar; u64 per = bt.scratch_per_thread * 128ull;
+	ar.base = bt.scratch + (u64)block * per; ar.used = 0; ar.cap = per; ar.ovf = false;
+	*job = (KbRescueJob*)ar.alloc(sizeof(KbRescueJob));
+	return ar;
 }
 
-// RescueUnpairedAlignment for one pair. a/b: candidate slices of read 1 / read 2 with capacities ca/cb.
-KB_HD bool kb_rescue_pair(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, KbArena& ar, int est,
-                          const u8* s1, int l1, const u8* s2, int l2, KbCand* a, int* pn1, int ca, KbCand* b, int* pn2, int cb, bool* attempted)
+// thread 0: set the job up (AlignmentRescue.cpp:86-99)
+KB_HD void kb_rj_begin(const KbParams& pm, const KbBatchDev& bt, KbRescueJob* j, KbArena& ar, int k)
 {
-	int n1 = *pn1, n2 = *pn2;
-	int sc1 = kb_top_score(a, n1), sc2 = kb_top_score(b, n2), strategy; bool mated = false;
-	*attempted = false;
-	if (sc1 == 0 && sc2 == 0) return false;
-	if (sc1 < (int)(l1 * 0.1) && sc2 < (int)(l2 * 0.1)) strategy = 4;
-	else if (sc1 > sc2 && sc1 - sc2 > 50) strategy = 1;
-	else if (sc2 > sc1 && sc2 - sc1 > 50) strategy = 2;
-	else strategy = 3;
-	if (strategy == 4) return false;
-	*attempted = true;
-	if (est > pm.max_insert) est = pm.max_insert;
-	u64 mark = ar.used;
-	int lm = l1 > l2 ? l1 : l2;
-	u32* wm = (u32*)ar.alloc((u64)lm * 4);
-	if (ar.ovf) return false;
-	if (strategy == 1 || strategy == 3)
+	j->p = bt.rescue_list[k]; j->ra = 2 * j->p; j->rb = j->ra + 1;
+	j->n1 = j->n1o = bt.n_cands[j->ra]; j->n2 = j->n2o = bt.n_cands[j->rb];
+	j->l1 = (int)(bt.seq_off[j->ra + 1] - bt.seq_off[j->ra]); j->l2 = (int)(bt.seq_off[j->rb + 1] - bt.seq_off[j->rb]);
+	j->est = bt.est[j->p]; j->mated = 0; j->attempted = 0; j->done = 0; j->ovf = 0; j->side = -1; j->idx = -1; j->npairs = 0;
+	const KbCand* a = bt.cands + bt.cand_off[j->ra]; const KbCand* b = bt.cands + bt.cand_off[j->rb];
+	j->sc1 = kb_top_score(a, j->n1); j->sc2 = kb_top_score(b, j->n2);
+	if (j->sc1 == 0 && j->sc2 == 0) j->strategy = 0;
+	else if (j->sc1 < (int)(j->l1 * 0.1) && j->sc2 < (int)(j->l2 * 0.1)) j->strategy = 4;
+	else if (j->sc1 > j->sc2 && j->sc1 - j->sc2 > 50) j->strategy = 1;
+	else if (j->sc2 > j->sc1 && j->sc2 - j->sc1 > 50) j->strategy = 2;
+	else j->strategy = 3;
+	if (j->strategy == 0 || j->strategy == 4) { j->done = 1; return; }
+	j->attempted = 1;
+	if (j->est > pm.max_insert) j->est = pm.max_insert;
+	int lm = j->l1 > j->l2 ? j->l1 : j->l2;
+	j->wm = (u32*)ar.alloc((u64)lm * 4);
+	j->arena_used = ar.used;
+	if (ar.ovf) { j->ovf = 1; j->done = 1; }
+}
+
+// thread 0: advance to the next anchor that has a usable window; switches from "rescue read 2 around read 1's candidates"
+// (side 0, :99-133) to "rescue read 1 around read 2's candidates" (side 1, :134-168) when the first list is exhausted
+KB_HD void kb_rj_next(const KbIndexDev& ix, const KbBatchDev& bt, KbRescueJob* j, KbArena& ar)
+{
+	const KbCand* a = bt.cands + bt.cand_off[j->ra]; const KbCand* b = bt.cands + bt.cand_off[j->rb];
+	ar.used = j->arena_used; j->npairs = 0;
+	while (true)
 	{
-		int thr = sc1 - 30 < 50 ? 50 : sc1 - 30;
-		kb_kmer_ids(l2, s2, wm);
-		for (int j = n2, i = 0; i < n1 && !ar.ovf; i++)
+		if (j->side < 0 || (j->side == 0 && j->idx + 1 >= j->n1o) || (j->side == 1 && j->idx + 1 >= j->n2o))
 		{
-			if (a[i].score < thr) continue;
-			i64 left = a[i].diff, right = a[i].diff + est + l2;
-			int e = kb_chr_lookup(ix, left); if (e >= ix.n_ends) continue;
-			int cid = ix.end_chr[e];
+			int ns = j->side + 1;
+			if (ns == 0 && !(j->strategy == 1 || j->strategy == 3)) ns = 1;
+			if (ns == 1 && !(j->strategy == 2 || j->strategy == 3)) ns = 2;
+			if (ns >= 2) { j->done = 1; return; }
+			j->side = ns; j->idx = -1;
+			if (ns == 0) { j->thr = j->sc1 - 30 < 50 ? 50 : j->sc1 - 30; j->mate = bt.seq + bt.seq_off[j->rb]; j->ml = j->l2; j->next_new = j->n2o; }
+			else { j->thr = j->sc2 - 30 < 50 ? 50 : j->sc2 - 30; j->mate = bt.seq + bt.seq_off[j->ra]; j->ml = j->l1; j->next_new = j->n1o; }
+			kb_kmer_ids(j->ml, j->mate, j->wm);
+			continue;
+		}
+		int i = ++j->idx; i64 left, right; int cid, e;
+		if (j->side == 0)
+		{
+			if (a[i].score < j->thr) continue;
+			left = a[i].diff; right = a[i].diff + j->est + j->l2;
+			e = kb_chr_lookup(ix, left); if (e >= ix.n_ends) continue;
+			cid = ix.end_chr[e];
 			if (right < ix.G && right > ix.chr_fwd[cid]) right = ix.chr_fwd[cid] - 1;
 			else if (right >= ix.G && right > ix.chr_rev[cid]) right = ix.chr_rev[cid] - 1;
-			int slen = (int)(right - left); if (slen < l2) continue;
-			KbCand c;
-			if (kb_rescue_window(ix, pm, bt, ar, wm, l2, left, slen, &c) > sc2 && j < cb) { mated = true; c.mate = i; a[i].mate = j; b[j++] = c; *pn2 = j; }
 		}
-	}
-	if (strategy == 2 || strategy == 3)
-	{
-		int thr = sc2 - 30 < 50 ? 50 : sc2 - 30;
-		kb_kmer_ids(l1, s1, wm);
-		for (int i = n1, j = 0; j < n2 && !ar.ovf; j++)
+		else
 		{
-			if (b[j].score < thr) continue;
-			i64 left = b[j].diff - est, right = b[j].diff + l2;
-			int e = kb_chr_lookup(ix, right); if (e >= ix.n_ends) continue;
-			int cid = ix.end_chr[e];
+			if (b[i].score < j->thr) continue;
+			left = b[i].diff - j->est; right = b[i].diff + j->l2;
+			e = kb_chr_lookup(ix, right); if (e >= ix.n_ends) continue;
+			cid = ix.end_chr[e];
 			if (left < ix.G && left < ix.chr_fwd[cid] - ix.chr_len[cid]) left = ix.chr_fwd[cid] - ix.chr_len[cid] + 1;
 			else if (right >= ix.G && left < ix.chr_rev[cid] - ix.chr_len[cid]) left = ix.chr_rev[cid] - ix.chr_len[cid] + 1;
-			int slen = (int)(right - left); if (slen < l1) continue;
-			KbCand c;
-			if (kb_rescue_window(ix, pm, bt, ar, wm, l1, left, slen, &c) > sc1 && i < ca) { mated = true; c.mate = j; b[j].mate = i; a[i++] = c; *pn1 = i; }
+		}
+		int slen = (int)(right - left);
+		if (slen < j->ml) continue;
+		j->left = left; j->slen = slen; j->clean = (left >= 0 && left + slen <= ix.G2) ? 1 : 0;
+		j->win = (u8*)ar.alloc((u64)slen); j->ww = (u32*)ar.alloc((u64)slen * 4);
+		u64 worst = (u64)((j->ml < slen ? j->ml : slen) / 9 + 2) * (u64)(j->ml + slen);
+		u64 room = ar.cap > ar.used ? (ar.cap - ar.used) / (2 * sizeof(KbSeg)) : 0;
+		j->cap_pairs = (int)(worst < room ? worst : room);
+		j->pairs = (KbSeg*)ar.alloc((u64)(j->cap_pairs > 0 ? j->cap_pairs : 1) * sizeof(KbSeg));
+		if (ar.ovf) { j->ovf = 1; j->done = 1; }
+		return;
+	}
+}
+
+// all threads: reference characters of the window
+KB_HD void kb_rj_window(const KbIndexDev& ix, KbRescueJob* j, int tid, int nth)
+{
+	for (int i = tid; i < j->slen; i += nth) j->win[i] = kb_code_char(kb_ref_code(ix, j->left + i));
+}
+
+// all threads: 8-mer ids of the window. A window inside the text is pure ACGT, where the reference's rolling ids equal the
+// 16-bit value of the 8 characters at every position; otherwise thread 0 replays the literal scan.
+KB_HD void kb_rj_ids(KbRescueJob* j, int tid, int nth)
+{
+	if (!j->clean) { if (tid == 0) kb_kmer_ids(j->slen, j->win, j->ww); return; }
+	for (int p = tid; p < j->slen; p += nth)
+	{
+		u32 id = KB_NOKMER;
+		if (p + 8 <= j->slen) { id = 0; for (int i = 0; i < 8; i++) id = (id << 2) | (u32)kb_nt4(j->win[p + i]); }
+		j->ww[p] = id;
+	}
+}
+
+// all threads: one diagonal of the match matrix at a time; exact runs of >= 10 bases are appended in arbitrary order
+KB_HD void kb_rj_pairs(KbRescueJob* j, int tid, int nth)
+{
+	int n1 = j->ml - 7, n2 = j->slen - 7; if (n1 <= 0 || n2 <= 0) return;
+	int dlo = -(n1 - 1), dhi = n2 - 1, ms = j->slen;   // IdentifyCommonKmers(MaxShift = slen): |g - r| < slen
+	if (dlo < -(ms - 1)) dlo = -(ms - 1);
+	if (dhi > ms - 1) dhi = ms - 1;
+	const u32* w1 = j->wm; const u32* w2 = j->ww;
+	for (int d = dlo + tid; d <= dhi; d += nth)
+	{
+		int r0 = d < 0 ? -d : 0, r1 = n1 < n2 - d ? n1 : n2 - d, run = 0;
+		for (int r = r0; r <= r1; r++)
+		{
+			bool m = r < r1 && w1[r] != KB_NOKMER && w1[r] == w2[r + d];
+			if (m) run++;
+			else if (run > 0)
+			{
+				int l = 8 + run - 1;
+				if (l >= 10)
+				{
+					u32 slot = KB_ATOMIC_ADD(&j->npairs, 1u);
+					if ((int)slot < j->cap_pairs) { KbSeg s; s.simple = 1; s.rpos = r - run; s.gpos = (i64)(r - run + d); s.rlen = s.glen = l; j->pairs[slot] = s; }
+					else j->ovf = 1;
+				}
+				run = 0;
+			}
 		}
 	}
-	ar.used = mark;
-	return mated;
+}
+
+// thread 0: order the runs like GenerateSimplePairsFromCommonKmers does, pick the best diagonal cluster, maybe append a candidate
+KB_HD void kb_rj_cluster(const KbParams& pm, const KbBatchDev& bt, KbRescueJob* j)
+{
+	if (j->ovf) { j->done = 1; return; }
+	int np = (int)j->npairs;
+	kb_sort_segs<false>(j->pairs, np);
+	KbCand c;
+	int score = kb_rescue_cluster(pm, bt, j->left, j->pairs, np, &c);
+	KbCand* a = bt.cands + bt.cand_off[j->ra]; KbCand* b = bt.cands + bt.cand_off[j->rb];
+	if (j->side == 0)
+	{
+		if (score > j->sc2 && j->next_new < bt.cand_cap[j->rb]) { j->mated = 1; c.mate = j->idx; a[j->idx].mate = j->next_new; b[j->next_new++] = c; j->n2 = j->next_new; }
+	}
+	else if (score > j->sc1 && j->next_new < bt.cand_cap[j->ra]) { j->mated = 1; c.mate = j->idx; b[j->idx].mate = j->next_new; a[j->next_new++] = c; j->n1 = j->next_new; }
+}
+
+// thread 0: what follows RescueUnpairedAlignment in ReadMapping (Mapping.cpp:561-563) and the EstDistance interval
+KB_HD void kb_rj_end(const KbParams& pm, const KbBatchDev& bt, KbRescueJob* j)
+{
+	if (j->ovf) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SCRATCH); return; }
+	KbCand* a = bt.cands + bt.cand_off[j->ra]; KbCand* b = bt.cands + bt.cand_off[j->rb];
+	bt.n_cands[j->ra] = j->n1; bt.n_cands[j->rb] = j->n2;
+	if (j->attempted)
+	{
+		KB_ATOMIC_ADD(&bt.counters[7], 1u);
+		KbPairStat& st = bt.pstat[j->p]; int est = bt.est[j->p];
+		if (est >= pm.max_insert) { if (st.est_lo < pm.max_insert) st.est_lo = pm.max_insert; }
+		else { st.est_lo = est; st.est_hi = est; }
+	}
+	if (j->mated) kb_keep_mated(a, j->n1, b, j->n2);
+	kb_prune(pm, a, j->n1); kb_prune(pm, b, j->n2);
 }
 
 // ---- final scoring -------------------------------------------------------------------------------

@@ -79,37 +79,6 @@ KB_HD void kb_stage_cand_pacbio(const KbIndexDev& ix, const KbParams& pm, const 
 	}
 }
 
-KB_HD void kb_stage_rescue(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int tid, int nth)
-{
-	if (tid >= bt.scratch_threads) return;
-	if (bt.counters[3]) return;
-	int count = (int)bt.counters[4];
-	KbArena ar = kb_thread_arena(bt, tid);
-	u32 attempts = 0;
-	for (int k = tid; k < count; k += nth)
-	{
-		int p = bt.rescue_list[k], ra = 2 * p, rb = ra + 1;
-		KbCand* a = bt.cands + bt.cand_off[ra]; KbCand* b = bt.cands + bt.cand_off[rb];
-		int n1 = bt.n_cands[ra], n2 = bt.n_cands[rb];
-		int l1 = (int)(bt.seq_off[ra + 1] - bt.seq_off[ra]), l2 = (int)(bt.seq_off[rb + 1] - bt.seq_off[rb]);
-		int est = bt.est[p]; bool attempted = false;
-		ar.used = 0;
-		bool mated = kb_rescue_pair(ix, pm, bt, ar, est, bt.seq + bt.seq_off[ra], l1, bt.seq + bt.seq_off[rb], l2, a, &n1, bt.cand_cap[ra], b, &n2, bt.cand_cap[rb], &attempted);
-		if (ar.ovf) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SCRATCH); return; }
-		bt.n_cands[ra] = n1; bt.n_cands[rb] = n2;
-		if (attempted)
-		{
-			attempts++;
-			KbPairStat& st = bt.pstat[p];
-			if (est >= pm.max_insert) { if (st.est_lo < pm.max_insert) st.est_lo = pm.max_insert; }
-			else { st.est_lo = est; st.est_hi = est; }
-		}
-		if (mated) kb_keep_mated(a, n1, b, n2);
-		kb_prune(pm, a, n1); kb_prune(pm, b, n2);
-	}
-	if (attempts) KB_ATOMIC_ADD(&bt.counters[7], attempts);
-}
-
 KB_HD void kb_stage_report(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int tid, int nth)
 {
 	if (tid >= bt.scratch_threads) return;

@@ -1,0 +1,98 @@
+"""CPU: the per-thread bodies of the CUDA kernels, compiled for the host (tests/emul, test infrastructure only), and the
+whole C-ABI / host flow around them, against the oracle. The real kernels are checked by the -m gpu tests."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import parity_util as pu
+from kart_b200 import KartIndex, Mapper, synth
+
+G = os.path.join(pu.ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def mini(built):
+    idx = KartIndex(pu.MINI_PREFIX)
+    return idx, pu.genome_of(idx)
+
+
+def test_paired_multi_contig(mini):
+    idx, g = mini
+    r1, r2, _ = synth.simulate(g, 1500, 150, 0.07, seed=31, indel=0.005, n_rate=0.003)
+    m = pu.make_mapper(idx, emul=True, paired=True)
+    assert pu.compare_pairs(m, pu.Oracle(pu.MINI_PREFIX), pu.interleave(r1, r2)) == 0
+    assert m.work()["rescues"] > 0
+
+
+def test_paired_small_est_and_full_sa(mini):
+    idx, g = mini
+    r1, r2, _ = synth.simulate(g, 600, 150, 0.02, seed=32)
+    m = pu.make_mapper(idx, emul=True, expand_sa=True, paired=True)
+    assert pu.compare_pairs(m, pu.Oracle(pu.MINI_PREFIX), pu.interleave(r1, r2), est=470) == 0
+
+
+def test_single_end_high_error(mini):
+    idx, g = mini
+    r, _, _ = synth.simulate(g, 1500, 100, 0.08, seed=33, paired=False, indel=0.003)
+    m = pu.make_mapper(idx, emul=True, paired=False)
+    assert pu.compare_singles(m, pu.Oracle(pu.MINI_PREFIX), r) == 0
+
+
+def test_pacbio_long_reads(mini):
+    idx, g = mini
+    r, _, _ = synth.simulate(g, 16, 3000, 0.15, seed=34, paired=False, indel=0.01)
+    m = pu.make_mapper(idx, emul=True, pacbio=True)
+    assert pu.compare_singles(m, pu.Oracle(pu.MINI_PREFIX, pacbio=True), r) == 0
+
+
+def test_edge_reads(mini):
+    idx, g = mini
+    m = pu.make_mapper(idx, emul=True, paired=False)
+    reads = [b"A", b"ACGTACGTACGTAC", b"N" * 60, g[0][:150].tobytes(), g[2][-150:].tobytes(), g[1][100:113].tobytes(),
+             (g[0][3000:3075].tobytes() + g[1][500:575].tobytes()), g[0][200:350].tobytes().lower(), b"ACGTRYKM" * 15]
+    assert pu.compare_singles(m, pu.Oracle(pu.MINI_PREFIX), reads) == 0
+    aln, pairs, cig = m.map_chunk(np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+    assert len(aln) == 0
+
+
+@pytest.fixture(scope="module")
+def kart_emul(built):
+    exe = os.path.join(pu.ROOT, "tests", "emul", "kart_emul")
+    src = [os.path.join(pu.ROOT, "kart_b200", "host", f) for f in os.listdir(os.path.join(pu.ROOT, "kart_b200", "host")) if f.endswith(".cpp")]
+    subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe] + src + ["-L" + os.path.dirname(exe), "-lkartb200_emul", "-Wl,-rpath,$ORIGIN", "-lz", "-lpthread"], check=True)
+    return exe
+
+
+@pytest.mark.parametrize("tag,args", [("pe150", ["-f", "pe150_1.fq", "-f2", "pe150_2.fq"]), ("se100", ["-f", "se100.fq"]), ("pb3k", ["-pacbio", "-f", "pb3k.fq"])])
+def test_cli_sam_is_byte_identical_to_reference(kart_emul, tmp_path, tag, args):
+    """The host C++ (CLI, input parsing, chunk recurrence, SAM text) over the emulated device code reproduces the reference's SAM bytes."""
+    out = str(tmp_path / (tag + ".sam"))
+    a = [os.path.join(G, x) if x.endswith(".fq") else x for x in args]
+    subprocess.run([kart_emul, "-silent", "-t", "2", "-i", pu.MINI_PREFIX] + a + ["-o", out, "--batch", "400"], check=True, stdout=subprocess.DEVNULL)
+    assert open(out, "rb").read() == open(os.path.join(G, tag + ".sam"), "rb").read()
+
+
+def test_cli_interleaved_and_gz_inputs(kart_emul, tmp_path):
+    import gzip
+    a = open(os.path.join(G, "pe150_1.fq"), "rb").read().split(b"\n")
+    b = open(os.path.join(G, "pe150_2.fq"), "rb").read().split(b"\n")
+    inter = []
+    for i in range(0, len(a) - 1, 4):
+        inter += a[i:i + 4] + b[i:i + 4]
+    p = tmp_path / "inter.fq.gz"
+    with gzip.open(p, "wb") as fh:
+        fh.write(b"\n".join(inter) + b"\n")
+    out = str(tmp_path / "i.sam")
+    subprocess.run([kart_emul, "-silent", "-i", pu.MINI_PREFIX, "-p", "-f", str(p), "-o", out], check=True, stdout=subprocess.DEVNULL)
+    assert open(out, "rb").read() == open(os.path.join(G, "pe150.sam"), "rb").read()
+
+
+def test_cli_argument_errors(kart_emul):
+    r = subprocess.run([kart_emul, "-i", pu.MINI_PREFIX, "-zzz"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Error! Unknown parameter: -zzz" in r.stdout
+    r = subprocess.run([kart_emul, "-i", pu.MINI_PREFIX], capture_output=True, text=True)
+    assert r.returncode == 1 and "Please specify a valid read input" in r.stdout
+    r = subprocess.run([kart_emul, "-v"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("kart v2.5.6")

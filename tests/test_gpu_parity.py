@@ -73,3 +73,48 @@ def test_empty_and_ragged_chunks(eco):
     assert len(aln) == 0
     reads = [b"ACGT", b"N" * 40, g[0][1000:1013].tobytes(), g[0][5000:5250].tobytes(), b"acgtn" * 20, g[0][70000:70031].tobytes().lower()]
     assert pu.compare_singles(m, pu.Oracle(prefix), reads) == 0
+
+
+def test_pacbio_vs_oracle(built):
+    idx = KartIndex(pu.MINI_PREFIX)
+    g = pu.genome_of(idx)
+    r, _, _ = synth.simulate(g, 64, 3000, 0.15, seed=34, paired=False, indel=0.01)
+    m = pu.make_mapper(idx, pacbio=True)
+    assert pu.compare_singles(m, pu.Oracle(pu.MINI_PREFIX, pacbio=True), r) == 0
+
+
+def test_multi_contig_paired_with_rescue(built):
+    idx = KartIndex(pu.MINI_PREFIX)
+    g = pu.genome_of(idx)
+    r1, r2, _ = synth.simulate(g, 4000, 150, 0.07, seed=31, indel=0.005, n_rate=0.003)
+    m = pu.make_mapper(idx, paired=True)
+    assert pu.compare_pairs(m, pu.Oracle(pu.MINI_PREFIX), pu.interleave(r1, r2)) == 0
+    assert m.work()["rescues"] > 0
+
+
+import os            # noqa: E402
+import subprocess    # noqa: E402
+
+G = os.path.join(pu.ROOT, "tests", "golden")
+KART = os.path.join(pu.ROOT, "kart_b200", "bin", "kart")
+
+
+@pytest.mark.parametrize("tag,args", [("pe150", ["-f", "pe150_1.fq", "-f2", "pe150_2.fq"]), ("se100", ["-f", "se100.fq"]), ("pb3k", ["-pacbio", "-f", "pb3k.fq"])])
+def test_cli_golden_sam(built, tmp_path, tag, args):
+    """kart_b200/bin/kart (CUDA) writes the reference's SAM bytes for the committed golden inputs."""
+    out = str(tmp_path / (tag + ".sam"))
+    a = [os.path.join(G, x) if x.endswith(".fq") else x for x in args]
+    subprocess.run([KART, "-silent", "-i", pu.MINI_PREFIX] + a + ["-o", out], check=True, stdout=subprocess.DEVNULL)
+    assert open(out, "rb").read() == open(os.path.join(G, tag + ".sam"), "rb").read()
+
+
+@pytest.mark.skipif(not (os.path.exists(pu.REF_KART) and pu.have_ecoli()), reason="needs oracle/_ref/kart and the E. coli index (built in the build container, shipped with the snapshot)")
+def test_cli_100k_pairs_identical_to_reference_t1(built, tmp_path):
+    """C2-shaped input through the real CLI: byte-identical to `kart -t 1` including the per-chunk EstDistance recurrence."""
+    idx = KartIndex(pu.ECOLI_PREFIX)
+    g = pu.genome_of(idx)
+    f1, f2 = synth.make_reads(g, str(tmp_path / "r"), 100000, 150, 0.02, seed=1)
+    ours, ref = str(tmp_path / "ours.sam"), str(tmp_path / "ref.sam")
+    subprocess.run([KART, "-silent", "-i", pu.ECOLI_PREFIX, "-f", f1, "-f2", f2, "-o", ours, "--batch", "60000"], check=True, stdout=subprocess.DEVNULL)
+    subprocess.run([pu.REF_KART, "-silent", "-t", "1", "-i", pu.ECOLI_PREFIX, "-f", f1, "-f2", f2, "-o", ref], check=True, stdout=subprocess.DEVNULL)
+    assert open(ours, "rb").read() == open(ref, "rb").read()
