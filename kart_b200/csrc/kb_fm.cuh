@@ -61,21 +61,51 @@ KB_HD void kb_occ4(const KbIndexDev& ix, u64 k, u64 out[4])
 	out[0] = cnt[0]; out[1] = cnt[1]; out[2] = cnt[2]; out[3] = cnt[3];
 }
 
+// ---- one 32-byte Occ block = one DRAM sector, fetched with a single 256-bit load (LDG.E.256 on sm_100a) ----
+struct KbBlk { u32 c0, c1, c2, c3, w0, w1, w2, w3; };
+KB_HD KbBlk kb_load_blk(const uint32_t* occ, u64 blk)
+{
+	KbBlk b; const uint32_t* p = occ + (blk << 3);
+#if defined(__CUDA_ARCH__)
+	asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=r"(b.c0), "=r"(b.c1), "=r"(b.c2), "=r"(b.c3), "=r"(b.w0), "=r"(b.w1), "=r"(b.w2), "=r"(b.w3) : "l"(p));
+#else
+	b.c0 = p[0]; b.c1 = p[1]; b.c2 = p[2]; b.c3 = p[3]; b.w0 = p[4]; b.w1 = p[5]; b.w2 = p[6]; b.w3 = p[7];
+#endif
+	return b;
+}
+
+// For base b: eq = Occ(row, b), gt = sum over bases j > b of Occ(row, j), where `off` is the row's offset in the block.
+// Two popcounts per 32 symbols instead of one per base: the interval update only needs these two sums.
+KB_HD void kb_rank_eq_gt(const KbBlk& k, int off, int b, u32* eq, u32* gt)
+{
+	const u64 M5 = 0x5555555555555555ull;
+	int n = off + 1, n0 = n < 32 ? n : 32, n1 = n - n0;
+	u64 pm0 = n0 >= 32 ? M5 : (M5 & ~(~0ull >> (2 * n0)));
+	u64 pm1 = n1 >= 32 ? M5 : (n1 == 0 ? 0ull : (M5 & ~(~0ull >> (2 * n1))));
+	u64 W0 = ((u64)k.w0 << 32) | k.w1, W1 = ((u64)k.w2 << 32) | k.w3;
+	u64 lo0 = W0 & pm0, hi0 = (W0 >> 1) & pm0, lo1 = W1 & pm1, hi1 = (W1 >> 1) & pm1;
+	u64 e0 = ((b & 2) ? hi0 : (~hi0 & pm0)) & ((b & 1) ? lo0 : (~lo0 & pm0));
+	u64 e1 = ((b & 2) ? hi1 : (~hi1 & pm1)) & ((b & 1) ? lo1 : (~lo1 & pm1));
+	u64 g0 = b == 0 ? (hi0 | lo0) : (b == 1 ? hi0 : (b == 2 ? (hi0 & lo0) : 0ull));
+	u64 g1 = b == 0 ? (hi1 | lo1) : (b == 1 ? hi1 : (b == 2 ? (hi1 & lo1) : 0ull));
+	u32 ceq = b == 0 ? k.c0 : (b == 1 ? k.c1 : (b == 2 ? k.c2 : k.c3));
+	u32 cgt = b == 0 ? k.c1 + k.c2 + k.c3 : (b == 1 ? k.c2 + k.c3 : (b == 2 ? k.c3 : 0u));
+	*eq = ceq + (u32)KB_POPCLL(e0) + (u32)KB_POPCLL(e1);
+	*gt = cgt + (u32)KB_POPCLL(g0) + (u32)KB_POPCLL(g1);
+}
+
 // LF step (bwt_invPsi :120 with bwt_occ :44 folded in; one 32-byte block per step)
 KB_HD u64 kb_lf(const KbIndexDev& ix, u64 k)
 {
 	if (k == ix.primary) return 0;
 	u64 r = k - (k > ix.primary);
-	const uint4* p = reinterpret_cast<const uint4*>(ix.occ) + ((r >> 6) << 1);
-	uint4 c = KB_LDG4(p), w = KB_LDG4(p + 1);
+	KbBlk bk = kb_load_blk(ix.occ, r >> 6);
 	int off = (int)(r & 63);
-	u32 word = off < 16 ? w.x : (off < 32 ? w.y : (off < 48 ? w.z : w.w));
+	u32 word = off < 16 ? bk.w0 : (off < 32 ? bk.w1 : (off < 48 ? bk.w2 : bk.w3));
 	int sym = (word >> ((~off & 15) << 1)) & 3;
-	u32 cnt[4] = {c.x, c.y, c.z, c.w};
-	int n = off + 1;
-	kb_count32(((u64)w.x << 32) | w.y, n < 32 ? n : 32, cnt);
-	if (n > 32) kb_count32(((u64)w.z << 32) | w.w, n - 32, cnt);
-	return ix.L2[sym] + cnt[sym];
+	u32 eq, gt; kb_rank_eq_gt(bk, off, sym, &eq, &gt);
+	return ix.L2[sym] + eq;
 }
 
 // SA locate (bwt_sa :128). Returns the text position; *steps receives the number of LF steps walked.
@@ -88,59 +118,69 @@ KB_HD u64 kb_sa(const KbIndexDev& ix, u64 k, u32* steps)
 	return s + KB_LDG(ix.sa + k / (u64)ix.sa_intv);
 }
 
-struct KbSearch { u64 x0, x2; int len; u32 steps, blocks; };
-
-// Forward extension of a bi-interval from seq[start] while the match is non-empty (BWT_Search :140-170).
-KB_HD KbSearch kb_search(const KbIndexDev& ix, const u8* seq, int start, int stop)
-{
-	KbSearch o; o.steps = 0; o.blocks = 0;
-	int p = kb_nt4(seq[start]), pos;
-	u64 x0 = ix.L2[p] + 1, x1 = ix.L2[3 - p] + 1, x2 = ix.L2[p + 1] - ix.L2[p];
-	for (pos = start + 1; pos < stop; pos++)
-	{
-		int c = kb_nt4(seq[pos]);
-		if (c > 3) break;
-		u64 tk[4], tl[4], k = x1 - 1, l = x1 - 1 + x2;
-		kb_occ4(ix, k, tk); kb_occ4(ix, l, tl);
-		o.steps++; o.blocks += 1 + (((k - (k >= ix.primary)) >> 6) != ((l - (l >= ix.primary)) >> 6));
-		int b = 3 - c;
-		u64 n2 = tl[b] - tk[b];
-		if (n2 == 0) break;
-		u64 n0 = x0 + ((x1 <= ix.primary && x1 + x2 - 1 >= ix.primary) ? 1 : 0);
-		for (int j = 3; j > b; j--) n0 += tl[j] - tk[j];
-		x0 = n0; x1 = ix.L2[b] + 1 + tk[b]; x2 = n2;
-	}
-	o.x0 = x0; o.x2 = x2; o.len = pos - start;
-	return o;
-}
-
-// One read: all searches of IdentifySeedPairs_FastMode (:49) or _SensitiveMode (:132); records the searches that
-// will yield seeds (len >= MinSeedLength and interval size <= OCC_Thr 50, bwt_search.cpp:3,172-176).
+// One read: all searches of IdentifySeedPairs_FastMode (:49) or _SensitiveMode (:132) with BWT_Search (:140-170) inlined as a
+// FLAT state machine: every trip of the single loop performs (at most) one extension step, so the lanes of a warp stay in
+// lock-step across search boundaries instead of waiting for the longest search of the warp (nested loops cost 4-5x here).
+// Records the searches that will yield seeds (len >= MinSeedLength and interval size <= OCC_Thr 50, bwt_search.cpp:3,172-176).
 KB_HD void kb_seed_read(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int r, u32* w_steps, u32* w_blocks)
 {
 	const u8* seq = bt.seq + bt.seq_off[r];
-	int rlen = (int)(bt.seq_off[r + 1] - bt.seq_off[r]);
+	const int rlen = (int)(bt.seq_off[r + 1] - bt.seq_off[r]);
 	KbHit* hits = bt.hits + (size_t)r * bt.max_hits;
-	int nh = 0, ns = 0, pos = 0, end = rlen - pm.min_seed, stop = 30;
-	bool ovf = false;
-	while (pos < end)
+	const u64 primary = ix.primary;
+	int nh = 0, ns = 0, pos = 0, cur = 0, lim = 0, stop = 30;
+	const int end = rlen - pm.min_seed;
+	u32 steps = 0, blocks = 0;
+	u64 x0 = 0, x1 = 0, x2 = 0;
+	bool searching = false, ovf = false;
+	while (searching || pos < end)
 	{
-		if (kb_nt4(seq[pos]) > 3) { pos++; stop++; continue; }
-		KbSearch s = kb_search(ix, seq, pos, pm.pacbio ? stop : rlen);
-		*w_steps += s.steps; *w_blocks += s.blocks;
-		bool hit = s.len >= pm.min_seed && (int)s.x2 <= 50;
-		if (hit)
+		if (!searching)
 		{
-			if (nh < bt.max_hits) { KbHit h; h.x0 = s.x0; h.rpos = (u32)pos; h.len_freq = ((u32)s.len << 8) | (u32)s.x2; hits[nh++] = h; ns += (int)s.x2; }
-			else ovf = true;
+			int p = kb_nt4(seq[pos]);
+			if (p > 3) { pos++; stop++; continue; }
+			x0 = ix.L2[p] + 1; x1 = ix.L2[3 - p] + 1; x2 = ix.L2[p + 1] - ix.L2[p];
+			cur = pos + 1; searching = true;
+			lim = pm.pacbio ? (stop < rlen ? stop : rlen) : rlen;
 		}
-		if (pm.pacbio)
+		bool ended = true;
+		if (cur < lim)
 		{
-			int adv = hit ? s.len : pm.min_seed;
-			pos += adv; stop += adv; if (stop > rlen) stop = rlen;
+			int c = kb_nt4(seq[cur]);
+			if (c <= 3)
+			{
+				int b = 3 - c;
+				u64 k = x1 - 1, l = k + x2;
+				u64 rk = k - (k >= primary), rl = l - (l >= primary);
+				KbBlk bk = kb_load_blk(ix.occ, rk >> 6), bl = kb_load_blk(ix.occ, rl >> 6);
+				u32 ek, gk, el, gl;
+				kb_rank_eq_gt(bk, (int)(rk & 63), b, &ek, &gk);
+				kb_rank_eq_gt(bl, (int)(rl & 63), b, &el, &gl);
+				steps++; blocks += 1 + ((rk >> 6) != (rl >> 6));
+				u32 n2 = el - ek;
+				if (n2 != 0)
+				{
+					x0 = x0 + ((x1 <= primary && x1 + x2 - 1 >= primary) ? 1 : 0) + (u64)(gl - gk);
+					x1 = ix.L2[b] + 1 + ek; x2 = n2;
+					cur++; ended = false;
+				}
+			}
 		}
-		else pos += s.len + 1;
+		if (ended)
+		{
+			int len = cur - pos;
+			bool hit = len >= pm.min_seed && (int)x2 <= 50;
+			if (hit)
+			{
+				if (nh < bt.max_hits) { KbHit h; h.x0 = x0; h.rpos = (u32)pos; h.len_freq = ((u32)len << 8) | (u32)x2; hits[nh++] = h; ns += (int)x2; }
+				else ovf = true;
+			}
+			if (pm.pacbio) { int adv = hit ? len : pm.min_seed; pos += adv; stop += adv; if (stop > rlen) stop = rlen; }
+			else pos += len + 1;
+			searching = false;
+		}
 	}
+	*w_steps += steps; *w_blocks += blocks;
 	if (ovf) KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_HITS);
 	bt.n_hits[r] = nh; bt.n_seeds[r] = ns;
 	u32 off = KB_ATOMIC_ADD(&bt.counters[0], (u32)ns);

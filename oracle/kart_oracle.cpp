@@ -981,7 +981,13 @@ static void map_pair(const char* s1, int l1, const char* s2, int l2, int est, Re
 // ------------------------------------------------------------------------------------------------
 // Text dumps (format in kart_oracle.h)
 // ------------------------------------------------------------------------------------------------
-static void put(std::string& s, const char* fmt, ...) { char buf[512]; va_list ap; va_start(ap, fmt); int n = vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap); s.append(buf, n); }
+static void put(std::string& s, const char* fmt, ...)
+{
+	va_list ap, ap2; va_start(ap, fmt); va_copy(ap2, ap);
+	int n = vsnprintf(NULL, 0, fmt, ap); va_end(ap);
+	std::vector<char> buf((size_t)n + 1); vsnprintf(buf.data(), buf.size(), fmt, ap2); va_end(ap2);
+	s.append(buf.data(), n);
+}
 static long emit(const std::string& s, char* out, long cap) { if (out && (long)s.size() < cap) { memcpy(out, s.data(), s.size()); out[s.size()] = 0; } return (long)s.size(); }
 static void dump_segs(std::string& s, const std::vector<Seg>& v) { for (size_t i = 0; i < v.size(); i++) put(s, "S %d %d %d %lld %d\n", v[i].rPos, v[i].rLen, v[i].gLen, (long long)v[i].gPos, v[i].simple ? 1 : 0); }
 static void dump_cands(std::string& s, const std::vector<Cand>& v) { for (size_t i = 0; i < v.size(); i++) { put(s, "C %d %lld %d %d\n", v[i].score, (long long)v[i].diff, v[i].mate, (int)v[i].segs.size()); dump_segs(s, v[i].segs); } }

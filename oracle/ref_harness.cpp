@@ -42,8 +42,10 @@ static long emit(const std::string& s, char* out, long cap)
 
 static void put(std::string& s, const char* fmt, ...)
 {
-	char buf[512]; va_list ap; va_start(ap, fmt); int n = vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
-	s.append(buf, n);
+	va_list ap, ap2; va_start(ap, fmt); va_copy(ap2, ap);
+	int n = vsnprintf(NULL, 0, fmt, ap); va_end(ap);
+	std::vector<char> buf((size_t)n + 1); vsnprintf(buf.data(), buf.size(), fmt, ap2); va_end(ap2);
+	s.append(buf.data(), n);
 }
 
 static void dump_seeds(std::string& s, const vector<SeedPair_t>& v)
