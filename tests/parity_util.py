@@ -42,8 +42,19 @@ class Oracle:
         rc = load(prefix.encode(), int(pacbio), max_gaps, int(multihit), 1) if ref else load(prefix.encode(), int(pacbio), max_gaps, int(multihit))
         if rc != 0:
             raise RuntimeError("oracle load failed: %d" % rc)
-        for f in ("map_pair", "map_single", "seeds", "candidates", "nw", "fragment_pairs", "normal_pairs", "process_pair"):
-            getattr(self.lib, self.p + f).restype = C.c_long
+        # explicit prototypes: arguments beyond the sixth travel on the stack, where an untyped Python int only fills 32 of 64 bits
+        sig = {"map_pair": [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_long],
+               "map_single": [C.c_char_p, C.c_int, C.c_char_p, C.c_long],
+               "seeds": [C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_long],
+               "candidates": [C.c_char_p, C.c_int, C.c_char_p, C.c_long],
+               "nw": [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_char_p],
+               "fragment_pairs": [C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_long],
+               "normal_pairs": [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_long],
+               "process_pair": [C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_char_p, C.c_long]}
+        for f, a in sig.items():
+            fn = getattr(self.lib, self.p + f)
+            fn.restype = C.c_long
+            fn.argtypes = a
         self.buf = C.create_string_buffer(1 << 22)
 
     def fn(self, name):
