@@ -22,7 +22,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-STAGES = ["fm_seed", "sa_locate", "cand_pair", "rescue", "report", "finalize"]
+STAGES = ["fm_seed", "sa_locate", "cand_pair", "rescue", "segments", "align", "assemble", "finalize"]
 
 
 def peaks():
@@ -216,7 +216,7 @@ def main():
            "gpu_launches": int(work["launches"]) * args.steps, "roofline": roof,
            "stage_ms": per, "mapped_fraction": mapped / n,
            "work_per_step": work, "seed_occ_gbs": alg["fm_seed"] / (per["fm_seed"] / 1e3) / 1e9,
-           "nw_gcups": work["nw_cells"] / (per["report"] / 1e3) / 1e9}
+           "nw_gcups": work["nw_cells"] / (per["align"] / 1e3) / 1e9}
     # ---- CPU baseline: the unmodified reference on this box's host cores, bounded sample ----
     if os.path.exists(pu.REF_KART):
         tmp = tempfile.mkdtemp(prefix="kartbench")

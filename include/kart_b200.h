@@ -110,7 +110,8 @@ int  kb_run(kb_ctx_t* ctx);                                                     
 int  kb_fetch_results(kb_ctx_t* ctx, kb_results_t* out);                         /* D2H */
 
 /* Instrumentation. kb_stage_ms: device time (CUDA events on the context's stream) of each kernel of the last kb_run:
- * [0] fm_seed [1] sa_locate [2] cand_pair [3] rescue [4] report [5] finalize [6] whole run. Returns entries written.
+ * [0] fm_seed [1] sa_locate [2] cand_pair [3] rescue [4] segments [5] align [6] assemble [7] finalize [8] whole run.
+ * Returns entries written.
  * kb_work: algorithmic work of the last run: [0] extension steps [1] Occ blocks touched (32-byte sectors)
  * [2] LF steps [3] NW cells [4] seeds [5] NW calls [6] rescue attempts [7] kernels launched. */
 int  kb_stage_ms(kb_ctx_t* ctx, float* ms, int n);
@@ -118,7 +119,7 @@ int  kb_work(kb_ctx_t* ctx, uint64_t* w, int n);
 void* kb_cuda_stream(kb_ctx_t* ctx);
 
 /* Test hook: copy an internal device array of the last run to the host. what: 0 n_seeds(i32) 1 seed_off(u32) 2 segs(KbSeg)
- * 3 n_cands(i32) 4 cand_off(u32) 5 cands(KbCand) 6 reports(KbReport) 7 res(KbReadRes) 8 cigar(u32) 9 counters(u32[8]).
+ * 3 n_cands(i32) 4 cand_off(u32) 5 cands(KbCand) 6 reports(KbReport) 7 res(KbReadRes) 8 cigar(u32) 9 counters(u32[16]).
  * Returns bytes copied (<= bytes) or a negative error. */
 int64_t kb_debug_fetch(kb_ctx_t* ctx, int what, void* dst, uint64_t bytes);
 

@@ -202,9 +202,9 @@ class Mapper:
         return aln, pairs, cig[:res.n_cigar]
 
     def stage_ms(self):
-        a = np.zeros(7, dtype=np.float32)
-        self.lib.kb_stage_ms(self.h, a.ctypes.data, 7)
-        return dict(zip(["fm_seed", "sa_locate", "cand_pair", "rescue", "report", "finalize", "total"], [float(x) for x in a]))
+        a = np.zeros(9, dtype=np.float32)
+        self.lib.kb_stage_ms(self.h, a.ctypes.data, 9)
+        return dict(zip(["fm_seed", "sa_locate", "cand_pair", "rescue", "segments", "align", "assemble", "finalize", "total"], [float(x) for x in a]))
 
     def work(self):
         a = np.zeros(8, dtype=np.uint64)
@@ -221,7 +221,7 @@ class Mapper:
     # ---- dumps in the oracle's text format (oracle/kart_oracle.h) ----
     def dump_state(self):
         n = self.n_reads
-        cnt = self.debug(9, np.uint32, 8)
+        cnt = self.debug(9, np.uint32, 16)
         st = {"n_seeds": self.debug(0, np.int32, n), "seed_off": self.debug(1, np.uint32, n), "segs": self.debug(2, SEG_DTYPE, int(cnt[0])),
               "n_cands": self.debug(3, np.int32, n), "cand_off": self.debug(4, np.uint32, n), "cands": self.debug(5, CAND_DTYPE, int(cnt[1])),
               "reports": self.debug(6, REPORT_DTYPE, int(cnt[1])), "res": self.debug(7, RES_DTYPE, n), "cigar": self.debug(8, np.uint32, int(cnt[2]))}

@@ -416,150 +416,12 @@ KB_HD void kb_align_fragments(const KbFragCtx& fc, const u8* f1, int rl0, const 
 }
 
 // ================================================================================================
-// Fragment-pair processing
-// ================================================================================================
-struct KbReadCtx
-{
-	const KbIndexDev* ix; const KbParams* pm; KbArena* ar;
-	const u8* seq; int rlen;
-	unsigned long long cells; u32 nw_calls;
-};
-
-// reference characters [gpos, gpos+len) into arena memory
-KB_HD u8* kb_fetch_ref(KbReadCtx& rc, i64 gpos, int len)
-{
-	u8* f = (u8*)rc.ar->alloc((u64)(len > 0 ? len : 1));
-	if (f == nullptr) return nullptr;
-	for (int i = 0; i < len; i++) f[i] = kb_code_char(kb_ref_code(*rc.ix, gpos + i));
-	return f;
-}
-
-KB_HD int kb_mismatches(const u8* a, const u8* b, int n) { int c = 0; for (int i = 0; i < n; i++) if (a[i] != b[i]) c++; return c; }
-
-// AddNewCigarElements: run list -> cigar elements (D/I/M), returns identity count
-KB_HD int kb_push_runs(const KbRuns& acc, int first, int last, KbCigar& cg)
-{
-	for (int k = first; k < last; k++)
-	{
-		int t = (int)(acc.r[k] & 3), len = (int)(acc.r[k] >> 2);
-		cg.push(len, t == KB_RUN_D ? KB_OP_D : (t == KB_RUN_I ? KB_OP_I : KB_OP_M));
-	}
-	return acc.ident;
-}
-
-KB_HD bool kb_init_runs(KbReadCtx& rc, KbRuns& acc, int rl, int gl)
-{
-	acc.cap = rl + gl + 2; acc.n = 0; acc.ident = 0; acc.aligned = 0; acc.ovf = false;
-	acc.r = (u32*)rc.ar->alloc((u64)acc.cap * 4);
-	return acc.r != nullptr;
-}
-
-KB_HD void kb_align(KbReadCtx& rc, const u8* f1, int rl, const u8* f2, int gl, KbRuns& acc)
-{
-	KbFragCtx fc; fc.pm = rc.pm; fc.ar = rc.ar; fc.cells = &rc.cells; fc.nw_calls = &rc.nw_calls;
-	kb_align_fragments(fc, f1, rl, f2, gl, acc);
-	if (acc.ovf) rc.ar->ovf = true;
-}
-
-// quick test of tools.cpp:240/301/352: equal length, <= 2 mismatches and <= 20 %
-KB_HD bool kb_quick_match(const u8* f1, const u8* f2, int rl, int gl, int* n)
-{
-	if (rl != gl) return false;
-	*n = kb_mismatches(f1, f2, rl);
-	return *n <= 2 && *n <= (int)(rl * 0.2);
-}
-
-KB_HD int kb_do_middle(KbReadCtx& rc, KbSeg& sp, KbCigar& cg)   // ProcessNormalSequencePair :225
-{
-	if (sp.rlen == 0 || sp.glen == 0)
-	{
-		if (sp.rlen > 0) cg.push(sp.rlen, KB_OP_I); else if (sp.glen > 0) cg.push(sp.glen, KB_OP_D);
-		return 0;
-	}
-	u64 mark = rc.ar->used; int score = 0, n;
-	const u8* f1 = rc.seq + sp.rpos; u8* f2 = kb_fetch_ref(rc, sp.gpos, sp.glen);
-	if (f2 != nullptr)
-	{
-		if (kb_quick_match(f1, f2, sp.rlen, sp.glen, &n)) { cg.push(sp.rlen, KB_OP_M); score = sp.rlen - n; }
-		else
-		{
-			KbRuns acc;
-			if (kb_init_runs(rc, acc, sp.rlen, sp.glen)) { kb_align(rc, f1, sp.rlen, f2, sp.glen, acc); score = kb_push_runs(acc, 0, acc.n, cg); }
-		}
-	}
-	rc.ar->used = mark;
-	return score;
-}
-
-// CheckLocalAlignmentQuality :255 on the run list
-KB_HD bool kb_quality_ok(const KbRuns& acc)
-{
-	int mis = acc.aligned - acc.ident;
-	return !(acc.n >= 4 || (mis >= 3 && mis >= (int)(acc.aligned * 0.3)));
-}
-
-KB_HD int kb_do_head(KbReadCtx& rc, KbSeg& sp, KbCigar& cg)   // ProcessHeadSequencePair :292
-{
-	u64 mark = rc.ar->used; int score = 0, n;
-	const u8* f1 = rc.seq + sp.rpos; u8* f2 = kb_fetch_ref(rc, sp.gpos, sp.glen);
-	if (f2 != nullptr)
-	{
-		if (!rc.pm->pacbio && kb_quick_match(f1, f2, sp.rlen, sp.glen, &n)) { cg.push(sp.rlen, KB_OP_M); score = sp.rlen - n; }
-		else if (!rc.pm->pacbio && sp.rlen > 50) cg.push(sp.rlen, KB_OP_S);
-		else
-		{
-			KbRuns acc;
-			if (kb_init_runs(rc, acc, sp.rlen, sp.glen))
-			{
-				kb_align(rc, f1, sp.rlen, f2, sp.glen, acc);
-				if (!kb_quality_ok(acc)) cg.push(sp.rlen, KB_OP_S);
-				else
-				{
-					int first = 0;
-					// leading gaps in the read block shrink the genome block; then leading gaps in the genome block become a soft clip
-					if (first < acc.n && (acc.r[first] & 3) == KB_RUN_D) { int p = (int)(acc.r[first] >> 2); sp.gpos += p; sp.glen -= p; first++; }
-					if (first < acc.n && (acc.r[first] & 3) == KB_RUN_I) { int p = (int)(acc.r[first] >> 2); sp.rpos += p; sp.rlen -= p; cg.push(p, KB_OP_S); first++; }
-					score = kb_push_runs(acc, first, acc.n, cg);
-				}
-			}
-		}
-	}
-	rc.ar->used = mark;
-	return score;
-}
-
-KB_HD int kb_do_tail(KbReadCtx& rc, KbSeg& sp, KbCigar& cg)   // ProcessTailSequencePair :344
-{
-	u64 mark = rc.ar->used; int score = 0, n;
-	const u8* f1 = rc.seq + sp.rpos; u8* f2 = kb_fetch_ref(rc, sp.gpos, sp.glen);
-	if (f2 != nullptr)
-	{
-		if (!rc.pm->pacbio && kb_quick_match(f1, f2, sp.rlen, sp.glen, &n)) { cg.push(sp.rlen, KB_OP_M); score = sp.rlen - n; }
-		else if (!rc.pm->pacbio && sp.rlen > 100) cg.push(sp.rlen, KB_OP_S);
-		else
-		{
-			KbRuns acc;
-			if (kb_init_runs(rc, acc, sp.rlen, sp.glen))
-			{
-				kb_align(rc, f1, sp.rlen, f2, sp.glen, acc);
-				if (!kb_quality_ok(acc)) cg.push(sp.rlen, KB_OP_S);
-				else
-				{
-					int last = acc.n, clip = 0;
-					if (last > 0 && (acc.r[last - 1] & 3) == KB_RUN_D) { int c = (int)(acc.r[last - 1] >> 2); sp.glen -= c; last--; }
-					if (last > 0 && (acc.r[last - 1] & 3) == KB_RUN_I) { clip = (int)(acc.r[last - 1] >> 2); sp.rlen -= clip; last--; }
-					score = kb_push_runs(acc, 0, last, cg);
-					if (clip > 0) cg.push(clip, KB_OP_S);
-				}
-			}
-		}
-	}
-	rc.ar->used = mark;
-	return score;
-}
-
-// ================================================================================================
-// Reports
+// Fragment-pair processing, split in three phases so that the expensive, divergent part (partition + NW) runs in its own
+// kernel over a compact job list:
+//   phase A  kb_segments_read : IdentifyNormalPairs per surviving candidate, every segment classified; the quick tests of
+//                                Process{Normal,Head,Tail}SequencePair (tools.cpp:229-244,301-311,352-362) are decided here
+//   phase B  kb_align_job     : GenerateNormalPairAlignment (tools.cpp:142) for the segments that need it
+//   phase C  kb_assemble_read : cigar elements, head/tail post-processing, GapPenalty, coordinates, best/sub-score
 // ================================================================================================
 KB_HD bool kb_same_chromosome(const KbIndexDev& ix, const KbSeg* v, int n)   // CheckCoordinateValidity :582
 {
@@ -571,6 +433,142 @@ KB_HD bool kb_same_chromosome(const KbIndexDev& ix, const KbSeg* v, int n)   // 
 	return ea < ix.n_ends && eb < ix.n_ends && ix.end_chr[ea] == ix.end_chr[eb];
 }
 
+KB_HD u8 kb_ref_char(const KbIndexDev& ix, i64 p) { return kb_code_char(kb_ref_code(ix, p)); }
+
+// mismatches between read[rpos..] and the reference at gpos, stopping once more than `limit` were seen
+KB_HD int kb_mismatch_ref(const KbIndexDev& ix, const u8* f1, i64 gpos, int n, int limit)
+{
+	int c = 0;
+	for (int i = 0; i < n && c <= limit; i++) if (f1[i] != kb_ref_char(ix, gpos + i)) c++;
+	return c;
+}
+
+// quick test of tools.cpp:240/301/352: equal length, <= 2 mismatches and <= 20 %
+KB_HD bool kb_quick_match_ref(const KbIndexDev& ix, const u8* f1, const KbSeg& sp, int* n)
+{
+	if (sp.rlen != sp.glen) return false;
+	*n = kb_mismatch_ref(ix, f1, sp.gpos, sp.rlen, 2);
+	return *n <= 2 && *n <= (int)(sp.rlen * 0.2);
+}
+
+KB_HD void kb_classify_segment(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int r, const u8* seq, const KbSeg& sp, int j, int n, KbSegX* out)
+{
+	out->s = sp; out->info = KB_SEG_SKIP; out->aux = 0;
+	if (sp.rlen == 0 && sp.glen == 0) return;
+	if (sp.simple) { out->info = KB_SEG_SIMPLE; return; }
+	const u8* f1 = seq + sp.rpos; int mm;
+	if (j == 0 || j == n - 1)
+	{
+		if (sp.rlen > 3000) { out->info = KB_SEG_SOFT; return; }                                  // AlignmentCandidates.cpp:671,690
+		if (!pm.pacbio && kb_quick_match_ref(ix, f1, sp, &mm)) { out->info = KB_SEG_QUICK; out->aux = (u32)(sp.rlen - mm); return; }
+		if (!pm.pacbio && sp.rlen > (j == 0 ? 50 : 100)) { out->info = KB_SEG_SOFT; return; }     // tools.cpp:307,358
+	}
+	else
+	{
+		if (sp.rlen == 0 || sp.glen == 0) { out->info = KB_SEG_GAP; return; }
+		if (kb_quick_match_ref(ix, f1, sp, &mm)) { out->info = KB_SEG_QUICK; out->aux = (u32)(sp.rlen - mm); return; }
+	}
+	if (sp.rlen == 1 && sp.glen == 1)
+	{
+		// nw_alignment on 1 x 1 always yields one aligned column (diag +-3 beats both gap paths at -6)
+		out->info = KB_SEG_ONE; out->aux = f1[0] == kb_ref_char(ix, sp.gpos) ? 1u : 0u;
+		return;
+	}
+	u32 id = KB_ATOMIC_ADD(&bt.counters[9], 1u);
+	u32 need = (u32)(sp.rlen + sp.glen + 2);
+	u32 ro = KB_ATOMIC_ADD(&bt.counters[10], need);
+	if (id >= bt.cap_jobs) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_JOBS); return; }
+	if ((u64)ro + need > (u64)bt.cap_runs) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_RUNS); return; }
+	KbJob jb; jb.gpos = sp.gpos; jb.read = (u32)r; jb.rpos = sp.rpos; jb.rlen = sp.rlen; jb.glen = sp.glen; jb.run_off = ro; jb.nruns = 0; jb.ident = 0; jb.aligned = 0;
+	bt.jobs[id] = jb;
+	out->info = KB_SEG_JOB; out->aux = id;
+}
+
+// phase A
+KB_HD void kb_segments_read(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int r, KbArena& ar)
+{
+	KbCand* cv = bt.cands + bt.cand_off[r];
+	int ncan = bt.n_cands[r];
+	const u8* seq = bt.seq + bt.seq_off[r]; int rlen = (int)(bt.seq_off[r + 1] - bt.seq_off[r]);
+	for (int i = 0; i < ncan; i++)
+	{
+		u32 ci = bt.cand_off[r] + (u32)i;
+		bt.cseg_n[ci] = -1; bt.cseg_off[ci] = 0;
+		if (cv[i].score == 0) continue;
+		u64 mark = ar.used;
+		int ns = cv[i].nseg;
+		KbSeg* in = (KbSeg*)ar.alloc((u64)(ns > 0 ? ns : 1) * sizeof(KbSeg));
+		KbSeg* sv = (KbSeg*)ar.alloc((u64)(2 * ns + 2) * sizeof(KbSeg));
+		i32* order = (i32*)ar.alloc((u64)(ns > 0 ? ns : 1) * 4);
+		if (ar.ovf) return;
+		for (int k = 0; k < ns; k++) in[k] = bt.segs[cv[i].seg_start + k];
+		int n = kb_fill_pairs(rlen, -1, in, ns, sv, order);
+		if (kb_same_chromosome(ix, sv, n))
+		{
+			u32 off = KB_ATOMIC_ADD(&bt.counters[8], (u32)n);
+			if ((u64)off + (u64)n > (u64)bt.cap_segx) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SEGX); ar.used = mark; return; }
+			bt.cseg_off[ci] = off; bt.cseg_n[ci] = n;
+			for (int j = 0; j < n; j++) kb_classify_segment(ix, pm, bt, r, seq, sv[j], j, n, &bt.segx[off + j]);
+		}
+		ar.used = mark;
+	}
+}
+
+// phase B: one job (thread-sequential version)
+KB_HD void kb_align_job(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, u32 id, KbArena& ar, unsigned long long* cells, u32* nw_calls)
+{
+	KbJob& jb = bt.jobs[id];
+	u64 mark = ar.used;
+	u8* f2 = (u8*)ar.alloc((u64)jb.glen);
+	if (f2 == nullptr) return;
+	for (int i = 0; i < jb.glen; i++) f2[i] = kb_ref_char(ix, jb.gpos + i);
+	const u8* f1 = bt.seq + bt.seq_off[jb.read] + jb.rpos;
+	KbRuns acc; acc.r = bt.runs + jb.run_off; acc.cap = jb.rlen + jb.glen + 2; acc.n = 0; acc.ident = 0; acc.aligned = 0; acc.ovf = false;
+	KbFragCtx fc; fc.pm = &pm; fc.ar = &ar; fc.cells = cells; fc.nw_calls = nw_calls;
+	kb_align_fragments(fc, f1, jb.rlen, f2, jb.glen, acc);
+	if (acc.ovf) ar.ovf = true;
+	jb.nruns = acc.n; jb.ident = acc.ident; jb.aligned = acc.aligned;
+	ar.used = mark;
+}
+
+// AddNewCigarElements: run list -> cigar elements (D/I/M)
+KB_HD void kb_push_runs(const u32* runs, int first, int last, KbCigar& cg)
+{
+	for (int k = first; k < last; k++)
+	{
+		int t = (int)(runs[k] & 3), len = (int)(runs[k] >> 2);
+		cg.push(len, t == KB_RUN_D ? KB_OP_D : (t == KB_RUN_I ? KB_OP_I : KB_OP_M));
+	}
+}
+
+// the alignment of one non-trivial segment as phase C sees it
+struct KbAlnView { const u32* runs; int n, ident, aligned; u32 one; };
+KB_HD KbAlnView kb_view(const KbBatchDev& bt, const KbSegX& x)
+{
+	KbAlnView v;
+	if (x.info == KB_SEG_ONE) { v.one = (1u << 2) | (u32)KB_RUN_M; v.runs = nullptr; v.n = 1; v.ident = (int)x.aux; v.aligned = 1; }
+	else { const KbJob& jb = bt.jobs[x.aux]; v.one = 0; v.runs = bt.runs + jb.run_off; v.n = jb.nruns; v.ident = jb.ident; v.aligned = jb.aligned; }
+	return v;
+}
+KB_HD u32 kb_view_run(const KbAlnView& v, int k) { return v.runs ? v.runs[k] : v.one; }
+KB_HD void kb_view_push(const KbAlnView& v, int first, int last, KbCigar& cg)
+{
+	for (int k = first; k < last; k++)
+	{
+		u32 e = kb_view_run(v, k); int t = (int)(e & 3), len = (int)(e >> 2);
+		cg.push(len, t == KB_RUN_D ? KB_OP_D : (t == KB_RUN_I ? KB_OP_I : KB_OP_M));
+	}
+}
+// CheckLocalAlignmentQuality :255 on the run list
+KB_HD bool kb_quality_ok(const KbAlnView& v)
+{
+	int mis = v.aligned - v.ident;
+	return !(v.n >= 4 || (mis >= 3 && mis >= (int)(v.aligned * 0.3)));
+}
+
+// ================================================================================================
+// Reports
+// ================================================================================================
 // GenCoordinateInfo + GenerateCIGAR: writes the merged cigar into the global arena
 KB_HD void kb_locate_report(const KbIndexDev& ix, const KbBatchDev& bt, bool first, i64 gpos, i64 gend, KbCigar& cg, KbReport& rp)
 {
@@ -605,16 +603,15 @@ KB_HD void kb_locate_report(const KbIndexDev& ix, const KbBatchDev& bt, bool fir
 	}
 }
 
-// GenMappingReport for one read. cands/reports are this read's slices.
-KB_HD void kb_report_read(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int r, KbArena& ar)
+// phase C: GenMappingReport for one read from the stored segments and job results. cands/reports are this read's slices.
+KB_HD void kb_assemble_read(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int r, KbArena& ar)
 {
 	KbReadRes& rd = bt.res[r];
 	KbCand* cv = bt.cands + bt.cand_off[r];
 	KbReport* rep = bt.reports + bt.cand_off[r];
 	int ncan = bt.n_cands[r];
 	bool first = pm.paired ? ((r & 1) == 0) : true;
-	KbReadCtx rc; rc.ix = &ix; rc.pm = &pm; rc.ar = &ar; rc.seq = bt.seq + bt.seq_off[r]; rc.rlen = (int)(bt.seq_off[r + 1] - bt.seq_off[r]);
-	rc.cells = 0; rc.nw_calls = 0;
+	int rlen = (int)(bt.seq_off[r + 1] - bt.seq_off[r]);
 	rd.score = 0; rd.sub = 0; rd.best = 0; rd.mapq = 0; rd.rep_off = bt.cand_off[r];
 	if (ncan == 0)
 	{
@@ -630,63 +627,90 @@ KB_HD void kb_report_read(const KbIndexDev& ix, const KbParams& pm, const KbBatc
 		rep[i] = rp;
 		if (cv[i].score == 0) continue;
 		if (pm.pacbio && rd.score > 0) { rd.sub = rd.score; continue; }
+		u32 ci = bt.cand_off[r] + (u32)i;
+		int n = bt.cseg_n[ci];
+		if (n < 0) continue;                       // CheckCoordinateValidity failed
+		const KbSegX* sx = bt.segx + bt.cseg_off[ci];
 		u64 mark = ar.used;
-		int ns = cv[i].nseg;
-		KbSeg* in = (KbSeg*)ar.alloc((u64)(ns > 0 ? ns : 1) * sizeof(KbSeg));
-		KbSeg* sv = (KbSeg*)ar.alloc((u64)(2 * ns + 2) * sizeof(KbSeg));
-		i32* order = (i32*)ar.alloc((u64)(ns > 0 ? ns : 1) * 4);
-		KbCigar cg; cg.n = 0; cg.ovf = false; cg.cap = 3 * rc.rlen + 2 * ns + 64; cg.e = (u32*)ar.alloc((u64)cg.cap * 4);
-		if (ar.ovf) { ar.used = mark; break; }
-		for (int k = 0; k < ns; k++) in[k] = bt.segs[cv[i].seg_start + k];
-		int n = kb_fill_pairs(rc.rlen, -1, in, ns, sv, order);
-		if (kb_same_chromosome(ix, sv, n))
+		KbCigar cg; cg.n = 0; cg.ovf = false; cg.cap = 3 * rlen + 2 * n + 64; cg.e = (u32*)ar.alloc((u64)cg.cap * 4);
+		if (ar.ovf) break;
+		i64 g_first = n > 0 ? sx[0].s.gpos : 0, g_end = n > 0 ? sx[n - 1].s.gpos + sx[n - 1].s.glen - 1 : 0;
+		for (int j = 0; j < n; j++)
 		{
-			for (int j = 0; j < n; j++)
+			const KbSegX& x = sx[j]; const KbSeg& sp = x.s;
+			if (x.info == KB_SEG_SKIP) continue;
+			if (x.info == KB_SEG_SIMPLE) { cg.push(sp.rlen, KB_OP_M); rp.aln += sp.rlen; continue; }
+			if (j == 0)   // ProcessHeadSequencePair :292 and AlignmentCandidates.cpp:669-687
 			{
-				if (sv[j].rlen == 0 && sv[j].glen == 0) continue;
-				if (sv[j].simple) { cg.push(sv[j].rlen, KB_OP_M); rp.aln += sv[j].rlen; continue; }
-				if (j == 0)
+				int s = 0; i64 gpos = sp.gpos;
+				if (x.info == KB_SEG_SOFT) cg.push(sp.rlen, KB_OP_S);
+				else if (x.info == KB_SEG_QUICK) { cg.push(sp.rlen, KB_OP_M); s = (int)x.aux; }
+				else
 				{
-					int s = 0;
-					if (sv[0].rlen > 3000) cg.push(sv[0].rlen, KB_OP_S);
-					else { s = kb_do_head(rc, sv[0], cg); rp.aln += s; }
-					if (s == 0) { sv[0].gpos = sv[1].gpos; sv[0].glen = 0; }
+					KbAlnView v = kb_view(bt, x);
+					if (!kb_quality_ok(v)) cg.push(sp.rlen, KB_OP_S);
+					else
+					{
+						int f = 0;
+						if (f < v.n && (kb_view_run(v, f) & 3) == KB_RUN_D) { gpos += (int)(kb_view_run(v, f) >> 2); f++; }
+						if (f < v.n && (kb_view_run(v, f) & 3) == KB_RUN_I) { cg.push((int)(kb_view_run(v, f) >> 2), KB_OP_S); f++; }
+						kb_view_push(v, f, v.n, cg); s = v.ident;
+					}
 				}
-				else if (j == n - 1)
-				{
-					int s = 0;
-					if (sv[j].rlen > 3000) cg.push(sv[j].rlen, KB_OP_S);
-					else { s = kb_do_tail(rc, sv[j], cg); rp.aln += s; }
-					if (s == 0) { sv[j].gpos = sv[j - 1].gpos + sv[j - 1].glen; sv[j].glen = 0; }
-				}
-				else rp.aln += kb_do_middle(rc, sv[j], cg);
+				rp.aln += s;
+				g_first = s == 0 ? sx[1].s.gpos : gpos;
 			}
-			if (cg.ovf) ar.ovf = true;
-			bool dead = false;
-			if (!pm.pacbio && cg.n > 1)
+			else if (j == n - 1)   // ProcessTailSequencePair :344 and AlignmentCandidates.cpp:688-706
 			{
-				int gp = 0; for (int k = 0; k < cg.n; k++) { int op = (int)(cg.e[k] & 15); if (op == KB_OP_I || op == KB_OP_D) gp += (int)(cg.e[k] >> 4); }
-				rp.aln -= gp;
-				if (rp.aln <= 0) { rp.aln = 0; dead = true; }
-			}
-			if (!dead)
-			{
-				if (cg.n == 0) rp.aln = 0;
-				else { kb_locate_report(ix, bt, first, sv[0].gpos, sv[n - 1].gpos + sv[n - 1].glen - 1, cg, rp); if (rp.pos <= 0) rp.aln = 0; }
-				if (rp.aln > rd.score) { rd.best = i; rd.sub = rd.score; rd.score = rp.aln; }
-				else if (rp.aln == rd.score)
+				int s = 0, glen = sp.glen;
+				if (x.info == KB_SEG_SOFT) cg.push(sp.rlen, KB_OP_S);
+				else if (x.info == KB_SEG_QUICK) { cg.push(sp.rlen, KB_OP_M); s = (int)x.aux; }
+				else
 				{
-					rd.sub = rd.score;
-					if (!pm.multihit && ix.chr_len[rp.chr] > ix.chr_len[rep[rd.best].chr]) rd.best = i;
+					KbAlnView v = kb_view(bt, x);
+					if (!kb_quality_ok(v)) cg.push(sp.rlen, KB_OP_S);
+					else
+					{
+						int last = v.n, clip = 0;
+						if (last > 0 && (kb_view_run(v, last - 1) & 3) == KB_RUN_D) { glen -= (int)(kb_view_run(v, last - 1) >> 2); last--; }
+						if (last > 0 && (kb_view_run(v, last - 1) & 3) == KB_RUN_I) { clip = (int)(kb_view_run(v, last - 1) >> 2); last--; }
+						kb_view_push(v, 0, last, cg); s = v.ident;
+						if (clip > 0) cg.push(clip, KB_OP_S);
+					}
 				}
+				rp.aln += s;
+				g_end = s == 0 ? sx[j - 1].s.gpos + sx[j - 1].s.glen - 1 : sp.gpos + glen - 1;
+			}
+			else   // ProcessNormalSequencePair :225
+			{
+				if (x.info == KB_SEG_GAP) { if (sp.rlen > 0) cg.push(sp.rlen, KB_OP_I); else cg.push(sp.glen, KB_OP_D); }
+				else if (x.info == KB_SEG_QUICK) { cg.push(sp.rlen, KB_OP_M); rp.aln += (int)x.aux; }
+				else { KbAlnView v = kb_view(bt, x); kb_view_push(v, 0, v.n, cg); rp.aln += v.ident; }
+			}
+		}
+		if (cg.ovf) ar.ovf = true;
+		bool dead = false;
+		if (!pm.pacbio && cg.n > 1)
+		{
+			int gp = 0; for (int k = 0; k < cg.n; k++) { int op = (int)(cg.e[k] & 15); if (op == KB_OP_I || op == KB_OP_D) gp += (int)(cg.e[k] >> 4); }   // GapPenalty :612
+			rp.aln -= gp;
+			if (rp.aln <= 0) { rp.aln = 0; dead = true; }
+		}
+		if (!dead)
+		{
+			if (cg.n == 0) rp.aln = 0;
+			else { kb_locate_report(ix, bt, first, g_first, g_end, cg, rp); if (rp.pos <= 0) rp.aln = 0; }
+			if (rp.aln > rd.score) { rd.best = i; rd.sub = rd.score; rd.score = rp.aln; }
+			else if (rp.aln == rd.score)
+			{
+				rd.sub = rd.score;
+				if (!pm.multihit && ix.chr_len[rp.chr] > ix.chr_len[rep[rd.best].chr]) rd.best = i;
 			}
 		}
 		rep[i] = rp;
 		ar.used = mark;
 		if (ar.ovf) break;
 	}
-	if (rc.cells) KB_ATOMIC_ADD(&bt.work[3], rc.cells);
-	if (rc.nw_calls) KB_ATOMIC_ADD(&bt.counters[6], rc.nw_calls);
 }
 
 #endif

@@ -1,6 +1,6 @@
 // kart_b200: CUDA kernels (sm_100a) and the C ABI declared in include/kart_b200.h.
 // One context = one device, one stream. The pipeline of a batch is six kernels with no host round trip in between:
-//   k_fm_seed -> k_sa_locate -> k_cand_pair -> k_rescue -> k_report -> k_finalize
+//   k_fm_seed -> k_sa_locate -> k_cand_pair -> k_rescue -> k_segments -> k_align -> k_assemble -> k_finalize
 // Capacities of the bump-allocated arenas are checked on the device; a batch that overflowed anything is rerun with
 // larger arenas (never silently truncated, never sent to a CPU path -- there is none).
 #ifndef KB_EMUL
@@ -129,7 +129,14 @@ static void k_rescue(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulation: 
 	}
 }
 #endif
-__global__ void __launch_bounds__(KB_BLOCK) k_report(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_report(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
+__global__ void __launch_bounds__(KB_BLOCK) k_segments(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_segments(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
+__global__ void __launch_bounds__(KB_BLOCK) k_align(KbIndexDev ix, KbParams pm, KbBatchDev bt)
+{
+	unsigned long long cells = 0; u32 calls = 0;
+	kb_stage_align(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, &cells, &calls);
+	kb_warp_add64(&bt.work[3], cells); kb_warp_add64(&bt.work[4], calls);
+}
+__global__ void __launch_bounds__(KB_BLOCK) k_assemble(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_assemble(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
 __global__ void __launch_bounds__(KB_BLOCK) k_finalize(KbIndexDev ix, KbParams pm, KbBatchDev bt, kb_aln_t* aln) { kb_stage_finalize(ix, pm, bt, aln, blockIdx.x * blockDim.x + threadIdx.x); }
 
 // ------------------------------------------------------------------------------------------------
@@ -151,11 +158,11 @@ struct kb_ctx
 	int64_t l_pac = 0;
 	// batch
 	KbBatchDev bt; bool staged = false, ran = false; int n_reads = 0; size_t seq_bytes = 0;
-	DevBuf<u8> seq, scratch; DevBuf<u64> seq_off; DevBuf<unsigned long long> work; DevBuf<i32> est, n_hits, n_seeds, n_cands, cand_cap, rescue; DevBuf<u32> seed_off, cand_off, cigar, counters;
+	DevBuf<u8> seq, scratch; DevBuf<u64> seq_off; DevBuf<unsigned long long> work; DevBuf<i32> est, n_hits, n_seeds, n_cands, cand_cap, rescue; DevBuf<u32> seed_off, cand_off, cigar, counters, cseg_off, runs; DevBuf<i32> cseg_n; DevBuf<KbSegX> segx; DevBuf<KbJob> jobs;
 	DevBuf<KbHit> hits; DevBuf<KbSeg> segs; DevBuf<KbCand> cands; DevBuf<KbReport> reports; DevBuf<KbReadRes> res; DevBuf<KbPairStat> pstat; DevBuf<kb_aln_t> aln;
-	size_t cap_segs = 0, cap_cands = 0, cap_cigar = 0, scratch_per_thread = 0; int scratch_threads = 0; int max_rlen = 0;
-	double seg_factor = 32, cigar_factor = 8, scratch_factor = 1;
-	cudaEvent_t ev[8]; float stage_ms[7]; uint64_t work_host[8]; u32 counters_host[8]; int launches = 0;
+	size_t cap_segs = 0, cap_cands = 0, cap_cigar = 0, cap_segx = 0, cap_jobs = 0, cap_runs = 0, scratch_per_thread = 0; int scratch_threads = 0; int max_rlen = 0;
+	double seg_factor = 32, cigar_factor = 8, scratch_factor = 1, segx_factor = 8, job_factor = 4, run_factor = 96;
+	cudaEvent_t ev[10]; float stage_ms[9]; uint64_t work_host[8]; u32 counters_host[16]; int launches = 0;
 };
 
 static int fail(kb_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess)
@@ -200,7 +207,7 @@ int kb_init(int device, kb_ctx_t** out)
 	memset(&ctx->ix, 0, sizeof(ctx->ix)); memset(&ctx->bt, 0, sizeof(ctx->bt)); memset(ctx->stage_ms, 0, sizeof(ctx->stage_ms)); memset(ctx->work_host, 0, sizeof(ctx->work_host));
 	ctx->pm.min_seed = 0; ctx->pm.max_gaps = 5; ctx->pm.max_insert = 1500; ctx->pm.pacbio = 0; ctx->pm.multihit = 0; ctx->pm.paired = 0;
 	if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return KB_ECUDA; }
-	for (int i = 0; i < 8; i++) cudaEventCreate(&ctx->ev[i]);
+	for (int i = 0; i < 10; i++) cudaEventCreate(&ctx->ev[i]);
 	*out = ctx;
 	return KB_OK;
 }
@@ -213,8 +220,8 @@ void kb_destroy(kb_ctx_t* ctx)
 	ctx->occ.release(); ctx->sa.release(); ctx->sa_full.release(); ctx->pac.release(); ctx->lut.release(); ctx->chr64.release(); ctx->chr32.release();
 	ctx->seq.release(); ctx->scratch.release(); ctx->seq_off.release(); ctx->work.release(); ctx->est.release(); ctx->n_hits.release(); ctx->n_seeds.release();
 	ctx->n_cands.release(); ctx->cand_cap.release(); ctx->rescue.release(); ctx->seed_off.release(); ctx->cand_off.release(); ctx->cigar.release(); ctx->counters.release();
-	ctx->hits.release(); ctx->segs.release(); ctx->cands.release(); ctx->reports.release(); ctx->res.release(); ctx->pstat.release(); ctx->aln.release();
-	for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->ev[i]);
+	ctx->cseg_off.release(); ctx->runs.release(); ctx->cseg_n.release(); ctx->segx.release(); ctx->jobs.release(); ctx->hits.release(); ctx->segs.release(); ctx->cands.release(); ctx->reports.release(); ctx->res.release(); ctx->pstat.release(); ctx->aln.release();
+	for (int i = 0; i < 10; i++) cudaEventDestroy(ctx->ev[i]);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -308,6 +315,10 @@ static int alloc_batch(kb_ctx* ctx)
 	ctx->cap_cands = 2 * ctx->cap_segs + 2 * n + 1024;
 	if (ctx->cap_cands > 0xF0000000ull) ctx->cap_cands = 0xF0000000ull;
 	ctx->cap_cigar = (size_t)(ctx->cigar_factor * (double)n) + (ctx->pm.pacbio ? (size_t)n * (size_t)(L / 2) : 0) + 65536;
+	ctx->cap_segx = (size_t)(ctx->segx_factor * (double)n) + (ctx->pm.pacbio ? (size_t)n * (size_t)(L / 16 + 64) : 0) + 65536;
+	ctx->cap_jobs = (size_t)(ctx->job_factor * (double)n) + (ctx->pm.pacbio ? (size_t)n * (size_t)(L / 32 + 32) : 0) + 65536;
+	ctx->cap_runs = (size_t)(ctx->run_factor * (double)n) + (ctx->pm.pacbio ? (size_t)n * (size_t)(3 * L) : 0) + (1 << 20);
+	if (ctx->cap_runs > 0xF0000000ull) ctx->cap_runs = 0xF0000000ull;
 	// per-thread scratch of the report / rescue kernels: NW traceback (2 bit / cell) dominates
 	double side = L < 3100 ? L + 64 : 3100 + 64;
 	size_t per = (size_t)(side * side / 4) + (size_t)L * 160 + (64 << 10);
@@ -322,11 +333,13 @@ static int alloc_batch(kb_ctx* ctx)
 	CK(ctx->segs.ensure(ctx->cap_segs)); CK(ctx->cands.ensure(ctx->cap_cands)); CK(ctx->reports.ensure(ctx->cap_cands));
 	CK(ctx->n_cands.ensure(n)); CK(ctx->cand_off.ensure(n)); CK(ctx->cand_cap.ensure(n)); CK(ctx->rescue.ensure(n / 2 + 1));
 	CK(ctx->res.ensure(n)); CK(ctx->pstat.ensure(n / 2 + 1)); CK(ctx->aln.ensure(n)); CK(ctx->cigar.ensure(ctx->cap_cigar));
-	CK(ctx->counters.ensure(8)); CK(ctx->work.ensure(4)); CK(ctx->scratch.ensure(per * threads));
+	CK(ctx->segx.ensure(ctx->cap_segx)); CK(ctx->jobs.ensure(ctx->cap_jobs)); CK(ctx->runs.ensure(ctx->cap_runs)); CK(ctx->cseg_off.ensure(ctx->cap_cands)); CK(ctx->cseg_n.ensure(ctx->cap_cands));
+	CK(ctx->counters.ensure(16)); CK(ctx->work.ensure(8)); CK(ctx->scratch.ensure(per * threads));
 	bt.n_reads = ctx->n_reads; bt.seq = ctx->seq.p; bt.seq_off = ctx->seq_off.p; bt.est = ctx->est.p;
 	bt.hits = ctx->hits.p; bt.max_hits = max_hits; bt.n_hits = ctx->n_hits.p; bt.n_seeds = ctx->n_seeds.p; bt.seed_off = ctx->seed_off.p;
 	bt.segs = ctx->segs.p; bt.cap_segs = (u32)ctx->cap_segs; bt.cands = ctx->cands.p; bt.cap_cands = (u32)ctx->cap_cands; bt.n_cands = ctx->n_cands.p;
 	bt.cand_off = ctx->cand_off.p; bt.cand_cap = ctx->cand_cap.p; bt.rescue_list = ctx->rescue.p; bt.reports = ctx->reports.p; bt.res = ctx->res.p; bt.pstat = ctx->pstat.p;
+	bt.segx = ctx->segx.p; bt.cap_segx = (u32)ctx->cap_segx; bt.cseg_off = ctx->cseg_off.p; bt.cseg_n = ctx->cseg_n.p; bt.jobs = ctx->jobs.p; bt.cap_jobs = (u32)ctx->cap_jobs; bt.runs = ctx->runs.p; bt.cap_runs = (u32)ctx->cap_runs;
 	bt.cigar = ctx->cigar.p; bt.cap_cigar = (u32)ctx->cap_cigar; bt.scratch = ctx->scratch.p; bt.scratch_per_thread = per; bt.scratch_threads = (int)threads;
 	bt.max_rlen = L; bt.nw_max_m = 0; bt.nw_max_n = 0; bt.seg_cap = 0; bt.kmer_cap = 0; bt.counters = ctx->counters.p; bt.work = ctx->work.p;
 	return KB_OK;
@@ -358,7 +371,7 @@ static int launch_pipeline(kb_ctx* ctx)
 {
 	KbBatchDev& bt = ctx->bt; const KbIndexDev& ix = ctx->ix; const KbParams& pm = ctx->pm;
 	int n = ctx->n_reads; cudaStream_t s = ctx->stream;
-	CK(cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(u32), s)); CK(cudaMemsetAsync(ctx->work.p, 0, 4 * sizeof(u64), s));
+	CK(cudaMemsetAsync(ctx->counters.p, 0, 16 * sizeof(u32), s)); CK(cudaMemsetAsync(ctx->work.p, 0, 8 * sizeof(u64), s));
 	unsigned g_reads = (unsigned)((n + KB_BLOCK - 1) / KB_BLOCK);
 	unsigned g_items = pm.paired ? (unsigned)((n / 2 + KB_BLOCK - 1) / KB_BLOCK) : g_reads;
 	unsigned g_hits = (unsigned)(((long long)n * bt.max_hits + KB_BLOCK - 1) / KB_BLOCK);
@@ -374,10 +387,14 @@ static int launch_pipeline(kb_ctx* ctx)
 	CK(cudaEventRecord(ctx->ev[3], s));
 	if (pm.paired) { KB_LAUNCH(k_rescue, g_scr, KB_BLOCK, s, ix, pm, bt); ctx->launches++; }
 	CK(cudaEventRecord(ctx->ev[4], s));
-	KB_LAUNCH(k_report, g_scr, KB_BLOCK, s, ix, pm, bt); ctx->launches++;
+	KB_LAUNCH(k_segments, g_scr, KB_BLOCK, s, ix, pm, bt); ctx->launches++;
 	CK(cudaEventRecord(ctx->ev[5], s));
-	KB_LAUNCH(k_finalize, g_items, KB_BLOCK, s, ix, pm, bt, ctx->aln.p); ctx->launches++;
+	KB_LAUNCH(k_align, g_scr, KB_BLOCK, s, ix, pm, bt); ctx->launches++;
 	CK(cudaEventRecord(ctx->ev[6], s));
+	KB_LAUNCH(k_assemble, g_scr, KB_BLOCK, s, ix, pm, bt); ctx->launches++;
+	CK(cudaEventRecord(ctx->ev[7], s));
+	KB_LAUNCH(k_finalize, g_items, KB_BLOCK, s, ix, pm, bt, ctx->aln.p); ctx->launches++;
+	CK(cudaEventRecord(ctx->ev[8], s));
 	CK(cudaGetLastError());
 	return KB_OK;
 }
@@ -393,17 +410,17 @@ int kb_run(kb_ctx_t* ctx)
 	{
 		int rc = alloc_batch(ctx); if (rc) return rc;
 		rc = launch_pipeline(ctx); if (rc) return rc;
-		CK(cudaMemcpyAsync(ctx->counters_host, ctx->counters.p, 8 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
-		unsigned long long w[4];
-		CK(cudaMemcpyAsync(w, ctx->work.p, 4 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaMemcpyAsync(ctx->counters_host, ctx->counters.p, 16 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+		unsigned long long w[8];
+		CK(cudaMemcpyAsync(w, ctx->work.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
 		CK(cudaStreamSynchronize(ctx->stream));
 		u32 st = ctx->counters_host[3];
 		if (st == 0)
 		{
-			for (int i = 0; i < 6; i++) cudaEventElapsedTime(&ctx->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]);
-			cudaEventElapsedTime(&ctx->stage_ms[6], ctx->ev[0], ctx->ev[6]);
+			for (int i = 0; i < 8; i++) cudaEventElapsedTime(&ctx->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]);
+			cudaEventElapsedTime(&ctx->stage_ms[8], ctx->ev[0], ctx->ev[8]);
 			ctx->work_host[0] = w[0]; ctx->work_host[1] = w[1]; ctx->work_host[2] = w[2]; ctx->work_host[3] = w[3];
-			ctx->work_host[4] = ctx->counters_host[0]; ctx->work_host[5] = ctx->counters_host[6]; ctx->work_host[6] = ctx->counters_host[7]; ctx->work_host[7] = (uint64_t)ctx->launches;
+			ctx->work_host[4] = ctx->counters_host[0]; ctx->work_host[5] = w[4]; ctx->work_host[6] = ctx->counters_host[7]; ctx->work_host[7] = (uint64_t)ctx->launches;
 			ctx->ran = true;
 			return KB_OK;
 		}
@@ -411,6 +428,9 @@ int kb_run(kb_ctx_t* ctx)
 		if (st & (KB_OVF_SEEDS | KB_OVF_CANDS | KB_OVF_HITS)) ctx->seg_factor *= 4;
 		if (st & KB_OVF_CIGAR) ctx->cigar_factor *= 4;
 		if (st & (KB_OVF_SCRATCH | KB_OVF_NW | KB_OVF_RESCUE)) ctx->scratch_factor *= 2;
+		if (st & KB_OVF_SEGX) ctx->segx_factor *= 4;
+		if (st & KB_OVF_JOBS) ctx->job_factor *= 4;
+		if (st & KB_OVF_RUNS) ctx->run_factor *= 4;
 	}
 	return fail(ctx, KB_EOVERFLOW, "kb_run: arenas still overflow after regrowth");
 }
@@ -439,7 +459,7 @@ int kb_map_chunk(kb_ctx_t* ctx, const kb_reads_t* in, const int32_t* est, kb_res
 	return kb_fetch_results(ctx, out);
 }
 
-int kb_stage_ms(kb_ctx_t* ctx, float* ms, int n) { if (!ctx || !ms) return KB_EINVAL; int k = n < 7 ? n : 7; for (int i = 0; i < k; i++) ms[i] = ctx->stage_ms[i]; return k; }
+int kb_stage_ms(kb_ctx_t* ctx, float* ms, int n) { if (!ctx || !ms) return KB_EINVAL; int k = n < 9 ? n : 9; for (int i = 0; i < k; i++) ms[i] = ctx->stage_ms[i]; return k; }
 int kb_work(kb_ctx_t* ctx, uint64_t* w, int n) { if (!ctx || !w) return KB_EINVAL; int k = n < 8 ? n : 8; for (int i = 0; i < k; i++) w[i] = ctx->work_host[i]; return k; }
 
 int64_t kb_debug_fetch(kb_ctx_t* ctx, int what, void* dst, uint64_t bytes)
@@ -459,7 +479,7 @@ int64_t kb_debug_fetch(kb_ctx_t* ctx, int what, void* dst, uint64_t bytes)
 	case 6: src = ctx->reports.p; have = (size_t)ctx->counters_host[1] * sizeof(KbReport); break;
 	case 7: src = ctx->res.p; have = n * sizeof(KbReadRes); break;
 	case 8: src = ctx->cigar.p; have = (size_t)ctx->counters_host[2] * 4; break;
-	case 9: src = ctx->counters.p; have = 8 * 4; break;
+	case 9: src = ctx->counters.p; have = 16 * 4; break;
 	default: return KB_EINVAL;
 	}
 	if (have > bytes) have = bytes;

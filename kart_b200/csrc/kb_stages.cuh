@@ -79,7 +79,8 @@ KB_HD void kb_stage_cand_pacbio(const KbIndexDev& ix, const KbParams& pm, const 
 	}
 }
 
-KB_HD void kb_stage_report(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int tid, int nth)
+// phase A of the report stage: segments of every surviving candidate (grid-stride, private arena)
+KB_HD void kb_stage_segments(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int tid, int nth)
 {
 	if (tid >= bt.scratch_threads) return;
 	if (bt.counters[3]) return;
@@ -87,7 +88,36 @@ KB_HD void kb_stage_report(const KbIndexDev& ix, const KbParams& pm, const KbBat
 	for (int r = tid; r < bt.n_reads; r += nth)
 	{
 		ar.used = 0;
-		kb_report_read(ix, pm, bt, r, ar);
+		kb_segments_read(ix, pm, bt, r, ar);
+		if (ar.ovf) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SCRATCH); return; }
+	}
+}
+
+// phase B: one alignment job per trip (grid-stride over the job list, private arena)
+KB_HD void kb_stage_align(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int tid, int nth, unsigned long long* cells, u32* calls)
+{
+	if (tid >= bt.scratch_threads) return;
+	if (bt.counters[3]) return;
+	u32 njobs = bt.counters[9];
+	KbArena ar = kb_thread_arena(bt, tid);
+	for (u32 id = (u32)tid; id < njobs; id += (u32)nth)
+	{
+		ar.used = 0;
+		kb_align_job(ix, pm, bt, id, ar, cells, calls);
+		if (ar.ovf) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SCRATCH); return; }
+	}
+}
+
+// phase C: reports
+KB_HD void kb_stage_assemble(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int tid, int nth)
+{
+	if (tid >= bt.scratch_threads) return;
+	if (bt.counters[3]) return;
+	KbArena ar = kb_thread_arena(bt, tid);
+	for (int r = tid; r < bt.n_reads; r += nth)
+	{
+		ar.used = 0;
+		kb_assemble_read(ix, pm, bt, r, ar);
 		if (ar.ovf) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SCRATCH); return; }
 	}
 }

@@ -63,9 +63,14 @@ struct KbCand { i64 diff; i32 score; i32 mate; u32 seg_start; i32 nseg; };
 struct KbReport { i64 pos; i32 aln; i32 flag; i32 mate; i32 chr; u32 cig_off; i32 cig_len; i32 fwd; i32 pad; };
 struct KbReadRes { i32 score, sub, mapq, ncan, best; u32 rep_off; };
 struct KbPairStat { i32 counted, absdist, est_lo, est_hi; };
+// one segment of a candidate after IdentifyNormalPairs, with how it is resolved (info) and a class-specific value (aux)
+struct KbSegX { KbSeg s; u32 info; u32 aux; };
+enum { KB_SEG_SKIP = 0, KB_SEG_SIMPLE = 1, KB_SEG_QUICK = 2 /* aux = score */, KB_SEG_GAP = 3, KB_SEG_SOFT = 4, KB_SEG_JOB = 5 /* aux = job id */, KB_SEG_ONE = 6 /* 1x1, aux = identical? */ };
+// one fragment pair that needs GenerateNormalPairAlignment (k-mer partition + NW); result = run list in the run arena
+struct KbJob { i64 gpos; u32 read; i32 rpos, rlen, glen; u32 run_off; i32 nruns, ident, aligned; };
 
 // status bits written by kernels (any non-zero value fails the batch loudly; capacities are then grown and the batch rerun)
-enum { KB_OVF_SEEDS = 1, KB_OVF_CANDS = 2, KB_OVF_CIGAR = 4, KB_OVF_SCRATCH = 8, KB_OVF_HITS = 16, KB_OVF_RESCUE = 32, KB_OVF_NW = 64 };
+enum { KB_OVF_SEEDS = 1, KB_OVF_CANDS = 2, KB_OVF_CIGAR = 4, KB_OVF_SCRATCH = 8, KB_OVF_HITS = 16, KB_OVF_RESCUE = 32, KB_OVF_NW = 64, KB_OVF_SEGX = 128, KB_OVF_JOBS = 256, KB_OVF_RUNS = 512 };
 
 // cigar op codes in the arena: len << 4 | op  (BAM numbering)
 enum { KB_OP_M = 0, KB_OP_I = 1, KB_OP_D = 2, KB_OP_S = 4 };
@@ -85,7 +90,10 @@ struct KbBatchDev
 	// stage 2
 	KbCand* cands; u32 cap_cands; i32* n_cands; u32* cand_off; i32* cand_cap;
 	i32* rescue_list;                   // pair ids that need rescue
-	// stage 3/4
+	// stage 3: segments of the surviving candidates, alignment jobs, run arena
+	KbSegX* segx; u32 cap_segx; u32* cseg_off; i32* cseg_n;   // cseg_* indexed like cands (cseg_n < 0: candidate dropped)
+	KbJob* jobs; u32 cap_jobs; u32* runs; u32 cap_runs;
+	// stage 4
 	KbReport* reports;                  // indexed like cands
 	KbReadRes* res;
 	KbPairStat* pstat;
@@ -95,7 +103,7 @@ struct KbBatchDev
 	i32 max_rlen;                       // longest read in the batch
 	i32 nw_max_m, nw_max_n, seg_cap, kmer_cap;
 	// counters: [0] seeds cursor [1] cands cursor [2] cigar cursor [3] status bits [4] rescue count [5] max seeds/read
-	//           [6] nw calls [7] (unused) ; 64-bit: work[0] extension steps, work[1] occ blocks, work[2] LF steps, work[3] NW cells
+	//           [6] nw calls [7] rescue attempts [8] segx cursor [9] job cursor [10] run cursor ; 64-bit: work[0] extension steps, work[1] occ blocks, work[2] LF steps, work[3] NW cells
 	u32* counters;
 	unsigned long long* work;
 };
