@@ -155,24 +155,35 @@ class Mapper:
         r.seq_off = off.ctypes.data
         return r
 
-    def _results(self, n, cap_cigar):
-        aln = np.zeros(n, dtype=ALN_DTYPE)
-        pairs = np.zeros(max(n // 2, 1), dtype=PAIR_DTYPE)
-        cig = np.zeros(max(cap_cigar, 1), dtype=np.uint32)
+    def _results(self, n, cap_cigar, out=None):
+        """Result buffers: freshly allocated, or views of caller-owned (e.g. pinned) buffers `out = (aln, pairs, cigar)`."""
+        if out is not None:
+            aln, pairs, cig = out
+            assert len(aln) >= n and len(pairs) >= n // 2
+            aln, pairs = aln[:n], pairs[:max(n // 2, 1)]
+        else:
+            aln = np.empty(n, dtype=ALN_DTYPE)
+            pairs = np.empty(max(n // 2, 1), dtype=PAIR_DTYPE)
+            cig = np.empty(max(cap_cigar, 1), dtype=np.uint32)
         res = KbResults(aln.ctypes.data, pairs.ctypes.data, cig.ctypes.data, len(cig), 0)
         return aln, pairs, cig, res
 
-    def map_chunk(self, flat, off, est=None):
+    def _est(self, n, est):
+        if not self.params.paired:
+            return None
+        if isinstance(est, np.ndarray) and est.dtype == np.int32 and len(est) == n // 2 and est.flags.c_contiguous:
+            return est
+        return np.ascontiguousarray(np.broadcast_to(np.asarray(1500 if est is None else est, dtype=np.int32), (n // 2,)))
+
+    def map_chunk(self, flat, off, est=None, out=None):
         """Host buffers in, host buffers out (the drop-in call). Returns (aln, pairs, cigar)."""
         n = len(off) - 1
         self.n_reads = n
-        est_arr = None
-        if self.params.paired:
-            est_arr = np.ascontiguousarray(np.broadcast_to(np.asarray(1500 if est is None else est, dtype=np.int32), (n // 2,)))
+        est_arr = self._est(n, est)
         reads = self._reads_struct(flat, off)
-        aln, pairs, cig, res = self._results(n, 16 * n + 1024)
+        aln, pairs, cig, res = self._results(n, 4 * n + 1024, out)
         rc = self.lib.kb_map_chunk(self.h, C.byref(reads), est_arr.ctypes.data if est_arr is not None else None, C.byref(res))
-        if rc == -6:   # KB_ECAPACITY: results are still on the device, fetch again with a big enough cigar buffer
+        if rc == -6 and out is None:   # KB_ECAPACITY: results are still on the device, fetch again with a big enough cigar buffer
             aln, pairs, cig, res = self._results(n, int(res.n_cigar))
             rc = self.lib.kb_fetch_results(self.h, C.byref(res))
         self._check(rc, "kb_map_chunk")
@@ -182,9 +193,7 @@ class Mapper:
         n = len(off) - 1
         self.n_reads = n
         self._keep = (flat, off)
-        est_arr = None
-        if self.params.paired:
-            est_arr = np.ascontiguousarray(np.broadcast_to(np.asarray(1500 if est is None else est, dtype=np.int32), (n // 2,)))
+        est_arr = self._est(n, est)
         reads = self._reads_struct(flat, off)
         self._check(self.lib.kb_stage_reads(self.h, C.byref(reads), est_arr.ctypes.data if est_arr is not None else None), "kb_stage_reads")
 
@@ -193,7 +202,7 @@ class Mapper:
 
     def fetch(self):
         n = self.n_reads
-        aln, pairs, cig, res = self._results(n, 16 * n + 1024)
+        aln, pairs, cig, res = self._results(n, 4 * n + 1024)
         rc = self.lib.kb_fetch_results(self.h, C.byref(res))
         if rc == -6:
             aln, pairs, cig, res = self._results(n, int(res.n_cigar))
