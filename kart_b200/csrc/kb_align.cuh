@@ -272,148 +272,210 @@ KB_HD int kb_kmer_pairs(const u32* w1, int len1, const u32* w2, int len2, int ma
 // ================================================================================================
 // Needleman-Wunsch, integer recurrence with all scores doubled (exactly equivalent to the float DP of
 // nw_alignment.cpp because every value there is a multiple of 0.5), 2-bit traceback.
+//
+// Warp-per-fragment, anti-diagonal wavefront: rows are processed in strips of 32, lane t owns row i0+t+1 and at
+// step d computes column j = d-t+1, so all lanes of a strip advance along one anti-diagonal per step. A lane needs
+//   left  S[i][j-1], R[i][j-1]   its own previous step (registers)
+//   up    S[i-1][j], T[i-1][j]   lane t-1's previous step (exchanged through a double-buffered shared array),
+//                                 or the stored last row of the previous strip for lane 0
+//   diag  S[i-1][j-1]            the `up` value it saw one step earlier (register)
+// The step is written as a function of (warp state, lane state, step, lane) so that the host-emulation build can replay
+// a warp by looping over lanes; on the GPU the 32 calls are the 32 lanes and `__syncwarp()` separates the steps.
 // ================================================================================================
-KB_HD void kb_nw(const u8* c1, int m, const u8* c2, int n, KbArena& ar, KbRuns& acc, unsigned long long* cells)
+#define KB_NW_NEG (-131072)
+struct KbNwWarp
 {
-	*cells += (unsigned long long)m * n;
-	u64 mark = ar.used;
-	int* S = (int*)ar.alloc((u64)(n + 1) * 4);
-	int* T = (int*)ar.alloc((u64)(n + 1) * 4);
-	u8* code2 = (u8*)ar.alloc((u64)n + 1);
-	u64 stride = ((u64)n + 3) >> 2;
-	u8* tb = (u8*)ar.alloc(stride * (u64)m);
+	const u8* c1; const u8* c2; int m, n;
+	int* bS[2]; int* bT[2];     // stored boundary row (row i0) : read buffer = cur, written buffer = cur ^ 1
+	u8* code2;                  // nt4 codes of c2, 1-based
+	u8* tb; u64 stride;         // traceback: 2 bits per cell (bit 0: S==R, bit 1: S==T), 4 cells per byte, row-major
+	int xs[2][32], xt[2][32];   // neighbour exchange, indexed [step & 1][lane]
+	int i0, h, cur;
+	u64 mark;
+};
+struct KbNwLane { int left_s, left_r, diag, a; u32 pack; };
+
+// lane 0: storage for one (m x n) problem out of the warp's arena
+KB_HD bool kb_nww_setup(KbNwWarp& w, KbArena& ar, const u8* c1, int m, const u8* c2, int n)
+{
+	w.c1 = c1; w.c2 = c2; w.m = m; w.n = n; w.mark = ar.used;
+	for (int k = 0; k < 2; k++) { w.bS[k] = (int*)ar.alloc((u64)(n + 1) * 4); w.bT[k] = (int*)ar.alloc((u64)(n + 1) * 4); }
+	w.code2 = (u8*)ar.alloc((u64)n + 1);
+	w.stride = ((u64)n + 3) >> 2;
+	w.tb = (u8*)ar.alloc(w.stride * (u64)m);
+	w.i0 = 0; w.cur = 0; w.h = m < 32 ? m : 32;
+	return !ar.ovf;
+}
+
+// all lanes: row 0 of the DP and the codes of c2
+KB_HD void kb_nww_init_rows(KbNwWarp& w, int t)
+{
+	for (int j = t; j <= w.n; j += 32)
+	{
+		w.bS[0][j] = j == 0 ? 0 : -2 - j; w.bT[0][j] = j == 0 ? 0 : KB_NW_NEG;
+		if (j > 0) w.code2[j] = (u8)kb_nt4(w.c2[j - 1]);
+	}
+}
+
+// all lanes: start of a strip (column 0 of the lane's row)
+KB_HD void kb_nww_strip_begin(KbNwWarp& w, KbNwLane& L, int t)
+{
+	int i = w.i0 + t + 1;
+	L.a = t < w.h ? kb_nt4(w.c1[i - 1]) : 4;
+	L.left_s = -2 - i; L.left_r = KB_NW_NEG; L.diag = i == 1 ? 0 : -2 - (i - 1); L.pack = 0;
+	if (t == 0) { w.bS[w.cur ^ 1][0] = -2 - (w.i0 + w.h); w.bT[w.cur ^ 1][0] = -2 - (w.i0 + w.h); }
+}
+
+// all lanes: one anti-diagonal step
+KB_HD void kb_nww_step(KbNwWarp& w, KbNwLane& L, int d, int t)
+{
+	int j = d - t + 1;
+	if (t >= w.h || j < 1 || j > w.n) return;
+	int us, ut;
+	if (t == 0) { us = w.bS[w.cur][j]; ut = w.bT[w.cur][j]; }
+	else { us = w.xs[(d - 1) & 1][t - 1]; ut = w.xt[(d - 1) & 1][t - 1]; }
+	int r = L.left_r - 1 > L.left_s - 3 ? L.left_r - 1 : L.left_s - 3;
+	int tt = ut - 1 > us - 3 ? ut - 1 : us - 3;
+	int dg = L.diag + (L.a == (int)w.code2[j] ? 3 : -3);
+	int s = dg > r ? dg : r; if (tt > s) s = tt;
+	L.diag = us; L.left_s = s; L.left_r = r;
+	w.xs[d & 1][t] = s; w.xt[d & 1][t] = tt;
+	if (t == w.h - 1) { w.bS[w.cur ^ 1][j] = s; w.bT[w.cur ^ 1][j] = tt; }
+	u32 bits = (s == r ? 1u : 0u) | (s == tt ? 2u : 0u);
+	int q = (j - 1) & 3;
+	L.pack |= bits << (q << 1);
+	if (q == 3 || j == w.n) { w.tb[w.stride * (u64)(w.i0 + t) + (u64)((j - 1) >> 2)] = (u8)L.pack; L.pack = 0; }
+}
+
+// lane 0: next strip; returns false when all rows are done
+KB_HD bool kb_nww_strip_end(KbNwWarp& w)
+{
+	w.i0 += 32; w.cur ^= 1;
+	if (w.i0 >= w.m) return false;
+	w.h = w.m - w.i0 < 32 ? w.m - w.i0 : 32;
+	return true;
+}
+
+// lane 0: traceback (nw_alignment.cpp:59-72): gap-in-read first, then gap-in-genome, else diagonal; appends the runs to acc
+KB_HD void kb_nww_traceback(KbNwWarp& w, KbArena& ar, KbRuns& acc)
+{
+	int m = w.m, n = w.n;
 	u32* rev = (u32*)ar.alloc((u64)(m + n) * 4);
-	if (ar.ovf) { ar.used = mark; return; }
-	const int NEG = -131072;
-	S[0] = 0; T[0] = 0;
-	for (int j = 1; j <= n; j++) { S[j] = -2 - j; T[j] = NEG; code2[j] = (u8)kb_nt4(c2[j - 1]); }
-	for (int i = 1; i <= m; i++)
+	if (rev != nullptr)
 	{
-		int a = kb_nt4(c1[i - 1]);
-		int diag = S[0], left_s = -2 - i, left_r = NEG;   // S[i-1][0] ; S[i][0] ; R[i][0]
-		S[0] = left_s; T[0] = left_s;
-		u8* row = tb + stride * (u64)(i - 1);
-		u8 pack = 0;
-		for (int j = 1; j <= n; j++)
+		int i = m, j = n, nr = 0, ident = 0, aligned = 0, cur = -1, len = 0;
+		while (i > 0 || j > 0)
 		{
-			int r = left_r - 1 > left_s - 3 ? left_r - 1 : left_s - 3;
-			int t = T[j] - 1 > S[j] - 3 ? T[j] - 1 : S[j] - 3;
-			int d = diag + (a == code2[j] ? 3 : -3);
-			int s = d > r ? d : r; if (t > s) s = t;
-			diag = S[j]; S[j] = s; T[j] = t; left_s = s; left_r = r;
-			int bits = (s == r ? 1 : 0) | (s == t ? 2 : 0);
-			int q = (j - 1) & 3;
-			pack |= (u8)(bits << (q << 1));
-			if (q == 3 || j == n) { row[(j - 1) >> 2] = pack; pack = 0; }
+			int type;
+			if (i == 0) type = KB_RUN_D;
+			else if (j == 0) type = KB_RUN_I;
+			else
+			{
+				int bits = (w.tb[w.stride * (u64)(i - 1) + (u64)((j - 1) >> 2)] >> (((j - 1) & 3) << 1)) & 3;
+				type = (bits & 1) ? KB_RUN_D : ((bits & 2) ? KB_RUN_I : KB_RUN_M);
+			}
+			if (type == KB_RUN_D) j--;
+			else if (type == KB_RUN_I) i--;
+			else { i--; j--; aligned++; if (w.c1[i] == w.c2[j]) ident++; }
+			if (type == cur) len++;
+			else { if (len > 0) rev[nr++] = ((u32)len << 2) | (u32)cur; cur = type; len = 1; }
 		}
+		if (len > 0) rev[nr++] = ((u32)len << 2) | (u32)cur;
+		for (int k = nr - 1; k >= 0; k--) acc.push((int)(rev[k] & 3), (int)(rev[k] >> 2));
+		acc.ident += ident; acc.aligned += aligned;
 	}
-	// traceback (:59-72): gap-in-read first, then gap-in-genome, else diagonal
-	int i = m, j = n, nr = 0; int ident = 0, aligned = 0;
-	int cur = -1, len = 0;
-	while (i > 0 || j > 0)
-	{
-		int type;
-		if (i == 0) type = KB_RUN_D;
-		else if (j == 0) type = KB_RUN_I;
-		else
-		{
-			int bits = (tb[stride * (u64)(i - 1) + ((j - 1) >> 2)] >> (((j - 1) & 3) << 1)) & 3;
-			type = (bits & 1) ? KB_RUN_D : ((bits & 2) ? KB_RUN_I : KB_RUN_M);
-		}
-		if (type == KB_RUN_D) j--;
-		else if (type == KB_RUN_I) i--;
-		else { i--; j--; aligned++; if (c1[i] == c2[j]) ident++; }
-		if (type == cur) len++;
-		else { if (len > 0) rev[nr++] = ((u32)len << 2) | (u32)cur; cur = type; len = 1; }
-	}
-	if (len > 0) rev[nr++] = ((u32)len << 2) | (u32)cur;
-	for (int k = nr - 1; k >= 0; k--) acc.push((int)(rev[k] & 3), (int)(rev[k] >> 2));
-	acc.ident += ident; acc.aligned += aligned;
-	ar.used = mark;
+	ar.used = w.mark;
 }
 
 // ================================================================================================
-// GenerateNormalPairAlignment: optional 8-mer partition, then NW on what is left. Appends to acc.
-// f1 = read characters [0,rl), f2 = reference characters [0,gl).
+// GenerateNormalPairAlignment as a resumable iterator: optional 8-mer partition, pure-gap / copy pieces are appended to
+// the run list directly, every piece that needs nw_alignment is handed back to the caller (the warp).
+// The reference recurses (tools.cpp:197, pacbio pieces > 300); here the recursion is an explicit depth-first work stack
+// so that pieces are appended to `acc` in exactly the reference's left-to-right order.
 // ================================================================================================
-struct KbFragCtx { const KbParams* pm; KbArena* ar; unsigned long long* cells; u32* nw_calls; };
-
-// work-stack entry: a sub-fragment (offsets into f1 / f2) and what to do with it
 enum { KB_W_FRAG = 0, KB_W_NW = 1, KB_W_COPY = 2, KB_W_INS = 3, KB_W_DEL = 4 };
 struct KbWork { i32 r0, rl, g0, gl, kind, pad; };
 
-// The reference recurses (tools.cpp:197, pacbio pieces > 300); here the recursion is an explicit depth-first work stack
-// so that pieces are appended to `acc` in exactly the reference's left-to-right order.
-KB_HD void kb_align_fragments(const KbFragCtx& fc, const u8* f1, int rl0, const u8* f2, int gl0, KbRuns& acc)
+struct KbFragIter
 {
-	KbArena& ar = *fc.ar;
-	u64 mark0 = ar.used;
-	int scap = rl0 + gl0 + 4;
-	KbWork* st = (KbWork*)ar.alloc((u64)scap * sizeof(KbWork));
-	if (st == nullptr) return;
-	int sp = 0;
-	{ KbWork w; w.r0 = 0; w.rl = rl0; w.g0 = 0; w.gl = gl0; w.kind = KB_W_FRAG; w.pad = 0; st[sp++] = w; }
-	while (sp > 0 && !ar.ovf)
+	const KbParams* pm; KbArena* ar; const u8* f1; const u8* f2; KbRuns* acc;
+	KbWork* st; int sp, scap; u64 mark0;
+
+	KB_HD bool init(const KbParams* pm_, KbArena* ar_, const u8* f1_, int rl0, const u8* f2_, int gl0, KbRuns* acc_)
 	{
-		const KbWork e = st[--sp];
-		const u8* a = f1 + e.r0; const u8* b = f2 + e.g0;
-		if (e.kind == KB_W_INS) { acc.push(KB_RUN_I, e.rl); continue; }
-		if (e.kind == KB_W_DEL) { acc.push(KB_RUN_D, e.gl); continue; }
-		if (e.kind == KB_W_COPY)
+		pm = pm_; ar = ar_; f1 = f1_; f2 = f2_; acc = acc_; mark0 = ar->used; sp = 0;
+		scap = rl0 + gl0 + 4;
+		st = (KbWork*)ar->alloc((u64)scap * sizeof(KbWork));
+		if (st == nullptr) return false;
+		KbWork w; w.r0 = 0; w.rl = rl0; w.g0 = 0; w.gl = gl0; w.kind = KB_W_FRAG; w.pad = 0; st[sp++] = w;
+		return true;
+	}
+
+	// true: *piece (r0,rl,g0,gl) needs nw_alignment; false: finished (or the arena overflowed: ar->ovf)
+	KB_HD bool next(KbWork* piece)
+	{
+		while (sp > 0 && !ar->ovf)
 		{
-			int id = 0; for (int t = 0; t < e.rl; t++) if (a[t] == b[t]) id++;
-			acc.push(KB_RUN_M, e.rl); acc.ident += id; acc.aligned += e.rl;
-			continue;
-		}
-		if (e.kind == KB_W_FRAG && e.rl > 30 && e.gl > 30)
-		{
-			int rl = e.rl, gl = e.gl, shift;
-			if (fc.pm->pacbio) { shift = rl > gl ? (int)(rl * 0.2) : (int)(gl * 0.2); if (shift > 50) shift = 50; }
-			else shift = fc.pm->max_gaps;
-			u64 mark = ar.used;
-			u32* w1 = (u32*)ar.alloc((u64)rl * 4); u32* w2 = (u32*)ar.alloc((u64)gl * 4);
-			int cap = ((rl < gl ? rl : gl) / 9 + 2) * (2 * shift + 1);   // exact-match runs on one diagonal start >= 9 apart
-			if (cap > rl + gl) cap = rl + gl;
-			KbSeg* raw = (KbSeg*)ar.alloc((u64)cap * sizeof(KbSeg));
-			if (ar.ovf) break;
-			kb_kmer_ids(rl, a, w1); kb_kmer_ids(gl, b, w2);
-			bool povf = false;
-			int np = kb_kmer_pairs(w1, rl, w2, gl, shift, 8, raw, cap, &povf);
-			if (povf) { ar.ovf = true; break; }
-			int tot = 0; KbSeg* part = nullptr;
-			if (np > 0)
+			const KbWork e = st[--sp];
+			const u8* a = f1 + e.r0; const u8* b = f2 + e.g0;
+			if (e.kind == KB_W_INS) { acc->push(KB_RUN_I, e.rl); continue; }
+			if (e.kind == KB_W_DEL) { acc->push(KB_RUN_D, e.gl); continue; }
+			if (e.kind == KB_W_COPY)
 			{
-				kb_sort_segs<true>(raw, np);
-				part = (KbSeg*)ar.alloc((u64)(2 * np + 2) * sizeof(KbSeg));
-				i32* order = (i32*)ar.alloc((u64)np * 4);
-				if (ar.ovf) break;
-				tot = kb_fill_pairs(rl, gl, raw, np, part, order);
-			}
-			if (tot > 0)
-			{
-				if (sp + tot > scap) { ar.ovf = true; break; }
-				for (int i = tot - 1; i >= 0; i--)   // reversed, so that pops come out left to right
-				{
-					const KbSeg p = part[i];
-					if (p.rlen <= 0 && p.glen <= 0) continue;
-					KbWork w; w.r0 = e.r0 + p.rpos; w.rl = p.rlen; w.g0 = e.g0 + (i32)p.gpos; w.gl = p.glen; w.pad = 0;
-					if (p.glen == 0) w.kind = KB_W_INS;
-					else if (p.rlen == 0) w.kind = KB_W_DEL;
-					else if ((p.rlen == 1 && p.glen == 1) || p.simple) w.kind = KB_W_COPY;
-					else if (fc.pm->pacbio && (p.rlen > 300 || p.glen > 300)) w.kind = KB_W_FRAG;
-					else w.kind = KB_W_NW;
-					st[sp++] = w;
-				}
-				ar.used = mark;
+				int id = 0; for (int t = 0; t < e.rl; t++) if (a[t] == b[t]) id++;
+				acc->push(KB_RUN_M, e.rl); acc->ident += id; acc->aligned += e.rl;
 				continue;
 			}
-			ar.used = mark;
+			if (e.kind == KB_W_FRAG && e.rl > 30 && e.gl > 30)
+			{
+				int rl = e.rl, gl = e.gl, shift;
+				if (pm->pacbio) { shift = rl > gl ? (int)(rl * 0.2) : (int)(gl * 0.2); if (shift > 50) shift = 50; }
+				else shift = pm->max_gaps;
+				u64 mark = ar->used;
+				u32* w1 = (u32*)ar->alloc((u64)rl * 4); u32* w2 = (u32*)ar->alloc((u64)gl * 4);
+				int cap = ((rl < gl ? rl : gl) / 9 + 2) * (2 * shift + 1);   // exact-match runs on one diagonal start >= 9 apart
+				if (cap > rl + gl) cap = rl + gl;
+				KbSeg* raw = (KbSeg*)ar->alloc((u64)cap * sizeof(KbSeg));
+				if (ar->ovf) return false;
+				kb_kmer_ids(rl, a, w1); kb_kmer_ids(gl, b, w2);
+				bool povf = false;
+				int np = kb_kmer_pairs(w1, rl, w2, gl, shift, 8, raw, cap, &povf);
+				if (povf) { ar->ovf = true; return false; }
+				int tot = 0; KbSeg* part = nullptr;
+				if (np > 0)
+				{
+					kb_sort_segs<true>(raw, np);
+					part = (KbSeg*)ar->alloc((u64)(2 * np + 2) * sizeof(KbSeg));
+					i32* order = (i32*)ar->alloc((u64)np * 4);
+					if (ar->ovf) return false;
+					tot = kb_fill_pairs(rl, gl, raw, np, part, order);
+				}
+				if (tot > 0)
+				{
+					if (sp + tot > scap) { ar->ovf = true; return false; }
+					for (int i = tot - 1; i >= 0; i--)   // reversed, so that pops come out left to right
+					{
+						const KbSeg p = part[i];
+						if (p.rlen <= 0 && p.glen <= 0) continue;
+						KbWork w; w.r0 = e.r0 + p.rpos; w.rl = p.rlen; w.g0 = e.g0 + (i32)p.gpos; w.gl = p.glen; w.pad = 0;
+						if (p.glen == 0) w.kind = KB_W_INS;
+						else if (p.rlen == 0) w.kind = KB_W_DEL;
+						else if ((p.rlen == 1 && p.glen == 1) || p.simple) w.kind = KB_W_COPY;
+						else if (pm->pacbio && (p.rlen > 300 || p.glen > 300)) w.kind = KB_W_FRAG;
+						else w.kind = KB_W_NW;
+						st[sp++] = w;
+					}
+					ar->used = mark;
+					continue;
+				}
+				ar->used = mark;
+			}
+			*piece = e;
+			return true;
 		}
-		(*fc.nw_calls)++;
-		kb_nw(a, e.rl, b, e.gl, ar, acc, fc.cells);
+		return false;
 	}
-	ar.used = mark0;
-}
+};
 
 // ================================================================================================
 // Fragment-pair processing, split in three phases so that the expensive, divergent part (partition + NW) runs in its own
@@ -514,21 +576,49 @@ KB_HD void kb_segments_read(const KbIndexDev& ix, const KbParams& pm, const KbBa
 	}
 }
 
-// phase B: one job (thread-sequential version)
-KB_HD void kb_align_job(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, u32 id, KbArena& ar, unsigned long long* cells, u32* nw_calls)
+// phase B, warp per job. State shared by the lanes of the warp (shared memory on the GPU):
+struct KbAlignWarp
 {
-	KbJob& jb = bt.jobs[id];
-	u64 mark = ar.used;
-	u8* f2 = (u8*)ar.alloc((u64)jb.glen);
-	if (f2 == nullptr) return;
-	for (int i = 0; i < jb.glen; i++) f2[i] = kb_ref_char(ix, jb.gpos + i);
-	const u8* f1 = bt.seq + bt.seq_off[jb.read] + jb.rpos;
-	KbRuns acc; acc.r = bt.runs + jb.run_off; acc.cap = jb.rlen + jb.glen + 2; acc.n = 0; acc.ident = 0; acc.aligned = 0; acc.ovf = false;
-	KbFragCtx fc; fc.pm = &pm; fc.ar = &ar; fc.cells = cells; fc.nw_calls = nw_calls;
-	kb_align_fragments(fc, f1, jb.rlen, f2, jb.glen, acc);
-	if (acc.ovf) ar.ovf = true;
-	jb.nruns = acc.n; jb.ident = acc.ident; jb.aligned = acc.aligned;
-	ar.used = mark;
+	KbNwWarp nw; KbFragIter it; KbRuns acc; KbArena ar;
+	KbWork piece; u8* f2; const u8* f1; u32 job; int ok, has_piece, more_strips, glen;
+	unsigned long long cells; u32 calls;
+};
+
+// lane 0: open job `id`
+KB_HD void kb_aw_begin(const KbParams& pm, const KbBatchDev& bt, KbAlignWarp& w, u32 id)
+{
+	const KbJob& jb = bt.jobs[id];
+	w.job = id; w.ar.used = 0; w.ar.ovf = false; w.glen = jb.glen;
+	w.f2 = (u8*)w.ar.alloc((u64)jb.glen);
+	w.f1 = bt.seq + bt.seq_off[jb.read] + jb.rpos;
+	w.acc.r = bt.runs + jb.run_off; w.acc.cap = jb.rlen + jb.glen + 2; w.acc.n = 0; w.acc.ident = 0; w.acc.aligned = 0; w.acc.ovf = false;
+	w.ok = (w.f2 != nullptr && w.it.init(&pm, &w.ar, w.f1, jb.rlen, w.f2, jb.glen, &w.acc)) ? 1 : 0;
+}
+// all lanes: reference characters of the fragment
+KB_HD void kb_aw_fetch(const KbIndexDev& ix, const KbBatchDev& bt, KbAlignWarp& w, int t)
+{
+	if (!w.ok) return;
+	i64 g = bt.jobs[w.job].gpos;
+	for (int i = t; i < w.glen; i += 32) w.f2[i] = kb_ref_char(ix, g + i);
+}
+// lane 0: advance to the next piece that needs NW and set the DP up
+KB_HD void kb_aw_next(KbAlignWarp& w)
+{
+	w.has_piece = 0;
+	if (!w.ok) return;
+	if (w.it.next(&w.piece))
+	{
+		w.calls++; w.cells += (unsigned long long)w.piece.rl * (unsigned long long)w.piece.gl;
+		if (kb_nww_setup(w.nw, w.ar, w.f1 + w.piece.r0, w.piece.rl, w.f2 + w.piece.g0, w.piece.gl)) { w.has_piece = 1; w.more_strips = 1; }
+	}
+}
+// lane 0: close the job
+KB_HD void kb_aw_end(const KbBatchDev& bt, KbAlignWarp& w)
+{
+	KbJob& jb = bt.jobs[w.job];
+	if (w.acc.ovf) w.ar.ovf = true;
+	jb.nruns = w.acc.n; jb.ident = w.acc.ident; jb.aligned = w.acc.aligned;
+	if (w.ar.ovf || !w.ok) KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SCRATCH);
 }
 
 // AddNewCigarElements: run list -> cigar elements (D/I/M)

@@ -130,12 +130,83 @@ static void k_rescue(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulation: 
 }
 #endif
 __global__ void __launch_bounds__(KB_BLOCK) k_segments(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_segments(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
+// phase B: one warp per alignment job (kb_align.cuh "warp-per-fragment")
+#ifndef KB_EMUL
 __global__ void __launch_bounds__(KB_BLOCK) k_align(KbIndexDev ix, KbParams pm, KbBatchDev bt)
 {
-	unsigned long long cells = 0; u32 calls = 0;
-	kb_stage_align(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, &cells, &calls);
-	kb_warp_add64(&bt.work[3], cells); kb_warp_add64(&bt.work[4], calls);
+	__shared__ KbAlignWarp sw[KB_BLOCK / 32];
+	if (bt.counters[3]) return;
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const u32 gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+	if ((int)(gwarp * 32) >= bt.scratch_threads) return;
+	KbAlignWarp& w = sw[wib];
+	const u32 njobs = bt.counters[9];
+	if (lane == 0) { w.ar.base = bt.scratch + (u64)gwarp * 32ull * bt.scratch_per_thread; w.ar.cap = 32ull * bt.scratch_per_thread; w.cells = 0; w.calls = 0; }
+	__syncwarp();
+	for (u32 id = gwarp; id < njobs; id += nwarps)
+	{
+		if (lane == 0) kb_aw_begin(pm, bt, w, id);
+		__syncwarp();
+		kb_aw_fetch(ix, bt, w, lane);
+		__syncwarp();
+		while (true)
+		{
+			if (lane == 0) kb_aw_next(w);
+			__syncwarp();
+			if (!w.has_piece) break;
+			kb_nww_init_rows(w.nw, lane);
+			__syncwarp();
+			while (true)
+			{
+				KbNwLane L;
+				kb_nww_strip_begin(w.nw, L, lane);
+				__syncwarp();
+				const int steps = w.nw.n + w.nw.h - 1;
+				for (int d = 0; d < steps; d++) { kb_nww_step(w.nw, L, d, lane); __syncwarp(); }
+				if (lane == 0) w.more_strips = kb_nww_strip_end(w.nw) ? 1 : 0;
+				__syncwarp();
+				if (!w.more_strips) break;
+			}
+			if (lane == 0) kb_nww_traceback(w.nw, w.ar, w.acc);
+			__syncwarp();
+		}
+		if (lane == 0) kb_aw_end(bt, w);
+		__syncwarp();
+	}
+	if (lane == 0) { if (w.cells) atomicAdd(&bt.work[3], w.cells); if (w.calls) atomicAdd(&bt.work[4], (unsigned long long)w.calls); }
 }
+#else
+static void k_align(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulation: the same phases, a warp = a loop over 32 lanes
+{
+	if (blockIdx.x != 0 || threadIdx.x != 0) return;
+	if (bt.counters[3]) return;
+	static KbAlignWarp w; KbNwLane L[32];
+	w.ar.base = bt.scratch; w.ar.cap = 32ull * bt.scratch_per_thread; w.cells = 0; w.calls = 0;
+	const u32 njobs = bt.counters[9];
+	for (u32 id = 0; id < njobs; id++)
+	{
+		kb_aw_begin(pm, bt, w, id);
+		for (int t = 31; t >= 0; t--) kb_aw_fetch(ix, bt, w, t);
+		while (true)
+		{
+			kb_aw_next(w);
+			if (!w.has_piece) break;
+			for (int t = 0; t < 32; t++) kb_nww_init_rows(w.nw, t);
+			while (true)
+			{
+				for (int t = 0; t < 32; t++) kb_nww_strip_begin(w.nw, L[t], t);
+				const int steps = w.nw.n + w.nw.h - 1;
+				for (int d = 0; d < steps; d++) for (int t = 31; t >= 0; t--) kb_nww_step(w.nw, L[t], d, t);   // lane order must not matter
+				w.more_strips = kb_nww_strip_end(w.nw) ? 1 : 0;
+				if (!w.more_strips) break;
+			}
+			kb_nww_traceback(w.nw, w.ar, w.acc);
+		}
+		kb_aw_end(bt, w);
+	}
+	bt.work[3] += w.cells; bt.work[4] += w.calls;
+}
+#endif
 __global__ void __launch_bounds__(KB_BLOCK) k_assemble(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_assemble(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
 __global__ void __launch_bounds__(KB_BLOCK) k_finalize(KbIndexDev ix, KbParams pm, KbBatchDev bt, kb_aln_t* aln) { kb_stage_finalize(ix, pm, bt, aln, blockIdx.x * blockDim.x + threadIdx.x); }
 

@@ -93,21 +93,6 @@ KB_HD void kb_stage_segments(const KbIndexDev& ix, const KbParams& pm, const KbB
 	}
 }
 
-// phase B: one alignment job per trip (grid-stride over the job list, private arena)
-KB_HD void kb_stage_align(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int tid, int nth, unsigned long long* cells, u32* calls)
-{
-	if (tid >= bt.scratch_threads) return;
-	if (bt.counters[3]) return;
-	u32 njobs = bt.counters[9];
-	KbArena ar = kb_thread_arena(bt, tid);
-	for (u32 id = (u32)tid; id < njobs; id += (u32)nth)
-	{
-		ar.used = 0;
-		kb_align_job(ix, pm, bt, id, ar, cells, calls);
-		if (ar.ovf) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SCRATCH); return; }
-	}
-}
-
 // phase C: reports
 KB_HD void kb_stage_assemble(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int tid, int nth)
 {
