@@ -38,12 +38,20 @@ enum { KB_RUN_D = 0, KB_RUN_I = 1, KB_RUN_M = 2 };   // gap in read / gap in gen
 struct KbRuns
 {
 	u32* r; int n, cap; int ident, aligned; bool ovf;
+	u32 tail;            // the open run (not yet stored); 0 = none. Keeps the read-modify-write of the last run out of memory.
+	KB_HD void reset(u32* dst, int capacity) { r = dst; cap = capacity; n = 0; ident = 0; aligned = 0; ovf = false; tail = 0; }
 	KB_HD void push(int type, int len)
 	{
 		if (len <= 0) return;
-		if (n > 0 && (int)(r[n - 1] & 3) == type) { r[n - 1] += (u32)len << 2; return; }
-		if (n >= cap) { ovf = true; return; }
-		r[n++] = ((u32)len << 2) | (u32)type;
+		if (tail != 0 && (int)(tail & 3) == type) { tail += (u32)len << 2; return; }
+		flush();
+		tail = ((u32)len << 2) | (u32)type;
+	}
+	KB_HD void flush()
+	{
+		if (tail == 0) return;
+		if (n >= cap) ovf = true; else r[n++] = tail;
+		tail = 0;
 	}
 };
 
@@ -286,65 +294,80 @@ KB_HD int kb_kmer_pairs(const u32* w1, int len1, const u32* w2, int len2, int ma
 struct KbNwWarp
 {
 	const u8* c1; const u8* c2; int m, n;
-	int* bS[2]; int* bT[2];     // stored boundary row (row i0) : read buffer = cur, written buffer = cur ^ 1
+	int* bS[2]; int* bT[2];     // stored boundary row (row i0), only when m > 32: read buffer = cur, written buffer = cur ^ 1
 	u8* code2;                  // nt4 codes of c2, 1-based
-	u8* tb; u64 stride;         // traceback: 2 bits per cell (bit 0: S==R, bit 1: S==T), 4 cells per byte, row-major
+	u8* tb; u32 stride;         // traceback: 2 bits per cell (bit 0: S==R, bit 1: S==T), 4 cells per byte, row-major
+	u32* rev;                   // traceback scratch (m + n runs)
 	int xs[2][32], xt[2][32];   // neighbour exchange, indexed [step & 1][lane]
 	int i0, h, cur;
-	u64 mark;
+	u64 mark, fmark;
 };
-struct KbNwLane { int left_s, left_r, diag, a; u32 pack; };
+// per-lane registers: DP state of the lane's row plus the strip constants it needs every step
+struct KbNwLane { int left_s, left_r, diag, a, n, h, last; u32 pack; const u8* code2; u8* tbrow; const int* rS; const int* rT; int* wS; int* wT; };
 
-// lane 0: storage for one (m x n) problem out of the warp's arena
-KB_HD bool kb_nww_setup(KbNwWarp& w, KbArena& ar, const u8* c1, int m, const u8* c2, int n)
+// two-level allocation: the warp's shared-memory pool first, the (L2-latency) HBM arena when the problem is too large
+KB_HD void* kb_alloc2(KbArena& fast, KbArena& slow, u64 bytes)
 {
-	w.c1 = c1; w.c2 = c2; w.m = m; w.n = n; w.mark = ar.used;
-	for (int k = 0; k < 2; k++) { w.bS[k] = (int*)ar.alloc((u64)(n + 1) * 4); w.bT[k] = (int*)ar.alloc((u64)(n + 1) * 4); }
-	w.code2 = (u8*)ar.alloc((u64)n + 1);
-	w.stride = ((u64)n + 3) >> 2;
-	w.tb = (u8*)ar.alloc(w.stride * (u64)m);
+	u64 need = (bytes + 15) & ~(u64)15;
+	if (fast.used + need <= fast.cap) { void* p = fast.base + fast.used; fast.used += need; return p; }
+	return slow.alloc(bytes);
+}
+
+// lane 0: storage for one (m x n) problem
+KB_HD bool kb_nww_setup(KbNwWarp& w, KbArena& fast, KbArena& ar, const u8* c1, int m, const u8* c2, int n)
+{
+	w.c1 = c1; w.c2 = c2; w.m = m; w.n = n; w.mark = ar.used; w.fmark = fast.used;
+	w.code2 = (u8*)kb_alloc2(fast, ar, (u64)n + 1);
+	w.stride = ((u32)n + 3) >> 2;
+	w.tb = (u8*)kb_alloc2(fast, ar, (u64)w.stride * (u64)m);
+	w.rev = (u32*)kb_alloc2(fast, ar, (u64)(m + n) * 4);
+	for (int k = 0; k < 2; k++)
+	{
+		w.bS[k] = m > 32 ? (int*)kb_alloc2(fast, ar, (u64)(n + 1) * 4) : nullptr;
+		w.bT[k] = m > 32 ? (int*)kb_alloc2(fast, ar, (u64)(n + 1) * 4) : nullptr;
+	}
 	w.i0 = 0; w.cur = 0; w.h = m < 32 ? m : 32;
 	return !ar.ovf;
 }
 
-// all lanes: row 0 of the DP and the codes of c2
+// all lanes: the codes of c2 (row 0 of the DP is analytic: S[0][j] = -2-j, T[0][j] = -inf)
 KB_HD void kb_nww_init_rows(KbNwWarp& w, int t)
 {
-	for (int j = t; j <= w.n; j += 32)
-	{
-		w.bS[0][j] = j == 0 ? 0 : -2 - j; w.bT[0][j] = j == 0 ? 0 : KB_NW_NEG;
-		if (j > 0) w.code2[j] = (u8)kb_nt4(w.c2[j - 1]);
-	}
+	for (int j = t + 1; j <= w.n; j += 32) w.code2[j] = (u8)kb_nt4(w.c2[j - 1]);
 }
 
-// all lanes: start of a strip (column 0 of the lane's row)
+// all lanes: start of a strip (column 0 of the lane's row); caches the strip constants in the lane
 KB_HD void kb_nww_strip_begin(KbNwWarp& w, KbNwLane& L, int t)
 {
 	int i = w.i0 + t + 1;
+	L.n = w.n; L.h = w.h; L.last = (t == w.h - 1 && w.i0 + w.h < w.m) ? 1 : 0;
 	L.a = t < w.h ? kb_nt4(w.c1[i - 1]) : 4;
 	L.left_s = -2 - i; L.left_r = KB_NW_NEG; L.diag = i == 1 ? 0 : -2 - (i - 1); L.pack = 0;
-	if (t == 0) { w.bS[w.cur ^ 1][0] = -2 - (w.i0 + w.h); w.bT[w.cur ^ 1][0] = -2 - (w.i0 + w.h); }
+	L.code2 = w.code2; L.tbrow = w.tb + (u64)w.stride * (u64)(w.i0 + t);
+	L.rS = w.i0 > 0 ? w.bS[w.cur] : nullptr; L.rT = w.i0 > 0 ? w.bT[w.cur] : nullptr;
+	L.wS = w.bS[w.cur ^ 1]; L.wT = w.bT[w.cur ^ 1];
+	if (t == 0 && L.wS != nullptr) { L.wS[0] = -2 - (w.i0 + w.h); L.wT[0] = -2 - (w.i0 + w.h); }
 }
 
 // all lanes: one anti-diagonal step
 KB_HD void kb_nww_step(KbNwWarp& w, KbNwLane& L, int d, int t)
 {
 	int j = d - t + 1;
-	if (t >= w.h || j < 1 || j > w.n) return;
+	if (t >= L.h || j < 1 || j > L.n) return;
 	int us, ut;
-	if (t == 0) { us = w.bS[w.cur][j]; ut = w.bT[w.cur][j]; }
+	if (t == 0) { if (L.rS != nullptr) { us = L.rS[j]; ut = L.rT[j]; } else { us = -2 - j; ut = KB_NW_NEG; } }
 	else { us = w.xs[(d - 1) & 1][t - 1]; ut = w.xt[(d - 1) & 1][t - 1]; }
 	int r = L.left_r - 1 > L.left_s - 3 ? L.left_r - 1 : L.left_s - 3;
 	int tt = ut - 1 > us - 3 ? ut - 1 : us - 3;
-	int dg = L.diag + (L.a == (int)w.code2[j] ? 3 : -3);
+	int dg = L.diag + (L.a == (int)L.code2[j] ? 3 : -3);
 	int s = dg > r ? dg : r; if (tt > s) s = tt;
 	L.diag = us; L.left_s = s; L.left_r = r;
 	w.xs[d & 1][t] = s; w.xt[d & 1][t] = tt;
-	if (t == w.h - 1) { w.bS[w.cur ^ 1][j] = s; w.bT[w.cur ^ 1][j] = tt; }
+	if (L.last) { L.wS[j] = s; L.wT[j] = tt; }
 	u32 bits = (s == r ? 1u : 0u) | (s == tt ? 2u : 0u);
 	int q = (j - 1) & 3;
 	L.pack |= bits << (q << 1);
-	if (q == 3 || j == w.n) { w.tb[w.stride * (u64)(w.i0 + t) + (u64)((j - 1) >> 2)] = (u8)L.pack; L.pack = 0; }
+	if (q == 3 || j == L.n) { L.tbrow[(j - 1) >> 2] = (u8)L.pack; L.pack = 0; }
 }
 
 // lane 0: next strip; returns false when all rows are done
@@ -357,10 +380,10 @@ KB_HD bool kb_nww_strip_end(KbNwWarp& w)
 }
 
 // lane 0: traceback (nw_alignment.cpp:59-72): gap-in-read first, then gap-in-genome, else diagonal; appends the runs to acc
-KB_HD void kb_nww_traceback(KbNwWarp& w, KbArena& ar, KbRuns& acc)
+KB_HD void kb_nww_traceback(KbNwWarp& w, KbArena& fast, KbArena& ar, KbRuns& acc)
 {
 	int m = w.m, n = w.n;
-	u32* rev = (u32*)ar.alloc((u64)(m + n) * 4);
+	u32* rev = w.rev;
 	if (rev != nullptr)
 	{
 		int i = m, j = n, nr = 0, ident = 0, aligned = 0, cur = -1, len = 0;
@@ -371,7 +394,7 @@ KB_HD void kb_nww_traceback(KbNwWarp& w, KbArena& ar, KbRuns& acc)
 			else if (j == 0) type = KB_RUN_I;
 			else
 			{
-				int bits = (w.tb[w.stride * (u64)(i - 1) + (u64)((j - 1) >> 2)] >> (((j - 1) & 3) << 1)) & 3;
+				int bits = (w.tb[(u64)w.stride * (u64)(i - 1) + (u64)((j - 1) >> 2)] >> (((j - 1) & 3) << 1)) & 3;
 				type = (bits & 1) ? KB_RUN_D : ((bits & 2) ? KB_RUN_I : KB_RUN_M);
 			}
 			if (type == KB_RUN_D) j--;
@@ -384,7 +407,7 @@ KB_HD void kb_nww_traceback(KbNwWarp& w, KbArena& ar, KbRuns& acc)
 		for (int k = nr - 1; k >= 0; k--) acc.push((int)(rev[k] & 3), (int)(rev[k] >> 2));
 		acc.ident += ident; acc.aligned += aligned;
 	}
-	ar.used = w.mark;
+	ar.used = w.mark; fast.used = w.fmark;
 }
 
 // ================================================================================================
@@ -579,8 +602,8 @@ KB_HD void kb_segments_read(const KbIndexDev& ix, const KbParams& pm, const KbBa
 // phase B, warp per job. State shared by the lanes of the warp (shared memory on the GPU):
 struct KbAlignWarp
 {
-	KbNwWarp nw; KbFragIter it; KbRuns acc; KbArena ar;
-	KbWork piece; u8* f2; const u8* f1; u32 job; int ok, has_piece, more_strips, glen;
+	KbNwWarp nw; KbFragIter it; KbRuns acc; KbArena ar, fast;
+	KbWork piece; u8* f2; u8* f1; const u8* f1g; u32 job; int ok, has_piece, more_strips, rlen, glen, whole, whole_done;
 	unsigned long long cells; u32 calls;
 };
 
@@ -588,34 +611,43 @@ struct KbAlignWarp
 KB_HD void kb_aw_begin(const KbParams& pm, const KbBatchDev& bt, KbAlignWarp& w, u32 id)
 {
 	const KbJob& jb = bt.jobs[id];
-	w.job = id; w.ar.used = 0; w.ar.ovf = false; w.glen = jb.glen;
-	w.f2 = (u8*)w.ar.alloc((u64)jb.glen);
-	w.f1 = bt.seq + bt.seq_off[jb.read] + jb.rpos;
-	w.acc.r = bt.runs + jb.run_off; w.acc.cap = jb.rlen + jb.glen + 2; w.acc.n = 0; w.acc.ident = 0; w.acc.aligned = 0; w.acc.ovf = false;
-	w.ok = (w.f2 != nullptr && w.it.init(&pm, &w.ar, w.f1, jb.rlen, w.f2, jb.glen, &w.acc)) ? 1 : 0;
+	w.job = id; w.ar.used = 0; w.ar.ovf = false; w.fast.used = 0; w.rlen = jb.rlen; w.glen = jb.glen;
+	w.f1 = (u8*)kb_alloc2(w.fast, w.ar, (u64)jb.rlen);
+	w.f2 = (u8*)kb_alloc2(w.fast, w.ar, (u64)jb.glen);
+	w.f1g = bt.seq + bt.seq_off[jb.read] + jb.rpos;
+	w.acc.reset(bt.runs + jb.run_off, jb.rlen + jb.glen + 2);
+	w.ok = (w.f1 != nullptr && w.f2 != nullptr) ? 1 : 0;
+	// fragments that cannot be partitioned (tools.cpp:146) are one NW problem: no work stack needed
+	w.whole = !(jb.rlen > 30 && jb.glen > 30); w.whole_done = 0;
+	if (w.ok && !w.whole) w.ok = w.it.init(&pm, &w.ar, w.f1, jb.rlen, w.f2, jb.glen, &w.acc) ? 1 : 0;
 }
-// all lanes: reference characters of the fragment
+// all lanes: read and reference characters of the fragment into the warp's pool
 KB_HD void kb_aw_fetch(const KbIndexDev& ix, const KbBatchDev& bt, KbAlignWarp& w, int t)
 {
 	if (!w.ok) return;
 	i64 g = bt.jobs[w.job].gpos;
 	for (int i = t; i < w.glen; i += 32) w.f2[i] = kb_ref_char(ix, g + i);
+	for (int i = t; i < w.rlen; i += 32) w.f1[i] = w.f1g[i];
 }
 // lane 0: advance to the next piece that needs NW and set the DP up
 KB_HD void kb_aw_next(KbAlignWarp& w)
 {
 	w.has_piece = 0;
 	if (!w.ok) return;
-	if (w.it.next(&w.piece))
+	bool got;
+	if (w.whole) { got = !w.whole_done; w.whole_done = 1; w.piece.r0 = 0; w.piece.rl = w.rlen; w.piece.g0 = 0; w.piece.gl = w.glen; }
+	else got = w.it.next(&w.piece);
+	if (got)
 	{
 		w.calls++; w.cells += (unsigned long long)w.piece.rl * (unsigned long long)w.piece.gl;
-		if (kb_nww_setup(w.nw, w.ar, w.f1 + w.piece.r0, w.piece.rl, w.f2 + w.piece.g0, w.piece.gl)) { w.has_piece = 1; w.more_strips = 1; }
+		if (kb_nww_setup(w.nw, w.fast, w.ar, w.f1 + w.piece.r0, w.piece.rl, w.f2 + w.piece.g0, w.piece.gl)) { w.has_piece = 1; w.more_strips = 1; }
 	}
 }
 // lane 0: close the job
 KB_HD void kb_aw_end(const KbBatchDev& bt, KbAlignWarp& w)
 {
 	KbJob& jb = bt.jobs[w.job];
+	w.acc.flush();
 	if (w.acc.ovf) w.ar.ovf = true;
 	jb.nruns = w.acc.n; jb.ident = w.acc.ident; jb.aligned = w.acc.aligned;
 	if (w.ar.ovf || !w.ok) KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SCRATCH);

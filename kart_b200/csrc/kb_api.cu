@@ -19,6 +19,7 @@
 #include "kb_stages.cuh"
 
 #define KB_BLOCK 128
+#define KB_ALIGN_POOL 6144   // shared-memory bytes per warp of k_align (fragment chars, codes, 2-bit traceback)
 
 // ------------------------------------------------------------------------------------------------
 // kernels
@@ -135,13 +136,14 @@ __global__ void __launch_bounds__(KB_BLOCK) k_segments(KbIndexDev ix, KbParams p
 __global__ void __launch_bounds__(KB_BLOCK) k_align(KbIndexDev ix, KbParams pm, KbBatchDev bt)
 {
 	__shared__ KbAlignWarp sw[KB_BLOCK / 32];
+	__shared__ __align__(16) u8 pool[KB_BLOCK / 32][KB_ALIGN_POOL];
 	if (bt.counters[3]) return;
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	const u32 gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
 	if ((int)(gwarp * 32) >= bt.scratch_threads) return;
 	KbAlignWarp& w = sw[wib];
 	const u32 njobs = bt.counters[9];
-	if (lane == 0) { w.ar.base = bt.scratch + (u64)gwarp * 32ull * bt.scratch_per_thread; w.ar.cap = 32ull * bt.scratch_per_thread; w.cells = 0; w.calls = 0; }
+	if (lane == 0) { w.ar.base = bt.scratch + (u64)gwarp * 32ull * bt.scratch_per_thread; w.ar.cap = 32ull * bt.scratch_per_thread; w.fast.base = pool[wib]; w.fast.cap = KB_ALIGN_POOL; w.fast.ovf = false; w.cells = 0; w.calls = 0; }
 	__syncwarp();
 	for (u32 id = gwarp; id < njobs; id += nwarps)
 	{
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(KB_BLOCK) k_align(KbIndexDev ix, KbParams pm, 
 				__syncwarp();
 				if (!w.more_strips) break;
 			}
-			if (lane == 0) kb_nww_traceback(w.nw, w.ar, w.acc);
+			if (lane == 0) kb_nww_traceback(w.nw, w.fast, w.ar, w.acc);
 			__syncwarp();
 		}
 		if (lane == 0) kb_aw_end(bt, w);
@@ -180,8 +182,8 @@ static void k_align(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulation: t
 {
 	if (blockIdx.x != 0 || threadIdx.x != 0) return;
 	if (bt.counters[3]) return;
-	static KbAlignWarp w; KbNwLane L[32];
-	w.ar.base = bt.scratch; w.ar.cap = 32ull * bt.scratch_per_thread; w.cells = 0; w.calls = 0;
+	static KbAlignWarp w; KbNwLane L[32]; static u8 pool[KB_ALIGN_POOL];
+	w.ar.base = bt.scratch; w.ar.cap = 32ull * bt.scratch_per_thread; w.fast.base = pool; w.fast.cap = KB_ALIGN_POOL; w.fast.ovf = false; w.cells = 0; w.calls = 0;
 	const u32 njobs = bt.counters[9];
 	for (u32 id = 0; id < njobs; id++)
 	{
@@ -200,7 +202,7 @@ static void k_align(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulation: t
 				w.more_strips = kb_nww_strip_end(w.nw) ? 1 : 0;
 				if (!w.more_strips) break;
 			}
-			kb_nww_traceback(w.nw, w.ar, w.acc);
+			kb_nww_traceback(w.nw, w.fast, w.ar, w.acc);
 		}
 		kb_aw_end(bt, w);
 	}
