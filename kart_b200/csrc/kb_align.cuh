@@ -32,6 +32,36 @@ KB_HD int kb_ref_code(const KbIndexDev& ix, i64 p)   // 0..3, or 4 outside [0,2G
 	return rev ? 3 - c : c;
 }
 KB_HD u8 kb_code_char(int c) { return c == 0 ? 'A' : (c == 1 ? 'C' : (c == 2 ? 'G' : (c == 3 ? 'T' : 'N'))); }
+// 32 characters of the 2G text starting at p as 2-bit codes, MSB first; *inval flags (bit 31-i) the positions outside [0,2G)
+KB_HD u64 kb_ref_win(const KbIndexDev& ix, i64 p, u32* inval)
+{
+	const u64 M5 = 0x5555555555555555ull;
+	*inval = 0;
+	if (p >= 0 && p + 32 <= ix.G)
+	{
+		const u64* w = ix.ref64 + (p >> 5); const int s = (int)(p & 31) * 2;
+		u64 hi = KB_LDG(w); if (s == 0) return hi;
+		return (hi << s) | (KB_LDG(w + 1) >> (64 - s));
+	}
+	if (p >= ix.G && p + 32 <= ix.G2)
+	{
+		const i64 f = ix.G2 - 32 - p;   // forward bases f..f+31 are the window read backwards
+		const u64* w = ix.ref64 + (f >> 5); const int s = (int)(f & 31) * 2;
+		u64 v = KB_LDG(w); if (s) v = (v << s) | (KB_LDG(w + 1) >> (64 - s));
+#if defined(__CUDA_ARCH__)
+		v = __brevll(v);
+#else
+		{ u64 x = v; x = ((x >> 1) & M5) | ((x & M5) << 1); x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+		  x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4); v = __builtin_bswap64(x); }
+#endif
+		v = ((v >> 1) & M5) | ((v & M5) << 1);   // bit reversal swapped the two bits of every base
+		return ~v;
+	}
+	u64 v = 0; u32 bad = 0;
+	for (int i = 0; i < 32; i++) { int c = kb_ref_code(ix, p + i); if (c > 3) bad |= 1u << (31 - i); else v |= (u64)c << (62 - 2 * i); }
+	*inval = bad;
+	return v;
+}
 
 // ---- run-list accumulator ----------------------------------------------------------------------
 enum { KB_RUN_D = 0, KB_RUN_I = 1, KB_RUN_M = 2 };   // gap in read / gap in genome / aligned column  (CheckLocalAlignmentQuality types 0,1,2)
@@ -528,15 +558,37 @@ KB_HD int kb_mismatch_ref(const KbIndexDev& ix, const u8* f1, i64 gpos, int n, i
 	return c;
 }
 
+// the same count, 32 characters per step on the packed read and the 64-bit reference words; a chunk that holds a character
+// other than upper-case ACGT on either side is compared character by character (raw char equality, tools.cpp:44)
+KB_HD int kb_mismatch_packed(const KbIndexDev& ix, const KbPk* rd, const u8* f1, int rpos, i64 gpos, int n, int limit)
+{
+	const u64 M5 = 0x5555555555555555ull;
+	int c = 0;
+	for (int o = 0; o < n && c <= limit; o += 32)
+	{
+		const int m = n - o < 32 ? n - o : 32;
+		KbPk rw = kb_read_win(rd, rpos + o); u32 ginv; u64 gw = kb_ref_win(ix, gpos + o, &ginv);
+		const u32 lm = ~((~0u >> (m - 1)) >> 1);   // first m of 32
+		if (((rw.bad | ginv) & lm) == 0)
+		{
+			u64 x = rw.code ^ gw; x = (x | (x >> 1)) & M5;
+			x &= ~(((~0ull >> (m - 1)) >> (m - 1)) >> 2);   // first m of 32 two-bit fields
+			c += (int)KB_POPCLL(x);
+		}
+		else for (int i = 0; i < m; i++) if (f1[o + i] != kb_ref_char(ix, gpos + o + i)) c++;
+	}
+	return c;
+}
+
 // quick test of tools.cpp:240/301/352: equal length, <= 2 mismatches and <= 20 %
-KB_HD bool kb_quick_match_ref(const KbIndexDev& ix, const u8* f1, const KbSeg& sp, int* n)
+KB_HD bool kb_quick_match_ref(const KbIndexDev& ix, const KbPk* rd, const u8* f1, const KbSeg& sp, int* n)
 {
 	if (sp.rlen != sp.glen) return false;
-	*n = kb_mismatch_ref(ix, f1, sp.gpos, sp.rlen, 2);
+	*n = kb_mismatch_packed(ix, rd, f1, sp.rpos, sp.gpos, sp.rlen, 2);
 	return *n <= 2 && *n <= (int)(sp.rlen * 0.2);
 }
 
-KB_HD void kb_classify_segment(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int r, const u8* seq, const KbSeg& sp, int j, int n, KbSegX* out)
+KB_HD void kb_classify_segment(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int r, const u8* seq, const KbPk* rd, const KbSeg& sp, int j, int n, KbSegX* out)
 {
 	out->s = sp; out->info = KB_SEG_SKIP; out->aux = 0;
 	if (sp.rlen == 0 && sp.glen == 0) return;
@@ -545,13 +597,13 @@ KB_HD void kb_classify_segment(const KbIndexDev& ix, const KbParams& pm, const K
 	if (j == 0 || j == n - 1)
 	{
 		if (sp.rlen > 3000) { out->info = KB_SEG_SOFT; return; }                                  // AlignmentCandidates.cpp:671,690
-		if (!pm.pacbio && kb_quick_match_ref(ix, f1, sp, &mm)) { out->info = KB_SEG_QUICK; out->aux = (u32)(sp.rlen - mm); return; }
+		if (!pm.pacbio && kb_quick_match_ref(ix, rd, f1, sp, &mm)) { out->info = KB_SEG_QUICK; out->aux = (u32)(sp.rlen - mm); return; }
 		if (!pm.pacbio && sp.rlen > (j == 0 ? 50 : 100)) { out->info = KB_SEG_SOFT; return; }     // tools.cpp:307,358
 	}
 	else
 	{
 		if (sp.rlen == 0 || sp.glen == 0) { out->info = KB_SEG_GAP; return; }
-		if (kb_quick_match_ref(ix, f1, sp, &mm)) { out->info = KB_SEG_QUICK; out->aux = (u32)(sp.rlen - mm); return; }
+		if (kb_quick_match_ref(ix, rd, f1, sp, &mm)) { out->info = KB_SEG_QUICK; out->aux = (u32)(sp.rlen - mm); return; }
 	}
 	if (sp.rlen == 1 && sp.glen == 1)
 	{
@@ -575,6 +627,7 @@ KB_HD void kb_segments_read(const KbIndexDev& ix, const KbParams& pm, const KbBa
 	KbCand* cv = bt.cands + bt.cand_off[r];
 	int ncan = bt.n_cands[r];
 	const u8* seq = bt.seq + bt.seq_off[r]; int rlen = (int)(bt.seq_off[r + 1] - bt.seq_off[r]);
+	const KbPk* rd = kb_pk_read(bt, r);
 	for (int i = 0; i < ncan; i++)
 	{
 		u32 ci = bt.cand_off[r] + (u32)i;
@@ -593,7 +646,7 @@ KB_HD void kb_segments_read(const KbIndexDev& ix, const KbParams& pm, const KbBa
 			u32 off = KB_ATOMIC_ADD(&bt.counters[8], (u32)n);
 			if ((u64)off + (u64)n > (u64)bt.cap_segx) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SEGX); ar.used = mark; return; }
 			bt.cseg_off[ci] = off; bt.cseg_n[ci] = n;
-			for (int j = 0; j < n; j++) kb_classify_segment(ix, pm, bt, r, seq, sv[j], j, n, &bt.segx[off + j]);
+			for (int j = 0; j < n; j++) kb_classify_segment(ix, pm, bt, r, seq, rd, sv[j], j, n, &bt.segx[off + j]);
 		}
 		ar.used = mark;
 	}

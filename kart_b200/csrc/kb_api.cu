@@ -34,6 +34,23 @@ __device__ __forceinline__ void kb_warp_add64(unsigned long long* dst, unsigned 
 #endif
 }
 
+// read characters -> packed words (kb_fm.cuh "packed reads"); one thread per (read, word)
+__global__ void __launch_bounds__(KB_BLOCK) k_pack(KbBatchDev bt)
+{
+	long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t < (long long)bt.n_reads * bt.pk_wpr) kb_pack_word(bt, (int)(t / bt.pk_wpr), (int)(t % bt.pk_wpr));
+}
+
+// .pac bytes -> big-endian 64-bit words (upload time only)
+__global__ void k_ref64(const u8* pac, u64 bytes, u64 words, u64* out)
+{
+	u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (w >= words) return;
+	u64 v = 0;
+	for (int i = 0; i < 8; i++) { u64 b = w * 8 + i; v = (v << 8) | (u64)(b < bytes ? pac[b] : 0); }
+	out[w] = v;
+}
+
 __global__ void __launch_bounds__(KB_BLOCK) k_fm_seed(KbIndexDev ix, KbParams pm, KbBatchDev bt)
 {
 	int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -56,6 +73,13 @@ __global__ void k_expand_sa(KbIndexDev ix, u64* full)
 	u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
 	if (k > ix.seq_len) return;
 	u32 steps; full[k] = kb_sa(ix, k, &steps);
+}
+
+// seeding table (upload time only)
+__global__ void k_build_ktab(KbIndexDev ix, int K, KbKtab* out)
+{
+	u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t < (1ull << (2 * K))) out[t] = kb_ktab_entry(ix, (u32)t, K);
 }
 
 // re-blocks the BWA Occ/BWT interleave (16 words / 128 rows, u64 counts) into 8 words / 64 rows with u32 counts
@@ -96,10 +120,10 @@ __global__ void __launch_bounds__(KB_BLOCK) k_rescue(KbIndexDev ix, KbParams pm,
 			if (tid == 0 && !j->done) kb_rj_next(ix, bt, j, ar);
 			__syncthreads();
 			if (j->done) break;
-			kb_rj_window(ix, j, tid, nth); __syncthreads();
-			kb_rj_ids(j, tid, nth); __syncthreads();
+			kb_rj_window(ix, j, tid, nth); kb_rj_index_clear(j, tid, nth); __syncthreads();
+			kb_rj_ids(j, tid, nth); kb_rj_index_fill(j, tid, nth); __syncthreads();
 			kb_rj_pairs(j, tid, nth); __syncthreads();
-			if (tid == 0) kb_rj_cluster(pm, bt, j);
+			if (tid == 0) { j->reindex = 0; kb_rj_cluster(pm, bt, j); }
 			__syncthreads();
 		}
 		if (tid == 0) { kb_rj_end(pm, bt, j); ar.used = base_used; }
@@ -121,10 +145,10 @@ static void k_rescue(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulation: 
 		{
 			if (!j->done) kb_rj_next(ix, bt, j, ar);
 			if (j->done) break;
-			for (int t = 0; t < nth; t++) kb_rj_window(ix, j, t, nth);
-			for (int t = 0; t < nth; t++) kb_rj_ids(j, t, nth);
+			for (int t = 0; t < nth; t++) { kb_rj_window(ix, j, t, nth); kb_rj_index_clear(j, t, nth); }
+			for (int t = nth - 1; t >= 0; t--) { kb_rj_ids(j, t, nth); kb_rj_index_fill(j, t, nth); }
 			for (int t = nth - 1; t >= 0; t--) kb_rj_pairs(j, t, nth);   // reversed on purpose: the result must not depend on append order
-			kb_rj_cluster(pm, bt, j);
+			j->reindex = 0; kb_rj_cluster(pm, bt, j);
 		}
 		kb_rj_end(pm, bt, j); ar.used = base_used;
 	}
@@ -227,7 +251,7 @@ struct kb_ctx
 {
 	int device = 0; cudaStream_t stream = nullptr; std::string err;
 	bool have_index = false; KbIndexDev ix; KbParams pm;
-	DevBuf<u32> occ; DevBuf<u64> sa, sa_full; DevBuf<u8> pac, lut; DevBuf<i64> chr64; DevBuf<i32> chr32;
+	DevBuf<u32> occ; DevBuf<u64> sa, sa_full, ref64; DevBuf<KbPk> pk; DevBuf<KbKtab> ktab; DevBuf<u8> pac, lut; DevBuf<i64> chr64; DevBuf<i32> chr32;
 	int64_t l_pac = 0;
 	// batch
 	KbBatchDev bt; bool staged = false, ran = false; int n_reads = 0; size_t seq_bytes = 0;
@@ -290,7 +314,7 @@ void kb_destroy(kb_ctx_t* ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
-	ctx->occ.release(); ctx->sa.release(); ctx->sa_full.release(); ctx->pac.release(); ctx->lut.release(); ctx->chr64.release(); ctx->chr32.release();
+	ctx->occ.release(); ctx->ktab.release(); ctx->ref64.release(); ctx->pk.release(); ctx->sa.release(); ctx->sa_full.release(); ctx->pac.release(); ctx->lut.release(); ctx->chr64.release(); ctx->chr32.release();
 	ctx->seq.release(); ctx->scratch.release(); ctx->seq_off.release(); ctx->work.release(); ctx->est.release(); ctx->n_hits.release(); ctx->n_seeds.release();
 	ctx->n_cands.release(); ctx->cand_cap.release(); ctx->rescue.release(); ctx->seed_off.release(); ctx->cand_off.release(); ctx->cigar.release(); ctx->counters.release();
 	ctx->cseg_off.release(); ctx->runs.release(); ctx->cseg_n.release(); ctx->segx.release(); ctx->jobs.release(); ctx->hits.release(); ctx->segs.release(); ctx->cands.release(); ctx->reports.release(); ctx->res.release(); ctx->pstat.release(); ctx->aln.release();
@@ -329,6 +353,13 @@ int kb_upload_index(kb_ctx_t* ctx, const kb_index_host_t* h, int expand_sa)
 	size_t pac_bytes = (size_t)(h->l_pac / 4 + 1);
 	CK(ctx->pac.ensure(pac_bytes)); CK(cudaMemcpyAsync(ctx->pac.p, h->pac, pac_bytes, cudaMemcpyHostToDevice, ctx->stream));
 	ix.pac = ctx->pac.p; ix.G = h->l_pac; ix.G2 = h->l_pac * 2; ctx->l_pac = h->l_pac;
+	{
+		u64 words = (pac_bytes + 7) / 8 + 2;
+		CK(ctx->ref64.ensure(words));
+		KB_LAUNCH(k_ref64, (unsigned)((words + 255) / 256), 256, ctx->stream, ctx->pac.p, (u64)pac_bytes, words, ctx->ref64.p);
+		CK(cudaGetLastError());
+		ix.ref64 = ctx->ref64.p;
+	}
 	// chromosome tables: ChrLocMap (src/bwt_index.cpp:250-251) as a sorted key array
 	int nc = h->n_chr, ne = 2 * nc;
 	std::vector<i64> t64((size_t)ne + 3 * nc); std::vector<i32> t32(ne);
@@ -354,6 +385,20 @@ int kb_upload_index(kb_ctx_t* ctx, const kb_index_host_t* h, int expand_sa)
 	CK(ctx->lut.ensure(lut.size())); CK(cudaMemcpyAsync(ctx->lut.p, lut.data(), lut.size(), cudaMemcpyHostToDevice, ctx->stream));
 	ix.mapq_lut = ctx->lut.p; ix.mapq_lut_scores = lut_scores;
 	CK(cudaStreamSynchronize(ctx->stream));
+	{
+		// seeding table: K = floor(log4(2G)) - 1, so that it stays a fraction of the text (E. coli: K = 10, 32 MB, L2-resident)
+		int K = 0; while (K < 13 && (1ull << (2 * (K + 1))) <= h->seq_len) K++;
+		K -= 1; if (K > 12) K = 12;
+		if (K >= 4)
+		{
+			u64 ne = 1ull << (2 * K);
+			CK(ctx->ktab.ensure(ne));
+			ix.ktab = nullptr; ix.ktab_k = 0;
+			KB_LAUNCH(k_build_ktab, (unsigned)((ne + 255) / 256), 256, ctx->stream, ix, K, ctx->ktab.p);
+			CK(cudaGetLastError()); CK(cudaStreamSynchronize(ctx->stream));
+			ix.ktab = ctx->ktab.p; ix.ktab_k = K;
+		}
+	}
 	if (expand_sa)
 	{
 		CK(ctx->sa_full.ensure(h->seq_len + 1));
@@ -408,7 +453,8 @@ static int alloc_batch(kb_ctx* ctx)
 	CK(ctx->res.ensure(n)); CK(ctx->pstat.ensure(n / 2 + 1)); CK(ctx->aln.ensure(n)); CK(ctx->cigar.ensure(ctx->cap_cigar));
 	CK(ctx->segx.ensure(ctx->cap_segx)); CK(ctx->jobs.ensure(ctx->cap_jobs)); CK(ctx->runs.ensure(ctx->cap_runs)); CK(ctx->cseg_off.ensure(ctx->cap_cands)); CK(ctx->cseg_n.ensure(ctx->cap_cands));
 	CK(ctx->counters.ensure(16)); CK(ctx->work.ensure(8)); CK(ctx->scratch.ensure(per * threads));
-	bt.n_reads = ctx->n_reads; bt.seq = ctx->seq.p; bt.seq_off = ctx->seq_off.p; bt.est = ctx->est.p;
+	CK(ctx->pk.ensure((ctx->seq_bytes >> 5) + n + 4));
+	bt.n_reads = ctx->n_reads; bt.seq = ctx->seq.p; bt.seq_off = ctx->seq_off.p; bt.est = ctx->est.p; bt.pk = ctx->pk.p; bt.pk_wpr = (L + 31) / 32;
 	bt.hits = ctx->hits.p; bt.max_hits = max_hits; bt.n_hits = ctx->n_hits.p; bt.n_seeds = ctx->n_seeds.p; bt.seed_off = ctx->seed_off.p;
 	bt.segs = ctx->segs.p; bt.cap_segs = (u32)ctx->cap_segs; bt.cands = ctx->cands.p; bt.cap_cands = (u32)ctx->cap_cands; bt.n_cands = ctx->n_cands.p;
 	bt.cand_off = ctx->cand_off.p; bt.cand_cap = ctx->cand_cap.p; bt.rescue_list = ctx->rescue.p; bt.reports = ctx->reports.p; bt.res = ctx->res.p; bt.pstat = ctx->pstat.p;
@@ -451,6 +497,7 @@ static int launch_pipeline(kb_ctx* ctx)
 	unsigned g_scr = (unsigned)(bt.scratch_threads / KB_BLOCK);
 	ctx->launches = 0;
 	CK(cudaEventRecord(ctx->ev[0], s));
+	KB_LAUNCH(k_pack, (unsigned)(((long long)n * bt.pk_wpr + KB_BLOCK - 1) / KB_BLOCK), KB_BLOCK, s, bt); ctx->launches++;
 	KB_LAUNCH(k_fm_seed, g_reads, KB_BLOCK, s, ix, pm, bt); ctx->launches++;
 	CK(cudaEventRecord(ctx->ev[1], s));
 	KB_LAUNCH(k_sa_locate, g_hits, KB_BLOCK, s, ix, bt); ctx->launches++;

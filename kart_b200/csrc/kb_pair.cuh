@@ -40,11 +40,12 @@ KB_HD int kb_rescue_cluster(const KbParams& pm, const KbBatchDev& bt, i64 left, 
 struct KbRescueJob
 {
 	i32 p, ra, rb, n1, n2, n1o, n2o, l1, l2, est, sc1, sc2, strategy, attempted, mated;
-	i32 side, idx, thr, next_new, done, ovf, clean, slen, cap_pairs, ml;
+	i32 side, idx, thr, next_new, done, ovf, clean, slen, cap_pairs, ml, reindex, hmask;
 	u32 npairs;
 	i64 left;
 	u64 arena_used;
 	u32* wm; u8* win; u32* ww; KbSeg* pairs;
+	u32* hkey; i32* hhead; i32* hnext;   // open-addressing index of the mate's 8-mers: id+1 per slot, chain of positions per slot
 	const u8* mate;
 };
 
@@ -75,6 +76,9 @@ KB_HD void kb_rj_begin(const KbParams& pm, const KbBatchDev& bt, KbRescueJob* j,
 	if (j->est > pm.max_insert) j->est = pm.max_insert;
 	int lm = j->l1 > j->l2 ? j->l1 : j->l2;
 	j->wm = (u32*)ar.alloc((u64)lm * 4);
+	int hs = 256; while (hs < 2 * lm) hs <<= 1;
+	j->hmask = hs - 1; j->reindex = 0;
+	j->hkey = (u32*)ar.alloc((u64)hs * 4); j->hhead = (i32*)ar.alloc((u64)hs * 4); j->hnext = (i32*)ar.alloc((u64)lm * 4);
 	j->arena_used = ar.used;
 	if (ar.ovf) { j->ovf = 1; j->done = 1; }
 }
@@ -96,7 +100,7 @@ KB_HD void kb_rj_next(const KbIndexDev& ix, const KbBatchDev& bt, KbRescueJob* j
 			j->side = ns; j->idx = -1;
 			if (ns == 0) { j->thr = j->sc1 - 30 < 50 ? 50 : j->sc1 - 30; j->mate = bt.seq + bt.seq_off[j->rb]; j->ml = j->l2; j->next_new = j->n2o; }
 			else { j->thr = j->sc2 - 30 < 50 ? 50 : j->sc2 - 30; j->mate = bt.seq + bt.seq_off[j->ra]; j->ml = j->l1; j->next_new = j->n1o; }
-			kb_kmer_ids(j->ml, j->mate, j->wm);
+			kb_kmer_ids(j->ml, j->mate, j->wm); j->reindex = 1;
 			continue;
 		}
 		int i = ++j->idx; i64 left, right; int cid, e;
@@ -150,32 +154,53 @@ KB_HD void kb_rj_ids(KbRescueJob* j, int tid, int nth)
 	}
 }
 
-// all threads: one diagonal of the match matrix at a time; exact runs of >= 10 bases are appended in arbitrary order
+// all threads, after a side switch: index the mate's 8-mers (two barrier-separated phases: clear, insert)
+KB_HD u32 kb_rj_slot(u32 id, int mask) { return (id * 40503u + (id >> 7)) & (u32)mask; }
+KB_HD void kb_rj_index_clear(KbRescueJob* j, int tid, int nth)
+{
+	if (!j->reindex) return;
+	for (int s = tid; s <= j->hmask; s += nth) { j->hkey[s] = 0; j->hhead[s] = -1; }
+}
+KB_HD void kb_rj_index_fill(KbRescueJob* j, int tid, int nth)
+{
+	if (!j->reindex) return;
+	for (int r = tid; r < j->ml; r += nth)
+	{
+		u32 id = j->wm[r]; if (id == KB_NOKMER) continue;
+		u32 s = kb_rj_slot(id, j->hmask);
+		while (true)
+		{
+			u32 old = KB_ATOMIC_CAS(&j->hkey[s], 0u, id + 1u);
+			if (old == 0u || old == id + 1u) break;
+			s = (s + 1u) & (u32)j->hmask;
+		}
+		j->hnext[r] = KB_ATOMIC_EXCH(&j->hhead[s], (i32)r);
+	}
+}
+
+// all threads: exact runs of >= 10 bases between the mate and the window, appended in arbitrary order. Same set as
+// IdentifyCommonKmers(MaxShift = slen) + GenerateSimplePairsFromCommonKmers(10): every window position looks its 8-mer up
+// in the mate's index; a match (r,g) whose predecessor (r-1,g-1) is no match starts a run, which is then extended.
+// (|g - r| < slen holds for every pair since r < ml <= slen and g < slen.)
 KB_HD void kb_rj_pairs(KbRescueJob* j, int tid, int nth)
 {
-	int n1 = j->ml - 7, n2 = j->slen - 7; if (n1 <= 0 || n2 <= 0) return;
-	int dlo = -(n1 - 1), dhi = n2 - 1, ms = j->slen;   // IdentifyCommonKmers(MaxShift = slen): |g - r| < slen
-	if (dlo < -(ms - 1)) dlo = -(ms - 1);
-	if (dhi > ms - 1) dhi = ms - 1;
-	const u32* w1 = j->wm; const u32* w2 = j->ww;
-	for (int d = dlo + tid; d <= dhi; d += nth)
+	const u32* w1 = j->wm; const u32* w2 = j->ww; const int ml = j->ml, sl = j->slen;
+	for (int g = tid; g < sl; g += nth)
 	{
-		int r0 = d < 0 ? -d : 0, r1 = n1 < n2 - d ? n1 : n2 - d, run = 0;
-		for (int r = r0; r <= r1; r++)
+		u32 id = w2[g]; if (id == KB_NOKMER) continue;
+		u32 s = kb_rj_slot(id, j->hmask), key;
+		while ((key = j->hkey[s]) != 0u && key != id + 1u) s = (s + 1u) & (u32)j->hmask;
+		if (key == 0u) continue;
+		for (int r = j->hhead[s]; r >= 0; r = j->hnext[r])
 		{
-			bool m = r < r1 && w1[r] != KB_NOKMER && w1[r] == w2[r + d];
-			if (m) run++;
-			else if (run > 0)
-			{
-				int l = 8 + run - 1;
-				if (l >= 10)
-				{
-					u32 slot = KB_ATOMIC_ADD(&j->npairs, 1u);
-					if ((int)slot < j->cap_pairs) { KbSeg s; s.simple = 1; s.rpos = r - run; s.gpos = (i64)(r - run + d); s.rlen = s.glen = l; j->pairs[slot] = s; }
-					else j->ovf = 1;
-				}
-				run = 0;
-			}
+			if (r > 0 && g > 0 && w1[r - 1] != KB_NOKMER && w1[r - 1] == w2[g - 1]) continue;   // not the start of its run
+			int run = 1;
+			while (r + run < ml && g + run < sl && w1[r + run] != KB_NOKMER && w1[r + run] == w2[g + run]) run++;
+			int l = 8 + run - 1;
+			if (l < 10) continue;
+			u32 slot = KB_ATOMIC_ADD(&j->npairs, 1u);
+			if ((int)slot < j->cap_pairs) { KbSeg sg; sg.simple = 1; sg.rpos = r; sg.gpos = (i64)g; sg.rlen = sg.glen = l; j->pairs[slot] = sg; }
+			else j->ovf = 1;
 		}
 	}
 }

@@ -36,6 +36,9 @@ struct KbParams
 	i32 paired;        // reads come as (mate1, revcomp(mate2)) pairs
 };
 
+// seeding table: state of BWT_Search after the first K bases (x2 > 0), or the length at which the search died (x2 == 0)
+struct __attribute__((aligned(32))) KbKtab { u64 x0, x1; u32 x2, flen; u64 pad; };
+
 struct KbIndexDev
 {
 	u64 primary, L2[5], seq_len;
@@ -45,7 +48,10 @@ struct KbIndexDev
 	u64 n_sa;
 	i32 sa_intv;
 	const u64* sa_full;      // optional full SA (NULL when not expanded)
+	const KbKtab* ktab;      // 4^ktab_k entries, indexed by the 2-bit codes of the first ktab_k bases (first base most significant)
+	i32 ktab_k;
 	const u8* pac;           // forward strand, 2 bit / base, MSB first
+	const u64* ref64;        // the same bits as big-endian 64-bit words: word w = bases 32w..32w+31, base i at bits 62-2(i&31)
 	i64 G, G2;               // GenomeSize, TwoGenomeSize
 	i32 n_chr, n_ends;
 	const i64* end_key;      // ChrLocMap keys (last coordinate of each chromosome on each strand), ascending
@@ -57,6 +63,9 @@ struct KbIndexDev
 	i32 mapq_lut_scores;
 };
 
+// 32 read characters: nt4 codes (2 bit, MSB first, 0 where the character is no base), n4 = "nt4 code is 4" and
+// bad = "not one of the upper-case letters ACGT" (bit 31-i for character i; set beyond the end of the read)
+struct __attribute__((aligned(16))) KbPk { u64 code; u32 n4, bad; };
 struct KbHit { u64 x0; u32 rpos; u32 len_freq; };                 // len << 8 | freq   (freq <= 50)
 struct KbSeg { i64 gpos; i32 rpos; i32 rlen; i32 glen; i32 simple; };
 struct KbCand { i64 diff; i32 score; i32 mate; u32 seg_start; i32 nseg; };
@@ -82,6 +91,7 @@ struct KbBatchDev
 	const u8* seq;           // concatenated read characters (mate 2 already reverse-complemented, src/GetData.cpp:125-135)
 	const u64* seq_off;      // n_reads + 1
 	const i32* est;          // per pair EstDistance (n_reads / 2 entries) when paired
+	KbPk* pk; i32 pk_wpr;    // packed reads: read r starts at word (seq_off[r] >> 5) + r ; pk_wpr = words of the longest read
 	// stage 1
 	KbHit* hits; i32 max_hits;          // [n_reads][max_hits]
 	i32* n_hits;                        // hits stored per read
