@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(KB_BLOCK) k_fm_seed(KbIndexDev ix, KbParams pm
 {
 	int r = blockIdx.x * blockDim.x + threadIdx.x;
 	u32 steps = 0, blocks = 0;
-	if (r < bt.n_reads) kb_seed_read(ix, pm, bt, r, &steps, &blocks);
+	kb_seed_read(ix, pm, bt, r, r < bt.n_reads, &steps, &blocks);
 	kb_warp_add64(&bt.work[0], steps); kb_warp_add64(&bt.work[1], blocks);
 }
 
@@ -82,7 +82,7 @@ __global__ void k_build_ktab(KbIndexDev ix, int K, KbKtab* out)
 	if (t < (1ull << (2 * K))) out[t] = kb_ktab_entry(ix, (u32)t, K);
 }
 
-// re-blocks the BWA Occ/BWT interleave (16 words / 128 rows, u64 counts) into 8 words / 64 rows with u32 counts
+// re-blocks the BWA Occ/BWT interleave (16 words / 128 rows, u64 counts) into 8 words / 64 rows: u32 counts + two bit planes
 __global__ void k_reblock(const u32* bwt, u64 bwt_words, u64 n_new, u32* occ)
 {
 	u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -96,9 +96,15 @@ __global__ void k_reblock(const u32* bwt, u64 bwt_words, u64 n_new, u32* occ)
 		kb_count32(((u64)w[0] << 32) | w[1], 32, cnt);
 		kb_count32(((u64)w[2] << 32) | w[3], 32, cnt);
 	}
+	u64 lo = 0, hi = 0;
+	for (int i = 0; i < 64; i++)
+	{
+		u32 code = (w[4 * half + (i >> 4)] >> ((~i & 15) << 1)) & 3u;
+		lo |= (u64)(code & 1u) << (63 - i); hi |= (u64)(code >> 1) << (63 - i);
+	}
 	u32* o = occ + j * 8;
 	o[0] = cnt[0]; o[1] = cnt[1]; o[2] = cnt[2]; o[3] = cnt[3];
-	for (int k = 0; k < 4; k++) o[4 + k] = w[4 * half + k];
+	o[4] = (u32)lo; o[5] = (u32)(lo >> 32); o[6] = (u32)hi; o[7] = (u32)(hi >> 32);
 }
 
 __global__ void __launch_bounds__(KB_BLOCK) k_cand_pair(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_cand_pair(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x); }
@@ -386,9 +392,9 @@ int kb_upload_index(kb_ctx_t* ctx, const kb_index_host_t* h, int expand_sa)
 	ix.mapq_lut = ctx->lut.p; ix.mapq_lut_scores = lut_scores;
 	CK(cudaStreamSynchronize(ctx->stream));
 	{
-		// seeding table: K = floor(log4(2G)) - 1, so that it stays a fraction of the text (E. coli: K = 10, 32 MB, L2-resident)
-		int K = 0; while (K < 13 && (1ull << (2 * (K + 1))) <= h->seq_len) K++;
-		K -= 1; if (K > 12) K = 12;
+		// seeding table: the smallest K with 4^K >= 2G, at most 12 (512 MB): past it intervals are narrow, so nearly every
+		// remaining extension step is the one-block case of kb_extend
+		int K = 1; while (K < 12 && (1ull << (2 * K)) < h->seq_len) K++;
 		if (K >= 4)
 		{
 			u64 ne = 1ull << (2 * K);

@@ -98,86 +98,63 @@ KB_HD void kb_count32(u64 W, int n, u32 cnt[4])
 	cnt[3] += t; cnt[2] += g; cnt[1] += c; cnt[0] += (u32)n - t - g - c;
 }
 
-// Occ(k, .) for all four bases: number of each base in BWT rows [0..k] with '$' skipped. k != ~0.   (bwt_occ4 :68)
-KB_HD void kb_occ4(const KbIndexDev& ix, u64 k, u64 out[4])
-{
-	u64 r = k - (k >= ix.primary);
-	const uint4* p = reinterpret_cast<const uint4*>(ix.occ) + ((r >> 6) << 1);
-	uint4 c = KB_LDG4(p), w = KB_LDG4(p + 1);
-	int n = (int)(r & 63) + 1;
-	u32 cnt[4] = {c.x, c.y, c.z, c.w};
-	kb_count32(((u64)w.x << 32) | w.y, n < 32 ? n : 32, cnt);
-	if (n > 32) kb_count32(((u64)w.z << 32) | w.w, n - 32, cnt);
-	out[0] = cnt[0]; out[1] = cnt[1]; out[2] = cnt[2]; out[3] = cnt[3];
-}
-
 // ---- one 32-byte Occ block = one DRAM sector, fetched with a single 256-bit load (LDG.E.256 on sm_100a) ----
-struct KbBlk { u32 c0, c1, c2, c3, w0, w1, w2, w3; };
+// [u32 cntA,cntC,cntG,cntT : occurrences before the block][u64 lo][u64 hi]: the 64 BWT symbols of the block as two bit
+// planes (low and high bit of the 2-bit code), row i of the block at bit 63-i. Rank queries are then one mask per plane.
+struct KbBlk { u32 c0, c1, c2, c3; u64 lo, hi; };
 KB_HD KbBlk kb_load_blk(const uint32_t* occ, u64 blk)
 {
 	KbBlk b; const uint32_t* p = occ + (blk << 3);
 #if defined(__CUDA_ARCH__)
+	u32 l0, l1, h0, h1;
 	asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-	             : "=r"(b.c0), "=r"(b.c1), "=r"(b.c2), "=r"(b.c3), "=r"(b.w0), "=r"(b.w1), "=r"(b.w2), "=r"(b.w3) : "l"(p));
+	             : "=r"(b.c0), "=r"(b.c1), "=r"(b.c2), "=r"(b.c3), "=r"(l0), "=r"(l1), "=r"(h0), "=r"(h1) : "l"(p));
+	b.lo = ((u64)l1 << 32) | l0; b.hi = ((u64)h1 << 32) | h0;
 #else
-	b.c0 = p[0]; b.c1 = p[1]; b.c2 = p[2]; b.c3 = p[3]; b.w0 = p[4]; b.w1 = p[5]; b.w2 = p[6]; b.w3 = p[7];
+	b.c0 = p[0]; b.c1 = p[1]; b.c2 = p[2]; b.c3 = p[3]; b.lo = ((u64)p[5] << 32) | p[4]; b.hi = ((u64)p[7] << 32) | p[6];
 #endif
 	return b;
 }
+KB_HD u64 kb_top_bits(u32 n) { return n == 0 ? 0ull : (~0ull << (64u - n)); }   // the first n (0..64) rows of a block
+KB_HD u32 kb_sel4(int b, u32 v0, u32 v1, u32 v2, u32 v3) { u32 lo = (b & 1) ? v1 : v0, hi = (b & 1) ? v3 : v2; return (b & 2) ? hi : lo; }
 
-// For base b: eq = Occ(row, b), gt = sum over bases j > b of Occ(row, j), where `off` is the row's offset in the block.
-// Two popcounts per 32 symbols instead of one per base: the interval update only needs these two sums.
+// Occ(row, b) and the sum over bases j > b of Occ(row, j), `off` = the row's offset in its block
 KB_HD void kb_rank_eq_gt(const KbBlk& k, int off, int b, u32* eq, u32* gt)
 {
-	// all selections by `b` are mask arithmetic (see kb_nt4 for why): BL/BH broadcast b's low/high bit to every symbol slot
-	const u64 M5 = 0x5555555555555555ull;
-	u32 n = (u32)off + 1u, n0 = n < 32u ? n : 32u, n1 = n - n0;
-	u64 pm0 = M5 & ~((~0ull >> n0) >> n0);            // first n0 symbols of word 0 (n0 = 1..32)
-	u64 pm1 = M5 & ~((~0ull >> n1) >> n1);            // first n1 symbols of word 1 (n1 = 0..32)
-	u64 BL = M5 & (0ull - (u64)((u32)b & 1u)), BH = M5 & (0ull - (u64)(((u32)b >> 1) & 1u));
-	u64 W0 = ((u64)k.w0 << 32) | k.w1, W1 = ((u64)k.w2 << 32) | k.w3;
-	u64 lo0 = W0 & M5, hi0 = (W0 >> 1) & M5, lo1 = W1 & M5, hi1 = (W1 >> 1) & M5;
-	u64 e0 = ~((lo0 ^ BL) | (hi0 ^ BH)) & pm0, e1 = ~((lo1 ^ BL) | (hi1 ^ BH)) & pm1;                     // symbol == b
-	u64 g0 = ((hi0 & ~BH) | (~(hi0 ^ BH) & lo0 & ~BL)) & pm0, g1 = ((hi1 & ~BH) | (~(hi1 ^ BH) & lo1 & ~BL)) & pm1;   // symbol > b
-	u32 m0 = 0u - (u32)(b == 0), m1 = 0u - (u32)(b == 1), m2 = 0u - (u32)(b == 2), m3 = 0u - (u32)(b == 3);
-	u32 ceq = (k.c0 & m0) | (k.c1 & m1) | (k.c2 & m2) | (k.c3 & m3);
-	u32 cgt = ((k.c1 + k.c2 + k.c3) & m0) | ((k.c2 + k.c3) & m1) | (k.c3 & m2);
-	*eq = ceq + (u32)KB_POPCLL(e0) + (u32)KB_POPCLL(e1);
-	*gt = cgt + (u32)KB_POPCLL(g0) + (u32)KB_POPCLL(g1);
+	const u64 nBL = (b & 1) ? 0ull : ~0ull, nBH = (b & 2) ? 0ull : ~0ull;
+	const u64 pm = kb_top_bits((u32)off + 1u);
+	const u64 e = (k.lo ^ nBL) & (k.hi ^ nBH);                 // symbol == b
+	const u64 t = k.lo & nBL;
+	const u64 g = (k.hi & t) | (nBH & (k.hi | t));             // symbol > b
+	*eq = kb_sel4(b, k.c0, k.c1, k.c2, k.c3) + (u32)KB_POPCLL(e & pm);
+	*gt = kb_sel4(b, k.c1 + k.c2 + k.c3, k.c2 + k.c3, k.c3, 0u) + (u32)KB_POPCLL(g & pm);
 }
 
 // ---- one forward extension of a bi-interval by base c (BWT_Search :151-166 with bwt_2occ4 :87) -------------------------
 // b = 3 - c is the base looked up in the BWT. Returns false (state untouched) when the extended interval is empty.
-// Rows k' and l' usually share one 32-byte block (always, once the interval is narrow): then the block is loaded once,
-// Occ(k,b) comes from a prefix mask and the two differences Occ(l,.)-Occ(k,.) from a range mask.
+// Rows k'+1 .. l' usually lie in one 32-byte block (always for a one-row interval): then that block alone gives
+// Occ(k',b) = count before the block + matches among the rows in front of k'+1, and Occ(l',.)-Occ(k',.) from a range mask.
 KB_HD bool kb_extend(const KbIndexDev& ix, u64& x0, u64& x1, u64& x2, int c, u32* blocks)
 {
-	const u64 M5 = 0x5555555555555555ull;
 	const u64 primary = ix.primary;
 	const int b = 3 - c;
 	const u64 k = x1 - 1, l = k + x2;
 	const u64 rk = k - (k >= primary), rl = l - (l >= primary);
+	const u64 nBL = (b & 1) ? 0ull : ~0ull, nBH = (b & 2) ? 0ull : ~0ull;
 	u32 ek, n2, gt;
-	if ((rk >> 6) == (rl >> 6))
+	if (((rk + 1) >> 6) == (rl >> 6))
 	{
-		const KbBlk B = kb_load_blk(ix.occ, rk >> 6); *blocks += 1;
-		const u32 nk = (u32)(rk & 63) + 1u, nl = (u32)(rl & 63) + 1u;
-		const u32 nk0 = nk < 32u ? nk : 32u, nk1 = nk - nk0, nl0 = nl < 32u ? nl : 32u, nl1 = nl - nl0;
-		const u64 pk0 = M5 & ~((~0ull >> nk0) >> nk0), pk1 = M5 & ~((~0ull >> nk1) >> nk1);
-		const u64 r0 = M5 & ~((~0ull >> nl0) >> nl0) & ~pk0, r1 = M5 & ~((~0ull >> nl1) >> nl1) & ~pk1;   // rows (k', l']
-		const u64 BL = M5 & (0ull - (u64)((u32)b & 1u)), BH = M5 & (0ull - (u64)(((u32)b >> 1) & 1u));
-		const u64 W0 = ((u64)B.w0 << 32) | B.w1, W1 = ((u64)B.w2 << 32) | B.w3;
-		const u64 lo0 = W0 & M5, hi0 = (W0 >> 1) & M5, lo1 = W1 & M5, hi1 = (W1 >> 1) & M5;
-		const u64 e0 = ~((lo0 ^ BL) | (hi0 ^ BH)), e1 = ~((lo1 ^ BL) | (hi1 ^ BH));   // symbol == b (valid under the M5-based masks)
-		n2 = (u32)KB_POPCLL(e0 & r0) + (u32)KB_POPCLL(e1 & r1);
+		const KbBlk B = kb_load_blk(ix.occ, rl >> 6); *blocks += 1;
+		const u64 pk = kb_top_bits((u32)((rk + 1) & 63)), rg = kb_top_bits((u32)(rl & 63) + 1u) & ~pk;   // rows (k', l']
+		const u64 e = (B.lo ^ nBL) & (B.hi ^ nBH);
+		n2 = (u32)KB_POPCLL(e & rg);
 		if (n2 == 0) return false;
-		const u32 m0 = 0u - (u32)(b == 0), m1 = 0u - (u32)(b == 1), m2 = 0u - (u32)(b == 2), m3 = 0u - (u32)(b == 3);
-		ek = ((B.c0 & m0) | (B.c1 & m1) | (B.c2 & m2) | (B.c3 & m3)) + (u32)KB_POPCLL(e0 & pk0) + (u32)KB_POPCLL(e1 & pk1);
+		ek = kb_sel4(b, B.c0, B.c1, B.c2, B.c3) + (u32)KB_POPCLL(e & pk);
 		gt = 0;
 		if (x2 > 1)   // a one-row interval that survives holds b itself: nothing greater
 		{
-			const u64 g0 = (hi0 & ~BH) | (~(hi0 ^ BH) & lo0 & ~BL), g1 = (hi1 & ~BH) | (~(hi1 ^ BH) & lo1 & ~BL);   // symbol > b
-			gt = (u32)KB_POPCLL(g0 & r0) + (u32)KB_POPCLL(g1 & r1);
+			const u64 t = B.lo & nBL;
+			gt = (u32)KB_POPCLL(((B.hi & t) | (nBH & (B.hi | t))) & rg);
 		}
 	}
 	else
@@ -229,8 +206,7 @@ KB_HD u64 kb_lf(const KbIndexDev& ix, u64 k)
 	u64 r = k - (k > ix.primary);
 	KbBlk bk = kb_load_blk(ix.occ, r >> 6);
 	int off = (int)(r & 63);
-	u32 word = off < 16 ? bk.w0 : (off < 32 ? bk.w1 : (off < 48 ? bk.w2 : bk.w3));
-	int sym = (word >> ((~off & 15) << 1)) & 3;
+	int sym = (int)((bk.lo >> (63 - off)) & 1ull) | (int)(((bk.hi >> (63 - off)) & 1ull) << 1);
 	u32 eq, gt; kb_rank_eq_gt(bk, off, sym, &eq, &gt);
 	return ix.L2[sym] + eq;
 }
@@ -245,34 +221,64 @@ KB_HD u64 kb_sa(const KbIndexDev& ix, u64 k, u32* steps)
 	return s + KB_LDG(ix.sa + k / (u64)ix.sa_intv);
 }
 
-// One read: all searches of IdentifySeedPairs_FastMode (:49) or _SensitiveMode (:132) with BWT_Search (:140-170) inlined as a
-// FLAT state machine: every trip of the single loop performs (at most) one extension step, so the lanes of a warp stay in
-// lock-step across search boundaries instead of waiting for the longest search of the warp (nested loops cost 4-5x here).
+// One read: all searches of IdentifySeedPairs_FastMode (:49) or _SensitiveMode (:132) with BWT_Search (:140-170) inlined.
+// The lanes of a warp each own one read and advance in lock-step, one extension per trip. Everything that is not an
+// extension (closing a search: :172-181 and the caller's bookkeeping; opening the next one) is kept out of the extension
+// loop and done for several lanes at once: a lane whose search has ended parks until KB_SEED_QUORUM lanes are parked (or
+// nobody is searching), then all parked lanes close and reopen together. Per-lane results do not depend on the schedule.
 // The read is walked through its packed words (one 16-byte load per 32 bases); a search whose first K bases are clean and
 // inside its limit starts from the seeding table instead of K-1 extension steps (identical state by construction).
 // Records the searches that will yield seeds (len >= MinSeedLength and interval size <= OCC_Thr 50, bwt_search.cpp:3,172-176).
-KB_HD void kb_seed_read(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int r, u32* w_steps, u32* w_blocks)
+#define KB_SEED_QUORUM 6
+#if defined(__CUDA_ARCH__)
+#define KB_BALLOT(p) __ballot_sync(0xFFFFFFFFu, (p))
+#else
+#define KB_BALLOT(p) ((p) ? 1u : 0u)
+#endif
+KB_HD void kb_seed_read(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int r, bool valid, u32* w_steps, u32* w_blocks)
 {
-	const KbPk* rd = kb_pk_read(bt, r);
-	const int rlen = (int)(bt.seq_off[r + 1] - bt.seq_off[r]);
-	KbHit* hits = bt.hits + (size_t)r * bt.max_hits;
-	int nh = 0, ns = 0, pos = 0, cur = 0, lim = 0, stop = 30;
+	const KbPk* rd = valid ? kb_pk_read(bt, r) : bt.pk;
+	const int rlen = valid ? (int)(bt.seq_off[r + 1] - bt.seq_off[r]) : 0;
+	KbHit* hits = bt.hits + (size_t)(valid ? r : 0) * bt.max_hits;
+	int nh = 0, ns = 0, pos = 0, cur = 0, lim = 0, stop = 30, len = 0;
 	const int end = rlen - pm.min_seed, K = (ix.ktab != nullptr && ix.ktab_k <= pm.min_seed) ? ix.ktab_k : 0;
 	u32 steps = 0, blocks = 0;
 	u64 x0 = 0, x1 = 0, x2 = 0;
-	bool searching = false, ovf = false;
+	bool searching = false, closing = false, finished = !valid, ovf = false;
 	int cw = -1; u64 ccode = 0; u32 cn4 = 0;   // the packed word under the cursor
-	while (searching || pos < end)
+#if defined(__CUDA_ARCH__)
+	const u32 quorum = KB_SEED_QUORUM;
+#else
+	const u32 quorum = 1;
+#endif
+	while (KB_BALLOT(!finished))
 	{
-		bool ended = false; int len = 0;
-		if (!searching)
+		// parked lanes: close the search that ended, open the next one
+		while (!finished && !searching)
 		{
-			if ((pos >> 5) != cw) { cw = pos >> 5; KbPk w = kb_load_pk(rd + cw); ccode = w.code; cn4 = w.n4; }
-			const int o = pos & 31;
-			const int p = (int)((ccode >> (62 - 2 * o)) & 3u) | (int)(((cn4 >> (31 - o)) & 1u) << 2);
-			if (p > 3) { pos++; stop++; continue; }
+			if (closing)
+			{
+				closing = false;
+				bool hit = len >= pm.min_seed && (int)x2 <= 50;
+				if (hit)
+				{
+					if (nh < bt.max_hits) { KbHit h; h.x0 = x0; h.rpos = (u32)pos; h.len_freq = ((u32)len << 8) | (u32)x2; hits[nh++] = h; ns += (int)x2; }
+					else ovf = true;
+				}
+				if (pm.pacbio) { int adv = hit ? len : pm.min_seed; pos += adv; stop += adv; if (stop > rlen) stop = rlen; }
+				else pos += len + 1;
+			}
+			int p = 4;
+			while (pos < end)
+			{
+				if ((pos >> 5) != cw) { cw = pos >> 5; KbPk w = kb_load_pk(rd + cw); ccode = w.code; cn4 = w.n4; }
+				const int o = pos & 31;
+				p = (int)((ccode >> (62 - 2 * o)) & 3u) | (int)(((cn4 >> (31 - o)) & 1u) << 2);
+				if (p <= 3) break;
+				pos++; stop++;
+			}
+			if (pos >= end) { finished = true; break; }
 			lim = pm.pacbio ? (stop < rlen ? stop : rlen) : rlen;
-			searching = true;
 			bool seeded = false;
 			if (K > 0 && pos + K <= lim)
 			{
@@ -281,41 +287,37 @@ KB_HD void kb_seed_read(const KbIndexDev& ix, const KbParams& pm, const KbBatchD
 				{
 					const KbKtab e = kb_load_ktab(ix.ktab + (u32)(w.code >> (64 - 2 * K))); blocks++;
 					seeded = true;
-					if (e.x2 != 0) { x0 = e.x0; x1 = e.x1; x2 = e.x2; cur = pos + K; steps += (u32)(K - 1); }
-					else { ended = true; len = (int)e.flen; steps += e.flen; x2 = 0; }
+					if (e.x2 != 0) { x0 = e.x0; x1 = e.x1; x2 = e.x2; cur = pos + K; steps += (u32)(K - 1); searching = true; }
+					else { closing = true; len = (int)e.flen; steps += e.flen; x2 = 0; }
 				}
 			}
-			if (!seeded) { x0 = ix.L2[p] + 1; x1 = ix.L2[3 - p] + 1; x2 = ix.L2[p + 1] - ix.L2[p]; cur = pos + 1; }
+			if (!seeded) { x0 = ix.L2[p] + 1; x1 = ix.L2[3 - p] + 1; x2 = ix.L2[p + 1] - ix.L2[p]; cur = pos + 1; searching = true; }
 		}
-		if (!ended)
+		// extension trips until enough lanes are parked
+		u32 parked, active;
+		do
 		{
-			ended = true;
-			if (cur < lim)
+			if (searching)
 			{
-				if ((cur >> 5) != cw) { cw = cur >> 5; KbPk w = kb_load_pk(rd + cw); ccode = w.code; cn4 = w.n4; }
-				const int o = cur & 31;
-				const int c = (int)((ccode >> (62 - 2 * o)) & 3u) | (int)(((cn4 >> (31 - o)) & 1u) << 2);
-				if (c <= 3)
+				bool ended = true;
+				if (cur < lim)
 				{
-					steps++;
-					if (kb_extend(ix, x0, x1, x2, c, &blocks)) { cur++; ended = false; }
+					if ((cur >> 5) != cw) { cw = cur >> 5; KbPk w = kb_load_pk(rd + cw); ccode = w.code; cn4 = w.n4; }
+					const int o = cur & 31;
+					const int c = (int)((ccode >> (62 - 2 * o)) & 3u) | (int)(((cn4 >> (31 - o)) & 1u) << 2);
+					if (c <= 3)
+					{
+						steps++;
+						if (kb_extend(ix, x0, x1, x2, c, &blocks)) { cur++; ended = false; }
+					}
 				}
+				if (ended) { searching = false; closing = true; len = cur - pos; }
 			}
-			len = cur - pos;
-		}
-		if (ended)
-		{
-			bool hit = len >= pm.min_seed && (int)x2 <= 50;
-			if (hit)
-			{
-				if (nh < bt.max_hits) { KbHit h; h.x0 = x0; h.rpos = (u32)pos; h.len_freq = ((u32)len << 8) | (u32)x2; hits[nh++] = h; ns += (int)x2; }
-				else ovf = true;
-			}
-			if (pm.pacbio) { int adv = hit ? len : pm.min_seed; pos += adv; stop += adv; if (stop > rlen) stop = rlen; }
-			else pos += len + 1;
-			searching = false;
-		}
+			active = KB_BALLOT(searching);
+			parked = KB_BALLOT(!searching && !finished);
+		} while (active != 0 && (u32)KB_POPCLL((u64)parked) < quorum);
 	}
+	if (!valid) return;
 	*w_steps += steps; *w_blocks += blocks;
 	if (ovf) KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_HITS);
 	bt.n_hits[r] = nh; bt.n_seeds[r] = ns;
