@@ -453,6 +453,8 @@ struct KbFragIter
 {
 	const KbParams* pm; KbArena* ar; const u8* f1; const u8* f2; KbRuns* acc;
 	KbWork* st; int sp, scap; u64 mark0;
+	// the fragment being partitioned (between next() == 2 and part_finish())
+	KbWork cur; u32* w1; u32* w2; KbSeg* raw; int shift, cap, dirty; u32 np; u64 pmark;
 
 	KB_HD bool init(const KbParams* pm_, KbArena* ar_, const u8* f1_, int rl0, const u8* f2_, int gl0, KbRuns* acc_)
 	{
@@ -464,8 +466,9 @@ struct KbFragIter
 		return true;
 	}
 
-	// true: *piece (r0,rl,g0,gl) needs nw_alignment; false: finished (or the arena overflowed: ar->ovf)
-	KB_HD bool next(KbWork* piece)
+	// one lane. 1: *piece (r0,rl,g0,gl) needs nw_alignment; 2: a fragment is ready to be partitioned (part_scan, part_ids,
+	// part_pairs by all lanes with a barrier after each, then part_finish by one lane); 0: finished (or the arena overflowed)
+	KB_HD int next(KbWork* piece)
 	{
 		while (sp > 0 && !ar->ovf)
 		{
@@ -481,52 +484,99 @@ struct KbFragIter
 			}
 			if (e.kind == KB_W_FRAG && e.rl > 30 && e.gl > 30)
 			{
-				int rl = e.rl, gl = e.gl, shift;
+				int rl = e.rl, gl = e.gl;
 				if (pm->pacbio) { shift = rl > gl ? (int)(rl * 0.2) : (int)(gl * 0.2); if (shift > 50) shift = 50; }
 				else shift = pm->max_gaps;
-				u64 mark = ar->used;
-				u32* w1 = (u32*)ar->alloc((u64)rl * 4); u32* w2 = (u32*)ar->alloc((u64)gl * 4);
-				int cap = ((rl < gl ? rl : gl) / 9 + 2) * (2 * shift + 1);   // exact-match runs on one diagonal start >= 9 apart
+				pmark = ar->used;
+				w1 = (u32*)ar->alloc((u64)rl * 4); w2 = (u32*)ar->alloc((u64)gl * 4);
+				cap = ((rl < gl ? rl : gl) / 9 + 2) * (2 * shift + 1);   // exact-match runs on one diagonal start >= 9 apart
 				if (cap > rl + gl) cap = rl + gl;
-				KbSeg* raw = (KbSeg*)ar->alloc((u64)cap * sizeof(KbSeg));
-				if (ar->ovf) return false;
-				kb_kmer_ids(rl, a, w1); kb_kmer_ids(gl, b, w2);
-				bool povf = false;
-				int np = kb_kmer_pairs(w1, rl, w2, gl, shift, 8, raw, cap, &povf);
-				if (povf) { ar->ovf = true; return false; }
-				int tot = 0; KbSeg* part = nullptr;
-				if (np > 0)
-				{
-					kb_sort_segs<true>(raw, np);
-					part = (KbSeg*)ar->alloc((u64)(2 * np + 2) * sizeof(KbSeg));
-					i32* order = (i32*)ar->alloc((u64)np * 4);
-					if (ar->ovf) return false;
-					tot = kb_fill_pairs(rl, gl, raw, np, part, order);
-				}
-				if (tot > 0)
-				{
-					if (sp + tot > scap) { ar->ovf = true; return false; }
-					for (int i = tot - 1; i >= 0; i--)   // reversed, so that pops come out left to right
-					{
-						const KbSeg p = part[i];
-						if (p.rlen <= 0 && p.glen <= 0) continue;
-						KbWork w; w.r0 = e.r0 + p.rpos; w.rl = p.rlen; w.g0 = e.g0 + (i32)p.gpos; w.gl = p.glen; w.pad = 0;
-						if (p.glen == 0) w.kind = KB_W_INS;
-						else if (p.rlen == 0) w.kind = KB_W_DEL;
-						else if ((p.rlen == 1 && p.glen == 1) || p.simple) w.kind = KB_W_COPY;
-						else if (pm->pacbio && (p.rlen > 300 || p.glen > 300)) w.kind = KB_W_FRAG;
-						else w.kind = KB_W_NW;
-						st[sp++] = w;
-					}
-					ar->used = mark;
-					continue;
-				}
-				ar->used = mark;
+				raw = (KbSeg*)ar->alloc((u64)cap * sizeof(KbSeg));
+				if (ar->ovf) return 0;
+				cur = e; np = 0; dirty = 0;
+				return 2;
 			}
 			*piece = e;
-			return true;
+			return 1;
 		}
-		return false;
+		return 0;
+	}
+
+	// all lanes: does either side hold a character that is no base? (then the literal scan of kb_kmer_ids is replayed)
+	KB_HD void part_scan(int lane)
+	{
+		const u8* a = f1 + cur.r0; const u8* b = f2 + cur.g0; int bad = 0;
+		for (int i = lane; i < cur.rl; i += 32) if (kb_nt4(a[i]) > 3) bad = 1;
+		for (int i = lane; i < cur.gl; i += 32) if (kb_nt4(b[i]) > 3) bad = 1;
+		if (bad) dirty = 1;
+	}
+	// all lanes: 8-mer ids of both sides. Pure-base strings: id(p) is the 16-bit value of the 8 characters at p, for p <= len-8.
+	KB_HD void part_ids(int lane)
+	{
+		const u8* a = f1 + cur.r0; const u8* b = f2 + cur.g0;
+		if (dirty) { if (lane == 0) { kb_kmer_ids(cur.rl, a, w1); kb_kmer_ids(cur.gl, b, w2); } return; }
+		for (int p = lane; p < cur.rl; p += 32) { u32 id = KB_NOKMER; if (p + 8 <= cur.rl) { id = 0; for (int i = 0; i < 8; i++) id = (id << 2) | (u32)kb_nt4(a[p + i]); } w1[p] = id; }
+		for (int p = lane; p < cur.gl; p += 32) { u32 id = KB_NOKMER; if (p + 8 <= cur.gl) { id = 0; for (int i = 0; i < 8; i++) id = (id << 2) | (u32)kb_nt4(b[p + i]); } w2[p] = id; }
+	}
+	// all lanes: the exact-match runs of kb_kmer_pairs (min_len 8), one (position, diagonal) cell per lane and step, appended in
+	// arbitrary order (part_finish sorts them by a total order)
+	KB_HD void part_pairs(int lane)
+	{
+		const int n1 = cur.rl - 7, n2 = cur.gl - 7;
+		if (n1 <= 0 || n2 <= 0) return;
+		int dlo = -(n1 - 1), dhi = n2 - 1;
+		if (dlo < -(shift - 1)) dlo = -(shift - 1);
+		if (dhi > shift - 1) dhi = shift - 1;
+		const int nd = dhi - dlo + 1; if (nd <= 0) return;
+		const int total = n1 * nd;
+		for (int idx = lane; idx < total; idx += 32)
+		{
+			const int r = idx / nd, d = dlo + idx % nd, g = r + d;
+			if (g < 0 || g >= n2) continue;
+			const u32 id = w1[r];
+			if (id == KB_NOKMER || id != w2[g]) continue;
+			if (r > 0 && g > 0 && w1[r - 1] != KB_NOKMER && w1[r - 1] == w2[g - 1]) continue;   // not the start of its run
+			int run = 1;
+			while (r + run < n1 && g + run < n2 && w1[r + run] != KB_NOKMER && w1[r + run] == w2[g + run]) run++;
+			u32 slot = KB_ATOMIC_ADD(&np, 1u);
+			if ((int)slot < cap) { KbSeg sg; sg.simple = 1; sg.rpos = r; sg.gpos = (i64)g; sg.rlen = sg.glen = 8 + run - 1; raw[slot] = sg; }
+		}
+	}
+	// one lane: IdentifyNormalPairs on the runs; pushes the pieces (or hands the whole fragment to NW: returns true and sets *piece)
+	KB_HD bool part_finish(KbWork* piece)
+	{
+		const KbWork e = cur; const int rl = e.rl, gl = e.gl;
+		if ((int)np > cap) { ar->ovf = true; return false; }
+		int tot = 0; KbSeg* part = nullptr; const int n = (int)np;
+		if (n > 0)
+		{
+			kb_sort_segs<true>(raw, n);
+			part = (KbSeg*)ar->alloc((u64)(2 * n + 2) * sizeof(KbSeg));
+			i32* order = (i32*)ar->alloc((u64)n * 4);
+			if (ar->ovf) return false;
+			tot = kb_fill_pairs(rl, gl, raw, n, part, order);
+		}
+		if (tot > 0)
+		{
+			if (sp + tot > scap) { ar->ovf = true; return false; }
+			for (int i = tot - 1; i >= 0; i--)   // reversed, so that pops come out left to right
+			{
+				const KbSeg p = part[i];
+				if (p.rlen <= 0 && p.glen <= 0) continue;
+				KbWork w; w.r0 = e.r0 + p.rpos; w.rl = p.rlen; w.g0 = e.g0 + (i32)p.gpos; w.gl = p.glen; w.pad = 0;
+				if (p.glen == 0) w.kind = KB_W_INS;
+				else if (p.rlen == 0) w.kind = KB_W_DEL;
+				else if ((p.rlen == 1 && p.glen == 1) || p.simple) w.kind = KB_W_COPY;
+				else if (pm->pacbio && (p.rlen > 300 || p.glen > 300)) w.kind = KB_W_FRAG;
+				else w.kind = KB_W_NW;
+				st[sp++] = w;
+			}
+			ar->used = pmark;
+			return false;
+		}
+		ar->used = pmark;
+		*piece = e;
+		return true;
 	}
 };
 
@@ -611,9 +661,10 @@ KB_HD void kb_classify_segment(const KbIndexDev& ix, const KbParams& pm, const K
 		out->info = KB_SEG_ONE; out->aux = f1[0] == kb_ref_char(ix, sp.gpos) ? 1u : 0u;
 		return;
 	}
-	u32 id = KB_ATOMIC_ADD(&bt.counters[9], 1u);
+	// one 64-bit atomic reserves the job id (high word = counters[11]) and its slice of the run arena (low word = counters[10])
 	u32 need = (u32)(sp.rlen + sp.glen + 2);
-	u32 ro = KB_ATOMIC_ADD(&bt.counters[10], need);
+	unsigned long long old = KB_ATOMIC_ADD(reinterpret_cast<unsigned long long*>(bt.counters + 10), (1ull << 32) | (unsigned long long)need);
+	u32 id = (u32)(old >> 32), ro = (u32)old;
 	if (id >= bt.cap_jobs) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_JOBS); return; }
 	if ((u64)ro + need > (u64)bt.cap_runs) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_RUNS); return; }
 	KbJob jb; jb.gpos = sp.gpos; jb.read = (u32)r; jb.rpos = sp.rpos; jb.rlen = sp.rlen; jb.glen = sp.glen; jb.run_off = ro; jb.nruns = 0; jb.ident = 0; jb.aligned = 0;
@@ -622,34 +673,46 @@ KB_HD void kb_classify_segment(const KbIndexDev& ix, const KbParams& pm, const K
 }
 
 // phase A
-KB_HD void kb_segments_read(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int r, KbArena& ar)
+#define KB_SEG_FAST 8   // candidates with at most this many seeds are expanded in local memory instead of the HBM arena
+KB_HD void kb_segments_cand(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int r, const u8* seq, const KbPk* rd, int rlen,
+                            u32 ci, const KbCand& c, KbSeg* in, KbSeg* sv, i32* order)
+{
+	const int ns = c.nseg;
+	for (int k = 0; k < ns; k++) in[k] = bt.segs[c.seg_start + k];
+	int n = kb_fill_pairs(rlen, -1, in, ns, sv, order);
+	if (!kb_same_chromosome(ix, sv, n)) return;
+	u32 off = KB_ATOMIC_ADD(&bt.counters[8], (u32)n);
+	if ((u64)off + (u64)n > (u64)bt.cap_segx) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SEGX); return; }
+	bt.cseg_off[ci] = off; bt.cseg_n[ci] = n;
+	for (int j = 0; j < n; j++) kb_classify_segment(ix, pm, bt, r, seq, rd, sv[j], j, n, &bt.segx[off + j]);
+}
+
+// ar == nullptr: local memory only; returns false (nothing written) when a candidate needs the arena
+KB_HD bool kb_segments_read(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int r, KbArena* ar)
 {
 	KbCand* cv = bt.cands + bt.cand_off[r];
 	int ncan = bt.n_cands[r];
+	if (ar == nullptr) for (int i = 0; i < ncan; i++) if (cv[i].score != 0 && cv[i].nseg > KB_SEG_FAST) return false;
 	const u8* seq = bt.seq + bt.seq_off[r]; int rlen = (int)(bt.seq_off[r + 1] - bt.seq_off[r]);
 	const KbPk* rd = kb_pk_read(bt, r);
+	KbSeg in_l[KB_SEG_FAST], sv_l[2 * KB_SEG_FAST + 2]; i32 order_l[KB_SEG_FAST];
 	for (int i = 0; i < ncan; i++)
 	{
 		u32 ci = bt.cand_off[r] + (u32)i;
 		bt.cseg_n[ci] = -1; bt.cseg_off[ci] = 0;
-		if (cv[i].score == 0) continue;
-		u64 mark = ar.used;
-		int ns = cv[i].nseg;
-		KbSeg* in = (KbSeg*)ar.alloc((u64)(ns > 0 ? ns : 1) * sizeof(KbSeg));
-		KbSeg* sv = (KbSeg*)ar.alloc((u64)(2 * ns + 2) * sizeof(KbSeg));
-		i32* order = (i32*)ar.alloc((u64)(ns > 0 ? ns : 1) * 4);
-		if (ar.ovf) return;
-		for (int k = 0; k < ns; k++) in[k] = bt.segs[cv[i].seg_start + k];
-		int n = kb_fill_pairs(rlen, -1, in, ns, sv, order);
-		if (kb_same_chromosome(ix, sv, n))
-		{
-			u32 off = KB_ATOMIC_ADD(&bt.counters[8], (u32)n);
-			if ((u64)off + (u64)n > (u64)bt.cap_segx) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SEGX); ar.used = mark; return; }
-			bt.cseg_off[ci] = off; bt.cseg_n[ci] = n;
-			for (int j = 0; j < n; j++) kb_classify_segment(ix, pm, bt, r, seq, rd, sv[j], j, n, &bt.segx[off + j]);
-		}
-		ar.used = mark;
+		const KbCand c = cv[i];
+		if (c.score == 0) continue;
+		if (c.nseg <= KB_SEG_FAST) { kb_segments_cand(ix, pm, bt, r, seq, rd, rlen, ci, c, in_l, sv_l, order_l); continue; }
+		u64 mark = ar->used;
+		int ns = c.nseg;
+		KbSeg* in = (KbSeg*)ar->alloc((u64)ns * sizeof(KbSeg));
+		KbSeg* sv = (KbSeg*)ar->alloc((u64)(2 * ns + 2) * sizeof(KbSeg));
+		i32* order = (i32*)ar->alloc((u64)ns * 4);
+		if (ar->ovf) return true;
+		kb_segments_cand(ix, pm, bt, r, seq, rd, rlen, ci, c, in, sv, order);
+		ar->used = mark;
 	}
+	return true;
 }
 
 // phase B, warp per job. State shared by the lanes of the warp (shared memory on the GPU):
@@ -682,19 +745,29 @@ KB_HD void kb_aw_fetch(const KbIndexDev& ix, const KbBatchDev& bt, KbAlignWarp& 
 	for (int i = t; i < w.glen; i += 32) w.f2[i] = kb_ref_char(ix, g + i);
 	for (int i = t; i < w.rlen; i += 32) w.f1[i] = w.f1g[i];
 }
-// lane 0: advance to the next piece that needs NW and set the DP up
+// lane 0: the DP of w.piece
+KB_HD void kb_aw_setup_piece(KbAlignWarp& w)
+{
+	w.calls++; w.cells += (unsigned long long)w.piece.rl * (unsigned long long)w.piece.gl;
+	if (kb_nww_setup(w.nw, w.fast, w.ar, w.f1 + w.piece.r0, w.piece.rl, w.f2 + w.piece.g0, w.piece.gl)) { w.has_piece = 1; w.more_strips = 1; }
+}
+// lane 0: advance to the next piece that needs NW and set the DP up (has_piece = 1), or to a fragment that all lanes
+// partition first (has_piece = 2, followed by kb_aw_part_done), or to the end of the job (has_piece = 0)
 KB_HD void kb_aw_next(KbAlignWarp& w)
 {
 	w.has_piece = 0;
 	if (!w.ok) return;
-	bool got;
-	if (w.whole) { got = !w.whole_done; w.whole_done = 1; w.piece.r0 = 0; w.piece.rl = w.rlen; w.piece.g0 = 0; w.piece.gl = w.glen; }
+	int got;
+	if (w.whole) { got = w.whole_done ? 0 : 1; w.whole_done = 1; w.piece.r0 = 0; w.piece.rl = w.rlen; w.piece.g0 = 0; w.piece.gl = w.glen; }
 	else got = w.it.next(&w.piece);
-	if (got)
-	{
-		w.calls++; w.cells += (unsigned long long)w.piece.rl * (unsigned long long)w.piece.gl;
-		if (kb_nww_setup(w.nw, w.fast, w.ar, w.f1 + w.piece.r0, w.piece.rl, w.f2 + w.piece.g0, w.piece.gl)) { w.has_piece = 1; w.more_strips = 1; }
-	}
+	if (got == 2) w.has_piece = 2;
+	else if (got == 1) kb_aw_setup_piece(w);
+}
+// lane 0, after the lanes partitioned a fragment: has_piece = 1 when the fragment turned out to be one NW problem, else 3 (= call kb_aw_next again)
+KB_HD void kb_aw_part_done(KbAlignWarp& w)
+{
+	w.has_piece = 3;
+	if (w.it.part_finish(&w.piece)) { w.has_piece = 0; kb_aw_setup_piece(w); if (w.has_piece == 0) w.has_piece = 3; }
 }
 // lane 0: close the job
 KB_HD void kb_aw_end(const KbBatchDev& bt, KbAlignWarp& w)
@@ -778,8 +851,72 @@ KB_HD void kb_locate_report(const KbIndexDev& ix, const KbBatchDev& bt, bool fir
 	}
 }
 
+// cigar elements and score of one candidate from its classified segments (GenMappingReport :648-723). No side effects
+// besides cg / the outputs, so a candidate whose elements overflow the small local buffer is simply redone with a large one.
+KB_HD void kb_assemble_cigar(const KbParams& pm, const KbBatchDev& bt, const KbSegX* sx, int n, KbCigar& cg, int* aln_out, i64* gf_out, i64* ge_out)
+{
+	int aln = 0;
+	i64 g_first = n > 0 ? sx[0].s.gpos : 0, g_end = n > 0 ? sx[n - 1].s.gpos + sx[n - 1].s.glen - 1 : 0;
+	for (int j = 0; j < n; j++)
+	{
+		const KbSegX& x = sx[j]; const KbSeg& sp = x.s;
+		if (x.info == KB_SEG_SKIP) continue;
+		if (x.info == KB_SEG_SIMPLE) { cg.push(sp.rlen, KB_OP_M); aln += sp.rlen; continue; }
+		if (j == 0)   // ProcessHeadSequencePair :292 and AlignmentCandidates.cpp:669-687
+		{
+			int s = 0; i64 gpos = sp.gpos;
+			if (x.info == KB_SEG_SOFT) cg.push(sp.rlen, KB_OP_S);
+			else if (x.info == KB_SEG_QUICK) { cg.push(sp.rlen, KB_OP_M); s = (int)x.aux; }
+			else
+			{
+				KbAlnView v = kb_view(bt, x);
+				if (!kb_quality_ok(v)) cg.push(sp.rlen, KB_OP_S);
+				else
+				{
+					int f = 0;
+					if (f < v.n && (kb_view_run(v, f) & 3) == KB_RUN_D) { gpos += (int)(kb_view_run(v, f) >> 2); f++; }
+					if (f < v.n && (kb_view_run(v, f) & 3) == KB_RUN_I) { cg.push((int)(kb_view_run(v, f) >> 2), KB_OP_S); f++; }
+					kb_view_push(v, f, v.n, cg); s = v.ident;
+				}
+			}
+			aln += s;
+			g_first = s == 0 ? sx[1].s.gpos : gpos;
+		}
+		else if (j == n - 1)   // ProcessTailSequencePair :344 and AlignmentCandidates.cpp:688-706
+		{
+			int s = 0, glen = sp.glen;
+			if (x.info == KB_SEG_SOFT) cg.push(sp.rlen, KB_OP_S);
+			else if (x.info == KB_SEG_QUICK) { cg.push(sp.rlen, KB_OP_M); s = (int)x.aux; }
+			else
+			{
+				KbAlnView v = kb_view(bt, x);
+				if (!kb_quality_ok(v)) cg.push(sp.rlen, KB_OP_S);
+				else
+				{
+					int last = v.n, clip = 0;
+					if (last > 0 && (kb_view_run(v, last - 1) & 3) == KB_RUN_D) { glen -= (int)(kb_view_run(v, last - 1) >> 2); last--; }
+					if (last > 0 && (kb_view_run(v, last - 1) & 3) == KB_RUN_I) { clip = (int)(kb_view_run(v, last - 1) >> 2); last--; }
+					kb_view_push(v, 0, last, cg); s = v.ident;
+					if (clip > 0) cg.push(clip, KB_OP_S);
+				}
+			}
+			aln += s;
+			g_end = s == 0 ? sx[j - 1].s.gpos + sx[j - 1].s.glen - 1 : sp.gpos + glen - 1;
+		}
+		else   // ProcessNormalSequencePair :225
+		{
+			if (x.info == KB_SEG_GAP) { if (sp.rlen > 0) cg.push(sp.rlen, KB_OP_I); else cg.push(sp.glen, KB_OP_D); }
+			else if (x.info == KB_SEG_QUICK) { cg.push(sp.rlen, KB_OP_M); aln += (int)x.aux; }
+			else { KbAlnView v = kb_view(bt, x); kb_view_push(v, 0, v.n, cg); aln += v.ident; }
+		}
+	}
+	*aln_out = aln; *gf_out = g_first; *ge_out = g_end;
+}
+
 // phase C: GenMappingReport for one read from the stored segments and job results. cands/reports are this read's slices.
-KB_HD void kb_assemble_read(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int r, KbArena& ar)
+#define KB_CIG_FAST 24   // cigar elements kept in local memory before the HBM arena is used
+// ar == nullptr: local memory only; returns false when a candidate's cigar does not fit (the read is then redone with an arena)
+KB_HD bool kb_assemble_read(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int r, KbArena* ar)
 {
 	KbReadRes& rd = bt.res[r];
 	KbCand* cv = bt.cands + bt.cand_off[r];
@@ -787,83 +924,39 @@ KB_HD void kb_assemble_read(const KbIndexDev& ix, const KbParams& pm, const KbBa
 	int ncan = bt.n_cands[r];
 	bool first = pm.paired ? ((r & 1) == 0) : true;
 	int rlen = (int)(bt.seq_off[r + 1] - bt.seq_off[r]);
-	rd.score = 0; rd.sub = 0; rd.best = 0; rd.mapq = 0; rd.rep_off = bt.cand_off[r];
+	int score = 0, sub = 0, best = 0, best_chr = 0;
+	rd.mapq = 0; rd.rep_off = bt.cand_off[r];
 	if (ncan == 0)
 	{
-		rd.ncan = 1;
+		rd.ncan = 1; rd.score = 0; rd.sub = 0; rd.best = 0;
 		KbReport z; z.pos = 0; z.aln = 0; z.flag = 0; z.mate = -1; z.chr = 0; z.cig_off = 0; z.cig_len = 0; z.fwd = 1; z.pad = 0;
 		rep[0] = z;
-		return;
+		return true;
 	}
 	rd.ncan = ncan;
+	u32 cgl[KB_CIG_FAST];
 	for (int i = 0; i < ncan; i++)
 	{
-		KbReport rp; rp.pos = 0; rp.aln = 0; rp.flag = 0; rp.mate = cv[i].mate; rp.chr = 0; rp.cig_off = 0; rp.cig_len = 0; rp.fwd = 1; rp.pad = 0;
-		rep[i] = rp;
-		if (cv[i].score == 0) continue;
-		if (pm.pacbio && rd.score > 0) { rd.sub = rd.score; continue; }
+		const KbCand c = cv[i];
+		KbReport rp; rp.pos = 0; rp.aln = 0; rp.flag = 0; rp.mate = c.mate; rp.chr = 0; rp.cig_off = 0; rp.cig_len = 0; rp.fwd = 1; rp.pad = 0;
+		if (c.score == 0) { rep[i] = rp; continue; }
+		if (pm.pacbio && score > 0) { sub = score; rep[i] = rp; continue; }
 		u32 ci = bt.cand_off[r] + (u32)i;
 		int n = bt.cseg_n[ci];
-		if (n < 0) continue;                       // CheckCoordinateValidity failed
+		if (n < 0) { rep[i] = rp; continue; }      // CheckCoordinateValidity failed
 		const KbSegX* sx = bt.segx + bt.cseg_off[ci];
-		u64 mark = ar.used;
-		KbCigar cg; cg.n = 0; cg.ovf = false; cg.cap = 3 * rlen + 2 * n + 64; cg.e = (u32*)ar.alloc((u64)cg.cap * 4);
-		if (ar.ovf) break;
-		i64 g_first = n > 0 ? sx[0].s.gpos : 0, g_end = n > 0 ? sx[n - 1].s.gpos + sx[n - 1].s.glen - 1 : 0;
-		for (int j = 0; j < n; j++)
+		u64 mark = ar ? ar->used : 0;
+		KbCigar cg; cg.n = 0; cg.ovf = false; cg.cap = KB_CIG_FAST; cg.e = cgl;
+		i64 g_first, g_end;
+		kb_assemble_cigar(pm, bt, sx, n, cg, &rp.aln, &g_first, &g_end);
+		if (cg.ovf)
 		{
-			const KbSegX& x = sx[j]; const KbSeg& sp = x.s;
-			if (x.info == KB_SEG_SKIP) continue;
-			if (x.info == KB_SEG_SIMPLE) { cg.push(sp.rlen, KB_OP_M); rp.aln += sp.rlen; continue; }
-			if (j == 0)   // ProcessHeadSequencePair :292 and AlignmentCandidates.cpp:669-687
-			{
-				int s = 0; i64 gpos = sp.gpos;
-				if (x.info == KB_SEG_SOFT) cg.push(sp.rlen, KB_OP_S);
-				else if (x.info == KB_SEG_QUICK) { cg.push(sp.rlen, KB_OP_M); s = (int)x.aux; }
-				else
-				{
-					KbAlnView v = kb_view(bt, x);
-					if (!kb_quality_ok(v)) cg.push(sp.rlen, KB_OP_S);
-					else
-					{
-						int f = 0;
-						if (f < v.n && (kb_view_run(v, f) & 3) == KB_RUN_D) { gpos += (int)(kb_view_run(v, f) >> 2); f++; }
-						if (f < v.n && (kb_view_run(v, f) & 3) == KB_RUN_I) { cg.push((int)(kb_view_run(v, f) >> 2), KB_OP_S); f++; }
-						kb_view_push(v, f, v.n, cg); s = v.ident;
-					}
-				}
-				rp.aln += s;
-				g_first = s == 0 ? sx[1].s.gpos : gpos;
-			}
-			else if (j == n - 1)   // ProcessTailSequencePair :344 and AlignmentCandidates.cpp:688-706
-			{
-				int s = 0, glen = sp.glen;
-				if (x.info == KB_SEG_SOFT) cg.push(sp.rlen, KB_OP_S);
-				else if (x.info == KB_SEG_QUICK) { cg.push(sp.rlen, KB_OP_M); s = (int)x.aux; }
-				else
-				{
-					KbAlnView v = kb_view(bt, x);
-					if (!kb_quality_ok(v)) cg.push(sp.rlen, KB_OP_S);
-					else
-					{
-						int last = v.n, clip = 0;
-						if (last > 0 && (kb_view_run(v, last - 1) & 3) == KB_RUN_D) { glen -= (int)(kb_view_run(v, last - 1) >> 2); last--; }
-						if (last > 0 && (kb_view_run(v, last - 1) & 3) == KB_RUN_I) { clip = (int)(kb_view_run(v, last - 1) >> 2); last--; }
-						kb_view_push(v, 0, last, cg); s = v.ident;
-						if (clip > 0) cg.push(clip, KB_OP_S);
-					}
-				}
-				rp.aln += s;
-				g_end = s == 0 ? sx[j - 1].s.gpos + sx[j - 1].s.glen - 1 : sp.gpos + glen - 1;
-			}
-			else   // ProcessNormalSequencePair :225
-			{
-				if (x.info == KB_SEG_GAP) { if (sp.rlen > 0) cg.push(sp.rlen, KB_OP_I); else cg.push(sp.glen, KB_OP_D); }
-				else if (x.info == KB_SEG_QUICK) { cg.push(sp.rlen, KB_OP_M); rp.aln += (int)x.aux; }
-				else { KbAlnView v = kb_view(bt, x); kb_view_push(v, 0, v.n, cg); rp.aln += v.ident; }
-			}
+			if (ar == nullptr) return false;
+			cg.n = 0; cg.ovf = false; cg.cap = 3 * rlen + 2 * n + 64; cg.e = (u32*)ar->alloc((u64)cg.cap * 4);
+			if (ar->ovf) break;
+			kb_assemble_cigar(pm, bt, sx, n, cg, &rp.aln, &g_first, &g_end);
+			if (cg.ovf) ar->ovf = true;
 		}
-		if (cg.ovf) ar.ovf = true;
 		bool dead = false;
 		if (!pm.pacbio && cg.n > 1)
 		{
@@ -875,17 +968,18 @@ KB_HD void kb_assemble_read(const KbIndexDev& ix, const KbParams& pm, const KbBa
 		{
 			if (cg.n == 0) rp.aln = 0;
 			else { kb_locate_report(ix, bt, first, g_first, g_end, cg, rp); if (rp.pos <= 0) rp.aln = 0; }
-			if (rp.aln > rd.score) { rd.best = i; rd.sub = rd.score; rd.score = rp.aln; }
-			else if (rp.aln == rd.score)
+			if (rp.aln > score) { best = i; best_chr = rp.chr; sub = score; score = rp.aln; }
+			else if (rp.aln == score)
 			{
-				rd.sub = rd.score;
-				if (!pm.multihit && ix.chr_len[rp.chr] > ix.chr_len[rep[rd.best].chr]) rd.best = i;
+				sub = score;
+				if (!pm.multihit && ix.chr_len[rp.chr] > ix.chr_len[best_chr]) { best = i; best_chr = rp.chr; }
 			}
 		}
 		rep[i] = rp;
-		ar.used = mark;
-		if (ar.ovf) break;
+		if (ar) { ar->used = mark; if (ar->ovf) break; }
 	}
+	rd.score = score; rd.sub = sub; rd.best = best;
+	return true;
 }
 
 #endif

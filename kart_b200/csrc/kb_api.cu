@@ -160,7 +160,8 @@ static void k_rescue(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulation: 
 	}
 }
 #endif
-__global__ void __launch_bounds__(KB_BLOCK) k_segments(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_segments(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
+__global__ void __launch_bounds__(KB_BLOCK) k_segments(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_segments(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x); }
+__global__ void __launch_bounds__(KB_BLOCK) k_segments_slow(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_segments_slow(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
 // phase B: one warp per alignment job (kb_align.cuh "warp-per-fragment")
 #ifndef KB_EMUL
 __global__ void __launch_bounds__(KB_BLOCK) k_align(KbIndexDev ix, KbParams pm, KbBatchDev bt)
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(KB_BLOCK) k_align(KbIndexDev ix, KbParams pm, 
 	const u32 gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
 	if ((int)(gwarp * 32) >= bt.scratch_threads) return;
 	KbAlignWarp& w = sw[wib];
-	const u32 njobs = bt.counters[9];
+	const u32 njobs = bt.counters[11];
 	if (lane == 0) { w.ar.base = bt.scratch + (u64)gwarp * 32ull * bt.scratch_per_thread; w.ar.cap = 32ull * bt.scratch_per_thread; w.fast.base = pool[wib]; w.fast.cap = KB_ALIGN_POOL; w.fast.ovf = false; w.cells = 0; w.calls = 0; }
 	__syncwarp();
 	for (u32 id = gwarp; id < njobs; id += nwarps)
@@ -185,6 +186,15 @@ __global__ void __launch_bounds__(KB_BLOCK) k_align(KbIndexDev ix, KbParams pm, 
 		{
 			if (lane == 0) kb_aw_next(w);
 			__syncwarp();
+			if (w.has_piece == 2)
+			{
+				w.it.part_scan(lane); __syncwarp();
+				w.it.part_ids(lane); __syncwarp();
+				w.it.part_pairs(lane); __syncwarp();
+				if (lane == 0) kb_aw_part_done(w);
+				__syncwarp();
+				if (w.has_piece == 3) continue;
+			}
 			if (!w.has_piece) break;
 			kb_nww_init_rows(w.nw, lane);
 			__syncwarp();
@@ -214,7 +224,7 @@ static void k_align(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulation: t
 	if (bt.counters[3]) return;
 	static KbAlignWarp w; KbNwLane L[32]; static u8 pool[KB_ALIGN_POOL];
 	w.ar.base = bt.scratch; w.ar.cap = 32ull * bt.scratch_per_thread; w.fast.base = pool; w.fast.cap = KB_ALIGN_POOL; w.fast.ovf = false; w.cells = 0; w.calls = 0;
-	const u32 njobs = bt.counters[9];
+	const u32 njobs = bt.counters[11];
 	for (u32 id = 0; id < njobs; id++)
 	{
 		kb_aw_begin(pm, bt, w, id);
@@ -222,6 +232,14 @@ static void k_align(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulation: t
 		while (true)
 		{
 			kb_aw_next(w);
+			if (w.has_piece == 2)
+			{
+				for (int t = 0; t < 32; t++) w.it.part_scan(t);
+				for (int t = 31; t >= 0; t--) w.it.part_ids(t);
+				for (int t = 31; t >= 0; t--) w.it.part_pairs(t);
+				kb_aw_part_done(w);
+				if (w.has_piece == 3) continue;
+			}
 			if (!w.has_piece) break;
 			for (int t = 0; t < 32; t++) kb_nww_init_rows(w.nw, t);
 			while (true)
@@ -239,7 +257,8 @@ static void k_align(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulation: t
 	bt.work[3] += w.cells; bt.work[4] += w.calls;
 }
 #endif
-__global__ void __launch_bounds__(KB_BLOCK) k_assemble(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_assemble(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
+__global__ void __launch_bounds__(KB_BLOCK) k_assemble(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_assemble(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x); }
+__global__ void __launch_bounds__(KB_BLOCK) k_assemble_slow(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_assemble_slow(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
 __global__ void __launch_bounds__(KB_BLOCK) k_finalize(KbIndexDev ix, KbParams pm, KbBatchDev bt, kb_aln_t* aln) { kb_stage_finalize(ix, pm, bt, aln, blockIdx.x * blockDim.x + threadIdx.x); }
 
 // ------------------------------------------------------------------------------------------------
@@ -261,7 +280,7 @@ struct kb_ctx
 	int64_t l_pac = 0;
 	// batch
 	KbBatchDev bt; bool staged = false, ran = false; int n_reads = 0; size_t seq_bytes = 0;
-	DevBuf<u8> seq, scratch; DevBuf<u64> seq_off; DevBuf<unsigned long long> work; DevBuf<i32> est, n_hits, n_seeds, n_cands, cand_cap, rescue; DevBuf<u32> seed_off, cand_off, cigar, counters, cseg_off, runs; DevBuf<i32> cseg_n; DevBuf<KbSegX> segx; DevBuf<KbJob> jobs;
+	DevBuf<u8> seq, scratch; DevBuf<u64> seq_off; DevBuf<unsigned long long> work; DevBuf<i32> est, n_hits, n_seeds, n_cands, cand_cap, rescue, slow1, slow2; DevBuf<u32> seed_off, cand_off, cigar, counters, cseg_off, runs; DevBuf<i32> cseg_n; DevBuf<KbSegX> segx; DevBuf<KbJob> jobs;
 	DevBuf<KbHit> hits; DevBuf<KbSeg> segs; DevBuf<KbCand> cands; DevBuf<KbReport> reports; DevBuf<KbReadRes> res; DevBuf<KbPairStat> pstat; DevBuf<kb_aln_t> aln;
 	size_t cap_segs = 0, cap_cands = 0, cap_cigar = 0, cap_segx = 0, cap_jobs = 0, cap_runs = 0, scratch_per_thread = 0; int scratch_threads = 0; int max_rlen = 0;
 	double seg_factor = 32, cigar_factor = 8, scratch_factor = 1, segx_factor = 8, job_factor = 4, run_factor = 96;
@@ -322,7 +341,7 @@ void kb_destroy(kb_ctx_t* ctx)
 	cudaStreamSynchronize(ctx->stream);
 	ctx->occ.release(); ctx->ktab.release(); ctx->ref64.release(); ctx->pk.release(); ctx->sa.release(); ctx->sa_full.release(); ctx->pac.release(); ctx->lut.release(); ctx->chr64.release(); ctx->chr32.release();
 	ctx->seq.release(); ctx->scratch.release(); ctx->seq_off.release(); ctx->work.release(); ctx->est.release(); ctx->n_hits.release(); ctx->n_seeds.release();
-	ctx->n_cands.release(); ctx->cand_cap.release(); ctx->rescue.release(); ctx->seed_off.release(); ctx->cand_off.release(); ctx->cigar.release(); ctx->counters.release();
+	ctx->n_cands.release(); ctx->cand_cap.release(); ctx->rescue.release(); ctx->slow1.release(); ctx->slow2.release(); ctx->seed_off.release(); ctx->cand_off.release(); ctx->cigar.release(); ctx->counters.release();
 	ctx->cseg_off.release(); ctx->runs.release(); ctx->cseg_n.release(); ctx->segx.release(); ctx->jobs.release(); ctx->hits.release(); ctx->segs.release(); ctx->cands.release(); ctx->reports.release(); ctx->res.release(); ctx->pstat.release(); ctx->aln.release();
 	for (int i = 0; i < 10; i++) cudaEventDestroy(ctx->ev[i]);
 	cudaStreamDestroy(ctx->stream);
@@ -459,11 +478,11 @@ static int alloc_batch(kb_ctx* ctx)
 	CK(ctx->res.ensure(n)); CK(ctx->pstat.ensure(n / 2 + 1)); CK(ctx->aln.ensure(n)); CK(ctx->cigar.ensure(ctx->cap_cigar));
 	CK(ctx->segx.ensure(ctx->cap_segx)); CK(ctx->jobs.ensure(ctx->cap_jobs)); CK(ctx->runs.ensure(ctx->cap_runs)); CK(ctx->cseg_off.ensure(ctx->cap_cands)); CK(ctx->cseg_n.ensure(ctx->cap_cands));
 	CK(ctx->counters.ensure(16)); CK(ctx->work.ensure(8)); CK(ctx->scratch.ensure(per * threads));
-	CK(ctx->pk.ensure((ctx->seq_bytes >> 5) + n + 4));
+	CK(ctx->pk.ensure((ctx->seq_bytes >> 5) + n + 4)); CK(ctx->slow1.ensure(n + 1)); CK(ctx->slow2.ensure(n + 1));
 	bt.n_reads = ctx->n_reads; bt.seq = ctx->seq.p; bt.seq_off = ctx->seq_off.p; bt.est = ctx->est.p; bt.pk = ctx->pk.p; bt.pk_wpr = (L + 31) / 32;
 	bt.hits = ctx->hits.p; bt.max_hits = max_hits; bt.n_hits = ctx->n_hits.p; bt.n_seeds = ctx->n_seeds.p; bt.seed_off = ctx->seed_off.p;
 	bt.segs = ctx->segs.p; bt.cap_segs = (u32)ctx->cap_segs; bt.cands = ctx->cands.p; bt.cap_cands = (u32)ctx->cap_cands; bt.n_cands = ctx->n_cands.p;
-	bt.cand_off = ctx->cand_off.p; bt.cand_cap = ctx->cand_cap.p; bt.rescue_list = ctx->rescue.p; bt.reports = ctx->reports.p; bt.res = ctx->res.p; bt.pstat = ctx->pstat.p;
+	bt.cand_off = ctx->cand_off.p; bt.cand_cap = ctx->cand_cap.p; bt.rescue_list = ctx->rescue.p; bt.slow_list = ctx->slow1.p; bt.slow_list2 = ctx->slow2.p; bt.reports = ctx->reports.p; bt.res = ctx->res.p; bt.pstat = ctx->pstat.p;
 	bt.segx = ctx->segx.p; bt.cap_segx = (u32)ctx->cap_segx; bt.cseg_off = ctx->cseg_off.p; bt.cseg_n = ctx->cseg_n.p; bt.jobs = ctx->jobs.p; bt.cap_jobs = (u32)ctx->cap_jobs; bt.runs = ctx->runs.p; bt.cap_runs = (u32)ctx->cap_runs;
 	bt.cigar = ctx->cigar.p; bt.cap_cigar = (u32)ctx->cap_cigar; bt.scratch = ctx->scratch.p; bt.scratch_per_thread = per; bt.scratch_threads = (int)threads;
 	bt.max_rlen = L; bt.nw_max_m = 0; bt.nw_max_n = 0; bt.seg_cap = 0; bt.kmer_cap = 0; bt.counters = ctx->counters.p; bt.work = ctx->work.p;
@@ -513,11 +532,13 @@ static int launch_pipeline(kb_ctx* ctx)
 	CK(cudaEventRecord(ctx->ev[3], s));
 	if (pm.paired) { KB_LAUNCH(k_rescue, g_scr, KB_BLOCK, s, ix, pm, bt); ctx->launches++; }
 	CK(cudaEventRecord(ctx->ev[4], s));
-	KB_LAUNCH(k_segments, g_scr, KB_BLOCK, s, ix, pm, bt); ctx->launches++;
+	KB_LAUNCH(k_segments, g_reads, KB_BLOCK, s, ix, pm, bt); ctx->launches++;
+	KB_LAUNCH(k_segments_slow, g_scr, KB_BLOCK, s, ix, pm, bt); ctx->launches++;
 	CK(cudaEventRecord(ctx->ev[5], s));
 	KB_LAUNCH(k_align, g_scr, KB_BLOCK, s, ix, pm, bt); ctx->launches++;
 	CK(cudaEventRecord(ctx->ev[6], s));
-	KB_LAUNCH(k_assemble, g_scr, KB_BLOCK, s, ix, pm, bt); ctx->launches++;
+	KB_LAUNCH(k_assemble, g_reads, KB_BLOCK, s, ix, pm, bt); ctx->launches++;
+	KB_LAUNCH(k_assemble_slow, g_scr, KB_BLOCK, s, ix, pm, bt); ctx->launches++;
 	CK(cudaEventRecord(ctx->ev[7], s));
 	KB_LAUNCH(k_finalize, g_items, KB_BLOCK, s, ix, pm, bt, ctx->aln.p); ctx->launches++;
 	CK(cudaEventRecord(ctx->ev[8], s));

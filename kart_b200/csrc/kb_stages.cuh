@@ -79,30 +79,45 @@ KB_HD void kb_stage_cand_pacbio(const KbIndexDev& ix, const KbParams& pm, const 
 	}
 }
 
-// phase A of the report stage: segments of every surviving candidate (grid-stride, private arena)
-KB_HD void kb_stage_segments(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int tid, int nth)
+// phase A of the report stage: segments of every surviving candidate. One thread per read, local memory only; reads with a
+// candidate of more than KB_SEG_FAST seeds go to the slow list and are done by the arena version (grid-stride, private arena)
+KB_HD void kb_stage_segments(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int r)
+{
+	if (r >= bt.n_reads) return;
+	if (bt.counters[3]) return;
+	if (!kb_segments_read(ix, pm, bt, r, nullptr)) { u32 slot = KB_ATOMIC_ADD(&bt.counters[12], 1u); bt.slow_list[slot] = r; }
+}
+KB_HD void kb_stage_segments_slow(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int tid, int nth)
 {
 	if (tid >= bt.scratch_threads) return;
 	if (bt.counters[3]) return;
 	KbArena ar = kb_thread_arena(bt, tid);
-	for (int r = tid; r < bt.n_reads; r += nth)
+	const int count = (int)bt.counters[12];
+	for (int k = tid; k < count; k += nth)
 	{
 		ar.used = 0;
-		kb_segments_read(ix, pm, bt, r, ar);
+		kb_segments_read(ix, pm, bt, bt.slow_list[k], &ar);
 		if (ar.ovf) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SCRATCH); return; }
 	}
 }
 
-// phase C: reports
-KB_HD void kb_stage_assemble(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int tid, int nth)
+// phase C: reports; same split (a cigar of more than KB_CIG_FAST elements sends the read to the arena version)
+KB_HD void kb_stage_assemble(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int r)
+{
+	if (r >= bt.n_reads) return;
+	if (bt.counters[3]) return;
+	if (!kb_assemble_read(ix, pm, bt, r, nullptr)) { u32 slot = KB_ATOMIC_ADD(&bt.counters[13], 1u); bt.slow_list2[slot] = r; }
+}
+KB_HD void kb_stage_assemble_slow(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int tid, int nth)
 {
 	if (tid >= bt.scratch_threads) return;
 	if (bt.counters[3]) return;
 	KbArena ar = kb_thread_arena(bt, tid);
-	for (int r = tid; r < bt.n_reads; r += nth)
+	const int count = (int)bt.counters[13];
+	for (int k = tid; k < count; k += nth)
 	{
 		ar.used = 0;
-		kb_assemble_read(ix, pm, bt, r, ar);
+		kb_assemble_read(ix, pm, bt, bt.slow_list2[k], &ar);
 		if (ar.ovf) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SCRATCH); return; }
 	}
 }

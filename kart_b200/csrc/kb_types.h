@@ -100,6 +100,7 @@ struct KbBatchDev
 	// stage 2
 	KbCand* cands; u32 cap_cands; i32* n_cands; u32* cand_off; i32* cand_cap;
 	i32* rescue_list;                   // pair ids that need rescue
+	i32* slow_list; i32* slow_list2;    // reads whose segments / reports need the HBM arena (counters[12], counters[13])
 	// stage 3: segments of the surviving candidates, alignment jobs, run arena
 	KbSegX* segx; u32 cap_segx; u32* cseg_off; i32* cseg_n;   // cseg_* indexed like cands (cseg_n < 0: candidate dropped)
 	KbJob* jobs; u32 cap_jobs; u32* runs; u32 cap_runs;
@@ -113,7 +114,7 @@ struct KbBatchDev
 	i32 max_rlen;                       // longest read in the batch
 	i32 nw_max_m, nw_max_n, seg_cap, kmer_cap;
 	// counters: [0] seeds cursor [1] cands cursor [2] cigar cursor [3] status bits [4] rescue count [5] max seeds/read
-	//           [6] nw calls [7] rescue attempts [8] segx cursor [9] job cursor [10] run cursor ; 64-bit: work[0] extension steps, work[1] occ blocks, work[2] LF steps, work[3] NW cells
+	//           [6] nw calls [7] rescue attempts [8] segx cursor [10] run cursor + [11] job cursor (one u64) ; 64-bit: work[0] extension steps, work[1] occ blocks, work[2] LF steps, work[3] NW cells
 	u32* counters;
 	unsigned long long* work;
 };
