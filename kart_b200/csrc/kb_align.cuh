@@ -839,7 +839,7 @@ KB_HD void kb_locate_report(const KbIndexDev& ix, const KbBatchDev& bt, bool fir
 		int prev = -1;
 		for (int k = 0; k < cg.n; k++) { int op = (int)(cg.e[rev ? cg.n - 1 - k : k] & 15); if (op != prev) { merged++; prev = op; } }
 	}
-	u32 off = KB_ATOMIC_ADD(&bt.counters[2], (u32)merged);
+	u32 off = KB_ATOMIC_ADD(bt.cig_cursor, (u32)merged);
 	rp.cig_off = off; rp.cig_len = merged;
 	if ((u64)off + (u64)merged > (u64)bt.cap_cigar) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_CIGAR); rp.cig_len = 0; return; }
 	int w = -1, prev = -1;

@@ -272,19 +272,38 @@ struct DevBuf
 	void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
 
+// Everything one batch in flight owns: a stream, its device arrays and a small pinned block for the counters that come back.
+// kb_stage_reads/kb_run/kb_fetch_results use slot 0; kb_map_chunk streams a large chunk through both slots so that the
+// H2D copy of one sub-batch, the kernels of the previous one and the D2H copy of the one before overlap.
+struct kb_slot
+{
+	cudaStream_t stream = nullptr; cudaEvent_t ev[10]; cudaEvent_t done = nullptr;
+	KbBatchDev bt; int n_reads = 0; size_t seq_bytes = 0; u64 seq_first = 0; int max_rlen = 0; int first_read = 0;
+	DevBuf<u8> seq, scratch; DevBuf<u64> seq_off; DevBuf<unsigned long long> work; DevBuf<i32> est, n_hits, n_seeds, n_cands, cand_cap, rescue, slow1, slow2; DevBuf<u32> seed_off, cand_off, cigar, counters, cseg_off, runs; DevBuf<i32> cseg_n; DevBuf<KbSegX> segx; DevBuf<KbJob> jobs;
+	DevBuf<KbHit> hits; DevBuf<KbSeg> segs; DevBuf<KbCand> cands; DevBuf<KbReport> reports; DevBuf<KbReadRes> res; DevBuf<KbPairStat> pstat; DevBuf<kb_aln_t> aln; DevBuf<KbPk> pk;
+	size_t cap_segs = 0, cap_cands = 0, cap_cigar = 0, cap_segx = 0, cap_jobs = 0, cap_runs = 0, scratch_per_thread = 0; int scratch_threads = 0;
+	u32* counters_host = nullptr; unsigned long long* work_dev_host = nullptr;   // pinned: 16 x u32, 8 x u64
+	int launches = 0;
+	void release()
+	{
+		seq.release(); scratch.release(); seq_off.release(); work.release(); est.release(); n_hits.release(); n_seeds.release(); n_cands.release(); cand_cap.release();
+		rescue.release(); slow1.release(); slow2.release(); seed_off.release(); cand_off.release(); cigar.release(); counters.release(); cseg_off.release(); runs.release();
+		cseg_n.release(); segx.release(); jobs.release(); hits.release(); segs.release(); cands.release(); reports.release(); res.release(); pstat.release(); aln.release(); pk.release();
+	}
+};
+
 struct kb_ctx
 {
-	int device = 0; cudaStream_t stream = nullptr; std::string err;
+	int device = 0; std::string err;
 	bool have_index = false; KbIndexDev ix; KbParams pm;
-	DevBuf<u32> occ; DevBuf<u64> sa, sa_full, ref64; DevBuf<KbPk> pk; DevBuf<KbKtab> ktab; DevBuf<u8> pac, lut; DevBuf<i64> chr64; DevBuf<i32> chr32;
+	DevBuf<u32> occ; DevBuf<u64> sa, sa_full, ref64; DevBuf<KbKtab> ktab; DevBuf<u8> pac, lut; DevBuf<i64> chr64; DevBuf<i32> chr32;
 	int64_t l_pac = 0;
-	// batch
-	KbBatchDev bt; bool staged = false, ran = false; int n_reads = 0; size_t seq_bytes = 0;
-	DevBuf<u8> seq, scratch; DevBuf<u64> seq_off; DevBuf<unsigned long long> work; DevBuf<i32> est, n_hits, n_seeds, n_cands, cand_cap, rescue, slow1, slow2; DevBuf<u32> seed_off, cand_off, cigar, counters, cseg_off, runs; DevBuf<i32> cseg_n; DevBuf<KbSegX> segx; DevBuf<KbJob> jobs;
-	DevBuf<KbHit> hits; DevBuf<KbSeg> segs; DevBuf<KbCand> cands; DevBuf<KbReport> reports; DevBuf<KbReadRes> res; DevBuf<KbPairStat> pstat; DevBuf<kb_aln_t> aln;
-	size_t cap_segs = 0, cap_cands = 0, cap_cigar = 0, cap_segx = 0, cap_jobs = 0, cap_runs = 0, scratch_per_thread = 0; int scratch_threads = 0; int max_rlen = 0;
+	kb_slot slot[2];
+	DevBuf<u32> chunk_cigar, chunk_cursor;   // cigar arena and cursor shared by the sub-batches of one pipelined chunk
+	bool staged = false, ran = false, ran_pipelined = false; u32 n_cigar_last = 0;
 	double seg_factor = 32, cigar_factor = 8, scratch_factor = 1, segx_factor = 8, job_factor = 4, run_factor = 96;
-	cudaEvent_t ev[10]; float stage_ms[9]; uint64_t work_host[8]; u32 counters_host[16]; int launches = 0;
+	float stage_ms[9]; uint64_t work_host[8]; u32 counters_host[16];
+	int pipe_min_reads = 262144, pipe_sub_reads = 0;   // chunks of at least pipe_min_reads go through the two-slot pipeline
 };
 
 static int fail(kb_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess)
@@ -326,10 +345,21 @@ int kb_init(int device, kb_ctx_t** out)
 	if (device < 0 || device >= n) return KB_EINVAL;
 	kb_ctx* ctx = new kb_ctx();
 	ctx->device = device;
-	memset(&ctx->ix, 0, sizeof(ctx->ix)); memset(&ctx->bt, 0, sizeof(ctx->bt)); memset(ctx->stage_ms, 0, sizeof(ctx->stage_ms)); memset(ctx->work_host, 0, sizeof(ctx->work_host));
+	memset(&ctx->ix, 0, sizeof(ctx->ix)); memset(ctx->stage_ms, 0, sizeof(ctx->stage_ms)); memset(ctx->work_host, 0, sizeof(ctx->work_host)); memset(ctx->counters_host, 0, sizeof(ctx->counters_host));
 	ctx->pm.min_seed = 0; ctx->pm.max_gaps = 5; ctx->pm.max_insert = 1500; ctx->pm.pacbio = 0; ctx->pm.multihit = 0; ctx->pm.paired = 0;
-	if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return KB_ECUDA; }
-	for (int i = 0; i < 10; i++) cudaEventCreate(&ctx->ev[i]);
+	if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return KB_ECUDA; }
+	for (int k = 0; k < 2; k++)
+	{
+		kb_slot& sl = ctx->slot[k];
+		memset(&sl.bt, 0, sizeof(sl.bt));
+		if (cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return KB_ECUDA; }
+		for (int i = 0; i < 10; i++) cudaEventCreate(&sl.ev[i]);
+		cudaEventCreate(&sl.done);
+		if (cudaMallocHost((void**)&sl.counters_host, 16 * sizeof(u32)) != cudaSuccess || cudaMallocHost((void**)&sl.work_dev_host, 8 * sizeof(unsigned long long)) != cudaSuccess) { delete ctx; return KB_ECUDA; }
+		memset(sl.counters_host, 0, 16 * sizeof(u32)); memset(sl.work_dev_host, 0, 8 * sizeof(unsigned long long));
+	}
+	const char* e = getenv("KB_PIPE_MIN_READS"); if (e && atoi(e) > 0) ctx->pipe_min_reads = atoi(e);
+	e = getenv("KB_PIPE_SUB_READS"); if (e && atoi(e) > 0) ctx->pipe_sub_reads = atoi(e);
 	*out = ctx;
 	return KB_OK;
 }
@@ -338,13 +368,19 @@ void kb_destroy(kb_ctx_t* ctx)
 {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
-	cudaStreamSynchronize(ctx->stream);
-	ctx->occ.release(); ctx->ktab.release(); ctx->ref64.release(); ctx->pk.release(); ctx->sa.release(); ctx->sa_full.release(); ctx->pac.release(); ctx->lut.release(); ctx->chr64.release(); ctx->chr32.release();
-	ctx->seq.release(); ctx->scratch.release(); ctx->seq_off.release(); ctx->work.release(); ctx->est.release(); ctx->n_hits.release(); ctx->n_seeds.release();
-	ctx->n_cands.release(); ctx->cand_cap.release(); ctx->rescue.release(); ctx->slow1.release(); ctx->slow2.release(); ctx->seed_off.release(); ctx->cand_off.release(); ctx->cigar.release(); ctx->counters.release();
-	ctx->cseg_off.release(); ctx->runs.release(); ctx->cseg_n.release(); ctx->segx.release(); ctx->jobs.release(); ctx->hits.release(); ctx->segs.release(); ctx->cands.release(); ctx->reports.release(); ctx->res.release(); ctx->pstat.release(); ctx->aln.release();
-	for (int i = 0; i < 10; i++) cudaEventDestroy(ctx->ev[i]);
-	cudaStreamDestroy(ctx->stream);
+	for (int k = 0; k < 2; k++) if (ctx->slot[k].stream) cudaStreamSynchronize(ctx->slot[k].stream);
+	ctx->occ.release(); ctx->ktab.release(); ctx->ref64.release(); ctx->sa.release(); ctx->sa_full.release(); ctx->pac.release(); ctx->lut.release(); ctx->chr64.release(); ctx->chr32.release();
+	ctx->chunk_cigar.release(); ctx->chunk_cursor.release();
+	for (int k = 0; k < 2; k++)
+	{
+		kb_slot& sl = ctx->slot[k];
+		sl.release();
+		for (int i = 0; i < 10; i++) cudaEventDestroy(sl.ev[i]);
+		cudaEventDestroy(sl.done);
+		if (sl.counters_host) cudaFreeHost(sl.counters_host);
+		if (sl.work_dev_host) cudaFreeHost(sl.work_dev_host);
+		cudaStreamDestroy(sl.stream);
+	}
 	delete ctx;
 }
 
@@ -359,6 +395,7 @@ int kb_upload_index(kb_ctx_t* ctx, const kb_index_host_t* h, int expand_sa)
 {
 	if (!ctx || !h || !h->bwt || !h->sa || !h->pac || h->n_chr <= 0 || !h->chr_len || h->sa_intv <= 0 || (h->sa_intv & (h->sa_intv - 1))) return fail(ctx, KB_EINVAL, "kb_upload_index: bad index description");
 	CK(cudaSetDevice(ctx->device));
+	cudaStream_t stream = ctx->slot[0].stream;
 	for (int c = 1; c <= 4; c++) if (h->L2[c] - h->L2[c - 1] >= 0xFFFFFFFFull) return fail(ctx, KB_EINVAL, "kb_upload_index: a base count exceeds 2^32-1 (u32 Occ layout)");
 	KbIndexDev& ix = ctx->ix; memset(&ix, 0, sizeof(ix));
 	ix.primary = h->primary; for (int i = 0; i < 5; i++) ix.L2[i] = h->L2[i]; ix.seq_len = h->seq_len;
@@ -367,21 +404,21 @@ int kb_upload_index(kb_ctx_t* ctx, const kb_index_host_t* h, int expand_sa)
 	{
 		DevBuf<u32> raw;
 		CK(raw.ensure(h->bwt_words)); CK(ctx->occ.ensure(n_new * 8));
-		CK(cudaMemcpyAsync(raw.p, h->bwt, h->bwt_words * 4, cudaMemcpyHostToDevice, ctx->stream));
-		KB_LAUNCH(k_reblock, (unsigned)((n_new + 255) / 256), 256, ctx->stream, raw.p, h->bwt_words, n_new, ctx->occ.p);
-		CK(cudaGetLastError()); CK(cudaStreamSynchronize(ctx->stream));
+		CK(cudaMemcpyAsync(raw.p, h->bwt, h->bwt_words * 4, cudaMemcpyHostToDevice, stream));
+		KB_LAUNCH(k_reblock, (unsigned)((n_new + 255) / 256), 256, stream, raw.p, h->bwt_words, n_new, ctx->occ.p);
+		CK(cudaGetLastError()); CK(cudaStreamSynchronize(stream));
 		raw.release();
 	}
 	ix.occ = ctx->occ.p; ix.n_blocks = n_new;
-	CK(ctx->sa.ensure(h->n_sa)); CK(cudaMemcpyAsync(ctx->sa.p, h->sa, h->n_sa * 8, cudaMemcpyHostToDevice, ctx->stream));
+	CK(ctx->sa.ensure(h->n_sa)); CK(cudaMemcpyAsync(ctx->sa.p, h->sa, h->n_sa * 8, cudaMemcpyHostToDevice, stream));
 	ix.sa = ctx->sa.p; ix.n_sa = h->n_sa; ix.sa_intv = h->sa_intv; ix.sa_full = nullptr;
 	size_t pac_bytes = (size_t)(h->l_pac / 4 + 1);
-	CK(ctx->pac.ensure(pac_bytes)); CK(cudaMemcpyAsync(ctx->pac.p, h->pac, pac_bytes, cudaMemcpyHostToDevice, ctx->stream));
+	CK(ctx->pac.ensure(pac_bytes)); CK(cudaMemcpyAsync(ctx->pac.p, h->pac, pac_bytes, cudaMemcpyHostToDevice, stream));
 	ix.pac = ctx->pac.p; ix.G = h->l_pac; ix.G2 = h->l_pac * 2; ctx->l_pac = h->l_pac;
 	{
 		u64 words = (pac_bytes + 7) / 8 + 2;
 		CK(ctx->ref64.ensure(words));
-		KB_LAUNCH(k_ref64, (unsigned)((words + 255) / 256), 256, ctx->stream, ctx->pac.p, (u64)pac_bytes, words, ctx->ref64.p);
+		KB_LAUNCH(k_ref64, (unsigned)((words + 255) / 256), 256, stream, ctx->pac.p, (u64)pac_bytes, words, ctx->ref64.p);
 		CK(cudaGetLastError());
 		ix.ref64 = ctx->ref64.p;
 	}
@@ -394,8 +431,8 @@ int kb_upload_index(kb_ctx_t* ctx, const kb_index_host_t* h, int expand_sa)
 	for (int i = 0; i < nc; i++) { key[i] = fwd[i] + len[i] - 1; t32[i] = i; }                       // forward ends ascend with i
 	for (int i = 0; i < nc; i++) { int c = nc - 1 - i; key[nc + i] = rev[c] + len[c] - 1; t32[nc + i] = c; }   // reverse ends ascend with descending i
 	CK(ctx->chr64.ensure(t64.size())); CK(ctx->chr32.ensure(t32.size()));
-	CK(cudaMemcpyAsync(ctx->chr64.p, t64.data(), t64.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-	CK(cudaMemcpyAsync(ctx->chr32.p, t32.data(), t32.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaMemcpyAsync(ctx->chr64.p, t64.data(), t64.size() * 8, cudaMemcpyHostToDevice, stream));
+	CK(cudaMemcpyAsync(ctx->chr32.p, t32.data(), t32.size() * 4, cudaMemcpyHostToDevice, stream));
 	ix.n_chr = nc; ix.n_ends = ne; ix.end_key = ctx->chr64.p; ix.chr_fwd = ctx->chr64.p + ne; ix.chr_rev = ix.chr_fwd + nc; ix.chr_len = ix.chr_rev + nc; ix.end_chr = ctx->chr32.p;
 	// MAPQ table with the reference expression (src/Mapping.cpp:172), evaluated by the host libm exactly like the reference
 	const int lut_scores = 1 << 16;
@@ -407,28 +444,28 @@ int kb_upload_index(kb_ctx_t* ctx, const kb_index_host_t* h, int expand_sa)
 			int q = (int)(30 * (1 - (float)(score - sub) / score) * log(score) + 0.4999);
 			lut[(size_t)s * 5 + d - 1] = (u8)(q > 60 ? 60 : (q < 0 ? 0 : q));
 		}
-	CK(ctx->lut.ensure(lut.size())); CK(cudaMemcpyAsync(ctx->lut.p, lut.data(), lut.size(), cudaMemcpyHostToDevice, ctx->stream));
+	CK(ctx->lut.ensure(lut.size())); CK(cudaMemcpyAsync(ctx->lut.p, lut.data(), lut.size(), cudaMemcpyHostToDevice, stream));
 	ix.mapq_lut = ctx->lut.p; ix.mapq_lut_scores = lut_scores;
-	CK(cudaStreamSynchronize(ctx->stream));
+	CK(cudaStreamSynchronize(stream));
 	{
 		// seeding table: the smallest K with 4^K >= 2G, at most 12 (512 MB): past it intervals are narrow, so nearly every
 		// remaining extension step is the one-block case of kb_extend
 		int K = 1; while (K < 12 && (1ull << (2 * K)) < h->seq_len) K++;
 		if (K >= 4)
 		{
-			u64 ne = 1ull << (2 * K);
-			CK(ctx->ktab.ensure(ne));
+			u64 ne2 = 1ull << (2 * K);
+			CK(ctx->ktab.ensure(ne2));
 			ix.ktab = nullptr; ix.ktab_k = 0;
-			KB_LAUNCH(k_build_ktab, (unsigned)((ne + 255) / 256), 256, ctx->stream, ix, K, ctx->ktab.p);
-			CK(cudaGetLastError()); CK(cudaStreamSynchronize(ctx->stream));
+			KB_LAUNCH(k_build_ktab, (unsigned)((ne2 + 255) / 256), 256, stream, ix, K, ctx->ktab.p);
+			CK(cudaGetLastError()); CK(cudaStreamSynchronize(stream));
 			ix.ktab = ctx->ktab.p; ix.ktab_k = K;
 		}
 	}
 	if (expand_sa)
 	{
 		CK(ctx->sa_full.ensure(h->seq_len + 1));
-		KB_LAUNCH(k_expand_sa, (unsigned)((h->seq_len + 256) / 256), 256, ctx->stream, ix, ctx->sa_full.p);
-		CK(cudaGetLastError()); CK(cudaStreamSynchronize(ctx->stream));
+		KB_LAUNCH(k_expand_sa, (unsigned)((h->seq_len + 256) / 256), 256, stream, ix, ctx->sa_full.p);
+		CK(cudaGetLastError()); CK(cudaStreamSynchronize(stream));
 		ix.sa_full = ctx->sa_full.p;
 	}
 	if (ctx->pm.min_seed <= 0) ctx->pm.min_seed = derive_min_seed(h->l_pac);
@@ -446,46 +483,70 @@ int kb_set_params(kb_ctx_t* ctx, const kb_params_t* p)
 }
 
 int kb_get_min_seed_len(kb_ctx_t* ctx) { return ctx ? ctx->pm.min_seed : KB_EINVAL; }
-void* kb_cuda_stream(kb_ctx_t* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+void* kb_cuda_stream(kb_ctx_t* ctx) { return ctx ? (void*)ctx->slot[0].stream : nullptr; }
 
-static int alloc_batch(kb_ctx* ctx)
+// device arrays of one slot for its n_reads / max_rlen; shared != 0: cigar elements go to the chunk-wide arena
+static int alloc_batch(kb_ctx* ctx, kb_slot& sl, int shared)
 {
-	size_t n = (size_t)ctx->n_reads; KbBatchDev& bt = ctx->bt;
-	int L = ctx->max_rlen > 0 ? ctx->max_rlen : 1;
+	size_t n = (size_t)sl.n_reads; KbBatchDev& bt = sl.bt;
+	int L = sl.max_rlen > 0 ? sl.max_rlen : 1;
 	int max_hits = ctx->pm.pacbio ? L / ctx->pm.min_seed + 2 : L / (ctx->pm.min_seed + 1) + 2;
-	ctx->cap_segs = (size_t)(ctx->seg_factor * (double)n) + (ctx->pm.pacbio ? (size_t)n * (size_t)(L / 8 + 64) : 0) + 65536;
-	if (ctx->cap_segs > 0xF0000000ull) ctx->cap_segs = 0xF0000000ull;
-	ctx->cap_cands = 2 * ctx->cap_segs + 2 * n + 1024;
-	if (ctx->cap_cands > 0xF0000000ull) ctx->cap_cands = 0xF0000000ull;
-	ctx->cap_cigar = (size_t)(ctx->cigar_factor * (double)n) + (ctx->pm.pacbio ? (size_t)n * (size_t)(L / 2) : 0) + 65536;
-	ctx->cap_segx = (size_t)(ctx->segx_factor * (double)n) + (ctx->pm.pacbio ? (size_t)n * (size_t)(L / 16 + 64) : 0) + 65536;
-	ctx->cap_jobs = (size_t)(ctx->job_factor * (double)n) + (ctx->pm.pacbio ? (size_t)n * (size_t)(L / 32 + 32) : 0) + 65536;
-	ctx->cap_runs = (size_t)(ctx->run_factor * (double)n) + (ctx->pm.pacbio ? (size_t)n * (size_t)(3 * L) : 0) + (1 << 20);
-	if (ctx->cap_runs > 0xF0000000ull) ctx->cap_runs = 0xF0000000ull;
-	// per-thread scratch of the report / rescue kernels: NW traceback (2 bit / cell) dominates
+	sl.cap_segs = (size_t)(ctx->seg_factor * (double)n) + (ctx->pm.pacbio ? (size_t)n * (size_t)(L / 8 + 64) : 0) + 65536;
+	if (sl.cap_segs > 0xF0000000ull) sl.cap_segs = 0xF0000000ull;
+	sl.cap_cands = 2 * sl.cap_segs + 2 * n + 1024;
+	if (sl.cap_cands > 0xF0000000ull) sl.cap_cands = 0xF0000000ull;
+	sl.cap_cigar = (size_t)(ctx->cigar_factor * (double)n) + (ctx->pm.pacbio ? (size_t)n * (size_t)(L / 2) : 0) + 65536;
+	sl.cap_segx = (size_t)(ctx->segx_factor * (double)n) + (ctx->pm.pacbio ? (size_t)n * (size_t)(L / 16 + 64) : 0) + 65536;
+	sl.cap_jobs = (size_t)(ctx->job_factor * (double)n) + (ctx->pm.pacbio ? (size_t)n * (size_t)(L / 32 + 32) : 0) + 65536;
+	sl.cap_runs = (size_t)(ctx->run_factor * (double)n) + (ctx->pm.pacbio ? (size_t)n * (size_t)(3 * L) : 0) + (1 << 20);
+	if (sl.cap_runs > 0xF0000000ull) sl.cap_runs = 0xF0000000ull;
+	// per-thread scratch of the arena kernels: NW traceback (2 bit / cell) dominates
 	double side = L < 3100 ? L + 64 : 3100 + 64;
 	size_t per = (size_t)(side * side / 4) + (size_t)L * 160 + (64 << 10);
 	if (ctx->pm.pacbio) per += (size_t)L * 64;
 	per = (size_t)((double)per * ctx->scratch_factor); per = (per + 255) & ~(size_t)255;
 	size_t budget = (size_t)24 << 30;
 	size_t threads = budget / per; if (threads > 148 * 1024) threads = 148 * 1024;
-	size_t need_threads = ctx->pm.paired ? n : n; if (threads > need_threads) threads = need_threads;
+	if (threads > n) threads = n;
 	threads = (threads + KB_BLOCK - 1) / KB_BLOCK * KB_BLOCK; if (threads < KB_BLOCK) threads = KB_BLOCK;
-	ctx->scratch_per_thread = per; ctx->scratch_threads = (int)threads;
-	CK(ctx->hits.ensure(n * max_hits)); CK(ctx->n_hits.ensure(n)); CK(ctx->n_seeds.ensure(n)); CK(ctx->seed_off.ensure(n));
-	CK(ctx->segs.ensure(ctx->cap_segs)); CK(ctx->cands.ensure(ctx->cap_cands)); CK(ctx->reports.ensure(ctx->cap_cands));
-	CK(ctx->n_cands.ensure(n)); CK(ctx->cand_off.ensure(n)); CK(ctx->cand_cap.ensure(n)); CK(ctx->rescue.ensure(n / 2 + 1));
-	CK(ctx->res.ensure(n)); CK(ctx->pstat.ensure(n / 2 + 1)); CK(ctx->aln.ensure(n)); CK(ctx->cigar.ensure(ctx->cap_cigar));
-	CK(ctx->segx.ensure(ctx->cap_segx)); CK(ctx->jobs.ensure(ctx->cap_jobs)); CK(ctx->runs.ensure(ctx->cap_runs)); CK(ctx->cseg_off.ensure(ctx->cap_cands)); CK(ctx->cseg_n.ensure(ctx->cap_cands));
-	CK(ctx->counters.ensure(16)); CK(ctx->work.ensure(8)); CK(ctx->scratch.ensure(per * threads));
-	CK(ctx->pk.ensure((ctx->seq_bytes >> 5) + n + 4)); CK(ctx->slow1.ensure(n + 1)); CK(ctx->slow2.ensure(n + 1));
-	bt.n_reads = ctx->n_reads; bt.seq = ctx->seq.p; bt.seq_off = ctx->seq_off.p; bt.est = ctx->est.p; bt.pk = ctx->pk.p; bt.pk_wpr = (L + 31) / 32;
-	bt.hits = ctx->hits.p; bt.max_hits = max_hits; bt.n_hits = ctx->n_hits.p; bt.n_seeds = ctx->n_seeds.p; bt.seed_off = ctx->seed_off.p;
-	bt.segs = ctx->segs.p; bt.cap_segs = (u32)ctx->cap_segs; bt.cands = ctx->cands.p; bt.cap_cands = (u32)ctx->cap_cands; bt.n_cands = ctx->n_cands.p;
-	bt.cand_off = ctx->cand_off.p; bt.cand_cap = ctx->cand_cap.p; bt.rescue_list = ctx->rescue.p; bt.slow_list = ctx->slow1.p; bt.slow_list2 = ctx->slow2.p; bt.reports = ctx->reports.p; bt.res = ctx->res.p; bt.pstat = ctx->pstat.p;
-	bt.segx = ctx->segx.p; bt.cap_segx = (u32)ctx->cap_segx; bt.cseg_off = ctx->cseg_off.p; bt.cseg_n = ctx->cseg_n.p; bt.jobs = ctx->jobs.p; bt.cap_jobs = (u32)ctx->cap_jobs; bt.runs = ctx->runs.p; bt.cap_runs = (u32)ctx->cap_runs;
-	bt.cigar = ctx->cigar.p; bt.cap_cigar = (u32)ctx->cap_cigar; bt.scratch = ctx->scratch.p; bt.scratch_per_thread = per; bt.scratch_threads = (int)threads;
-	bt.max_rlen = L; bt.nw_max_m = 0; bt.nw_max_n = 0; bt.seg_cap = 0; bt.kmer_cap = 0; bt.counters = ctx->counters.p; bt.work = ctx->work.p;
+	sl.scratch_per_thread = per; sl.scratch_threads = (int)threads;
+	CK(sl.hits.ensure(n * max_hits)); CK(sl.n_hits.ensure(n)); CK(sl.n_seeds.ensure(n)); CK(sl.seed_off.ensure(n));
+	CK(sl.segs.ensure(sl.cap_segs)); CK(sl.cands.ensure(sl.cap_cands)); CK(sl.reports.ensure(sl.cap_cands));
+	CK(sl.n_cands.ensure(n)); CK(sl.cand_off.ensure(n)); CK(sl.cand_cap.ensure(n)); CK(sl.rescue.ensure(n / 2 + 1));
+	CK(sl.res.ensure(n)); CK(sl.pstat.ensure(n / 2 + 1)); CK(sl.aln.ensure(n));
+	if (!shared) CK(sl.cigar.ensure(sl.cap_cigar));
+	CK(sl.segx.ensure(sl.cap_segx)); CK(sl.jobs.ensure(sl.cap_jobs)); CK(sl.runs.ensure(sl.cap_runs)); CK(sl.cseg_off.ensure(sl.cap_cands)); CK(sl.cseg_n.ensure(sl.cap_cands));
+	CK(sl.counters.ensure(16)); CK(sl.work.ensure(8)); CK(sl.scratch.ensure(per * threads));
+	CK(sl.pk.ensure((sl.seq_bytes >> 5) + n + 4)); CK(sl.slow1.ensure(n + 1)); CK(sl.slow2.ensure(n + 1));
+	// reads keep their chunk-wide offsets: the device copies start at seq_first, so the base pointers are shifted back by it
+	bt.n_reads = sl.n_reads; bt.seq = sl.seq.p - sl.seq_first; bt.seq_off = sl.seq_off.p; bt.est = sl.est.p; bt.pk = sl.pk.p - (sl.seq_first >> 5); bt.pk_wpr = (L + 31) / 32;
+	bt.hits = sl.hits.p; bt.max_hits = max_hits; bt.n_hits = sl.n_hits.p; bt.n_seeds = sl.n_seeds.p; bt.seed_off = sl.seed_off.p;
+	bt.segs = sl.segs.p; bt.cap_segs = (u32)sl.cap_segs; bt.cands = sl.cands.p; bt.cap_cands = (u32)sl.cap_cands; bt.n_cands = sl.n_cands.p;
+	bt.cand_off = sl.cand_off.p; bt.cand_cap = sl.cand_cap.p; bt.rescue_list = sl.rescue.p; bt.slow_list = sl.slow1.p; bt.slow_list2 = sl.slow2.p; bt.reports = sl.reports.p; bt.res = sl.res.p; bt.pstat = sl.pstat.p;
+	bt.segx = sl.segx.p; bt.cap_segx = (u32)sl.cap_segx; bt.cseg_off = sl.cseg_off.p; bt.cseg_n = sl.cseg_n.p; bt.jobs = sl.jobs.p; bt.cap_jobs = (u32)sl.cap_jobs; bt.runs = sl.runs.p; bt.cap_runs = (u32)sl.cap_runs;
+	if (shared) { bt.cigar = ctx->chunk_cigar.p; bt.cap_cigar = (u32)ctx->chunk_cigar.n; bt.cig_cursor = ctx->chunk_cursor.p; }
+	else { bt.cigar = sl.cigar.p; bt.cap_cigar = (u32)sl.cap_cigar; bt.cig_cursor = sl.counters.p + 2; }
+	bt.scratch = sl.scratch.p; bt.scratch_per_thread = per; bt.scratch_threads = (int)threads;
+	bt.max_rlen = L; bt.nw_max_m = 0; bt.nw_max_n = 0; bt.seg_cap = 0; bt.kmer_cap = 0; bt.counters = sl.counters.p; bt.work = sl.work.p;
+	return KB_OK;
+}
+
+// H2D of reads [first, first + count) of `in` into a slot (asynchronous on the slot's stream)
+static int stage_slot(kb_ctx* ctx, kb_slot& sl, const kb_reads_t* in, int first, int count, const int32_t* est)
+{
+	size_t n = (size_t)count;
+	sl.n_reads = count; sl.first_read = first;
+	sl.seq_first = n ? in->seq_off[first] : 0;
+	sl.seq_bytes = n ? (size_t)(in->seq_off[first + n] - sl.seq_first) : 0;
+	int L = 0; for (size_t i = 0; i < n; i++) { u64 l = in->seq_off[first + i + 1] - in->seq_off[first + i]; if (l > 0x7FFFFFF0ull) return fail(ctx, KB_EINVAL, "read too long"); if ((int)l > L) L = (int)l; }
+	sl.max_rlen = L;
+	CK(sl.seq.ensure(sl.seq_bytes + 64)); CK(sl.seq_off.ensure(n + 1)); CK(sl.est.ensure(n / 2 + 1));
+	if (n)
+	{
+		CK(cudaMemcpyAsync(sl.seq.p, in->seq + sl.seq_first, sl.seq_bytes, cudaMemcpyHostToDevice, sl.stream));
+		CK(cudaMemcpyAsync(sl.seq_off.p, in->seq_off + first, (n + 1) * 8, cudaMemcpyHostToDevice, sl.stream));
+		if (ctx->pm.paired) CK(cudaMemcpyAsync(sl.est.p, est + first / 2, (n / 2) * 4, cudaMemcpyHostToDevice, sl.stream));
+	}
 	return KB_OK;
 }
 
@@ -495,55 +556,67 @@ int kb_stage_reads(kb_ctx_t* ctx, const kb_reads_t* in, const int32_t* est)
 	if (!ctx->have_index) return fail(ctx, KB_ENOINDEX, "kb_stage_reads: no index");
 	if (ctx->pm.paired && ((in->n_reads & 1) || (in->n_reads > 0 && !est))) return fail(ctx, KB_EINVAL, "kb_stage_reads: paired chunks need an even read count and one EstDistance per pair");
 	CK(cudaSetDevice(ctx->device));
-	ctx->n_reads = in->n_reads; ctx->staged = false; ctx->ran = false;
-	size_t n = (size_t)in->n_reads;
-	ctx->seq_bytes = n ? (size_t)in->seq_off[n] : 0;
-	int L = 0; for (size_t i = 0; i < n; i++) { u64 l = in->seq_off[i + 1] - in->seq_off[i]; if (l > 0x7FFFFFF0ull) return fail(ctx, KB_EINVAL, "read too long"); if ((int)l > L) L = (int)l; }
-	ctx->max_rlen = L;
-	CK(ctx->seq.ensure(ctx->seq_bytes + 64)); CK(ctx->seq_off.ensure(n + 1)); CK(ctx->est.ensure(n / 2 + 1));
-	if (n)
-	{
-		CK(cudaMemcpyAsync(ctx->seq.p, in->seq, ctx->seq_bytes, cudaMemcpyHostToDevice, ctx->stream));
-		CK(cudaMemcpyAsync(ctx->seq_off.p, in->seq_off, (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-		if (ctx->pm.paired) CK(cudaMemcpyAsync(ctx->est.p, est, (n / 2) * 4, cudaMemcpyHostToDevice, ctx->stream));
-	}
+	ctx->staged = false; ctx->ran = false; ctx->ran_pipelined = false;
+	int rc = stage_slot(ctx, ctx->slot[0], in, 0, in->n_reads, est); if (rc) return rc;
 	ctx->staged = true;
 	return KB_OK;
 }
 
-static int launch_pipeline(kb_ctx* ctx)
+static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 {
-	KbBatchDev& bt = ctx->bt; const KbIndexDev& ix = ctx->ix; const KbParams& pm = ctx->pm;
-	int n = ctx->n_reads; cudaStream_t s = ctx->stream;
-	CK(cudaMemsetAsync(ctx->counters.p, 0, 16 * sizeof(u32), s)); CK(cudaMemsetAsync(ctx->work.p, 0, 8 * sizeof(u64), s));
+	KbBatchDev& bt = sl.bt; const KbIndexDev& ix = ctx->ix; const KbParams& pm = ctx->pm;
+	int n = sl.n_reads; cudaStream_t s = sl.stream;
+	CK(cudaMemsetAsync(sl.counters.p, 0, 16 * sizeof(u32), s)); CK(cudaMemsetAsync(sl.work.p, 0, 8 * sizeof(u64), s));
 	unsigned g_reads = (unsigned)((n + KB_BLOCK - 1) / KB_BLOCK);
 	unsigned g_items = pm.paired ? (unsigned)((n / 2 + KB_BLOCK - 1) / KB_BLOCK) : g_reads;
 	unsigned g_hits = (unsigned)(((long long)n * bt.max_hits + KB_BLOCK - 1) / KB_BLOCK);
 	unsigned g_scr = (unsigned)(bt.scratch_threads / KB_BLOCK);
-	ctx->launches = 0;
-	CK(cudaEventRecord(ctx->ev[0], s));
-	KB_LAUNCH(k_pack, (unsigned)(((long long)n * bt.pk_wpr + KB_BLOCK - 1) / KB_BLOCK), KB_BLOCK, s, bt); ctx->launches++;
-	KB_LAUNCH(k_fm_seed, g_reads, KB_BLOCK, s, ix, pm, bt); ctx->launches++;
-	CK(cudaEventRecord(ctx->ev[1], s));
-	KB_LAUNCH(k_sa_locate, g_hits, KB_BLOCK, s, ix, bt); ctx->launches++;
-	CK(cudaEventRecord(ctx->ev[2], s));
-	KB_LAUNCH(k_cand_pair, g_items, KB_BLOCK, s, ix, pm, bt); ctx->launches++;
-	if (pm.pacbio) { KB_LAUNCH(k_cand_pacbio, g_scr, KB_BLOCK, s, ix, pm, bt); ctx->launches++; }
-	CK(cudaEventRecord(ctx->ev[3], s));
-	if (pm.paired) { KB_LAUNCH(k_rescue, g_scr, KB_BLOCK, s, ix, pm, bt); ctx->launches++; }
-	CK(cudaEventRecord(ctx->ev[4], s));
-	KB_LAUNCH(k_segments, g_reads, KB_BLOCK, s, ix, pm, bt); ctx->launches++;
-	KB_LAUNCH(k_segments_slow, g_scr, KB_BLOCK, s, ix, pm, bt); ctx->launches++;
-	CK(cudaEventRecord(ctx->ev[5], s));
-	KB_LAUNCH(k_align, g_scr, KB_BLOCK, s, ix, pm, bt); ctx->launches++;
-	CK(cudaEventRecord(ctx->ev[6], s));
-	KB_LAUNCH(k_assemble, g_reads, KB_BLOCK, s, ix, pm, bt); ctx->launches++;
-	KB_LAUNCH(k_assemble_slow, g_scr, KB_BLOCK, s, ix, pm, bt); ctx->launches++;
-	CK(cudaEventRecord(ctx->ev[7], s));
-	KB_LAUNCH(k_finalize, g_items, KB_BLOCK, s, ix, pm, bt, ctx->aln.p); ctx->launches++;
-	CK(cudaEventRecord(ctx->ev[8], s));
+	sl.launches = 0;
+	CK(cudaEventRecord(sl.ev[0], s));
+	KB_LAUNCH(k_pack, (unsigned)(((long long)n * bt.pk_wpr + KB_BLOCK - 1) / KB_BLOCK), KB_BLOCK, s, bt); sl.launches++;
+	KB_LAUNCH(k_fm_seed, g_reads, KB_BLOCK, s, ix, pm, bt); sl.launches++;
+	CK(cudaEventRecord(sl.ev[1], s));
+	KB_LAUNCH(k_sa_locate, g_hits, KB_BLOCK, s, ix, bt); sl.launches++;
+	CK(cudaEventRecord(sl.ev[2], s));
+	KB_LAUNCH(k_cand_pair, g_items, KB_BLOCK, s, ix, pm, bt); sl.launches++;
+	if (pm.pacbio) { KB_LAUNCH(k_cand_pacbio, g_scr, KB_BLOCK, s, ix, pm, bt); sl.launches++; }
+	CK(cudaEventRecord(sl.ev[3], s));
+	if (pm.paired) { KB_LAUNCH(k_rescue, g_scr, KB_BLOCK, s, ix, pm, bt); sl.launches++; }
+	CK(cudaEventRecord(sl.ev[4], s));
+	KB_LAUNCH(k_segments, g_reads, KB_BLOCK, s, ix, pm, bt); sl.launches++;
+	KB_LAUNCH(k_segments_slow, g_scr, KB_BLOCK, s, ix, pm, bt); sl.launches++;
+	CK(cudaEventRecord(sl.ev[5], s));
+	KB_LAUNCH(k_align, g_scr, KB_BLOCK, s, ix, pm, bt); sl.launches++;
+	CK(cudaEventRecord(sl.ev[6], s));
+	KB_LAUNCH(k_assemble, g_reads, KB_BLOCK, s, ix, pm, bt); sl.launches++;
+	KB_LAUNCH(k_assemble_slow, g_scr, KB_BLOCK, s, ix, pm, bt); sl.launches++;
+	CK(cudaEventRecord(sl.ev[7], s));
+	KB_LAUNCH(k_finalize, g_items, KB_BLOCK, s, ix, pm, bt, sl.aln.p); sl.launches++;
+	CK(cudaEventRecord(sl.ev[8], s));
 	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(sl.counters_host, sl.counters.p, 16 * sizeof(u32), cudaMemcpyDeviceToHost, s));
+	CK(cudaMemcpyAsync(sl.work_dev_host, sl.work.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, s));
 	return KB_OK;
+}
+
+static void grow_factors(kb_ctx* ctx, u32 st)
+{
+	if (st & (KB_OVF_SEEDS | KB_OVF_CANDS | KB_OVF_HITS)) ctx->seg_factor *= 4;
+	if (st & KB_OVF_CIGAR) ctx->cigar_factor *= 4;
+	if (st & (KB_OVF_SCRATCH | KB_OVF_NW | KB_OVF_RESCUE)) ctx->scratch_factor *= 2;
+	if (st & KB_OVF_SEGX) ctx->segx_factor *= 4;
+	if (st & KB_OVF_JOBS) ctx->job_factor *= 4;
+	if (st & KB_OVF_RUNS) ctx->run_factor *= 4;
+}
+
+// adds a finished slot's instrumentation to the context totals
+static void account_slot(kb_ctx* ctx, kb_slot& sl)
+{
+	for (int i = 0; i < 8; i++) { float ms = 0; cudaEventElapsedTime(&ms, sl.ev[i], sl.ev[i + 1]); ctx->stage_ms[i] += ms; }
+	{ float ms = 0; cudaEventElapsedTime(&ms, sl.ev[0], sl.ev[8]); ctx->stage_ms[8] += ms; }
+	const unsigned long long* w = sl.work_dev_host; const u32* c = sl.counters_host;
+	ctx->work_host[0] += w[0]; ctx->work_host[1] += w[1]; ctx->work_host[2] += w[2]; ctx->work_host[3] += w[3];
+	ctx->work_host[4] += c[0]; ctx->work_host[5] += w[4]; ctx->work_host[6] += c[7]; ctx->work_host[7] += (uint64_t)sl.launches;
 }
 
 int kb_run(kb_ctx_t* ctx)
@@ -551,33 +624,25 @@ int kb_run(kb_ctx_t* ctx)
 	if (!ctx) return KB_EINVAL;
 	if (!ctx->staged) return fail(ctx, KB_ESTATE, "kb_run: no staged reads");
 	CK(cudaSetDevice(ctx->device));
+	kb_slot& sl = ctx->slot[0];
 	memset(ctx->stage_ms, 0, sizeof(ctx->stage_ms)); memset(ctx->work_host, 0, sizeof(ctx->work_host));
-	if (ctx->n_reads == 0) { ctx->ran = true; memset(ctx->counters_host, 0, sizeof(ctx->counters_host)); return KB_OK; }
+	ctx->ran_pipelined = false;
+	if (sl.n_reads == 0) { ctx->ran = true; memset(ctx->counters_host, 0, sizeof(ctx->counters_host)); ctx->n_cigar_last = 0; return KB_OK; }
 	for (int attempt = 0; attempt < 6; attempt++)
 	{
-		int rc = alloc_batch(ctx); if (rc) return rc;
-		rc = launch_pipeline(ctx); if (rc) return rc;
-		CK(cudaMemcpyAsync(ctx->counters_host, ctx->counters.p, 16 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
-		unsigned long long w[8];
-		CK(cudaMemcpyAsync(w, ctx->work.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
-		CK(cudaStreamSynchronize(ctx->stream));
-		u32 st = ctx->counters_host[3];
+		int rc = alloc_batch(ctx, sl, 0); if (rc) return rc;
+		rc = launch_pipeline(ctx, sl); if (rc) return rc;
+		CK(cudaStreamSynchronize(sl.stream));
+		u32 st = sl.counters_host[3];
 		if (st == 0)
 		{
-			for (int i = 0; i < 8; i++) cudaEventElapsedTime(&ctx->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]);
-			cudaEventElapsedTime(&ctx->stage_ms[8], ctx->ev[0], ctx->ev[8]);
-			ctx->work_host[0] = w[0]; ctx->work_host[1] = w[1]; ctx->work_host[2] = w[2]; ctx->work_host[3] = w[3];
-			ctx->work_host[4] = ctx->counters_host[0]; ctx->work_host[5] = w[4]; ctx->work_host[6] = ctx->counters_host[7]; ctx->work_host[7] = (uint64_t)ctx->launches;
+			account_slot(ctx, sl);
+			memcpy(ctx->counters_host, sl.counters_host, sizeof(ctx->counters_host));
+			ctx->n_cigar_last = sl.counters_host[2];
 			ctx->ran = true;
 			return KB_OK;
 		}
-		// something overflowed: grow what was flagged and run the batch again
-		if (st & (KB_OVF_SEEDS | KB_OVF_CANDS | KB_OVF_HITS)) ctx->seg_factor *= 4;
-		if (st & KB_OVF_CIGAR) ctx->cigar_factor *= 4;
-		if (st & (KB_OVF_SCRATCH | KB_OVF_NW | KB_OVF_RESCUE)) ctx->scratch_factor *= 2;
-		if (st & KB_OVF_SEGX) ctx->segx_factor *= 4;
-		if (st & KB_OVF_JOBS) ctx->job_factor *= 4;
-		if (st & KB_OVF_RUNS) ctx->run_factor *= 4;
+		grow_factors(ctx, st);   // something overflowed: grow what was flagged and run the batch again
 	}
 	return fail(ctx, KB_EOVERFLOW, "kb_run: arenas still overflow after regrowth");
 }
@@ -585,22 +650,85 @@ int kb_run(kb_ctx_t* ctx)
 int kb_fetch_results(kb_ctx_t* ctx, kb_results_t* out)
 {
 	if (!ctx || !out) return KB_EINVAL;
-	if (!ctx->ran) return fail(ctx, KB_ESTATE, "kb_fetch_results: nothing has run");
+	if (!ctx->ran || ctx->ran_pipelined) return fail(ctx, KB_ESTATE, "kb_fetch_results: nothing has run");
 	CK(cudaSetDevice(ctx->device));
-	size_t n = (size_t)ctx->n_reads;
-	out->n_cigar = n ? ctx->counters_host[2] : 0;
+	kb_slot& sl = ctx->slot[0];
+	size_t n = (size_t)sl.n_reads;
+	out->n_cigar = n ? ctx->n_cigar_last : 0;
 	if (n == 0) return KB_OK;
 	if (!out->aln || (out->n_cigar > 0 && !out->cigar)) return fail(ctx, KB_EINVAL, "kb_fetch_results: missing buffers");
 	if (out->n_cigar > out->cap_cigar) return fail(ctx, KB_ECAPACITY, "kb_fetch_results: cigar buffer too small");
-	CK(cudaMemcpyAsync(out->aln, ctx->aln.p, n * sizeof(kb_aln_t), cudaMemcpyDeviceToHost, ctx->stream));
-	if (out->n_cigar) CK(cudaMemcpyAsync(out->cigar, ctx->cigar.p, (size_t)out->n_cigar * 4, cudaMemcpyDeviceToHost, ctx->stream));
-	if (ctx->pm.paired && out->pairs) CK(cudaMemcpyAsync(out->pairs, ctx->pstat.p, (n / 2) * sizeof(kb_pair_stat_t), cudaMemcpyDeviceToHost, ctx->stream));
-	CK(cudaStreamSynchronize(ctx->stream));
+	CK(cudaMemcpyAsync(out->aln, sl.aln.p, n * sizeof(kb_aln_t), cudaMemcpyDeviceToHost, sl.stream));
+	if (out->n_cigar) CK(cudaMemcpyAsync(out->cigar, sl.cigar.p, (size_t)out->n_cigar * 4, cudaMemcpyDeviceToHost, sl.stream));
+	if (ctx->pm.paired && out->pairs) CK(cudaMemcpyAsync(out->pairs, sl.pstat.p, (n / 2) * sizeof(kb_pair_stat_t), cudaMemcpyDeviceToHost, sl.stream));
+	CK(cudaStreamSynchronize(sl.stream));
 	return KB_OK;
+}
+
+// Large chunks: sub-batches alternate between the two slots. Each slot's stream carries H2D -> kernels -> D2H of its
+// sub-batch, so the copies of one sub-batch overlap the kernels of its neighbours. Cigar elements of all sub-batches go to
+// one chunk-wide arena behind one cursor (offsets in kb_aln_t are chunk-wide) and are copied once at the end.
+static int map_chunk_pipelined(kb_ctx* ctx, const kb_reads_t* in, const int32_t* est, kb_results_t* out)
+{
+	const int n = in->n_reads;
+	int sub = ctx->pipe_sub_reads;
+	if (sub <= 0) { sub = n / 6; if (sub < 65536) sub = 65536; if (sub > 1048576) sub = 1048576; }
+	sub &= ~1; if (sub < 2) sub = 2;
+	const int nsub = (n + sub - 1) / sub;
+	memset(ctx->stage_ms, 0, sizeof(ctx->stage_ms)); memset(ctx->work_host, 0, sizeof(ctx->work_host));
+	int L = 0;
+	for (int attempt = 0; attempt < 6; attempt++)
+	{
+		size_t cap = (size_t)(ctx->cigar_factor * (double)n) + (ctx->pm.pacbio ? in->seq_off[n] / 2 : 0) + 65536;
+		if (cap > 0xF0000000ull) cap = 0xF0000000ull;
+		CK(ctx->chunk_cigar.ensure(cap)); CK(ctx->chunk_cursor.ensure(4));
+		CK(cudaMemsetAsync(ctx->chunk_cursor.p, 0, 4 * sizeof(u32), ctx->slot[0].stream));
+		CK(cudaStreamSynchronize(ctx->slot[0].stream));
+		u32 status = 0;
+		memset(ctx->stage_ms, 0, sizeof(ctx->stage_ms)); memset(ctx->work_host, 0, sizeof(ctx->work_host));
+		for (int k = 0; k < nsub + 2; k++)
+		{
+			kb_slot& sl = ctx->slot[k & 1];
+			if (k >= 2)   // retire the sub-batch that used this slot
+			{
+				CK(cudaStreamSynchronize(sl.stream));
+				status |= sl.counters_host[3];
+				account_slot(ctx, sl);
+			}
+			if (status || k >= nsub) continue;
+			const int first = k * sub, count = first + sub <= n ? sub : n - first;
+			int rc = stage_slot(ctx, sl, in, first, count, est); if (rc) return rc;
+			if (sl.max_rlen > L) L = sl.max_rlen;
+			rc = alloc_batch(ctx, sl, 1); if (rc) return rc;
+			rc = launch_pipeline(ctx, sl); if (rc) return rc;
+			CK(cudaMemcpyAsync(out->aln + first, sl.aln.p, (size_t)count * sizeof(kb_aln_t), cudaMemcpyDeviceToHost, sl.stream));
+			if (ctx->pm.paired && out->pairs) CK(cudaMemcpyAsync(out->pairs + first / 2, sl.pstat.p, (size_t)(count / 2) * sizeof(kb_pair_stat_t), cudaMemcpyDeviceToHost, sl.stream));
+		}
+		if (status == 0)
+		{
+			u32* cur = ctx->slot[0].counters_host;
+			CK(cudaMemcpyAsync(cur, ctx->chunk_cursor.p, sizeof(u32), cudaMemcpyDeviceToHost, ctx->slot[0].stream));
+			CK(cudaStreamSynchronize(ctx->slot[0].stream));
+			out->n_cigar = cur[0]; ctx->n_cigar_last = cur[0];
+			ctx->ran = true; ctx->ran_pipelined = true;
+			if (out->n_cigar > out->cap_cigar) return fail(ctx, KB_ECAPACITY, "kb_map_chunk: cigar buffer too small");
+			if (out->n_cigar) { CK(cudaMemcpyAsync(out->cigar, ctx->chunk_cigar.p, (size_t)out->n_cigar * 4, cudaMemcpyDeviceToHost, ctx->slot[0].stream)); CK(cudaStreamSynchronize(ctx->slot[0].stream)); }
+			return KB_OK;
+		}
+		grow_factors(ctx, status);
+	}
+	return fail(ctx, KB_EOVERFLOW, "kb_map_chunk: arenas still overflow after regrowth");
 }
 
 int kb_map_chunk(kb_ctx_t* ctx, const kb_reads_t* in, const int32_t* est, kb_results_t* out)
 {
+	if (ctx && in && out && ctx->have_index && in->n_reads >= ctx->pipe_min_reads && in->seq && in->seq_off && out->aln && out->cigar
+	    && !(ctx->pm.paired && ((in->n_reads & 1) || !est)))
+	{
+		CK(cudaSetDevice(ctx->device));
+		ctx->staged = false; ctx->ran = false;
+		return map_chunk_pipelined(ctx, in, est, out);
+	}
 	int rc = kb_stage_reads(ctx, in, est); if (rc) return rc;
 	rc = kb_run(ctx); if (rc) return rc;
 	return kb_fetch_results(ctx, out);
@@ -612,21 +740,22 @@ int kb_work(kb_ctx_t* ctx, uint64_t* w, int n) { if (!ctx || !w) return KB_EINVA
 int64_t kb_debug_fetch(kb_ctx_t* ctx, int what, void* dst, uint64_t bytes)
 {
 	if (!ctx || !dst) return KB_EINVAL;
-	if (!ctx->ran) return KB_ESTATE;
+	if (!ctx->ran || ctx->ran_pipelined) return KB_ESTATE;
 	cudaSetDevice(ctx->device);
-	size_t n = (size_t)ctx->n_reads; const void* src = nullptr; size_t have = 0;
+	kb_slot& sl = ctx->slot[0];
+	size_t n = (size_t)sl.n_reads; const void* src = nullptr; size_t have = 0;
 	switch (what)
 	{
-	case 0: src = ctx->n_seeds.p; have = n * 4; break;
-	case 1: src = ctx->seed_off.p; have = n * 4; break;
-	case 2: src = ctx->segs.p; have = (size_t)ctx->counters_host[0] * sizeof(KbSeg); break;
-	case 3: src = ctx->n_cands.p; have = n * 4; break;
-	case 4: src = ctx->cand_off.p; have = n * 4; break;
-	case 5: src = ctx->cands.p; have = (size_t)ctx->counters_host[1] * sizeof(KbCand); break;
-	case 6: src = ctx->reports.p; have = (size_t)ctx->counters_host[1] * sizeof(KbReport); break;
-	case 7: src = ctx->res.p; have = n * sizeof(KbReadRes); break;
-	case 8: src = ctx->cigar.p; have = (size_t)ctx->counters_host[2] * 4; break;
-	case 9: src = ctx->counters.p; have = 16 * 4; break;
+	case 0: src = sl.n_seeds.p; have = n * 4; break;
+	case 1: src = sl.seed_off.p; have = n * 4; break;
+	case 2: src = sl.segs.p; have = (size_t)ctx->counters_host[0] * sizeof(KbSeg); break;
+	case 3: src = sl.n_cands.p; have = n * 4; break;
+	case 4: src = sl.cand_off.p; have = n * 4; break;
+	case 5: src = sl.cands.p; have = (size_t)ctx->counters_host[1] * sizeof(KbCand); break;
+	case 6: src = sl.reports.p; have = (size_t)ctx->counters_host[1] * sizeof(KbReport); break;
+	case 7: src = sl.res.p; have = n * sizeof(KbReadRes); break;
+	case 8: src = sl.cigar.p; have = (size_t)ctx->counters_host[2] * 4; break;
+	case 9: src = sl.counters.p; have = 16 * 4; break;
 	default: return KB_EINVAL;
 	}
 	if (have > bytes) have = bytes;

@@ -108,7 +108,7 @@ struct KbBatchDev
 	KbReport* reports;                  // indexed like cands
 	KbReadRes* res;
 	KbPairStat* pstat;
-	u32* cigar; u32 cap_cigar;
+	u32* cigar; u32 cap_cigar; u32* cig_cursor;   // cursor: counters[2] of the batch, or the chunk-wide cursor of a pipelined chunk
 	// per-thread scratch for the report / rescue kernels
 	u8* scratch; u64 scratch_per_thread; i32 scratch_threads;
 	i32 max_rlen;                       // longest read in the batch

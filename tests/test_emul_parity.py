@@ -96,3 +96,26 @@ def test_cli_argument_errors(kart_emul):
     assert r.returncode == 1 and "Please specify a valid read input" in r.stdout
     r = subprocess.run([kart_emul, "-v"], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.startswith("kart v2.5.6")
+
+
+def test_pipelined_chunk_equals_single_batch(mini, monkeypatch):
+    """kb_map_chunk streams large chunks through two slots (sub-batches, chunk-wide cigar arena): same records as one batch."""
+    idx, g = mini
+    r1, r2, _ = synth.simulate(g, 700, 150, 0.04, seed=41, indel=0.004, n_rate=0.002)
+    reads = pu.interleave(r1, r2)
+    flat, off = Mapper.pack_reads(reads)
+    est = np.full(len(reads) // 2, 1500, dtype=np.int32)
+    est[::7] = 480
+    m0 = pu.make_mapper(idx, emul=True, paired=True)
+    a0, p0, c0 = m0.map_chunk(flat, off, est)
+    monkeypatch.setenv("KB_PIPE_MIN_READS", "64")
+    monkeypatch.setenv("KB_PIPE_SUB_READS", "250")
+    m1 = pu.make_mapper(idx, emul=True, paired=True)
+    a1, p1, c1 = m1.map_chunk(flat, off, est)
+    assert m1.work()["launches"] > 3 * m0.work()["launches"]          # really went through several sub-batches
+    for f in ("pos", "mate_pos", "kind", "flag", "chr", "mapq", "score", "sub_score", "tlen", "fwd", "cig_len"):
+        assert np.array_equal(a0[f], a1[f]), f
+    assert np.array_equal(p0, p1)
+    for i in range(len(a0)):
+        assert np.array_equal(c0[a0["cig_off"][i]:a0["cig_off"][i] + a0["cig_len"][i]], c1[a1["cig_off"][i]:a1["cig_off"][i] + a1["cig_len"][i]])
+    assert m0.work()["ext_steps"] == m1.work()["ext_steps"] and m0.work()["nw_cells"] == m1.work()["nw_cells"]

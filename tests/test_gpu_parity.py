@@ -92,6 +92,31 @@ def test_multi_contig_paired_with_rescue(built):
     assert m.work()["rescues"] > 0
 
 
+def test_pipelined_chunk_full_size_equals_single_batch(eco, monkeypatch):
+    """C2 at size: 400k reads through kb_map_chunk's two-slot pipeline (sub-batches of 65536) and as one resident batch
+    give the same records (the single-batch path is the one the oracle checks read by read above)."""
+    idx, g, prefix = eco
+    r1, r2, _ = synth.simulate(g, 200000, 150, 0.02, seed=77, indel=0.001)
+    flat, off = Mapper.pack_reads(pu.interleave(r1, r2))
+    est = np.full(200000, 1500, dtype=np.int32)
+    monkeypatch.setenv("KB_PIPE_MIN_READS", "2000000000")
+    m0 = pu.make_mapper(idx, expand_sa=True, paired=True)
+    a0, p0, c0 = m0.map_chunk(flat, off, est)
+    monkeypatch.setenv("KB_PIPE_MIN_READS", "1000")
+    monkeypatch.setenv("KB_PIPE_SUB_READS", "65536")
+    m1 = pu.make_mapper(idx, expand_sa=True, paired=True)
+    a1, p1, c1 = m1.map_chunk(flat, off, est)
+    assert m1.work()["launches"] >= 7 * 11
+    for f in ("pos", "mate_pos", "kind", "flag", "chr", "mapq", "score", "sub_score", "tlen", "fwd", "cig_len"):
+        assert np.array_equal(a0[f], a1[f]), f
+    assert np.array_equal(p0, p1)
+    assert len(c0) == len(c1)
+    idx0 = np.repeat(a0["cig_off"].astype(np.int64), a0["cig_len"]) + (np.arange(int(a0["cig_len"].sum())) - np.repeat(np.cumsum(a0["cig_len"]) - a0["cig_len"], a0["cig_len"]))
+    idx1 = np.repeat(a1["cig_off"].astype(np.int64), a1["cig_len"]) + (np.arange(int(a1["cig_len"].sum())) - np.repeat(np.cumsum(a1["cig_len"]) - a1["cig_len"], a1["cig_len"]))
+    assert np.array_equal(c0[idx0], c1[idx1])
+    assert (a0["score"] > 0).mean() > 0.99
+
+
 import os            # noqa: E402
 import subprocess    # noqa: E402
 
