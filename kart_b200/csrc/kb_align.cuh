@@ -669,6 +669,12 @@ KB_HD void kb_classify_segment(const KbIndexDev& ix, const KbParams& pm, const K
 	if ((u64)ro + need > (u64)bt.cap_runs) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_RUNS); return; }
 	KbJob jb; jb.gpos = sp.gpos; jb.read = (u32)r; jb.rpos = sp.rpos; jb.rlen = sp.rlen; jb.glen = sp.glen; jb.run_off = ro; jb.nruns = 0; jb.ident = 0; jb.aligned = 0;
 	bt.jobs[id] = jb;
+	// route: one thread (by size class) when it is a single small NW problem inside the text, else the warp kernel
+	const int mx = sp.rlen > sp.glen ? sp.rlen : sp.glen;
+	const bool small = mx <= KB_NW_SMALL && !(sp.rlen > 30 && sp.glen > 30) && sp.rlen > 0 && sp.glen > 0 && sp.gpos >= 0 && sp.gpos + sp.glen <= ix.G2;
+	const u32 cls = small ? (u32)((mx - 1) >> 3) : (u32)KB_NW_CLASSES;
+	const u32 slot = KB_ATOMIC_ADD(&bt.counters[16 + cls], 1u);
+	bt.job_list[(size_t)cls * bt.cap_jobs + slot] = id;
 	out->info = KB_SEG_JOB; out->aux = id;
 }
 
@@ -713,6 +719,61 @@ KB_HD bool kb_segments_read(const KbIndexDev& ix, const KbParams& pm, const KbBa
 		ar->used = mark;
 	}
 	return true;
+}
+
+// phase B, thread-per-fragment: the whole m x n (both <= KB_NW_SMALL) problem of job `id` in one thread. Same recurrence, tie
+// order and run list as the warp version below (kb_nww_*); the two previous-row vectors and the 2-bit traceback rows live
+// in local memory, the read comes from its packed word and the reference from one 64-bit window (the job lies inside the text).
+KB_HD void kb_nw_task(const KbIndexDev& ix, const KbBatchDev& bt, u32 id, unsigned long long* cells)
+{
+	KbJob& jb = bt.jobs[id];
+	const int m = jb.rlen, n = jb.glen;
+	const KbPk rw = kb_read_win(kb_pk_read(bt, (int)jb.read), jb.rpos);
+	u32 ginv; const u64 gw = kb_ref_win(ix, jb.gpos, &ginv);
+	int S[KB_NW_SMALL + 1], T[KB_NW_SMALL + 1]; u64 tb[KB_NW_SMALL]; u32 rev[2 * KB_NW_SMALL];
+	for (int j = 0; j <= n; j++) { S[j] = j ? -2 - j : 0; T[j] = KB_NW_NEG; }
+	for (int i = 1; i <= m; i++)
+	{
+		const int a = (int)((rw.code >> (64 - 2 * i)) & 3u) | (int)(((rw.n4 >> (32 - i)) & 1u) << 2);
+		int diag = S[0], left_s = -2 - i, left_r = KB_NW_NEG;
+		S[0] = left_s;
+		u64 bits = 0, bw = gw;
+		for (int j = 1; j <= n; j++)
+		{
+			const int b = (int)(bw >> 62); bw <<= 2;
+			const int us = S[j], ut = T[j];
+			const int r = left_r - 1 > left_s - 3 ? left_r - 1 : left_s - 3;
+			const int t = ut - 1 > us - 3 ? ut - 1 : us - 3;
+			const int dg = diag + (a == b ? 3 : -3);
+			int s = dg > r ? dg : r; if (t > s) s = t;
+			bits |= (u64)((s == r ? 1u : 0u) | (s == t ? 2u : 0u)) << (2 * (j - 1));
+			diag = us; S[j] = s; T[j] = t; left_s = s; left_r = r;
+		}
+		tb[i - 1] = bits;
+	}
+	int i = m, j = n, nr = 0, ident = 0, aligned = 0, cur = -1, len = 0;
+	while (i > 0 || j > 0)
+	{
+		int type;
+		if (i == 0) type = KB_RUN_D;
+		else if (j == 0) type = KB_RUN_I;
+		else { const u32 b2 = (u32)(tb[i - 1] >> (2 * (j - 1))) & 3u; type = (b2 & 1u) ? KB_RUN_D : ((b2 & 2u) ? KB_RUN_I : KB_RUN_M); }
+		if (type == KB_RUN_D) j--;
+		else if (type == KB_RUN_I) i--;
+		else
+		{
+			i--; j--; aligned++;
+			// raw character equality against the upper-case reference: the read character must be an upper-case base with the same code
+			if ((((rw.bad >> (31 - i)) & 1u) == 0u) && (((rw.code >> (62 - 2 * i)) & 3u) == ((gw >> (62 - 2 * j)) & 3u))) ident++;
+		}
+		if (type == cur) len++;
+		else { if (len > 0) rev[nr++] = ((u32)len << 2) | (u32)cur; cur = type; len = 1; }
+	}
+	if (len > 0) rev[nr++] = ((u32)len << 2) | (u32)cur;
+	u32* out = bt.runs + jb.run_off;
+	for (int k = 0; k < nr; k++) out[k] = rev[nr - 1 - k];
+	jb.nruns = nr; jb.ident = ident; jb.aligned = aligned;
+	*cells += (unsigned long long)m * (unsigned long long)n;
 }
 
 // phase B, warp per job. State shared by the lanes of the warp (shared memory on the GPU):

@@ -19,6 +19,7 @@
 #include "kb_stages.cuh"
 
 #define KB_BLOCK 128
+#define KB_SLOTS 3           // batches in flight in kb_map_chunk's pipeline
 #define KB_ALIGN_POOL 6144   // shared-memory bytes per warp of k_align (fragment chars, codes, 2-bit traceback)
 
 // ------------------------------------------------------------------------------------------------
@@ -162,7 +163,22 @@ static void k_rescue(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulation: 
 #endif
 __global__ void __launch_bounds__(KB_BLOCK) k_segments(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_segments(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x); }
 __global__ void __launch_bounds__(KB_BLOCK) k_segments_slow(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_segments_slow(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
-// phase B: one warp per alignment job (kb_align.cuh "warp-per-fragment")
+// phase B, small fragments: one thread per Needleman-Wunsch problem, problems grouped by size class (kb_align.cuh "thread-per-fragment")
+__global__ void __launch_bounds__(KB_BLOCK) k_nw_small(KbIndexDev ix, KbParams pm, KbBatchDev bt)
+{
+	if (bt.counters[3]) return;
+	unsigned long long cells = 0, calls = 0;
+	u32 c0 = bt.counters[16], c1 = c0 + bt.counters[17], c2 = c1 + bt.counters[18], c3 = c2 + bt.counters[19];
+	for (u32 q = blockIdx.x * blockDim.x + threadIdx.x; q < c3; q += gridDim.x * blockDim.x)
+	{
+		u32 cls = q < c0 ? 0u : (q < c1 ? 1u : (q < c2 ? 2u : 3u));
+		u32 k = q - (cls == 0 ? 0u : (cls == 1 ? c0 : (cls == 2 ? c1 : c2)));
+		kb_nw_task(ix, bt, bt.job_list[(size_t)cls * bt.cap_jobs + k], &cells);
+		calls++;
+	}
+	kb_warp_add64(&bt.work[3], cells); kb_warp_add64(&bt.work[4], calls);
+}
+// phase B, everything else: one warp per alignment job (kb_align.cuh "warp-per-fragment")
 #ifndef KB_EMUL
 __global__ void __launch_bounds__(KB_BLOCK) k_align(KbIndexDev ix, KbParams pm, KbBatchDev bt)
 {
@@ -173,12 +189,12 @@ __global__ void __launch_bounds__(KB_BLOCK) k_align(KbIndexDev ix, KbParams pm, 
 	const u32 gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
 	if ((int)(gwarp * 32) >= bt.scratch_threads) return;
 	KbAlignWarp& w = sw[wib];
-	const u32 njobs = bt.counters[11];
+	const u32 njobs = bt.counters[20]; const u32* list = bt.job_list + (size_t)KB_NW_CLASSES * bt.cap_jobs;
 	if (lane == 0) { w.ar.base = bt.scratch + (u64)gwarp * 32ull * bt.scratch_per_thread; w.ar.cap = 32ull * bt.scratch_per_thread; w.fast.base = pool[wib]; w.fast.cap = KB_ALIGN_POOL; w.fast.ovf = false; w.cells = 0; w.calls = 0; }
 	__syncwarp();
-	for (u32 id = gwarp; id < njobs; id += nwarps)
+	for (u32 q = gwarp; q < njobs; q += nwarps)
 	{
-		if (lane == 0) kb_aw_begin(pm, bt, w, id);
+		if (lane == 0) kb_aw_begin(pm, bt, w, list[q]);
 		__syncwarp();
 		kb_aw_fetch(ix, bt, w, lane);
 		__syncwarp();
@@ -224,10 +240,10 @@ static void k_align(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulation: t
 	if (bt.counters[3]) return;
 	static KbAlignWarp w; KbNwLane L[32]; static u8 pool[KB_ALIGN_POOL];
 	w.ar.base = bt.scratch; w.ar.cap = 32ull * bt.scratch_per_thread; w.fast.base = pool; w.fast.cap = KB_ALIGN_POOL; w.fast.ovf = false; w.cells = 0; w.calls = 0;
-	const u32 njobs = bt.counters[11];
-	for (u32 id = 0; id < njobs; id++)
+	const u32 njobs = bt.counters[20]; const u32* list = bt.job_list + (size_t)KB_NW_CLASSES * bt.cap_jobs;
+	for (u32 q = 0; q < njobs; q++)
 	{
-		kb_aw_begin(pm, bt, w, id);
+		kb_aw_begin(pm, bt, w, list[q]);
 		for (int t = 31; t >= 0; t--) kb_aw_fetch(ix, bt, w, t);
 		while (true)
 		{
@@ -273,13 +289,13 @@ struct DevBuf
 };
 
 // Everything one batch in flight owns: a stream, its device arrays and a small pinned block for the counters that come back.
-// kb_stage_reads/kb_run/kb_fetch_results use slot 0; kb_map_chunk streams a large chunk through both slots so that the
+// kb_stage_reads/kb_run/kb_fetch_results use slot 0; kb_map_chunk streams a large chunk through all slots so that the
 // H2D copy of one sub-batch, the kernels of the previous one and the D2H copy of the one before overlap.
 struct kb_slot
 {
 	cudaStream_t stream = nullptr; cudaEvent_t ev[10]; cudaEvent_t done = nullptr;
 	KbBatchDev bt; int n_reads = 0; size_t seq_bytes = 0; u64 seq_first = 0; int max_rlen = 0; int first_read = 0;
-	DevBuf<u8> seq, scratch; DevBuf<u64> seq_off; DevBuf<unsigned long long> work; DevBuf<i32> est, n_hits, n_seeds, n_cands, cand_cap, rescue, slow1, slow2; DevBuf<u32> seed_off, cand_off, cigar, counters, cseg_off, runs; DevBuf<i32> cseg_n; DevBuf<KbSegX> segx; DevBuf<KbJob> jobs;
+	DevBuf<u8> seq, scratch; DevBuf<u64> seq_off; DevBuf<unsigned long long> work; DevBuf<i32> est, n_hits, n_seeds, n_cands, cand_cap, rescue, slow1, slow2; DevBuf<u32> seed_off, cand_off, cigar, counters, cseg_off, runs; DevBuf<i32> cseg_n; DevBuf<KbSegX> segx; DevBuf<KbJob> jobs; DevBuf<u32> job_list;
 	DevBuf<KbHit> hits; DevBuf<KbSeg> segs; DevBuf<KbCand> cands; DevBuf<KbReport> reports; DevBuf<KbReadRes> res; DevBuf<KbPairStat> pstat; DevBuf<kb_aln_t> aln; DevBuf<KbPk> pk;
 	size_t cap_segs = 0, cap_cands = 0, cap_cigar = 0, cap_segx = 0, cap_jobs = 0, cap_runs = 0, scratch_per_thread = 0; int scratch_threads = 0;
 	u32* counters_host = nullptr; unsigned long long* work_dev_host = nullptr;   // pinned: 16 x u32, 8 x u64
@@ -288,7 +304,7 @@ struct kb_slot
 	{
 		seq.release(); scratch.release(); seq_off.release(); work.release(); est.release(); n_hits.release(); n_seeds.release(); n_cands.release(); cand_cap.release();
 		rescue.release(); slow1.release(); slow2.release(); seed_off.release(); cand_off.release(); cigar.release(); counters.release(); cseg_off.release(); runs.release();
-		cseg_n.release(); segx.release(); jobs.release(); hits.release(); segs.release(); cands.release(); reports.release(); res.release(); pstat.release(); aln.release(); pk.release();
+		cseg_n.release(); segx.release(); jobs.release(); job_list.release(); hits.release(); segs.release(); cands.release(); reports.release(); res.release(); pstat.release(); aln.release(); pk.release();
 	}
 };
 
@@ -298,11 +314,12 @@ struct kb_ctx
 	bool have_index = false; KbIndexDev ix; KbParams pm;
 	DevBuf<u32> occ; DevBuf<u64> sa, sa_full, ref64; DevBuf<KbKtab> ktab; DevBuf<u8> pac, lut; DevBuf<i64> chr64; DevBuf<i32> chr32;
 	int64_t l_pac = 0;
-	kb_slot slot[2];
+	kb_slot slot[KB_SLOTS];
 	DevBuf<u32> chunk_cigar, chunk_cursor;   // cigar arena and cursor shared by the sub-batches of one pipelined chunk
 	bool staged = false, ran = false, ran_pipelined = false; u32 n_cigar_last = 0;
 	double seg_factor = 32, cigar_factor = 8, scratch_factor = 1, segx_factor = 8, job_factor = 4, run_factor = 96;
-	float stage_ms[9]; uint64_t work_host[8]; u32 counters_host[16];
+	float stage_ms[9]; uint64_t work_host[8]; u32 counters_host[KB_NCOUNTERS];
+	cudaEvent_t chunk_start = nullptr; int trace = 0;
 	int pipe_min_reads = 262144, pipe_sub_reads = 0;   // chunks of at least pipe_min_reads go through the two-slot pipeline
 };
 
@@ -348,16 +365,17 @@ int kb_init(int device, kb_ctx_t** out)
 	memset(&ctx->ix, 0, sizeof(ctx->ix)); memset(ctx->stage_ms, 0, sizeof(ctx->stage_ms)); memset(ctx->work_host, 0, sizeof(ctx->work_host)); memset(ctx->counters_host, 0, sizeof(ctx->counters_host));
 	ctx->pm.min_seed = 0; ctx->pm.max_gaps = 5; ctx->pm.max_insert = 1500; ctx->pm.pacbio = 0; ctx->pm.multihit = 0; ctx->pm.paired = 0;
 	if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return KB_ECUDA; }
-	for (int k = 0; k < 2; k++)
+	for (int k = 0; k < KB_SLOTS; k++)
 	{
 		kb_slot& sl = ctx->slot[k];
 		memset(&sl.bt, 0, sizeof(sl.bt));
 		if (cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return KB_ECUDA; }
 		for (int i = 0; i < 10; i++) cudaEventCreate(&sl.ev[i]);
 		cudaEventCreate(&sl.done);
-		if (cudaMallocHost((void**)&sl.counters_host, 16 * sizeof(u32)) != cudaSuccess || cudaMallocHost((void**)&sl.work_dev_host, 8 * sizeof(unsigned long long)) != cudaSuccess) { delete ctx; return KB_ECUDA; }
-		memset(sl.counters_host, 0, 16 * sizeof(u32)); memset(sl.work_dev_host, 0, 8 * sizeof(unsigned long long));
+		if (cudaMallocHost((void**)&sl.counters_host, KB_NCOUNTERS * sizeof(u32)) != cudaSuccess || cudaMallocHost((void**)&sl.work_dev_host, 8 * sizeof(unsigned long long)) != cudaSuccess) { delete ctx; return KB_ECUDA; }
+		memset(sl.counters_host, 0, KB_NCOUNTERS * sizeof(u32)); memset(sl.work_dev_host, 0, 8 * sizeof(unsigned long long));
 	}
+	cudaEventCreate(&ctx->chunk_start); ctx->trace = getenv("KB_PIPE_TRACE") ? 1 : 0;
 	const char* e = getenv("KB_PIPE_MIN_READS"); if (e && atoi(e) > 0) ctx->pipe_min_reads = atoi(e);
 	e = getenv("KB_PIPE_SUB_READS"); if (e && atoi(e) > 0) ctx->pipe_sub_reads = atoi(e);
 	*out = ctx;
@@ -368,10 +386,11 @@ void kb_destroy(kb_ctx_t* ctx)
 {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
-	for (int k = 0; k < 2; k++) if (ctx->slot[k].stream) cudaStreamSynchronize(ctx->slot[k].stream);
+	for (int k = 0; k < KB_SLOTS; k++) if (ctx->slot[k].stream) cudaStreamSynchronize(ctx->slot[k].stream);
+	if (ctx->chunk_start) cudaEventDestroy(ctx->chunk_start);
 	ctx->occ.release(); ctx->ktab.release(); ctx->ref64.release(); ctx->sa.release(); ctx->sa_full.release(); ctx->pac.release(); ctx->lut.release(); ctx->chr64.release(); ctx->chr32.release();
 	ctx->chunk_cigar.release(); ctx->chunk_cursor.release();
-	for (int k = 0; k < 2; k++)
+	for (int k = 0; k < KB_SLOTS; k++)
 	{
 		kb_slot& sl = ctx->slot[k];
 		sl.release();
@@ -515,15 +534,15 @@ static int alloc_batch(kb_ctx* ctx, kb_slot& sl, int shared)
 	CK(sl.n_cands.ensure(n)); CK(sl.cand_off.ensure(n)); CK(sl.cand_cap.ensure(n)); CK(sl.rescue.ensure(n / 2 + 1));
 	CK(sl.res.ensure(n)); CK(sl.pstat.ensure(n / 2 + 1)); CK(sl.aln.ensure(n));
 	if (!shared) CK(sl.cigar.ensure(sl.cap_cigar));
-	CK(sl.segx.ensure(sl.cap_segx)); CK(sl.jobs.ensure(sl.cap_jobs)); CK(sl.runs.ensure(sl.cap_runs)); CK(sl.cseg_off.ensure(sl.cap_cands)); CK(sl.cseg_n.ensure(sl.cap_cands));
-	CK(sl.counters.ensure(16)); CK(sl.work.ensure(8)); CK(sl.scratch.ensure(per * threads));
+	CK(sl.segx.ensure(sl.cap_segx)); CK(sl.jobs.ensure(sl.cap_jobs)); CK(sl.job_list.ensure(sl.cap_jobs * (KB_NW_CLASSES + 1))); CK(sl.runs.ensure(sl.cap_runs)); CK(sl.cseg_off.ensure(sl.cap_cands)); CK(sl.cseg_n.ensure(sl.cap_cands));
+	CK(sl.counters.ensure(KB_NCOUNTERS)); CK(sl.work.ensure(8)); CK(sl.scratch.ensure(per * threads));
 	CK(sl.pk.ensure((sl.seq_bytes >> 5) + n + 4)); CK(sl.slow1.ensure(n + 1)); CK(sl.slow2.ensure(n + 1));
 	// reads keep their chunk-wide offsets: the device copies start at seq_first, so the base pointers are shifted back by it
 	bt.n_reads = sl.n_reads; bt.seq = sl.seq.p - sl.seq_first; bt.seq_off = sl.seq_off.p; bt.est = sl.est.p; bt.pk = sl.pk.p - (sl.seq_first >> 5); bt.pk_wpr = (L + 31) / 32;
 	bt.hits = sl.hits.p; bt.max_hits = max_hits; bt.n_hits = sl.n_hits.p; bt.n_seeds = sl.n_seeds.p; bt.seed_off = sl.seed_off.p;
 	bt.segs = sl.segs.p; bt.cap_segs = (u32)sl.cap_segs; bt.cands = sl.cands.p; bt.cap_cands = (u32)sl.cap_cands; bt.n_cands = sl.n_cands.p;
 	bt.cand_off = sl.cand_off.p; bt.cand_cap = sl.cand_cap.p; bt.rescue_list = sl.rescue.p; bt.slow_list = sl.slow1.p; bt.slow_list2 = sl.slow2.p; bt.reports = sl.reports.p; bt.res = sl.res.p; bt.pstat = sl.pstat.p;
-	bt.segx = sl.segx.p; bt.cap_segx = (u32)sl.cap_segx; bt.cseg_off = sl.cseg_off.p; bt.cseg_n = sl.cseg_n.p; bt.jobs = sl.jobs.p; bt.cap_jobs = (u32)sl.cap_jobs; bt.runs = sl.runs.p; bt.cap_runs = (u32)sl.cap_runs;
+	bt.segx = sl.segx.p; bt.cap_segx = (u32)sl.cap_segx; bt.cseg_off = sl.cseg_off.p; bt.cseg_n = sl.cseg_n.p; bt.jobs = sl.jobs.p; bt.cap_jobs = (u32)sl.cap_jobs; bt.job_list = sl.job_list.p; bt.runs = sl.runs.p; bt.cap_runs = (u32)sl.cap_runs;
 	if (shared) { bt.cigar = ctx->chunk_cigar.p; bt.cap_cigar = (u32)ctx->chunk_cigar.n; bt.cig_cursor = ctx->chunk_cursor.p; }
 	else { bt.cigar = sl.cigar.p; bt.cap_cigar = (u32)sl.cap_cigar; bt.cig_cursor = sl.counters.p + 2; }
 	bt.scratch = sl.scratch.p; bt.scratch_per_thread = per; bt.scratch_threads = (int)threads;
@@ -566,7 +585,7 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 {
 	KbBatchDev& bt = sl.bt; const KbIndexDev& ix = ctx->ix; const KbParams& pm = ctx->pm;
 	int n = sl.n_reads; cudaStream_t s = sl.stream;
-	CK(cudaMemsetAsync(sl.counters.p, 0, 16 * sizeof(u32), s)); CK(cudaMemsetAsync(sl.work.p, 0, 8 * sizeof(u64), s));
+	CK(cudaMemsetAsync(sl.counters.p, 0, KB_NCOUNTERS * sizeof(u32), s)); CK(cudaMemsetAsync(sl.work.p, 0, 8 * sizeof(u64), s));
 	unsigned g_reads = (unsigned)((n + KB_BLOCK - 1) / KB_BLOCK);
 	unsigned g_items = pm.paired ? (unsigned)((n / 2 + KB_BLOCK - 1) / KB_BLOCK) : g_reads;
 	unsigned g_hits = (unsigned)(((long long)n * bt.max_hits + KB_BLOCK - 1) / KB_BLOCK);
@@ -586,6 +605,7 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 	KB_LAUNCH(k_segments, g_reads, KB_BLOCK, s, ix, pm, bt); sl.launches++;
 	KB_LAUNCH(k_segments_slow, g_scr, KB_BLOCK, s, ix, pm, bt); sl.launches++;
 	CK(cudaEventRecord(sl.ev[5], s));
+	KB_LAUNCH(k_nw_small, 148 * 8, KB_BLOCK, s, ix, pm, bt); sl.launches++;
 	KB_LAUNCH(k_align, g_scr, KB_BLOCK, s, ix, pm, bt); sl.launches++;
 	CK(cudaEventRecord(sl.ev[6], s));
 	KB_LAUNCH(k_assemble, g_reads, KB_BLOCK, s, ix, pm, bt); sl.launches++;
@@ -594,7 +614,7 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 	KB_LAUNCH(k_finalize, g_items, KB_BLOCK, s, ix, pm, bt, sl.aln.p); sl.launches++;
 	CK(cudaEventRecord(sl.ev[8], s));
 	CK(cudaGetLastError());
-	CK(cudaMemcpyAsync(sl.counters_host, sl.counters.p, 16 * sizeof(u32), cudaMemcpyDeviceToHost, s));
+	CK(cudaMemcpyAsync(sl.counters_host, sl.counters.p, KB_NCOUNTERS * sizeof(u32), cudaMemcpyDeviceToHost, s));
 	CK(cudaMemcpyAsync(sl.work_dev_host, sl.work.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, s));
 	return KB_OK;
 }
@@ -672,7 +692,7 @@ static int map_chunk_pipelined(kb_ctx* ctx, const kb_reads_t* in, const int32_t*
 {
 	const int n = in->n_reads;
 	int sub = ctx->pipe_sub_reads;
-	if (sub <= 0) { sub = n / 6; if (sub < 65536) sub = 65536; if (sub > 1048576) sub = 1048576; }
+	if (sub <= 0) { sub = n / 10; if (sub < 65536) sub = 65536; if (sub > 1048576) sub = 1048576; }
 	sub &= ~1; if (sub < 2) sub = 2;
 	const int nsub = (n + sub - 1) / sub;
 	memset(ctx->stage_ms, 0, sizeof(ctx->stage_ms)); memset(ctx->work_host, 0, sizeof(ctx->work_host));
@@ -683,26 +703,36 @@ static int map_chunk_pipelined(kb_ctx* ctx, const kb_reads_t* in, const int32_t*
 		if (cap > 0xF0000000ull) cap = 0xF0000000ull;
 		CK(ctx->chunk_cigar.ensure(cap)); CK(ctx->chunk_cursor.ensure(4));
 		CK(cudaMemsetAsync(ctx->chunk_cursor.p, 0, 4 * sizeof(u32), ctx->slot[0].stream));
+		CK(cudaEventRecord(ctx->chunk_start, ctx->slot[0].stream));
 		CK(cudaStreamSynchronize(ctx->slot[0].stream));
 		u32 status = 0;
 		memset(ctx->stage_ms, 0, sizeof(ctx->stage_ms)); memset(ctx->work_host, 0, sizeof(ctx->work_host));
-		for (int k = 0; k < nsub + 2; k++)
+		for (int k = 0; k < nsub + KB_SLOTS; k++)
 		{
-			kb_slot& sl = ctx->slot[k & 1];
-			if (k >= 2)   // retire the sub-batch that used this slot
+			kb_slot& sl = ctx->slot[k % KB_SLOTS];
+			if (k >= KB_SLOTS)   // retire the sub-batch that used this slot
 			{
 				CK(cudaStreamSynchronize(sl.stream));
 				status |= sl.counters_host[3];
 				account_slot(ctx, sl);
+				if (ctx->trace)
+				{
+					float a = 0, b = 0, c = 0, d = 0;
+					cudaEventElapsedTime(&a, ctx->chunk_start, sl.ev[9]); cudaEventElapsedTime(&b, ctx->chunk_start, sl.ev[0]);
+					cudaEventElapsedTime(&c, ctx->chunk_start, sl.ev[8]); cudaEventElapsedTime(&d, ctx->chunk_start, sl.done);
+					fprintf(stderr, "[kb pipe] sub %d: h2d %.2f..%.2f  kernels ..%.2f  d2h ..%.2f ms\n", k - KB_SLOTS, a, b, c, d);
+				}
 			}
 			if (status || k >= nsub) continue;
 			const int first = k * sub, count = first + sub <= n ? sub : n - first;
+			CK(cudaEventRecord(sl.ev[9], sl.stream));
 			int rc = stage_slot(ctx, sl, in, first, count, est); if (rc) return rc;
 			if (sl.max_rlen > L) L = sl.max_rlen;
 			rc = alloc_batch(ctx, sl, 1); if (rc) return rc;
 			rc = launch_pipeline(ctx, sl); if (rc) return rc;
 			CK(cudaMemcpyAsync(out->aln + first, sl.aln.p, (size_t)count * sizeof(kb_aln_t), cudaMemcpyDeviceToHost, sl.stream));
 			if (ctx->pm.paired && out->pairs) CK(cudaMemcpyAsync(out->pairs + first / 2, sl.pstat.p, (size_t)(count / 2) * sizeof(kb_pair_stat_t), cudaMemcpyDeviceToHost, sl.stream));
+			CK(cudaEventRecord(sl.done, sl.stream));
 		}
 		if (status == 0)
 		{
@@ -755,7 +785,8 @@ int64_t kb_debug_fetch(kb_ctx_t* ctx, int what, void* dst, uint64_t bytes)
 	case 6: src = sl.reports.p; have = (size_t)ctx->counters_host[1] * sizeof(KbReport); break;
 	case 7: src = sl.res.p; have = n * sizeof(KbReadRes); break;
 	case 8: src = sl.cigar.p; have = (size_t)ctx->counters_host[2] * 4; break;
-	case 9: src = sl.counters.p; have = 16 * 4; break;
+	case 9: src = sl.counters.p; have = KB_NCOUNTERS * 4; break;
+	case 10: src = sl.jobs.p; have = (size_t)ctx->counters_host[11] * sizeof(KbJob); break;
 	default: return KB_EINVAL;
 	}
 	if (have > bytes) have = bytes;

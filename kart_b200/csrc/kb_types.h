@@ -24,6 +24,10 @@ typedef uint8_t u8;
 #else
 #define KB_HD inline
 #define KB_D inline
+#define KB_NCOUNTERS 32
+#define KB_NW_CLASSES 4
+#define KB_NW_SMALL 32   // a fragment pair with both sides <= this (and no 8-mer partition) is one thread's Needleman-Wunsch problem
+
 #endif
 
 struct KbParams
@@ -104,6 +108,7 @@ struct KbBatchDev
 	// stage 3: segments of the surviving candidates, alignment jobs, run arena
 	KbSegX* segx; u32 cap_segx; u32* cseg_off; i32* cseg_n;   // cseg_* indexed like cands (cseg_n < 0: candidate dropped)
 	KbJob* jobs; u32 cap_jobs; u32* runs; u32 cap_runs;
+	u32* job_list;                      // KB_NW_CLASSES + 1 lists of cap_jobs job ids: thread-per-problem size classes (counters[16..19]), then the warp list (counters[20])
 	// stage 4
 	KbReport* reports;                  // indexed like cands
 	KbReadRes* res;
@@ -118,5 +123,9 @@ struct KbBatchDev
 	u32* counters;
 	unsigned long long* work;
 };
+
+#define KB_NCOUNTERS 32
+#define KB_NW_CLASSES 4
+#define KB_NW_SMALL 32   // a fragment pair with both sides <= this (and no 8-mer partition) is one thread's Needleman-Wunsch problem
 
 #endif
