@@ -25,6 +25,19 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 STAGES = ["fm_seed", "sa_locate", "cand_pair", "rescue", "segments", "align", "assemble", "finalize"]
 
 
+def ncu_traffic(kernel, pairs):
+    """DRAM bytes per launch of `kernel` from the newest committed ncu --set full capture, scaled linearly to this launch's read count."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files:
+        return None, None
+    d = json.load(open(files[-1]))
+    k = d["kernels"].get(kernel)
+    if not k:
+        return None, None
+    return k["dram_bytes"] * pairs / d["pairs_per_launch"], "%s (captured at %d pairs/launch, scaled by reads)" % (os.path.basename(files[-1]), d["pairs_per_launch"])
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -58,13 +71,13 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None, "reasons": reasons}
 
 
-def workload(pairs, seed):
+def workload(pairs, seed, prefix=None, err=0.02):
     import parity_util as pu
     from kart_b200 import KartIndex, synth
-    prefix = pu.default_prefix()
+    prefix = prefix or pu.default_prefix()
     idx = KartIndex(prefix)
     genome = pu.genome_of(idx)
-    r1, r2, pos = synth.simulate(genome, pairs, 150, 0.02, seed=seed)
+    r1, r2, pos = synth.simulate(genome, pairs, 150, err, seed=seed)
     return prefix, idx, r1, r2, pos
 
 
@@ -98,12 +111,15 @@ def main():
     ap.add_argument("--pairs", type=int, default=1_000_000, help="read pairs per step per GPU (C2: 1M pairs)")
     ap.add_argument("--cpu-sample-pairs", type=int, default=400_000)
     ap.add_argument("--full-sa", type=int, default=1, help="expand the sampled SA into a full SA in HBM at upload")
+    ap.add_argument("--prefix", default=None, help="index prefix (default: the E. coli index of config C2); e.g. data/_gen/syn/syn400 for the HBM-bound regime")
+    ap.add_argument("--error", type=float, default=0.02)
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     import parity_util as pu
     ncores = os.cpu_count() or 1
-    config = {"workload": "C2: E. coli K-12 (4.64 Mbp, index from test/ecoli.fa), %d synthetic paired-end reads 2x150 bp @ 2%% error per GPU per step, seed %d+rank" % (2 * args.pairs, 1),
-              "reads_per_step_per_gpu": 2 * args.pairs, "read_len": 150, "error_rate": 0.02, "full_sa_in_hbm": bool(args.full_sa),
+    wl = "C2: E. coli K-12 (4.64 Mbp, index from test/ecoli.fa)" if not args.prefix else "index %s" % os.path.basename(args.prefix)
+    config = {"workload": "%s, %d synthetic paired-end reads 2x150 bp @ %g%% error per GPU per step, seed %d+rank" % (wl, 2 * args.pairs, 100 * args.error, 1),
+              "reads_per_step_per_gpu": 2 * args.pairs, "read_len": 150, "error_rate": args.error, "full_sa_in_hbm": bool(args.full_sa),
               "l2": "read batch (%.0f MB) exceeds L2; the E. coli FM-index (4.6 MB) is L2-resident by construction of this config" % (2 * args.pairs * 150 / 1e6)}
 
     if args.impl == "reference":
@@ -112,7 +128,7 @@ def main():
         if not os.path.exists(pu.REF_KART):
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/kart was not built (needs /root/reference at build time)"}))
             return
-        prefix, idx, r1, r2, pos = workload(args.cpu_sample_pairs, 1)
+        prefix, idx, r1, r2, pos = workload(args.cpu_sample_pairs, 1, args.prefix, args.error)
         tmp = tempfile.mkdtemp(prefix="kartbench")
         vals = []
         for it in range(args.warmup + args.steps):
@@ -136,7 +152,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    prefix, idx, r1, r2, pos = workload(args.pairs, 1 + rank)
+    prefix, idx, r1, r2, pos = workload(args.pairs, 1 + rank, args.prefix, args.error)
     reads = pu.interleave(r1, r2)
     n = reads.shape[0]
     m = Mapper(device=local)
@@ -212,7 +228,8 @@ def main():
     peak, which = peaks()
     rk = dom if dom in alg else "fm_seed"
     achieved = alg[rk] / (per[rk] / 1e3) / 1e9
-    roof = {"kernel": "k_" + rk, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    traffic, traffic_src = ncu_traffic("k_" + rk, args.pairs)
+    roof = {"kernel": "k_" + rk, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": which, "dominant_kernel": "k_" + dom, "share_of_step": per[rk] / max(sum(per.values()), 1e-9),
             "note": "E. coli index is L2-resident: achieved GB/s is L2->SM sector traffic expressed against the HBM copy peak; dram traffic is in profiles/"}
     out = {"metric": "mapped reads/s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

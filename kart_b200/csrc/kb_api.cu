@@ -467,9 +467,11 @@ int kb_upload_index(kb_ctx_t* ctx, const kb_index_host_t* h, int expand_sa)
 	ix.mapq_lut = ctx->lut.p; ix.mapq_lut_scores = lut_scores;
 	CK(cudaStreamSynchronize(stream));
 	{
-		// seeding table: the smallest K with 4^K >= 2G, at most 12 (512 MB): past it intervals are narrow, so nearly every
-		// remaining extension step is the one-block case of kb_extend
-		int K = 1; while (K < 12 && (1ull << (2 * K)) < h->seq_len) K++;
+		// seeding table: the smallest K with 4^K >= 2G, at most 14 (8.6 GB of the 180 GB): past it intervals are narrow, so
+		// nearly every remaining extension step is the one-block case of kb_extend. Never longer than MinSeedLength.
+		int K = 1; while (K < 14 && (1ull << (2 * K)) < h->seq_len) K++;
+		{ int ms = derive_min_seed(h->l_pac); if (K > ms) K = ms; }
+		{ const char* e = getenv("KB_KTAB_K"); if (e && atoi(e) >= 0 && atoi(e) <= 14) K = atoi(e); }
 		if (K >= 4)
 		{
 			u64 ne2 = 1ull << (2 * K);

@@ -44,6 +44,18 @@ def main():
             lines.append("")
         open(out, "w").write("\n".join(lines))
         print("wrote", out)
+        # per-kernel DRAM traffic of the largest launch (the resident-batch launch), for bench.py's roofline.traffic
+        import json
+        tr = {}
+        gi, ri, wi, ti = hdr.index("launch__grid_size"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for r in rows[2:]:
+            name = r[ki].split("(")[0]
+            g = int(float(r[gi]))
+            if name not in tr or g > tr[name]["grid"]:
+                tr[name] = {"grid": g, "dram_bytes": float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]], "duration_ms": float(r[ti]) * {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(units[ti], 1.0)}
+        pairs = int(sys.argv[2]) if len(sys.argv) > 2 else 500000
+        json.dump({"tag": tag, "pairs_per_launch": pairs, "kernels": tr}, open(os.path.join(ROOT, "profiles", tag + "_traffic.json"), "w"), indent=1)
     lc = os.path.join(ROOT, "gpurun_out", tag + "_launches.csv")
     if os.path.exists(lc):
         rows = [r for r in csv.reader(open(lc, errors="replace")) if len(r) > 10 and r[0].isdigit()]

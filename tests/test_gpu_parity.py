@@ -143,3 +143,22 @@ def test_cli_100k_pairs_identical_to_reference_t1(built, tmp_path):
     subprocess.run([KART, "-silent", "-i", pu.ECOLI_PREFIX, "-f", f1, "-f2", f2, "-o", ours, "--batch", "60000"], check=True, stdout=subprocess.DEVNULL)
     subprocess.run([pu.REF_KART, "-silent", "-t", "1", "-i", pu.ECOLI_PREFIX, "-f", f1, "-f2", f2, "-o", ref], check=True, stdout=subprocess.DEVNULL)
     assert open(ours, "rb").read() == open(ref, "rb").read()
+
+
+SYN = os.path.join(pu.ROOT, "data", "_gen", "syn", "syn100")
+
+
+@pytest.mark.skipif(not os.path.exists(SYN + ".bwt"), reason="100 Mbp synthetic index (scripts/make_syn_index.py 100 4) not built")
+def test_c3_c4_shaped_on_100mbp_vs_oracle(built):
+    """C3/C4-shaped reads (PE 2x150 @ 1 %, SE 100 @ 8 %) on a 100 Mbp, 4-contig genome with injected repeat families:
+    33-bit-free but HBM-sized index, many rescues, multi-contig coordinates."""
+    idx = KartIndex(SYN)
+    g = pu.genome_of(idx)
+    r1, r2, _ = synth.simulate(g, 6000, 150, 0.01, seed=2)
+    m = pu.make_mapper(idx, paired=True)
+    orc = pu.Oracle(SYN)
+    assert pu.compare_pairs(m, orc, pu.interleave(r1, r2)) == 0
+    assert m.work()["rescues"] > 50
+    r, _, _ = synth.simulate(g, 6000, 100, 0.08, seed=3, paired=False)
+    m = pu.make_mapper(idx, paired=False)
+    assert pu.compare_singles(m, orc, r) == 0
