@@ -110,54 +110,56 @@ __global__ void k_reblock(const u32* bwt, u64 bwt_words, u64 n_new, u32* occ)
 
 __global__ void __launch_bounds__(KB_BLOCK) k_cand_pair(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_cand_pair(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x); }
 __global__ void __launch_bounds__(KB_BLOCK) k_cand_pacbio(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_cand_pacbio(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
-// one thread block per unpaired pair; see kb_pair.cuh "block-cooperative rescue"
+// one warp per unpaired pair; see kb_pair.cuh "warp-cooperative rescue"
 #ifndef KB_EMUL
 __global__ void __launch_bounds__(KB_BLOCK) k_rescue(KbIndexDev ix, KbParams pm, KbBatchDev bt)
 {
+	__shared__ KbRescueJob sj[KB_BLOCK / 32];
 	if (bt.counters[3]) return;
-	int count = (int)bt.counters[4], tid = threadIdx.x, nth = blockDim.x;
-	KbRescueJob* j; KbArena ar = kb_job_arena(bt, blockIdx.x, &j);
-	const u64 base_used = ar.used;
-	for (int k = blockIdx.x; k < count; k += gridDim.x)
+	const int count = (int)bt.counters[4], lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const int gwarp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+	if (gwarp * 32 >= bt.scratch_threads) return;
+	KbRescueJob* j = &sj[wib]; KbArena ar = kb_job_arena(bt, gwarp);
+	for (int k = gwarp; k < count; k += nwarps)
 	{
-		if (tid == 0) kb_rj_begin(pm, bt, j, ar, k);
-		__syncthreads();
+		if (lane == 0) { ar.used = 0; ar.ovf = false; kb_rj_begin(pm, bt, j, ar, k); }
+		__syncwarp();
 		while (true)
 		{
-			if (tid == 0 && !j->done) kb_rj_next(ix, bt, j, ar);
-			__syncthreads();
+			if (lane == 0 && !j->done) kb_rj_next(ix, bt, j, ar);
+			__syncwarp();
 			if (j->done) break;
-			kb_rj_window(ix, j, tid, nth); kb_rj_index_clear(j, tid, nth); __syncthreads();
-			kb_rj_ids(j, tid, nth); kb_rj_index_fill(j, tid, nth); __syncthreads();
-			kb_rj_pairs(j, tid, nth); __syncthreads();
-			if (tid == 0) { j->reindex = 0; kb_rj_cluster(pm, bt, j); }
-			__syncthreads();
+			kb_rj_window(ix, j, lane, 32); kb_rj_index_clear(bt, j, lane, 32); __syncwarp();
+			kb_rj_ids(j, lane, 32); kb_rj_index_fill(j, lane, 32); __syncwarp();
+			kb_rj_pairs(j, lane, 32); __syncwarp();
+			if (lane == 0) { j->reindex = 0; kb_rj_cluster(pm, bt, j); }
+			__syncwarp();
 		}
-		if (tid == 0) { kb_rj_end(pm, bt, j); ar.used = base_used; }
-		__syncthreads();
+		if (lane == 0) kb_rj_end(pm, bt, j);
+		__syncwarp();
 	}
 }
 #else
-static void k_rescue(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulation: the same phases, barriers replaced by loops over tid
+static void k_rescue(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulation: the same phases, barriers replaced by loops over the lanes
 {
 	if (blockIdx.x != 0 || threadIdx.x != 0) return;
 	if (bt.counters[3]) return;
-	int count = (int)bt.counters[4], nth = KB_BLOCK;
-	KbRescueJob* j; KbArena ar = kb_job_arena(bt, 0, &j);
-	const u64 base_used = ar.used;
+	int count = (int)bt.counters[4], nth = 32;
+	static KbRescueJob job; KbRescueJob* j = &job; KbArena ar = kb_job_arena(bt, 0);
 	for (int k = 0; k < count; k++)
 	{
+		ar.used = 0; ar.ovf = false;
 		kb_rj_begin(pm, bt, j, ar, k);
 		while (true)
 		{
 			if (!j->done) kb_rj_next(ix, bt, j, ar);
 			if (j->done) break;
-			for (int t = 0; t < nth; t++) { kb_rj_window(ix, j, t, nth); kb_rj_index_clear(j, t, nth); }
+			for (int t = 0; t < nth; t++) { kb_rj_window(ix, j, t, nth); kb_rj_index_clear(bt, j, t, nth); }
 			for (int t = nth - 1; t >= 0; t--) { kb_rj_ids(j, t, nth); kb_rj_index_fill(j, t, nth); }
 			for (int t = nth - 1; t >= 0; t--) kb_rj_pairs(j, t, nth);   // reversed on purpose: the result must not depend on append order
 			j->reindex = 0; kb_rj_cluster(pm, bt, j);
 		}
-		kb_rj_end(pm, bt, j); ar.used = base_used;
+		kb_rj_end(pm, bt, j);
 	}
 }
 #endif

@@ -32,11 +32,11 @@ KB_HD int kb_rescue_cluster(const KbParams& pm, const KbBatchDev& bt, i64 left, 
 	return best_s;
 }
 
-// ---- block-cooperative rescue ---------------------------------------------------------------------
-// One thread block per pair that failed to pair (RescueUnpairedAlignment). The block walks the anchors in the reference's
-// order; for every reference window the threads share the work: decode the window, 8-mer ids, one diagonal of the
-// (mate x window) match matrix per thread. Control flow is decided by thread 0 between barriers and published through the
-// job record, so the phases below are plain functions of (job, tid, nth) that the host-emulation build can replay.
+// ---- warp-cooperative rescue ----------------------------------------------------------------------
+// One warp per pair that failed to pair (RescueUnpairedAlignment). The warp walks the anchors in the reference's order; for
+// every reference window the lanes share the work: decode the window, 8-mer ids, look every window 8-mer up in a small
+// index of the mate's 8-mers. Control flow is decided by lane 0 between barriers and published through the job record
+// (shared memory), so the phases below are plain functions of (job, tid, nth) that the host-emulation build can replay.
 struct KbRescueJob
 {
 	i32 p, ra, rb, n1, n2, n1o, n2o, l1, l2, est, sc1, sc2, strategy, attempted, mated;
@@ -49,11 +49,10 @@ struct KbRescueJob
 	const u8* mate;
 };
 
-KB_HD KbArena kb_job_arena(const KbBatchDev& bt, int block, KbRescueJob** job)
+KB_HD KbArena kb_job_arena(const KbBatchDev& bt, int warp)
 {
-	KbArena ar; u64 per = bt.scratch_per_thread * 128ull;
-	ar.base = bt.scratch + (u64)block * per; ar.used = 0; ar.cap = per; ar.ovf = false;
-	*job = (KbRescueJob*)ar.alloc(sizeof(KbRescueJob));
+	KbArena ar; u64 per = bt.scratch_per_thread * 32ull;
+	ar.base = bt.scratch + (u64)warp * per; ar.used = 0; ar.cap = per; ar.ovf = false;
 	return ar;
 }
 
@@ -100,7 +99,7 @@ KB_HD void kb_rj_next(const KbIndexDev& ix, const KbBatchDev& bt, KbRescueJob* j
 			j->side = ns; j->idx = -1;
 			if (ns == 0) { j->thr = j->sc1 - 30 < 50 ? 50 : j->sc1 - 30; j->mate = bt.seq + bt.seq_off[j->rb]; j->ml = j->l2; j->next_new = j->n2o; }
 			else { j->thr = j->sc2 - 30 < 50 ? 50 : j->sc2 - 30; j->mate = bt.seq + bt.seq_off[j->ra]; j->ml = j->l1; j->next_new = j->n1o; }
-			kb_kmer_ids(j->ml, j->mate, j->wm); j->reindex = 1;
+			j->reindex = 1;   // the mate's 8-mer ids and their index are (re)built by all lanes: kb_rj_index_clear / _fill
 			continue;
 		}
 		int i = ++j->idx; i64 left, right; int cid, e;
@@ -156,10 +155,17 @@ KB_HD void kb_rj_ids(KbRescueJob* j, int tid, int nth)
 
 // all threads, after a side switch: index the mate's 8-mers (two barrier-separated phases: clear, insert)
 KB_HD u32 kb_rj_slot(u32 id, int mask) { return (id * 40503u + (id >> 7)) & (u32)mask; }
-KB_HD void kb_rj_index_clear(KbRescueJob* j, int tid, int nth)
+KB_HD void kb_rj_index_clear(const KbBatchDev& bt, KbRescueJob* j, int tid, int nth)
 {
 	if (!j->reindex) return;
 	for (int s = tid; s <= j->hmask; s += nth) { j->hkey[s] = 0; j->hhead[s] = -1; }
+	// 8-mer ids of the mate (CreateKmerVecFromReadSeq): a mate of pure bases has id(p) = its 16 packed bits at p; anything
+	// else replays the literal scan on one lane
+	const KbPk* rd = kb_pk_read(bt, j->side == 0 ? j->rb : j->ra);
+	bool dirty = false;
+	for (int w = 0; 32 * w < j->ml; w++) { u32 n4 = kb_load_pk(rd + w).n4; int rem = j->ml - 32 * w; if (rem < 32) n4 &= ~(~0u >> rem); if (n4) dirty = true; }
+	if (dirty) { if (tid == 0) kb_kmer_ids(j->ml, j->mate, j->wm); return; }
+	for (int p = tid; p < j->ml; p += nth) j->wm[p] = p + 8 <= j->ml ? (u32)(kb_read_win(rd, p).code >> 48) : KB_NOKMER;
 }
 KB_HD void kb_rj_index_fill(KbRescueJob* j, int tid, int nth)
 {
