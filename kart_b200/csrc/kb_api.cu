@@ -52,7 +52,7 @@ __global__ void k_ref64(const u8* pac, u64 bytes, u64 words, u64* out)
 	out[w] = v;
 }
 
-__global__ void __launch_bounds__(KB_BLOCK) k_fm_seed(KbIndexDev ix, KbParams pm, KbBatchDev bt)
+__global__ void __launch_bounds__(KB_BLOCK, 10) k_fm_seed(KbIndexDev ix, KbParams pm, KbBatchDev bt)
 {
 	int r = blockIdx.x * blockDim.x + threadIdx.x;
 	u32 steps = 0, blocks = 0;
@@ -110,41 +110,39 @@ __global__ void k_reblock(const u32* bwt, u64 bwt_words, u64 n_new, u32* occ)
 
 __global__ void __launch_bounds__(KB_BLOCK) k_cand_pair(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_cand_pair(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x); }
 __global__ void __launch_bounds__(KB_BLOCK) k_cand_pacbio(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_cand_pacbio(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
-// one warp per unpaired pair; see kb_pair.cuh "warp-cooperative rescue"
+// one thread block per unpaired pair; see kb_pair.cuh "block-cooperative rescue"
 #ifndef KB_EMUL
 __global__ void __launch_bounds__(KB_BLOCK) k_rescue(KbIndexDev ix, KbParams pm, KbBatchDev bt)
 {
-	__shared__ KbRescueJob sj[KB_BLOCK / 32];
+	__shared__ KbRescueJob sj;
 	if (bt.counters[3]) return;
-	const int count = (int)bt.counters[4], lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-	const int gwarp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), nwarps = (int)((gridDim.x * blockDim.x) >> 5);
-	if (gwarp * 32 >= bt.scratch_threads) return;
-	KbRescueJob* j = &sj[wib]; KbArena ar = kb_job_arena(bt, gwarp);
-	for (int k = gwarp; k < count; k += nwarps)
+	const int count = (int)bt.counters[4], tid = threadIdx.x, nth = blockDim.x;
+	KbRescueJob* j = &sj; KbArena ar = kb_job_arena(bt, blockIdx.x);
+	for (int k = blockIdx.x; k < count; k += gridDim.x)
 	{
-		if (lane == 0) { ar.used = 0; ar.ovf = false; kb_rj_begin(pm, bt, j, ar, k); }
-		__syncwarp();
+		if (tid == 0) { ar.used = 0; ar.ovf = false; kb_rj_begin(pm, bt, j, ar, k); }
+		__syncthreads();
 		while (true)
 		{
-			if (lane == 0 && !j->done) kb_rj_next(ix, bt, j, ar);
-			__syncwarp();
+			if (tid == 0 && !j->done) kb_rj_next(ix, bt, j, ar);
+			__syncthreads();
 			if (j->done) break;
-			kb_rj_window(ix, j, lane, 32); kb_rj_index_clear(bt, j, lane, 32); __syncwarp();
-			kb_rj_ids(j, lane, 32); kb_rj_index_fill(j, lane, 32); __syncwarp();
-			kb_rj_pairs(j, lane, 32); __syncwarp();
-			if (lane == 0) { j->reindex = 0; kb_rj_cluster(pm, bt, j); }
-			__syncwarp();
+			kb_rj_window(ix, j, tid, nth); kb_rj_index_clear(bt, j, tid, nth); __syncthreads();
+			kb_rj_ids(j, tid, nth); kb_rj_index_fill(j, tid, nth); __syncthreads();
+			kb_rj_pairs(ix, j, tid, nth); __syncthreads();
+			if (tid == 0) { j->reindex = 0; kb_rj_cluster(pm, bt, j); }
+			__syncthreads();
 		}
-		if (lane == 0) kb_rj_end(pm, bt, j);
-		__syncwarp();
+		if (tid == 0) kb_rj_end(pm, bt, j);
+		__syncthreads();
 	}
 }
 #else
-static void k_rescue(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulation: the same phases, barriers replaced by loops over the lanes
+static void k_rescue(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulation: the same phases, barriers replaced by loops over tid
 {
 	if (blockIdx.x != 0 || threadIdx.x != 0) return;
 	if (bt.counters[3]) return;
-	int count = (int)bt.counters[4], nth = 32;
+	int count = (int)bt.counters[4], nth = KB_BLOCK;
 	static KbRescueJob job; KbRescueJob* j = &job; KbArena ar = kb_job_arena(bt, 0);
 	for (int k = 0; k < count; k++)
 	{
@@ -156,7 +154,7 @@ static void k_rescue(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulation: 
 			if (j->done) break;
 			for (int t = 0; t < nth; t++) { kb_rj_window(ix, j, t, nth); kb_rj_index_clear(bt, j, t, nth); }
 			for (int t = nth - 1; t >= 0; t--) { kb_rj_ids(j, t, nth); kb_rj_index_fill(j, t, nth); }
-			for (int t = nth - 1; t >= 0; t--) kb_rj_pairs(j, t, nth);   // reversed on purpose: the result must not depend on append order
+			for (int t = nth - 1; t >= 0; t--) kb_rj_pairs(ix, j, t, nth);   // reversed on purpose: the result must not depend on append order
 			j->reindex = 0; kb_rj_cluster(pm, bt, j);
 		}
 		kb_rj_end(pm, bt, j);

@@ -32,28 +32,42 @@ KB_HD int kb_rescue_cluster(const KbParams& pm, const KbBatchDev& bt, i64 left, 
 	return best_s;
 }
 
-// ---- warp-cooperative rescue ----------------------------------------------------------------------
-// One warp per pair that failed to pair (RescueUnpairedAlignment). The warp walks the anchors in the reference's order; for
-// every reference window the lanes share the work: decode the window, 8-mer ids, look every window 8-mer up in a small
-// index of the mate's 8-mers. Control flow is decided by lane 0 between barriers and published through the job record
+// ---- block-cooperative rescue ---------------------------------------------------------------------
+// One thread block per pair that failed to pair (RescueUnpairedAlignment). The block walks the anchors in the reference's order;
+// for every reference window the threads share the work: look every window 8-mer up in a small index of the mate's 8-mers
+// and extend the run starts. Control flow is decided by thread 0 between barriers and published through the job record
 // (shared memory), so the phases below are plain functions of (job, tid, nth) that the host-emulation build can replay.
 struct KbRescueJob
 {
 	i32 p, ra, rb, n1, n2, n1o, n2o, l1, l2, est, sc1, sc2, strategy, attempted, mated;
-	i32 side, idx, thr, next_new, done, ovf, clean, slen, cap_pairs, ml, reindex, hmask;
+	i32 side, idx, thr, next_new, done, ovf, clean, mclean, slen, cap_pairs, ml, reindex, hmask;
 	u32 npairs;
 	i64 left;
 	u64 arena_used;
 	u32* wm; u8* win; u32* ww; KbSeg* pairs;
 	u32* hkey; i32* hhead; i32* hnext;   // open-addressing index of the mate's 8-mers: id+1 per slot, chain of positions per slot
-	const u8* mate;
+	const u8* mate; const KbPk* mate_pk;
 };
 
-KB_HD KbArena kb_job_arena(const KbBatchDev& bt, int warp)
+KB_HD KbArena kb_job_arena(const KbBatchDev& bt, int block)
 {
-	KbArena ar; u64 per = bt.scratch_per_thread * 32ull;
-	ar.base = bt.scratch + (u64)warp * per; ar.used = 0; ar.cap = per; ar.ovf = false;
+	KbArena ar; u64 per = bt.scratch_per_thread * 128ull;
+	ar.base = bt.scratch + (u64)block * per; ar.used = 0; ar.cap = per; ar.ovf = false;
 	return ar;
+}
+// 8-mer id at window position g / mate position r. Inside the text (and for a mate of pure bases) the id is the 16 bits of the
+// packed sequence at that position, so neither the window characters nor the id arrays are materialised.
+KB_HD u32 kb_rj_wid(const KbIndexDev& ix, const KbRescueJob* j, int g)
+{
+	if (!j->clean) return j->ww[g];
+	if (g + 8 > j->slen) return KB_NOKMER;
+	u32 inv; return (u32)(kb_ref_win(ix, j->left + g, &inv) >> 48);
+}
+KB_HD u32 kb_rj_mid(const KbRescueJob* j, int r)
+{
+	if (!j->mclean) return j->wm[r];
+	if (r + 8 > j->ml) return KB_NOKMER;
+	return (u32)(kb_read_win(j->mate_pk, r).code >> 48);
 }
 
 // thread 0: set the job up (AlignmentRescue.cpp:86-99)
@@ -137,6 +151,7 @@ KB_HD void kb_rj_next(const KbIndexDev& ix, const KbBatchDev& bt, KbRescueJob* j
 // all threads: reference characters of the window
 KB_HD void kb_rj_window(const KbIndexDev& ix, KbRescueJob* j, int tid, int nth)
 {
+	if (j->clean) return;
 	for (int i = tid; i < j->slen; i += nth) j->win[i] = kb_code_char(kb_ref_code(ix, j->left + i));
 }
 
@@ -144,13 +159,7 @@ KB_HD void kb_rj_window(const KbIndexDev& ix, KbRescueJob* j, int tid, int nth)
 // 16-bit value of the 8 characters at every position; otherwise thread 0 replays the literal scan.
 KB_HD void kb_rj_ids(KbRescueJob* j, int tid, int nth)
 {
-	if (!j->clean) { if (tid == 0) kb_kmer_ids(j->slen, j->win, j->ww); return; }
-	for (int p = tid; p < j->slen; p += nth)
-	{
-		u32 id = KB_NOKMER;
-		if (p + 8 <= j->slen) { id = 0; for (int i = 0; i < 8; i++) id = (id << 2) | (u32)kb_nt4(j->win[p + i]); }
-		j->ww[p] = id;
-	}
+	if (!j->clean && tid == 0) kb_kmer_ids(j->slen, j->win, j->ww);
 }
 
 // all threads, after a side switch: index the mate's 8-mers (two barrier-separated phases: clear, insert)
@@ -164,15 +173,14 @@ KB_HD void kb_rj_index_clear(const KbBatchDev& bt, KbRescueJob* j, int tid, int 
 	const KbPk* rd = kb_pk_read(bt, j->side == 0 ? j->rb : j->ra);
 	bool dirty = false;
 	for (int w = 0; 32 * w < j->ml; w++) { u32 n4 = kb_load_pk(rd + w).n4; int rem = j->ml - 32 * w; if (rem < 32) n4 &= ~(~0u >> rem); if (n4) dirty = true; }
-	if (dirty) { if (tid == 0) kb_kmer_ids(j->ml, j->mate, j->wm); return; }
-	for (int p = tid; p < j->ml; p += nth) j->wm[p] = p + 8 <= j->ml ? (u32)(kb_read_win(rd, p).code >> 48) : KB_NOKMER;
+	if (tid == 0) { j->mclean = dirty ? 0 : 1; j->mate_pk = rd; if (dirty) kb_kmer_ids(j->ml, j->mate, j->wm); }
 }
 KB_HD void kb_rj_index_fill(KbRescueJob* j, int tid, int nth)
 {
 	if (!j->reindex) return;
 	for (int r = tid; r < j->ml; r += nth)
 	{
-		u32 id = j->wm[r]; if (id == KB_NOKMER) continue;
+		u32 id = kb_rj_mid(j, r); if (id == KB_NOKMER) continue;
 		u32 s = kb_rj_slot(id, j->hmask);
 		while (true)
 		{
@@ -188,20 +196,20 @@ KB_HD void kb_rj_index_fill(KbRescueJob* j, int tid, int nth)
 // IdentifyCommonKmers(MaxShift = slen) + GenerateSimplePairsFromCommonKmers(10): every window position looks its 8-mer up
 // in the mate's index; a match (r,g) whose predecessor (r-1,g-1) is no match starts a run, which is then extended.
 // (|g - r| < slen holds for every pair since r < ml <= slen and g < slen.)
-KB_HD void kb_rj_pairs(KbRescueJob* j, int tid, int nth)
+KB_HD void kb_rj_pairs(const KbIndexDev& ix, KbRescueJob* j, int tid, int nth)
 {
-	const u32* w1 = j->wm; const u32* w2 = j->ww; const int ml = j->ml, sl = j->slen;
+	const int ml = j->ml, sl = j->slen;
 	for (int g = tid; g < sl; g += nth)
 	{
-		u32 id = w2[g]; if (id == KB_NOKMER) continue;
+		u32 id = kb_rj_wid(ix, j, g); if (id == KB_NOKMER) continue;
 		u32 s = kb_rj_slot(id, j->hmask), key;
 		while ((key = j->hkey[s]) != 0u && key != id + 1u) s = (s + 1u) & (u32)j->hmask;
 		if (key == 0u) continue;
 		for (int r = j->hhead[s]; r >= 0; r = j->hnext[r])
 		{
-			if (r > 0 && g > 0 && w1[r - 1] != KB_NOKMER && w1[r - 1] == w2[g - 1]) continue;   // not the start of its run
+			if (r > 0 && g > 0) { u32 a = kb_rj_mid(j, r - 1); if (a != KB_NOKMER && a == kb_rj_wid(ix, j, g - 1)) continue; }   // not the start of its run
 			int run = 1;
-			while (r + run < ml && g + run < sl && w1[r + run] != KB_NOKMER && w1[r + run] == w2[g + run]) run++;
+			while (r + run < ml && g + run < sl) { u32 a = kb_rj_mid(j, r + run); if (a == KB_NOKMER || a != kb_rj_wid(ix, j, g + run)) break; run++; }
 			int l = 8 + run - 1;
 			if (l < 10) continue;
 			u32 slot = KB_ATOMIC_ADD(&j->npairs, 1u);

@@ -11,7 +11,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
-#define __launch_bounds__(x)
+#define __launch_bounds__(...)
 struct kb_dim3 { unsigned x, y, z; };
 static thread_local kb_dim3 blockIdx, blockDim, threadIdx, gridDim;
 typedef int cudaError_t;
