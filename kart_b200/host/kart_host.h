@@ -59,4 +59,22 @@ int run_mapping(const RunOptions& opt, const HostIndex& idx);     // Mapping(), 
 void sam_header(std::string& out, const HostIndex& idx);
 void sam_read_line(std::string& out, const HostIndex& idx, const ReadBatch& b, int r, bool stored_fwd, const kb_aln_t& a, const uint32_t* cigar, bool fastq);
 
+
+// BAM output (src/Mapping.cpp:610-621 via htslib sam_parse1 + sam_write1), see bam_writer.cpp
+void bam_tables_init();
+void bam_read_record(std::string& out, std::vector<uint32_t>& rec_end, const std::vector<int32_t>& name2id, const ReadBatch& b, int r, bool stored_fwd,
+                     const kb_aln_t& a, const uint32_t* cigar, bool fastq);
+class BamWriter
+{
+public:
+	bool open(const char* path, int n_threads);
+	void write_header(const std::string& text, const std::vector<std::string>& names, const std::vector<int64_t>& lens);
+	void append(const std::string& bytes, const std::vector<uint32_t>& unit_end, bool records);   // unit_end: end offset of every record in `bytes`
+	bool close();
+private:
+	void emit(const std::string& stream, const std::vector<size_t>& cuts);
+	void flush();
+	FILE* fp = nullptr; int threads = 1; std::string pend;
+};
+
 #endif

@@ -84,12 +84,29 @@ int run_mapping(const RunOptions& opt, const HostIndex& idx)
 	kb_index_host_t hi; idx.describe(&hi);
 	if ((rc = kb_upload_index(ctx, &hi, opt.expand_sa ? 1 : 0)) != 0) { fprintf(stderr, "Error! index upload failed: %s (%s)\n", kb_strerror(rc), kb_last_error(ctx)); kb_destroy(ctx); return 1; }
 
-	FILE* out = nullptr;
+	FILE* out = nullptr; BamWriter bam; const bool to_bam = opt.out_format == 1 && !opt.debug;
+	std::vector<int32_t> name2id(idx.chr_name.size(), -1);   // bam_name2id: a repeated @SQ name keeps its first id (htslib sam.c:725-733)
 	if (!opt.debug)
 	{
-		out = fopen(opt.out_name.c_str(), "w");
-		if (!out) { fprintf(stderr, "Error! Cannot open file [%s]\n", opt.out_name.c_str()); kb_destroy(ctx); exit(1); }
-		std::string h; sam_header(h, idx); fwrite(h.data(), 1, h.size(), out);
+		std::string h; sam_header(h, idx);
+		if (to_bam)
+		{
+			if (!bam.open(opt.out_name.c_str(), opt.threads)) { fprintf(stderr, "Error! Cannot open file [%s]\n", opt.out_name.c_str()); kb_destroy(ctx); exit(1); }
+			std::vector<std::string> un; std::vector<int64_t> ul;
+			for (size_t i = 0; i < idx.chr_name.size(); i++)
+			{
+				size_t k = 0; while (k < un.size() && un[k] != idx.chr_name[i]) k++;
+				if (k == un.size()) { un.push_back(idx.chr_name[i]); ul.push_back(idx.chr_len[i]); }
+				name2id[i] = (int32_t)k;
+			}
+			bam_tables_init(); bam.write_header(h, un, ul);
+		}
+		else
+		{
+			out = fopen(opt.out_name.c_str(), "w");
+			if (!out) { fprintf(stderr, "Error! Cannot open file [%s]\n", opt.out_name.c_str()); kb_destroy(ctx); exit(1); }
+			fwrite(h.data(), 1, h.size(), out);
+		}
 	}
 	if (opt.silent) fprintf(stdout, "Start read mapping...\n");
 	time_t t0 = time(NULL);
@@ -142,7 +159,7 @@ int run_mapping(const RunOptions& opt, const HostIndex& idx)
 			}
 			if (rc) { fprintf(stderr, "\nError! GPU mapping failed: %s (%s)\n", kb_strerror(rc), kb_last_error(ctx)); reader.join(); break; }
 			// format SAM in parallel slices, write in input order
-			std::vector<std::string> parts(fmt_threads); std::vector<std::thread> th;
+			std::vector<std::string> parts(fmt_threads); std::vector<std::thread> th; std::vector<std::vector<uint32_t>> rec_ends(fmt_threads);
 			std::vector<long long> um(fmt_threads, 0), uq(fmt_threads, 0);
 			for (int t = 0; t < fmt_threads; t++) th.emplace_back([&, t]() {
 				int lo = (int)((long long)n * t / fmt_threads), hi = (int)((long long)n * (t + 1) / fmt_threads);
@@ -154,11 +171,13 @@ int run_mapping(const RunOptions& opt, const HostIndex& idx)
 					const kb_aln_t& a = in_pe ? br.aln[r] : tail.aln[r - n_pe];
 					const uint32_t* cg = in_pe ? br.cigar.data() : tail.cigar.data();
 					if (a.score == 0) um[t]++; else if (a.mapq == 60) uq[t]++;
-					sam_read_line(o, idx, cur, r, !(in_pe && (r & 1)), a, cg, fastq);   // mate 2 of a mapped pair is held reverse-complemented
+					if (to_bam) bam_read_record(o, rec_ends[t], name2id, cur, r, !(in_pe && (r & 1)), a, cg, fastq);
+					else sam_read_line(o, idx, cur, r, !(in_pe && (r & 1)), a, cg, fastq);   // mate 2 of a mapped pair is held reverse-complemented
 				}
 			});
 			for (auto& t : th) t.join();
 			if (out) for (auto& p : parts) fwrite(p.data(), 1, p.size(), out);
+			if (to_bam) for (int t = 0; t < fmt_threads; t++) bam.append(parts[t], rec_ends[t], true);
 			for (int t = 0; t < fmt_threads; t++) { unmapped += um[t]; unique += uq[t]; }
 			total += n;
 			reader.join();
@@ -168,6 +187,7 @@ int run_mapping(const RunOptions& opt, const HostIndex& idx)
 	}
 	fprintf(stdout, "\rAll the %lld %s reads have been processed in %lld seconds.\n", total, pair_end ? "paired-end" : "single-end", (long long)(time(NULL) - t0));
 	if (out) fclose(out);
+	if (to_bam) bam.close();
 	if (total > 0)
 	{
 		if (pair_end) fprintf(stdout, "\t# of total mapped sequences = %lld (sensitivity = %.2f%%)\n\t# of paired sequences = %lld (%.2f%%), average insert size = %d\n", total - unmapped, (int)(10000 * (1.0 * (total - unmapped) / total) + 0.5) / 100.0, st.iPaired, (int)(10000 * (1.0 * st.iPaired / total) + 0.5) / 100.0, (st.iPaired > 1 ? (int)(st.iDistance / (st.iPaired >> 1)) : 0));

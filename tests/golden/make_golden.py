@@ -12,6 +12,8 @@ Outputs (all under tests/golden/):
   nw_vectors.txt                      200 nw_alignment input/output pairs
   frag_vectors.txt                    8-mer partition (+IdentifyNormalPairs) of 60 fragment pairs
   ecoli_c1.md5                        md5 of the reference SAM for run_test.sh (C1), raw and `LC_ALL=C sort`ed
+  pe150.bam se100.bam pb3k.bam        the same three runs with `-bo` (reference linked against its vendored htslib 1.5:
+                                      oracle/_ref/kart_hts); bam_zlib.txt records the zlib version the bytes depend on
 """
 import hashlib
 import os
@@ -32,7 +34,22 @@ def kart(prefix, args, out):
     subprocess.run([pu.REF_KART, "-silent", "-t", "1", "-i", prefix] + args + ["-o", out], check=True, stdout=subprocess.DEVNULL)
 
 
+def kart_bam(prefix, args, out):
+    subprocess.run([os.path.join(os.path.dirname(pu.REF_KART), "kart_hts"), "-silent", "-t", "1", "-i", prefix] + args + ["-bo", out], check=True, stdout=subprocess.DEVNULL)
+
+
+def bam_goldens():
+    import zlib
+    g = HERE + "/"
+    kart_bam(pu.MINI_PREFIX, ["-f", g + "pe150_1.fq", "-f2", g + "pe150_2.fq"], g + "pe150.bam")
+    kart_bam(pu.MINI_PREFIX, ["-f", g + "se100.fq"], g + "se100.bam")
+    kart_bam(pu.MINI_PREFIX, ["-pacbio", "-f", g + "pb3k.fq"], g + "pb3k.bam")
+    open(g + "bam_zlib.txt", "w").write(zlib.ZLIB_RUNTIME_VERSION + "\n")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "bam":
+        return bam_goldens()
     assert os.path.exists(pu.REF_KART) and os.path.exists(pu.REF_LIB), "build oracle/_ref first (python -c 'import __graft_entry__ as g; g.build()')"
     mini = os.path.join(HERE, "mini")
     os.makedirs(mini, exist_ok=True)

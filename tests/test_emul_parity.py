@@ -74,6 +74,43 @@ def test_cli_sam_is_byte_identical_to_reference(kart_emul, tmp_path, tag, args):
     assert open(out, "rb").read() == open(os.path.join(G, tag + ".sam"), "rb").read()
 
 
+@pytest.mark.parametrize("tag,args", [("pe150", ["-f", "pe150_1.fq", "-f2", "pe150_2.fq"]), ("se100", ["-f", "se100.fq"]), ("pb3k", ["-pacbio", "-f", "pb3k.fq"])])
+def test_cli_bam_is_byte_identical_to_reference(kart_emul, tmp_path, tag, args):
+    """-bo: the freshly written BAM encoder + BGZF blocker (kart_b200/host/bam_writer.cpp, parallel deflate) reproduces the
+    bytes of the reference linked against its vendored htslib 1.5 (goldens: tests/golden/*.bam, made by make_golden.py bam)."""
+    out = str(tmp_path / (tag + ".bam"))
+    a = [os.path.join(G, x) if x.endswith(".fq") else x for x in args]
+    subprocess.run([kart_emul, "-silent", "-t", "3", "-i", pu.MINI_PREFIX] + a + ["-bo", out, "--batch", "400"], check=True, stdout=subprocess.DEVNULL)
+    assert pu.bam_equal(out, os.path.join(G, tag + ".bam"))
+
+
+KART_HTS = os.path.join(pu.ROOT, "oracle", "_ref", "kart_hts")
+
+
+@pytest.mark.skipif(not os.path.exists(KART_HTS), reason="oracle/_ref/kart_hts (reference + its htslib) not built")
+def test_cli_bam_fasta_unmapped_and_odd_characters(kart_emul, tmp_path):
+    """FASTA input (QUAL 0xff), unmappable reads (bin 4680, flag |= 4), lower-case and IUPAC characters (4-bit codes), long names."""
+    rng = np.random.default_rng(5)
+    lines = open(os.path.join(G, "se100.fq")).read().split("\n")
+    fa, fq = [], []
+    for i in range(0, len(lines) - 1, 4):
+        s = lines[i + 1]
+        if i % 40 == 0:
+            s = "".join("ACGT"[k] for k in rng.integers(0, 4, size=100))
+        if i % 28 == 0:
+            s = s[:10] + "nRYK" + s[14:].lower()
+        name = lines[i][1:] + ("x" * 260 if i == 8 else "")
+        fa += [">" + name, s]
+        fq += ["@" + name + " extra words", s, "+", "".join(chr(33 + int(q)) for q in rng.integers(0, 42, size=len(s)))]
+    for ext, rec in (("fa", fa), ("fq", fq)):
+        f = str(tmp_path / ("in." + ext))
+        open(f, "w").write("\n".join(rec) + "\n")
+        ours, ref = str(tmp_path / ("o_" + ext + ".bam")), str(tmp_path / ("r_" + ext + ".bam"))
+        subprocess.run([kart_emul, "-silent", "-t", "2", "-i", pu.MINI_PREFIX, "-f", f, "-bo", ours], check=True, stdout=subprocess.DEVNULL)
+        subprocess.run([KART_HTS, "-silent", "-t", "1", "-i", pu.MINI_PREFIX, "-f", f, "-bo", ref], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        assert open(ours, "rb").read() == open(ref, "rb").read()
+
+
 def test_cli_interleaved_and_gz_inputs(kart_emul, tmp_path):
     import gzip
     a = open(os.path.join(G, "pe150_1.fq"), "rb").read().split(b"\n")

@@ -133,6 +133,15 @@ def test_cli_golden_sam(built, tmp_path, tag, args):
     assert open(out, "rb").read() == open(os.path.join(G, tag + ".sam"), "rb").read()
 
 
+@pytest.mark.parametrize("tag,args", [("pe150", ["-f", "pe150_1.fq", "-f2", "pe150_2.fq"]), ("pb3k", ["-pacbio", "-f", "pb3k.fq"])])
+def test_cli_golden_bam(built, tmp_path, tag, args):
+    """-bo through the CUDA CLI: the reference's BAM bytes (htslib 1.5 record encoding and BGZF block policy)."""
+    out = str(tmp_path / (tag + ".bam"))
+    a = [os.path.join(G, x) if x.endswith(".fq") else x for x in args]
+    subprocess.run([KART, "-silent", "-i", pu.MINI_PREFIX] + a + ["-bo", out], check=True, stdout=subprocess.DEVNULL)
+    assert pu.bam_equal(out, os.path.join(G, tag + ".bam"))
+
+
 @pytest.mark.skipif(not (os.path.exists(pu.REF_KART) and pu.have_ecoli()), reason="needs oracle/_ref/kart and the E. coli index (built in the build container, shipped with the snapshot)")
 def test_cli_100k_pairs_identical_to_reference_t1(built, tmp_path):
     """C2-shaped input through the real CLI: byte-identical to `kart -t 1` including the per-chunk EstDistance recurrence."""
