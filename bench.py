@@ -25,17 +25,22 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 STAGES = ["fm_seed", "sa_locate", "cand_pair", "rescue", "segments", "align", "assemble", "finalize"]
 
 
-def ncu_traffic(kernel, pairs):
-    """DRAM bytes per launch of `kernel` from the newest committed ncu --set full capture, scaled linearly to this launch's read count."""
+def ncu_traffic(kernel, reads, syn):
+    """DRAM bytes per launch of `kernel` from the newest committed ncu --set full capture of this kind of workload (C2, or a
+    --prefix index: tags ending in 'syn'), scaled linearly from the captured launch's read count (one thread per read: grid x block)
+    to this launch's."""
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    import re
+    files = [f for f in glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")) if ("syn" in os.path.basename(f)) == bool(syn)]
     if not files:
         return None, None
-    d = json.load(open(files[-1]))
+    f = max(files, key=lambda p: int(re.findall(r"r(\d+)", os.path.basename(p))[0]))
+    d = json.load(open(f))
     k = d["kernels"].get(kernel)
     if not k:
         return None, None
-    return k["dram_bytes"] * pairs / d["pairs_per_launch"], "%s (captured at %d pairs/launch, scaled by reads)" % (os.path.basename(files[-1]), d["pairs_per_launch"])
+    cap_reads = k["grid"] * k.get("block", 128)
+    return k["dram_bytes"] * reads / cap_reads, "%s (captured at %d reads/launch, scaled by reads)" % (os.path.basename(f), cap_reads)
 
 
 def peaks():
@@ -230,7 +235,7 @@ def main():
     peak, which = peaks()
     rk = dom if dom in alg else "fm_seed"
     achieved = alg[rk] / (per[rk] / 1e3) / 1e9
-    traffic, traffic_src = ncu_traffic("k_" + rk, args.pairs)
+    traffic, traffic_src = ncu_traffic("k_" + rk, n, args.prefix)
     roof = {"kernel": "k_" + rk, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": which, "dominant_kernel": "k_" + dom, "share_of_step": per[rk] / max(sum(per.values()), 1e-9),
             "note": ("E. coli index is L2-resident: achieved GB/s is L2->SM sector traffic expressed against the HBM copy peak; dram traffic is in profiles/"

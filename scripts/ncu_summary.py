@@ -53,7 +53,7 @@ def main():
             name = r[ki].split("(")[0]
             g = int(float(r[gi]))
             if name not in tr or g > tr[name]["grid"]:
-                tr[name] = {"grid": g, "dram_bytes": float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]], "duration_ms": float(r[ti]) * {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(units[ti], 1.0)}
+                tr[name] = {"grid": g, "block": int(float(r[hdr.index("launch__block_size")])), "dram_bytes": float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]], "duration_ms": float(r[ti]) * {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(units[ti], 1.0)}
         pairs = int(sys.argv[2]) if len(sys.argv) > 2 else 500000
         json.dump({"tag": tag, "pairs_per_launch": pairs, "kernels": tr}, open(os.path.join(ROOT, "profiles", tag + "_traffic.json"), "w"), indent=1)
     lc = os.path.join(ROOT, "gpurun_out", tag + "_launches.csv")
