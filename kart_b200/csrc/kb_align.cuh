@@ -327,7 +327,6 @@ struct KbNwWarp
 	int* bS[2]; int* bT[2];     // stored boundary row (row i0), only when m > 32: read buffer = cur, written buffer = cur ^ 1
 	u8* code2;                  // nt4 codes of c2, 1-based
 	u8* tb; u32 stride;         // traceback: 2 bits per cell (bit 0: S==R, bit 1: S==T), 4 cells per byte, row-major
-	u32* rev;                   // traceback scratch (m + n runs)
 	int xs[2][32], xt[2][32];   // neighbour exchange, indexed [step & 1][lane]
 	int i0, h, cur;
 	u64 mark, fmark;
@@ -350,7 +349,6 @@ KB_HD bool kb_nww_setup(KbNwWarp& w, KbArena& fast, KbArena& ar, const u8* c1, i
 	w.code2 = (u8*)kb_alloc2(fast, ar, (u64)n + 1);
 	w.stride = ((u32)n + 3) >> 2;
 	w.tb = (u8*)kb_alloc2(fast, ar, (u64)w.stride * (u64)m);
-	w.rev = (u32*)kb_alloc2(fast, ar, (u64)(m + n) * 4);
 	for (int k = 0; k < 2; k++)
 	{
 		w.bS[k] = m > 32 ? (int*)kb_alloc2(fast, ar, (u64)(n + 1) * 4) : nullptr;
@@ -409,35 +407,32 @@ KB_HD bool kb_nww_strip_end(KbNwWarp& w)
 	return true;
 }
 
-// lane 0: traceback (nw_alignment.cpp:59-72): gap-in-read first, then gap-in-genome, else diagonal; appends the runs to acc
-KB_HD void kb_nww_traceback(KbNwWarp& w, KbArena& fast, KbArena& ar, KbRuns& acc)
+// lane 0: traceback (nw_alignment.cpp:59-72): gap-in-read first, then gap-in-genome, else diagonal. The runs are written
+// backwards from out[cap) (cap >= m + n), so they end up in alignment order at out[first .. cap); returns first.
+KB_HD int kb_nww_traceback(KbNwWarp& w, KbArena& fast, KbArena& ar, u32* out, int cap, int* ident_out, int* aligned_out)
 {
 	int m = w.m, n = w.n;
-	u32* rev = w.rev;
-	if (rev != nullptr)
+	int i = m, j = n, wr = cap, ident = 0, aligned = 0, cur = -1, len = 0;
+	while (i > 0 || j > 0)
 	{
-		int i = m, j = n, nr = 0, ident = 0, aligned = 0, cur = -1, len = 0;
-		while (i > 0 || j > 0)
+		int type;
+		if (i == 0) type = KB_RUN_D;
+		else if (j == 0) type = KB_RUN_I;
+		else
 		{
-			int type;
-			if (i == 0) type = KB_RUN_D;
-			else if (j == 0) type = KB_RUN_I;
-			else
-			{
-				int bits = (w.tb[(u64)w.stride * (u64)(i - 1) + (u64)((j - 1) >> 2)] >> (((j - 1) & 3) << 1)) & 3;
-				type = (bits & 1) ? KB_RUN_D : ((bits & 2) ? KB_RUN_I : KB_RUN_M);
-			}
-			if (type == KB_RUN_D) j--;
-			else if (type == KB_RUN_I) i--;
-			else { i--; j--; aligned++; if (w.c1[i] == w.c2[j]) ident++; }
-			if (type == cur) len++;
-			else { if (len > 0) rev[nr++] = ((u32)len << 2) | (u32)cur; cur = type; len = 1; }
+			int bits = (w.tb[(u64)w.stride * (u64)(i - 1) + (u64)((j - 1) >> 2)] >> (((j - 1) & 3) << 1)) & 3;
+			type = (bits & 1) ? KB_RUN_D : ((bits & 2) ? KB_RUN_I : KB_RUN_M);
 		}
-		if (len > 0) rev[nr++] = ((u32)len << 2) | (u32)cur;
-		for (int k = nr - 1; k >= 0; k--) acc.push((int)(rev[k] & 3), (int)(rev[k] >> 2));
-		acc.ident += ident; acc.aligned += aligned;
+		if (type == KB_RUN_D) j--;
+		else if (type == KB_RUN_I) i--;
+		else { i--; j--; aligned++; if (w.c1[i] == w.c2[j]) ident++; }
+		if (type == cur) len++;
+		else { if (len > 0) out[--wr] = ((u32)len << 2) | (u32)cur; cur = type; len = 1; }
 	}
+	if (len > 0) out[--wr] = ((u32)len << 2) | (u32)cur;
+	*ident_out = ident; *aligned_out = aligned;
 	ar.used = w.mark; fast.used = w.fmark;
+	return wr;
 }
 
 // ================================================================================================
@@ -449,16 +444,57 @@ KB_HD void kb_nww_traceback(KbNwWarp& w, KbArena& fast, KbArena& ar, KbRuns& acc
 enum { KB_W_FRAG = 0, KB_W_NW = 1, KB_W_COPY = 2, KB_W_INS = 3, KB_W_DEL = 4 };
 struct KbWork { i32 r0, rl, g0, gl, kind, pad; };
 
+// nw_alignment size class of an (rl x gl) problem at text position g
+KB_HD u32 kb_piece_class(const KbIndexDev& ix, int rl, int gl, i64 g)
+{
+	const int mx = rl > gl ? rl : gl;
+	if (mx > KB_NW_TMAX || g < 0 || g + gl > ix.G2) return (u32)(KB_NW_CLASSES - 1);   // too large for one thread, or touching the outside of the text
+	return mx <= 32 ? (u32)((mx - 1) >> 3) : (mx <= 64 ? 4u : 5u);
+}
+// registers one nw_alignment problem; false when the piece arena is full (flagged)
+KB_HD bool kb_emit_piece(const KbIndexDev& ix, const KbBatchDev& bt, u32 job, i64 job_gpos, int r0, int rl, int g0, int gl, u32 out_off, u32 whole)
+{
+	const u32 id = KB_ATOMIC_ADD(&bt.counters[24], 1u);
+	if (id >= bt.cap_pieces) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_JOBS); return false; }
+	KbPiece pc; pc.job = job; pc.r0 = r0; pc.rl = rl; pc.g0 = g0; pc.gl = gl; pc.out_off = out_off; pc.whole = whole; pc.pad = 0;
+	bt.pieces[id] = pc;
+	const u32 cls = kb_piece_class(ix, rl, gl, job_gpos + g0);
+	const u32 slot = KB_ATOMIC_ADD(&bt.counters[16 + cls], 1u);
+	bt.piece_list[(size_t)cls * bt.cap_pieces + slot] = id;
+	return true;
+}
+
+// Where the pieces of a partitioned job go: the job's slice of the run arena (zeroed beforehand), filled left to right.
+// Every piece owns max(1, rl + gl) consecutive entries: literal pieces (pure gaps, copies) store their single run there,
+// nw_alignment pieces are registered and their solver writes into the same entries later; k_align_gather then squeezes
+// the zeros out and merges equal neighbours, which is what the reference's sequential AddNewCigarElements calls produce.
+struct KbSink
+{
+	const KbIndexDev* ix; const KbBatchDev* bt; u32 job; i64 gpos; u32 base, cap, cur; int ident, aligned; bool ovf;
+	KB_HD void lit(int type, int len, int span)
+	{
+		if (len <= 0) return;
+		if (cur + (u32)span > cap) { ovf = true; return; }
+		bt->runs[base + cur] = ((u32)len << 2) | (u32)type; cur += (u32)span;
+	}
+	KB_HD void piece(int r0, int rl, int g0, int gl)
+	{
+		if (cur + (u32)(rl + gl) > cap) { ovf = true; return; }
+		if (!kb_emit_piece(*ix, *bt, job, gpos, r0, rl, g0, gl, base + cur, 0u)) ovf = true;
+		cur += (u32)(rl + gl);
+	}
+};
+
 struct KbFragIter
 {
-	const KbParams* pm; KbArena* ar; const u8* f1; const u8* f2; KbRuns* acc;
+	const KbParams* pm; KbArena* ar; const u8* f1; const u8* f2; KbSink* sink;
 	KbWork* st; int sp, scap; u64 mark0;
 	// the fragment being partitioned (between next() == 2 and part_finish())
 	KbWork cur; u32* w1; u32* w2; KbSeg* raw; int shift, cap, dirty; u32 np; u64 pmark;
 
-	KB_HD bool init(const KbParams* pm_, KbArena* ar_, const u8* f1_, int rl0, const u8* f2_, int gl0, KbRuns* acc_)
+	KB_HD bool init(const KbParams* pm_, KbArena* ar_, const u8* f1_, int rl0, const u8* f2_, int gl0, KbSink* sink_)
 	{
-		pm = pm_; ar = ar_; f1 = f1_; f2 = f2_; acc = acc_; mark0 = ar->used; sp = 0;
+		pm = pm_; ar = ar_; f1 = f1_; f2 = f2_; sink = sink_; mark0 = ar->used; sp = 0;
 		scap = rl0 + gl0 + 4;
 		st = (KbWork*)ar->alloc((u64)scap * sizeof(KbWork));
 		if (st == nullptr) return false;
@@ -466,20 +502,20 @@ struct KbFragIter
 		return true;
 	}
 
-	// one lane. 1: *piece (r0,rl,g0,gl) needs nw_alignment; 2: a fragment is ready to be partitioned (part_scan, part_ids,
-	// part_pairs by all lanes with a barrier after each, then part_finish by one lane); 0: finished (or the arena overflowed)
-	KB_HD int next(KbWork* piece)
+	// one lane. 2: a fragment is ready to be partitioned (part_scan, part_ids, part_pairs by all lanes with a barrier after
+	// each, then part_finish by one lane); 0: finished (or something overflowed). Everything else is written to the sink.
+	KB_HD int next()
 	{
-		while (sp > 0 && !ar->ovf)
+		while (sp > 0 && !ar->ovf && !sink->ovf)
 		{
 			const KbWork e = st[--sp];
 			const u8* a = f1 + e.r0; const u8* b = f2 + e.g0;
-			if (e.kind == KB_W_INS) { acc->push(KB_RUN_I, e.rl); continue; }
-			if (e.kind == KB_W_DEL) { acc->push(KB_RUN_D, e.gl); continue; }
+			if (e.kind == KB_W_INS) { sink->lit(KB_RUN_I, e.rl, e.rl); continue; }
+			if (e.kind == KB_W_DEL) { sink->lit(KB_RUN_D, e.gl, e.gl); continue; }
 			if (e.kind == KB_W_COPY)
 			{
 				int id = 0; for (int t = 0; t < e.rl; t++) if (a[t] == b[t]) id++;
-				acc->push(KB_RUN_M, e.rl); acc->ident += id; acc->aligned += e.rl;
+				sink->lit(KB_RUN_M, e.rl, e.rl + e.gl); sink->ident += id; sink->aligned += e.rl;
 				continue;
 			}
 			if (e.kind == KB_W_FRAG && e.rl > 30 && e.gl > 30)
@@ -496,8 +532,7 @@ struct KbFragIter
 				cur = e; np = 0; dirty = 0;
 				return 2;
 			}
-			*piece = e;
-			return 1;
+			sink->piece(e.r0, e.rl, e.g0, e.gl);
 		}
 		return 0;
 	}
@@ -542,23 +577,23 @@ struct KbFragIter
 			if ((int)slot < cap) { KbSeg sg; sg.simple = 1; sg.rpos = r; sg.gpos = (i64)g; sg.rlen = sg.glen = 8 + run - 1; raw[slot] = sg; }
 		}
 	}
-	// one lane: IdentifyNormalPairs on the runs; pushes the pieces (or hands the whole fragment to NW: returns true and sets *piece)
-	KB_HD bool part_finish(KbWork* piece)
+	// one lane: IdentifyNormalPairs on the runs; pushes the pieces, or registers the whole fragment as one nw_alignment problem
+	KB_HD void part_finish()
 	{
 		const KbWork e = cur; const int rl = e.rl, gl = e.gl;
-		if ((int)np > cap) { ar->ovf = true; return false; }
+		if ((int)np > cap) { ar->ovf = true; return; }
 		int tot = 0; KbSeg* part = nullptr; const int n = (int)np;
 		if (n > 0)
 		{
 			kb_sort_segs<true>(raw, n);
 			part = (KbSeg*)ar->alloc((u64)(2 * n + 2) * sizeof(KbSeg));
 			i32* order = (i32*)ar->alloc((u64)n * 4);
-			if (ar->ovf) return false;
+			if (ar->ovf) return;
 			tot = kb_fill_pairs(rl, gl, raw, n, part, order);
 		}
 		if (tot > 0)
 		{
-			if (sp + tot > scap) { ar->ovf = true; return false; }
+			if (sp + tot > scap) { ar->ovf = true; return; }
 			for (int i = tot - 1; i >= 0; i--)   // reversed, so that pops come out left to right
 			{
 				const KbSeg p = part[i];
@@ -572,11 +607,10 @@ struct KbFragIter
 				st[sp++] = w;
 			}
 			ar->used = pmark;
-			return false;
+			return;
 		}
 		ar->used = pmark;
-		*piece = e;
-		return true;
+		sink->piece(e.r0, e.rl, e.g0, e.gl);
 	}
 };
 
@@ -669,12 +703,10 @@ KB_HD void kb_classify_segment(const KbIndexDev& ix, const KbParams& pm, const K
 	if ((u64)ro + need > (u64)bt.cap_runs) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_RUNS); return; }
 	KbJob jb; jb.gpos = sp.gpos; jb.read = (u32)r; jb.rpos = sp.rpos; jb.rlen = sp.rlen; jb.glen = sp.glen; jb.run_off = ro; jb.nruns = 0; jb.ident = 0; jb.aligned = 0;
 	bt.jobs[id] = jb;
-	// route: one thread (by size class) when it is a single small NW problem inside the text, else the warp kernel
-	const int mx = sp.rlen > sp.glen ? sp.rlen : sp.glen;
-	const bool small = mx <= KB_NW_SMALL && !(sp.rlen > 30 && sp.glen > 30) && sp.rlen > 0 && sp.glen > 0 && sp.gpos >= 0 && sp.gpos + sp.glen <= ix.G2;
-	const u32 cls = small ? (u32)((mx - 1) >> 3) : (u32)KB_NW_CLASSES;
-	const u32 slot = KB_ATOMIC_ADD(&bt.counters[16 + cls], 1u);
-	bt.job_list[(size_t)cls * bt.cap_jobs + slot] = id;
+	// route: fragments with both sides > 30 go through the 8-mer partition first (tools.cpp:146); everything else is one
+	// nw_alignment problem, registered right away
+	if (sp.rlen > 30 && sp.glen > 30) { const u32 slot = KB_ATOMIC_ADD(&bt.counters[23], 1u); bt.part_list[slot] = id; }
+	else kb_emit_piece(ix, bt, id, sp.gpos, 0, sp.rlen, 0, sp.glen, ro, 1u);
 	out->info = KB_SEG_JOB; out->aux = id;
 }
 
@@ -721,123 +753,196 @@ KB_HD bool kb_segments_read(const KbIndexDev& ix, const KbParams& pm, const KbBa
 	return true;
 }
 
-// phase B, thread-per-fragment: the whole m x n (both <= KB_NW_SMALL) problem of job `id` in one thread. Same recurrence, tie
-// order and run list as the warp version below (kb_nww_*); the two previous-row vectors and the 2-bit traceback rows live
-// in local memory, the read comes from its packed word and the reference from one 64-bit window (the job lies inside the text).
-KB_HD void kb_nw_task(const KbIndexDev& ix, const KbBatchDev& bt, u32 id, unsigned long long* cells)
+// ---- phase B -----------------------------------------------------------------------------------------------------
+// B1 k_align_part   : warp per job of the partition list: 8-mer partition (recursive in pacbio mode), literal pieces written,
+//                     nw_alignment pieces registered (KbSink / KbFragIter above)
+// B2 k_nw_tile<...> : one thread per nw_alignment problem with both sides <= KB_NW_TMAX, by size class (below)
+//    k_nw_warp      : one warp per larger problem (anti-diagonal wavefront, kb_nww_*)
+// B3 k_align_gather : one thread per partitioned job: squeeze and merge the runs of its pieces
+//
+// Thread-per-problem solver. The DP is walked in column tiles of TW (<= 32) columns whose S and T values of the previous row
+// live in registers (the column loop is fully unrolled), so a cell costs ~15 integer instructions and no memory access;
+// per row and tile there is one 64-bit traceback word and, with several tiles, one boundary (S,R) pair carried through
+// local memory. Read and reference come as 2-bit packed words (the problem lies inside the text; read characters that are
+// no base are flagged in n4/bad and never match, exactly like nst_nt4_table code 4 against a reference base).
+// Same recurrence, tie order and run list as kb_nww_*.
+#if defined(__CUDA_ARCH__)
+#define KB_ADDMAX(a, b, c) __viaddmax_s32((a), (b), (c))   // max(a + b, c): one DPX instruction on sm_100a
+#define KB_MAX3(a, b, c) __vimax3_s32((a), (b), (c))
+#define KB_UNROLL _Pragma("unroll")
+#else
+#define KB_ADDMAX(a, b, c) (((a) + (b)) > (c) ? ((a) + (b)) : (c))
+#define KB_MAX3(a, b, c) ((a) > (b) ? ((a) > (c) ? (a) : (c)) : ((b) > (c) ? (b) : (c)))
+#define KB_UNROLL
+#endif
+
+template <int TW, int MAXM, int MAXT>
+KB_HD void kb_nwt_solve(const KbIndexDev& ix, const KbBatchDev& bt, const KbPiece& pc, unsigned long long* cells)
 {
-	KbJob& jb = bt.jobs[id];
-	const int m = jb.rlen, n = jb.glen;
-	const KbPk rw = kb_read_win(kb_pk_read(bt, (int)jb.read), jb.rpos);
-	u32 ginv; const u64 gw = kb_ref_win(ix, jb.gpos, &ginv);
-	int S[KB_NW_SMALL + 1], T[KB_NW_SMALL + 1]; u64 tb[KB_NW_SMALL]; u32 rev[2 * KB_NW_SMALL];
-	for (int j = 0; j <= n; j++) { S[j] = j ? -2 - j : 0; T[j] = KB_NW_NEG; }
-	for (int i = 1; i <= m; i++)
+	const u64 M5 = 0x5555555555555555ull;
+	KbJob& jb = bt.jobs[pc.job];
+	const int m = pc.rl, n = pc.gl;
+	const KbPk* rd = kb_pk_read(bt, (int)jb.read); const int rp = jb.rpos + pc.r0; const i64 gp = jb.gpos + pc.g0;
+	const int MAXW = (MAXM + 31) / 32;
+	u64 rc[MAXW]; u32 rn4[MAXW], rbad[MAXW]; u64 gc[MAXT];
+	for (int w = 0; w < MAXW; w++) if (32 * w < m) { const KbPk k = kb_read_win(rd, rp + 32 * w); rc[w] = k.code; rn4[w] = k.n4; rbad[w] = k.bad; } else { rc[w] = 0; rn4[w] = ~0u; rbad[w] = ~0u; }
+	const int nt = (n + 31) >> 5;
+	for (int t = 0; t < MAXT; t++) { u32 inv; gc[t] = t < nt ? kb_ref_win(ix, gp + 32 * t, &inv) : 0; }
+	u64 tb[MAXM * MAXT];
+	int lbs[MAXT > 1 ? MAXM + 1 : 1], lbr[MAXT > 1 ? MAXM + 1 : 1];
+	for (int t = 0; t < nt; t++)
 	{
-		const int a = (int)((rw.code >> (64 - 2 * i)) & 3u) | (int)(((rw.n4 >> (32 - i)) & 1u) << 2);
-		int diag = S[0], left_s = -2 - i, left_r = KB_NW_NEG;
-		S[0] = left_s;
-		u64 bits = 0, bw = gw;
-		for (int j = 1; j <= n; j++)
+		const u64 gw = gc[t]; const int nc = n - 32 * t < TW ? n - 32 * t : TW;
+		int S[TW], T[TW];
+		KB_UNROLL
+		for (int j = 0; j < TW; j++) { S[j] = -2 - (32 * t + j + 1); T[j] = KB_NW_NEG; }
+		int prev_old = t == 0 ? 0 : -2 - 32 * t;   // S[i-1][first column of the tile - 1]
+		for (int i = 1; i <= m; i++)
 		{
-			const int b = (int)(bw >> 62); bw <<= 2;
-			const int us = S[j], ut = T[j];
-			const int r = left_r - 1 > left_s - 3 ? left_r - 1 : left_s - 3;
-			const int t = ut - 1 > us - 3 ? ut - 1 : us - 3;
-			const int dg = diag + (a == b ? 3 : -3);
-			int s = dg > r ? dg : r; if (t > s) s = t;
-			bits |= (u64)((s == r ? 1u : 0u) | (s == t ? 2u : 0u)) << (2 * (j - 1));
-			diag = us; S[j] = s; T[j] = t; left_s = s; left_r = r;
+			const int w = (i - 1) >> 5, o = (i - 1) & 31;
+			const u64 a2 = (rc[w] >> (62 - 2 * o)) & 3ull;
+			const u64 x = gw ^ (M5 * a2);
+			u64 eq = ~(x | (x >> 1)) & M5;                        // bit 62-2j set: column j of the tile matches the read base
+			if ((rn4[w] >> (31 - o)) & 1u) eq = 0;
+			int left_s, left_r;
+			if (MAXT == 1 || t == 0) { left_s = -2 - i; left_r = KB_NW_NEG; } else { left_s = lbs[i]; left_r = lbr[i]; }
+			int diag = prev_old; prev_old = left_s;
+			u64 bits = 0;
+			KB_UNROLL
+			for (int j = 0; j < TW; j++)
+			{
+				if (j < nc)
+				{
+					const int us = S[j], ut = T[j];
+					const int r = KB_ADDMAX(left_r, -1, left_s - 3);
+					const int tt = KB_ADDMAX(ut, -1, us - 3);
+					const int dg = diag + (((eq >> (62 - 2 * j)) & 1ull) ? 3 : -3);
+					const int sc = KB_MAX3(dg, r, tt);
+					bits |= (u64)((sc == r ? 1u : 0u) | (sc == tt ? 2u : 0u)) << (2 * j);
+					diag = us; S[j] = sc; T[j] = tt; left_s = sc; left_r = r;
+				}
+			}
+			tb[(i - 1) * MAXT + t] = bits;
+			if (MAXT > 1) { lbs[i] = left_s; lbr[i] = left_r; }
 		}
-		tb[i - 1] = bits;
 	}
-	int i = m, j = n, nr = 0, ident = 0, aligned = 0, cur = -1, len = 0;
+	// traceback; runs are written backwards from the end of the piece's slice
+	u32* out = bt.runs + pc.out_off; int wr = m + n;
+	int i = m, j = n, ident = 0, aligned = 0, cur = -1, len = 0;
 	while (i > 0 || j > 0)
 	{
 		int type;
 		if (i == 0) type = KB_RUN_D;
 		else if (j == 0) type = KB_RUN_I;
-		else { const u32 b2 = (u32)(tb[i - 1] >> (2 * (j - 1))) & 3u; type = (b2 & 1u) ? KB_RUN_D : ((b2 & 2u) ? KB_RUN_I : KB_RUN_M); }
+		else { const u32 b2 = (u32)(tb[(i - 1) * MAXT + ((j - 1) >> 5)] >> (2 * ((j - 1) & 31))) & 3u; type = (b2 & 1u) ? KB_RUN_D : ((b2 & 2u) ? KB_RUN_I : KB_RUN_M); }
 		if (type == KB_RUN_D) j--;
 		else if (type == KB_RUN_I) i--;
 		else
 		{
 			i--; j--; aligned++;
 			// raw character equality against the upper-case reference: the read character must be an upper-case base with the same code
-			if ((((rw.bad >> (31 - i)) & 1u) == 0u) && (((rw.code >> (62 - 2 * i)) & 3u) == ((gw >> (62 - 2 * j)) & 3u))) ident++;
+			if ((((rbad[i >> 5] >> (31 - (i & 31))) & 1u) == 0u) && (((rc[i >> 5] >> (62 - 2 * (i & 31))) & 3ull) == ((gc[j >> 5] >> (62 - 2 * (j & 31))) & 3ull))) ident++;
 		}
 		if (type == cur) len++;
-		else { if (len > 0) rev[nr++] = ((u32)len << 2) | (u32)cur; cur = type; len = 1; }
+		else { if (len > 0) out[--wr] = ((u32)len << 2) | (u32)cur; cur = type; len = 1; }
 	}
-	if (len > 0) rev[nr++] = ((u32)len << 2) | (u32)cur;
-	u32* out = bt.runs + jb.run_off;
-	for (int k = 0; k < nr; k++) out[k] = rev[nr - 1 - k];
-	jb.nruns = nr; jb.ident = ident; jb.aligned = aligned;
+	if (len > 0) out[--wr] = ((u32)len << 2) | (u32)cur;
+	if (pc.whole) { jb.run_off = pc.out_off + (u32)wr; jb.nruns = m + n - wr; jb.ident = ident; jb.aligned = aligned; }
+	else { KB_ATOMIC_ADD(&jb.ident, ident); KB_ATOMIC_ADD(&jb.aligned, aligned); }
 	*cells += (unsigned long long)m * (unsigned long long)n;
 }
 
-// phase B, warp per job. State shared by the lanes of the warp (shared memory on the GPU):
-struct KbAlignWarp
+// grid-stride loop of one size class
+template <int TW, int MAXM, int MAXT>
+KB_HD void kb_nwt_class(const KbIndexDev& ix, const KbBatchDev& bt, int cls, u32 first, u32 stride, unsigned long long* cells, unsigned long long* calls)
 {
-	KbNwWarp nw; KbFragIter it; KbRuns acc; KbArena ar, fast;
-	KbWork piece; u8* f2; u8* f1; const u8* f1g; u32 job; int ok, has_piece, more_strips, rlen, glen, whole, whole_done;
-	unsigned long long cells; u32 calls;
-};
+	const u32 count = bt.counters[16 + cls]; const u32* list = bt.piece_list + (size_t)cls * bt.cap_pieces;
+	for (u32 q = first; q < count; q += stride) { kb_nwt_solve<TW, MAXM, MAXT>(ix, bt, bt.pieces[list[q]], cells); *calls += 1; }
+}
 
+// B2, warp per large problem. State shared by the lanes of the warp (shared memory on the GPU):
+struct KbPieceWarp { KbNwWarp nw; KbArena ar, fast; KbPiece pc; u8* f1; u8* f2; const u8* f1g; i64 g; int ok, more_strips; unsigned long long cells; u32 calls; };
+// lane 0: open a piece
+KB_HD void kb_pw_begin(const KbBatchDev& bt, KbPieceWarp& w, u32 id)
+{
+	w.pc = bt.pieces[id]; const KbJob& jb = bt.jobs[w.pc.job];
+	w.ar.used = 0; w.ar.ovf = false; w.fast.used = 0;
+	w.f1 = (u8*)kb_alloc2(w.fast, w.ar, (u64)w.pc.rl); w.f2 = (u8*)kb_alloc2(w.fast, w.ar, (u64)w.pc.gl);
+	w.f1g = bt.seq + bt.seq_off[jb.read] + jb.rpos + w.pc.r0; w.g = jb.gpos + w.pc.g0;
+	w.ok = (w.f1 != nullptr && w.f2 != nullptr) ? 1 : 0;
+	if (w.ok) w.ok = kb_nww_setup(w.nw, w.fast, w.ar, w.f1, w.pc.rl, w.f2, w.pc.gl) ? 1 : 0;
+	w.more_strips = 1;
+}
+// all lanes: characters of both sides into the warp's pool
+KB_HD void kb_pw_fetch(const KbIndexDev& ix, KbPieceWarp& w, int t)
+{
+	if (!w.ok) return;
+	for (int i = t; i < w.pc.gl; i += 32) w.f2[i] = kb_ref_char(ix, w.g + i);
+	for (int i = t; i < w.pc.rl; i += 32) w.f1[i] = w.f1g[i];
+}
+// lane 0: traceback and results
+KB_HD void kb_pw_end(const KbBatchDev& bt, KbPieceWarp& w)
+{
+	KbJob& jb = bt.jobs[w.pc.job];
+	if (w.ok)
+	{
+		int ident, aligned; const int cap = w.pc.rl + w.pc.gl;
+		const int first = kb_nww_traceback(w.nw, w.fast, w.ar, bt.runs + w.pc.out_off, cap, &ident, &aligned);
+		if (w.pc.whole) { jb.run_off = w.pc.out_off + (u32)first; jb.nruns = cap - first; jb.ident = ident; jb.aligned = aligned; }
+		else { KB_ATOMIC_ADD(&jb.ident, ident); KB_ATOMIC_ADD(&jb.aligned, aligned); }
+		w.calls++; w.cells += (unsigned long long)w.pc.rl * (unsigned long long)w.pc.gl;
+	}
+	if (w.ar.ovf || !w.ok) KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SCRATCH);
+}
+
+// B1, warp per partitioned job
+struct KbPartWarp { KbFragIter it; KbSink sink; KbArena ar, fast; u8* f1; u8* f2; const u8* f1g; u32 job; int ok, state, rlen, glen; };
 // lane 0: open job `id`
-KB_HD void kb_aw_begin(const KbParams& pm, const KbBatchDev& bt, KbAlignWarp& w, u32 id)
+KB_HD void kb_pt_begin(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, KbPartWarp& w, u32 id)
 {
 	const KbJob& jb = bt.jobs[id];
 	w.job = id; w.ar.used = 0; w.ar.ovf = false; w.fast.used = 0; w.rlen = jb.rlen; w.glen = jb.glen;
 	w.f1 = (u8*)kb_alloc2(w.fast, w.ar, (u64)jb.rlen);
 	w.f2 = (u8*)kb_alloc2(w.fast, w.ar, (u64)jb.glen);
 	w.f1g = bt.seq + bt.seq_off[jb.read] + jb.rpos;
-	w.acc.reset(bt.runs + jb.run_off, jb.rlen + jb.glen + 2);
+	w.sink.ix = &ix; w.sink.bt = &bt; w.sink.job = id; w.sink.gpos = jb.gpos; w.sink.base = jb.run_off; w.sink.cap = (u32)(jb.rlen + jb.glen + 2); w.sink.cur = 0;
+	w.sink.ident = 0; w.sink.aligned = 0; w.sink.ovf = false;
 	w.ok = (w.f1 != nullptr && w.f2 != nullptr) ? 1 : 0;
-	// fragments that cannot be partitioned (tools.cpp:146) are one NW problem: no work stack needed
-	w.whole = !(jb.rlen > 30 && jb.glen > 30); w.whole_done = 0;
-	if (w.ok && !w.whole) w.ok = w.it.init(&pm, &w.ar, w.f1, jb.rlen, w.f2, jb.glen, &w.acc) ? 1 : 0;
+	if (w.ok) w.ok = w.it.init(&pm, &w.ar, w.f1, jb.rlen, w.f2, jb.glen, &w.sink) ? 1 : 0;
 }
-// all lanes: read and reference characters of the fragment into the warp's pool
-KB_HD void kb_aw_fetch(const KbIndexDev& ix, const KbBatchDev& bt, KbAlignWarp& w, int t)
+// all lanes: characters of the fragment into the warp's pool, and the job's slice of the run arena zeroed
+KB_HD void kb_pt_fetch(const KbIndexDev& ix, const KbBatchDev& bt, KbPartWarp& w, int t)
 {
 	if (!w.ok) return;
-	i64 g = bt.jobs[w.job].gpos;
+	const i64 g = bt.jobs[w.job].gpos;
 	for (int i = t; i < w.glen; i += 32) w.f2[i] = kb_ref_char(ix, g + i);
 	for (int i = t; i < w.rlen; i += 32) w.f1[i] = w.f1g[i];
+	for (u32 i = (u32)t; i < w.sink.cap; i += 32) bt.runs[w.sink.base + i] = 0;
 }
-// lane 0: the DP of w.piece
-KB_HD void kb_aw_setup_piece(KbAlignWarp& w)
-{
-	w.calls++; w.cells += (unsigned long long)w.piece.rl * (unsigned long long)w.piece.gl;
-	if (kb_nww_setup(w.nw, w.fast, w.ar, w.f1 + w.piece.r0, w.piece.rl, w.f2 + w.piece.g0, w.piece.gl)) { w.has_piece = 1; w.more_strips = 1; }
-}
-// lane 0: advance to the next piece that needs NW and set the DP up (has_piece = 1), or to a fragment that all lanes
-// partition first (has_piece = 2, followed by kb_aw_part_done), or to the end of the job (has_piece = 0)
-KB_HD void kb_aw_next(KbAlignWarp& w)
-{
-	w.has_piece = 0;
-	if (!w.ok) return;
-	int got;
-	if (w.whole) { got = w.whole_done ? 0 : 1; w.whole_done = 1; w.piece.r0 = 0; w.piece.rl = w.rlen; w.piece.g0 = 0; w.piece.gl = w.glen; }
-	else got = w.it.next(&w.piece);
-	if (got == 2) w.has_piece = 2;
-	else if (got == 1) kb_aw_setup_piece(w);
-}
-// lane 0, after the lanes partitioned a fragment: has_piece = 1 when the fragment turned out to be one NW problem, else 3 (= call kb_aw_next again)
-KB_HD void kb_aw_part_done(KbAlignWarp& w)
-{
-	w.has_piece = 3;
-	if (w.it.part_finish(&w.piece)) { w.has_piece = 0; kb_aw_setup_piece(w); if (w.has_piece == 0) w.has_piece = 3; }
-}
-// lane 0: close the job
-KB_HD void kb_aw_end(const KbBatchDev& bt, KbAlignWarp& w)
+// lane 0: close the job (identities of the literal pieces; the nw_alignment pieces add theirs later)
+KB_HD void kb_pt_end(const KbBatchDev& bt, KbPartWarp& w)
 {
 	KbJob& jb = bt.jobs[w.job];
-	w.acc.flush();
-	if (w.acc.ovf) w.ar.ovf = true;
-	jb.nruns = w.acc.n; jb.ident = w.acc.ident; jb.aligned = w.acc.aligned;
-	if (w.ar.ovf || !w.ok) KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SCRATCH);
+	jb.nruns = 0;
+	if (w.sink.ident) KB_ATOMIC_ADD(&jb.ident, w.sink.ident);
+	if (w.sink.aligned) KB_ATOMIC_ADD(&jb.aligned, w.sink.aligned);
+	if (w.ar.ovf || w.sink.ovf || !w.ok) KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SCRATCH);
+}
+// B3: the runs of the job's pieces, in place: zeros squeezed out, equal neighbours merged (= KbRuns::push over the pieces in order)
+KB_HD void kb_gather_job(const KbBatchDev& bt, u32 id)
+{
+	KbJob& jb = bt.jobs[id];
+	u32* r = bt.runs + jb.run_off; const int cap = jb.rlen + jb.glen + 2;
+	int n = 0; u32 tail = 0;
+	for (int k = 0; k < cap; k++)
+	{
+		const u32 e = r[k]; if (e == 0) continue;
+		if (tail != 0 && (tail & 3u) == (e & 3u)) { tail += (e >> 2) << 2; continue; }
+		if (tail != 0) r[n++] = tail;
+		tail = e;
+	}
+	if (tail != 0) r[n++] = tail;
+	jb.nruns = n;
 }
 
 // AddNewCigarElements: run list -> cigar elements (D/I/M)

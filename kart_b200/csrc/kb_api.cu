@@ -163,55 +163,62 @@ static void k_rescue(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulation: 
 #endif
 __global__ void __launch_bounds__(KB_BLOCK) k_segments(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_segments(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x); }
 __global__ void __launch_bounds__(KB_BLOCK) k_segments_slow(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_segments_slow(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
-// phase B, small fragments: one thread per Needleman-Wunsch problem, problems grouped by size class (kb_align.cuh "thread-per-fragment")
-__global__ void __launch_bounds__(KB_BLOCK) k_nw_small(KbIndexDev ix, KbParams pm, KbBatchDev bt)
-{
-	if (bt.counters[3]) return;
-	unsigned long long cells = 0, calls = 0;
-	u32 c0 = bt.counters[16], c1 = c0 + bt.counters[17], c2 = c1 + bt.counters[18], c3 = c2 + bt.counters[19];
-	for (u32 q = blockIdx.x * blockDim.x + threadIdx.x; q < c3; q += gridDim.x * blockDim.x)
-	{
-		u32 cls = q < c0 ? 0u : (q < c1 ? 1u : (q < c2 ? 2u : 3u));
-		u32 k = q - (cls == 0 ? 0u : (cls == 1 ? c0 : (cls == 2 ? c1 : c2)));
-		kb_nw_task(ix, bt, bt.job_list[(size_t)cls * bt.cap_jobs + k], &cells);
-		calls++;
-	}
-	kb_warp_add64(&bt.work[3], cells); kb_warp_add64(&bt.work[4], calls);
-}
-// phase B, everything else: one warp per alignment job (kb_align.cuh "warp-per-fragment")
+// phase B (kb_align.cuh "phase B"): partition -> nw_alignment problems by size class -> gather
 #ifndef KB_EMUL
-__global__ void __launch_bounds__(KB_BLOCK) k_align(KbIndexDev ix, KbParams pm, KbBatchDev bt)
+__global__ void __launch_bounds__(KB_BLOCK) k_align_part(KbIndexDev ix, KbParams pm, KbBatchDev bt)
 {
-	__shared__ KbAlignWarp sw[KB_BLOCK / 32];
+	__shared__ KbPartWarp sw[KB_BLOCK / 32];
 	__shared__ __align__(16) u8 pool[KB_BLOCK / 32][KB_ALIGN_POOL];
 	if (bt.counters[3]) return;
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	const u32 gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
 	if ((int)(gwarp * 32) >= bt.scratch_threads) return;
-	KbAlignWarp& w = sw[wib];
-	const u32 njobs = bt.counters[20]; const u32* list = bt.job_list + (size_t)KB_NW_CLASSES * bt.cap_jobs;
-	if (lane == 0) { w.ar.base = bt.scratch + (u64)gwarp * 32ull * bt.scratch_per_thread; w.ar.cap = 32ull * bt.scratch_per_thread; w.fast.base = pool[wib]; w.fast.cap = KB_ALIGN_POOL; w.fast.ovf = false; w.cells = 0; w.calls = 0; }
+	KbPartWarp& w = sw[wib];
+	const u32 njobs = bt.counters[23];
+	if (lane == 0) { w.ar.base = bt.scratch + (u64)gwarp * 32ull * bt.scratch_per_thread; w.ar.cap = 32ull * bt.scratch_per_thread; w.fast.base = pool[wib]; w.fast.cap = KB_ALIGN_POOL; w.fast.ovf = false; }
 	__syncwarp();
 	for (u32 q = gwarp; q < njobs; q += nwarps)
 	{
-		if (lane == 0) kb_aw_begin(pm, bt, w, list[q]);
+		if (lane == 0) kb_pt_begin(ix, pm, bt, w, bt.part_list[q]);
 		__syncwarp();
-		kb_aw_fetch(ix, bt, w, lane);
+		kb_pt_fetch(ix, bt, w, lane);
 		__syncwarp();
-		while (true)
+		while (w.ok)
 		{
-			if (lane == 0) kb_aw_next(w);
+			if (lane == 0) w.state = w.it.next();
 			__syncwarp();
-			if (w.has_piece == 2)
-			{
-				w.it.part_scan(lane); __syncwarp();
-				w.it.part_ids(lane); __syncwarp();
-				w.it.part_pairs(lane); __syncwarp();
-				if (lane == 0) kb_aw_part_done(w);
-				__syncwarp();
-				if (w.has_piece == 3) continue;
-			}
-			if (!w.has_piece) break;
+			if (w.state != 2) break;
+			w.it.part_scan(lane); __syncwarp();
+			w.it.part_ids(lane); __syncwarp();
+			w.it.part_pairs(lane); __syncwarp();
+			if (lane == 0) w.it.part_finish();
+			__syncwarp();
+		}
+		if (lane == 0) kb_pt_end(bt, w);
+		__syncwarp();
+	}
+}
+__global__ void __launch_bounds__(KB_BLOCK) k_nw_warp(KbIndexDev ix, KbParams pm, KbBatchDev bt)
+{
+	__shared__ KbPieceWarp sw[KB_BLOCK / 32];
+	__shared__ __align__(16) u8 pool[KB_BLOCK / 32][KB_ALIGN_POOL];
+	if (bt.counters[3]) return;
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const u32 gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+	if ((int)(gwarp * 32) >= bt.scratch_threads) return;
+	KbPieceWarp& w = sw[wib];
+	const int cls = KB_NW_CLASSES - 1;
+	const u32 count = bt.counters[16 + cls]; const u32* list = bt.piece_list + (size_t)cls * bt.cap_pieces;
+	if (lane == 0) { w.ar.base = bt.scratch + (u64)gwarp * 32ull * bt.scratch_per_thread; w.ar.cap = 32ull * bt.scratch_per_thread; w.fast.base = pool[wib]; w.fast.cap = KB_ALIGN_POOL; w.fast.ovf = false; w.cells = 0; w.calls = 0; }
+	__syncwarp();
+	for (u32 q = gwarp; q < count; q += nwarps)
+	{
+		if (lane == 0) kb_pw_begin(bt, w, list[q]);
+		__syncwarp();
+		kb_pw_fetch(ix, w, lane);
+		__syncwarp();
+		if (w.ok)
+		{
 			kb_nww_init_rows(w.nw, lane);
 			__syncwarp();
 			while (true)
@@ -225,38 +232,50 @@ __global__ void __launch_bounds__(KB_BLOCK) k_align(KbIndexDev ix, KbParams pm, 
 				__syncwarp();
 				if (!w.more_strips) break;
 			}
-			if (lane == 0) kb_nww_traceback(w.nw, w.fast, w.ar, w.acc);
-			__syncwarp();
 		}
-		if (lane == 0) kb_aw_end(bt, w);
+		if (lane == 0) kb_pw_end(bt, w);
 		__syncwarp();
 	}
 	if (lane == 0) { if (w.cells) atomicAdd(&bt.work[3], w.cells); if (w.calls) atomicAdd(&bt.work[4], (unsigned long long)w.calls); }
 }
 #else
-static void k_align(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulation: the same phases, a warp = a loop over 32 lanes
+static void k_align_part(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulation: the same phases, a warp = a loop over 32 lanes
 {
 	if (blockIdx.x != 0 || threadIdx.x != 0) return;
 	if (bt.counters[3]) return;
-	static KbAlignWarp w; KbNwLane L[32]; static u8 pool[KB_ALIGN_POOL];
-	w.ar.base = bt.scratch; w.ar.cap = 32ull * bt.scratch_per_thread; w.fast.base = pool; w.fast.cap = KB_ALIGN_POOL; w.fast.ovf = false; w.cells = 0; w.calls = 0;
-	const u32 njobs = bt.counters[20]; const u32* list = bt.job_list + (size_t)KB_NW_CLASSES * bt.cap_jobs;
+	static KbPartWarp w; static u8 pool[KB_ALIGN_POOL];
+	w.ar.base = bt.scratch; w.ar.cap = 32ull * bt.scratch_per_thread; w.fast.base = pool; w.fast.cap = KB_ALIGN_POOL; w.fast.ovf = false;
+	const u32 njobs = bt.counters[23];
 	for (u32 q = 0; q < njobs; q++)
 	{
-		kb_aw_begin(pm, bt, w, list[q]);
-		for (int t = 31; t >= 0; t--) kb_aw_fetch(ix, bt, w, t);
-		while (true)
+		kb_pt_begin(ix, pm, bt, w, bt.part_list[q]);
+		for (int t = 31; t >= 0; t--) kb_pt_fetch(ix, bt, w, t);
+		while (w.ok)
 		{
-			kb_aw_next(w);
-			if (w.has_piece == 2)
-			{
-				for (int t = 0; t < 32; t++) w.it.part_scan(t);
-				for (int t = 31; t >= 0; t--) w.it.part_ids(t);
-				for (int t = 31; t >= 0; t--) w.it.part_pairs(t);
-				kb_aw_part_done(w);
-				if (w.has_piece == 3) continue;
-			}
-			if (!w.has_piece) break;
+			w.state = w.it.next();
+			if (w.state != 2) break;
+			for (int t = 0; t < 32; t++) w.it.part_scan(t);
+			for (int t = 31; t >= 0; t--) w.it.part_ids(t);
+			for (int t = 31; t >= 0; t--) w.it.part_pairs(t);
+			w.it.part_finish();
+		}
+		kb_pt_end(bt, w);
+	}
+}
+static void k_nw_warp(KbIndexDev ix, KbParams pm, KbBatchDev bt)
+{
+	if (blockIdx.x != 0 || threadIdx.x != 0) return;
+	if (bt.counters[3]) return;
+	static KbPieceWarp w; KbNwLane L[32]; static u8 pool[KB_ALIGN_POOL];
+	w.ar.base = bt.scratch; w.ar.cap = 32ull * bt.scratch_per_thread; w.fast.base = pool; w.fast.cap = KB_ALIGN_POOL; w.fast.ovf = false; w.cells = 0; w.calls = 0;
+	const int cls = KB_NW_CLASSES - 1;
+	const u32 count = bt.counters[16 + cls]; const u32* list = bt.piece_list + (size_t)cls * bt.cap_pieces;
+	for (u32 q = 0; q < count; q++)
+	{
+		kb_pw_begin(bt, w, list[q]);
+		for (int t = 31; t >= 0; t--) kb_pw_fetch(ix, w, t);
+		if (w.ok)
+		{
 			for (int t = 0; t < 32; t++) kb_nww_init_rows(w.nw, t);
 			while (true)
 			{
@@ -266,13 +285,27 @@ static void k_align(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulation: t
 				w.more_strips = kb_nww_strip_end(w.nw) ? 1 : 0;
 				if (!w.more_strips) break;
 			}
-			kb_nww_traceback(w.nw, w.fast, w.ar, w.acc);
 		}
-		kb_aw_end(bt, w);
+		kb_pw_end(bt, w);
 	}
 	bt.work[3] += w.cells; bt.work[4] += w.calls;
 }
 #endif
+// one thread per nw_alignment problem of size class CLS: TW columns in registers, up to MAXM rows, MAXT column tiles
+template <int CLS, int TW, int MAXM, int MAXT>
+__global__ void __launch_bounds__(KB_BLOCK) k_nw_tile(KbIndexDev ix, KbParams pm, KbBatchDev bt)
+{
+	if (bt.counters[3]) return;
+	unsigned long long cells = 0, calls = 0;
+	kb_nwt_class<TW, MAXM, MAXT>(ix, bt, CLS, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, &cells, &calls);
+	kb_warp_add64(&bt.work[3], cells); kb_warp_add64(&bt.work[4], calls);
+}
+__global__ void __launch_bounds__(KB_BLOCK) k_align_gather(KbBatchDev bt)
+{
+	if (bt.counters[3]) return;
+	const u32 njobs = bt.counters[23];
+	for (u32 q = blockIdx.x * blockDim.x + threadIdx.x; q < njobs; q += gridDim.x * blockDim.x) kb_gather_job(bt, bt.part_list[q]);
+}
 __global__ void __launch_bounds__(KB_BLOCK) k_assemble(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_assemble(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x); }
 __global__ void __launch_bounds__(KB_BLOCK) k_assemble_slow(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_assemble_slow(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
 __global__ void __launch_bounds__(KB_BLOCK) k_finalize(KbIndexDev ix, KbParams pm, KbBatchDev bt, kb_aln_t* aln) { kb_stage_finalize(ix, pm, bt, aln, blockIdx.x * blockDim.x + threadIdx.x); }
@@ -295,16 +328,16 @@ struct kb_slot
 {
 	cudaStream_t stream = nullptr; cudaEvent_t ev[10]; cudaEvent_t done = nullptr;
 	KbBatchDev bt; int n_reads = 0; size_t seq_bytes = 0; u64 seq_first = 0; int max_rlen = 0; int first_read = 0;
-	DevBuf<u8> seq, scratch; DevBuf<u64> seq_off; DevBuf<unsigned long long> work; DevBuf<i32> est, n_hits, n_seeds, n_cands, cand_cap, rescue, slow1, slow2; DevBuf<u32> seed_off, cand_off, cigar, counters, cseg_off, runs; DevBuf<i32> cseg_n; DevBuf<KbSegX> segx; DevBuf<KbJob> jobs; DevBuf<u32> job_list;
+	DevBuf<u8> seq, scratch; DevBuf<u64> seq_off; DevBuf<unsigned long long> work; DevBuf<i32> est, n_hits, n_seeds, n_cands, cand_cap, rescue, slow1, slow2; DevBuf<u32> seed_off, cand_off, cigar, counters, cseg_off, runs; DevBuf<i32> cseg_n; DevBuf<KbSegX> segx; DevBuf<KbJob> jobs; DevBuf<u32> piece_list, part_list; DevBuf<KbPiece> pieces;
 	DevBuf<KbHit> hits; DevBuf<KbSeg> segs; DevBuf<KbCand> cands; DevBuf<KbReport> reports; DevBuf<KbReadRes> res; DevBuf<KbPairStat> pstat; DevBuf<kb_aln_t> aln; DevBuf<KbPk> pk;
-	size_t cap_segs = 0, cap_cands = 0, cap_cigar = 0, cap_segx = 0, cap_jobs = 0, cap_runs = 0, scratch_per_thread = 0; int scratch_threads = 0;
+	size_t cap_segs = 0, cap_cands = 0, cap_cigar = 0, cap_segx = 0, cap_jobs = 0, cap_pieces = 0, cap_runs = 0, scratch_per_thread = 0; int scratch_threads = 0;
 	u32* counters_host = nullptr; unsigned long long* work_dev_host = nullptr;   // pinned: 16 x u32, 8 x u64
 	int launches = 0;
 	void release()
 	{
 		seq.release(); scratch.release(); seq_off.release(); work.release(); est.release(); n_hits.release(); n_seeds.release(); n_cands.release(); cand_cap.release();
 		rescue.release(); slow1.release(); slow2.release(); seed_off.release(); cand_off.release(); cigar.release(); counters.release(); cseg_off.release(); runs.release();
-		cseg_n.release(); segx.release(); jobs.release(); job_list.release(); hits.release(); segs.release(); cands.release(); reports.release(); res.release(); pstat.release(); aln.release(); pk.release();
+		cseg_n.release(); segx.release(); jobs.release(); piece_list.release(); part_list.release(); pieces.release(); hits.release(); segs.release(); cands.release(); reports.release(); res.release(); pstat.release(); aln.release(); pk.release();
 	}
 };
 
@@ -519,6 +552,7 @@ static int alloc_batch(kb_ctx* ctx, kb_slot& sl, int shared)
 	sl.cap_cigar = (size_t)(ctx->cigar_factor * (double)n) + (ctx->pm.pacbio ? (size_t)n * (size_t)(L / 2) : 0) + 65536;
 	sl.cap_segx = (size_t)(ctx->segx_factor * (double)n) + (ctx->pm.pacbio ? (size_t)n * (size_t)(L / 16 + 64) : 0) + 65536;
 	sl.cap_jobs = (size_t)(ctx->job_factor * (double)n) + (ctx->pm.pacbio ? (size_t)n * (size_t)(L / 32 + 32) : 0) + 65536;
+	sl.cap_pieces = 2 * sl.cap_jobs;
 	sl.cap_runs = (size_t)(ctx->run_factor * (double)n) + (ctx->pm.pacbio ? (size_t)n * (size_t)(3 * L) : 0) + (1 << 20);
 	if (sl.cap_runs > 0xF0000000ull) sl.cap_runs = 0xF0000000ull;
 	// per-thread scratch of the arena kernels: NW traceback (2 bit / cell) dominates
@@ -536,7 +570,7 @@ static int alloc_batch(kb_ctx* ctx, kb_slot& sl, int shared)
 	CK(sl.n_cands.ensure(n)); CK(sl.cand_off.ensure(n)); CK(sl.cand_cap.ensure(n)); CK(sl.rescue.ensure(n / 2 + 1));
 	CK(sl.res.ensure(n)); CK(sl.pstat.ensure(n / 2 + 1)); CK(sl.aln.ensure(n));
 	if (!shared) CK(sl.cigar.ensure(sl.cap_cigar));
-	CK(sl.segx.ensure(sl.cap_segx)); CK(sl.jobs.ensure(sl.cap_jobs)); CK(sl.job_list.ensure(sl.cap_jobs * (KB_NW_CLASSES + 1))); CK(sl.runs.ensure(sl.cap_runs)); CK(sl.cseg_off.ensure(sl.cap_cands)); CK(sl.cseg_n.ensure(sl.cap_cands));
+	CK(sl.segx.ensure(sl.cap_segx)); CK(sl.jobs.ensure(sl.cap_jobs)); CK(sl.pieces.ensure(sl.cap_pieces)); CK(sl.piece_list.ensure(sl.cap_pieces * KB_NW_CLASSES)); CK(sl.part_list.ensure(sl.cap_jobs)); CK(sl.runs.ensure(sl.cap_runs)); CK(sl.cseg_off.ensure(sl.cap_cands)); CK(sl.cseg_n.ensure(sl.cap_cands));
 	CK(sl.counters.ensure(KB_NCOUNTERS)); CK(sl.work.ensure(8)); CK(sl.scratch.ensure(per * threads));
 	CK(sl.pk.ensure((sl.seq_bytes >> 5) + n + 4)); CK(sl.slow1.ensure(n + 1)); CK(sl.slow2.ensure(n + 1));
 	// reads keep their chunk-wide offsets: the device copies start at seq_first, so the base pointers are shifted back by it
@@ -544,7 +578,7 @@ static int alloc_batch(kb_ctx* ctx, kb_slot& sl, int shared)
 	bt.hits = sl.hits.p; bt.max_hits = max_hits; bt.n_hits = sl.n_hits.p; bt.n_seeds = sl.n_seeds.p; bt.seed_off = sl.seed_off.p;
 	bt.segs = sl.segs.p; bt.cap_segs = (u32)sl.cap_segs; bt.cands = sl.cands.p; bt.cap_cands = (u32)sl.cap_cands; bt.n_cands = sl.n_cands.p;
 	bt.cand_off = sl.cand_off.p; bt.cand_cap = sl.cand_cap.p; bt.rescue_list = sl.rescue.p; bt.slow_list = sl.slow1.p; bt.slow_list2 = sl.slow2.p; bt.reports = sl.reports.p; bt.res = sl.res.p; bt.pstat = sl.pstat.p;
-	bt.segx = sl.segx.p; bt.cap_segx = (u32)sl.cap_segx; bt.cseg_off = sl.cseg_off.p; bt.cseg_n = sl.cseg_n.p; bt.jobs = sl.jobs.p; bt.cap_jobs = (u32)sl.cap_jobs; bt.job_list = sl.job_list.p; bt.runs = sl.runs.p; bt.cap_runs = (u32)sl.cap_runs;
+	bt.segx = sl.segx.p; bt.cap_segx = (u32)sl.cap_segx; bt.cseg_off = sl.cseg_off.p; bt.cseg_n = sl.cseg_n.p; bt.jobs = sl.jobs.p; bt.cap_jobs = (u32)sl.cap_jobs; bt.pieces = sl.pieces.p; bt.cap_pieces = (u32)sl.cap_pieces; bt.piece_list = sl.piece_list.p; bt.part_list = sl.part_list.p; bt.runs = sl.runs.p; bt.cap_runs = (u32)sl.cap_runs;
 	if (shared) { bt.cigar = ctx->chunk_cigar.p; bt.cap_cigar = (u32)ctx->chunk_cigar.n; bt.cig_cursor = ctx->chunk_cursor.p; }
 	else { bt.cigar = sl.cigar.p; bt.cap_cigar = (u32)sl.cap_cigar; bt.cig_cursor = sl.counters.p + 2; }
 	bt.scratch = sl.scratch.p; bt.scratch_per_thread = per; bt.scratch_threads = (int)threads;
@@ -607,8 +641,15 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 	KB_LAUNCH(k_segments, g_reads, KB_BLOCK, s, ix, pm, bt); sl.launches++;
 	KB_LAUNCH(k_segments_slow, g_scr, KB_BLOCK, s, ix, pm, bt); sl.launches++;
 	CK(cudaEventRecord(sl.ev[5], s));
-	KB_LAUNCH(k_nw_small, 148 * 8, KB_BLOCK, s, ix, pm, bt); sl.launches++;
-	KB_LAUNCH(k_align, g_scr, KB_BLOCK, s, ix, pm, bt); sl.launches++;
+	KB_LAUNCH(k_align_part, g_scr, KB_BLOCK, s, ix, pm, bt); sl.launches++;
+	KB_LAUNCH((k_nw_tile<0, 8, 32, 1>), 148 * 8, KB_BLOCK, s, ix, pm, bt); sl.launches++;
+	KB_LAUNCH((k_nw_tile<1, 16, 32, 1>), 148 * 8, KB_BLOCK, s, ix, pm, bt); sl.launches++;
+	KB_LAUNCH((k_nw_tile<2, 24, 32, 1>), 148 * 8, KB_BLOCK, s, ix, pm, bt); sl.launches++;
+	KB_LAUNCH((k_nw_tile<3, 32, 32, 1>), 148 * 8, KB_BLOCK, s, ix, pm, bt); sl.launches++;
+	KB_LAUNCH((k_nw_tile<4, 32, 64, 2>), 148 * 4, KB_BLOCK, s, ix, pm, bt); sl.launches++;
+	KB_LAUNCH((k_nw_tile<5, 32, 128, 4>), 148 * 4, KB_BLOCK, s, ix, pm, bt); sl.launches++;
+	KB_LAUNCH(k_nw_warp, g_scr, KB_BLOCK, s, ix, pm, bt); sl.launches++;
+	KB_LAUNCH(k_align_gather, 148 * 4, KB_BLOCK, s, bt); sl.launches++;
 	CK(cudaEventRecord(sl.ev[6], s));
 	KB_LAUNCH(k_assemble, g_reads, KB_BLOCK, s, ix, pm, bt); sl.launches++;
 	KB_LAUNCH(k_assemble_slow, g_scr, KB_BLOCK, s, ix, pm, bt); sl.launches++;

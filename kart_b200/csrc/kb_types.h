@@ -25,8 +25,8 @@ typedef uint8_t u8;
 #define KB_HD inline
 #define KB_D inline
 #define KB_NCOUNTERS 32
-#define KB_NW_CLASSES 4
-#define KB_NW_SMALL 32   // a fragment pair with both sides <= this (and no 8-mer partition) is one thread's Needleman-Wunsch problem
+#define KB_NW_CLASSES 7  // nw_alignment size classes: longer side <= 8, 16, 24, 32 (one register tile), <= 64, <= 128 (column tiles of 32), else warp wavefront
+#define KB_NW_TMAX 128   // largest side a single thread solves
 
 #endif
 
@@ -81,6 +81,9 @@ struct KbSegX { KbSeg s; u32 info; u32 aux; };
 enum { KB_SEG_SKIP = 0, KB_SEG_SIMPLE = 1, KB_SEG_QUICK = 2 /* aux = score */, KB_SEG_GAP = 3, KB_SEG_SOFT = 4, KB_SEG_JOB = 5 /* aux = job id */, KB_SEG_ONE = 6 /* 1x1, aux = identical? */ };
 // one fragment pair that needs GenerateNormalPairAlignment (k-mer partition + NW); result = run list in the run arena
 struct KbJob { i64 gpos; u32 read; i32 rpos, rlen, glen; u32 run_off; i32 nruns, ident, aligned; };
+// one nw_alignment call: the sub-rectangle (r0,rl) x (g0,gl) of job `job`; its runs go to runs[out_off .. out_off + rl + gl), written from
+// the end of that slice backwards. whole != 0: the piece is the entire job (no 8-mer partition): the solver finishes the job itself.
+struct KbPiece { u32 job; i32 r0, rl, g0, gl; u32 out_off; u32 whole; u32 pad; };
 
 // status bits written by kernels (any non-zero value fails the batch loudly; capacities are then grown and the batch rerun)
 enum { KB_OVF_SEEDS = 1, KB_OVF_CANDS = 2, KB_OVF_CIGAR = 4, KB_OVF_SCRATCH = 8, KB_OVF_HITS = 16, KB_OVF_RESCUE = 32, KB_OVF_NW = 64, KB_OVF_SEGX = 128, KB_OVF_JOBS = 256, KB_OVF_RUNS = 512 };
@@ -108,7 +111,9 @@ struct KbBatchDev
 	// stage 3: segments of the surviving candidates, alignment jobs, run arena
 	KbSegX* segx; u32 cap_segx; u32* cseg_off; i32* cseg_n;   // cseg_* indexed like cands (cseg_n < 0: candidate dropped)
 	KbJob* jobs; u32 cap_jobs; u32* runs; u32 cap_runs;
-	u32* job_list;                      // KB_NW_CLASSES + 1 lists of cap_jobs job ids: thread-per-problem size classes (counters[16..19]), then the warp list (counters[20])
+	KbPiece* pieces; u32 cap_pieces;    // nw_alignment problems (cursor: counters[24])
+	u32* piece_list;                    // KB_NW_CLASSES lists of cap_pieces piece ids by size class (counts: counters[16 + class])
+	u32* part_list;                     // cap_jobs ids of the jobs that go through the 8-mer partition first (count: counters[23])
 	// stage 4
 	KbReport* reports;                  // indexed like cands
 	KbReadRes* res;
@@ -119,13 +124,15 @@ struct KbBatchDev
 	i32 max_rlen;                       // longest read in the batch
 	i32 nw_max_m, nw_max_n, seg_cap, kmer_cap;
 	// counters: [0] seeds cursor [1] cands cursor [2] cigar cursor [3] status bits [4] rescue count [5] max seeds/read
-	//           [6] nw calls [7] rescue attempts [8] segx cursor [10] run cursor + [11] job cursor (one u64) ; 64-bit: work[0] extension steps, work[1] occ blocks, work[2] LF steps, work[3] NW cells
+	//           [6] nw calls [7] rescue attempts [8] segx cursor [10] run cursor + [11] job cursor (one u64) [12],[13] slow lists
+	//           [16..22] pieces per size class [23] partition jobs [24] piece cursor
+	//           64-bit: work[0] extension steps, work[1] occ blocks, work[2] LF steps, work[3] NW cells, work[4] NW calls
 	u32* counters;
 	unsigned long long* work;
 };
 
 #define KB_NCOUNTERS 32
-#define KB_NW_CLASSES 4
-#define KB_NW_SMALL 32   // a fragment pair with both sides <= this (and no 8-mer partition) is one thread's Needleman-Wunsch problem
+#define KB_NW_CLASSES 7  // nw_alignment size classes: longer side <= 8, 16, 24, 32 (one register tile), <= 64, <= 128 (column tiles of 32), else warp wavefront
+#define KB_NW_TMAX 128   // largest side a single thread solves
 
 #endif

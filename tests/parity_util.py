@@ -150,6 +150,19 @@ def compare_singles(m: Mapper, orc: Oracle, reads, show: int = 3):
 
 
 
+def big_gap_reads(g):
+    """2.5 kbp reads whose middle 150..420 bases are random: fragment pairs without common 8-mers, i.e. nw_alignment problems
+    larger than one thread takes (warp wavefront class) next to all the small ones."""
+    rng = np.random.default_rng(9)
+    reads = []
+    for k in range(6):
+        s = g[k % 3][2000 + 500 * k:2000 + 500 * k + 2500].copy()
+        a, L = 800 + 100 * k, [150, 250, 350, 200, 420, 300][k]
+        s[a:a + L] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=L)]
+        reads.append(s.tobytes())
+    return reads
+
+
 def bam_equal(path, golden):
     """Byte-identical when the zlib in this process matches the one the golden was deflated with; always identical in the BGZF
     block structure (ISIZE sequence) and in the inflated BAM payload."""

@@ -47,6 +47,22 @@ def test_pacbio_long_reads(mini):
     assert pu.compare_singles(m, pu.Oracle(pu.MINI_PREFIX, pacbio=True), r) == 0
 
 
+def test_all_nw_size_classes(mini):
+    """Every nw_alignment size class (register tiles <= 8/16/24/32, column tiles <= 64/128, warp wavefront) against the oracle."""
+    idx, g = mini
+    reads = pu.big_gap_reads(g)
+    seen = np.zeros(7, dtype=np.int64)
+    for pac in (True, False):
+        m = pu.make_mapper(idx, emul=True, pacbio=pac)
+        assert pu.compare_singles(m, pu.Oracle(pu.MINI_PREFIX, pacbio=pac), reads) == 0
+        seen += m.debug(9, np.uint32, 32)[16:23]
+    r, _, _ = synth.simulate(g, 300, 100, 0.08, seed=35, paired=False, indel=0.003)
+    m = pu.make_mapper(idx, emul=True, paired=False)
+    assert pu.compare_singles(m, pu.Oracle(pu.MINI_PREFIX), r) == 0
+    seen += m.debug(9, np.uint32, 32)[16:23]
+    assert (seen > 0).all(), seen
+
+
 def test_edge_reads(mini):
     idx, g = mini
     m = pu.make_mapper(idx, emul=True, paired=False)

@@ -83,6 +83,23 @@ def test_pacbio_vs_oracle(built):
     assert pu.compare_singles(m, pu.Oracle(pu.MINI_PREFIX, pacbio=True), r) == 0
 
 
+def test_all_nw_size_classes(built):
+    """Every nw_alignment size class of the CUDA path (thread-per-problem register tiles, column tiles, warp wavefront) against the oracle."""
+    idx = KartIndex(pu.MINI_PREFIX)
+    g = pu.genome_of(idx)
+    reads = pu.big_gap_reads(g)
+    seen = np.zeros(7, dtype=np.int64)
+    for pac in (True, False):
+        m = pu.make_mapper(idx, pacbio=pac)
+        assert pu.compare_singles(m, pu.Oracle(pu.MINI_PREFIX, pacbio=pac), reads) == 0
+        seen += m.debug(9, np.uint32, 32)[16:23]
+    r, _, _ = synth.simulate(g, 3000, 100, 0.08, seed=35, paired=False, indel=0.003)
+    m = pu.make_mapper(idx, paired=False)
+    assert pu.compare_singles(m, pu.Oracle(pu.MINI_PREFIX), r) == 0
+    seen += m.debug(9, np.uint32, 32)[16:23]
+    assert (seen > 0).all(), seen
+
+
 def test_multi_contig_paired_with_rescue(built):
     idx = KartIndex(pu.MINI_PREFIX)
     g = pu.genome_of(idx)
