@@ -725,14 +725,85 @@ KB_HD void kb_segments_cand(const KbIndexDev& ix, const KbParams& pm, const KbBa
 	for (int j = 0; j < n; j++) kb_classify_segment(ix, pm, bt, r, seq, rd, sv[j], j, n, &bt.segx[off + j]);
 }
 
+// The common case needs no staging at all: when the (gPos,rPos)-sorted seeds of a candidate neither overlap nor invert (each
+// ends before the next begins, in the read and in the genome), RemoveTandemRepeatSeeds, RemoveTranslocatedSeeds and
+// CheckOverlappingSeeds change nothing and the stable merge of :449 simply interleaves seed, gap, seed, ... So the segment
+// list is streamed straight from the seed array: one pass to count and validate, one pass to classify and store.
+// Returns false (nothing written) when the seeds need the general path.
+KB_HD bool kb_segments_cand_stream(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int r, const u8* seq, const KbPk* rd, int rlen, u32 ci, const KbCand& c)
+{
+	const KbSeg* in = bt.segs + c.seg_start; const int ns = c.nseg;
+	KbSeg prev = in[0]; const KbSeg first = prev;
+	int n = ns;
+	for (int k = 1; k < ns; k++)
+	{
+		const KbSeg cur = in[k];
+		const int rg = cur.rpos - (prev.rpos + prev.rlen); const i64 gg = cur.gpos - (prev.gpos + prev.glen);
+		if (rg < 0 || gg < 0) return false;
+		if (rg > 0 || gg > 0) n++;
+		prev = cur;
+	}
+	const int head = first.rpos > 0 ? first.rpos : 0, tail = rlen - (prev.rpos + prev.rlen);
+	if (head > 0) n++;
+	if (tail > 0) n++;
+	// CheckCoordinateValidity :582 on the first and last segment with a genome side
+	{
+		i64 a = first.gpos, b = prev.gpos + prev.glen - 1;
+		if (head > 0) { a = first.gpos - head; if (a < 0) a = 0; }
+		if (tail > 0) b = prev.gpos + prev.glen + tail - 1;
+		if ((a < ix.G) != (b < ix.G)) return true;
+		int ea = kb_chr_lookup(ix, a), eb = kb_chr_lookup(ix, b);
+		if (!(ea < ix.n_ends && eb < ix.n_ends && ix.end_chr[ea] == ix.end_chr[eb])) return true;
+	}
+	u32 off = KB_ATOMIC_ADD(&bt.counters[8], (u32)n);
+	if ((u64)off + (u64)n > (u64)bt.cap_segx) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SEGX); return true; }
+	bt.cseg_off[ci] = off; bt.cseg_n[ci] = n;
+	int j = 0;
+	if (head > 0)
+	{
+		KbSeg h; h.simple = 0; h.rpos = 0; h.gpos = first.gpos - head; if (h.gpos < 0) h.gpos = 0; h.rlen = head; h.glen = head;
+		kb_classify_segment(ix, pm, bt, r, seq, rd, h, j, n, &bt.segx[off + j]); j++;
+	}
+	prev = first;
+	kb_classify_segment(ix, pm, bt, r, seq, rd, prev, j, n, &bt.segx[off + j]); j++;
+	for (int k = 1; k < ns; k++)
+	{
+		const KbSeg cur = in[k];
+		const int rg = cur.rpos - (prev.rpos + prev.rlen); const int gg = (int)(cur.gpos - (prev.gpos + prev.glen));
+		if (rg > 0 || gg > 0)
+		{
+			KbSeg g; g.simple = 0; g.rpos = prev.rpos + prev.rlen; g.gpos = prev.gpos + prev.glen; g.rlen = rg; g.glen = gg;
+			kb_classify_segment(ix, pm, bt, r, seq, rd, g, j, n, &bt.segx[off + j]); j++;
+		}
+		kb_classify_segment(ix, pm, bt, r, seq, rd, cur, j, n, &bt.segx[off + j]); j++;
+		prev = cur;
+	}
+	if (tail > 0)
+	{
+		KbSeg e; e.simple = 0; e.rpos = prev.rpos + prev.rlen; e.gpos = prev.gpos + prev.glen; e.rlen = tail; e.glen = tail;
+		kb_classify_segment(ix, pm, bt, r, seq, rd, e, j, n, &bt.segx[off + j]); j++;
+	}
+	return true;
+}
+
 // ar == nullptr: local memory only; returns false (nothing written) when a candidate needs the arena
 KB_HD bool kb_segments_read(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int r, KbArena* ar)
 {
 	KbCand* cv = bt.cands + bt.cand_off[r];
 	int ncan = bt.n_cands[r];
-	if (ar == nullptr) for (int i = 0; i < ncan; i++) if (cv[i].score != 0 && cv[i].nseg > KB_SEG_FAST) return false;
 	const u8* seq = bt.seq + bt.seq_off[r]; int rlen = (int)(bt.seq_off[r + 1] - bt.seq_off[r]);
 	const KbPk* rd = kb_pk_read(bt, r);
+	if (ar == nullptr)
+	{
+		// all candidates streamable or small? (decided before anything is written: a read is done entirely by one of the two kernels)
+		for (int i = 0; i < ncan; i++)
+		{
+			if (cv[i].score == 0 || cv[i].nseg <= KB_SEG_FAST) continue;
+			const KbSeg* in = bt.segs + cv[i].seg_start; bool ok = true;
+			for (int k = 1; k < cv[i].nseg && ok; k++) ok = in[k].rpos >= in[k - 1].rpos + in[k - 1].rlen && in[k].gpos >= in[k - 1].gpos + in[k - 1].glen;
+			if (!ok) return false;
+		}
+	}
 	KbSeg in_l[KB_SEG_FAST], sv_l[2 * KB_SEG_FAST + 2]; i32 order_l[KB_SEG_FAST];
 	for (int i = 0; i < ncan; i++)
 	{
@@ -740,6 +811,7 @@ KB_HD bool kb_segments_read(const KbIndexDev& ix, const KbParams& pm, const KbBa
 		bt.cseg_n[ci] = -1; bt.cseg_off[ci] = 0;
 		const KbCand c = cv[i];
 		if (c.score == 0) continue;
+		if (kb_segments_cand_stream(ix, pm, bt, r, seq, rd, rlen, ci, c)) continue;
 		if (c.nseg <= KB_SEG_FAST) { kb_segments_cand(ix, pm, bt, r, seq, rd, rlen, ci, c, in_l, sv_l, order_l); continue; }
 		u64 mark = ar->used;
 		int ns = c.nseg;

@@ -52,11 +52,15 @@ __global__ void k_ref64(const u8* pac, u64 bytes, u64 words, u64* out)
 	out[w] = v;
 }
 
-__global__ void __launch_bounds__(KB_BLOCK, 10) k_fm_seed(KbIndexDev ix, KbParams pm, KbBatchDev bt)
+// MINB = resident blocks per SM the register allocation is tuned for: 10 (48 registers, more loads in flight: HBM-sized indexes)
+// or 8 (64 registers, no spills: L2-resident indexes, where the kernel is ALU-bound)
+template <int MINB>
+__global__ void __launch_bounds__(KB_BLOCK, MINB) k_fm_seed(KbIndexDev ix, KbParams pm, KbBatchDev bt)
 {
-	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const long long r0 = w * KB_SEED_WARP_READS, r1 = r0 + KB_SEED_WARP_READS;
 	u32 steps = 0, blocks = 0;
-	kb_seed_read(ix, pm, bt, r, r < bt.n_reads, &steps, &blocks);
+	kb_seed_reads(ix, pm, bt, (int)(r0 < bt.n_reads ? r0 : bt.n_reads), (int)(r1 < bt.n_reads ? r1 : bt.n_reads), bt.seed_next + w, &steps, &blocks);
 	kb_warp_add64(&bt.work[0], steps); kb_warp_add64(&bt.work[1], blocks);
 }
 
@@ -328,7 +332,7 @@ struct kb_slot
 {
 	cudaStream_t stream = nullptr; cudaEvent_t ev[10]; cudaEvent_t done = nullptr;
 	KbBatchDev bt; int n_reads = 0; size_t seq_bytes = 0; u64 seq_first = 0; int max_rlen = 0; int first_read = 0;
-	DevBuf<u8> seq, scratch; DevBuf<u64> seq_off; DevBuf<unsigned long long> work; DevBuf<i32> est, n_hits, n_seeds, n_cands, cand_cap, rescue, slow1, slow2; DevBuf<u32> seed_off, cand_off, cigar, counters, cseg_off, runs; DevBuf<i32> cseg_n; DevBuf<KbSegX> segx; DevBuf<KbJob> jobs; DevBuf<u32> piece_list, part_list; DevBuf<KbPiece> pieces;
+	DevBuf<u8> seq, scratch; DevBuf<u64> seq_off; DevBuf<unsigned long long> work; DevBuf<i32> est, n_hits, n_seeds, n_cands, cand_cap, rescue, slow1, slow2; DevBuf<u32> seed_next, seed_off, cand_off, cigar, counters, cseg_off, runs; DevBuf<i32> cseg_n; DevBuf<KbSegX> segx; DevBuf<KbJob> jobs; DevBuf<u32> piece_list, part_list; DevBuf<KbPiece> pieces;
 	DevBuf<KbHit> hits; DevBuf<KbSeg> segs; DevBuf<KbCand> cands; DevBuf<KbReport> reports; DevBuf<KbReadRes> res; DevBuf<KbPairStat> pstat; DevBuf<kb_aln_t> aln; DevBuf<KbPk> pk;
 	size_t cap_segs = 0, cap_cands = 0, cap_cigar = 0, cap_segx = 0, cap_jobs = 0, cap_pieces = 0, cap_runs = 0, scratch_per_thread = 0; int scratch_threads = 0;
 	u32* counters_host = nullptr; unsigned long long* work_dev_host = nullptr;   // pinned: 16 x u32, 8 x u64
@@ -336,7 +340,7 @@ struct kb_slot
 	void release()
 	{
 		seq.release(); scratch.release(); seq_off.release(); work.release(); est.release(); n_hits.release(); n_seeds.release(); n_cands.release(); cand_cap.release();
-		rescue.release(); slow1.release(); slow2.release(); seed_off.release(); cand_off.release(); cigar.release(); counters.release(); cseg_off.release(); runs.release();
+		rescue.release(); seed_next.release(); slow1.release(); slow2.release(); seed_off.release(); cand_off.release(); cigar.release(); counters.release(); cseg_off.release(); runs.release();
 		cseg_n.release(); segx.release(); jobs.release(); piece_list.release(); part_list.release(); pieces.release(); hits.release(); segs.release(); cands.release(); reports.release(); res.release(); pstat.release(); aln.release(); pk.release();
 	}
 };
@@ -353,6 +357,7 @@ struct kb_ctx
 	double seg_factor = 32, cigar_factor = 8, scratch_factor = 1, segx_factor = 8, job_factor = 4, run_factor = 96;
 	float stage_ms[9]; uint64_t work_host[8]; u32 counters_host[KB_NCOUNTERS];
 	cudaEvent_t chunk_start = nullptr; int trace = 0;
+	int seed_minb = 10;
 	int pipe_min_reads = 262144, pipe_sub_reads = 0;   // chunks of at least pipe_min_reads go through the two-slot pipeline
 };
 
@@ -410,6 +415,7 @@ int kb_init(int device, kb_ctx_t** out)
 	}
 	cudaEventCreate(&ctx->chunk_start); ctx->trace = getenv("KB_PIPE_TRACE") ? 1 : 0;
 	const char* e = getenv("KB_PIPE_MIN_READS"); if (e && atoi(e) > 0) ctx->pipe_min_reads = atoi(e);
+	e = getenv("KB_SEED_MINB"); if (e && atoi(e) == 8) ctx->seed_minb = 8;
 	e = getenv("KB_PIPE_SUB_READS"); if (e && atoi(e) > 0) ctx->pipe_sub_reads = atoi(e);
 	*out = ctx;
 	return KB_OK;
@@ -565,7 +571,7 @@ static int alloc_batch(kb_ctx* ctx, kb_slot& sl, int shared)
 	if (threads > n) threads = n;
 	threads = (threads + KB_BLOCK - 1) / KB_BLOCK * KB_BLOCK; if (threads < KB_BLOCK) threads = KB_BLOCK;
 	sl.scratch_per_thread = per; sl.scratch_threads = (int)threads;
-	CK(sl.hits.ensure(n * max_hits)); CK(sl.n_hits.ensure(n)); CK(sl.n_seeds.ensure(n)); CK(sl.seed_off.ensure(n));
+	CK(sl.hits.ensure(n * max_hits)); CK(sl.n_hits.ensure(n)); CK(sl.seed_next.ensure((n + KB_SEED_WARP_READS - 1) / KB_SEED_WARP_READS + KB_BLOCK / 32)); CK(sl.n_seeds.ensure(n)); CK(sl.seed_off.ensure(n));
 	CK(sl.segs.ensure(sl.cap_segs)); CK(sl.cands.ensure(sl.cap_cands)); CK(sl.reports.ensure(sl.cap_cands));
 	CK(sl.n_cands.ensure(n)); CK(sl.cand_off.ensure(n)); CK(sl.cand_cap.ensure(n)); CK(sl.rescue.ensure(n / 2 + 1));
 	CK(sl.res.ensure(n)); CK(sl.pstat.ensure(n / 2 + 1)); CK(sl.aln.ensure(n));
@@ -575,7 +581,7 @@ static int alloc_batch(kb_ctx* ctx, kb_slot& sl, int shared)
 	CK(sl.pk.ensure((sl.seq_bytes >> 5) + n + 4)); CK(sl.slow1.ensure(n + 1)); CK(sl.slow2.ensure(n + 1));
 	// reads keep their chunk-wide offsets: the device copies start at seq_first, so the base pointers are shifted back by it
 	bt.n_reads = sl.n_reads; bt.seq = sl.seq.p - sl.seq_first; bt.seq_off = sl.seq_off.p; bt.est = sl.est.p; bt.pk = sl.pk.p - (sl.seq_first >> 5); bt.pk_wpr = (L + 31) / 32;
-	bt.hits = sl.hits.p; bt.max_hits = max_hits; bt.n_hits = sl.n_hits.p; bt.n_seeds = sl.n_seeds.p; bt.seed_off = sl.seed_off.p;
+	bt.hits = sl.hits.p; bt.max_hits = max_hits; bt.n_hits = sl.n_hits.p; bt.seed_next = sl.seed_next.p; bt.n_seeds = sl.n_seeds.p; bt.seed_off = sl.seed_off.p;
 	bt.segs = sl.segs.p; bt.cap_segs = (u32)sl.cap_segs; bt.cands = sl.cands.p; bt.cap_cands = (u32)sl.cap_cands; bt.n_cands = sl.n_cands.p;
 	bt.cand_off = sl.cand_off.p; bt.cand_cap = sl.cand_cap.p; bt.rescue_list = sl.rescue.p; bt.slow_list = sl.slow1.p; bt.slow_list2 = sl.slow2.p; bt.reports = sl.reports.p; bt.res = sl.res.p; bt.pstat = sl.pstat.p;
 	bt.segx = sl.segx.p; bt.cap_segx = (u32)sl.cap_segx; bt.cseg_off = sl.cseg_off.p; bt.cseg_n = sl.cseg_n.p; bt.jobs = sl.jobs.p; bt.cap_jobs = (u32)sl.cap_jobs; bt.pieces = sl.pieces.p; bt.cap_pieces = (u32)sl.cap_pieces; bt.piece_list = sl.piece_list.p; bt.part_list = sl.part_list.p; bt.runs = sl.runs.p; bt.cap_runs = (u32)sl.cap_runs;
@@ -629,7 +635,12 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 	sl.launches = 0;
 	CK(cudaEventRecord(sl.ev[0], s));
 	KB_LAUNCH(k_pack, (unsigned)(((long long)n * bt.pk_wpr + KB_BLOCK - 1) / KB_BLOCK), KB_BLOCK, s, bt); sl.launches++;
-	KB_LAUNCH(k_fm_seed, g_reads, KB_BLOCK, s, ix, pm, bt); sl.launches++;
+	{
+		const unsigned warps = (unsigned)((n + KB_SEED_WARP_READS - 1) / KB_SEED_WARP_READS), g_seed = (warps * 32 + KB_BLOCK - 1) / KB_BLOCK;
+		CK(cudaMemsetAsync(sl.seed_next.p, 0, (size_t)g_seed * (KB_BLOCK / 32) * sizeof(u32), s));
+		if (ctx->seed_minb == 8) { KB_LAUNCH(k_fm_seed<8>, g_seed, KB_BLOCK, s, ix, pm, bt); } else { KB_LAUNCH(k_fm_seed<10>, g_seed, KB_BLOCK, s, ix, pm, bt); }
+		sl.launches++;
+	}
 	CK(cudaEventRecord(sl.ev[1], s));
 	KB_LAUNCH(k_sa_locate, g_hits, KB_BLOCK, s, ix, bt); sl.launches++;
 	CK(cudaEventRecord(sl.ev[2], s));

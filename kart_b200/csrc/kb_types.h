@@ -102,6 +102,7 @@ struct KbBatchDev
 	// stage 1
 	KbHit* hits; i32 max_hits;          // [n_reads][max_hits]
 	i32* n_hits;                        // hits stored per read
+	u32* seed_next;                     // k_fm_seed: per warp, how many of its KB_SEED_WARP_READS reads have been taken
 	i32* n_seeds; u32* seed_off;        // seeds per read and their offset in `segs`
 	KbSeg* segs; u32 cap_segs;
 	// stage 2

@@ -35,11 +35,12 @@ open(e1, "wb").write(b"".join(open(f1, "rb").readlines()[:4]))
 empty = ["-f", e1] + (["-pacbio"] if a.mode == "pacbio" else [])
 gen_s = time.time() - t
 extra = a.extra.split()
+OURS = os.environ.get("KART_BIN", os.path.join(ROOT, "kart_b200", "bin", "kart"))
 
 
 def run(binary, threads, args, out):
     t = time.perf_counter()
-    subprocess.run([binary, "-silent", "-t", str(threads), "-i", prefix] + args + ["-o", out] + extra, check=True, stdout=subprocess.DEVNULL)
+    subprocess.run([binary, "-silent", "-t", str(threads), "-i", prefix] + args + ["-o", out] + (extra if binary == OURS else []), check=True, stdout=subprocess.DEVNULL)
     return time.perf_counter() - t
 
 
@@ -55,7 +56,6 @@ def md5(path, sort=False):
     return h.hexdigest()
 
 
-OURS = os.environ.get("KART_BIN", os.path.join(ROOT, "kart_b200", "bin", "kart"))
 res = {"prefix": os.path.basename(prefix), "mode": a.mode, "reads": n_reads, "read_len": L, "error": a.error, "threads": a.threads, "gen_s": round(gen_s, 2)}
 ours_sam, ref_sam, ref1_sam = (os.path.join(tmp, x) for x in ("ours.sam", "ref.sam", "ref1.sam"))
 res["ours_load_s"] = min(run(OURS, a.threads, empty, os.path.join(tmp, "e.sam")) for _ in range(2))
