@@ -443,6 +443,9 @@ KB_HD int kb_nww_traceback(KbNwWarp& w, KbArena& fast, KbArena& ar, u32* out, in
 // ================================================================================================
 enum { KB_W_FRAG = 0, KB_W_NW = 1, KB_W_COPY = 2, KB_W_INS = 3, KB_W_DEL = 4 };
 struct KbWork { i32 r0, rl, g0, gl, kind, pad; };
+struct KbWorkP { i32 r0, rl, g0; u32 glk; };   // the work stack's 16-byte form: gl in the low 28 bits, kind above
+KB_HD KbWorkP kb_work_pack(const KbWork& w) { KbWorkP p; p.r0 = w.r0; p.rl = w.rl; p.g0 = w.g0; p.glk = (u32)w.gl | ((u32)w.kind << 28); return p; }
+KB_HD KbWork kb_work_unpack(const KbWorkP& p) { KbWork w; w.r0 = p.r0; w.rl = p.rl; w.g0 = p.g0; w.gl = (i32)(p.glk & 0x0FFFFFFFu); w.kind = (i32)(p.glk >> 28); w.pad = 0; return w; }
 
 // nw_alignment size class of an (rl x gl) problem at text position g
 KB_HD u32 kb_piece_class(const KbIndexDev& ix, int rl, int gl, i64 g)
@@ -487,18 +490,19 @@ struct KbSink
 
 struct KbFragIter
 {
-	const KbParams* pm; KbArena* ar; const u8* f1; const u8* f2; KbSink* sink;
-	KbWork* st; int sp, scap; u64 mark0;
+	const KbParams* pm; KbArena* ar; KbArena* fast; const u8* f1; const u8* f2; KbSink* sink;
+	KbWorkP* st; int sp, scap;
 	// the fragment being partitioned (between next() == 2 and part_finish())
-	KbWork cur; u32* w1; u32* w2; KbSeg* raw; int shift, cap, dirty; u32 np; u64 pmark;
+	KbWork cur; u32* w1; u32* w2; KbSeg* raw; int shift, cap, dirty; u32 np; u64 pmark, fmark;
 
-	KB_HD bool init(const KbParams* pm_, KbArena* ar_, const u8* f1_, int rl0, const u8* f2_, int gl0, KbSink* sink_)
+	// fast_: the warp's shared-memory pool, used for whatever fits; ar_: its arena in HBM
+	KB_HD bool init(const KbParams* pm_, KbArena* fast_, KbArena* ar_, const u8* f1_, int rl0, const u8* f2_, int gl0, KbSink* sink_)
 	{
-		pm = pm_; ar = ar_; f1 = f1_; f2 = f2_; sink = sink_; mark0 = ar->used; sp = 0;
+		pm = pm_; ar = ar_; fast = fast_; f1 = f1_; f2 = f2_; sink = sink_; sp = 0;
 		scap = rl0 + gl0 + 4;
-		st = (KbWork*)ar->alloc((u64)scap * sizeof(KbWork));
+		st = (KbWorkP*)kb_alloc2(*fast, *ar, (u64)scap * sizeof(KbWorkP));
 		if (st == nullptr) return false;
-		KbWork w; w.r0 = 0; w.rl = rl0; w.g0 = 0; w.gl = gl0; w.kind = KB_W_FRAG; w.pad = 0; st[sp++] = w;
+		KbWork w; w.r0 = 0; w.rl = rl0; w.g0 = 0; w.gl = gl0; w.kind = KB_W_FRAG; w.pad = 0; st[sp++] = kb_work_pack(w);
 		return true;
 	}
 
@@ -508,7 +512,7 @@ struct KbFragIter
 	{
 		while (sp > 0 && !ar->ovf && !sink->ovf)
 		{
-			const KbWork e = st[--sp];
+			const KbWork e = kb_work_unpack(st[--sp]);
 			const u8* a = f1 + e.r0; const u8* b = f2 + e.g0;
 			if (e.kind == KB_W_INS) { sink->lit(KB_RUN_I, e.rl, e.rl); continue; }
 			if (e.kind == KB_W_DEL) { sink->lit(KB_RUN_D, e.gl, e.gl); continue; }
@@ -523,11 +527,11 @@ struct KbFragIter
 				int rl = e.rl, gl = e.gl;
 				if (pm->pacbio) { shift = rl > gl ? (int)(rl * 0.2) : (int)(gl * 0.2); if (shift > 50) shift = 50; }
 				else shift = pm->max_gaps;
-				pmark = ar->used;
-				w1 = (u32*)ar->alloc((u64)rl * 4); w2 = (u32*)ar->alloc((u64)gl * 4);
+				pmark = ar->used; fmark = fast->used;
+				w1 = (u32*)kb_alloc2(*fast, *ar, (u64)rl * 4); w2 = (u32*)kb_alloc2(*fast, *ar, (u64)gl * 4);
 				cap = ((rl < gl ? rl : gl) / 9 + 2) * (2 * shift + 1);   // exact-match runs on one diagonal start >= 9 apart
 				if (cap > rl + gl) cap = rl + gl;
-				raw = (KbSeg*)ar->alloc((u64)cap * sizeof(KbSeg));
+				raw = (KbSeg*)kb_alloc2(*fast, *ar, (u64)cap * sizeof(KbSeg));
 				if (ar->ovf) return 0;
 				cur = e; np = 0; dirty = 0;
 				return 2;
@@ -586,8 +590,8 @@ struct KbFragIter
 		if (n > 0)
 		{
 			kb_sort_segs<true>(raw, n);
-			part = (KbSeg*)ar->alloc((u64)(2 * n + 2) * sizeof(KbSeg));
-			i32* order = (i32*)ar->alloc((u64)n * 4);
+			part = (KbSeg*)kb_alloc2(*fast, *ar, (u64)(2 * n + 2) * sizeof(KbSeg));
+			i32* order = (i32*)kb_alloc2(*fast, *ar, (u64)n * 4);
 			if (ar->ovf) return;
 			tot = kb_fill_pairs(rl, gl, raw, n, part, order);
 		}
@@ -604,12 +608,12 @@ struct KbFragIter
 				else if ((p.rlen == 1 && p.glen == 1) || p.simple) w.kind = KB_W_COPY;
 				else if (pm->pacbio && (p.rlen > 300 || p.glen > 300)) w.kind = KB_W_FRAG;
 				else w.kind = KB_W_NW;
-				st[sp++] = w;
+				st[sp++] = kb_work_pack(w);
 			}
-			ar->used = pmark;
+			ar->used = pmark; fast->used = fmark;
 			return;
 		}
-		ar->used = pmark;
+		ar->used = pmark; fast->used = fmark;
 		sink->piece(e.r0, e.rl, e.g0, e.gl);
 	}
 };
@@ -758,30 +762,23 @@ KB_HD bool kb_segments_cand_stream(const KbIndexDev& ix, const KbParams& pm, con
 	u32 off = KB_ATOMIC_ADD(&bt.counters[8], (u32)n);
 	if ((u64)off + (u64)n > (u64)bt.cap_segx) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SEGX); return true; }
 	bt.cseg_off[ci] = off; bt.cseg_n[ci] = n;
-	int j = 0;
-	if (head > 0)
-	{
-		KbSeg h; h.simple = 0; h.rpos = 0; h.gpos = first.gpos - head; if (h.gpos < 0) h.gpos = 0; h.rlen = head; h.glen = head;
-		kb_classify_segment(ix, pm, bt, r, seq, rd, h, j, n, &bt.segx[off + j]); j++;
-	}
+	// one loop, one call site of kb_classify_segment: the lanes of a warp then classify their j-th segments together,
+	// whatever kind they are (four call sites would serialise heads, seeds, gaps and tails behind one another)
+	int k = 0; bool gap_done = false;
 	prev = first;
-	kb_classify_segment(ix, pm, bt, r, seq, rd, prev, j, n, &bt.segx[off + j]); j++;
-	for (int k = 1; k < ns; k++)
+	for (int j = 0; j < n; j++)
 	{
-		const KbSeg cur = in[k];
-		const int rg = cur.rpos - (prev.rpos + prev.rlen); const int gg = (int)(cur.gpos - (prev.gpos + prev.glen));
-		if (rg > 0 || gg > 0)
+		KbSeg sg;
+		if (j == 0 && head > 0) { sg.simple = 0; sg.rpos = 0; sg.gpos = first.gpos - head; if (sg.gpos < 0) sg.gpos = 0; sg.rlen = head; sg.glen = head; }
+		else if (k >= ns) { sg.simple = 0; sg.rpos = prev.rpos + prev.rlen; sg.gpos = prev.gpos + prev.glen; sg.rlen = tail; sg.glen = tail; }
+		else
 		{
-			KbSeg g; g.simple = 0; g.rpos = prev.rpos + prev.rlen; g.gpos = prev.gpos + prev.glen; g.rlen = rg; g.glen = gg;
-			kb_classify_segment(ix, pm, bt, r, seq, rd, g, j, n, &bt.segx[off + j]); j++;
+			const KbSeg cur = in[k];
+			const int rg = k > 0 ? cur.rpos - (prev.rpos + prev.rlen) : 0, gg = k > 0 ? (int)(cur.gpos - (prev.gpos + prev.glen)) : 0;
+			if (!gap_done && (rg > 0 || gg > 0)) { sg.simple = 0; sg.rpos = prev.rpos + prev.rlen; sg.gpos = prev.gpos + prev.glen; sg.rlen = rg; sg.glen = gg; gap_done = true; }
+			else { sg = cur; prev = cur; k++; gap_done = false; }
 		}
-		kb_classify_segment(ix, pm, bt, r, seq, rd, cur, j, n, &bt.segx[off + j]); j++;
-		prev = cur;
-	}
-	if (tail > 0)
-	{
-		KbSeg e; e.simple = 0; e.rpos = prev.rpos + prev.rlen; e.gpos = prev.gpos + prev.glen; e.rlen = tail; e.glen = tail;
-		kb_classify_segment(ix, pm, bt, r, seq, rd, e, j, n, &bt.segx[off + j]); j++;
+		kb_classify_segment(ix, pm, bt, r, seq, rd, sg, j, n, &bt.segx[off + j]);
 	}
 	return true;
 }
@@ -980,7 +977,7 @@ KB_HD void kb_pt_begin(const KbIndexDev& ix, const KbParams& pm, const KbBatchDe
 	w.sink.ix = &ix; w.sink.bt = &bt; w.sink.job = id; w.sink.gpos = jb.gpos; w.sink.base = jb.run_off; w.sink.cap = (u32)(jb.rlen + jb.glen + 2); w.sink.cur = 0;
 	w.sink.ident = 0; w.sink.aligned = 0; w.sink.ovf = false;
 	w.ok = (w.f1 != nullptr && w.f2 != nullptr) ? 1 : 0;
-	if (w.ok) w.ok = w.it.init(&pm, &w.ar, w.f1, jb.rlen, w.f2, jb.glen, &w.sink) ? 1 : 0;
+	if (w.ok) w.ok = w.it.init(&pm, &w.fast, &w.ar, w.f1, jb.rlen, w.f2, jb.glen, &w.sink) ? 1 : 0;
 }
 // all lanes: characters of the fragment into the warp's pool, and the job's slice of the run arena zeroed
 KB_HD void kb_pt_fetch(const KbIndexDev& ix, const KbBatchDev& bt, KbPartWarp& w, int t)

@@ -20,7 +20,8 @@
 
 #define KB_BLOCK 128
 #define KB_SLOTS 3           // batches in flight in kb_map_chunk's pipeline
-#define KB_ALIGN_POOL 6144   // shared-memory bytes per warp of k_align (fragment chars, codes, 2-bit traceback)
+#define KB_ALIGN_WARPS (148 * 8)   // warps of the warp-per-job kernels (k_align_part, k_nw_warp), each with a private arena
+#define KB_ALIGN_POOL 10240  // shared-memory bytes per warp of k_align (fragment chars, codes, 2-bit traceback)
 
 // ------------------------------------------------------------------------------------------------
 // kernels
@@ -57,10 +58,9 @@ __global__ void k_ref64(const u8* pac, u64 bytes, u64 words, u64* out)
 template <int MINB>
 __global__ void __launch_bounds__(KB_BLOCK, MINB) k_fm_seed(KbIndexDev ix, KbParams pm, KbBatchDev bt)
 {
-	const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	const long long r0 = w * KB_SEED_WARP_READS, r1 = r0 + KB_SEED_WARP_READS;
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
 	u32 steps = 0, blocks = 0;
-	kb_seed_reads(ix, pm, bt, (int)(r0 < bt.n_reads ? r0 : bt.n_reads), (int)(r1 < bt.n_reads ? r1 : bt.n_reads), bt.seed_next + w, &steps, &blocks);
+	kb_seed_read(ix, pm, bt, r, r < bt.n_reads, &steps, &blocks);
 	kb_warp_add64(&bt.work[0], steps); kb_warp_add64(&bt.work[1], blocks);
 }
 
@@ -176,10 +176,10 @@ __global__ void __launch_bounds__(KB_BLOCK) k_align_part(KbIndexDev ix, KbParams
 	if (bt.counters[3]) return;
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	const u32 gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-	if ((int)(gwarp * 32) >= bt.scratch_threads) return;
+	if ((int)gwarp >= bt.wscratch_warps) return;
 	KbPartWarp& w = sw[wib];
 	const u32 njobs = bt.counters[23];
-	if (lane == 0) { w.ar.base = bt.scratch + (u64)gwarp * 32ull * bt.scratch_per_thread; w.ar.cap = 32ull * bt.scratch_per_thread; w.fast.base = pool[wib]; w.fast.cap = KB_ALIGN_POOL; w.fast.ovf = false; }
+	if (lane == 0) { w.ar.base = bt.wscratch + (u64)gwarp * bt.wscratch_per_warp; w.ar.cap = bt.wscratch_per_warp; w.fast.base = pool[wib]; w.fast.cap = KB_ALIGN_POOL; w.fast.ovf = false; }
 	__syncwarp();
 	for (u32 q = gwarp; q < njobs; q += nwarps)
 	{
@@ -209,11 +209,11 @@ __global__ void __launch_bounds__(KB_BLOCK) k_nw_warp(KbIndexDev ix, KbParams pm
 	if (bt.counters[3]) return;
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	const u32 gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-	if ((int)(gwarp * 32) >= bt.scratch_threads) return;
+	if ((int)gwarp >= bt.wscratch_warps) return;
 	KbPieceWarp& w = sw[wib];
 	const int cls = KB_NW_CLASSES - 1;
 	const u32 count = bt.counters[16 + cls]; const u32* list = bt.piece_list + (size_t)cls * bt.cap_pieces;
-	if (lane == 0) { w.ar.base = bt.scratch + (u64)gwarp * 32ull * bt.scratch_per_thread; w.ar.cap = 32ull * bt.scratch_per_thread; w.fast.base = pool[wib]; w.fast.cap = KB_ALIGN_POOL; w.fast.ovf = false; w.cells = 0; w.calls = 0; }
+	if (lane == 0) { w.ar.base = bt.wscratch + (u64)gwarp * bt.wscratch_per_warp; w.ar.cap = bt.wscratch_per_warp; w.fast.base = pool[wib]; w.fast.cap = KB_ALIGN_POOL; w.fast.ovf = false; w.cells = 0; w.calls = 0; }
 	__syncwarp();
 	for (u32 q = gwarp; q < count; q += nwarps)
 	{
@@ -248,7 +248,7 @@ static void k_align_part(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulati
 	if (blockIdx.x != 0 || threadIdx.x != 0) return;
 	if (bt.counters[3]) return;
 	static KbPartWarp w; static u8 pool[KB_ALIGN_POOL];
-	w.ar.base = bt.scratch; w.ar.cap = 32ull * bt.scratch_per_thread; w.fast.base = pool; w.fast.cap = KB_ALIGN_POOL; w.fast.ovf = false;
+	w.ar.base = bt.wscratch; w.ar.cap = bt.wscratch_per_warp; w.fast.base = pool; w.fast.cap = KB_ALIGN_POOL; w.fast.ovf = false;
 	const u32 njobs = bt.counters[23];
 	for (u32 q = 0; q < njobs; q++)
 	{
@@ -271,7 +271,7 @@ static void k_nw_warp(KbIndexDev ix, KbParams pm, KbBatchDev bt)
 	if (blockIdx.x != 0 || threadIdx.x != 0) return;
 	if (bt.counters[3]) return;
 	static KbPieceWarp w; KbNwLane L[32]; static u8 pool[KB_ALIGN_POOL];
-	w.ar.base = bt.scratch; w.ar.cap = 32ull * bt.scratch_per_thread; w.fast.base = pool; w.fast.cap = KB_ALIGN_POOL; w.fast.ovf = false; w.cells = 0; w.calls = 0;
+	w.ar.base = bt.wscratch; w.ar.cap = bt.wscratch_per_warp; w.fast.base = pool; w.fast.cap = KB_ALIGN_POOL; w.fast.ovf = false; w.cells = 0; w.calls = 0;
 	const int cls = KB_NW_CLASSES - 1;
 	const u32 count = bt.counters[16 + cls]; const u32* list = bt.piece_list + (size_t)cls * bt.cap_pieces;
 	for (u32 q = 0; q < count; q++)
@@ -332,15 +332,15 @@ struct kb_slot
 {
 	cudaStream_t stream = nullptr; cudaEvent_t ev[10]; cudaEvent_t done = nullptr;
 	KbBatchDev bt; int n_reads = 0; size_t seq_bytes = 0; u64 seq_first = 0; int max_rlen = 0; int first_read = 0;
-	DevBuf<u8> seq, scratch; DevBuf<u64> seq_off; DevBuf<unsigned long long> work; DevBuf<i32> est, n_hits, n_seeds, n_cands, cand_cap, rescue, slow1, slow2; DevBuf<u32> seed_next, seed_off, cand_off, cigar, counters, cseg_off, runs; DevBuf<i32> cseg_n; DevBuf<KbSegX> segx; DevBuf<KbJob> jobs; DevBuf<u32> piece_list, part_list; DevBuf<KbPiece> pieces;
+	DevBuf<u8> seq, scratch, wscratch; DevBuf<u64> seq_off; DevBuf<unsigned long long> work; DevBuf<i32> est, n_hits, n_seeds, n_cands, cand_cap, rescue, slow1, slow2; DevBuf<u32> seed_off, cand_off, cigar, counters, cseg_off, runs; DevBuf<i32> cseg_n; DevBuf<KbSegX> segx; DevBuf<KbJob> jobs; DevBuf<u32> piece_list, part_list; DevBuf<KbPiece> pieces;
 	DevBuf<KbHit> hits; DevBuf<KbSeg> segs; DevBuf<KbCand> cands; DevBuf<KbReport> reports; DevBuf<KbReadRes> res; DevBuf<KbPairStat> pstat; DevBuf<kb_aln_t> aln; DevBuf<KbPk> pk;
 	size_t cap_segs = 0, cap_cands = 0, cap_cigar = 0, cap_segx = 0, cap_jobs = 0, cap_pieces = 0, cap_runs = 0, scratch_per_thread = 0; int scratch_threads = 0;
 	u32* counters_host = nullptr; unsigned long long* work_dev_host = nullptr;   // pinned: 16 x u32, 8 x u64
 	int launches = 0;
 	void release()
 	{
-		seq.release(); scratch.release(); seq_off.release(); work.release(); est.release(); n_hits.release(); n_seeds.release(); n_cands.release(); cand_cap.release();
-		rescue.release(); seed_next.release(); slow1.release(); slow2.release(); seed_off.release(); cand_off.release(); cigar.release(); counters.release(); cseg_off.release(); runs.release();
+		seq.release(); scratch.release(); wscratch.release(); seq_off.release(); work.release(); est.release(); n_hits.release(); n_seeds.release(); n_cands.release(); cand_cap.release();
+		rescue.release(); slow1.release(); slow2.release(); seed_off.release(); cand_off.release(); cigar.release(); counters.release(); cseg_off.release(); runs.release();
 		cseg_n.release(); segx.release(); jobs.release(); piece_list.release(); part_list.release(); pieces.release(); hits.release(); segs.release(); cands.release(); reports.release(); res.release(); pstat.release(); aln.release(); pk.release();
 	}
 };
@@ -571,23 +571,26 @@ static int alloc_batch(kb_ctx* ctx, kb_slot& sl, int shared)
 	if (threads > n) threads = n;
 	threads = (threads + KB_BLOCK - 1) / KB_BLOCK * KB_BLOCK; if (threads < KB_BLOCK) threads = KB_BLOCK;
 	sl.scratch_per_thread = per; sl.scratch_threads = (int)threads;
-	CK(sl.hits.ensure(n * max_hits)); CK(sl.n_hits.ensure(n)); CK(sl.seed_next.ensure((n + KB_SEED_WARP_READS - 1) / KB_SEED_WARP_READS + KB_BLOCK / 32)); CK(sl.n_seeds.ensure(n)); CK(sl.seed_off.ensure(n));
+	// the warp-per-job kernels get their own arenas (one worst-case problem each), independent of the number of reads
+	const int wwarps = KB_ALIGN_WARPS;
+	CK(sl.hits.ensure(n * max_hits)); CK(sl.n_hits.ensure(n)); CK(sl.n_seeds.ensure(n)); CK(sl.seed_off.ensure(n));
 	CK(sl.segs.ensure(sl.cap_segs)); CK(sl.cands.ensure(sl.cap_cands)); CK(sl.reports.ensure(sl.cap_cands));
 	CK(sl.n_cands.ensure(n)); CK(sl.cand_off.ensure(n)); CK(sl.cand_cap.ensure(n)); CK(sl.rescue.ensure(n / 2 + 1));
 	CK(sl.res.ensure(n)); CK(sl.pstat.ensure(n / 2 + 1)); CK(sl.aln.ensure(n));
 	if (!shared) CK(sl.cigar.ensure(sl.cap_cigar));
 	CK(sl.segx.ensure(sl.cap_segx)); CK(sl.jobs.ensure(sl.cap_jobs)); CK(sl.pieces.ensure(sl.cap_pieces)); CK(sl.piece_list.ensure(sl.cap_pieces * KB_NW_CLASSES)); CK(sl.part_list.ensure(sl.cap_jobs)); CK(sl.runs.ensure(sl.cap_runs)); CK(sl.cseg_off.ensure(sl.cap_cands)); CK(sl.cseg_n.ensure(sl.cap_cands));
-	CK(sl.counters.ensure(KB_NCOUNTERS)); CK(sl.work.ensure(8)); CK(sl.scratch.ensure(per * threads));
+	CK(sl.counters.ensure(KB_NCOUNTERS)); CK(sl.work.ensure(8)); CK(sl.scratch.ensure(per * threads)); CK(sl.wscratch.ensure(per * (size_t)wwarps));
 	CK(sl.pk.ensure((sl.seq_bytes >> 5) + n + 4)); CK(sl.slow1.ensure(n + 1)); CK(sl.slow2.ensure(n + 1));
 	// reads keep their chunk-wide offsets: the device copies start at seq_first, so the base pointers are shifted back by it
 	bt.n_reads = sl.n_reads; bt.seq = sl.seq.p - sl.seq_first; bt.seq_off = sl.seq_off.p; bt.est = sl.est.p; bt.pk = sl.pk.p - (sl.seq_first >> 5); bt.pk_wpr = (L + 31) / 32;
-	bt.hits = sl.hits.p; bt.max_hits = max_hits; bt.n_hits = sl.n_hits.p; bt.seed_next = sl.seed_next.p; bt.n_seeds = sl.n_seeds.p; bt.seed_off = sl.seed_off.p;
+	bt.hits = sl.hits.p; bt.max_hits = max_hits; bt.n_hits = sl.n_hits.p; bt.n_seeds = sl.n_seeds.p; bt.seed_off = sl.seed_off.p;
 	bt.segs = sl.segs.p; bt.cap_segs = (u32)sl.cap_segs; bt.cands = sl.cands.p; bt.cap_cands = (u32)sl.cap_cands; bt.n_cands = sl.n_cands.p;
 	bt.cand_off = sl.cand_off.p; bt.cand_cap = sl.cand_cap.p; bt.rescue_list = sl.rescue.p; bt.slow_list = sl.slow1.p; bt.slow_list2 = sl.slow2.p; bt.reports = sl.reports.p; bt.res = sl.res.p; bt.pstat = sl.pstat.p;
 	bt.segx = sl.segx.p; bt.cap_segx = (u32)sl.cap_segx; bt.cseg_off = sl.cseg_off.p; bt.cseg_n = sl.cseg_n.p; bt.jobs = sl.jobs.p; bt.cap_jobs = (u32)sl.cap_jobs; bt.pieces = sl.pieces.p; bt.cap_pieces = (u32)sl.cap_pieces; bt.piece_list = sl.piece_list.p; bt.part_list = sl.part_list.p; bt.runs = sl.runs.p; bt.cap_runs = (u32)sl.cap_runs;
 	if (shared) { bt.cigar = ctx->chunk_cigar.p; bt.cap_cigar = (u32)ctx->chunk_cigar.n; bt.cig_cursor = ctx->chunk_cursor.p; }
 	else { bt.cigar = sl.cigar.p; bt.cap_cigar = (u32)sl.cap_cigar; bt.cig_cursor = sl.counters.p + 2; }
 	bt.scratch = sl.scratch.p; bt.scratch_per_thread = per; bt.scratch_threads = (int)threads;
+	bt.wscratch = sl.wscratch.p; bt.wscratch_per_warp = per; bt.wscratch_warps = wwarps;
 	bt.max_rlen = L; bt.nw_max_m = 0; bt.nw_max_n = 0; bt.seg_cap = 0; bt.kmer_cap = 0; bt.counters = sl.counters.p; bt.work = sl.work.p;
 	return KB_OK;
 }
@@ -632,38 +635,36 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 	unsigned g_items = pm.paired ? (unsigned)((n / 2 + KB_BLOCK - 1) / KB_BLOCK) : g_reads;
 	unsigned g_hits = (unsigned)(((long long)n * bt.max_hits + KB_BLOCK - 1) / KB_BLOCK);
 	unsigned g_scr = (unsigned)(bt.scratch_threads / KB_BLOCK);
+	unsigned g_warp = (unsigned)(KB_ALIGN_WARPS * 32 / KB_BLOCK);
+	unsigned g_slow = g_reads < 148u * 16u ? g_reads : 148u * 16u;   // arena kernels: one thread per read up to a full machine, slices cut on the device
 	sl.launches = 0;
 	CK(cudaEventRecord(sl.ev[0], s));
 	KB_LAUNCH(k_pack, (unsigned)(((long long)n * bt.pk_wpr + KB_BLOCK - 1) / KB_BLOCK), KB_BLOCK, s, bt); sl.launches++;
-	{
-		const unsigned warps = (unsigned)((n + KB_SEED_WARP_READS - 1) / KB_SEED_WARP_READS), g_seed = (warps * 32 + KB_BLOCK - 1) / KB_BLOCK;
-		CK(cudaMemsetAsync(sl.seed_next.p, 0, (size_t)g_seed * (KB_BLOCK / 32) * sizeof(u32), s));
-		if (ctx->seed_minb == 8) { KB_LAUNCH(k_fm_seed<8>, g_seed, KB_BLOCK, s, ix, pm, bt); } else { KB_LAUNCH(k_fm_seed<10>, g_seed, KB_BLOCK, s, ix, pm, bt); }
-		sl.launches++;
-	}
+	if (ctx->seed_minb == 8) { KB_LAUNCH(k_fm_seed<8>, g_reads, KB_BLOCK, s, ix, pm, bt); } else { KB_LAUNCH(k_fm_seed<10>, g_reads, KB_BLOCK, s, ix, pm, bt); }
+	sl.launches++;
 	CK(cudaEventRecord(sl.ev[1], s));
 	KB_LAUNCH(k_sa_locate, g_hits, KB_BLOCK, s, ix, bt); sl.launches++;
 	CK(cudaEventRecord(sl.ev[2], s));
 	KB_LAUNCH(k_cand_pair, g_items, KB_BLOCK, s, ix, pm, bt); sl.launches++;
-	if (pm.pacbio) { KB_LAUNCH(k_cand_pacbio, g_scr, KB_BLOCK, s, ix, pm, bt); sl.launches++; }
+	if (pm.pacbio) { KB_LAUNCH(k_cand_pacbio, g_slow, KB_BLOCK, s, ix, pm, bt); sl.launches++; }
 	CK(cudaEventRecord(sl.ev[3], s));
 	if (pm.paired) { KB_LAUNCH(k_rescue, g_scr, KB_BLOCK, s, ix, pm, bt); sl.launches++; }
 	CK(cudaEventRecord(sl.ev[4], s));
 	KB_LAUNCH(k_segments, g_reads, KB_BLOCK, s, ix, pm, bt); sl.launches++;
-	KB_LAUNCH(k_segments_slow, g_scr, KB_BLOCK, s, ix, pm, bt); sl.launches++;
+	KB_LAUNCH(k_segments_slow, g_slow, KB_BLOCK, s, ix, pm, bt); sl.launches++;
 	CK(cudaEventRecord(sl.ev[5], s));
-	KB_LAUNCH(k_align_part, g_scr, KB_BLOCK, s, ix, pm, bt); sl.launches++;
+	KB_LAUNCH(k_align_part, g_warp, KB_BLOCK, s, ix, pm, bt); sl.launches++;
 	KB_LAUNCH((k_nw_tile<0, 8, 32, 1>), 148 * 8, KB_BLOCK, s, ix, pm, bt); sl.launches++;
 	KB_LAUNCH((k_nw_tile<1, 16, 32, 1>), 148 * 8, KB_BLOCK, s, ix, pm, bt); sl.launches++;
 	KB_LAUNCH((k_nw_tile<2, 24, 32, 1>), 148 * 8, KB_BLOCK, s, ix, pm, bt); sl.launches++;
 	KB_LAUNCH((k_nw_tile<3, 32, 32, 1>), 148 * 8, KB_BLOCK, s, ix, pm, bt); sl.launches++;
 	KB_LAUNCH((k_nw_tile<4, 32, 64, 2>), 148 * 4, KB_BLOCK, s, ix, pm, bt); sl.launches++;
 	KB_LAUNCH((k_nw_tile<5, 32, 128, 4>), 148 * 4, KB_BLOCK, s, ix, pm, bt); sl.launches++;
-	KB_LAUNCH(k_nw_warp, g_scr, KB_BLOCK, s, ix, pm, bt); sl.launches++;
+	KB_LAUNCH(k_nw_warp, g_warp, KB_BLOCK, s, ix, pm, bt); sl.launches++;
 	KB_LAUNCH(k_align_gather, 148 * 4, KB_BLOCK, s, bt); sl.launches++;
 	CK(cudaEventRecord(sl.ev[6], s));
 	KB_LAUNCH(k_assemble, g_reads, KB_BLOCK, s, ix, pm, bt); sl.launches++;
-	KB_LAUNCH(k_assemble_slow, g_scr, KB_BLOCK, s, ix, pm, bt); sl.launches++;
+	KB_LAUNCH(k_assemble_slow, g_slow, KB_BLOCK, s, ix, pm, bt); sl.launches++;
 	CK(cudaEventRecord(sl.ev[7], s));
 	KB_LAUNCH(k_finalize, g_items, KB_BLOCK, s, ix, pm, bt, sl.aln.p); sl.launches++;
 	CK(cudaEventRecord(sl.ev[8], s));

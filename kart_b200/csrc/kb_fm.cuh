@@ -221,7 +221,7 @@ KB_HD u64 kb_sa(const KbIndexDev& ix, u64 k, u32* steps)
 	return s + KB_LDG(ix.sa + k / (u64)ix.sa_intv);
 }
 
-// Per read: all searches of IdentifySeedPairs_FastMode (:49) or _SensitiveMode (:132) with BWT_Search (:140-170) inlined.
+// One read: all searches of IdentifySeedPairs_FastMode (:49) or _SensitiveMode (:132) with BWT_Search (:140-170) inlined.
 // The lanes of a warp each own one read and advance in lock-step, one extension per trip. Everything that is not an
 // extension (closing a search: :172-181 and the caller's bookkeeping; opening the next one) is kept out of the extension
 // loop and done for several lanes at once: a lane whose search has ended parks until KB_SEED_QUORUM lanes are parked (or
@@ -230,23 +230,21 @@ KB_HD u64 kb_sa(const KbIndexDev& ix, u64 k, u32* steps)
 // inside its limit starts from the seeding table instead of K-1 extension steps (identical state by construction).
 // Records the searches that will yield seeds (len >= MinSeedLength and interval size <= OCC_Thr 50, bwt_search.cpp:3,172-176).
 #define KB_SEED_QUORUM 6
-#define KB_SEED_WARP_READS 128   // reads handed to one warp of k_fm_seed (its lanes pull them one by one)
 #if defined(__CUDA_ARCH__)
 #define KB_BALLOT(p) __ballot_sync(0xFFFFFFFFu, (p))
 #else
 #define KB_BALLOT(p) ((p) ? 1u : 0u)
 #endif
-KB_HD void kb_seed_reads(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int r_begin, int r_end, u32* next, u32* w_steps, u32* w_blocks)
+KB_HD void kb_seed_read(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int r, bool valid, u32* w_steps, u32* w_blocks)
 {
-	// The lanes of a warp share the reads [r_begin, r_end): a lane that is done with its read takes the next one from the
-	// warp's cursor, so lanes stay busy until the warp's range is exhausted (reads differ in the number of searches).
-	const KbPk* rd = bt.pk; KbHit* hits = bt.hits;
-	int r = -1, rlen = 0, end = 0;
+	const KbPk* rd = valid ? kb_pk_read(bt, r) : bt.pk;
+	const int rlen = valid ? (int)(bt.seq_off[r + 1] - bt.seq_off[r]) : 0;
+	KbHit* hits = bt.hits + (size_t)(valid ? r : 0) * bt.max_hits;
 	int nh = 0, ns = 0, pos = 0, cur = 0, lim = 0, stop = 30, len = 0;
-	const int K = (ix.ktab != nullptr && ix.ktab_k <= pm.min_seed) ? ix.ktab_k : 0;
+	const int end = rlen - pm.min_seed, K = (ix.ktab != nullptr && ix.ktab_k <= pm.min_seed) ? ix.ktab_k : 0;
 	u32 steps = 0, blocks = 0;
 	u64 x0 = 0, x1 = 0, x2 = 0;
-	bool searching = false, closing = false, finished = r_begin >= r_end, ovf = false;
+	bool searching = false, closing = false, finished = !valid, ovf = false;
 	int cw = -1; u64 ccode = 0; u32 cn4 = 0;   // the packed word under the cursor
 #if defined(__CUDA_ARCH__)
 	const u32 quorum = KB_SEED_QUORUM;
@@ -255,7 +253,7 @@ KB_HD void kb_seed_reads(const KbIndexDev& ix, const KbParams& pm, const KbBatch
 #endif
 	while (KB_BALLOT(!finished))
 	{
-		// parked lanes: close the search that ended, open the next one (of the next read when this one is through)
+		// parked lanes: close the search that ended, open the next one
 		while (!finished && !searching)
 		{
 			if (closing)
@@ -279,23 +277,7 @@ KB_HD void kb_seed_reads(const KbIndexDev& ix, const KbParams& pm, const KbBatch
 				if (p <= 3) break;
 				pos++; stop++;
 			}
-			if (pos >= end)
-			{
-				if (r >= 0)   // this read is through: publish its hit count and reserve its seeds
-				{
-					if (ovf) KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_HITS);
-					bt.n_hits[r] = nh; bt.n_seeds[r] = ns;
-					u32 off = KB_ATOMIC_ADD(&bt.counters[0], (u32)ns);
-					bt.seed_off[r] = off;
-					if ((u64)off + (u64)ns > (u64)bt.cap_segs) KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SEEDS);
-					KB_ATOMIC_MAX(&bt.counters[5], (u32)ns);
-				}
-				const int k = r_begin + (int)KB_ATOMIC_ADD(next, 1u);
-				if (k >= r_end) { finished = true; r = -1; break; }
-				r = k; rd = kb_pk_read(bt, r); rlen = (int)(bt.seq_off[r + 1] - bt.seq_off[r]); hits = bt.hits + (size_t)r * bt.max_hits;
-				end = rlen - pm.min_seed; nh = 0; ns = 0; pos = 0; stop = 30; ovf = false; cw = -1;
-				continue;
-			}
+			if (pos >= end) { finished = true; break; }
 			lim = pm.pacbio ? (stop < rlen ? stop : rlen) : rlen;
 			bool seeded = false;
 			if (K > 0 && pos + K <= lim)
@@ -335,7 +317,14 @@ KB_HD void kb_seed_reads(const KbIndexDev& ix, const KbParams& pm, const KbBatch
 			parked = KB_BALLOT(!searching && !finished);
 		} while (active != 0 && (u32)KB_POPCLL((u64)parked) < quorum);
 	}
+	if (!valid) return;
 	*w_steps += steps; *w_blocks += blocks;
+	if (ovf) KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_HITS);
+	bt.n_hits[r] = nh; bt.n_seeds[r] = ns;
+	u32 off = KB_ATOMIC_ADD(&bt.counters[0], (u32)ns);
+	bt.seed_off[r] = off;
+	if ((u64)off + (u64)ns > (u64)bt.cap_segs) KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SEEDS);
+	KB_ATOMIC_MAX(&bt.counters[5], (u32)ns);
 }
 
 // One (read, hit): resolve the SA interval to text positions, in SA-row order (bwt_search.cpp:176-179).

@@ -53,17 +53,24 @@ KB_HD void kb_stage_cand_pair(const KbIndexDev& ix, const KbParams& pm, const Kb
 	}
 }
 
-KB_HD KbArena kb_thread_arena(const KbBatchDev& bt, int tid)
+// Private arena of thread `tid` of an arena kernel launched with `nth` threads. The scratch buffer is sized for the worst
+// case per thread (a 3000 x 3000 traceback); the kernels that run one thread per read need far less than that per thread,
+// so they cut the same buffer into slices of `need` bytes (a bound computed on the device from the batch's own maxima) and
+// get that many more threads. Returns the number of threads that own a slice; the others must idle.
+KB_HD int kb_thread_arena(const KbBatchDev& bt, int tid, int nth, u64 need, KbArena* ar)
 {
-	KbArena ar; ar.base = bt.scratch + (u64)tid * bt.scratch_per_thread; ar.used = 0; ar.cap = bt.scratch_per_thread; ar.ovf = false;
-	return ar;
+	need = (need + 255) & ~(u64)255;
+	const u64 total = bt.scratch_per_thread * (u64)bt.scratch_threads;
+	u64 fit = total / need; if (fit > (u64)nth) fit = (u64)nth;
+	ar->base = bt.scratch + (u64)tid * need; ar->used = 0; ar->cap = need; ar->ovf = false;
+	return (int)fit;
 }
 
 KB_HD void kb_stage_cand_pacbio(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int tid, int nth)
 {
-	if (tid >= bt.scratch_threads) return;
 	if (bt.counters[3]) return;
-	KbArena ar = kb_thread_arena(bt, tid);
+	KbArena ar; nth = kb_thread_arena(bt, tid, nth, ((u64)bt.counters[5] + 2) * 32ull + 256ull, &ar);   // taken[] + a copy of the read's seeds
+	if (tid >= nth) return;
 	for (int r = tid; r < bt.n_reads; r += nth)
 	{
 		int n = bt.n_seeds[r];
@@ -89,9 +96,9 @@ KB_HD void kb_stage_segments(const KbIndexDev& ix, const KbParams& pm, const KbB
 }
 KB_HD void kb_stage_segments_slow(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int tid, int nth)
 {
-	if (tid >= bt.scratch_threads) return;
 	if (bt.counters[3]) return;
-	KbArena ar = kb_thread_arena(bt, tid);
+	KbArena ar; nth = kb_thread_arena(bt, tid, nth, (u64)(bt.counters[5] > 64u ? bt.counters[5] : 64u) * 128ull + 1024ull, &ar);   // seeds + 2 x segments + order of one candidate
+	if (tid >= nth) return;
 	const int count = (int)bt.counters[12];
 	for (int k = tid; k < count; k += nth)
 	{
@@ -110,9 +117,9 @@ KB_HD void kb_stage_assemble(const KbIndexDev& ix, const KbParams& pm, const KbB
 }
 KB_HD void kb_stage_assemble_slow(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int tid, int nth)
 {
-	if (tid >= bt.scratch_threads) return;
 	if (bt.counters[3]) return;
-	KbArena ar = kb_thread_arena(bt, tid);
+	KbArena ar; nth = kb_thread_arena(bt, tid, nth, 16ull * (u64)bt.max_rlen + 64ull * (u64)(bt.counters[5] > 64u ? bt.counters[5] : 64u) + 2048ull, &ar);   // cigar elements of one candidate (kb_assemble_read)
+	if (tid >= nth) return;
 	const int count = (int)bt.counters[13];
 	for (int k = tid; k < count; k += nth)
 	{

@@ -102,7 +102,6 @@ struct KbBatchDev
 	// stage 1
 	KbHit* hits; i32 max_hits;          // [n_reads][max_hits]
 	i32* n_hits;                        // hits stored per read
-	u32* seed_next;                     // k_fm_seed: per warp, how many of its KB_SEED_WARP_READS reads have been taken
 	i32* n_seeds; u32* seed_off;        // seeds per read and their offset in `segs`
 	KbSeg* segs; u32 cap_segs;
 	// stage 2
@@ -122,6 +121,7 @@ struct KbBatchDev
 	u32* cigar; u32 cap_cigar; u32* cig_cursor;   // cursor: counters[2] of the batch, or the chunk-wide cursor of a pipelined chunk
 	// per-thread scratch for the report / rescue kernels
 	u8* scratch; u64 scratch_per_thread; i32 scratch_threads;
+	u8* wscratch; u64 wscratch_per_warp; i32 wscratch_warps;   // arenas of the warp-per-job kernels (k_align_part, k_nw_warp)
 	i32 max_rlen;                       // longest read in the batch
 	i32 nw_max_m, nw_max_n, seg_cap, kmer_cap;
 	// counters: [0] seeds cursor [1] cands cursor [2] cigar cursor [3] status bits [4] rescue count [5] max seeds/read
