@@ -53,7 +53,7 @@ class KartB200Error(RuntimeError):
 
 
 def load_library(path: str | None = None) -> C.CDLL:
-    path = path or DEFAULT_LIB
+    path = path or os.environ.get("KART_B200_LIB") or DEFAULT_LIB   # the override is for A/B runs of an older build (scripts/gpu_ab.py)
     if not os.path.exists(path):
         raise KartB200Error("CUDA library %s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)" % path)
     lib = C.CDLL(path)

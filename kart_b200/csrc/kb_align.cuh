@@ -457,12 +457,12 @@ KB_HD u32 kb_piece_class(const KbIndexDev& ix, int rl, int gl, i64 g)
 // registers one nw_alignment problem; false when the piece arena is full (flagged)
 KB_HD bool kb_emit_piece(const KbIndexDev& ix, const KbBatchDev& bt, u32 job, i64 job_gpos, int r0, int rl, int g0, int gl, u32 out_off, u32 whole)
 {
-	const u32 id = KB_ATOMIC_ADD(&bt.counters[24], 1u);
+	const u32 id = KB_ALLOC(&bt.counters[24], 1u);
 	if (id >= bt.cap_pieces) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_JOBS); return false; }
 	KbPiece pc; pc.job = job; pc.r0 = r0; pc.rl = rl; pc.g0 = g0; pc.gl = gl; pc.out_off = out_off; pc.whole = whole; pc.pad = 0;
 	bt.pieces[id] = pc;
 	const u32 cls = kb_piece_class(ix, rl, gl, job_gpos + g0);
-	const u32 slot = KB_ATOMIC_ADD(&bt.counters[16 + cls], 1u);
+	const u32 slot = KB_ALLOC_KEYED(&bt.counters[16 + cls], 1u);
 	bt.piece_list[(size_t)cls * bt.cap_pieces + slot] = id;
 	return true;
 }
@@ -701,7 +701,7 @@ KB_HD void kb_classify_segment(const KbIndexDev& ix, const KbParams& pm, const K
 	}
 	// one 64-bit atomic reserves the job id (high word = counters[11]) and its slice of the run arena (low word = counters[10])
 	u32 need = (u32)(sp.rlen + sp.glen + 2);
-	unsigned long long old = KB_ATOMIC_ADD(reinterpret_cast<unsigned long long*>(bt.counters + 10), (1ull << 32) | (unsigned long long)need);
+	unsigned long long old = KB_ALLOC(reinterpret_cast<unsigned long long*>(bt.counters + 10), (unsigned long long)((1ull << 32) | (unsigned long long)need));
 	u32 id = (u32)(old >> 32), ro = (u32)old;
 	if (id >= bt.cap_jobs) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_JOBS); return; }
 	if ((u64)ro + need > (u64)bt.cap_runs) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_RUNS); return; }
@@ -709,7 +709,7 @@ KB_HD void kb_classify_segment(const KbIndexDev& ix, const KbParams& pm, const K
 	bt.jobs[id] = jb;
 	// route: fragments with both sides > 30 go through the 8-mer partition first (tools.cpp:146); everything else is one
 	// nw_alignment problem, registered right away
-	if (sp.rlen > 30 && sp.glen > 30) { const u32 slot = KB_ATOMIC_ADD(&bt.counters[23], 1u); bt.part_list[slot] = id; }
+	if (sp.rlen > 30 && sp.glen > 30) { const u32 slot = KB_ALLOC(&bt.counters[23], 1u); bt.part_list[slot] = id; }
 	else kb_emit_piece(ix, bt, id, sp.gpos, 0, sp.rlen, 0, sp.glen, ro, 1u);
 	out->info = KB_SEG_JOB; out->aux = id;
 }
@@ -723,7 +723,7 @@ KB_HD void kb_segments_cand(const KbIndexDev& ix, const KbParams& pm, const KbBa
 	for (int k = 0; k < ns; k++) in[k] = bt.segs[c.seg_start + k];
 	int n = kb_fill_pairs(rlen, -1, in, ns, sv, order);
 	if (!kb_same_chromosome(ix, sv, n)) return;
-	u32 off = KB_ATOMIC_ADD(&bt.counters[8], (u32)n);
+	u32 off = KB_ALLOC(&bt.counters[8], (u32)n);
 	if ((u64)off + (u64)n > (u64)bt.cap_segx) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SEGX); return; }
 	bt.cseg_off[ci] = off; bt.cseg_n[ci] = n;
 	for (int j = 0; j < n; j++) kb_classify_segment(ix, pm, bt, r, seq, rd, sv[j], j, n, &bt.segx[off + j]);
@@ -759,7 +759,7 @@ KB_HD bool kb_segments_cand_stream(const KbIndexDev& ix, const KbParams& pm, con
 		int ea = kb_chr_lookup(ix, a), eb = kb_chr_lookup(ix, b);
 		if (!(ea < ix.n_ends && eb < ix.n_ends && ix.end_chr[ea] == ix.end_chr[eb])) return true;
 	}
-	u32 off = KB_ATOMIC_ADD(&bt.counters[8], (u32)n);
+	u32 off = KB_ALLOC(&bt.counters[8], (u32)n);
 	if ((u64)off + (u64)n > (u64)bt.cap_segx) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SEGX); return true; }
 	bt.cseg_off[ci] = off; bt.cseg_n[ci] = n;
 	// one loop, one call site of kb_classify_segment: the lanes of a warp then classify their j-th segments together,
@@ -1074,7 +1074,7 @@ KB_HD void kb_locate_report(const KbIndexDev& ix, const KbBatchDev& bt, bool fir
 		int prev = -1;
 		for (int k = 0; k < cg.n; k++) { int op = (int)(cg.e[rev ? cg.n - 1 - k : k] & 15); if (op != prev) { merged++; prev = op; } }
 	}
-	u32 off = KB_ATOMIC_ADD(bt.cig_cursor, (u32)merged);
+	u32 off = KB_ALLOC(bt.cig_cursor, (u32)merged);
 	rp.cig_off = off; rp.cig_len = merged;
 	if ((u64)off + (u64)merged > (u64)bt.cap_cigar) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_CIGAR); rp.cig_len = 0; return; }
 	int w = -1, prev = -1;

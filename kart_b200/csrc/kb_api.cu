@@ -331,6 +331,7 @@ struct DevBuf
 struct kb_slot
 {
 	cudaStream_t stream = nullptr; cudaEvent_t ev[10]; cudaEvent_t done = nullptr;
+	cudaStream_t aux[KB_NW_CLASSES]; cudaEvent_t fork = nullptr, join[KB_NW_CLASSES];   // the nw_alignment size classes run side by side (launch_pipeline)
 	KbBatchDev bt; int n_reads = 0; size_t seq_bytes = 0; u64 seq_first = 0; int max_rlen = 0; int first_read = 0;
 	DevBuf<u8> seq, scratch, wscratch; DevBuf<u64> seq_off; DevBuf<unsigned long long> work; DevBuf<i32> est, n_hits, n_seeds, n_cands, cand_cap, rescue, slow1, slow2; DevBuf<u32> seed_off, cand_off, cigar, counters, cseg_off, runs; DevBuf<i32> cseg_n; DevBuf<KbSegX> segx; DevBuf<KbJob> jobs; DevBuf<u32> piece_list, part_list; DevBuf<KbPiece> pieces;
 	DevBuf<KbHit> hits; DevBuf<KbSeg> segs; DevBuf<KbCand> cands; DevBuf<KbReport> reports; DevBuf<KbReadRes> res; DevBuf<KbPairStat> pstat; DevBuf<kb_aln_t> aln; DevBuf<KbPk> pk;
@@ -358,6 +359,8 @@ struct kb_ctx
 	float stage_ms[9]; uint64_t work_host[8]; u32 counters_host[KB_NCOUNTERS];
 	cudaEvent_t chunk_start = nullptr; int trace = 0;
 	int seed_minb = 10;
+	int nw_streams = 1;          // 1: the size-class kernels of phase B are forked onto the slot's aux streams and joined before the gather
+	int align_warps = KB_ALIGN_WARPS;
 	int pipe_min_reads = 262144, pipe_sub_reads = 0;   // chunks of at least pipe_min_reads go through the two-slot pipeline
 };
 
@@ -410,6 +413,8 @@ int kb_init(int device, kb_ctx_t** out)
 		if (cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return KB_ECUDA; }
 		for (int i = 0; i < 10; i++) cudaEventCreate(&sl.ev[i]);
 		cudaEventCreate(&sl.done);
+		cudaEventCreateWithFlags(&sl.fork, cudaEventDisableTiming);
+		for (int i = 0; i < KB_NW_CLASSES; i++) { if (cudaStreamCreateWithFlags(&sl.aux[i], cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return KB_ECUDA; } cudaEventCreateWithFlags(&sl.join[i], cudaEventDisableTiming); }
 		if (cudaMallocHost((void**)&sl.counters_host, KB_NCOUNTERS * sizeof(u32)) != cudaSuccess || cudaMallocHost((void**)&sl.work_dev_host, 8 * sizeof(unsigned long long)) != cudaSuccess) { delete ctx; return KB_ECUDA; }
 		memset(sl.counters_host, 0, KB_NCOUNTERS * sizeof(u32)); memset(sl.work_dev_host, 0, 8 * sizeof(unsigned long long));
 	}
@@ -417,6 +422,8 @@ int kb_init(int device, kb_ctx_t** out)
 	const char* e = getenv("KB_PIPE_MIN_READS"); if (e && atoi(e) > 0) ctx->pipe_min_reads = atoi(e);
 	e = getenv("KB_SEED_MINB"); if (e && atoi(e) == 8) ctx->seed_minb = 8;
 	e = getenv("KB_PIPE_SUB_READS"); if (e && atoi(e) > 0) ctx->pipe_sub_reads = atoi(e);
+	e = getenv("KB_NW_STREAMS"); if (e) ctx->nw_streams = atoi(e) ? 1 : 0;
+	e = getenv("KB_ALIGN_WARPS"); if (e && atoi(e) >= 148 && atoi(e) <= 148 * 64) ctx->align_warps = atoi(e) / 4 * 4;
 	*out = ctx;
 	return KB_OK;
 }
@@ -435,6 +442,8 @@ void kb_destroy(kb_ctx_t* ctx)
 		sl.release();
 		for (int i = 0; i < 10; i++) cudaEventDestroy(sl.ev[i]);
 		cudaEventDestroy(sl.done);
+		cudaEventDestroy(sl.fork);
+		for (int i = 0; i < KB_NW_CLASSES; i++) { cudaEventDestroy(sl.join[i]); cudaStreamDestroy(sl.aux[i]); }
 		if (sl.counters_host) cudaFreeHost(sl.counters_host);
 		if (sl.work_dev_host) cudaFreeHost(sl.work_dev_host);
 		cudaStreamDestroy(sl.stream);
@@ -572,7 +581,7 @@ static int alloc_batch(kb_ctx* ctx, kb_slot& sl, int shared)
 	threads = (threads + KB_BLOCK - 1) / KB_BLOCK * KB_BLOCK; if (threads < KB_BLOCK) threads = KB_BLOCK;
 	sl.scratch_per_thread = per; sl.scratch_threads = (int)threads;
 	// the warp-per-job kernels get their own arenas (one worst-case problem each), independent of the number of reads
-	const int wwarps = KB_ALIGN_WARPS;
+	const int wwarps = ctx->align_warps;
 	CK(sl.hits.ensure(n * max_hits)); CK(sl.n_hits.ensure(n)); CK(sl.n_seeds.ensure(n)); CK(sl.seed_off.ensure(n));
 	CK(sl.segs.ensure(sl.cap_segs)); CK(sl.cands.ensure(sl.cap_cands)); CK(sl.reports.ensure(sl.cap_cands));
 	CK(sl.n_cands.ensure(n)); CK(sl.cand_off.ensure(n)); CK(sl.cand_cap.ensure(n)); CK(sl.rescue.ensure(n / 2 + 1));
@@ -635,7 +644,7 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 	unsigned g_items = pm.paired ? (unsigned)((n / 2 + KB_BLOCK - 1) / KB_BLOCK) : g_reads;
 	unsigned g_hits = (unsigned)(((long long)n * bt.max_hits + KB_BLOCK - 1) / KB_BLOCK);
 	unsigned g_scr = (unsigned)(bt.scratch_threads / KB_BLOCK);
-	unsigned g_warp = (unsigned)(KB_ALIGN_WARPS * 32 / KB_BLOCK);
+	unsigned g_warp = (unsigned)(bt.wscratch_warps * 32 / KB_BLOCK);
 	unsigned g_slow = g_reads < 148u * 16u ? g_reads : 148u * 16u;   // arena kernels: one thread per read up to a full machine, slices cut on the device
 	sl.launches = 0;
 	CK(cudaEventRecord(sl.ev[0], s));
@@ -654,13 +663,21 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 	KB_LAUNCH(k_segments_slow, g_slow, KB_BLOCK, s, ix, pm, bt); sl.launches++;
 	CK(cudaEventRecord(sl.ev[5], s));
 	KB_LAUNCH(k_align_part, g_warp, KB_BLOCK, s, ix, pm, bt); sl.launches++;
-	KB_LAUNCH((k_nw_tile<0, 8, 32, 1>), 148 * 8, KB_BLOCK, s, ix, pm, bt); sl.launches++;
-	KB_LAUNCH((k_nw_tile<1, 16, 32, 1>), 148 * 8, KB_BLOCK, s, ix, pm, bt); sl.launches++;
-	KB_LAUNCH((k_nw_tile<2, 24, 32, 1>), 148 * 8, KB_BLOCK, s, ix, pm, bt); sl.launches++;
-	KB_LAUNCH((k_nw_tile<3, 32, 32, 1>), 148 * 8, KB_BLOCK, s, ix, pm, bt); sl.launches++;
-	KB_LAUNCH((k_nw_tile<4, 32, 64, 2>), 148 * 4, KB_BLOCK, s, ix, pm, bt); sl.launches++;
-	KB_LAUNCH((k_nw_tile<5, 32, 128, 4>), 148 * 4, KB_BLOCK, s, ix, pm, bt); sl.launches++;
-	KB_LAUNCH(k_nw_warp, g_warp, KB_BLOCK, s, ix, pm, bt); sl.launches++;
+	// The size classes are independent and each is latency-bound on its own (one problem per thread: a launch lasts as long as
+	// its longest chain of cells), so they run side by side on the slot's aux streams, heaviest first, and join before the gather.
+	{
+		cudaStream_t q[KB_NW_CLASSES];
+		for (int i = 0; i < KB_NW_CLASSES; i++) q[i] = ctx->nw_streams ? sl.aux[i] : s;
+		if (ctx->nw_streams) { CK(cudaEventRecord(sl.fork, s)); for (int i = 0; i < KB_NW_CLASSES; i++) CK(cudaStreamWaitEvent(q[i], sl.fork, 0)); }
+		KB_LAUNCH((k_nw_tile<5, 32, 128, 4>), 148 * 4, KB_BLOCK, q[5], ix, pm, bt); sl.launches++;
+		KB_LAUNCH((k_nw_tile<4, 32, 64, 2>), 148 * 4, KB_BLOCK, q[4], ix, pm, bt); sl.launches++;
+		KB_LAUNCH(k_nw_warp, g_warp, KB_BLOCK, q[6], ix, pm, bt); sl.launches++;
+		KB_LAUNCH((k_nw_tile<3, 32, 32, 1>), 148 * 8, KB_BLOCK, q[3], ix, pm, bt); sl.launches++;
+		KB_LAUNCH((k_nw_tile<2, 24, 32, 1>), 148 * 8, KB_BLOCK, q[2], ix, pm, bt); sl.launches++;
+		KB_LAUNCH((k_nw_tile<1, 16, 32, 1>), 148 * 8, KB_BLOCK, q[1], ix, pm, bt); sl.launches++;
+		KB_LAUNCH((k_nw_tile<0, 8, 32, 1>), 148 * 8, KB_BLOCK, q[0], ix, pm, bt); sl.launches++;
+		if (ctx->nw_streams) for (int i = 0; i < KB_NW_CLASSES; i++) { CK(cudaEventRecord(sl.join[i], q[i])); CK(cudaStreamWaitEvent(s, sl.join[i], 0)); }
+	}
 	KB_LAUNCH(k_align_gather, 148 * 4, KB_BLOCK, s, bt); sl.launches++;
 	CK(cudaEventRecord(sl.ev[6], s));
 	KB_LAUNCH(k_assemble, g_reads, KB_BLOCK, s, ix, pm, bt); sl.launches++;

@@ -90,7 +90,7 @@ KB_HD int kb_cands_pacbio(const KbBatchDev& bt, const KbSeg* sv, int n, u8* take
 		if (score >= thr)
 		{
 			thr = score;
-			u32 off = KB_ATOMIC_ADD(&bt.counters[0], (u32)m);
+			u32 off = KB_ALLOC(&bt.counters[0], (u32)m);
 			if ((u64)off + (u64)m > (u64)bt.cap_segs) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SEEDS); return nc; }
 			for (int t = 0; t < m; t++) bt.segs[off + t] = tmp[t];
 			i64 d = sv[i].gpos - sv[i].rpos;

@@ -9,6 +9,12 @@
 #define KB_FM_CUH
 #include "kb_types.h"
 
+#if defined(__CUDACC__) && !defined(KB_EMUL)
+#include <cooperative_groups.h>
+#include <cooperative_groups/reduce.h>
+#include <cooperative_groups/scan.h>
+#endif
+
 #if defined(__CUDA_ARCH__)
 #define KB_POPCLL(x) __popcll(x)
 #define KB_LDG4(p) __ldg(p)
@@ -35,6 +41,52 @@ template <class T> static inline T kb_host_exch(T* p, T v) { T o = *p; *p = v; r
 #define KB_ATOMIC_MAX(p, v) kb_host_max((p), (v))
 #define KB_ATOMIC_CAS(p, c, v) kb_host_cas((p), (c), (v))
 #define KB_ATOMIC_EXCH(p, v) kb_host_exch((p), (v))
+#endif
+
+// ---- bump allocation from a grid-wide cursor ----------------------------------------------------------------------
+// Every per-batch arena (seeds, candidates, segments, jobs, pieces, cigar elements) is handed out by one 32-bit cursor in
+// HBM. One atomicAdd per item makes that cursor the bottleneck of whole kernels: same-address atomics retire at roughly one
+// per nanosecond at the L2, which for 2 M reads is milliseconds (ncu, profiles/r11: half of k_segments' stall samples sat
+// on three such atomics). So the lanes of a warp that arrive at an allocation together (whatever subset that is) combine
+// their requests: exclusive scan inside the coalesced group, ONE atomicAdd by its first lane, base broadcast back.
+// Which slots a lane gets depends on scheduling, exactly as with plain atomics; nothing downstream depends on slot order.
+#if defined(__CUDA_ARCH__)
+template <class T> __device__ __forceinline__ T kb_alloc_slots(T* cursor, T n)
+{
+	namespace cg = cooperative_groups;
+	cg::coalesced_group g = cg::coalesced_threads();
+	if (g.size() == 1) return atomicAdd(cursor, n);
+	const T pre = cg::exclusive_scan(g, n);
+	T base = 0;
+	if (g.thread_rank() == g.size() - 1) base = atomicAdd(cursor, (T)(pre + n));
+	return g.shfl(base, g.size() - 1) + pre;
+}
+// the same when lanes may name different cursors (one group per distinct cursor)
+__device__ __forceinline__ u32 kb_alloc_slots_keyed(u32* cursor, u32 n)
+{
+	namespace cg = cooperative_groups;
+	cg::coalesced_group a = cg::coalesced_threads();
+	if (a.size() == 1) return atomicAdd(cursor, n);
+	cg::coalesced_group g = cg::labeled_partition(a, (unsigned long long)cursor);
+	const u32 pre = cg::exclusive_scan(g, n);
+	u32 base = 0;
+	if (g.thread_rank() == g.size() - 1) base = atomicAdd(cursor, pre + n);
+	return g.shfl(base, g.size() - 1) + pre;
+}
+__device__ __forceinline__ void kb_max_u32(u32* dst, u32 v)
+{
+	namespace cg = cooperative_groups;
+	cg::coalesced_group g = cg::coalesced_threads();
+	const u32 m = cg::reduce(g, v, cg::greater<u32>());
+	if (g.thread_rank() == 0 && m) atomicMax(dst, m);
+}
+#define KB_ALLOC(p, n) kb_alloc_slots((p), (n))
+#define KB_ALLOC_KEYED(p, n) kb_alloc_slots_keyed((p), (n))
+#define KB_MAX_U32(p, v) kb_max_u32((p), (v))
+#else
+#define KB_ALLOC(p, n) KB_ATOMIC_ADD((p), (n))
+#define KB_ALLOC_KEYED(p, n) KB_ATOMIC_ADD((p), (n))
+#define KB_MAX_U32(p, v) KB_ATOMIC_MAX((p), (v))
 #endif
 
 // nst_nt4_table (src/BWT_Index/bntseq.c:40): A/a 0, C/c 1, G/g 2, T/t 3, everything else 4
@@ -321,10 +373,10 @@ KB_HD void kb_seed_read(const KbIndexDev& ix, const KbParams& pm, const KbBatchD
 	*w_steps += steps; *w_blocks += blocks;
 	if (ovf) KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_HITS);
 	bt.n_hits[r] = nh; bt.n_seeds[r] = ns;
-	u32 off = KB_ATOMIC_ADD(&bt.counters[0], (u32)ns);
+	u32 off = KB_ALLOC(&bt.counters[0], (u32)ns);
 	bt.seed_off[r] = off;
 	if ((u64)off + (u64)ns > (u64)bt.cap_segs) KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SEEDS);
-	KB_ATOMIC_MAX(&bt.counters[5], (u32)ns);
+	KB_MAX_U32(&bt.counters[5], (u32)ns);
 }
 
 // One (read, hit): resolve the SA interval to text positions, in SA-row order (bwt_search.cpp:176-179).

@@ -14,7 +14,7 @@ KB_HD void kb_stage_cand_pair(const KbIndexDev& ix, const KbParams& pm, const Kb
 		int ra = 2 * t, rb = ra + 1;
 		int s1 = bt.n_seeds[ra], s2 = bt.n_seeds[rb];
 		int cap = s1 + s2 + 1;
-		u32 off = KB_ATOMIC_ADD(&bt.counters[1], (u32)(2 * cap));
+		u32 off = KB_ALLOC(&bt.counters[1], (u32)(2 * cap));
 		bt.cand_off[ra] = off; bt.cand_off[rb] = off + cap; bt.cand_cap[ra] = cap; bt.cand_cap[rb] = cap;
 		bt.n_cands[ra] = 0; bt.n_cands[rb] = 0;
 		KbPairStat st; st.counted = 0; st.absdist = 0; st.est_lo = -2147483647 - 1; st.est_hi = 2147483647; bt.pstat[t] = st;
@@ -32,13 +32,13 @@ KB_HD void kb_stage_cand_pair(const KbIndexDev& ix, const KbParams& pm, const Kb
 		bt.pstat[t].est_lo = lo; bt.pstat[t].est_hi = hi;
 		if (paired) { kb_keep_mated(a, n1, b, n2); kb_prune(pm, a, n1); kb_prune(pm, b, n2); }
 		else if (kb_top_score(a, n1) == 0 && kb_top_score(b, n2) == 0) { kb_prune(pm, a, n1); kb_prune(pm, b, n2); }   // AlignmentRescue.cpp:89
-		else { u32 slot = KB_ATOMIC_ADD(&bt.counters[4], 1u); bt.rescue_list[slot] = t; }
+		else { u32 slot = KB_ALLOC(&bt.counters[4], 1u); bt.rescue_list[slot] = t; }
 	}
 	else
 	{
 		if (t >= bt.n_reads) return;
 		int s1 = bt.n_seeds[t], cap = s1 + 1;
-		u32 off = KB_ATOMIC_ADD(&bt.counters[1], (u32)cap);
+		u32 off = KB_ALLOC(&bt.counters[1], (u32)cap);
 		bt.cand_off[t] = off; bt.cand_cap[t] = cap; bt.n_cands[t] = 0;
 		if ((u64)off + (u64)cap > (u64)bt.cap_cands) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_CANDS); bt.cand_off[t] = 0; return; }
 		if (bt.counters[3] & (KB_OVF_SEEDS | KB_OVF_HITS)) return;
@@ -92,7 +92,7 @@ KB_HD void kb_stage_segments(const KbIndexDev& ix, const KbParams& pm, const KbB
 {
 	if (r >= bt.n_reads) return;
 	if (bt.counters[3]) return;
-	if (!kb_segments_read(ix, pm, bt, r, nullptr)) { u32 slot = KB_ATOMIC_ADD(&bt.counters[12], 1u); bt.slow_list[slot] = r; }
+	if (!kb_segments_read(ix, pm, bt, r, nullptr)) { u32 slot = KB_ALLOC(&bt.counters[12], 1u); bt.slow_list[slot] = r; }
 }
 KB_HD void kb_stage_segments_slow(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int tid, int nth)
 {
@@ -113,7 +113,7 @@ KB_HD void kb_stage_assemble(const KbIndexDev& ix, const KbParams& pm, const KbB
 {
 	if (r >= bt.n_reads) return;
 	if (bt.counters[3]) return;
-	if (!kb_assemble_read(ix, pm, bt, r, nullptr)) { u32 slot = KB_ATOMIC_ADD(&bt.counters[13], 1u); bt.slow_list2[slot] = r; }
+	if (!kb_assemble_read(ix, pm, bt, r, nullptr)) { u32 slot = KB_ALLOC(&bt.counters[13], 1u); bt.slow_list2[slot] = r; }
 }
 KB_HD void kb_stage_assemble_slow(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int tid, int nth)
 {
