@@ -36,7 +36,8 @@ def ncu_traffic(kernel, reads, syn):
         return None, None
     f = max(files, key=lambda p: int(re.findall(r"r(\d+)", os.path.basename(p))[0]))
     d = json.load(open(f))
-    k = d["kernels"].get(kernel)
+    norm = {re.sub(r"^void |<.*$", "", name): v for name, v in d["kernels"].items()}   # "void k_fm_seed<10>" -> "k_fm_seed"
+    k = norm.get(kernel)
     if not k:
         return None, None
     cap_reads = k["grid"] * k.get("block", 128)

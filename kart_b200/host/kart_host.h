@@ -5,6 +5,8 @@
 #define KART_HOST_H
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
+#include <functional>
 #include <string>
 #include <vector>
 #include <zlib.h>
@@ -20,30 +22,74 @@ struct HostIndex
 };
 bool check_index_files(const std::string& prefix);                // CheckBWAIndexFiles, GetData.cpp:222
 
+// Grow-only host array without value-initialisation. `pinned` arrays come from kb_host_alloc (page-locked, so the copies of
+// kb_map_chunk are asynchronous DMA at full PCIe rate) and fall back to malloc when that fails.
+void* host_buf_alloc(size_t bytes, bool want_pinned, bool* got_pinned);
+void  host_buf_free(void* p, bool pinned);
+template <class T> struct HBuf
+{
+	T* p = nullptr; size_t n = 0, cap = 0; bool want_pinned = false, is_pinned = false;
+	explicit HBuf(bool pin = false) : want_pinned(pin) {}
+	HBuf(const HBuf&) = delete; HBuf& operator=(const HBuf&) = delete;
+	~HBuf() { if (p) host_buf_free(p, is_pinned); }
+	void reserve(size_t c)
+	{
+		if (c <= cap) return;
+		size_t nc = cap + cap / 2; if (nc < c) nc = c; if (nc < 64) nc = 64;
+		bool pin = false; T* q = (T*)host_buf_alloc(nc * sizeof(T), want_pinned, &pin);
+		if (n) memcpy(q, p, n * sizeof(T));
+		if (p) host_buf_free(p, is_pinned);
+		p = q; cap = nc; is_pinned = pin;
+	}
+	void resize(size_t k) { reserve(k); n = k; }                       // new elements are uninitialised
+	void clear() { n = 0; }
+	void push_back(const T& v) { if (n == cap) reserve(n + 1); p[n++] = v; }
+	void append(const T* a, size_t k) { reserve(n + k); memcpy(p + n, a, k * sizeof(T)); n += k; }
+	void assign(size_t k, const T& v) { resize(k); for (size_t i = 0; i < k; i++) p[i] = v; }
+	T* data() { return p; } const T* data() const { return p; }
+	size_t size() const { return n; } bool empty() const { return n == 0; }
+	T& operator[](size_t i) { return p[i]; } const T& operator[](size_t i) const { return p[i]; }
+	T& back() { return p[n - 1]; }
+};
+
 // One batch of reads in structure-of-arrays form (what the C ABI takes) plus what SAM output needs.
 struct ReadBatch
 {
-	std::vector<uint8_t> seq;  std::vector<uint64_t> seq_off;     // mate 2 stored reverse-complemented (GetData.cpp:125-135)
-	std::vector<char> qual;                                       // same offsets as seq (mate 2 reversed), empty for FASTA
-	std::vector<char> names;   std::vector<uint32_t> name_off;
+	HBuf<uint8_t> seq{true};  HBuf<uint64_t> seq_off{true};           // mate 2 stored reverse-complemented (GetData.cpp:125-135)
+	HBuf<char> qual;                                                   // same offsets as seq (mate 2 reversed), empty for FASTA
+	HBuf<char> names;   HBuf<uint32_t> name_off;
+	bool fastq = true, pair_end = false;                               // format / pairing of the library this batch was read from
 	int n() const { return (int)seq_off.size() - 1; }
 	void clear() { seq.clear(); seq_off.assign(1, 0); qual.clear(); names.clear(); name_off.assign(1, 0); }
 };
 
+// FASTA / FASTQ (plain or .gz) input with the reference's parsing rules. FASTQ goes through a block reader: every stream
+// buffers a large piece of (decompressed) text, newline positions are indexed by `threads` workers, and the records are
+// parsed and copied into the batch by the same workers (read_input.cpp). FASTA keeps the entry-at-a-time path.
 class ReadSource   // GetNextChunk / gzGetNextChunk semantics on top of zlib (which reads plain files transparently)
 {
 public:
 	bool open(const char* f1, const char* f2);
 	void close();
-	bool fastq = true;
+	bool fastq = true; int threads = 1;
 	// appends up to max_reads reads (always whole pairs of entries, like the reference) ; returns reads appended
 	int fill(ReadBatch& b, int max_reads, bool pair_end);
+	int fill_serial(ReadBatch& b, int max_reads, bool pair_end);       // entry-at-a-time path (FASTA; and the cross-check of the block path in tests)
+	struct Stream
+	{
+		gzFile fp = nullptr; std::vector<char> buf; size_t pos = 0, end = 0; bool eof = false; std::string pending; bool has_pending = false;
+		// block path: text[lo, hi) is buffered, nl[] holds the offsets of the newlines in it, rec = lines already consumed
+		HBuf<char> text; size_t lo = 0, hi = 0; HBuf<uint32_t> nl; size_t nl_used = 0; bool drained = false;
+	};
 private:
-	struct Stream { gzFile fp = nullptr; std::vector<char> buf; size_t pos = 0, end = 0; bool eof = false; std::string pending; bool has_pending = false; };
 	Stream s1, s2; bool two = false;
 	bool line(Stream& s, std::string& out);
 	bool entry(Stream& s, std::string& name, std::string& seq, std::string& qual);
+	size_t buffer_records(Stream& s, size_t want);                     // ensures `want` complete 4-line records (or everything up to EOF) are indexed; returns the count
+	int fill_blocks(ReadBatch& b, int max_reads, bool pair_end);
 };
+
+void parallel_for(int threads, size_t n, const std::function<void(int, size_t, size_t)>& body);   // body(worker, lo, hi) over [0,n) in `threads` contiguous slices
 
 struct RunOptions
 {
