@@ -109,6 +109,12 @@ int  kb_stage_reads(kb_ctx_t* ctx, const kb_reads_t* in, const int32_t* est);   
 int  kb_run(kb_ctx_t* ctx);                                                      /* kernels only, returns after they finish */
 int  kb_fetch_results(kb_ctx_t* ctx, kb_results_t* out);                         /* D2H */
 
+/* Page-locked host memory for the caller-owned buffers (reads in, results out): with it the copies of kb_map_chunk are
+ * asynchronous DMA and overlap the kernels; pageable buffers work but are staged by the driver. NULL when no device /
+ * no memory. Usable from any thread, before or after kb_init. */
+void* kb_host_alloc(uint64_t bytes);
+void  kb_host_free(void* p);
+
 /* Instrumentation. kb_stage_ms: device time (CUDA events on the context's stream) of each kernel of the last kb_run:
  * [0] fm_seed [1] sa_locate [2] cand_pair [3] rescue [4] segments [5] align [6] assemble [7] finalize [8] whole run.
  * Returns entries written.

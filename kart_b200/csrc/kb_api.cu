@@ -552,6 +552,25 @@ int kb_set_params(kb_ctx_t* ctx, const kb_params_t* p)
 }
 
 int kb_get_min_seed_len(kb_ctx_t* ctx) { return ctx ? ctx->pm.min_seed : KB_EINVAL; }
+void* kb_host_alloc(uint64_t bytes)
+{
+	void* p = nullptr;
+#ifndef KB_EMUL
+	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+#else
+	p = malloc(bytes ? bytes : 1);
+#endif
+	return p;
+}
+void kb_host_free(void* p)
+{
+	if (!p) return;
+#ifndef KB_EMUL
+	cudaFreeHost(p);
+#else
+	free(p);
+#endif
+}
 void* kb_cuda_stream(kb_ctx_t* ctx) { return ctx ? (void*)ctx->slot[0].stream : nullptr; }
 
 // device arrays of one slot for its n_reads / max_rlen; shared != 0: cigar elements go to the chunk-wide arena

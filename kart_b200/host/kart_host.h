@@ -96,14 +96,14 @@ struct RunOptions
 	std::string index_prefix, out_name = "output.sam";
 	std::vector<std::string> files1, files2;
 	int threads = 4, max_gaps = 5, out_format = 0, n_gpus = 1; bool pair_flag = false, pacbio = false, multihit = false, silent = false, debug = false;
-	int batch_reads = 1 << 20; bool expand_sa = false;
+	int batch_reads = 1 << 18; bool expand_sa = false;
 };
 
 int run_mapping(const RunOptions& opt, const HostIndex& idx);     // Mapping(), src/Mapping.cpp:639
 
 // SAM text (src/Mapping.cpp:177-315)
 void sam_header(std::string& out, const HostIndex& idx);
-void sam_read_line(std::string& out, const HostIndex& idx, const ReadBatch& b, int r, bool stored_fwd, const kb_aln_t& a, const uint32_t* cigar, bool fastq);
+void sam_read_line(HBuf<char>& out, const HostIndex& idx, const ReadBatch& b, int r, bool stored_fwd, const kb_aln_t& a, const uint32_t* cigar, bool fastq);
 
 
 // BAM output (src/Mapping.cpp:610-621 via htslib sam_parse1 + sam_write1), see bam_writer.cpp

@@ -12,23 +12,30 @@
 #include <mutex>
 #include <string.h>
 #include <thread>
+#include <deque>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <time.h>
 
-struct BatchResult { std::vector<kb_aln_t> aln; std::vector<kb_pair_stat_t> pairs; std::vector<uint32_t> cigar; std::vector<int32_t> est_used; };
+struct BatchResult
+{
+	HBuf<kb_aln_t> aln{true}; HBuf<kb_pair_stat_t> pairs{true}; HBuf<uint32_t> cigar{true}; std::vector<int32_t> est_used;
+};
 
 static int map_batch(kb_ctx_t* ctx, const uint8_t* seq, const uint64_t* off, int n, const int32_t* est, BatchResult& out)
 {
 	kb_reads_t in; in.n_reads = n; in.seq = seq; in.seq_off = off;
 	out.aln.resize(n); out.pairs.resize(n / 2 + 1);
-	if (out.cigar.size() < (size_t)n * 4 + 1024) out.cigar.resize((size_t)n * 4 + 1024);
-	kb_results_t res; res.aln = out.aln.data(); res.pairs = out.pairs.data(); res.cigar = out.cigar.data(); res.cap_cigar = (uint32_t)out.cigar.size(); res.n_cigar = 0;
+	if (out.cigar.cap < (size_t)n * 4 + 1024) { out.cigar.clear(); out.cigar.reserve((size_t)n * 4 + 1024); }
+	kb_results_t res; res.aln = out.aln.data(); res.pairs = out.pairs.data(); res.cigar = out.cigar.data(); res.cap_cigar = (uint32_t)out.cigar.cap; res.n_cigar = 0;
 	int rc = kb_map_chunk(ctx, &in, est, &res);
 	if (rc == KB_ECAPACITY)
 	{
-		out.cigar.resize((size_t)res.n_cigar + 1024); res.cigar = out.cigar.data(); res.cap_cigar = (uint32_t)out.cigar.size();
+		out.cigar.clear(); out.cigar.reserve((size_t)res.n_cigar + 1024); res.cigar = out.cigar.data(); res.cap_cigar = (uint32_t)out.cigar.cap;
 		rc = kb_fetch_results(ctx, &res);
 	}
-	if (rc == KB_OK) out.cigar.resize(res.n_cigar);
+	if (rc == KB_OK) out.cigar.n = res.n_cigar;
 	return rc;
 }
 
@@ -37,9 +44,8 @@ static inline int est_of(const PairState& s) { if (s.iPaired >= 1000) { int e = 
 
 // Replays the chunk recurrence over one mapped batch; re-maps the pairs whose result depends on the difference between the
 // predicted and the true EstDistance. Returns 0 or a kb error code.
-static int settle_est(kb_ctx_t* ctx, const ReadBatch& b, BatchResult& br, PairState& st, int chunk_reads, long long* remapped)
+static int settle_est(kb_ctx_t* ctx, const ReadBatch& b, BatchResult& br, PairState& st, int chunk_reads, int n, long long* remapped)
 {
-	int n = b.n(), np = n / 2;
 	while (true)
 	{
 		PairState s = st; std::vector<int> viol; std::vector<int32_t> viol_est;
@@ -57,7 +63,7 @@ static int settle_est(kb_ctx_t* ctx, const ReadBatch& b, BatchResult& br, PairSt
 		*remapped += (long long)viol.size();
 		// gather the affected pairs into a small batch and map them again with their true EstDistance
 		std::vector<uint8_t> seq; std::vector<uint64_t> off(1, 0);
-		for (int p : viol) for (int r = 2 * p; r < 2 * p + 2; r++) { seq.insert(seq.end(), b.seq.begin() + b.seq_off[r], b.seq.begin() + b.seq_off[r + 1]); off.push_back(seq.size()); }
+		for (int p : viol) for (int r = 2 * p; r < 2 * p + 2; r++) { seq.insert(seq.end(), b.seq.data() + b.seq_off[r], b.seq.data() + b.seq_off[r + 1]); off.push_back(seq.size()); }
 		BatchResult fix;
 		int rc = map_batch(ctx, seq.data(), off.data(), (int)off.size() - 1, viol_est.data(), fix); if (rc) return rc;
 		for (size_t k = 0; k < viol.size(); k++)
@@ -67,31 +73,108 @@ static int settle_est(kb_ctx_t* ctx, const ReadBatch& b, BatchResult& br, PairSt
 			{
 				kb_aln_t a = fix.aln[2 * k + h];
 				uint32_t at = (uint32_t)br.cigar.size();
-				br.cigar.insert(br.cigar.end(), fix.cigar.begin() + a.cig_off, fix.cigar.begin() + a.cig_off + a.cig_len);
+				br.cigar.append(fix.cigar.data() + a.cig_off, (size_t)a.cig_len);
 				a.cig_off = at; br.aln[2 * p + h] = a;
 			}
 			br.pairs[p] = fix.pairs[k]; br.est_used[p] = viol_est[k];
 		}
-		(void)np;
 	}
 }
 
+// One batch travelling through the three stages (reader thread -> GPU on the main thread -> writer thread).
+struct Job
+{
+	ReadBatch rb; BatchResult br, tail; int n_pe = 0; bool last_of_run = false;
+};
+template <class T> class Channel   // small blocking queue
+{
+public:
+	void put(T v) { { std::lock_guard<std::mutex> g(m); q.push_back(v); } cv.notify_one(); }
+	T take() { std::unique_lock<std::mutex> g(m); cv.wait(g, [&]() { return !q.empty(); }); T v = q.front(); q.pop_front(); return v; }
+private:
+	std::mutex m; std::condition_variable cv; std::deque<T> q;
+};
+
+// Output file: header and batches in input order; a batch's slices are written with parallel pwrite when the file is seekable.
+struct SamSink
+{
+	int fd = -1; bool seekable = false; off_t at = 0;
+	bool open(const char* path)
+	{
+		fd = ::open(path, O_CREAT | O_TRUNC | O_WRONLY, 0666); if (fd < 0) return false;
+		struct stat st; seekable = fstat(fd, &st) == 0 && S_ISREG(st.st_mode);
+		return true;
+	}
+	static void write_all(int fd, const char* p, size_t n) { while (n) { ssize_t w = ::write(fd, p, n); if (w <= 0) { fprintf(stderr, "Error! write failed\n"); exit(1); } p += w; n -= (size_t)w; } }
+	static void pwrite_all(int fd, const char* p, size_t n, off_t o) { while (n) { ssize_t w = ::pwrite(fd, p, n > (64u << 20) ? (64u << 20) : n, o); if (w <= 0) { fprintf(stderr, "Error! write failed\n"); exit(1); } p += w; n -= (size_t)w; o += w; } }
+	void write(const char* p, size_t n) { write_all(fd, p, n); at += (off_t)n; if (seekable) lseek(fd, at, SEEK_SET); }
+	void write_parts(std::vector<HBuf<char>>& parts)
+	{
+		if (!seekable) { for (auto& p : parts) write_all(fd, p.data(), p.size()); return; }
+		std::vector<off_t> o(parts.size() + 1, at); for (size_t i = 0; i < parts.size(); i++) o[i + 1] = o[i] + (off_t)parts[i].size();
+		std::vector<std::thread> th;
+		for (size_t i = 1; i < parts.size(); i++) th.emplace_back([&, i]() { pwrite_all(fd, parts[i].data(), parts[i].size(), o[i]); });
+		if (!parts.empty()) pwrite_all(fd, parts[0].data(), parts[0].size(), o[0]);
+		for (auto& t : th) t.join();
+		at = o[parts.size()]; lseek(fd, at, SEEK_SET);
+	}
+	void close() { if (fd >= 0) ::close(fd); fd = -1; }
+};
+
 int run_mapping(const RunOptions& opt, const HostIndex& idx)
 {
+	const int chunk_reads = opt.pacbio ? 10 : 4000;
+	const int io_threads = std::max(1, opt.threads);
+	const int batch_reads = std::max(chunk_reads, opt.batch_reads / chunk_reads * chunk_reads);
+
+	// stage 1 starts before the device is ready: the first batch is parsed while the index is uploaded
+	const int n_jobs = 3;
+	std::vector<Job> jobs(n_jobs);
+	Channel<Job*> free_q, ready_q, done_q;
+	for (auto& j : jobs) free_q.put(&j);
+	bool pair_end_final = opt.pair_flag;
+	std::thread reader([&]() {
+		bool pair_end = opt.pair_flag;
+		for (size_t lib = 0; lib < opt.files1.size(); lib++)
+		{
+			ReadSource src; src.threads = io_threads; bool sep = opt.files1.size() == opt.files2.size();
+			if (sep) pair_end = true;
+			if (sep)
+			{
+				// both files must have the same format (Mapping.cpp:700-709)
+				ReadSource a, b2; bool ok1 = a.open(opt.files1[lib].c_str(), nullptr), ok2 = b2.open(opt.files2[lib].c_str(), nullptr);
+				bool same = ok1 && ok2 && a.fastq == b2.fastq; if (ok1) a.close(); if (ok2) b2.close();
+				if (ok1 && ok2 && !same) { fprintf(stdout, "Error! %s and %s are with different format...\n", opt.files1[lib].c_str(), opt.files2[lib].c_str()); continue; }
+				if (!ok1 || !ok2) continue;
+			}
+			if (!src.open(opt.files1[lib].c_str(), sep ? opt.files2[lib].c_str() : nullptr)) continue;
+			while (true)
+			{
+				Job* j = free_q.take(); j->rb.clear();
+				if (src.fill(j->rb, batch_reads, pair_end) <= 0) { free_q.put(j); break; }
+				ready_q.put(j);
+			}
+			src.close();
+		}
+		pair_end_final = pair_end;
+		ready_q.put(nullptr);
+	});
+	auto drain_reader = [&]() { while (Job* j = ready_q.take()) free_q.put(j); reader.join(); };
+
 	kb_ctx_t* ctx = nullptr;
 	int rc = kb_init(0, &ctx);
-	if (rc) { fprintf(stderr, "Error! kart_b200 needs a CUDA device: %s\n", kb_strerror(rc)); return 1; }
+	if (rc) { fprintf(stderr, "Error! kart_b200 needs a CUDA device: %s\n", kb_strerror(rc)); drain_reader(); return 1; }
 	kb_index_host_t hi; idx.describe(&hi);
-	if ((rc = kb_upload_index(ctx, &hi, opt.expand_sa ? 1 : 0)) != 0) { fprintf(stderr, "Error! index upload failed: %s (%s)\n", kb_strerror(rc), kb_last_error(ctx)); kb_destroy(ctx); return 1; }
+	if ((rc = kb_upload_index(ctx, &hi, opt.expand_sa ? 1 : 0)) != 0) { fprintf(stderr, "Error! index upload failed: %s (%s)\n", kb_strerror(rc), kb_last_error(ctx)); drain_reader(); kb_destroy(ctx); return 1; }
 
-	FILE* out = nullptr; BamWriter bam; const bool to_bam = opt.out_format == 1 && !opt.debug;
+	SamSink out; BamWriter bam; const bool to_bam = opt.out_format == 1 && !opt.debug;
 	std::vector<int32_t> name2id(idx.chr_name.size(), -1);   // bam_name2id: a repeated @SQ name keeps its first id (htslib sam.c:725-733)
 	if (!opt.debug)
 	{
 		std::string h; sam_header(h, idx);
 		if (to_bam)
 		{
-			if (!bam.open(opt.out_name.c_str(), opt.threads)) { fprintf(stderr, "Error! Cannot open file [%s]\n", opt.out_name.c_str()); kb_destroy(ctx); exit(1); }
+			if (!bam.open(opt.out_name.c_str(), opt.threads)) { fprintf(stderr, "Error! Cannot open file [%s]\n", opt.out_name.c_str()); drain_reader(); kb_destroy(ctx); exit(1); }
 			std::vector<std::string> un; std::vector<int64_t> ul;
 			for (size_t i = 0; i < idx.chr_name.size(); i++)
 			{
@@ -103,90 +186,81 @@ int run_mapping(const RunOptions& opt, const HostIndex& idx)
 		}
 		else
 		{
-			out = fopen(opt.out_name.c_str(), "w");
-			if (!out) { fprintf(stderr, "Error! Cannot open file [%s]\n", opt.out_name.c_str()); kb_destroy(ctx); exit(1); }
-			fwrite(h.data(), 1, h.size(), out);
+			if (!out.open(opt.out_name.c_str())) { fprintf(stderr, "Error! Cannot open file [%s]\n", opt.out_name.c_str()); drain_reader(); kb_destroy(ctx); exit(1); }
+			out.write(h.data(), h.size());
 		}
 	}
 	if (opt.silent) fprintf(stdout, "Start read mapping...\n");
 	time_t t0 = time(NULL);
-	long long total = 0, unmapped = 0, unique = 0, remapped = 0; PairState st; bool pair_end = opt.pair_flag;
-	const int chunk_reads = opt.pacbio ? 10 : 4000;
-	int fmt_threads = std::max(1, opt.threads);
+	long long total = 0, unmapped = 0, unique = 0, remapped = 0; PairState st;
 
-	for (size_t lib = 0; lib < opt.files1.size(); lib++)
-	{
-		ReadSource src; bool sep = opt.files1.size() == opt.files2.size();
-		if (sep) pair_end = true;
-		if (sep)
+	// stage 3: SAM/BAM text of batch k is formatted in slices and written while batch k+1 is on the GPU
+	std::thread writer([&]() {
+		std::vector<HBuf<char>> parts(io_threads); std::vector<std::string> bparts(io_threads); std::vector<std::vector<uint32_t>> rec_ends(io_threads);
+		while (Job* j = done_q.take())
 		{
-			// both files must have the same format (Mapping.cpp:700-709)
-			ReadSource a, b2; bool ok1 = a.open(opt.files1[lib].c_str(), nullptr), ok2 = b2.open(opt.files2[lib].c_str(), nullptr);
-			bool same = ok1 && ok2 && a.fastq == b2.fastq; a.close(); b2.close();
-			if (ok1 && ok2 && !same) { fprintf(stdout, "Error! %s and %s are with different format...\n", opt.files1[lib].c_str(), opt.files2[lib].c_str()); continue; }
-			if (!ok1 || !ok2) continue;
-		}
-		if (!src.open(opt.files1[lib].c_str(), sep ? opt.files2[lib].c_str() : nullptr)) continue;
-		bool fastq = src.fastq;
-		kb_params_t pm; pm.min_seed_len = 0; pm.max_gaps = opt.max_gaps; pm.max_insert = 1500; pm.pacbio = opt.pacbio; pm.multihit = opt.multihit;
-
-		// pipeline: reader thread fills batch k+1 while the GPU maps batch k
-		ReadBatch cur, nxt; cur.clear(); nxt.clear();
-		int batch_reads = std::max(chunk_reads, opt.batch_reads / chunk_reads * chunk_reads);
-		int got = src.fill(cur, batch_reads, pair_end);
-		while (got > 0)
-		{
-			std::thread reader([&]() { nxt.clear(); src.fill(nxt, batch_reads, pair_end); });
-			if (!opt.silent) { fprintf(stdout, "\r%lld %s reads have been processed in %ld seconds...", total, pair_end ? "paired-end" : "singled-end", (long)(time(NULL) - t0)); fflush(stdout); }
-			int n = cur.n();
-			// a batch with an odd number of reads can only be the last one: its final read goes through the single-end branch (Mapping.cpp:531,598)
-			// (the reference sends a whole chunk through the single-end branch when its read count is odd: the final short chunk)
-			int n_pe = (!opt.pacbio && pair_end) ? ((n & 1) ? (n / chunk_reads) * chunk_reads : n) : 0;
-			BatchResult br, tail;
-			if (n_pe > 0)
-			{
-				pm.paired = 1; kb_set_params(ctx, &pm);
-				br.est_used.assign(n_pe / 2, est_of(st));
-				rc = map_batch(ctx, cur.seq.data(), cur.seq_off.data(), n_pe, br.est_used.data(), br);
-				if (!rc) rc = settle_est(ctx, cur, br, st, chunk_reads, &remapped);
-			}
-			if (!rc && n > n_pe)
-			{
-				pm.paired = 0; kb_set_params(ctx, &pm);
-				std::vector<uint64_t> off(cur.seq_off.begin() + n_pe, cur.seq_off.end());
-				uint64_t base = off[0]; for (auto& o : off) o -= base;
-				rc = map_batch(ctx, cur.seq.data() + base, off.data(), n - n_pe, nullptr, tail);
-			}
-			if (rc) { fprintf(stderr, "\nError! GPU mapping failed: %s (%s)\n", kb_strerror(rc), kb_last_error(ctx)); reader.join(); break; }
-			// format SAM in parallel slices, write in input order
-			std::vector<std::string> parts(fmt_threads); std::vector<std::thread> th; std::vector<std::vector<uint32_t>> rec_ends(fmt_threads);
-			std::vector<long long> um(fmt_threads, 0), uq(fmt_threads, 0);
-			for (int t = 0; t < fmt_threads; t++) th.emplace_back([&, t]() {
-				int lo = (int)((long long)n * t / fmt_threads), hi = (int)((long long)n * (t + 1) / fmt_threads);
-				if (n_pe) { lo &= ~1; if (t + 1 < fmt_threads) hi &= ~1; }
-				std::string& o = parts[t]; o.reserve((size_t)(hi - lo) * 400);
-				for (int r = lo; r < hi; r++)
+			const ReadBatch& cur = j->rb; const int n = cur.n(), n_pe = j->n_pe; const bool fastq = cur.fastq;
+			std::vector<long long> um(io_threads, 0), uq(io_threads, 0);
+			parallel_for(io_threads, (size_t)io_threads, [&](int, size_t t0_, size_t t1_) {
+				for (size_t t = t0_; t < t1_; t++)
 				{
-					bool in_pe = r < n_pe;
-					const kb_aln_t& a = in_pe ? br.aln[r] : tail.aln[r - n_pe];
-					const uint32_t* cg = in_pe ? br.cigar.data() : tail.cigar.data();
-					if (a.score == 0) um[t]++; else if (a.mapq == 60) uq[t]++;
-					if (to_bam) bam_read_record(o, rec_ends[t], name2id, cur, r, !(in_pe && (r & 1)), a, cg, fastq);
-					else sam_read_line(o, idx, cur, r, !(in_pe && (r & 1)), a, cg, fastq);   // mate 2 of a mapped pair is held reverse-complemented
+					int lo = (int)((long long)n * (long long)t / io_threads), hi = (int)((long long)n * (long long)(t + 1) / io_threads);
+					if (n_pe) { lo &= ~1; if ((int)t + 1 < io_threads) hi &= ~1; }
+					parts[t].clear(); bparts[t].clear(); rec_ends[t].clear();
+					for (int r = lo; r < hi; r++)
+					{
+						bool in_pe = r < n_pe;
+						const kb_aln_t& a = in_pe ? j->br.aln[r] : j->tail.aln[r - n_pe];
+						const uint32_t* cg = in_pe ? j->br.cigar.data() : j->tail.cigar.data();
+						if (a.score == 0) um[t]++; else if (a.mapq == 60) uq[t]++;
+						if (to_bam) bam_read_record(bparts[t], rec_ends[t], name2id, cur, r, !(in_pe && (r & 1)), a, cg, fastq);
+						else if (!opt.debug) sam_read_line(parts[t], idx, cur, r, !(in_pe && (r & 1)), a, cg, fastq);   // mate 2 of a mapped pair is held reverse-complemented
+					}
 				}
 			});
-			for (auto& t : th) t.join();
-			if (out) for (auto& p : parts) fwrite(p.data(), 1, p.size(), out);
-			if (to_bam) for (int t = 0; t < fmt_threads; t++) bam.append(parts[t], rec_ends[t], true);
-			for (int t = 0; t < fmt_threads; t++) { unmapped += um[t]; unique += uq[t]; }
-			total += n;
-			reader.join();
-			std::swap(cur, nxt); got = cur.n();
+			if (to_bam) for (int t = 0; t < io_threads; t++) bam.append(bparts[t], rec_ends[t], true);
+			else if (!opt.debug) out.write_parts(parts);
+			for (int t = 0; t < io_threads; t++) { unmapped += um[t]; unique += uq[t]; }
+			free_q.put(j);
 		}
-		src.close();
+	});
+
+	// stage 2: the GPU
+	kb_params_t pm; pm.min_seed_len = 0; pm.max_gaps = opt.max_gaps; pm.max_insert = 1500; pm.pacbio = opt.pacbio; pm.multihit = opt.multihit; pm.paired = 0;
+	bool pair_end_seen = opt.pair_flag;
+	while (Job* j = ready_q.take())
+	{
+		if (rc) { free_q.put(j); continue; }      // after an error: let the reader run out
+		ReadBatch& cur = j->rb; const bool pair_end = cur.pair_end; pair_end_seen = pair_end;
+		if (!opt.silent) { fprintf(stdout, "\r%lld %s reads have been processed in %ld seconds...", total, pair_end ? "paired-end" : "singled-end", (long)(time(NULL) - t0)); fflush(stdout); }
+		int n = cur.n();
+		// a batch with an odd number of reads can only be the last one of its library: the reference sends a whole chunk through the
+		// single-end branch when its read count is odd (Mapping.cpp:531,598), i.e. the final short chunk
+		int n_pe = (!opt.pacbio && pair_end) ? ((n & 1) ? (n / chunk_reads) * chunk_reads : n) : 0;
+		j->n_pe = n_pe;
+		if (n_pe > 0)
+		{
+			pm.paired = 1; kb_set_params(ctx, &pm);
+			j->br.est_used.assign(n_pe / 2, est_of(st));
+			rc = map_batch(ctx, cur.seq.data(), cur.seq_off.data(), n_pe, j->br.est_used.data(), j->br);
+			if (!rc) rc = settle_est(ctx, cur, j->br, st, chunk_reads, n_pe, &remapped);
+		}
+		if (!rc && n > n_pe)
+		{
+			pm.paired = 0; kb_set_params(ctx, &pm);
+			std::vector<uint64_t> off(cur.seq_off.data() + n_pe, cur.seq_off.data() + n + 1);
+			uint64_t base = off[0]; for (auto& o : off) o -= base;
+			rc = map_batch(ctx, cur.seq.data() + base, off.data(), n - n_pe, nullptr, j->tail);
+		}
+		if (rc) { fprintf(stderr, "\nError! GPU mapping failed: %s (%s)\n", kb_strerror(rc), kb_last_error(ctx)); free_q.put(j); continue; }
+		total += n;
+		done_q.put(j);
 	}
+	reader.join();
+	done_q.put(nullptr); writer.join();
+	const bool pair_end = opt.files1.empty() ? pair_end_seen : pair_end_final;
 	fprintf(stdout, "\rAll the %lld %s reads have been processed in %lld seconds.\n", total, pair_end ? "paired-end" : "single-end", (long long)(time(NULL) - t0));
-	if (out) fclose(out);
+	out.close();
 	if (to_bam) bam.close();
 	if (total > 0)
 	{

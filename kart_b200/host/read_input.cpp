@@ -4,6 +4,10 @@
 #include <algorithm>
 #include <string.h>
 #include <thread>
+#include <stdlib.h>
+#include <sys/mman.h>
+
+static size_t KB_IO_CHUNK = 32u << 20;             // bytes per gzread (KART_B200_IO_CHUNK overrides it: the tests use tiny chunks to exercise refills)
 
 static inline char comp_base(char c)   // GetComplementaryBase, src/tools.cpp:3
 {
@@ -15,6 +19,7 @@ bool ReadSource::open(const char* f1, const char* f2)
 	{ gzFile t = gzopen(f1, "rb"); if (!t) return false; char c = 0; gzread(t, &c, 1); gzclose(t); fastq = (c == '@'); }   // CheckReadFormat :8
 	for (Stream* s : {&s1, &s2}) { s->fp = nullptr; s->pos = s->end = 0; s->eof = false; s->pending.clear(); s->has_pending = false; s->lo = s->hi = 0; s->nl.clear(); s->nl_used = 0; s->drained = false; }
 	two = f2 != nullptr;
+	{ const char* e = getenv("KART_B200_IO_CHUNK"); if (e && atol(e) >= 16) KB_IO_CHUNK = (size_t)atol(e); }
 	s1.fp = gzopen(f1, "rb"); if (!s1.fp) return false; gzbuffer(s1.fp, 1 << 20); s1.buf.resize(1 << 22);
 	if (two) { s2.fp = gzopen(f2, "rb"); if (!s2.fp) { gzclose(s1.fp); s1.fp = nullptr; return false; } gzbuffer(s2.fp, 1 << 20); s2.buf.resize(1 << 22); }
 	return true;
@@ -122,7 +127,6 @@ void parallel_for(int threads, size_t n, const std::function<void(int, size_t, s
 	for (auto& x : th) x.join();
 }
 
-static const size_t KB_IO_CHUNK = 32u << 20;       // bytes per gzread
 static const size_t KB_IO_MAX_TEXT = 1u << 30;     // soft cap of buffered text per stream (offsets are 32 bit)
 
 static void index_newlines(ReadSource::Stream& s, size_t from, size_t to, int threads)
@@ -158,7 +162,7 @@ size_t ReadSource::buffer_records(Stream& s, size_t want)
 			s.nl.resize(nk); s.nl_used = 0; s.hi = keep; s.lo = 0;
 		}
 		if (s.hi + KB_IO_CHUNK > 0xFFFFFF00u) { s.drained = true; continue; }      // an "entry" beyond 4 GB: give up on the stream like a read error
-		s.text.n = s.hi; s.text.reserve(s.hi + KB_IO_CHUNK);
+		s.text.n = s.hi; if (s.text.cap < s.hi + KB_IO_CHUNK) s.text.reserve(std::max(s.hi + KB_IO_CHUNK, std::min((size_t)KB_IO_MAX_TEXT, want * 512) + 2 * KB_IO_CHUNK));
 		int got = gzread(s.fp, s.text.data() + s.hi, (unsigned)KB_IO_CHUNK);
 		if (got <= 0) { s.drained = true; continue; }
 		index_newlines(s, s.hi, s.hi + (size_t)got, threads > 1 && two ? (threads + 1) / 2 : threads);
@@ -322,6 +326,12 @@ void* host_buf_alloc(size_t bytes, bool want_pinned, bool* got_pinned)
 {
 	void* p = want_pinned ? kb_host_alloc(bytes ? bytes : 1) : nullptr;
 	*got_pinned = p != nullptr;
+	if (!p && bytes >= (4u << 20))
+	{
+		// large pageable buffers: 2 MB alignment + MADV_HUGEPAGE (first-touch faults of 4 KB pages cost more than the parsing itself)
+		if (posix_memalign(&p, 2u << 20, (bytes + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1)) != 0) p = nullptr;
+		else madvise(p, (bytes + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1), MADV_HUGEPAGE);
+	}
 	if (!p) p = malloc(bytes ? bytes : 1);
 	if (!p) { fprintf(stderr, "Error! out of host memory (%zu bytes)\n", bytes); exit(1); }
 	return p;
