@@ -39,6 +39,11 @@ static int map_batch(kb_ctx_t* ctx, const uint8_t* seq, const uint64_t* off, int
 	return rc;
 }
 
+// KART_B200_TRACE=1: wall time of every pipeline stage per batch on stderr (reader fill, GPU map, EstDistance settle, format, write)
+static double now_s() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec; }
+static const bool g_trace = getenv("KART_B200_TRACE") != nullptr;
+static double g_t0 = 0;
+
 struct PairState { long long iPaired = 0, iDistance = 0; };
 static inline int est_of(const PairState& s) { if (s.iPaired >= 1000) { int e = (int)(s.iDistance / (s.iPaired >> 2)); return e + (e >> 1); } return 1500; }
 
@@ -129,6 +134,7 @@ int run_mapping(const RunOptions& opt, const HostIndex& idx)
 
 	// stage 1 starts before the device is ready: the first batch is parsed while the index is uploaded
 	const int n_jobs = 3;
+	g_t0 = now_s();
 	std::vector<Job> jobs(n_jobs);
 	Channel<Job*> free_q, ready_q, done_q;
 	for (auto& j : jobs) free_q.put(&j);
@@ -151,7 +157,9 @@ int run_mapping(const RunOptions& opt, const HostIndex& idx)
 			while (true)
 			{
 				Job* j = free_q.take(); j->rb.clear();
+				double ta = now_s();
 				if (src.fill(j->rb, batch_reads, pair_end) <= 0) { free_q.put(j); break; }
+				if (g_trace) fprintf(stderr, "[kart trace] read   %8d reads  %.3f..%.3f s\n", j->rb.n(), ta - g_t0, now_s() - g_t0);
 				ready_q.put(j);
 			}
 			src.close();
@@ -163,10 +171,12 @@ int run_mapping(const RunOptions& opt, const HostIndex& idx)
 
 	kb_ctx_t* ctx = nullptr;
 	int rc = kb_init(0, &ctx);
+	if (g_trace) fprintf(stderr, "[kart trace] kb_init done %.3f s\n", now_s() - g_t0);
 	if (rc) { fprintf(stderr, "Error! kart_b200 needs a CUDA device: %s\n", kb_strerror(rc)); drain_reader(); return 1; }
 	kb_index_host_t hi; idx.describe(&hi);
 	if ((rc = kb_upload_index(ctx, &hi, opt.expand_sa ? 1 : 0)) != 0) { fprintf(stderr, "Error! index upload failed: %s (%s)\n", kb_strerror(rc), kb_last_error(ctx)); drain_reader(); kb_destroy(ctx); return 1; }
 
+	if (g_trace) fprintf(stderr, "[kart trace] index uploaded %.3f s\n", now_s() - g_t0);
 	SamSink out; BamWriter bam; const bool to_bam = opt.out_format == 1 && !opt.debug;
 	std::vector<int32_t> name2id(idx.chr_name.size(), -1);   // bam_name2id: a repeated @SQ name keeps its first id (htslib sam.c:725-733)
 	if (!opt.debug)
@@ -201,6 +211,7 @@ int run_mapping(const RunOptions& opt, const HostIndex& idx)
 		{
 			const ReadBatch& cur = j->rb; const int n = cur.n(), n_pe = j->n_pe; const bool fastq = cur.fastq;
 			std::vector<long long> um(io_threads, 0), uq(io_threads, 0);
+			double ta = now_s();
 			parallel_for(io_threads, (size_t)io_threads, [&](int, size_t t0_, size_t t1_) {
 				for (size_t t = t0_; t < t1_; t++)
 				{
@@ -218,8 +229,10 @@ int run_mapping(const RunOptions& opt, const HostIndex& idx)
 					}
 				}
 			});
+			double tb = now_s();
 			if (to_bam) for (int t = 0; t < io_threads; t++) bam.append(bparts[t], rec_ends[t], true);
 			else if (!opt.debug) out.write_parts(parts);
+			if (g_trace) fprintf(stderr, "[kart trace] format %8d reads  %.3f..%.3f s  write ..%.3f s\n", n, ta - g_t0, tb - g_t0, now_s() - g_t0);
 			for (int t = 0; t < io_threads; t++) { unmapped += um[t]; unique += uq[t]; }
 			free_q.put(j);
 		}
@@ -233,7 +246,7 @@ int run_mapping(const RunOptions& opt, const HostIndex& idx)
 		if (rc) { free_q.put(j); continue; }      // after an error: let the reader run out
 		ReadBatch& cur = j->rb; const bool pair_end = cur.pair_end; pair_end_seen = pair_end;
 		if (!opt.silent) { fprintf(stdout, "\r%lld %s reads have been processed in %ld seconds...", total, pair_end ? "paired-end" : "singled-end", (long)(time(NULL) - t0)); fflush(stdout); }
-		int n = cur.n();
+		int n = cur.n(); double ta = now_s(), tb = ta;
 		// a batch with an odd number of reads can only be the last one of its library: the reference sends a whole chunk through the
 		// single-end branch when its read count is odd (Mapping.cpp:531,598), i.e. the final short chunk
 		int n_pe = (!opt.pacbio && pair_end) ? ((n & 1) ? (n / chunk_reads) * chunk_reads : n) : 0;
@@ -243,6 +256,7 @@ int run_mapping(const RunOptions& opt, const HostIndex& idx)
 			pm.paired = 1; kb_set_params(ctx, &pm);
 			j->br.est_used.assign(n_pe / 2, est_of(st));
 			rc = map_batch(ctx, cur.seq.data(), cur.seq_off.data(), n_pe, j->br.est_used.data(), j->br);
+			tb = now_s();
 			if (!rc) rc = settle_est(ctx, cur, j->br, st, chunk_reads, n_pe, &remapped);
 		}
 		if (!rc && n > n_pe)
@@ -254,6 +268,7 @@ int run_mapping(const RunOptions& opt, const HostIndex& idx)
 		}
 		if (rc) { fprintf(stderr, "\nError! GPU mapping failed: %s (%s)\n", kb_strerror(rc), kb_last_error(ctx)); free_q.put(j); continue; }
 		total += n;
+		if (g_trace) fprintf(stderr, "[kart trace] gpu    %8d reads  %.3f..%.3f s  settle ..%.3f s (remapped %lld)\n", n, ta - g_t0, tb - g_t0, now_s() - g_t0, remapped);
 		done_q.put(j);
 	}
 	reader.join();
