@@ -75,6 +75,14 @@ typedef struct {
 	int32_t cig_len;             /* ops: len << 4 | op with BAM op numbers (M=0,I=1,D=2,S=4)        */
 } kb_aln_t;
 
+/* -m (bMultiHit): a read prints one line per report from iBestAlnCanIdx on (src/Mapping.cpp:194-223,242-263,289-308). kb_aln_t
+ * carries the first of them; every further line is one kb_extra_t. rank orders the extra lines of one read. */
+typedef struct kb_extra_s {
+	uint32_t read;               /* index of the read in the chunk                                  */
+	uint32_t rank;               /* 0, 1, ... in AlnReportArr order                                 */
+	kb_aln_t aln;                /* kind is always 1; cig_off points into the chunk's cigar array   */
+} kb_extra_t;
+
 /* Per pair: contribution to the running insert-size statistic (iPaired/iDistance, src/Mapping.cpp:206-213) and the
  * closed interval of EstDistance values for which this pair's result is provably unchanged (host-side recurrence,
  * src/Mapping.cpp:533-540). */
@@ -108,6 +116,11 @@ int  kb_map_chunk(kb_ctx_t* ctx, const kb_reads_t* in, const int32_t* est, kb_re
 int  kb_stage_reads(kb_ctx_t* ctx, const kb_reads_t* in, const int32_t* est);   /* H2D */
 int  kb_run(kb_ctx_t* ctx);                                                      /* kernels only, returns after they finish */
 int  kb_fetch_results(kb_ctx_t* ctx, kb_results_t* out);                         /* D2H */
+
+/* -m only: the extra lines of the last kb_map_chunk / kb_run, sorted by (read, rank). *n receives the number of entries the
+ * chunk has; when that exceeds cap nothing is copied and KB_ECAPACITY is returned (call again with a larger buffer).
+ * Chunks are not pipelined while multihit is set. */
+int  kb_fetch_extra(kb_ctx_t* ctx, kb_extra_t* out, uint32_t cap, uint32_t* n);
 
 /* Page-locked host memory for the caller-owned buffers (reads in, results out): with it the copies of kb_map_chunk are
  * asynchronous DMA and overlap the kernels; pageable buffers work but are staged by the driver. NULL when no device /

@@ -36,6 +36,7 @@ class KbResults(C.Structure):
 
 ALN_DTYPE = np.dtype([("pos", "<i8"), ("mate_pos", "<i8"), ("kind", "<i4"), ("flag", "<i4"), ("chr", "<i4"), ("mapq", "<i4"),
                       ("score", "<i4"), ("sub_score", "<i4"), ("tlen", "<i4"), ("fwd", "<i4"), ("cig_off", "<u4"), ("cig_len", "<i4")])
+EXTRA_DTYPE = np.dtype([("read", "<u4"), ("rank", "<u4"), ("aln", ALN_DTYPE)])   # kb_extra_t
 PAIR_DTYPE = np.dtype([("counted", "<i4"), ("absdist", "<i4"), ("est_lo", "<i4"), ("est_hi", "<i4")])
 SEG_DTYPE = np.dtype([("gpos", "<i8"), ("rpos", "<i4"), ("rlen", "<i4"), ("glen", "<i4"), ("simple", "<i4")])
 CAND_DTYPE = np.dtype([("diff", "<i8"), ("score", "<i4"), ("mate", "<i4"), ("seg_start", "<u4"), ("nseg", "<i4")])
@@ -45,7 +46,7 @@ RES_DTYPE = np.dtype([("score", "<i4"), ("sub", "<i4"), ("mapq", "<i4"), ("ncan"
 CIGAR_OPS = "MIDNSHP=X"
 
 EXPORTS = ["kb_init", "kb_destroy", "kb_strerror", "kb_last_error", "kb_upload_index", "kb_set_params", "kb_get_min_seed_len",
-           "kb_map_chunk", "kb_stage_reads", "kb_run", "kb_fetch_results", "kb_stage_ms", "kb_work", "kb_cuda_stream", "kb_debug_fetch", "kb_host_alloc", "kb_host_free"]
+           "kb_map_chunk", "kb_stage_reads", "kb_run", "kb_fetch_results", "kb_fetch_extra", "kb_stage_ms", "kb_work", "kb_cuda_stream", "kb_debug_fetch", "kb_host_alloc", "kb_host_free"]
 
 
 class KartB200Error(RuntimeError):
@@ -71,6 +72,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.kb_stage_reads.argtypes = [C.c_void_p, C.POINTER(KbReads), C.c_void_p]
     lib.kb_run.argtypes = [C.c_void_p]
     lib.kb_fetch_results.argtypes = [C.c_void_p, C.POINTER(KbResults)]
+    lib.kb_fetch_extra.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
     lib.kb_stage_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.kb_work.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.kb_cuda_stream.restype = C.c_void_p
@@ -209,6 +211,16 @@ class Mapper:
             rc = self.lib.kb_fetch_results(self.h, C.byref(res))
         self._check(rc, "kb_fetch_results")
         return aln, pairs, cig[:res.n_cigar]
+
+    def fetch_extra(self):
+        """-m: the further lines of the last chunk as a structured array (read, rank, aln), sorted by (read, rank)."""
+        n = C.c_uint32(0)
+        rc = self.lib.kb_fetch_extra(self.h, None, 0, C.byref(n))
+        ext = np.zeros(n.value, dtype=EXTRA_DTYPE)
+        if rc == -6:
+            rc = self.lib.kb_fetch_extra(self.h, ext.ctypes.data, n.value, C.byref(n))
+        self._check(rc, "kb_fetch_extra")
+        return ext
 
     def stage_ms(self):
         a = np.zeros(9, dtype=np.float32)

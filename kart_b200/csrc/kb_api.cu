@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <string>
+#include <algorithm>
 #include <vector>
 #include "../../include/kart_b200.h"
 #include "kb_stages.cuh"
@@ -334,15 +335,15 @@ struct kb_slot
 	cudaStream_t aux[KB_NW_CLASSES]; cudaEvent_t fork = nullptr, join[KB_NW_CLASSES];   // the nw_alignment size classes run side by side (launch_pipeline)
 	KbBatchDev bt; int n_reads = 0; size_t seq_bytes = 0; u64 seq_first = 0; int max_rlen = 0; int first_read = 0;
 	DevBuf<u8> seq, scratch, wscratch; DevBuf<u64> seq_off; DevBuf<unsigned long long> work; DevBuf<i32> est, n_hits, n_seeds, n_cands, cand_cap, rescue, slow1, slow2; DevBuf<u32> seed_off, cand_off, cigar, counters, cseg_off, runs; DevBuf<i32> cseg_n; DevBuf<KbSegX> segx; DevBuf<KbJob> jobs; DevBuf<u32> piece_list, part_list; DevBuf<KbPiece> pieces;
-	DevBuf<KbHit> hits; DevBuf<KbSeg> segs; DevBuf<KbCand> cands; DevBuf<KbReport> reports; DevBuf<KbReadRes> res; DevBuf<KbPairStat> pstat; DevBuf<kb_aln_t> aln; DevBuf<KbPk> pk;
-	size_t cap_segs = 0, cap_cands = 0, cap_cigar = 0, cap_segx = 0, cap_jobs = 0, cap_pieces = 0, cap_runs = 0, scratch_per_thread = 0; int scratch_threads = 0;
+	DevBuf<KbHit> hits; DevBuf<KbSeg> segs; DevBuf<KbCand> cands; DevBuf<KbReport> reports; DevBuf<KbReadRes> res; DevBuf<KbPairStat> pstat; DevBuf<kb_aln_t> aln; DevBuf<KbPk> pk; DevBuf<kb_extra_t> extra;
+	size_t cap_segs = 0, cap_cands = 0, cap_cigar = 0, cap_segx = 0, cap_jobs = 0, cap_pieces = 0, cap_runs = 0, cap_extra = 0, scratch_per_thread = 0; int scratch_threads = 0;
 	u32* counters_host = nullptr; unsigned long long* work_dev_host = nullptr;   // pinned: 16 x u32, 8 x u64
 	int launches = 0;
 	void release()
 	{
 		seq.release(); scratch.release(); wscratch.release(); seq_off.release(); work.release(); est.release(); n_hits.release(); n_seeds.release(); n_cands.release(); cand_cap.release();
 		rescue.release(); slow1.release(); slow2.release(); seed_off.release(); cand_off.release(); cigar.release(); counters.release(); cseg_off.release(); runs.release();
-		cseg_n.release(); segx.release(); jobs.release(); piece_list.release(); part_list.release(); pieces.release(); hits.release(); segs.release(); cands.release(); reports.release(); res.release(); pstat.release(); aln.release(); pk.release();
+		cseg_n.release(); segx.release(); jobs.release(); piece_list.release(); part_list.release(); pieces.release(); hits.release(); segs.release(); cands.release(); reports.release(); res.release(); pstat.release(); aln.release(); pk.release(); extra.release();
 	}
 };
 
@@ -355,7 +356,7 @@ struct kb_ctx
 	kb_slot slot[KB_SLOTS];
 	DevBuf<u32> chunk_cigar, chunk_cursor;   // cigar arena and cursor shared by the sub-batches of one pipelined chunk
 	bool staged = false, ran = false, ran_pipelined = false; u32 n_cigar_last = 0;
-	double seg_factor = 32, cigar_factor = 8, scratch_factor = 1, segx_factor = 8, job_factor = 4, run_factor = 96;
+	double seg_factor = 32, cigar_factor = 8, scratch_factor = 1, segx_factor = 8, job_factor = 4, run_factor = 96, extra_factor = 0.25;
 	float stage_ms[9]; uint64_t work_host[8]; u32 counters_host[KB_NCOUNTERS];
 	cudaEvent_t chunk_start = nullptr; int trace = 0;
 	int seed_minb = 10;
@@ -606,6 +607,10 @@ static int alloc_batch(kb_ctx* ctx, kb_slot& sl, int shared)
 	CK(sl.n_cands.ensure(n)); CK(sl.cand_off.ensure(n)); CK(sl.cand_cap.ensure(n)); CK(sl.rescue.ensure(n / 2 + 1));
 	CK(sl.res.ensure(n)); CK(sl.pstat.ensure(n / 2 + 1)); CK(sl.aln.ensure(n));
 	if (!shared) CK(sl.cigar.ensure(sl.cap_cigar));
+	sl.cap_extra = ctx->pm.multihit ? (size_t)(ctx->extra_factor * (double)n) + 65536 : 0;
+	if (sl.cap_extra > 0xF0000000ull) sl.cap_extra = 0xF0000000ull;
+	if (sl.cap_extra) CK(sl.extra.ensure(sl.cap_extra));
+	bt.extra = sl.extra.p; bt.cap_extra = (u32)sl.cap_extra;
 	CK(sl.segx.ensure(sl.cap_segx)); CK(sl.jobs.ensure(sl.cap_jobs)); CK(sl.pieces.ensure(sl.cap_pieces)); CK(sl.piece_list.ensure(sl.cap_pieces * KB_NW_CLASSES)); CK(sl.part_list.ensure(sl.cap_jobs)); CK(sl.runs.ensure(sl.cap_runs)); CK(sl.cseg_off.ensure(sl.cap_cands)); CK(sl.cseg_n.ensure(sl.cap_cands));
 	CK(sl.counters.ensure(KB_NCOUNTERS)); CK(sl.work.ensure(8)); CK(sl.scratch.ensure(per * threads)); CK(sl.wscratch.ensure(per * (size_t)wwarps));
 	CK(sl.pk.ensure((sl.seq_bytes >> 5) + n + 4)); CK(sl.slow1.ensure(n + 1)); CK(sl.slow2.ensure(n + 1));
@@ -718,6 +723,7 @@ static void grow_factors(kb_ctx* ctx, u32 st)
 	if (st & KB_OVF_SEGX) ctx->segx_factor *= 4;
 	if (st & KB_OVF_JOBS) ctx->job_factor *= 4;
 	if (st & KB_OVF_RUNS) ctx->run_factor *= 4;
+	if (st & KB_OVF_EXTRA) ctx->extra_factor *= 8;
 }
 
 // adds a finished slot's instrumentation to the context totals
@@ -773,6 +779,21 @@ int kb_fetch_results(kb_ctx_t* ctx, kb_results_t* out)
 	if (out->n_cigar) CK(cudaMemcpyAsync(out->cigar, sl.cigar.p, (size_t)out->n_cigar * 4, cudaMemcpyDeviceToHost, sl.stream));
 	if (ctx->pm.paired && out->pairs) CK(cudaMemcpyAsync(out->pairs, sl.pstat.p, (n / 2) * sizeof(kb_pair_stat_t), cudaMemcpyDeviceToHost, sl.stream));
 	CK(cudaStreamSynchronize(sl.stream));
+	return KB_OK;
+}
+
+int kb_fetch_extra(kb_ctx_t* ctx, kb_extra_t* out, uint32_t cap, uint32_t* n)
+{
+	if (!ctx || !n) return KB_EINVAL;
+	if (!ctx->ran || ctx->ran_pipelined) return fail(ctx, KB_ESTATE, "kb_fetch_extra: nothing has run");
+	CK(cudaSetDevice(ctx->device));
+	kb_slot& sl = ctx->slot[0];
+	*n = (ctx->pm.multihit && sl.n_reads) ? ctx->counters_host[14] : 0;
+	if (*n == 0) return KB_OK;
+	if (!out || *n > cap) return fail(ctx, KB_ECAPACITY, "kb_fetch_extra: buffer too small");
+	CK(cudaMemcpyAsync(out, sl.extra.p, (size_t)*n * sizeof(kb_extra_t), cudaMemcpyDeviceToHost, sl.stream));
+	CK(cudaStreamSynchronize(sl.stream));
+	std::sort(out, out + *n, [](const kb_extra_t& a, const kb_extra_t& b) { return a.read != b.read ? a.read < b.read : a.rank < b.rank; });
 	return KB_OK;
 }
 
@@ -843,7 +864,7 @@ static int map_chunk_pipelined(kb_ctx* ctx, const kb_reads_t* in, const int32_t*
 
 int kb_map_chunk(kb_ctx_t* ctx, const kb_reads_t* in, const int32_t* est, kb_results_t* out)
 {
-	if (ctx && in && out && ctx->have_index && in->n_reads >= ctx->pipe_min_reads && in->seq && in->seq_off && out->aln && out->cigar
+	if (ctx && in && out && ctx->have_index && !ctx->pm.multihit && in->n_reads >= ctx->pipe_min_reads && in->seq && in->seq_off && out->aln && out->cigar
 	    && !(ctx->pm.paired && ((in->n_reads & 1) || !est)))
 	{
 		CK(cudaSetDevice(ctx->device));

@@ -140,6 +140,35 @@ KB_HD void kb_fill_aln(kb_aln_t& o, const KbReadRes& rd, const KbReport* rep, co
 	if (mate_ok) { o.mate_pos = mate_rep->pos; o.tlen = tlen; }
 }
 
+// -m: the further lines of a read = the reports after iBestAlnCanIdx, in AlnReportArr order, that the loops of
+// OutputPairedAlignments (AlnScore > 0, src/Mapping.cpp:194-223,242-263) / OutputSingledAlignments (AlnScore == score, :289-308) print.
+// which: 0 single-end, 1 first mate, 2 second mate. l1/l2: lengths of the two mates.
+KB_HD void kb_emit_extra(const KbBatchDev& bt, int r, const KbReadRes& rd, const KbReport* rep, const KbReport* mrep, int l1, int l2, int which)
+{
+	if (rd.score == 0) return;
+	int cnt = 0;
+	for (int i = rd.best + 1; i < rd.ncan; i++) cnt += (which ? rep[i].aln > 0 : rep[i].aln == rd.score) ? 1 : 0;
+	if (cnt == 0) return;
+	u32 at = KB_ALLOC(&bt.counters[14], (u32)cnt);
+	if ((u64)at + (u64)cnt > (u64)bt.cap_extra) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_EXTRA); return; }
+	u32 k = 0;
+	for (int i = rd.best + 1; i < rd.ncan; i++)
+	{
+		const KbReport& a = rep[i];
+		if (!(which ? a.aln > 0 : a.aln == rd.score)) continue;
+		kb_extra_t& e = bt.extra[at + k]; e.read = (u32)r; e.rank = k; k++;
+		kb_aln_t& o = e.aln;
+		o.score = rd.score; o.sub_score = rd.sub; o.mapq = rd.mapq; o.mate_pos = -1; o.tlen = 0;
+		o.kind = 1; o.flag = a.flag; o.chr = a.chr; o.pos = a.pos; o.cig_off = a.cig_off; o.cig_len = a.cig_len; o.fwd = a.fwd;
+		int j = which ? a.mate : -1;
+		if (j != -1 && mrep[j].aln > 0)
+		{
+			o.mate_pos = mrep[j].pos;
+			o.tlen = which == 1 ? (int)(mrep[j].pos - a.pos + (a.fwd ? l2 : 0 - l1)) : 0 - (int)(a.pos - mrep[j].pos + (mrep[j].fwd ? l2 : 0 - l1));
+		}
+	}
+}
+
 KB_HD void kb_stage_finalize(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, kb_aln_t* aln, int t)
 {
 	if (bt.counters[3]) return;
@@ -161,6 +190,7 @@ KB_HD void kb_stage_finalize(const KbIndexDev& ix, const KbParams& pm, const KbB
 			int dist = ok ? 0 - (int)(b.pos - p1[i].pos + (p1[i].fwd ? l2 : 0 - l1)) : 0;
 			kb_fill_aln(aln[rb], r2, p2, ok ? &p1[i] : nullptr, ok, dist);
 		}
+		if (pm.multihit) { kb_emit_extra(bt, ra, r1, p1, p2, l1, l2, 1); kb_emit_extra(bt, rb, r2, p2, p1, l1, l2, 2); }
 	}
 	else
 	{
@@ -169,6 +199,7 @@ KB_HD void kb_stage_finalize(const KbIndexDev& ix, const KbParams& pm, const KbB
 		const KbReadRes& rd = bt.res[t]; const KbReport* rep = bt.reports + rd.rep_off;
 		kb_fill_aln(aln[t], rd, rep, nullptr, false, 0);
 		if (rd.score > 0 && rep[rd.best].aln != rd.score) aln[t].kind = 2;   // OutputSingledAlignments prints reports with AlnScore == score (:293)
+		if (pm.multihit) kb_emit_extra(bt, t, rd, rep, nullptr, 0, 0, 0);
 	}
 }
 

@@ -86,7 +86,7 @@ struct KbJob { i64 gpos; u32 read; i32 rpos, rlen, glen; u32 run_off; i32 nruns,
 struct KbPiece { u32 job; i32 r0, rl, g0, gl; u32 out_off; u32 whole; u32 pad; };
 
 // status bits written by kernels (any non-zero value fails the batch loudly; capacities are then grown and the batch rerun)
-enum { KB_OVF_SEEDS = 1, KB_OVF_CANDS = 2, KB_OVF_CIGAR = 4, KB_OVF_SCRATCH = 8, KB_OVF_HITS = 16, KB_OVF_RESCUE = 32, KB_OVF_NW = 64, KB_OVF_SEGX = 128, KB_OVF_JOBS = 256, KB_OVF_RUNS = 512 };
+enum { KB_OVF_SEEDS = 1, KB_OVF_CANDS = 2, KB_OVF_CIGAR = 4, KB_OVF_SCRATCH = 8, KB_OVF_HITS = 16, KB_OVF_RESCUE = 32, KB_OVF_NW = 64, KB_OVF_SEGX = 128, KB_OVF_JOBS = 256, KB_OVF_RUNS = 512, KB_OVF_EXTRA = 1024 };
 
 // cigar op codes in the arena: len << 4 | op  (BAM numbering)
 enum { KB_OP_M = 0, KB_OP_I = 1, KB_OP_D = 2, KB_OP_S = 4 };
@@ -118,6 +118,7 @@ struct KbBatchDev
 	KbReport* reports;                  // indexed like cands
 	KbReadRes* res;
 	KbPairStat* pstat;
+	struct kb_extra_s* extra; u32 cap_extra;      // -m: further lines per read (cursor: counters[14]); kb_extra_t of include/kart_b200.h
 	u32* cigar; u32 cap_cigar; u32* cig_cursor;   // cursor: counters[2] of the batch, or the chunk-wide cursor of a pipelined chunk
 	// per-thread scratch for the report / rescue kernels
 	u8* scratch; u64 scratch_per_thread; i32 scratch_threads;
@@ -125,7 +126,7 @@ struct KbBatchDev
 	i32 max_rlen;                       // longest read in the batch
 	i32 nw_max_m, nw_max_n, seg_cap, kmer_cap;
 	// counters: [0] seeds cursor [1] cands cursor [2] cigar cursor [3] status bits [4] rescue count [5] max seeds/read
-	//           [6] nw calls [7] rescue attempts [8] segx cursor [10] run cursor + [11] job cursor (one u64) [12],[13] slow lists
+	//           [6] nw calls [7] rescue attempts [8] segx cursor [10] run cursor + [11] job cursor (one u64) [12],[13] slow lists [14] extra-line cursor (-m)
 	//           [16..22] pieces per size class [23] partition jobs [24] piece cursor
 	//           64-bit: work[0] extension steps, work[1] occ blocks, work[2] LF steps, work[3] NW cells, work[4] NW calls
 	u32* counters;

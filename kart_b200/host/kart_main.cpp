@@ -84,7 +84,6 @@ int main(int argc, char* argv[])
 		exit(1);
 	}
 	if (!check_inputs(o) || !check_output_name(o.out_name)) exit(0);
-	if (o.multihit) { fprintf(stderr, "Error! -m (multiple alignments) is not implemented in kart_b200 yet\n"); exit(1); }
 	HostIndex idx; std::string err;
 	if (o.index_prefix.empty() || !check_index_files(o.index_prefix)) { fprintf(stdout, "Error! Please specify a valid reference index!\n"); usage(argv[0]); exit(1); }
 	fprintf(stdout, "Load the genome index files...");

@@ -21,7 +21,9 @@
 struct BatchResult
 {
 	HBuf<kb_aln_t> aln{true}; HBuf<kb_pair_stat_t> pairs{true}; HBuf<uint32_t> cigar{true}; std::vector<int32_t> est_used;
+	std::vector<kb_extra_t> extra;   // -m: further lines, sorted by (read, rank)
 };
+static bool g_multihit = false;
 
 static int map_batch(kb_ctx_t* ctx, const uint8_t* seq, const uint64_t* off, int n, const int32_t* est, BatchResult& out)
 {
@@ -36,6 +38,12 @@ static int map_batch(kb_ctx_t* ctx, const uint8_t* seq, const uint64_t* off, int
 		rc = kb_fetch_results(ctx, &res);
 	}
 	if (rc == KB_OK) out.cigar.n = res.n_cigar;
+	out.extra.clear();
+	if (rc == KB_OK && g_multihit)
+	{
+		uint32_t ne = 0; rc = kb_fetch_extra(ctx, nullptr, 0, &ne);
+		if (rc == KB_ECAPACITY) { out.extra.resize(ne); rc = kb_fetch_extra(ctx, out.extra.data(), ne, &ne); }
+	}
 	return rc;
 }
 
@@ -71,17 +79,22 @@ static int settle_est(kb_ctx_t* ctx, const ReadBatch& b, BatchResult& br, PairSt
 		for (int p : viol) for (int r = 2 * p; r < 2 * p + 2; r++) { seq.insert(seq.end(), b.seq.data() + b.seq_off[r], b.seq.data() + b.seq_off[r + 1]); off.push_back(seq.size()); }
 		BatchResult fix;
 		int rc = map_batch(ctx, seq.data(), off.data(), (int)off.size() - 1, viol_est.data(), fix); if (rc) return rc;
+		const uint32_t base = (uint32_t)br.cigar.size();   // the re-mapped pairs' cigar elements go behind the batch's, offsets shift by base
+		br.cigar.append(fix.cigar.data(), fix.cigar.size());
 		for (size_t k = 0; k < viol.size(); k++)
 		{
 			int p = viol[k];
-			for (int h = 0; h < 2; h++)
-			{
-				kb_aln_t a = fix.aln[2 * k + h];
-				uint32_t at = (uint32_t)br.cigar.size();
-				br.cigar.append(fix.cigar.data() + a.cig_off, (size_t)a.cig_len);
-				a.cig_off = at; br.aln[2 * p + h] = a;
-			}
+			for (int h = 0; h < 2; h++) { kb_aln_t a = fix.aln[2 * k + h]; a.cig_off += base; br.aln[2 * p + h] = a; }
 			br.pairs[p] = fix.pairs[k]; br.est_used[p] = viol_est[k];
+		}
+		if (g_multihit)
+		{
+			std::vector<char> redo((size_t)n / 2 + 1, 0); for (int p : viol) redo[p] = 1;
+			std::vector<kb_extra_t> keep; keep.reserve(br.extra.size() + fix.extra.size());
+			for (const kb_extra_t& e : br.extra) if (!redo[e.read >> 1]) keep.push_back(e);
+			for (kb_extra_t e : fix.extra) { e.read = (uint32_t)(2 * viol[e.read >> 1]) + (e.read & 1); e.aln.cig_off += base; keep.push_back(e); }
+			std::sort(keep.begin(), keep.end(), [](const kb_extra_t& a, const kb_extra_t& b) { return a.read != b.read ? a.read < b.read : a.rank < b.rank; });
+			br.extra.swap(keep);
 		}
 	}
 }
@@ -218,6 +231,9 @@ int run_mapping(const RunOptions& opt, const HostIndex& idx)
 					int lo = (int)((long long)n * (long long)t / io_threads), hi = (int)((long long)n * (long long)(t + 1) / io_threads);
 					if (n_pe) { lo &= ~1; if ((int)t + 1 < io_threads) hi &= ~1; }
 					parts[t].clear(); bparts[t].clear(); rec_ends[t].clear();
+					// -m: cursors into the extra lines of the paired part and of the single-end tail
+					auto first_of = [](const std::vector<kb_extra_t>& v, uint32_t r) { return (size_t)(std::lower_bound(v.begin(), v.end(), r, [](const kb_extra_t& e, uint32_t x) { return e.read < x; }) - v.begin()); };
+					size_t xe = first_of(j->br.extra, (uint32_t)std::min(lo, n_pe)), xt = first_of(j->tail.extra, (uint32_t)std::max(lo - n_pe, 0));
 					for (int r = lo; r < hi; r++)
 					{
 						bool in_pe = r < n_pe;
@@ -226,6 +242,12 @@ int run_mapping(const RunOptions& opt, const HostIndex& idx)
 						if (a.score == 0) um[t]++; else if (a.mapq == 60) uq[t]++;
 						if (to_bam) bam_read_record(bparts[t], rec_ends[t], name2id, cur, r, !(in_pe && (r & 1)), a, cg, fastq);
 						else if (!opt.debug) sam_read_line(parts[t], idx, cur, r, !(in_pe && (r & 1)), a, cg, fastq);   // mate 2 of a mapped pair is held reverse-complemented
+						const std::vector<kb_extra_t>& xv = in_pe ? j->br.extra : j->tail.extra; size_t& x = in_pe ? xe : xt; const uint32_t xr = (uint32_t)(in_pe ? r : r - n_pe);
+						for (; x < xv.size() && xv[x].read == xr; x++)
+						{
+							if (to_bam) bam_read_record(bparts[t], rec_ends[t], name2id, cur, r, !(in_pe && (r & 1)), xv[x].aln, cg, fastq);
+							else if (!opt.debug) sam_read_line(parts[t], idx, cur, r, !(in_pe && (r & 1)), xv[x].aln, cg, fastq);
+						}
 					}
 				}
 			});
@@ -240,7 +262,7 @@ int run_mapping(const RunOptions& opt, const HostIndex& idx)
 
 	// stage 2: the GPU
 	kb_params_t pm; pm.min_seed_len = 0; pm.max_gaps = opt.max_gaps; pm.max_insert = 1500; pm.pacbio = opt.pacbio; pm.multihit = opt.multihit; pm.paired = 0;
-	bool pair_end_seen = opt.pair_flag;
+	bool pair_end_seen = opt.pair_flag; g_multihit = opt.multihit;
 	while (Job* j = ready_q.take())
 	{
 		if (rc) { free_q.put(j); continue; }      // after an error: let the reader run out

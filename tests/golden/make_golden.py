@@ -12,6 +12,7 @@ Outputs (all under tests/golden/):
   nw_vectors.txt                      200 nw_alignment input/output pairs
   frag_vectors.txt                    8-mer partition (+IdentifyNormalPairs) of 60 fragment pairs
   ecoli_c1.md5                        md5 of the reference SAM for run_test.sh (C1), raw and `LC_ALL=C sort`ed
+  dup/dup.* pe150m_{1,2}.fq pe150m.sam pe150m.bam se100m.sam pb3km.sam   -m (multiple alignments) runs, `make_golden.py multihit`
   pe150.bam se100.bam pb3k.bam        the same three runs with `-bo` (reference linked against its vendored htslib 1.5:
                                       oracle/_ref/kart_hts); bam_zlib.txt records the zlib version the bytes depend on
 """
@@ -47,9 +48,27 @@ def bam_goldens():
     open(g + "bam_zlib.txt", "w").write(zlib.ZLIB_RUNTIME_VERSION + "\n")
 
 
+def multihit_goldens():
+    """-m: dup/ = 60 kbp, 2 contigs with EXACT repeats (so that whole pairs tie), 300 pairs @0.5 % -> pe150m.sam / .bam; the mini
+    single-end and pacbio sets again with -m -> se100m.sam, pb3km.sam."""
+    g = HERE + "/"
+    dup = os.path.join(HERE, "dup"); os.makedirs(dup, exist_ok=True)
+    names, seqs = synth.make_genome(60_000, 2, seed=777, repeats=((2500, 4, 0.0), (600, 8, 0.0), (300, 10, 0.01)))
+    synth.write_fasta(os.path.join(dup, "dup.fa"), names, seqs)
+    prefix = os.path.join(dup, "dup")
+    subprocess.run([pu.REF_BWT_INDEX, prefix + ".fa", prefix], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    f1, f2 = synth.make_reads(seqs, g + "pe150m", 300, 150, 0.005, seed=201, indel=0.001)
+    kart(prefix, ["-m", "-f", f1, "-f2", f2], g + "pe150m.sam")
+    kart_bam(prefix, ["-m", "-f", f1, "-f2", f2], g + "pe150m.bam")
+    kart(pu.MINI_PREFIX, ["-m", "-f", g + "se100.fq"], g + "se100m.sam")
+    kart(pu.MINI_PREFIX, ["-m", "-pacbio", "-f", g + "pb3k.fq"], g + "pb3km.sam")
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "bam":
         return bam_goldens()
+    if len(sys.argv) > 1 and sys.argv[1] == "multihit":
+        return multihit_goldens()
     assert os.path.exists(pu.REF_KART) and os.path.exists(pu.REF_LIB), "build oracle/_ref first (python -c 'import __graft_entry__ as g; g.build()')"
     mini = os.path.join(HERE, "mini")
     os.makedirs(mini, exist_ok=True)

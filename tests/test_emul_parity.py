@@ -100,6 +100,44 @@ def test_cli_bam_is_byte_identical_to_reference(kart_emul, tmp_path, tag, args):
     assert pu.bam_equal(out, os.path.join(G, tag + ".bam"))
 
 
+MH_CASES = [("pe150m", "dup", ["-f", "pe150m_1.fq", "-f2", "pe150m_2.fq"]), ("se100m", "mini", ["-f", "se100.fq"]), ("pb3km", "mini", ["-pacbio", "-f", "pb3k.fq"])]
+
+
+@pytest.mark.parametrize("tag,genome,args", MH_CASES)
+def test_cli_multihit_sam_is_byte_identical_to_reference(kart_emul, tmp_path, tag, genome, args):
+    """-m (bMultiHit): one line per report from iBestAlnCanIdx on (Mapping.cpp:194-223,242-263,289-308). dup/ has exact repeats, so
+    whole pairs tie (198 extra lines in pe150m.sam); goldens from `kart -t 1 -m` (make_golden.py multihit)."""
+    out = str(tmp_path / (tag + ".sam"))
+    a = [os.path.join(G, x) if x.endswith(".fq") else x for x in args]
+    subprocess.run([kart_emul, "-silent", "-t", "2", "-m", "-i", os.path.join(G, genome, genome)] + a + ["-o", out, "--batch", "400"], check=True, stdout=subprocess.DEVNULL)
+    gold = open(os.path.join(G, tag + ".sam"), "rb").read()
+    assert open(out, "rb").read() == gold
+    if tag == "pe150m":
+        assert len(gold.splitlines()) > 2 * 300 + 3 + 100   # the case does exercise extra lines
+        bam = str(tmp_path / "pe150m.bam")
+        subprocess.run([kart_emul, "-silent", "-t", "3", "-m", "-i", os.path.join(G, genome, genome)] + a + ["-bo", bam, "--batch", "400"], check=True, stdout=subprocess.DEVNULL)
+        assert pu.bam_equal(bam, os.path.join(G, "pe150m.bam"))
+
+
+@pytest.mark.skipif(not os.path.exists(pu.REF_KART), reason="needs oracle/_ref/kart")
+def test_cli_multihit_with_est_recurrence_vs_reference(kart_emul, tmp_path):
+    """-m past 1000 counted pairs (settle_est replaces re-mapped pairs together with their extra lines): identical to `kart -t 1 -m`
+    except for the flag of lines whose report the reference never flags (uninitialised SamFlag, AlignmentCandidates.cpp:636; we print 0)."""
+    from kart_b200 import KartIndex, synth
+    prefix = os.path.join(G, "dup", "dup")
+    g = pu.genome_of(KartIndex(prefix))
+    f1, f2 = synth.make_reads(g, str(tmp_path / "mh"), 3000, 150, 0.01, seed=5, indel=0.002)
+    ours, ref = str(tmp_path / "ours.sam"), str(tmp_path / "ref.sam")
+    subprocess.run([kart_emul, "-silent", "-t", "2", "-m", "-i", prefix, "-f", f1, "-f2", f2, "-o", ours], check=True, stdout=subprocess.DEVNULL)
+    subprocess.run([pu.REF_KART, "-silent", "-t", "1", "-m", "-i", prefix, "-f", f1, "-f2", f2, "-o", ref], check=True, stdout=subprocess.DEVNULL)
+    a, b = open(ours, "rb").read().splitlines(), open(ref, "rb").read().splitlines()
+    assert len(a) == len(b) and len(a) > 6000 + 500
+    for x, y in zip(a, b):
+        if x != y:
+            fx, fy = x.split(b"\t"), y.split(b"\t")
+            assert fx[:1] + fx[2:] == fy[:1] + fy[2:] and fx[1] == b"0"
+
+
 KART_HTS = os.path.join(pu.ROOT, "oracle", "_ref", "kart_hts")
 
 

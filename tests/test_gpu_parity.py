@@ -159,6 +159,36 @@ def test_cli_golden_bam(built, tmp_path, tag, args):
     assert pu.bam_equal(out, os.path.join(G, tag + ".bam"))
 
 
+@pytest.mark.parametrize("tag,genome,args", [("pe150m", "dup", ["-f", "pe150m_1.fq", "-f2", "pe150m_2.fq"]), ("se100m", "mini", ["-f", "se100.fq"]), ("pb3km", "mini", ["-pacbio", "-f", "pb3k.fq"])])
+def test_cli_multihit_golden_sam(built, tmp_path, tag, genome, args):
+    """-m through the CUDA CLI (k_finalize emits the further lines, kb_fetch_extra returns them): the reference's bytes."""
+    out = str(tmp_path / (tag + ".sam"))
+    a = [os.path.join(G, x) if x.endswith(".fq") else x for x in args]
+    subprocess.run([KART, "-silent", "-m", "-i", os.path.join(G, genome, genome)] + a + ["-o", out], check=True, stdout=subprocess.DEVNULL)
+    assert open(out, "rb").read() == open(os.path.join(G, tag + ".sam"), "rb").read()
+
+
+@pytest.mark.skipif(not os.path.exists(pu.REF_KART), reason="needs oracle/_ref/kart (built in the build container, shipped with the snapshot)")
+def test_cli_multihit_6000_pairs_vs_reference(built, tmp_path):
+    """-m with the EstDistance recurrence active (>= 1000 counted pairs): identical to `kart -t 1 -m` except for the SAM flag of the
+    lines whose report the reference never flags (uninitialised AlignmentReport_t::SamFlag, AlignmentCandidates.cpp:636; we print 0)."""
+    prefix = os.path.join(G, "dup", "dup")
+    g = pu.genome_of(KartIndex(prefix))
+    f1, f2 = synth.make_reads(g, str(tmp_path / "mh"), 6000, 150, 0.01, seed=5, indel=0.002)
+    ours, ref = str(tmp_path / "ours.sam"), str(tmp_path / "ref.sam")
+    subprocess.run([KART, "-silent", "-m", "-i", prefix, "-f", f1, "-f2", f2, "-o", ours], check=True, stdout=subprocess.DEVNULL)
+    subprocess.run([pu.REF_KART, "-silent", "-t", "1", "-m", "-i", prefix, "-f", f1, "-f2", f2, "-o", ref], check=True, stdout=subprocess.DEVNULL)
+    a, b = open(ours, "rb").read().splitlines(), open(ref, "rb").read().splitlines()
+    assert len(a) == len(b) and len(a) > 12000 + 1000
+    n_flag = 0
+    for x, y in zip(a, b):
+        if x != y:
+            fx, fy = x.split(b"\t"), y.split(b"\t")
+            assert fx[:1] + fx[2:] == fy[:1] + fy[2:] and fx[1] == b"0"
+            n_flag += 1
+    assert n_flag < 100
+
+
 @pytest.mark.skipif(not (os.path.exists(pu.REF_KART) and pu.have_ecoli()), reason="needs oracle/_ref/kart and the E. coli index (built in the build container, shipped with the snapshot)")
 def test_cli_100k_pairs_identical_to_reference_t1(built, tmp_path):
     """C2-shaped input through the real CLI: byte-identical to `kart -t 1` including the per-chunk EstDistance recurrence."""
