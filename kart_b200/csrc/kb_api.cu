@@ -307,13 +307,20 @@ __global__ void __launch_bounds__(KB_BLOCK) k_nw_tile(KbIndexDev ix, KbParams pm
 }
 __global__ void __launch_bounds__(KB_BLOCK) k_align_gather(KbBatchDev bt)
 {
+	// cigar elements are only handed out by the assemble kernels that follow: the cursor as it stands now and as k_finalize
+	// finds it bracket this batch's elements in a chunk-wide arena (map_chunk_pipelined copies that range back on its own)
+	if (blockIdx.x == 0 && threadIdx.x == 0) bt.counters[30] = KB_ATOMIC_ADD(bt.cig_cursor, 0u);
 	if (bt.counters[3]) return;
 	const u32 njobs = bt.counters[23];
 	for (u32 q = blockIdx.x * blockDim.x + threadIdx.x; q < njobs; q += gridDim.x * blockDim.x) kb_gather_job(bt, bt.part_list[q]);
 }
 __global__ void __launch_bounds__(KB_BLOCK) k_assemble(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_assemble(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x); }
 __global__ void __launch_bounds__(KB_BLOCK) k_assemble_slow(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_assemble_slow(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
-__global__ void __launch_bounds__(KB_BLOCK) k_finalize(KbIndexDev ix, KbParams pm, KbBatchDev bt, kb_aln_t* aln) { kb_stage_finalize(ix, pm, bt, aln, blockIdx.x * blockDim.x + threadIdx.x); }
+__global__ void __launch_bounds__(KB_BLOCK) k_finalize(KbIndexDev ix, KbParams pm, KbBatchDev bt, kb_aln_t* aln)
+{
+	if (blockIdx.x == 0 && threadIdx.x == 0) bt.counters[31] = KB_ATOMIC_ADD(bt.cig_cursor, 0u);
+	kb_stage_finalize(ix, pm, bt, aln, blockIdx.x * blockDim.x + threadIdx.x);
+}
 
 // ------------------------------------------------------------------------------------------------
 // context
@@ -362,7 +369,9 @@ struct kb_ctx
 	int seed_minb = 10;
 	int nw_streams = 1;          // 1: the size-class kernels of phase B are forked onto the slot's aux streams and joined before the gather
 	int align_warps = KB_ALIGN_WARPS;
-	int pipe_min_reads = 262144, pipe_sub_reads = 0;   // chunks of at least pipe_min_reads go through the two-slot pipeline
+	int pipe_min_reads = 262144, pipe_sub_reads = 0;   // chunks of at least pipe_min_reads go through the slot pipeline
+	int pipe_first = 0, pipe_grow = 200, pipe_tail = 0;   // sub-batch plan: first size, growth (percent), floor of the halving tail (0: uniform)
+	cudaStream_t copy_stream = nullptr;                   // D2H of each sub-batch's cigar range, in retirement order
 };
 
 static int fail(kb_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess)
@@ -423,6 +432,10 @@ int kb_init(int device, kb_ctx_t** out)
 	const char* e = getenv("KB_PIPE_MIN_READS"); if (e && atoi(e) > 0) ctx->pipe_min_reads = atoi(e);
 	e = getenv("KB_SEED_MINB"); if (e && atoi(e) == 8) ctx->seed_minb = 8;
 	e = getenv("KB_PIPE_SUB_READS"); if (e && atoi(e) > 0) ctx->pipe_sub_reads = atoi(e);
+	e = getenv("KB_PIPE_FIRST"); if (e && atoi(e) >= 0) ctx->pipe_first = atoi(e);
+	e = getenv("KB_PIPE_GROW"); if (e && atoi(e) >= 100) ctx->pipe_grow = atoi(e);
+	e = getenv("KB_PIPE_TAIL"); if (e && atoi(e) >= 0) ctx->pipe_tail = atoi(e);
+	if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return KB_ECUDA; }
 	e = getenv("KB_NW_STREAMS"); if (e) ctx->nw_streams = atoi(e) ? 1 : 0;
 	e = getenv("KB_ALIGN_WARPS"); if (e && atoi(e) >= 148 && atoi(e) <= 148 * 64) ctx->align_warps = atoi(e) / 4 * 4;
 	*out = ctx;
@@ -435,6 +448,7 @@ void kb_destroy(kb_ctx_t* ctx)
 	cudaSetDevice(ctx->device);
 	for (int k = 0; k < KB_SLOTS; k++) if (ctx->slot[k].stream) cudaStreamSynchronize(ctx->slot[k].stream);
 	if (ctx->chunk_start) cudaEventDestroy(ctx->chunk_start);
+	if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
 	ctx->occ.release(); ctx->ktab.release(); ctx->ref64.release(); ctx->sa.release(); ctx->sa_full.release(); ctx->pac.release(); ctx->lut.release(); ctx->chr64.release(); ctx->chr32.release();
 	ctx->chunk_cigar.release(); ctx->chunk_cursor.release();
 	for (int k = 0; k < KB_SLOTS; k++)
@@ -767,9 +781,16 @@ int kb_run(kb_ctx_t* ctx)
 int kb_fetch_results(kb_ctx_t* ctx, kb_results_t* out)
 {
 	if (!ctx || !out) return KB_EINVAL;
-	if (!ctx->ran || ctx->ran_pipelined) return fail(ctx, KB_ESTATE, "kb_fetch_results: nothing has run");
+	if (!ctx->ran) return fail(ctx, KB_ESTATE, "kb_fetch_results: nothing has run");
 	CK(cudaSetDevice(ctx->device));
 	kb_slot& sl = ctx->slot[0];
+	if (ctx->ran_pipelined)   // kb_map_chunk delivered aln/pairs already; KB_ECAPACITY left the cigar elements in the chunk-wide arena
+	{
+		out->n_cigar = ctx->n_cigar_last;
+		if (out->n_cigar > out->cap_cigar || (out->n_cigar > 0 && !out->cigar)) return fail(ctx, KB_ECAPACITY, "kb_fetch_results: cigar buffer too small");
+		if (out->n_cigar) { CK(cudaMemcpyAsync(out->cigar, ctx->chunk_cigar.p, (size_t)out->n_cigar * 4, cudaMemcpyDeviceToHost, sl.stream)); CK(cudaStreamSynchronize(sl.stream)); }
+		return KB_OK;
+	}
 	size_t n = (size_t)sl.n_reads;
 	out->n_cigar = n ? ctx->n_cigar_last : 0;
 	if (n == 0) return KB_OK;
@@ -797,27 +818,49 @@ int kb_fetch_extra(kb_ctx_t* ctx, kb_extra_t* out, uint32_t cap, uint32_t* n)
 	return KB_OK;
 }
 
-// Large chunks: sub-batches alternate between the two slots. Each slot's stream carries H2D -> kernels -> D2H of its
-// sub-batch, so the copies of one sub-batch overlap the kernels of its neighbours. Cigar elements of all sub-batches go to
-// one chunk-wide arena behind one cursor (offsets in kb_aln_t are chunk-wide) and are copied once at the end.
+// Large chunks: sub-batches rotate through the slots. Each slot's stream carries H2D -> kernels -> D2H of its sub-batch, so
+// the copies of one sub-batch overlap the kernels of its neighbours. Cigar elements of all sub-batches go to one chunk-wide
+// arena behind one cursor (offsets in kb_aln_t are chunk-wide). Only the assemble kernels hand out elements, so the cursor
+// values on either side of them (counters[30], [31]) bracket a sub-batch's elements; when a sub-batch retires that range is
+// copied back on copy_stream. Ranges of neighbouring sub-batches may overlap when their assemble phases ran side by side: the
+// later copy (queued after its sub-batch finished, same stream) then rewrites those elements with their final values.
+//
+// The plan: the GPU idles while the first sub-batch is copied in and the copy engine alone is busy while the last one is
+// copied out, so sub-batches start small (pipe_first), grow by pipe_grow percent up to the steady size, and the tail halves
+// the remainder down to pipe_tail. pipe_first = 0 gives uniform sub-batches.
+static void pipeline_plan(const kb_ctx* ctx, int n, std::vector<int>& first, std::vector<int>& count)
+{
+	int steady = ctx->pipe_sub_reads;
+	if (steady <= 0) { steady = n / 4; if (steady < 65536) steady = 65536; if (steady > 1048576) steady = 1048576; }
+	double s = ctx->pipe_first > 0 ? (double)ctx->pipe_first : (double)steady;
+	first.clear(); count.clear();
+	for (int at = 0; at < n;)
+	{
+		int rem = n - at, c = s < (double)steady ? (int)s : steady;
+		if (ctx->pipe_tail > 0) { int half = rem / 2 > ctx->pipe_tail ? rem / 2 : ctx->pipe_tail; if (c > half) c = half; }
+		c &= ~1; if (c < 2) c = 2; if (c > rem) c = rem;
+		if (rem - c < c / 4) c = rem;   // no crumbs
+		first.push_back(at); count.push_back(c); at += c;
+		s = s * (double)ctx->pipe_grow / 100.0;
+	}
+}
+
 static int map_chunk_pipelined(kb_ctx* ctx, const kb_reads_t* in, const int32_t* est, kb_results_t* out)
 {
 	const int n = in->n_reads;
-	int sub = ctx->pipe_sub_reads;
-	if (sub <= 0) { sub = n / 10; if (sub < 65536) sub = 65536; if (sub > 1048576) sub = 1048576; }
-	sub &= ~1; if (sub < 2) sub = 2;
-	const int nsub = (n + sub - 1) / sub;
+	std::vector<int> p_first, p_count; pipeline_plan(ctx, n, p_first, p_count);
+	const int nsub = (int)p_first.size();
 	memset(ctx->stage_ms, 0, sizeof(ctx->stage_ms)); memset(ctx->work_host, 0, sizeof(ctx->work_host));
-	int L = 0;
 	for (int attempt = 0; attempt < 6; attempt++)
 	{
 		size_t cap = (size_t)(ctx->cigar_factor * (double)n) + (ctx->pm.pacbio ? in->seq_off[n] / 2 : 0) + 65536;
 		if (cap > 0xF0000000ull) cap = 0xF0000000ull;
+		CK(cudaStreamSynchronize(ctx->copy_stream));   // copies of an abandoned attempt
 		CK(ctx->chunk_cigar.ensure(cap)); CK(ctx->chunk_cursor.ensure(4));
 		CK(cudaMemsetAsync(ctx->chunk_cursor.p, 0, 4 * sizeof(u32), ctx->slot[0].stream));
 		CK(cudaEventRecord(ctx->chunk_start, ctx->slot[0].stream));
 		CK(cudaStreamSynchronize(ctx->slot[0].stream));
-		u32 status = 0;
+		u32 status = 0, n_cigar = 0; bool fits = true;
 		memset(ctx->stage_ms, 0, sizeof(ctx->stage_ms)); memset(ctx->work_host, 0, sizeof(ctx->work_host));
 		for (int k = 0; k < nsub + KB_SLOTS; k++)
 		{
@@ -827,19 +870,22 @@ static int map_chunk_pipelined(kb_ctx* ctx, const kb_reads_t* in, const int32_t*
 				CK(cudaStreamSynchronize(sl.stream));
 				status |= sl.counters_host[3];
 				account_slot(ctx, sl);
+				const u32 lo = sl.counters_host[30], hi = sl.counters_host[31];
+				if (hi > n_cigar) n_cigar = hi;
+				if (hi > out->cap_cigar) fits = false;
+				if (!status && fits && hi > lo) CK(cudaMemcpyAsync(out->cigar + lo, ctx->chunk_cigar.p + lo, (size_t)(hi - lo) * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
 				if (ctx->trace)
 				{
 					float a = 0, b = 0, c = 0, d = 0;
 					cudaEventElapsedTime(&a, ctx->chunk_start, sl.ev[9]); cudaEventElapsedTime(&b, ctx->chunk_start, sl.ev[0]);
 					cudaEventElapsedTime(&c, ctx->chunk_start, sl.ev[8]); cudaEventElapsedTime(&d, ctx->chunk_start, sl.done);
-					fprintf(stderr, "[kb pipe] sub %d: h2d %.2f..%.2f  kernels ..%.2f  d2h ..%.2f ms\n", k - KB_SLOTS, a, b, c, d);
+					fprintf(stderr, "[kb pipe] sub %d (%d reads): h2d %.2f..%.2f  kernels ..%.2f  d2h ..%.2f ms  cigar [%u, %u)\n", k - KB_SLOTS, sl.n_reads, a, b, c, d, lo, hi);
 				}
 			}
 			if (status || k >= nsub) continue;
-			const int first = k * sub, count = first + sub <= n ? sub : n - first;
+			const int first = p_first[k], count = p_count[k];
 			CK(cudaEventRecord(sl.ev[9], sl.stream));
 			int rc = stage_slot(ctx, sl, in, first, count, est); if (rc) return rc;
-			if (sl.max_rlen > L) L = sl.max_rlen;
 			rc = alloc_batch(ctx, sl, 1); if (rc) return rc;
 			rc = launch_pipeline(ctx, sl); if (rc) return rc;
 			CK(cudaMemcpyAsync(out->aln + first, sl.aln.p, (size_t)count * sizeof(kb_aln_t), cudaMemcpyDeviceToHost, sl.stream));
@@ -848,13 +894,10 @@ static int map_chunk_pipelined(kb_ctx* ctx, const kb_reads_t* in, const int32_t*
 		}
 		if (status == 0)
 		{
-			u32* cur = ctx->slot[0].counters_host;
-			CK(cudaMemcpyAsync(cur, ctx->chunk_cursor.p, sizeof(u32), cudaMemcpyDeviceToHost, ctx->slot[0].stream));
-			CK(cudaStreamSynchronize(ctx->slot[0].stream));
-			out->n_cigar = cur[0]; ctx->n_cigar_last = cur[0];
+			CK(cudaStreamSynchronize(ctx->copy_stream));
+			out->n_cigar = n_cigar; ctx->n_cigar_last = n_cigar;
 			ctx->ran = true; ctx->ran_pipelined = true;
-			if (out->n_cigar > out->cap_cigar) return fail(ctx, KB_ECAPACITY, "kb_map_chunk: cigar buffer too small");
-			if (out->n_cigar) { CK(cudaMemcpyAsync(out->cigar, ctx->chunk_cigar.p, (size_t)out->n_cigar * 4, cudaMemcpyDeviceToHost, ctx->slot[0].stream)); CK(cudaStreamSynchronize(ctx->slot[0].stream)); }
+			if (!fits) return fail(ctx, KB_ECAPACITY, "kb_map_chunk: cigar buffer too small");   // kb_fetch_results() with a larger buffer delivers them
 			return KB_OK;
 		}
 		grow_factors(ctx, status);

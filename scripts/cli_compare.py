@@ -17,6 +17,7 @@ ap.add_argument("--len", type=int, default=0)
 ap.add_argument("--t1", action="store_true")
 ap.add_argument("--ours-only", action="store_true")
 ap.add_argument("--extra", default="")
+ap.add_argument("--diff-out", default=None, help="write the first differing lines (ours vs reference) to this file")
 ap.add_argument("--threads", type=int, default=os.cpu_count() or 1)
 a = ap.parse_args()
 prefix = a.prefix or pu.default_prefix()
@@ -72,8 +73,25 @@ res["ours_reads_per_s_incl_load"] = n_reads / res["ours_total_s"]
 res["ref_reads_per_s_incl_load"] = n_reads / res["ref_total_s"]
 res["sam_bytes"] = os.path.getsize(ours_sam)
 res["sorted_identical_to_ref_tN"] = md5(ours_sam, True) == md5(ref_sam, True)
+
+
+def dump_diff(a_path, b_path, tag):
+    if not a.diff_out:
+        return
+    d = subprocess.run("diff %s %s | head -60" % (a_path, b_path), shell=True, capture_output=True, text=True).stdout
+    n = subprocess.run("diff %s %s | grep -c '^<'" % (a_path, b_path), shell=True, capture_output=True, text=True).stdout.strip()
+    with open(a.diff_out, "a") as fh:
+        fh.write("== %s: %s differing lines\n%s\n" % (tag, n, d))
+
+
+if not res["sorted_identical_to_ref_tN"]:
+    dump_diff(ours_sam + ".sorted", ref_sam + ".sorted", "ours vs ref -t %d (sorted)" % a.threads)
 if a.t1:
     res["ref_t1_total_s"] = run(pu.REF_KART, 1, files, ref1_sam)
     res["raw_identical_to_ref_t1"] = md5(ours_sam) == md5(ref1_sam)
+    if not res["raw_identical_to_ref_t1"]:
+        dump_diff(ours_sam, ref1_sam, "ours vs ref -t 1 (raw)")
+    if not res["sorted_identical_to_ref_tN"]:
+        res["ref_tN_sorted_identical_to_ref_t1"] = md5(ref_sam, True) == md5(ref1_sam, True)
 print(json.dumps(res))
 subprocess.run(["rm", "-rf", tmp])

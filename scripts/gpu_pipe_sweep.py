@@ -18,14 +18,22 @@ aln_pin = torch.empty(n * ALN_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
 pair_pin = torch.empty((n // 2) * PAIR_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
 cig_pin = torch.empty(4 * n + 1024, dtype=torch.int32).pin_memory()
 out = (aln_pin.numpy().view(ALN_DTYPE), pair_pin.numpy().view(PAIR_DTYPE), cig_pin.numpy().view(np.uint32))
-for sub in [0, 2 * pairs + 2, 1000000, 500000, 333334, 250000, 200000, 131072, 65536]:
-    if sub: os.environ["KB_PIPE_SUB_READS"] = str(sub)
+plans = [dict(sub=2 * pairs + 2), dict(sub=500000), dict(sub=400000),
+         dict(sub=500000, first=65536, grow=200, tail=0), dict(sub=500000, first=65536, grow=200, tail=65536),
+         dict(sub=500000, first=131072, grow=200, tail=131072), dict(sub=400000, first=100000, grow=200, tail=100000),
+         dict(sub=600000, first=65536, grow=300, tail=65536), dict(sub=700000, first=131072, grow=250, tail=131072),
+         dict(sub=500000, first=32768, grow=200, tail=32768), dict(sub=333334, first=65536, grow=150, tail=65536)]
+if len(sys.argv) > 2:
+    plans = [dict(zip(("sub", "first", "grow", "tail"), (int(x) for x in a.split(",")))) for a in sys.argv[2:]]
+for pl in plans:
+    sub = pl["sub"]
+    os.environ["KB_PIPE_SUB_READS"] = str(sub)
+    os.environ["KB_PIPE_FIRST"] = str(pl.get("first", 0)); os.environ["KB_PIPE_GROW"] = str(pl.get("grow", 200)); os.environ["KB_PIPE_TAIL"] = str(pl.get("tail", 0))
     os.environ["KB_PIPE_MIN_READS"] = "1000" if sub != 2 * pairs + 2 else "2000000000"
     m = Mapper(device=0); m.upload_index(idx, expand_sa=True); m.set_params(paired=True)
     for _ in range(2): m.map_chunk(flat, off, est, out=out)
     torch.cuda.synchronize(); t = time.perf_counter()
-    for _ in range(4): m.map_chunk(flat, off, est, out=out)
-    torch.cuda.synchronize(); dt = (time.perf_counter() - t) / 4
-    sm = m.stage_ms()
-    print("sub %8d  e2e %.2f ms  (%.1f M reads/s)  kernels total %.2f ms  stages %s launches %d" % (sub, dt * 1e3, n / dt / 1e6, sm["total"], {k: round(v, 2) for k, v in sm.items() if k != "total"}, m.work()["launches"]), flush=True)
+    for _ in range(5): m.map_chunk(flat, off, est, out=out)
+    torch.cuda.synchronize(); dt = (time.perf_counter() - t) / 5
+    print("plan %-60s e2e %.2f ms  (%.1f M reads/s)  launches %d" % (pl, dt * 1e3, n / dt / 1e6, m.work()["launches"]), flush=True)
     del m

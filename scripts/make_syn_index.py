@@ -1,12 +1,12 @@
 """Builds a synthetic multi-contig genome (i.i.d. bases + injected repeat families, SURVEY.md Appendix B pilot, scaled) and
-indexes it with the reference's own bwt_index (oracle/_ref). Usage: python scripts/make_syn_index.py <Mbp> [contigs] [seed]
+indexes it with the reference's own bwt_index (oracle/_ref). Usage: python scripts/make_syn_index.py <Mbp> [contigs] [seed] [outdir]
 Output: data/_gen/syn/syn<Mbp>.{fa,bwt,sa,pac,ann,amb} (git-ignored; travels to the GPU box with the snapshot)."""
 import os, subprocess, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from kart_b200 import synth
 mbp = int(sys.argv[1]); contigs = int(sys.argv[2]) if len(sys.argv) > 2 else 4; seed = int(sys.argv[3]) if len(sys.argv) > 3 else 12345
-out = os.path.join(ROOT, "data", "_gen", "syn"); os.makedirs(out, exist_ok=True)
+out = sys.argv[4] if len(sys.argv) > 4 else os.path.join(ROOT, "data", "_gen", "syn"); os.makedirs(out, exist_ok=True)
 prefix = os.path.join(out, "syn%d" % mbp)
 t = time.time()
 scale = mbp / 100.0

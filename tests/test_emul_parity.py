@@ -189,8 +189,10 @@ def test_cli_argument_errors(kart_emul):
     assert r.returncode == 0 and r.stdout.startswith("kart v2.5.6")
 
 
-def test_pipelined_chunk_equals_single_batch(mini, monkeypatch):
-    """kb_map_chunk streams large chunks through two slots (sub-batches, chunk-wide cigar arena): same records as one batch."""
+@pytest.mark.parametrize("plan", [{}, {"KB_PIPE_FIRST": "60", "KB_PIPE_GROW": "150", "KB_PIPE_TAIL": "80"}])
+def test_pipelined_chunk_equals_single_batch(mini, monkeypatch, plan):
+    """kb_map_chunk streams large chunks through the slots (uniform or ramped sub-batches, chunk-wide cigar arena copied back
+    range by range): same records as one batch."""
     idx, g = mini
     r1, r2, _ = synth.simulate(g, 700, 150, 0.04, seed=41, indel=0.004, n_rate=0.002)
     reads = pu.interleave(r1, r2)
@@ -201,6 +203,8 @@ def test_pipelined_chunk_equals_single_batch(mini, monkeypatch):
     a0, p0, c0 = m0.map_chunk(flat, off, est)
     monkeypatch.setenv("KB_PIPE_MIN_READS", "64")
     monkeypatch.setenv("KB_PIPE_SUB_READS", "250")
+    for k, v in plan.items():
+        monkeypatch.setenv(k, v)
     m1 = pu.make_mapper(idx, emul=True, paired=True)
     a1, p1, c1 = m1.map_chunk(flat, off, est)
     assert m1.work()["launches"] > 3 * m0.work()["launches"]          # really went through several sub-batches

@@ -109,9 +109,11 @@ def test_multi_contig_paired_with_rescue(built):
     assert m.work()["rescues"] > 0
 
 
-def test_pipelined_chunk_full_size_equals_single_batch(eco, monkeypatch):
-    """C2 at size: 400k reads through kb_map_chunk's two-slot pipeline (sub-batches of 65536) and as one resident batch
-    give the same records (the single-batch path is the one the oracle checks read by read above)."""
+@pytest.mark.parametrize("plan", [{"KB_PIPE_SUB_READS": "65536"}, {"KB_PIPE_SUB_READS": "100000", "KB_PIPE_FIRST": "8192", "KB_PIPE_GROW": "150", "KB_PIPE_TAIL": "8192"}])
+def test_pipelined_chunk_full_size_equals_single_batch(eco, monkeypatch, plan):
+    """C2 at size: 400k reads through kb_map_chunk's slot pipeline (uniform sub-batches of 65536, or a ramped plan; cigar ranges
+    copied back as sub-batches retire) and as one resident batch give the same records (the single-batch path is the one the
+    oracle checks read by read above)."""
     idx, g, prefix = eco
     r1, r2, _ = synth.simulate(g, 200000, 150, 0.02, seed=77, indel=0.001)
     flat, off = Mapper.pack_reads(pu.interleave(r1, r2))
@@ -120,10 +122,11 @@ def test_pipelined_chunk_full_size_equals_single_batch(eco, monkeypatch):
     m0 = pu.make_mapper(idx, expand_sa=True, paired=True)
     a0, p0, c0 = m0.map_chunk(flat, off, est)
     monkeypatch.setenv("KB_PIPE_MIN_READS", "1000")
-    monkeypatch.setenv("KB_PIPE_SUB_READS", "65536")
+    for k, v in plan.items():
+        monkeypatch.setenv(k, v)
     m1 = pu.make_mapper(idx, expand_sa=True, paired=True)
     a1, p1, c1 = m1.map_chunk(flat, off, est)
-    assert m1.work()["launches"] >= 7 * 11
+    assert m1.work()["launches"] >= 5 * 19
     for f in ("pos", "mate_pos", "kind", "flag", "chr", "mapq", "score", "sub_score", "tlen", "fwd", "cig_len"):
         assert np.array_equal(a0[f], a1[f]), f
     assert np.array_equal(p0, p1)
