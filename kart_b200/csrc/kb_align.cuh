@@ -448,10 +448,10 @@ KB_HD KbWorkP kb_work_pack(const KbWork& w) { KbWorkP p; p.r0 = w.r0; p.rl = w.r
 KB_HD KbWork kb_work_unpack(const KbWorkP& p) { KbWork w; w.r0 = p.r0; w.rl = p.rl; w.g0 = p.g0; w.gl = (i32)(p.glk & 0x0FFFFFFFu); w.kind = (i32)(p.glk >> 28); w.pad = 0; return w; }
 
 // nw_alignment size class of an (rl x gl) problem at text position g
-KB_HD u32 kb_piece_class(const KbIndexDev& ix, int rl, int gl, i64 g)
+KB_HD u32 kb_piece_class(const KbIndexDev& ix, const KbBatchDev& bt, int rl, int gl, i64 g)
 {
 	const int mx = rl > gl ? rl : gl;
-	if (mx > KB_NW_TMAX || g < 0 || g + gl > ix.G2) return (u32)(KB_NW_CLASSES - 1);   // too large for one thread, or touching the outside of the text
+	if (mx > bt.nw_tmax || g < 0 || g + gl > ix.G2) return (u32)(KB_NW_CLASSES - 1);   // too large for one thread, or touching the outside of the text
 	return mx <= 32 ? (u32)((mx - 1) >> 3) : (mx <= 64 ? 4u : 5u);
 }
 // registers one nw_alignment problem; false when the piece arena is full (flagged)
@@ -461,7 +461,7 @@ KB_HD bool kb_emit_piece(const KbIndexDev& ix, const KbBatchDev& bt, u32 job, i6
 	if (id >= bt.cap_pieces) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_JOBS); return false; }
 	KbPiece pc; pc.job = job; pc.r0 = r0; pc.rl = rl; pc.g0 = g0; pc.gl = gl; pc.out_off = out_off; pc.whole = whole; pc.pad = 0;
 	bt.pieces[id] = pc;
-	const u32 cls = kb_piece_class(ix, rl, gl, job_gpos + g0);
+	const u32 cls = kb_piece_class(ix, bt, rl, gl, job_gpos + g0);
 	const u32 slot = KB_ALLOC_KEYED(&bt.counters[16 + cls], 1u);
 	bt.piece_list[(size_t)cls * bt.cap_pieces + slot] = id;
 	return true;

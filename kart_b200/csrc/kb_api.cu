@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(KB_BLOCK) k_rescue(KbIndexDev ix, KbParams pm,
 	__shared__ KbRescueJob sj;
 	if (bt.counters[3]) return;
 	const int count = (int)bt.counters[4], tid = threadIdx.x, nth = blockDim.x;
-	KbRescueJob* j = &sj; KbArena ar = kb_job_arena(bt, blockIdx.x);
+	KbRescueJob* j = &sj; KbArena ar = kb_job_arena(bt, blockIdx.x, blockDim.x);
 	for (int k = blockIdx.x; k < count; k += gridDim.x)
 	{
 		if (tid == 0) { ar.used = 0; ar.ovf = false; kb_rj_begin(pm, bt, j, ar, k); }
@@ -148,7 +148,7 @@ static void k_rescue(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulation: 
 	if (blockIdx.x != 0 || threadIdx.x != 0) return;
 	if (bt.counters[3]) return;
 	int count = (int)bt.counters[4], nth = KB_BLOCK;
-	static KbRescueJob job; KbRescueJob* j = &job; KbArena ar = kb_job_arena(bt, 0);
+	static KbRescueJob job; KbRescueJob* j = &job; KbArena ar = kb_job_arena(bt, 0, blockDim.x); nth = (int)blockDim.x;
 	for (int k = 0; k < count; k++)
 	{
 		ar.used = 0; ar.ovf = false;
@@ -170,20 +170,30 @@ __global__ void __launch_bounds__(KB_BLOCK) k_segments(KbIndexDev ix, KbParams p
 __global__ void __launch_bounds__(KB_BLOCK) k_segments_slow(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_segments_slow(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
 // phase B (kb_align.cuh "phase B"): partition -> nw_alignment problems by size class -> gather
 #ifndef KB_EMUL
-__global__ void __launch_bounds__(KB_BLOCK) k_align_part(KbIndexDev ix, KbParams pm, KbBatchDev bt)
+// One warp per partition job. A job is a chain of short phases with global-memory latency in between (ALU pipe ~11 %, ncu
+// r13), so throughput is the number of jobs in flight: the per-warp shared-memory pool is sized at launch (pool_bytes; what does
+// not fit spills to the warp's HBM arena) to trade pool size against resident warps, and warps draw jobs from a ticket counter
+// so that no SM is left holding a static share of long jobs.
+__global__ void __launch_bounds__(KB_BLOCK) k_align_part(KbIndexDev ix, KbParams pm, KbBatchDev bt, int pool_bytes)
 {
 	__shared__ KbPartWarp sw[KB_BLOCK / 32];
-	__shared__ __align__(16) u8 pool[KB_BLOCK / 32][KB_ALIGN_POOL];
+	__shared__ u32 ticket[KB_BLOCK / 32];
+	extern __shared__ __align__(16) u8 dyn_pool[];
 	if (bt.counters[3]) return;
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-	const u32 gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+	const u32 gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if ((int)gwarp >= bt.wscratch_warps) return;
 	KbPartWarp& w = sw[wib];
 	const u32 njobs = bt.counters[23];
-	if (lane == 0) { w.ar.base = bt.wscratch + (u64)gwarp * bt.wscratch_per_warp; w.ar.cap = bt.wscratch_per_warp; w.fast.base = pool[wib]; w.fast.cap = KB_ALIGN_POOL; w.fast.ovf = false; }
+	if (lane == 0) { w.ar.base = bt.wscratch + (u64)gwarp * bt.wscratch_per_warp; w.ar.cap = bt.wscratch_per_warp; w.fast.base = dyn_pool + (size_t)wib * (size_t)pool_bytes; w.fast.cap = (u64)pool_bytes; w.fast.ovf = false; }
 	__syncwarp();
-	for (u32 q = gwarp; q < njobs; q += nwarps)
+	while (true)
 	{
+		if (lane == 0) ticket[wib] = atomicAdd(&bt.counters[26], 1u);
+		__syncwarp();
+		const u32 q = ticket[wib];
+		__syncwarp();
+		if (q >= njobs) break;
 		if (lane == 0) kb_pt_begin(ix, pm, bt, w, bt.part_list[q]);
 		__syncwarp();
 		kb_pt_fetch(ix, bt, w, lane);
@@ -244,7 +254,7 @@ __global__ void __launch_bounds__(KB_BLOCK) k_nw_warp(KbIndexDev ix, KbParams pm
 	if (lane == 0) { if (w.cells) atomicAdd(&bt.work[3], w.cells); if (w.calls) atomicAdd(&bt.work[4], (unsigned long long)w.calls); }
 }
 #else
-static void k_align_part(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulation: the same phases, a warp = a loop over 32 lanes
+static void k_align_part(KbIndexDev ix, KbParams pm, KbBatchDev bt, int)   // emulation: the same phases, a warp = a loop over 32 lanes
 {
 	if (blockIdx.x != 0 || threadIdx.x != 0) return;
 	if (bt.counters[3]) return;
@@ -368,7 +378,11 @@ struct kb_ctx
 	cudaEvent_t chunk_start = nullptr; int trace = 0;
 	int seed_minb = 10;
 	int nw_streams = 1;          // 1: the size-class kernels of phase B are forked onto the slot's aux streams and joined before the gather
-	int align_warps = KB_ALIGN_WARPS;
+	int align_warps = KB_ALIGN_WARPS;   // k_nw_warp
+	int part_warps = 148 * 40, part_pool = 4096;   // k_align_part: warps in the grid (each with an HBM arena) and shared-memory pool bytes per warp (r14 A/B: 8 warps/SM + 10 KB pool 2.34 ms -> 40 warps/SM + 4 KB 1.34 ms for the align stage at C2)
+	int nw_tmax = 0;             // 0: 128 for -pacbio (many large problems: throughput), 32 otherwise (a handful of 33..128 problems per million reads,
+	                             // each a single thread's 0.2-0.3 ms chain on the align stage's critical path: the warp kernel does them in microseconds)
+	int rescue_threads = 128;    // block size of k_rescue (32, 64 or 128; measured r14: 128 best on C2, 64/128 equal on the 100 Mbp index -- the kernel is bound by its longest jobs, not by jobs in flight)
 	int pipe_min_reads = 262144, pipe_sub_reads = 0;   // chunks of at least pipe_min_reads go through the slot pipeline
 	int pipe_first = 0, pipe_grow = 200, pipe_tail = 0;   // sub-batch plan: first size, growth (percent), floor of the halving tail (0: uniform)
 	cudaStream_t copy_stream = nullptr;                   // D2H of each sub-batch's cigar range, in retirement order
@@ -430,14 +444,18 @@ int kb_init(int device, kb_ctx_t** out)
 	}
 	cudaEventCreate(&ctx->chunk_start); ctx->trace = getenv("KB_PIPE_TRACE") ? 1 : 0;
 	const char* e = getenv("KB_PIPE_MIN_READS"); if (e && atoi(e) > 0) ctx->pipe_min_reads = atoi(e);
-	e = getenv("KB_SEED_MINB"); if (e && atoi(e) == 8) ctx->seed_minb = 8;
+	e = getenv("KB_SEED_MINB"); if (e && (atoi(e) == 8 || atoi(e) == 12 || atoi(e) == 16)) ctx->seed_minb = atoi(e);
 	e = getenv("KB_PIPE_SUB_READS"); if (e && atoi(e) > 0) ctx->pipe_sub_reads = atoi(e);
+	e = getenv("KB_RESCUE_THREADS"); if (e && (atoi(e) == 32 || atoi(e) == 64 || atoi(e) == 128)) ctx->rescue_threads = atoi(e);
 	e = getenv("KB_PIPE_FIRST"); if (e && atoi(e) >= 0) ctx->pipe_first = atoi(e);
 	e = getenv("KB_PIPE_GROW"); if (e && atoi(e) >= 100) ctx->pipe_grow = atoi(e);
 	e = getenv("KB_PIPE_TAIL"); if (e && atoi(e) >= 0) ctx->pipe_tail = atoi(e);
 	if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return KB_ECUDA; }
 	e = getenv("KB_NW_STREAMS"); if (e) ctx->nw_streams = atoi(e) ? 1 : 0;
 	e = getenv("KB_ALIGN_WARPS"); if (e && atoi(e) >= 148 && atoi(e) <= 148 * 64) ctx->align_warps = atoi(e) / 4 * 4;
+	e = getenv("KB_NW_TMAX"); if (e && (atoi(e) == 32 || atoi(e) == 64 || atoi(e) == 128)) ctx->nw_tmax = atoi(e);
+	e = getenv("KB_PART_WARPS"); if (e && atoi(e) >= 148 && atoi(e) <= 148 * 64) ctx->part_warps = atoi(e) / 4 * 4;
+	e = getenv("KB_PART_POOL"); if (e && atoi(e) >= 1024 && atoi(e) <= 11264) ctx->part_pool = atoi(e) / 16 * 16;
 	*out = ctx;
 	return KB_OK;
 }
@@ -615,7 +633,7 @@ static int alloc_batch(kb_ctx* ctx, kb_slot& sl, int shared)
 	threads = (threads + KB_BLOCK - 1) / KB_BLOCK * KB_BLOCK; if (threads < KB_BLOCK) threads = KB_BLOCK;
 	sl.scratch_per_thread = per; sl.scratch_threads = (int)threads;
 	// the warp-per-job kernels get their own arenas (one worst-case problem each), independent of the number of reads
-	const int wwarps = ctx->align_warps;
+	const int wwarps = ctx->align_warps > ctx->part_warps ? ctx->align_warps : ctx->part_warps;
 	CK(sl.hits.ensure(n * max_hits)); CK(sl.n_hits.ensure(n)); CK(sl.n_seeds.ensure(n)); CK(sl.seed_off.ensure(n));
 	CK(sl.segs.ensure(sl.cap_segs)); CK(sl.cands.ensure(sl.cap_cands)); CK(sl.reports.ensure(sl.cap_cands));
 	CK(sl.n_cands.ensure(n)); CK(sl.cand_off.ensure(n)); CK(sl.cand_cap.ensure(n)); CK(sl.rescue.ensure(n / 2 + 1));
@@ -638,7 +656,7 @@ static int alloc_batch(kb_ctx* ctx, kb_slot& sl, int shared)
 	else { bt.cigar = sl.cigar.p; bt.cap_cigar = (u32)sl.cap_cigar; bt.cig_cursor = sl.counters.p + 2; }
 	bt.scratch = sl.scratch.p; bt.scratch_per_thread = per; bt.scratch_threads = (int)threads;
 	bt.wscratch = sl.wscratch.p; bt.wscratch_per_warp = per; bt.wscratch_warps = wwarps;
-	bt.max_rlen = L; bt.nw_max_m = 0; bt.nw_max_n = 0; bt.seg_cap = 0; bt.kmer_cap = 0; bt.counters = sl.counters.p; bt.work = sl.work.p;
+	bt.max_rlen = L; bt.nw_tmax = ctx->nw_tmax > 0 ? ctx->nw_tmax : (ctx->pm.pacbio ? KB_NW_TMAX : 32); bt.nw_max_n = 0; bt.seg_cap = 0; bt.kmer_cap = 0; bt.counters = sl.counters.p; bt.work = sl.work.p;
 	return KB_OK;
 }
 
@@ -681,13 +699,15 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 	unsigned g_reads = (unsigned)((n + KB_BLOCK - 1) / KB_BLOCK);
 	unsigned g_items = pm.paired ? (unsigned)((n / 2 + KB_BLOCK - 1) / KB_BLOCK) : g_reads;
 	unsigned g_hits = (unsigned)(((long long)n * bt.max_hits + KB_BLOCK - 1) / KB_BLOCK);
-	unsigned g_scr = (unsigned)(bt.scratch_threads / KB_BLOCK);
-	unsigned g_warp = (unsigned)(bt.wscratch_warps * 32 / KB_BLOCK);
+	unsigned g_warp = (unsigned)(ctx->align_warps * 32 / KB_BLOCK);
 	unsigned g_slow = g_reads < 148u * 16u ? g_reads : 148u * 16u;   // arena kernels: one thread per read up to a full machine, slices cut on the device
 	sl.launches = 0;
 	CK(cudaEventRecord(sl.ev[0], s));
 	KB_LAUNCH(k_pack, (unsigned)(((long long)n * bt.pk_wpr + KB_BLOCK - 1) / KB_BLOCK), KB_BLOCK, s, bt); sl.launches++;
-	if (ctx->seed_minb == 8) { KB_LAUNCH(k_fm_seed<8>, g_reads, KB_BLOCK, s, ix, pm, bt); } else { KB_LAUNCH(k_fm_seed<10>, g_reads, KB_BLOCK, s, ix, pm, bt); }
+	if (ctx->seed_minb == 8) { KB_LAUNCH(k_fm_seed<8>, g_reads, KB_BLOCK, s, ix, pm, bt); }
+	else if (ctx->seed_minb == 12) { KB_LAUNCH(k_fm_seed<12>, g_reads, KB_BLOCK, s, ix, pm, bt); }
+	else if (ctx->seed_minb == 16) { KB_LAUNCH(k_fm_seed<16>, g_reads, KB_BLOCK, s, ix, pm, bt); }
+	else { KB_LAUNCH(k_fm_seed<10>, g_reads, KB_BLOCK, s, ix, pm, bt); }
 	sl.launches++;
 	CK(cudaEventRecord(sl.ev[1], s));
 	KB_LAUNCH(k_sa_locate, g_hits, KB_BLOCK, s, ix, bt); sl.launches++;
@@ -695,12 +715,22 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 	KB_LAUNCH(k_cand_pair, g_items, KB_BLOCK, s, ix, pm, bt); sl.launches++;
 	if (pm.pacbio) { KB_LAUNCH(k_cand_pacbio, g_slow, KB_BLOCK, s, ix, pm, bt); sl.launches++; }
 	CK(cudaEventRecord(sl.ev[3], s));
-	if (pm.paired) { KB_LAUNCH(k_rescue, g_scr, KB_BLOCK, s, ix, pm, bt); sl.launches++; }
+	// one block per rescue job (block size is a knob: KB_RESCUE_THREADS)
+	if (pm.paired)
+	{
+		unsigned rt = (unsigned)ctx->rescue_threads, g = (unsigned)bt.scratch_threads / rt; if (g > 148u * 32u) g = 148u * 32u;
+		KB_LAUNCH(k_rescue, g, rt, s, ix, pm, bt); sl.launches++;
+	}
 	CK(cudaEventRecord(sl.ev[4], s));
 	KB_LAUNCH(k_segments, g_reads, KB_BLOCK, s, ix, pm, bt); sl.launches++;
 	KB_LAUNCH(k_segments_slow, g_slow, KB_BLOCK, s, ix, pm, bt); sl.launches++;
 	CK(cudaEventRecord(sl.ev[5], s));
-	KB_LAUNCH(k_align_part, g_warp, KB_BLOCK, s, ix, pm, bt); sl.launches++;
+#ifndef KB_EMUL
+	k_align_part<<<(unsigned)(ctx->part_warps * 32 / KB_BLOCK), KB_BLOCK, (size_t)(KB_BLOCK / 32) * (size_t)ctx->part_pool, s>>>(ix, pm, bt, ctx->part_pool);
+#else
+	KB_LAUNCH(k_align_part, g_warp, KB_BLOCK, s, ix, pm, bt, ctx->part_pool);
+#endif
+	sl.launches++;
 	// The size classes are independent and each is latency-bound on its own (one problem per thread: a launch lasts as long as
 	// its longest chain of cells), so they run side by side on the slot's aux streams, heaviest first, and join before the gather.
 	{

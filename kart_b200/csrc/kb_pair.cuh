@@ -49,9 +49,9 @@ struct KbRescueJob
 	const u8* mate; const KbPk* mate_pk;
 };
 
-KB_HD KbArena kb_job_arena(const KbBatchDev& bt, int block)
+KB_HD KbArena kb_job_arena(const KbBatchDev& bt, int block, int nth)   // the block's share of the per-thread scratch
 {
-	KbArena ar; u64 per = bt.scratch_per_thread * 128ull;
+	KbArena ar; u64 per = bt.scratch_per_thread * (u64)nth;
 	ar.base = bt.scratch + (u64)block * per; ar.used = 0; ar.cap = per; ar.ovf = false;
 	return ar;
 }

@@ -47,19 +47,26 @@ def test_pacbio_long_reads(mini):
     assert pu.compare_singles(m, pu.Oracle(pu.MINI_PREFIX, pacbio=True), r) == 0
 
 
-def test_all_nw_size_classes(mini):
+def test_all_nw_size_classes(mini, monkeypatch):
     """Every nw_alignment size class (register tiles <= 8/16/24/32, column tiles <= 64/128, warp wavefront) against the oracle."""
     idx, g = mini
     reads = pu.big_gap_reads(g)
     seen = np.zeros(7, dtype=np.int64)
-    for pac in (True, False):
+    # the thread-per-problem limit is 32 for short reads and 128 for -pacbio (KB_NW_TMAX overrides): cover every kernel in both regimes
+    for pac, tmax in ((True, None), (False, None), (False, "128"), (True, "32")):
+        if tmax:
+            monkeypatch.setenv("KB_NW_TMAX", tmax)
         m = pu.make_mapper(idx, emul=True, pacbio=pac)
         assert pu.compare_singles(m, pu.Oracle(pu.MINI_PREFIX, pacbio=pac), reads) == 0
         seen += m.debug(9, np.uint32, 32)[16:23]
+        monkeypatch.delenv("KB_NW_TMAX", raising=False)
     r, _, _ = synth.simulate(g, 300, 100, 0.08, seed=35, paired=False, indel=0.003)
-    m = pu.make_mapper(idx, emul=True, paired=False)
-    assert pu.compare_singles(m, pu.Oracle(pu.MINI_PREFIX), r) == 0
-    seen += m.debug(9, np.uint32, 32)[16:23]
+    for tmax in (None, "128"):
+        if tmax:
+            monkeypatch.setenv("KB_NW_TMAX", tmax)
+        m = pu.make_mapper(idx, emul=True, paired=False)
+        assert pu.compare_singles(m, pu.Oracle(pu.MINI_PREFIX), r) == 0
+        seen += m.debug(9, np.uint32, 32)[16:23]
     assert (seen > 0).all(), seen
 
 
