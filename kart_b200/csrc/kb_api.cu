@@ -222,10 +222,15 @@ __global__ void __launch_bounds__(KB_BLOCK) k_nw_warp(KbIndexDev ix, KbParams pm
 	const u32 gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
 	if ((int)gwarp >= bt.wscratch_warps) return;
 	KbPieceWarp& w = sw[wib];
-	const int cls = KB_NW_CLASSES - 1;
-	const u32 count = bt.counters[16 + cls]; const u32* list = bt.piece_list + (size_t)cls * bt.cap_pieces;
 	if (lane == 0) { w.ar.base = bt.wscratch + (u64)gwarp * bt.wscratch_per_warp; w.ar.cap = bt.wscratch_per_warp; w.fast.base = pool[wib]; w.fast.cap = KB_ALIGN_POOL; w.fast.ovf = false; w.cells = 0; w.calls = 0; }
 	__syncwarp();
+	// the wavefront class, plus a column-tile class (33..64, 65..128) when it holds too few problems to fill the machine with
+	// one thread each: such a launch lasts as long as one thread's DP over a whole problem (0.2-0.3 ms, ncu r13), a warp does
+	// the same problem in microseconds. k_nw_tile<4|5> steps aside on the same test.
+	for (int cls = 4; cls < KB_NW_CLASSES; cls++)
+	{
+	const u32 count = bt.counters[16 + cls]; const u32* list = bt.piece_list + (size_t)cls * bt.cap_pieces;
+	if (cls < KB_NW_CLASSES - 1 && count >= (u32)bt.nw_warp_below) continue;
 	for (u32 q = gwarp; q < count; q += nwarps)
 	{
 		if (lane == 0) kb_pw_begin(bt, w, list[q]);
@@ -250,6 +255,7 @@ __global__ void __launch_bounds__(KB_BLOCK) k_nw_warp(KbIndexDev ix, KbParams pm
 		}
 		if (lane == 0) kb_pw_end(bt, w);
 		__syncwarp();
+	}
 	}
 	if (lane == 0) { if (w.cells) atomicAdd(&bt.work[3], w.cells); if (w.calls) atomicAdd(&bt.work[4], (unsigned long long)w.calls); }
 }
@@ -283,8 +289,10 @@ static void k_nw_warp(KbIndexDev ix, KbParams pm, KbBatchDev bt)
 	if (bt.counters[3]) return;
 	static KbPieceWarp w; KbNwLane L[32]; static u8 pool[KB_ALIGN_POOL];
 	w.ar.base = bt.wscratch; w.ar.cap = bt.wscratch_per_warp; w.fast.base = pool; w.fast.cap = KB_ALIGN_POOL; w.fast.ovf = false; w.cells = 0; w.calls = 0;
-	const int cls = KB_NW_CLASSES - 1;
+	for (int cls = 4; cls < KB_NW_CLASSES; cls++)
+	{
 	const u32 count = bt.counters[16 + cls]; const u32* list = bt.piece_list + (size_t)cls * bt.cap_pieces;
+	if (cls < KB_NW_CLASSES - 1 && count >= (u32)bt.nw_warp_below) continue;
 	for (u32 q = 0; q < count; q++)
 	{
 		kb_pw_begin(bt, w, list[q]);
@@ -303,6 +311,7 @@ static void k_nw_warp(KbIndexDev ix, KbParams pm, KbBatchDev bt)
 		}
 		kb_pw_end(bt, w);
 	}
+	}
 	bt.work[3] += w.cells; bt.work[4] += w.calls;
 }
 #endif
@@ -311,6 +320,7 @@ template <int CLS, int TW, int MAXM, int MAXT>
 __global__ void __launch_bounds__(KB_BLOCK) k_nw_tile(KbIndexDev ix, KbParams pm, KbBatchDev bt)
 {
 	if (bt.counters[3]) return;
+	if (CLS >= 4 && bt.counters[16 + CLS] < (u32)bt.nw_warp_below) return;   // k_nw_warp takes a sparse class
 	unsigned long long cells = 0, calls = 0;
 	kb_nwt_class<TW, MAXM, MAXT>(ix, bt, CLS, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, &cells, &calls);
 	kb_warp_add64(&bt.work[3], cells); kb_warp_add64(&bt.work[4], calls);
@@ -380,8 +390,8 @@ struct kb_ctx
 	int nw_streams = 1;          // 1: the size-class kernels of phase B are forked onto the slot's aux streams and joined before the gather
 	int align_warps = KB_ALIGN_WARPS;   // k_nw_warp
 	int part_warps = 148 * 40, part_pool = 4096;   // k_align_part: warps in the grid (each with an HBM arena) and shared-memory pool bytes per warp (r14 A/B: 8 warps/SM + 10 KB pool 2.34 ms -> 40 warps/SM + 4 KB 1.34 ms for the align stage at C2)
-	int nw_tmax = 0;             // 0: 128 for -pacbio (many large problems: throughput), 32 otherwise (a handful of 33..128 problems per million reads,
-	                             // each a single thread's 0.2-0.3 ms chain on the align stage's critical path: the warp kernel does them in microseconds)
+	int nw_tmax = 0;             // largest side one thread solves (0: KB_NW_TMAX); KB_NW_TMAX=32|64 sends more to the wavefront kernel
+	int nw_warp_below = 8192;    // a column-tile class (33..64, 65..128) with fewer problems than this is solved by k_nw_warp instead
 	int rescue_threads = 128;    // block size of k_rescue (32, 64 or 128; measured r14: 128 best on C2, 64/128 equal on the 100 Mbp index -- the kernel is bound by its longest jobs, not by jobs in flight)
 	int pipe_min_reads = 262144, pipe_sub_reads = 0;   // chunks of at least pipe_min_reads go through the slot pipeline
 	int pipe_first = 0, pipe_grow = 200, pipe_tail = 0;   // sub-batch plan: first size, growth (percent), floor of the halving tail (0: uniform)
@@ -454,6 +464,7 @@ int kb_init(int device, kb_ctx_t** out)
 	e = getenv("KB_NW_STREAMS"); if (e) ctx->nw_streams = atoi(e) ? 1 : 0;
 	e = getenv("KB_ALIGN_WARPS"); if (e && atoi(e) >= 148 && atoi(e) <= 148 * 64) ctx->align_warps = atoi(e) / 4 * 4;
 	e = getenv("KB_NW_TMAX"); if (e && (atoi(e) == 32 || atoi(e) == 64 || atoi(e) == 128)) ctx->nw_tmax = atoi(e);
+	e = getenv("KB_NW_WARP_BELOW"); if (e && atoi(e) >= 0) ctx->nw_warp_below = atoi(e);
 	e = getenv("KB_PART_WARPS"); if (e && atoi(e) >= 148 && atoi(e) <= 148 * 64) ctx->part_warps = atoi(e) / 4 * 4;
 	e = getenv("KB_PART_POOL"); if (e && atoi(e) >= 1024 && atoi(e) <= 11264) ctx->part_pool = atoi(e) / 16 * 16;
 	*out = ctx;
@@ -656,7 +667,7 @@ static int alloc_batch(kb_ctx* ctx, kb_slot& sl, int shared)
 	else { bt.cigar = sl.cigar.p; bt.cap_cigar = (u32)sl.cap_cigar; bt.cig_cursor = sl.counters.p + 2; }
 	bt.scratch = sl.scratch.p; bt.scratch_per_thread = per; bt.scratch_threads = (int)threads;
 	bt.wscratch = sl.wscratch.p; bt.wscratch_per_warp = per; bt.wscratch_warps = wwarps;
-	bt.max_rlen = L; bt.nw_tmax = ctx->nw_tmax > 0 ? ctx->nw_tmax : (ctx->pm.pacbio ? KB_NW_TMAX : 32); bt.nw_max_n = 0; bt.seg_cap = 0; bt.kmer_cap = 0; bt.counters = sl.counters.p; bt.work = sl.work.p;
+	bt.max_rlen = L; bt.nw_tmax = ctx->nw_tmax > 0 ? ctx->nw_tmax : KB_NW_TMAX; bt.nw_warp_below = ctx->nw_warp_below; bt.seg_cap = 0; bt.kmer_cap = 0; bt.counters = sl.counters.p; bt.work = sl.work.p;
 	return KB_OK;
 }
 

@@ -125,7 +125,8 @@ struct KbBatchDev
 	u8* wscratch; u64 wscratch_per_warp; i32 wscratch_warps;   // arenas of the warp-per-job kernels (k_align_part, k_nw_warp)
 	i32 max_rlen;                       // longest read in the batch
 	i32 nw_tmax;                        // largest side one thread solves (<= KB_NW_TMAX); larger problems go to the warp wavefront kernel
-	i32 nw_max_n, seg_cap, kmer_cap;
+	i32 nw_warp_below;                  // a column-tile class with fewer problems than this goes to the warp wavefront kernel as well
+	i32 seg_cap, kmer_cap;
 	// counters: [0] seeds cursor [1] cands cursor [2] cigar cursor [3] status bits [4] rescue count [5] max seeds/read
 	//           [6] nw calls [7] rescue attempts [8] segx cursor [10] run cursor + [11] job cursor (one u64) [12],[13] slow lists [14] extra-line cursor (-m)
 	//           [16..22] pieces per size class [23] partition jobs [24] piece cursor [26] k_align_part job tickets

@@ -52,18 +52,20 @@ def test_all_nw_size_classes(mini, monkeypatch):
     idx, g = mini
     reads = pu.big_gap_reads(g)
     seen = np.zeros(7, dtype=np.int64)
-    # the thread-per-problem limit is 32 for short reads and 128 for -pacbio (KB_NW_TMAX overrides): cover every kernel in both regimes
-    for pac, tmax in ((True, None), (False, None), (False, "128"), (True, "32")):
-        if tmax:
-            monkeypatch.setenv("KB_NW_TMAX", tmax)
+    # sparse column-tile classes (33..128) are solved by the warp kernel (KB_NW_WARP_BELOW), KB_NW_TMAX moves the thread limit:
+    # cover every kernel on the same problems
+    for pac, env in ((True, {}), (False, {}), (False, {"KB_NW_WARP_BELOW": "0"}), (True, {"KB_NW_WARP_BELOW": "0"}), (True, {"KB_NW_TMAX": "32"})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
         m = pu.make_mapper(idx, emul=True, pacbio=pac)
         assert pu.compare_singles(m, pu.Oracle(pu.MINI_PREFIX, pacbio=pac), reads) == 0
         seen += m.debug(9, np.uint32, 32)[16:23]
-        monkeypatch.delenv("KB_NW_TMAX", raising=False)
+        for k in env:
+            monkeypatch.delenv(k)
     r, _, _ = synth.simulate(g, 300, 100, 0.08, seed=35, paired=False, indel=0.003)
-    for tmax in (None, "128"):
-        if tmax:
-            monkeypatch.setenv("KB_NW_TMAX", tmax)
+    for below in (None, "0"):
+        if below:
+            monkeypatch.setenv("KB_NW_WARP_BELOW", below)
         m = pu.make_mapper(idx, emul=True, paired=False)
         assert pu.compare_singles(m, pu.Oracle(pu.MINI_PREFIX), r) == 0
         seen += m.debug(9, np.uint32, 32)[16:23]
