@@ -56,12 +56,13 @@ __global__ void k_ref64(const u8* pac, u64 bytes, u64 words, u64* out)
 
 // MINB = resident blocks per SM the register allocation is tuned for: 10 (48 registers, more loads in flight: HBM-sized indexes)
 // or 8 (64 registers, no spills: L2-resident indexes, where the kernel is ALU-bound)
-template <int MINB>
+// ROW = u32 when every BWT row number fits 32 bits (kb_extend), u64 for the multi-Gbp indexes
+template <int MINB, class ROW>
 __global__ void __launch_bounds__(KB_BLOCK, MINB) k_fm_seed(KbIndexDev ix, KbParams pm, KbBatchDev bt)
 {
 	int r = blockIdx.x * blockDim.x + threadIdx.x;
 	u32 steps = 0, blocks = 0;
-	kb_seed_read(ix, pm, bt, r, r < bt.n_reads, &steps, &blocks);
+	kb_seed_read<ROW>(ix, pm, bt, r, r < bt.n_reads, &steps, &blocks);
 	kb_warp_add64(&bt.work[0], steps); kb_warp_add64(&bt.work[1], blocks);
 }
 
@@ -387,6 +388,7 @@ struct kb_ctx
 	float stage_ms[9]; uint64_t work_host[8]; u32 counters_host[KB_NCOUNTERS];
 	cudaEvent_t chunk_start = nullptr; int trace = 0;
 	int seed_minb = 10;
+	bool row32 = false;          // BWT row numbers fit 32 bits: k_fm_seed<.., u32> (set at index upload; KB_ROW64=1 forces the 64-bit kernel)
 	int nw_streams = 1;          // 1: the size-class kernels of phase B are forked onto the slot's aux streams and joined before the gather
 	int align_warps = KB_ALIGN_WARPS;   // k_nw_warp
 	int part_warps = 148 * 40, part_pool = 4096;   // k_align_part: warps in the grid (each with an HBM arena) and shared-memory pool bytes per warp (r14 A/B: 8 warps/SM + 10 KB pool 2.34 ms -> 40 warps/SM + 4 KB 1.34 ms for the align stage at C2)
@@ -454,7 +456,7 @@ int kb_init(int device, kb_ctx_t** out)
 	}
 	cudaEventCreate(&ctx->chunk_start); ctx->trace = getenv("KB_PIPE_TRACE") ? 1 : 0;
 	const char* e = getenv("KB_PIPE_MIN_READS"); if (e && atoi(e) > 0) ctx->pipe_min_reads = atoi(e);
-	e = getenv("KB_SEED_MINB"); if (e && (atoi(e) == 8 || atoi(e) == 12 || atoi(e) == 16)) ctx->seed_minb = atoi(e);
+	e = getenv("KB_SEED_MINB"); if (e && (atoi(e) == 8 || atoi(e) == 12)) ctx->seed_minb = atoi(e);
 	e = getenv("KB_PIPE_SUB_READS"); if (e && atoi(e) > 0) ctx->pipe_sub_reads = atoi(e);
 	e = getenv("KB_RESCUE_THREADS"); if (e && (atoi(e) == 32 || atoi(e) == 64 || atoi(e) == 128)) ctx->rescue_threads = atoi(e);
 	e = getenv("KB_PIPE_FIRST"); if (e && atoi(e) >= 0) ctx->pipe_first = atoi(e);
@@ -582,6 +584,7 @@ int kb_upload_index(kb_ctx_t* ctx, const kb_index_host_t* h, int expand_sa)
 		ix.sa_full = ctx->sa_full.p;
 	}
 	if (ctx->pm.min_seed <= 0) ctx->pm.min_seed = derive_min_seed(h->l_pac);
+	ctx->row32 = (h->seq_len + 2 < 0xFFFFFFFFull) && !(getenv("KB_ROW64") && atoi(getenv("KB_ROW64")));
 	ctx->have_index = true;
 	return KB_OK;
 }
@@ -715,10 +718,18 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 	sl.launches = 0;
 	CK(cudaEventRecord(sl.ev[0], s));
 	KB_LAUNCH(k_pack, (unsigned)(((long long)n * bt.pk_wpr + KB_BLOCK - 1) / KB_BLOCK), KB_BLOCK, s, bt); sl.launches++;
-	if (ctx->seed_minb == 8) { KB_LAUNCH(k_fm_seed<8>, g_reads, KB_BLOCK, s, ix, pm, bt); }
-	else if (ctx->seed_minb == 12) { KB_LAUNCH(k_fm_seed<12>, g_reads, KB_BLOCK, s, ix, pm, bt); }
-	else if (ctx->seed_minb == 16) { KB_LAUNCH(k_fm_seed<16>, g_reads, KB_BLOCK, s, ix, pm, bt); }
-	else { KB_LAUNCH(k_fm_seed<10>, g_reads, KB_BLOCK, s, ix, pm, bt); }
+	if (ctx->row32)
+	{
+		if (ctx->seed_minb == 8) { KB_LAUNCH((k_fm_seed<8, u32>), g_reads, KB_BLOCK, s, ix, pm, bt); }
+		else if (ctx->seed_minb == 12) { KB_LAUNCH((k_fm_seed<12, u32>), g_reads, KB_BLOCK, s, ix, pm, bt); }
+		else { KB_LAUNCH((k_fm_seed<10, u32>), g_reads, KB_BLOCK, s, ix, pm, bt); }
+	}
+	else
+	{
+		if (ctx->seed_minb == 8) { KB_LAUNCH((k_fm_seed<8, u64>), g_reads, KB_BLOCK, s, ix, pm, bt); }
+		else if (ctx->seed_minb == 12) { KB_LAUNCH((k_fm_seed<12, u64>), g_reads, KB_BLOCK, s, ix, pm, bt); }
+		else { KB_LAUNCH((k_fm_seed<10, u64>), g_reads, KB_BLOCK, s, ix, pm, bt); }
+	}
 	sl.launches++;
 	CK(cudaEventRecord(sl.ev[1], s));
 	KB_LAUNCH(k_sa_locate, g_hits, KB_BLOCK, s, ix, bt); sl.launches++;

@@ -186,17 +186,20 @@ KB_HD void kb_rank_eq_gt(const KbBlk& k, int off, int b, u32* eq, u32* gt)
 // b = 3 - c is the base looked up in the BWT. Returns false (state untouched) when the extended interval is empty.
 // Rows k'+1 .. l' usually lie in one 32-byte block (always for a one-row interval): then that block alone gives
 // Occ(k',b) = count before the block + matches among the rows in front of k'+1, and Occ(l',.)-Occ(k',.) from a range mask.
-KB_HD bool kb_extend(const KbIndexDev& ix, u64& x0, u64& x1, u64& x2, int c, u32* blocks)
+// ROW is the integer type of BWT row numbers: u32 when the text (2G + 1 rows) fits 32 bits, which halves the integer work of a
+// step on small genomes, where the kernel is ALU-bound (the index sits in L2); u64 otherwise (HBM-bound there anyway).
+template <class ROW>
+KB_HD bool kb_extend(const KbIndexDev& ix, ROW& x0, ROW& x1, ROW& x2, int c, u32* blocks)
 {
-	const u64 primary = ix.primary;
+	const ROW primary = (ROW)ix.primary;
 	const int b = 3 - c;
-	const u64 k = x1 - 1, l = k + x2;
-	const u64 rk = k - (k >= primary), rl = l - (l >= primary);
+	const ROW k = x1 - 1, l = k + x2;
+	const ROW rk = k - (ROW)(k >= primary), rl = l - (ROW)(l >= primary);
 	const u64 nBL = (b & 1) ? 0ull : ~0ull, nBH = (b & 2) ? 0ull : ~0ull;
 	u32 ek, n2, gt;
 	if (((rk + 1) >> 6) == (rl >> 6))
 	{
-		const KbBlk B = kb_load_blk(ix.occ, rl >> 6); *blocks += 1;
+		const KbBlk B = kb_load_blk(ix.occ, (u64)(rl >> 6)); *blocks += 1;
 		const u64 pk = kb_top_bits((u32)((rk + 1) & 63)), rg = kb_top_bits((u32)(rl & 63) + 1u) & ~pk;   // rows (k', l']
 		const u64 e = (B.lo ^ nBL) & (B.hi ^ nBH);
 		n2 = (u32)KB_POPCLL(e & rg);
@@ -211,15 +214,15 @@ KB_HD bool kb_extend(const KbIndexDev& ix, u64& x0, u64& x1, u64& x2, int c, u32
 	}
 	else
 	{
-		const KbBlk bk = kb_load_blk(ix.occ, rk >> 6), bl = kb_load_blk(ix.occ, rl >> 6); *blocks += 2;
+		const KbBlk bk = kb_load_blk(ix.occ, (u64)(rk >> 6)), bl = kb_load_blk(ix.occ, (u64)(rl >> 6)); *blocks += 2;
 		u32 gk, el, gl;
 		kb_rank_eq_gt(bk, (int)(rk & 63), b, &ek, &gk);
 		kb_rank_eq_gt(bl, (int)(rl & 63), b, &el, &gl);
 		n2 = el - ek; gt = gl - gk;
 		if (n2 == 0) return false;
 	}
-	x0 = x0 + ((x1 <= primary && x1 + x2 - 1 >= primary) ? 1 : 0) + (u64)gt;
-	x1 = ix.L2[b] + 1 + ek; x2 = n2;
+	x0 = x0 + (ROW)((x1 <= primary && x1 + x2 - 1 >= primary) ? 1 : 0) + (ROW)gt;
+	x1 = (ROW)ix.L2[b] + 1 + (ROW)ek; x2 = (ROW)n2;
 	return true;
 }
 
@@ -287,6 +290,7 @@ KB_HD u64 kb_sa(const KbIndexDev& ix, u64 k, u32* steps)
 #else
 #define KB_BALLOT(p) ((p) ? 1u : 0u)
 #endif
+template <class ROW>
 KB_HD void kb_seed_read(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int r, bool valid, u32* w_steps, u32* w_blocks)
 {
 	const KbPk* rd = valid ? kb_pk_read(bt, r) : bt.pk;
@@ -295,7 +299,7 @@ KB_HD void kb_seed_read(const KbIndexDev& ix, const KbParams& pm, const KbBatchD
 	int nh = 0, ns = 0, pos = 0, cur = 0, lim = 0, stop = 30, len = 0;
 	const int end = rlen - pm.min_seed, K = (ix.ktab != nullptr && ix.ktab_k <= pm.min_seed) ? ix.ktab_k : 0;
 	u32 steps = 0, blocks = 0;
-	u64 x0 = 0, x1 = 0, x2 = 0;
+	ROW x0 = 0, x1 = 0, x2 = 0;
 	bool searching = false, closing = false, finished = !valid, ovf = false;
 	int cw = -1; u64 ccode = 0; u32 cn4 = 0;   // the packed word under the cursor
 #if defined(__CUDA_ARCH__)
@@ -311,10 +315,10 @@ KB_HD void kb_seed_read(const KbIndexDev& ix, const KbParams& pm, const KbBatchD
 			if (closing)
 			{
 				closing = false;
-				bool hit = len >= pm.min_seed && (int)x2 <= 50;
+				bool hit = len >= pm.min_seed && x2 <= (ROW)50;
 				if (hit)
 				{
-					if (nh < bt.max_hits) { KbHit h; h.x0 = x0; h.rpos = (u32)pos; h.len_freq = ((u32)len << 8) | (u32)x2; hits[nh++] = h; ns += (int)x2; }
+					if (nh < bt.max_hits) { KbHit h; h.x0 = (u64)x0; h.rpos = (u32)pos; h.len_freq = ((u32)len << 8) | (u32)x2; hits[nh++] = h; ns += (int)x2; }
 					else ovf = true;
 				}
 				if (pm.pacbio) { int adv = hit ? len : pm.min_seed; pos += adv; stop += adv; if (stop > rlen) stop = rlen; }
@@ -339,11 +343,11 @@ KB_HD void kb_seed_read(const KbIndexDev& ix, const KbParams& pm, const KbBatchD
 				{
 					const KbKtab e = kb_load_ktab(ix.ktab + (u32)(w.code >> (64 - 2 * K))); blocks++;
 					seeded = true;
-					if (e.x2 != 0) { x0 = e.x0; x1 = e.x1; x2 = e.x2; cur = pos + K; steps += (u32)(K - 1); searching = true; }
+					if (e.x2 != 0) { x0 = (ROW)e.x0; x1 = (ROW)e.x1; x2 = (ROW)e.x2; cur = pos + K; steps += (u32)(K - 1); searching = true; }
 					else { closing = true; len = (int)e.flen; steps += e.flen; x2 = 0; }
 				}
 			}
-			if (!seeded) { x0 = ix.L2[p] + 1; x1 = ix.L2[3 - p] + 1; x2 = ix.L2[p + 1] - ix.L2[p]; cur = pos + 1; searching = true; }
+			if (!seeded) { x0 = (ROW)ix.L2[p] + 1; x1 = (ROW)ix.L2[3 - p] + 1; x2 = (ROW)(ix.L2[p + 1] - ix.L2[p]); cur = pos + 1; searching = true; }
 		}
 		// extension trips until enough lanes are parked
 		u32 parked, active;

@@ -18,8 +18,12 @@ def mini(built):
     return idx, pu.genome_of(idx)
 
 
-def test_paired_multi_contig(mini):
+@pytest.mark.parametrize("row64", [False, True])
+def test_paired_multi_contig(mini, monkeypatch, row64):
+    """Seeding runs with 32-bit BWT row numbers when the text allows it and with 64-bit ones otherwise (KB_ROW64 forces them)."""
     idx, g = mini
+    if row64:
+        monkeypatch.setenv("KB_ROW64", "1")
     r1, r2, _ = synth.simulate(g, 1500, 150, 0.07, seed=31, indel=0.005, n_rate=0.003)
     m = pu.make_mapper(idx, emul=True, paired=True)
     assert pu.compare_pairs(m, pu.Oracle(pu.MINI_PREFIX), pu.interleave(r1, r2)) == 0
