@@ -44,6 +44,24 @@ def ncu_traffic(kernel, reads, syn):
     return k["dram_bytes"] * reads / cap_reads, "%s (captured at %d reads/launch, scaled by reads)" % (os.path.basename(f), cap_reads)
 
 
+def random_sector_peak():
+    """Measured ceiling of random 32-byte sector reads on this GPU (scripts/gpu_randsector.cu, committed result): what an
+    FM-index walk over an index larger than L2 can reach at best; the HBM copy peak is not reachable with 32-byte requests."""
+    import glob
+    best = None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*randsector*.json*"))):
+        for ln in open(f):
+            try:
+                d = json.loads(ln)
+            except ValueError:
+                continue
+            if d.get("buffer_mib", 0) >= 4096 and (best is None or d["buffer_mib"] < best[0]["buffer_mib"]):
+                best = (d, os.path.basename(f))
+    if not best:
+        return None
+    return {"independent_gbs": best[0]["independent_gbs"], "dependent_chain_gbs": best[0]["dependent_1280_per_sm_gbs"], "buffer_mib": best[0]["buffer_mib"], "source": "profiles/" + best[1]}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -241,6 +259,11 @@ def main():
             "peak_source": which, "dominant_kernel": "k_" + dom, "share_of_step": per[rk] / max(sum(per.values()), 1e-9),
             "note": ("E. coli index is L2-resident: achieved GB/s is L2->SM sector traffic expressed against the HBM copy peak; dram traffic is in profiles/"
                      if not args.prefix else "random 32-byte sector reads of the Occ blocks and seeding table")}
+    rs = random_sector_peak()
+    if rs:
+        roof["random_sector_peak"] = rs
+        if args.prefix:
+            roof["frac_of_random_sector_peak"] = achieved / rs["independent_gbs"]
     out = {"metric": "mapped reads/s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64/int32", "data": "synthetic",
            "config": config, "clocks": sampler.summary(),

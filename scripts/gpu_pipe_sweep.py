@@ -28,7 +28,7 @@ if len(sys.argv) > 2:
 for pl in plans:
     sub = pl["sub"]
     os.environ["KB_PIPE_SUB_READS"] = str(sub)
-    os.environ["KB_PIPE_FIRST"] = str(pl.get("first", 0)); os.environ["KB_PIPE_GROW"] = str(pl.get("grow", 200)); os.environ["KB_PIPE_TAIL"] = str(pl.get("tail", 0))
+    os.environ["KB_PIPE_FIRST"] = str(pl.get("first", -1)); os.environ["KB_PIPE_GROW"] = str(pl.get("grow", 200)); os.environ["KB_PIPE_TAIL"] = str(pl.get("tail", 0))
     os.environ["KB_PIPE_MIN_READS"] = "1000" if sub != 2 * pairs + 2 else "2000000000"
     m = Mapper(device=0); m.upload_index(idx, expand_sa=True); m.set_params(paired=True)
     for _ in range(2): m.map_chunk(flat, off, est, out=out)
