@@ -1,6 +1,6 @@
 // kart_b200: CUDA kernels (sm_100a) and the C ABI declared in include/kart_b200.h.
 // One context = one device, one stream. The pipeline of a batch is six kernels with no host round trip in between:
-//   k_fm_seed -> k_sa_locate -> k_cand_pair -> k_rescue -> k_segments -> k_align -> k_assemble -> k_finalize
+//   k_fm_seed -> k_sa_locate -> k_cand_pair -> k_rescue_{plan,win,commit} -> k_segments -> k_align -> k_assemble -> k_finalize
 // Capacities of the bump-allocated arenas are checked on the device; a batch that overflowed anything is rerun with
 // larger arenas (never silently truncated, never sent to a CPU path -- there is none).
 #ifndef KB_EMUL
@@ -116,54 +116,61 @@ __global__ void k_reblock(const u32* bwt, u64 bwt_words, u64 n_new, u32* occ)
 
 __global__ void __launch_bounds__(KB_BLOCK) k_cand_pair(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_cand_pair(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x); }
 __global__ void __launch_bounds__(KB_BLOCK) k_cand_pacbio(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_cand_pacbio(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
-// one thread block per unpaired pair; see kb_pair.cuh "block-cooperative rescue"
-#ifndef KB_EMUL
-__global__ void __launch_bounds__(KB_BLOCK) k_rescue(KbIndexDev ix, KbParams pm, KbBatchDev bt)
+// rescue: plan (thread per job) -> windows (block per task) -> commit (thread per job); see kb_pair.cuh "task-parallel rescue"
+__global__ void __launch_bounds__(KB_BLOCK) k_rescue_plan(KbIndexDev ix, KbParams pm, KbBatchDev bt)
 {
-	__shared__ KbRescueJob sj;
 	if (bt.counters[3]) return;
-	const int count = (int)bt.counters[4], tid = threadIdx.x, nth = blockDim.x;
+	const int count = (int)bt.counters[4];
+	for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) kb_rescue_plan(ix, pm, bt, k);
+}
+__global__ void __launch_bounds__(KB_BLOCK) k_rescue_commit(KbIndexDev ix, KbParams pm, KbBatchDev bt)
+{
+	if (bt.counters[3]) return;
+	const int count = (int)bt.counters[4];
+	for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) kb_rescue_commit(pm, bt, k);
+}
+#ifndef KB_EMUL
+__global__ void __launch_bounds__(KB_BLOCK) k_rescue_win(KbIndexDev ix, KbParams pm, KbBatchDev bt)
+{
+	__shared__ KbRescueJob sj; __shared__ u32 ticket;
+	if (bt.counters[3]) return;
+	const u32 count = bt.counters[27]; const int tid = threadIdx.x, nth = blockDim.x;
 	KbRescueJob* j = &sj; KbArena ar = kb_job_arena(bt, blockIdx.x, blockDim.x);
-	for (int k = blockIdx.x; k < count; k += gridDim.x)
+	while (true)
 	{
-		if (tid == 0) { ar.used = 0; ar.ovf = false; kb_rj_begin(pm, bt, j, ar, k); }
+		if (tid == 0) ticket = atomicAdd(&bt.counters[28], 1u);
 		__syncthreads();
-		while (true)
+		const u32 q = ticket;
+		if (q >= count) break;
+		if (tid == 0) kb_rt_begin(ix, bt, j, ar, bt.rtasks[q]);
+		__syncthreads();
+		if (!j->ovf)
 		{
-			if (tid == 0 && !j->done) kb_rj_next(ix, bt, j, ar);
-			__syncthreads();
-			if (j->done) break;
 			kb_rj_window(ix, j, tid, nth); kb_rj_index_clear(bt, j, tid, nth); __syncthreads();
 			kb_rj_ids(j, tid, nth); kb_rj_index_fill(j, tid, nth); __syncthreads();
 			kb_rj_pairs(ix, j, tid, nth); __syncthreads();
-			if (tid == 0) { j->reindex = 0; kb_rj_cluster(pm, bt, j); }
-			__syncthreads();
 		}
-		if (tid == 0) kb_rj_end(pm, bt, j);
+		if (tid == 0) kb_rt_end(pm, bt, j, &bt.rtasks[q]);
 		__syncthreads();
 	}
 }
 #else
-static void k_rescue(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulation: the same phases, barriers replaced by loops over tid
+static void k_rescue_win(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulation: the same phases, barriers replaced by loops over tid
 {
 	if (blockIdx.x != 0 || threadIdx.x != 0) return;
 	if (bt.counters[3]) return;
-	int count = (int)bt.counters[4], nth = KB_BLOCK;
-	static KbRescueJob job; KbRescueJob* j = &job; KbArena ar = kb_job_arena(bt, 0, blockDim.x); nth = (int)blockDim.x;
-	for (int k = 0; k < count; k++)
+	const u32 count = bt.counters[27]; const int nth = (int)blockDim.x;
+	static KbRescueJob job; KbRescueJob* j = &job; KbArena ar = kb_job_arena(bt, 0, blockDim.x);
+	for (u32 q = 0; q < count; q++)
 	{
-		ar.used = 0; ar.ovf = false;
-		kb_rj_begin(pm, bt, j, ar, k);
-		while (true)
+		kb_rt_begin(ix, bt, j, ar, bt.rtasks[q]);
+		if (!j->ovf)
 		{
-			if (!j->done) kb_rj_next(ix, bt, j, ar);
-			if (j->done) break;
 			for (int t = 0; t < nth; t++) { kb_rj_window(ix, j, t, nth); kb_rj_index_clear(bt, j, t, nth); }
 			for (int t = nth - 1; t >= 0; t--) { kb_rj_ids(j, t, nth); kb_rj_index_fill(j, t, nth); }
 			for (int t = nth - 1; t >= 0; t--) kb_rj_pairs(ix, j, t, nth);   // reversed on purpose: the result must not depend on append order
-			j->reindex = 0; kb_rj_cluster(pm, bt, j);
 		}
-		kb_rj_end(pm, bt, j);
+		kb_rt_end(pm, bt, j, &bt.rtasks[q]);
 	}
 }
 #endif
@@ -363,7 +370,7 @@ struct kb_slot
 	cudaStream_t aux[KB_NW_CLASSES]; cudaEvent_t fork = nullptr, join[KB_NW_CLASSES];   // the nw_alignment size classes run side by side (launch_pipeline)
 	KbBatchDev bt; int n_reads = 0; size_t seq_bytes = 0; u64 seq_first = 0; int max_rlen = 0; int first_read = 0;
 	DevBuf<u8> seq, scratch, wscratch; DevBuf<u64> seq_off; DevBuf<unsigned long long> work; DevBuf<i32> est, n_hits, n_seeds, n_cands, cand_cap, rescue, slow1, slow2; DevBuf<u32> seed_off, cand_off, cigar, counters, cseg_off, runs; DevBuf<i32> cseg_n; DevBuf<KbSegX> segx; DevBuf<KbJob> jobs; DevBuf<u32> piece_list, part_list; DevBuf<KbPiece> pieces;
-	DevBuf<KbHit> hits; DevBuf<KbSeg> segs; DevBuf<KbCand> cands; DevBuf<KbReport> reports; DevBuf<KbReadRes> res; DevBuf<KbPairStat> pstat; DevBuf<kb_aln_t> aln; DevBuf<KbPk> pk; DevBuf<kb_extra_t> extra;
+	DevBuf<KbHit> hits; DevBuf<KbSeg> segs; DevBuf<KbCand> cands; DevBuf<KbReport> reports; DevBuf<KbReadRes> res; DevBuf<KbPairStat> pstat; DevBuf<kb_aln_t> aln; DevBuf<KbPk> pk; DevBuf<kb_extra_t> extra; DevBuf<KbRTask> rtasks; DevBuf<u32> rjob_first, rjob_count; size_t cap_rtasks = 0;
 	size_t cap_segs = 0, cap_cands = 0, cap_cigar = 0, cap_segx = 0, cap_jobs = 0, cap_pieces = 0, cap_runs = 0, cap_extra = 0, scratch_per_thread = 0; int scratch_threads = 0;
 	u32* counters_host = nullptr; unsigned long long* work_dev_host = nullptr;   // pinned: 16 x u32, 8 x u64
 	int launches = 0;
@@ -371,7 +378,7 @@ struct kb_slot
 	{
 		seq.release(); scratch.release(); wscratch.release(); seq_off.release(); work.release(); est.release(); n_hits.release(); n_seeds.release(); n_cands.release(); cand_cap.release();
 		rescue.release(); slow1.release(); slow2.release(); seed_off.release(); cand_off.release(); cigar.release(); counters.release(); cseg_off.release(); runs.release();
-		cseg_n.release(); segx.release(); jobs.release(); piece_list.release(); part_list.release(); pieces.release(); hits.release(); segs.release(); cands.release(); reports.release(); res.release(); pstat.release(); aln.release(); pk.release(); extra.release();
+		cseg_n.release(); segx.release(); jobs.release(); piece_list.release(); part_list.release(); pieces.release(); hits.release(); segs.release(); cands.release(); reports.release(); res.release(); pstat.release(); aln.release(); pk.release(); extra.release(); rtasks.release(); rjob_first.release(); rjob_count.release();
 	}
 };
 
@@ -384,7 +391,7 @@ struct kb_ctx
 	kb_slot slot[KB_SLOTS];
 	DevBuf<u32> chunk_cigar, chunk_cursor;   // cigar arena and cursor shared by the sub-batches of one pipelined chunk
 	bool staged = false, ran = false, ran_pipelined = false; u32 n_cigar_last = 0;
-	double seg_factor = 32, cigar_factor = 8, scratch_factor = 1, segx_factor = 8, job_factor = 4, run_factor = 96, extra_factor = 0.25;
+	double seg_factor = 32, cigar_factor = 8, scratch_factor = 1, segx_factor = 8, job_factor = 4, run_factor = 96, extra_factor = 0.25, rtask_factor = 0.25;
 	float stage_ms[9]; uint64_t work_host[8]; u32 counters_host[KB_NCOUNTERS];
 	cudaEvent_t chunk_start = nullptr; int trace = 0;
 	int seed_minb = 10;
@@ -394,7 +401,7 @@ struct kb_ctx
 	int part_warps = 148 * 40, part_pool = 4096;   // k_align_part: warps in the grid (each with an HBM arena) and shared-memory pool bytes per warp (r14 A/B: 8 warps/SM + 10 KB pool 2.34 ms -> 40 warps/SM + 4 KB 1.34 ms for the align stage at C2)
 	int nw_tmax = 0;             // largest side one thread solves (0: KB_NW_TMAX); KB_NW_TMAX=32|64 sends more to the wavefront kernel
 	int nw_warp_below = 8192;    // a column-tile class (33..64, 65..128) with fewer problems than this is solved by k_nw_warp instead
-	int rescue_threads = 128;    // block size of k_rescue (32, 64 or 128; measured r14: 128 best on C2, 64/128 equal on the 100 Mbp index -- the kernel is bound by its longest jobs, not by jobs in flight)
+	int rescue_threads = 64;     // block size of k_rescue_win (32, 64 or 128)
 	int pipe_min_reads = 262144, pipe_sub_reads = 0;   // chunks of at least pipe_min_reads go through the slot pipeline
 	int pipe_first = 0, pipe_grow = 200, pipe_tail = 0;   // sub-batch plan: first size, growth (percent), floor of the halving tail (0: uniform)
 	cudaStream_t copy_stream = nullptr;                   // D2H of each sub-batch's cigar range, in retirement order
@@ -651,6 +658,9 @@ static int alloc_batch(kb_ctx* ctx, kb_slot& sl, int shared)
 	CK(sl.hits.ensure(n * max_hits)); CK(sl.n_hits.ensure(n)); CK(sl.n_seeds.ensure(n)); CK(sl.seed_off.ensure(n));
 	CK(sl.segs.ensure(sl.cap_segs)); CK(sl.cands.ensure(sl.cap_cands)); CK(sl.reports.ensure(sl.cap_cands));
 	CK(sl.n_cands.ensure(n)); CK(sl.cand_off.ensure(n)); CK(sl.cand_cap.ensure(n)); CK(sl.rescue.ensure(n / 2 + 1));
+	sl.cap_rtasks = ctx->pm.paired ? (size_t)(ctx->rtask_factor * (double)n) + 65536 : 1;
+	CK(sl.rtasks.ensure(sl.cap_rtasks)); CK(sl.rjob_first.ensure(n / 2 + 1)); CK(sl.rjob_count.ensure(n / 2 + 1));
+	bt.rtasks = sl.rtasks.p; bt.cap_rtasks = (u32)sl.cap_rtasks; bt.rjob_first = sl.rjob_first.p; bt.rjob_count = sl.rjob_count.p;
 	CK(sl.res.ensure(n)); CK(sl.pstat.ensure(n / 2 + 1)); CK(sl.aln.ensure(n));
 	if (!shared) CK(sl.cigar.ensure(sl.cap_cigar));
 	sl.cap_extra = ctx->pm.multihit ? (size_t)(ctx->extra_factor * (double)n) + 65536 : 0;
@@ -737,11 +747,12 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 	KB_LAUNCH(k_cand_pair, g_items, KB_BLOCK, s, ix, pm, bt); sl.launches++;
 	if (pm.pacbio) { KB_LAUNCH(k_cand_pacbio, g_slow, KB_BLOCK, s, ix, pm, bt); sl.launches++; }
 	CK(cudaEventRecord(sl.ev[3], s));
-	// one block per rescue job (block size is a knob: KB_RESCUE_THREADS)
 	if (pm.paired)
 	{
 		unsigned rt = (unsigned)ctx->rescue_threads, g = (unsigned)bt.scratch_threads / rt; if (g > 148u * 32u) g = 148u * 32u;
-		KB_LAUNCH(k_rescue, g, rt, s, ix, pm, bt); sl.launches++;
+		KB_LAUNCH(k_rescue_plan, 148 * 4, KB_BLOCK, s, ix, pm, bt); sl.launches++;
+		KB_LAUNCH(k_rescue_win, g, rt, s, ix, pm, bt); sl.launches++;
+		KB_LAUNCH(k_rescue_commit, 148 * 4, KB_BLOCK, s, ix, pm, bt); sl.launches++;
 	}
 	CK(cudaEventRecord(sl.ev[4], s));
 	KB_LAUNCH(k_segments, g_reads, KB_BLOCK, s, ix, pm, bt); sl.launches++;
@@ -785,7 +796,8 @@ static void grow_factors(kb_ctx* ctx, u32 st)
 {
 	if (st & (KB_OVF_SEEDS | KB_OVF_CANDS | KB_OVF_HITS)) ctx->seg_factor *= 4;
 	if (st & KB_OVF_CIGAR) ctx->cigar_factor *= 4;
-	if (st & (KB_OVF_SCRATCH | KB_OVF_NW | KB_OVF_RESCUE)) ctx->scratch_factor *= 2;
+	if (st & (KB_OVF_SCRATCH | KB_OVF_NW)) ctx->scratch_factor *= 2;
+	if (st & KB_OVF_RESCUE) ctx->rtask_factor *= 8;
 	if (st & KB_OVF_SEGX) ctx->segx_factor *= 4;
 	if (st & KB_OVF_JOBS) ctx->job_factor *= 4;
 	if (st & KB_OVF_RUNS) ctx->run_factor *= 4;

@@ -32,11 +32,11 @@ KB_HD int kb_rescue_cluster(const KbParams& pm, const KbBatchDev& bt, i64 left, 
 	return best_s;
 }
 
-// ---- block-cooperative rescue ---------------------------------------------------------------------
-// One thread block per pair that failed to pair (RescueUnpairedAlignment). The block walks the anchors in the reference's order;
-// for every reference window the threads share the work: look every window 8-mer up in a small index of the mate's 8-mers
-// and extend the run starts. Control flow is decided by thread 0 between barriers and published through the job record
-// (shared memory), so the phases below are plain functions of (job, tid, nth) that the host-emulation build can replay.
+// ---- block-cooperative window search -----------------------------------------------------------------
+// One thread block per reference window of a pair that failed to pair (RescueUnpairedAlignment; the windows of a job are
+// enumerated by kb_rescue_plan below). The threads share the work: look every window 8-mer up in a small index of the mate's
+// 8-mers and extend the run starts. The record lives in shared memory; the phases are plain functions of (record, tid, nth)
+// that the host-emulation build can replay.
 struct KbRescueJob
 {
 	i32 p, ra, rb, n1, n2, n1o, n2o, l1, l2, est, sc1, sc2, strategy, attempted, mated;
@@ -68,84 +68,6 @@ KB_HD u32 kb_rj_mid(const KbRescueJob* j, int r)
 	if (!j->mclean) return j->wm[r];
 	if (r + 8 > j->ml) return KB_NOKMER;
 	return (u32)(kb_read_win(j->mate_pk, r).code >> 48);
-}
-
-// thread 0: set the job up (AlignmentRescue.cpp:86-99)
-KB_HD void kb_rj_begin(const KbParams& pm, const KbBatchDev& bt, KbRescueJob* j, KbArena& ar, int k)
-{
-	j->p = bt.rescue_list[k]; j->ra = 2 * j->p; j->rb = j->ra + 1;
-	j->n1 = j->n1o = bt.n_cands[j->ra]; j->n2 = j->n2o = bt.n_cands[j->rb];
-	j->l1 = (int)(bt.seq_off[j->ra + 1] - bt.seq_off[j->ra]); j->l2 = (int)(bt.seq_off[j->rb + 1] - bt.seq_off[j->rb]);
-	j->est = bt.est[j->p]; j->mated = 0; j->attempted = 0; j->done = 0; j->ovf = 0; j->side = -1; j->idx = -1; j->npairs = 0;
-	const KbCand* a = bt.cands + bt.cand_off[j->ra]; const KbCand* b = bt.cands + bt.cand_off[j->rb];
-	j->sc1 = kb_top_score(a, j->n1); j->sc2 = kb_top_score(b, j->n2);
-	if (j->sc1 == 0 && j->sc2 == 0) j->strategy = 0;
-	else if (j->sc1 < (int)(j->l1 * 0.1) && j->sc2 < (int)(j->l2 * 0.1)) j->strategy = 4;
-	else if (j->sc1 > j->sc2 && j->sc1 - j->sc2 > 50) j->strategy = 1;
-	else if (j->sc2 > j->sc1 && j->sc2 - j->sc1 > 50) j->strategy = 2;
-	else j->strategy = 3;
-	if (j->strategy == 0 || j->strategy == 4) { j->done = 1; return; }
-	j->attempted = 1;
-	if (j->est > pm.max_insert) j->est = pm.max_insert;
-	int lm = j->l1 > j->l2 ? j->l1 : j->l2;
-	j->wm = (u32*)ar.alloc((u64)lm * 4);
-	int hs = 256; while (hs < 2 * lm) hs <<= 1;
-	j->hmask = hs - 1; j->reindex = 0;
-	j->hkey = (u32*)ar.alloc((u64)hs * 4); j->hhead = (i32*)ar.alloc((u64)hs * 4); j->hnext = (i32*)ar.alloc((u64)lm * 4);
-	j->arena_used = ar.used;
-	if (ar.ovf) { j->ovf = 1; j->done = 1; }
-}
-
-// thread 0: advance to the next anchor that has a usable window; switches from "rescue read 2 around read 1's candidates"
-// (side 0, :99-133) to "rescue read 1 around read 2's candidates" (side 1, :134-168) when the first list is exhausted
-KB_HD void kb_rj_next(const KbIndexDev& ix, const KbBatchDev& bt, KbRescueJob* j, KbArena& ar)
-{
-	const KbCand* a = bt.cands + bt.cand_off[j->ra]; const KbCand* b = bt.cands + bt.cand_off[j->rb];
-	ar.used = j->arena_used; j->npairs = 0;
-	while (true)
-	{
-		if (j->side < 0 || (j->side == 0 && j->idx + 1 >= j->n1o) || (j->side == 1 && j->idx + 1 >= j->n2o))
-		{
-			int ns = j->side + 1;
-			if (ns == 0 && !(j->strategy == 1 || j->strategy == 3)) ns = 1;
-			if (ns == 1 && !(j->strategy == 2 || j->strategy == 3)) ns = 2;
-			if (ns >= 2) { j->done = 1; return; }
-			j->side = ns; j->idx = -1;
-			if (ns == 0) { j->thr = j->sc1 - 30 < 50 ? 50 : j->sc1 - 30; j->mate = bt.seq + bt.seq_off[j->rb]; j->ml = j->l2; j->next_new = j->n2o; }
-			else { j->thr = j->sc2 - 30 < 50 ? 50 : j->sc2 - 30; j->mate = bt.seq + bt.seq_off[j->ra]; j->ml = j->l1; j->next_new = j->n1o; }
-			j->reindex = 1;   // the mate's 8-mer ids and their index are (re)built by all lanes: kb_rj_index_clear / _fill
-			continue;
-		}
-		int i = ++j->idx; i64 left, right; int cid, e;
-		if (j->side == 0)
-		{
-			if (a[i].score < j->thr) continue;
-			left = a[i].diff; right = a[i].diff + j->est + j->l2;
-			e = kb_chr_lookup(ix, left); if (e >= ix.n_ends) continue;
-			cid = ix.end_chr[e];
-			if (right < ix.G && right > ix.chr_fwd[cid]) right = ix.chr_fwd[cid] - 1;
-			else if (right >= ix.G && right > ix.chr_rev[cid]) right = ix.chr_rev[cid] - 1;
-		}
-		else
-		{
-			if (b[i].score < j->thr) continue;
-			left = b[i].diff - j->est; right = b[i].diff + j->l2;
-			e = kb_chr_lookup(ix, right); if (e >= ix.n_ends) continue;
-			cid = ix.end_chr[e];
-			if (left < ix.G && left < ix.chr_fwd[cid] - ix.chr_len[cid]) left = ix.chr_fwd[cid] - ix.chr_len[cid] + 1;
-			else if (right >= ix.G && left < ix.chr_rev[cid] - ix.chr_len[cid]) left = ix.chr_rev[cid] - ix.chr_len[cid] + 1;
-		}
-		int slen = (int)(right - left);
-		if (slen < j->ml) continue;
-		j->left = left; j->slen = slen; j->clean = (left >= 0 && left + slen <= ix.G2) ? 1 : 0;
-		j->win = (u8*)ar.alloc((u64)slen); j->ww = (u32*)ar.alloc((u64)slen * 4);
-		u64 worst = (u64)((j->ml < slen ? j->ml : slen) / 9 + 2) * (u64)(j->ml + slen);
-		u64 room = ar.cap > ar.used ? (ar.cap - ar.used) / (2 * sizeof(KbSeg)) : 0;
-		j->cap_pairs = (int)(worst < room ? worst : room);
-		j->pairs = (KbSeg*)ar.alloc((u64)(j->cap_pairs > 0 ? j->cap_pairs : 1) * sizeof(KbSeg));
-		if (ar.ovf) { j->ovf = 1; j->done = 1; }
-		return;
-	}
 }
 
 // all threads: reference characters of the window
@@ -219,37 +141,154 @@ KB_HD void kb_rj_pairs(const KbIndexDev& ix, KbRescueJob* j, int tid, int nth)
 	}
 }
 
-// thread 0: order the runs like GenerateSimplePairsFromCommonKmers does, pick the best diagonal cluster, maybe append a candidate
-KB_HD void kb_rj_cluster(const KbParams& pm, const KbBatchDev& bt, KbRescueJob* j)
+// ---- task-parallel rescue ----------------------------------------------------------------------------
+// The anchors a rescue job visits, their reference windows and the thresholds all follow from the candidates the pair had
+// BEFORE rescue (scores sc1/sc2, thr, EstDistance): what one window yields never depends on what another window appended.
+// Only the bookkeeping is sequential (a rescued candidate takes the next free slot of its read). So the job is cut in three:
+//   kb_rescue_plan   (thread per job)    strategy, then one task per (side, anchor) that has a usable window, in the reference's order
+//   k_rescue_win     (block per task)    8-mer index of the mate, exact runs against the window, best diagonal cluster -> task result
+//   kb_rescue_commit (thread per job)    walks the job's tasks in order and appends / cross-links exactly as :125-130,:160-165 do
+// A pair with 100 anchors in a repeat family is then 100 blocks' work instead of one block's 100 windows in a row (the old
+// kernel lasted as long as its longest job: 2.6 ms of an 11 ms step on the 100 Mbp repeat-rich index, ncu r11syn/r14 A/B).
+KB_HD int kb_rescue_strategy(int sc1, int sc2, int l1, int l2)   // AlignmentRescue.cpp:86-93
 {
-	if (j->ovf) { j->done = 1; return; }
+	if (sc1 == 0 && sc2 == 0) return 0;
+	if (sc1 < (int)(l1 * 0.1) && sc2 < (int)(l2 * 0.1)) return 4;
+	if (sc1 > sc2 && sc1 - sc2 > 50) return 1;
+	if (sc2 > sc1 && sc2 - sc1 > 50) return 2;
+	return 3;
+}
+// the reference window of one anchor (:99-112 / :134-147); false when the anchor is skipped
+KB_HD bool kb_rescue_window(const KbIndexDev& ix, int side, const KbCand& c, int est, int l2, int ml, i64* left_out, int* slen_out)
+{
+	i64 left, right; int cid, e;
+	if (side == 0)
+	{
+		left = c.diff; right = c.diff + est + l2;
+		e = kb_chr_lookup(ix, left); if (e >= ix.n_ends) return false;
+		cid = ix.end_chr[e];
+		if (right < ix.G && right > ix.chr_fwd[cid]) right = ix.chr_fwd[cid] - 1;
+		else if (right >= ix.G && right > ix.chr_rev[cid]) right = ix.chr_rev[cid] - 1;
+	}
+	else
+	{
+		left = c.diff - est; right = c.diff + l2;
+		e = kb_chr_lookup(ix, right); if (e >= ix.n_ends) return false;
+		cid = ix.end_chr[e];
+		if (left < ix.G && left < ix.chr_fwd[cid] - ix.chr_len[cid]) left = ix.chr_fwd[cid] - ix.chr_len[cid] + 1;
+		else if (right >= ix.G && left < ix.chr_rev[cid] - ix.chr_len[cid]) left = ix.chr_rev[cid] - ix.chr_len[cid] + 1;
+	}
+	const int slen = (int)(right - left);
+	if (slen < ml) return false;
+	*left_out = left; *slen_out = slen;
+	return true;
+}
+// thread per rescue job: the job's tasks, contiguous and in visiting order
+KB_HD void kb_rescue_plan(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int k)
+{
+	const int p = bt.rescue_list[k], ra = 2 * p, rb = ra + 1;
+	const int n1o = bt.n_cands[ra], n2o = bt.n_cands[rb];
+	const int l1 = (int)(bt.seq_off[ra + 1] - bt.seq_off[ra]), l2 = (int)(bt.seq_off[rb + 1] - bt.seq_off[rb]);
+	const KbCand* a = bt.cands + bt.cand_off[ra]; const KbCand* b = bt.cands + bt.cand_off[rb];
+	const int sc1 = kb_top_score(a, n1o), sc2 = kb_top_score(b, n2o);
+	const int strategy = kb_rescue_strategy(sc1, sc2, l1, l2);
+	bt.rjob_first[k] = 0; bt.rjob_count[k] = 0;
+	if (strategy == 0 || strategy == 4) return;
+	int est = bt.est[p]; if (est > pm.max_insert) est = pm.max_insert;
+	u32 first = 0; int count = 0;
+	for (int pass = 0; pass < 2; pass++)   // count, then fill
+	{
+		int w = 0;
+		for (int side = 0; side < 2; side++)
+		{
+			if (side == 0 && !(strategy == 1 || strategy == 3)) continue;
+			if (side == 1 && !(strategy == 2 || strategy == 3)) continue;
+			const int top = side == 0 ? sc1 : sc2, thr = top - 30 < 50 ? 50 : top - 30;
+			const int n = side == 0 ? n1o : n2o, ml = side == 0 ? l2 : l1;
+			const KbCand* v = side == 0 ? a : b;
+			for (int i = 0; i < n; i++)
+			{
+				if (v[i].score < thr) continue;
+				i64 left; int slen;
+				if (!kb_rescue_window(ix, side, v[i], est, l2, ml, &left, &slen)) continue;
+				if (pass == 1 && (u64)first + (u64)w < (u64)bt.cap_rtasks)
+				{
+					KbRTask t; t.job = (u32)k; t.side = side; t.idx = i; t.slen = slen; t.left = left; t.score = 0; t.nseg = 0; t.diff = 0; t.seg_start = 0; t.pad = 0;
+					bt.rtasks[first + (u32)w] = t;
+				}
+				w++;
+			}
+		}
+		if (pass == 0)
+		{
+			count = w; if (count == 0) break;
+			first = KB_ALLOC(&bt.counters[27], (u32)count);
+			if ((u64)first + (u64)count > (u64)bt.cap_rtasks) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_RESCUE); return; }
+		}
+	}
+	bt.rjob_first[k] = first; bt.rjob_count[k] = (u32)count;
+}
+// thread 0 of a task's block: the job record for the window phases (kb_rj_window .. kb_rj_pairs are shared with the description above)
+KB_HD void kb_rt_begin(const KbIndexDev& ix, const KbBatchDev& bt, KbRescueJob* j, KbArena& ar, const KbRTask& t)
+{
+	j->p = bt.rescue_list[t.job]; j->ra = 2 * j->p; j->rb = j->ra + 1;
+	j->l1 = (int)(bt.seq_off[j->ra + 1] - bt.seq_off[j->ra]); j->l2 = (int)(bt.seq_off[j->rb + 1] - bt.seq_off[j->rb]);
+	j->side = t.side; j->idx = t.idx; j->done = 0; j->ovf = 0; j->npairs = 0; j->reindex = 1;
+	if (t.side == 0) { j->mate = bt.seq + bt.seq_off[j->rb]; j->ml = j->l2; } else { j->mate = bt.seq + bt.seq_off[j->ra]; j->ml = j->l1; }
+	const int lm = j->ml;
+	ar.used = 0; ar.ovf = false;
+	j->wm = (u32*)ar.alloc((u64)lm * 4);
+	int hs = 256; while (hs < 2 * lm) hs <<= 1;
+	j->hmask = hs - 1;
+	j->hkey = (u32*)ar.alloc((u64)hs * 4); j->hhead = (i32*)ar.alloc((u64)hs * 4); j->hnext = (i32*)ar.alloc((u64)lm * 4);
+	const int slen = t.slen;
+	j->left = t.left; j->slen = slen; j->clean = (t.left >= 0 && t.left + slen <= ix.G2) ? 1 : 0;
+	j->win = (u8*)ar.alloc((u64)slen); j->ww = (u32*)ar.alloc((u64)slen * 4);
+	u64 worst = (u64)((j->ml < slen ? j->ml : slen) / 9 + 2) * (u64)(j->ml + slen);
+	u64 room = ar.cap > ar.used ? (ar.cap - ar.used) / (2 * sizeof(KbSeg)) : 0;
+	j->cap_pairs = (int)(worst < room ? worst : room);
+	j->pairs = (KbSeg*)ar.alloc((u64)(j->cap_pairs > 0 ? j->cap_pairs : 1) * sizeof(KbSeg));
+	if (ar.ovf) j->ovf = 1;
+}
+// thread 0: order the runs like GenerateSimplePairsFromCommonKmers does, pick the best diagonal cluster, record it in the task
+KB_HD void kb_rt_end(const KbParams& pm, const KbBatchDev& bt, KbRescueJob* j, KbRTask* t)
+{
+	if (j->ovf) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SCRATCH); return; }
 	int np = (int)j->npairs;
 	kb_sort_segs<false>(j->pairs, np);
 	KbCand c;
-	int score = kb_rescue_cluster(pm, bt, j->left, j->pairs, np, &c);
-	KbCand* a = bt.cands + bt.cand_off[j->ra]; KbCand* b = bt.cands + bt.cand_off[j->rb];
-	if (j->side == 0)
-	{
-		if (score > j->sc2 && j->next_new < bt.cand_cap[j->rb]) { j->mated = 1; c.mate = j->idx; a[j->idx].mate = j->next_new; b[j->next_new++] = c; j->n2 = j->next_new; }
-	}
-	else if (score > j->sc1 && j->next_new < bt.cand_cap[j->ra]) { j->mated = 1; c.mate = j->idx; b[j->idx].mate = j->next_new; a[j->next_new++] = c; j->n1 = j->next_new; }
+	const int score = kb_rescue_cluster(pm, bt, j->left, j->pairs, np, &c);
+	t->score = score; t->diff = c.diff; t->seg_start = c.seg_start; t->nseg = c.nseg;
 }
-
-// thread 0: what follows RescueUnpairedAlignment in ReadMapping (Mapping.cpp:561-563) and the EstDistance interval
-KB_HD void kb_rj_end(const KbParams& pm, const KbBatchDev& bt, KbRescueJob* j)
+// thread per rescue job: AlignmentRescue.cpp:125-130 / :160-165 over the job's tasks, then what follows in ReadMapping (Mapping.cpp:561-563)
+KB_HD void kb_rescue_commit(const KbParams& pm, const KbBatchDev& bt, int k)
 {
-	if (j->ovf) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SCRATCH); return; }
-	KbCand* a = bt.cands + bt.cand_off[j->ra]; KbCand* b = bt.cands + bt.cand_off[j->rb];
-	bt.n_cands[j->ra] = j->n1; bt.n_cands[j->rb] = j->n2;
-	if (j->attempted)
+	const int p = bt.rescue_list[k], ra = 2 * p, rb = ra + 1;
+	const int n1o = bt.n_cands[ra], n2o = bt.n_cands[rb];
+	const int l1 = (int)(bt.seq_off[ra + 1] - bt.seq_off[ra]), l2 = (int)(bt.seq_off[rb + 1] - bt.seq_off[rb]);
+	KbCand* a = bt.cands + bt.cand_off[ra]; KbCand* b = bt.cands + bt.cand_off[rb];
+	const int sc1 = kb_top_score(a, n1o), sc2 = kb_top_score(b, n2o);
+	const int strategy = kb_rescue_strategy(sc1, sc2, l1, l2);
+	const bool attempted = !(strategy == 0 || strategy == 4);
+	int n1 = n1o, n2 = n2o; bool mated = false;
+	const u32 first = bt.rjob_first[k], count = bt.rjob_count[k];
+	for (u32 q = 0; q < count; q++)
+	{
+		const KbRTask t = bt.rtasks[first + q];
+		KbCand c; c.score = t.score; c.diff = t.diff; c.seg_start = t.seg_start; c.nseg = t.nseg; c.mate = t.idx;
+		if (t.side == 0) { if (t.score > sc2 && n2 < bt.cand_cap[rb]) { mated = true; a[t.idx].mate = n2; b[n2++] = c; } }
+		else if (t.score > sc1 && n1 < bt.cand_cap[ra]) { mated = true; b[t.idx].mate = n1; a[n1++] = c; }
+	}
+	bt.n_cands[ra] = n1; bt.n_cands[rb] = n2;
+	if (attempted)
 	{
 		KB_ATOMIC_ADD(&bt.counters[7], 1u);
-		KbPairStat& st = bt.pstat[j->p]; int est = bt.est[j->p];
+		KbPairStat& st = bt.pstat[p]; int est = bt.est[p];
 		if (est >= pm.max_insert) { if (st.est_lo < pm.max_insert) st.est_lo = pm.max_insert; }
 		else { st.est_lo = est; st.est_hi = est; }
 	}
-	if (j->mated) kb_keep_mated(a, j->n1, b, j->n2);
-	kb_prune(pm, a, j->n1); kb_prune(pm, b, j->n2);
+	if (mated) kb_keep_mated(a, n1, b, n2);
+	kb_prune(pm, a, n1); kb_prune(pm, b, n2);
 }
 
 // ---- final scoring -------------------------------------------------------------------------------

@@ -85,6 +85,9 @@ struct KbJob { i64 gpos; u32 read; i32 rpos, rlen, glen; u32 run_off; i32 nruns,
 // the end of that slice backwards. whole != 0: the piece is the entire job (no 8-mer partition): the solver finishes the job itself.
 struct KbPiece { u32 job; i32 r0, rl, g0, gl; u32 out_off; u32 whole; u32 pad; };
 
+// one reference window of a rescue job (kb_pair.cuh "task-parallel rescue"): the task, and what its block found there
+struct KbRTask { u32 job; i32 side, idx, slen; i64 left; i32 score, nseg; i64 diff; u32 seg_start, pad; };
+
 // status bits written by kernels (any non-zero value fails the batch loudly; capacities are then grown and the batch rerun)
 enum { KB_OVF_SEEDS = 1, KB_OVF_CANDS = 2, KB_OVF_CIGAR = 4, KB_OVF_SCRATCH = 8, KB_OVF_HITS = 16, KB_OVF_RESCUE = 32, KB_OVF_NW = 64, KB_OVF_SEGX = 128, KB_OVF_JOBS = 256, KB_OVF_RUNS = 512, KB_OVF_EXTRA = 1024 };
 
@@ -107,6 +110,8 @@ struct KbBatchDev
 	// stage 2
 	KbCand* cands; u32 cap_cands; i32* n_cands; u32* cand_off; i32* cand_cap;
 	i32* rescue_list;                   // pair ids that need rescue
+	KbRTask* rtasks; u32 cap_rtasks;    // rescue windows (cursor: counters[27]); a job's tasks are rtasks[rjob_first[k] .. + rjob_count[k])
+	u32* rjob_first; u32* rjob_count;
 	i32* slow_list; i32* slow_list2;    // reads whose segments / reports need the HBM arena (counters[12], counters[13])
 	// stage 3: segments of the surviving candidates, alignment jobs, run arena
 	KbSegX* segx; u32 cap_segx; u32* cseg_off; i32* cseg_n;   // cseg_* indexed like cands (cseg_n < 0: candidate dropped)
@@ -129,7 +134,7 @@ struct KbBatchDev
 	i32 seg_cap, kmer_cap;
 	// counters: [0] seeds cursor [1] cands cursor [2] cigar cursor [3] status bits [4] rescue count [5] max seeds/read
 	//           [6] nw calls [7] rescue attempts [8] segx cursor [10] run cursor + [11] job cursor (one u64) [12],[13] slow lists [14] extra-line cursor (-m)
-	//           [16..22] pieces per size class [23] partition jobs [24] piece cursor [26] k_align_part job tickets
+	//           [16..22] pieces per size class [23] partition jobs [24] piece cursor [26] k_align_part job tickets [27] rescue task cursor [28] rescue task tickets
 	//           [30],[31] cigar cursor before / after the assemble kernels (pipelined chunks)
 	//           64-bit: work[0] extension steps, work[1] occ blocks, work[2] LF steps, work[3] NW cells, work[4] NW calls
 	u32* counters;
