@@ -127,6 +127,10 @@ int  kb_fetch_extra(kb_ctx_t* ctx, kb_extra_t* out, uint32_t cap, uint32_t* n);
  * no memory. Usable from any thread, before or after kb_init. */
 void* kb_host_alloc(uint64_t bytes);
 void  kb_host_free(void* p);
+/* Page-locks memory the caller allocated itself (page-aligned is best), e.g. buffers filled while the device was still being
+ * initialised. Returns KB_OK or KB_ECUDA; a buffer that could not be registered still works, as pageable memory. */
+int   kb_host_register(void* p, uint64_t bytes);
+void  kb_host_unregister(void* p);
 
 /* Instrumentation. kb_stage_ms: device time (CUDA events on the context's stream) of each kernel of the last kb_run:
  * [0] fm_seed [1] sa_locate [2] cand_pair [3] rescue [4] segments [5] align [6] assemble [7] finalize [8] whole run.

@@ -625,6 +625,22 @@ void kb_host_free(void* p)
 	free(p);
 #endif
 }
+int kb_host_register(void* p, uint64_t bytes)
+{
+	if (!p || !bytes) return KB_EINVAL;
+#ifndef KB_EMUL
+	if (cudaHostRegister(p, bytes, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); return KB_ECUDA; }
+#endif
+	return KB_OK;
+}
+void kb_host_unregister(void* p)
+{
+#ifndef KB_EMUL
+	if (p) { if (cudaHostUnregister(p) != cudaSuccess) cudaGetLastError(); }
+#else
+	(void)p;
+#endif
+}
 void* kb_cuda_stream(kb_ctx_t* ctx) { return ctx ? (void*)ctx->slot[0].stream : nullptr; }
 
 // device arrays of one slot for its n_reads / max_rlen; shared != 0: cigar elements go to the chunk-wide arena

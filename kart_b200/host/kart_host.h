@@ -23,22 +23,27 @@ struct HostIndex
 bool check_index_files(const std::string& prefix);                // CheckBWAIndexFiles, GetData.cpp:222
 
 // Grow-only host array without value-initialisation. `pinned` arrays come from kb_host_alloc (page-locked, so the copies of
-// kb_map_chunk are asynchronous DMA at full PCIe rate) and fall back to malloc when that fails.
+// kb_map_chunk are asynchronous DMA at full PCIe rate) and fall back to malloc when that fails. Until the CUDA context
+// exists (host_cuda_ready) they are plain page-aligned memory, so that the reader can fill the first batches while the device
+// is being initialised; pin_now() page-locks such an array in place once the context is up.
 void* host_buf_alloc(size_t bytes, bool want_pinned, bool* got_pinned);
 void  host_buf_free(void* p, bool pinned);
+void  host_cuda_ready();
 template <class T> struct HBuf
 {
-	T* p = nullptr; size_t n = 0, cap = 0; bool want_pinned = false, is_pinned = false;
+	T* p = nullptr; size_t n = 0, cap = 0; bool want_pinned = false, is_pinned = false, registered = false;
 	explicit HBuf(bool pin = false) : want_pinned(pin) {}
 	HBuf(const HBuf&) = delete; HBuf& operator=(const HBuf&) = delete;
-	~HBuf() { if (p) host_buf_free(p, is_pinned); }
+	~HBuf() { release(); }
+	void release() { if (p) { if (registered) kb_host_unregister(p); host_buf_free(p, is_pinned); } p = nullptr; registered = false; }
+	void pin_now() { if (want_pinned && !is_pinned && !registered && p && cap) registered = kb_host_register(p, cap * sizeof(T)) == KB_OK; }
 	void reserve(size_t c)
 	{
 		if (c <= cap) return;
 		size_t nc = cap + cap / 2; if (nc < c) nc = c; if (nc < 64) nc = 64;
 		bool pin = false; T* q = (T*)host_buf_alloc(nc * sizeof(T), want_pinned, &pin);
 		if (n) memcpy(q, p, n * sizeof(T));
-		if (p) host_buf_free(p, is_pinned);
+		release();
 		p = q; cap = nc; is_pinned = pin;
 	}
 	void resize(size_t k) { reserve(k); n = k; }                       // new elements are uninitialised

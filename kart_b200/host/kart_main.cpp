@@ -1,6 +1,7 @@
 // Command line of kart_b200: same flags, defaults, messages and exit codes as the reference's src/main.cpp:87-214.
 // `kart index` / `kart update` are not part of the hot path; index files are built with the reference's bwt_index.
 #include "kart_host.h"
+#include <thread>
 #include <ctype.h>
 #include <stdlib.h>
 #include <string.h>
@@ -86,10 +87,14 @@ int main(int argc, char* argv[])
 	if (!check_inputs(o) || !check_output_name(o.out_name)) exit(0);
 	HostIndex idx; std::string err;
 	if (o.index_prefix.empty() || !check_index_files(o.index_prefix)) { fprintf(stdout, "Error! Please specify a valid reference index!\n"); usage(argv[0]); exit(1); }
+	// creating the CUDA context takes about a second on a B200 box: do it while the index files are read (kb_host_alloc
+	// initialises the runtime from any thread, before kb_init)
+	std::thread cuda_warm([]() { kb_host_free(kb_host_alloc(1)); });
 	fprintf(stdout, "Load the genome index files...");
 	bool ok = idx.load(o.index_prefix, err);
 	fprintf(stdout, "\n");
-	if (!ok) { fprintf(stdout, "\n\nError! Index files are corrupt!\n"); exit(1); }
+	if (!ok) { cuda_warm.join(); fprintf(stdout, "\n\nError! Index files are corrupt!\n"); exit(1); }
+	cuda_warm.detach();
 	fprintf(stdout, "Load the reference sequences...\n");
 	return run_mapping(o, idx);
 }

@@ -2,6 +2,7 @@
 // :51-107 entries, :109-143 chunks: entries are fetched two at a time, mate 2 is reverse-complemented at read time).
 #include "kart_host.h"
 #include <algorithm>
+#include <atomic>
 #include <string.h>
 #include <thread>
 #include <stdlib.h>
@@ -322,9 +323,11 @@ int ReadSource::fill(ReadBatch& b, int max_reads, bool pair_end)
 	return fastq ? fill_blocks(b, max_reads, pair_end) : fill_serial(b, max_reads, pair_end);
 }
 
+static std::atomic<bool> g_cuda_ready{false};
+void host_cuda_ready() { g_cuda_ready.store(true); }
 void* host_buf_alloc(size_t bytes, bool want_pinned, bool* got_pinned)
 {
-	void* p = want_pinned ? kb_host_alloc(bytes ? bytes : 1) : nullptr;
+	void* p = (want_pinned && g_cuda_ready.load()) ? kb_host_alloc(bytes ? bytes : 1) : nullptr;   // cudaHostAlloc would block on the context being created
 	*got_pinned = p != nullptr;
 	if (!p && bytes >= (4u << 20))
 	{

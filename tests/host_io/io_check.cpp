@@ -5,6 +5,8 @@
 #include <stdlib.h>
 extern "C" void* kb_host_alloc(uint64_t n) { return malloc(n ? n : 1); }
 extern "C" void kb_host_free(void* p) { free(p); }
+extern "C" int kb_host_register(void*, uint64_t) { return 0; }
+extern "C" void kb_host_unregister(void*) {}
 int main(int argc, char** argv)
 {
 	if (argc < 6) return 2;
