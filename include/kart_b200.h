@@ -102,8 +102,10 @@ void kb_destroy(kb_ctx_t* ctx);
 const char* kb_strerror(int code);
 const char* kb_last_error(kb_ctx_t* ctx);
 
-/* Copies the index to the device and re-blocks it (see kart_b200/csrc/kb_types.h). expand_sa != 0 additionally expands
- * the sampled SA into a full SA on the device (values identical by construction; the .sa file format is untouched). */
+/* Copies the index to the device and re-blocks it (see kart_b200/csrc/kb_types.h). expand_sa = 1 additionally expands
+ * the sampled SA into a full SA on the device (8 bytes per BWT row; values identical by construction, the .sa file format is
+ * untouched): locates become one load, and a search that is down to one row finishes by comparing the read with the text.
+ * expand_sa = 2 does so when the device has the memory to spare (the full SA plus 48 GB for batches), 0 never. */
 int  kb_upload_index(kb_ctx_t* ctx, const kb_index_host_t* idx, int expand_sa);
 int  kb_set_params(kb_ctx_t* ctx, const kb_params_t* p);
 int  kb_get_min_seed_len(kb_ctx_t* ctx);

@@ -583,6 +583,14 @@ int kb_upload_index(kb_ctx_t* ctx, const kb_index_host_t* h, int expand_sa)
 			ix.ktab = ctx->ktab.p; ix.ktab_k = K;
 		}
 	}
+	if (expand_sa == 2)   // auto: only when the full SA leaves room for the batches
+	{
+		size_t free_b = 0, total_b = 0;
+#ifndef KB_EMUL
+		if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 0; }
+#endif
+		expand_sa = ((h->seq_len + 1) * 8ull + (48ull << 30) <= (unsigned long long)free_b) ? 1 : 0;
+	}
 	if (expand_sa)
 	{
 		CK(ctx->sa_full.ensure(h->seq_len + 1));

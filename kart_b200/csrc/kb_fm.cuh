@@ -16,6 +16,8 @@
 #endif
 
 #if defined(__CUDA_ARCH__)
+#define KB_CLZLL(x) __clzll((long long)(x))
+#define KB_CLZ(x) __clz((int)(x))
 #define KB_POPCLL(x) __popcll(x)
 #define KB_LDG4(p) __ldg(p)
 #define KB_LDG(p) __ldg(p)
@@ -29,6 +31,8 @@
 struct uint4 { uint32_t x, y, z, w; };
 #endif
 #define KB_POPCLL(x) __builtin_popcountll(x)
+#define KB_CLZLL(x) ((x) ? __builtin_clzll((unsigned long long)(x)) : 64)
+#define KB_CLZ(x) ((x) ? __builtin_clz((unsigned)(x)) : 32)
 #define KB_LDG4(p) (*(p))
 #define KB_LDG(p) (*(p))
 template <class T, class V> static inline T kb_host_add(T* p, V v) { T o = *p; *p = (T)(o + v); return o; }
@@ -276,6 +280,35 @@ KB_HD u64 kb_sa(const KbIndexDev& ix, u64 k, u32* steps)
 	return s + KB_LDG(ix.sa + k / (u64)ix.sa_intv);
 }
 
+KB_HD u64 kb_ref_win(const KbIndexDev& ix, i64 p, u32* inval);   // kb_align.cuh: 32 characters of the 2G text as 2-bit codes
+
+// A search whose interval has shrunk to ONE row has a single occurrence in the text, at SA[x0]: every further extension step
+// only asks whether the next read base equals the next text base (the text is closed under reverse complement, so the forward
+// extension of P by c succeeds iff P's occurrence is followed by c; it fails at the end of the text, where kb_extend finds the
+// row next to `primary` empty; x0 of a surviving one-row interval never moves). With the full SA in HBM the rest of the search
+// is therefore one 8-byte load and a 32-bases-per-word comparison against the packed reference instead of one Occ block per
+// base: same length, same x0, same step count. Returns the number of bases matched; *fail = stopped by a base that does not
+// extend (what the step loop counts as one more, failed, step), as opposed to the search limit or a non-ACGT read character.
+KB_HD int kb_unique_tail(const KbIndexDev& ix, const KbPk* rd, u64 row, int done, int cur, int lim, bool* fail, u32* blocks)
+{
+	const u64 M5 = 0x5555555555555555ull;
+	const i64 tp = (i64)KB_LDG(ix.sa_full + row) + (i64)done;   // text position facing read position cur
+	*blocks += 1; *fail = false;
+	int m = 0;
+	while (cur + m < lim)
+	{
+		const KbPk rw = kb_read_win(rd, cur + m); u32 ginv; const u64 gw = kb_ref_win(ix, tp + m, &ginv); *blocks += 1;
+		const int want = lim - (cur + m) < 32 ? lim - (cur + m) : 32;
+		u64 x = rw.code ^ gw; x = (x | (x >> 1)) & M5;
+		const int i_mis = x ? (int)KB_CLZLL(x) >> 1 : 32, i_n = rw.n4 ? (int)KB_CLZ(rw.n4) : 32, i_t = ginv ? (int)KB_CLZ(ginv) : 32;
+		int s = i_mis < i_t ? i_mis : i_t; if (i_n < s) s = i_n;
+		if (s >= want) { m += want; continue; }
+		m += s; *fail = i_n != s;   // a non-ACGT read character ends the search without a step (it is looked at first)
+		break;
+	}
+	return m;
+}
+
 // One read: all searches of IdentifySeedPairs_FastMode (:49) or _SensitiveMode (:132) with BWT_Search (:140-170) inlined.
 // The lanes of a warp each own one read and advance in lock-step, one extension per trip. Everything that is not an
 // extension (closing a search: :172-181 and the caller's bookkeeping; opening the next one) is kept out of the extension
@@ -356,7 +389,12 @@ KB_HD void kb_seed_read(const KbIndexDev& ix, const KbParams& pm, const KbBatchD
 			if (searching)
 			{
 				bool ended = true;
-				if (cur < lim)
+				if (cur < lim && x2 == (ROW)1 && ix.sa_full != nullptr)
+				{
+					bool fail; const int m = kb_unique_tail(ix, rd, (u64)x0, cur - pos, cur, lim, &fail, &blocks);
+					cur += m; steps += (u32)m + (fail ? 1u : 0u);
+				}
+				else if (cur < lim)
 				{
 					if ((cur >> 5) != cw) { cw = cur >> 5; KbPk w = kb_load_pk(rd + cw); ccode = w.code; cn4 = w.n4; }
 					const int o = cur & 31;

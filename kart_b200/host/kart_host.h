@@ -101,7 +101,7 @@ struct RunOptions
 	std::string index_prefix, out_name = "output.sam";
 	std::vector<std::string> files1, files2;
 	int threads = 4, max_gaps = 5, out_format = 0, n_gpus = 1; bool pair_flag = false, pacbio = false, multihit = false, silent = false, debug = false;
-	int batch_reads = 1 << 18; bool expand_sa = false;
+	int batch_reads = 1 << 18; int expand_sa = 2;   // 0 sampled SA, 1 full SA in HBM, 2 full SA when the device has room (kb_upload_index)
 };
 
 int run_mapping(const RunOptions& opt, const HostIndex& idx);     // Mapping(), src/Mapping.cpp:639

@@ -188,7 +188,7 @@ int run_mapping(const RunOptions& opt, const HostIndex& idx)
 	if (rc) { fprintf(stderr, "Error! kart_b200 needs a CUDA device: %s\n", kb_strerror(rc)); drain_reader(); return 1; }
 	host_cuda_ready();   // from here on the batch buffers are page-locked at allocation; the ones filled meanwhile are pinned in place below
 	kb_index_host_t hi; idx.describe(&hi);
-	if ((rc = kb_upload_index(ctx, &hi, opt.expand_sa ? 1 : 0)) != 0) { fprintf(stderr, "Error! index upload failed: %s (%s)\n", kb_strerror(rc), kb_last_error(ctx)); drain_reader(); kb_destroy(ctx); return 1; }
+	if ((rc = kb_upload_index(ctx, &hi, opt.expand_sa)) != 0) { fprintf(stderr, "Error! index upload failed: %s (%s)\n", kb_strerror(rc), kb_last_error(ctx)); drain_reader(); kb_destroy(ctx); return 1; }
 
 	if (g_trace) fprintf(stderr, "[kart trace] index uploaded %.3f s\n", now_s() - g_t0);
 	SamSink out; BamWriter bam; const bool to_bam = opt.out_format == 1 && !opt.debug;

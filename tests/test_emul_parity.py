@@ -35,6 +35,11 @@ def test_paired_small_est_and_full_sa(mini):
     r1, r2, _ = synth.simulate(g, 600, 150, 0.02, seed=32)
     m = pu.make_mapper(idx, emul=True, expand_sa=True, paired=True)
     assert pu.compare_pairs(m, pu.Oracle(pu.MINI_PREFIX), pu.interleave(r1, r2), est=470) == 0
+    # with the full SA a search that is down to one row finishes by comparing against the text (kb_unique_tail): same step count
+    m2 = pu.make_mapper(idx, emul=True, expand_sa=False, paired=True)
+    assert pu.compare_pairs(m2, pu.Oracle(pu.MINI_PREFIX), pu.interleave(r1, r2), est=470) == 0
+    assert m.work()["ext_steps"] == m2.work()["ext_steps"] and m.work()["seeds"] == m2.work()["seeds"]
+    assert m.work()["occ_blocks"] < m2.work()["occ_blocks"]
 
 
 def test_single_end_high_error(mini):

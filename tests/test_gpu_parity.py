@@ -57,6 +57,11 @@ def test_paired_full_sa_identical(eco):
     m = pu.make_mapper(idx, expand_sa=True, paired=True)
     assert pu.compare_pairs(m, pu.Oracle(prefix), pu.interleave(r1, r2)) == 0
     assert m.work()["lf_steps"] == 0
+    # one-row searches finish against the text (kb_unique_tail): same searches, same step count, fewer sectors
+    m2 = pu.make_mapper(idx, expand_sa=False, paired=True)
+    assert pu.compare_pairs(m2, pu.Oracle(prefix), pu.interleave(r1, r2)) == 0
+    assert m.work()["ext_steps"] == m2.work()["ext_steps"] and m.work()["seeds"] == m2.work()["seeds"]
+    assert m.work()["occ_blocks"] < m2.work()["occ_blocks"]
 
 
 def test_single_end_high_error_vs_oracle(eco):
