@@ -66,6 +66,28 @@ __global__ void __launch_bounds__(KB_BLOCK, MINB) k_fm_seed(KbIndexDev ix, KbPar
 	kb_warp_add64(&bt.work[0], steps); kb_warp_add64(&bt.work[1], blocks);
 }
 
+// lane-queue seeding (kb_seed_lane): a fixed grid of warps, each with a contiguous range of reads that its lanes draw from
+#ifndef KB_EMUL
+struct KbSeedWarpQ { u32* cnt; u32 end; __device__ __forceinline__ int next() { const u32 k = atomicAdd(cnt, 1u); return k < end ? (int)k : -1; } };
+#endif
+template <int MINB, class ROW>
+__global__ void __launch_bounds__(KB_BLOCK, MINB) k_fm_seed_q(KbIndexDev ix, KbParams pm, KbBatchDev bt)
+{
+	u32 steps = 0, blocks = 0;
+#ifndef KB_EMUL
+	__shared__ u32 cnt[KB_BLOCK / 32];
+	const u32 gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5, wib = threadIdx.x >> 5;
+	const u32 lo = (u32)((u64)bt.n_reads * gwarp / nwarps), hi = (u32)((u64)bt.n_reads * (gwarp + 1) / nwarps);
+	if ((threadIdx.x & 31) == 0) cnt[wib] = lo;
+	__syncwarp();
+	KbSeedWarpQ q; q.cnt = &cnt[wib]; q.end = hi;
+	kb_seed_lane<ROW>(ix, pm, bt, q, &steps, &blocks);
+#else
+	for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < bt.n_reads; r += gridDim.x * blockDim.x) { KbSeedOne q; q.r = r; kb_seed_lane<ROW>(ix, pm, bt, q, &steps, &blocks); }
+#endif
+	kb_warp_add64(&bt.work[0], steps); kb_warp_add64(&bt.work[1], blocks);
+}
+
 __global__ void __launch_bounds__(KB_BLOCK) k_sa_locate(KbIndexDev ix, KbBatchDev bt)
 {
 	long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -395,6 +417,7 @@ struct kb_ctx
 	float stage_ms[9]; uint64_t work_host[8]; u32 counters_host[KB_NCOUNTERS];
 	cudaEvent_t chunk_start = nullptr; int trace = 0;
 	int seed_minb = 10;
+	int seed_queue = 1, seed_warps = 148 * 40;   // lane-queue seeding when the full SA is on the device; warps in its grid (KB_SEED_QUEUE, KB_SEED_WARPS)
 	bool row32 = false;          // BWT row numbers fit 32 bits: k_fm_seed<.., u32> (set at index upload; KB_ROW64=1 forces the 64-bit kernel)
 	int nw_streams = 1;          // 1: the size-class kernels of phase B are forked onto the slot's aux streams and joined before the gather
 	int align_warps = KB_ALIGN_WARPS;   // k_nw_warp
@@ -473,6 +496,8 @@ int kb_init(int device, kb_ctx_t** out)
 	e = getenv("KB_NW_STREAMS"); if (e) ctx->nw_streams = atoi(e) ? 1 : 0;
 	e = getenv("KB_ALIGN_WARPS"); if (e && atoi(e) >= 148 && atoi(e) <= 148 * 64) ctx->align_warps = atoi(e) / 4 * 4;
 	e = getenv("KB_NW_TMAX"); if (e && (atoi(e) == 32 || atoi(e) == 64 || atoi(e) == 128)) ctx->nw_tmax = atoi(e);
+	e = getenv("KB_SEED_QUEUE"); if (e) ctx->seed_queue = atoi(e) ? 1 : 0;
+	e = getenv("KB_SEED_WARPS"); if (e && atoi(e) >= 4 && atoi(e) <= 148 * 64) ctx->seed_warps = atoi(e);
 	e = getenv("KB_NW_WARP_BELOW"); if (e && atoi(e) >= 0) ctx->nw_warp_below = atoi(e);
 	e = getenv("KB_PART_WARPS"); if (e && atoi(e) >= 148 && atoi(e) <= 148 * 64) ctx->part_warps = atoi(e) / 4 * 4;
 	e = getenv("KB_PART_POOL"); if (e && atoi(e) >= 1024 && atoi(e) <= 11264) ctx->part_pool = atoi(e) / 16 * 16;
@@ -752,6 +777,15 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 	sl.launches = 0;
 	CK(cudaEventRecord(sl.ev[0], s));
 	KB_LAUNCH(k_pack, (unsigned)(((long long)n * bt.pk_wpr + KB_BLOCK - 1) / KB_BLOCK), KB_BLOCK, s, bt); sl.launches++;
+	if (ctx->seed_queue && ix.sa_full != nullptr)
+	{
+		// with the full SA most searches finish against the text and reads differ widely in work: lane queue (kb_seed_lane)
+		unsigned warps = (unsigned)((n + 63) / 64); if (warps > (unsigned)ctx->seed_warps) warps = (unsigned)ctx->seed_warps; if (warps < 4) warps = 4;
+		const unsigned gq = (warps + 3) / 4;
+		if (ctx->row32) { if (ctx->seed_minb == 12) { KB_LAUNCH((k_fm_seed_q<12, u32>), gq, KB_BLOCK, s, ix, pm, bt); } else { KB_LAUNCH((k_fm_seed_q<10, u32>), gq, KB_BLOCK, s, ix, pm, bt); } }
+		else { if (ctx->seed_minb == 12) { KB_LAUNCH((k_fm_seed_q<12, u64>), gq, KB_BLOCK, s, ix, pm, bt); } else { KB_LAUNCH((k_fm_seed_q<10, u64>), gq, KB_BLOCK, s, ix, pm, bt); } }
+	}
+	else
 	if (ctx->row32)
 	{
 		if (ctx->seed_minb == 8) { KB_LAUNCH((k_fm_seed<8, u32>), g_reads, KB_BLOCK, s, ix, pm, bt); }

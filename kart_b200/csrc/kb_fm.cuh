@@ -421,6 +421,132 @@ KB_HD void kb_seed_read(const KbIndexDev& ix, const KbParams& pm, const KbBatchD
 	KB_MAX_U32(&bt.counters[5], (u32)ns);
 }
 
+// ---- lane queue -------------------------------------------------------------------------------------------------------
+// With kb_unique_tail most reads need a dozen extension trips, a read inside a repeat family still needs ~150: one read per
+// lane leaves 31 lanes idle behind the slowest. Here a lane that has finished its read draws the next one from its warp's
+// range (Q::next), so the warp lasts as long as its share of the work, not as long as its slowest read. Per outer iteration:
+// one pass in which every lane without a running search does ONE of {finish a one-row search against the text, close a search,
+// open the next search (table lookup), finish the read and load the next} -- the lanes of a pass run converged -- and then
+// extension trips for the lanes that walk the index, at least KB_SEED_TRIPS of them so that a long walk is not throttled to
+// one step per pass. Results per read are identical to kb_seed_read whatever the schedule.
+#define KB_SEED_TRIPS 4
+struct KbSeedOne { int r; KB_HD int next() { int v = r; r = -1; return v; } };   // one read per lane: host emulation, and the reference for the queue
+template <class ROW, class Q>
+KB_HD void kb_seed_lane(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, Q& q, u32* w_steps, u32* w_blocks)
+{
+	const int K = (ix.ktab != nullptr && ix.ktab_k <= pm.min_seed) ? ix.ktab_k : 0;
+	const bool tails = ix.sa_full != nullptr;
+	int r = q.next();
+	const KbPk* rd = bt.pk; KbHit* hits = bt.hits; int rlen = 0, end = 0;
+	int nh = 0, ns = 0, pos = 0, cur = 0, lim = 0, stop = 30, len = 0;
+	u32 steps = 0, blocks = 0;
+	ROW x0 = 0, x1 = 0, x2 = 0;
+	bool searching = false, closing = false, tail = false, finished = r < 0, ovf = false, fresh = !finished;
+	int cw = -1; u64 ccode = 0; u32 cn4 = 0;   // the packed word under the cursor
+#if defined(__CUDA_ARCH__)
+	const u32 quorum = KB_SEED_QUORUM; const int min_trips = KB_SEED_TRIPS;
+#else
+	const u32 quorum = 1; const int min_trips = 1;
+#endif
+	while (KB_BALLOT(!finished))
+	{
+		if (!finished && !searching)
+		{
+			if (fresh)   // a new read
+			{
+				fresh = false;
+				rd = kb_pk_read(bt, r); rlen = (int)(bt.seq_off[r + 1] - bt.seq_off[r]); hits = bt.hits + (size_t)r * bt.max_hits;
+				end = rlen - pm.min_seed; nh = 0; ns = 0; pos = 0; stop = 30; cw = -1; ovf = false; closing = false; tail = false;
+			}
+			if (tail)
+			{
+				tail = false;
+				bool fail; const int m = kb_unique_tail(ix, rd, (u64)x0, cur - pos, cur, lim, &fail, &blocks);
+				cur += m; steps += (u32)m + (fail ? 1u : 0u); len = cur - pos; closing = true;
+			}
+			if (closing)
+			{
+				closing = false;
+				bool hit = len >= pm.min_seed && x2 <= (ROW)50;
+				if (hit)
+				{
+					if (nh < bt.max_hits) { KbHit h; h.x0 = (u64)x0; h.rpos = (u32)pos; h.len_freq = ((u32)len << 8) | (u32)x2; hits[nh++] = h; ns += (int)x2; }
+					else ovf = true;
+				}
+				if (pm.pacbio) { int adv = hit ? len : pm.min_seed; pos += adv; stop += adv; if (stop > rlen) stop = rlen; }
+				else pos += len + 1;
+			}
+			int p = 4;
+			while (pos < end)
+			{
+				if ((pos >> 5) != cw) { cw = pos >> 5; KbPk w = kb_load_pk(rd + cw); ccode = w.code; cn4 = w.n4; }
+				const int o = pos & 31;
+				p = (int)((ccode >> (62 - 2 * o)) & 3u) | (int)(((cn4 >> (31 - o)) & 1u) << 2);
+				if (p <= 3) break;
+				pos++; stop++;
+			}
+			if (pos >= end)   // the read is done: its counts and its slice of the seed arena, then the next read of the warp's range
+			{
+				if (ovf) KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_HITS);
+				bt.n_hits[r] = nh; bt.n_seeds[r] = ns;
+				u32 off = KB_ALLOC(&bt.counters[0], (u32)ns);
+				bt.seed_off[r] = off;
+				if ((u64)off + (u64)ns > (u64)bt.cap_segs) KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SEEDS);
+				KB_MAX_U32(&bt.counters[5], (u32)ns);
+				r = q.next();
+				if (r < 0) finished = true; else fresh = true;
+			}
+			else
+			{
+				lim = pm.pacbio ? (stop < rlen ? stop : rlen) : rlen;
+				bool seeded = false;
+				if (K > 0 && pos + K <= lim)
+				{
+					const KbPk w = kb_read_win(rd, pos);
+					if ((w.n4 >> (32 - K)) == 0)
+					{
+						const KbKtab e = kb_load_ktab(ix.ktab + (u32)(w.code >> (64 - 2 * K))); blocks++;
+						seeded = true;
+						if (e.x2 != 0) { x0 = (ROW)e.x0; x1 = (ROW)e.x1; x2 = (ROW)e.x2; cur = pos + K; steps += (u32)(K - 1); searching = true; }
+						else { closing = true; len = (int)e.flen; steps += e.flen; x2 = 0; }
+					}
+				}
+				if (!seeded) { x0 = (ROW)ix.L2[p] + 1; x1 = (ROW)ix.L2[3 - p] + 1; x2 = (ROW)(ix.L2[p + 1] - ix.L2[p]); cur = pos + 1; searching = true; }
+				if (searching && tails && x2 == (ROW)1 && cur < lim) { searching = false; tail = true; }   // straight to the text
+			}
+		}
+		// extension trips
+		u32 parked, active; int trips = 0;
+		do
+		{
+			if (searching)
+			{
+				bool ended = true;
+				if (cur < lim)
+				{
+					if (tails && x2 == (ROW)1) { tail = true; }
+					else
+					{
+						if ((cur >> 5) != cw) { cw = cur >> 5; KbPk w = kb_load_pk(rd + cw); ccode = w.code; cn4 = w.n4; }
+						const int o = cur & 31;
+						const int c = (int)((ccode >> (62 - 2 * o)) & 3u) | (int)(((cn4 >> (31 - o)) & 1u) << 2);
+						if (c <= 3)
+						{
+							steps++;
+							if (kb_extend(ix, x0, x1, x2, c, &blocks)) { cur++; ended = false; }
+						}
+					}
+				}
+				if (ended) { searching = false; if (!tail) { closing = true; len = cur - pos; } }
+			}
+			trips++;
+			active = KB_BALLOT(searching);
+			parked = KB_BALLOT(!searching && !finished);
+		} while (active != 0 && ((u32)KB_POPCLL((u64)parked) < quorum || trips < min_trips));
+	}
+	*w_steps += steps; *w_blocks += blocks;
+}
+
 // One (read, hit): resolve the SA interval to text positions, in SA-row order (bwt_search.cpp:176-179).
 KB_HD void kb_locate_hit(const KbIndexDev& ix, const KbBatchDev& bt, int r, int h, u32* w_lf)
 {
