@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(KB_BLOCK, MINB) k_fm_seed(KbIndexDev ix, KbPar
 struct KbSeedWarpQ { u32* cnt; u32 end; __device__ __forceinline__ int next() { const u32 k = atomicAdd(cnt, 1u); return k < end ? (int)k : -1; } };
 #endif
 template <int MINB, class ROW>
-__global__ void __launch_bounds__(KB_BLOCK, MINB) k_fm_seed_q(KbIndexDev ix, KbParams pm, KbBatchDev bt)
+__global__ void __launch_bounds__(KB_BLOCK, MINB) k_fm_seed_q(KbIndexDev ix, KbParams pm, KbBatchDev bt, int qp, int qs, int trips)
 {
 	u32 steps = 0, blocks = 0;
 #ifndef KB_EMUL
@@ -81,8 +81,9 @@ __global__ void __launch_bounds__(KB_BLOCK, MINB) k_fm_seed_q(KbIndexDev ix, KbP
 	if ((threadIdx.x & 31) == 0) cnt[wib] = lo;
 	__syncwarp();
 	KbSeedWarpQ q; q.cnt = &cnt[wib]; q.end = hi;
-	kb_seed_lane<ROW>(ix, pm, bt, q, &steps, &blocks);
+	kb_seed_lane<ROW>(ix, pm, bt, q, &steps, &blocks, qp, qs, trips);
 #else
+	(void)qp; (void)qs; (void)trips;
 	for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < bt.n_reads; r += gridDim.x * blockDim.x) { KbSeedOne q; q.r = r; kb_seed_lane<ROW>(ix, pm, bt, q, &steps, &blocks); }
 #endif
 	kb_warp_add64(&bt.work[0], steps); kb_warp_add64(&bt.work[1], blocks);
@@ -417,6 +418,7 @@ struct kb_ctx
 	float stage_ms[9]; uint64_t work_host[8]; u32 counters_host[KB_NCOUNTERS];
 	cudaEvent_t chunk_start = nullptr; int trace = 0;
 	int seed_minb = 10;
+	int seed_qp = 6, seed_qs = 1, seed_trips = 4;   // lane-queue schedule: lanes a pass waits for, lanes a walk waits for, trips per walk (KB_SEED_QP/QS/TRIPS)
 	int seed_queue = 1, seed_warps = 148 * 40;   // lane-queue seeding when the full SA is on the device; warps in its grid (KB_SEED_QUEUE, KB_SEED_WARPS)
 	bool row32 = false;          // BWT row numbers fit 32 bits: k_fm_seed<.., u32> (set at index upload; KB_ROW64=1 forces the 64-bit kernel)
 	int nw_streams = 1;          // 1: the size-class kernels of phase B are forked onto the slot's aux streams and joined before the gather
@@ -497,6 +499,9 @@ int kb_init(int device, kb_ctx_t** out)
 	e = getenv("KB_ALIGN_WARPS"); if (e && atoi(e) >= 148 && atoi(e) <= 148 * 64) ctx->align_warps = atoi(e) / 4 * 4;
 	e = getenv("KB_NW_TMAX"); if (e && (atoi(e) == 32 || atoi(e) == 64 || atoi(e) == 128)) ctx->nw_tmax = atoi(e);
 	e = getenv("KB_SEED_QUEUE"); if (e) ctx->seed_queue = atoi(e) ? 1 : 0;
+	e = getenv("KB_SEED_QP"); if (e && atoi(e) >= 1 && atoi(e) <= 32) ctx->seed_qp = atoi(e);
+	e = getenv("KB_SEED_QS"); if (e && atoi(e) >= 1 && atoi(e) <= 32) ctx->seed_qs = atoi(e);
+	e = getenv("KB_SEED_TRIPS"); if (e && atoi(e) >= 1 && atoi(e) <= 64) ctx->seed_trips = atoi(e);
 	e = getenv("KB_SEED_WARPS"); if (e && atoi(e) >= 4 && atoi(e) <= 148 * 64) ctx->seed_warps = atoi(e);
 	e = getenv("KB_NW_WARP_BELOW"); if (e && atoi(e) >= 0) ctx->nw_warp_below = atoi(e);
 	e = getenv("KB_PART_WARPS"); if (e && atoi(e) >= 148 && atoi(e) <= 148 * 64) ctx->part_warps = atoi(e) / 4 * 4;
@@ -782,8 +787,8 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 		// with the full SA most searches finish against the text and reads differ widely in work: lane queue (kb_seed_lane)
 		unsigned warps = (unsigned)((n + 63) / 64); if (warps > (unsigned)ctx->seed_warps) warps = (unsigned)ctx->seed_warps; if (warps < 4) warps = 4;
 		const unsigned gq = (warps + 3) / 4;
-		if (ctx->row32) { if (ctx->seed_minb == 12) { KB_LAUNCH((k_fm_seed_q<12, u32>), gq, KB_BLOCK, s, ix, pm, bt); } else { KB_LAUNCH((k_fm_seed_q<10, u32>), gq, KB_BLOCK, s, ix, pm, bt); } }
-		else { if (ctx->seed_minb == 12) { KB_LAUNCH((k_fm_seed_q<12, u64>), gq, KB_BLOCK, s, ix, pm, bt); } else { KB_LAUNCH((k_fm_seed_q<10, u64>), gq, KB_BLOCK, s, ix, pm, bt); } }
+		if (ctx->row32) { if (ctx->seed_minb == 12) { KB_LAUNCH((k_fm_seed_q<12, u32>), gq, KB_BLOCK, s, ix, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips); } else { KB_LAUNCH((k_fm_seed_q<10, u32>), gq, KB_BLOCK, s, ix, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips); } }
+		else { if (ctx->seed_minb == 12) { KB_LAUNCH((k_fm_seed_q<12, u64>), gq, KB_BLOCK, s, ix, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips); } else { KB_LAUNCH((k_fm_seed_q<10, u64>), gq, KB_BLOCK, s, ix, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips); } }
 	}
 	else
 	if (ctx->row32)

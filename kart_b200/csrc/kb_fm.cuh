@@ -432,7 +432,7 @@ KB_HD void kb_seed_read(const KbIndexDev& ix, const KbParams& pm, const KbBatchD
 #define KB_SEED_TRIPS 4
 struct KbSeedOne { int r; KB_HD int next() { int v = r; r = -1; return v; } };   // one read per lane: host emulation, and the reference for the queue
 template <class ROW, class Q>
-KB_HD void kb_seed_lane(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, Q& q, u32* w_steps, u32* w_blocks)
+KB_HD void kb_seed_lane(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, Q& q, u32* w_steps, u32* w_blocks, int qp = KB_SEED_QUORUM, int qs = 1, int min_trips_arg = KB_SEED_TRIPS)
 {
 	const int K = (ix.ktab != nullptr && ix.ktab_k <= pm.min_seed) ? ix.ktab_k : 0;
 	const bool tails = ix.sa_full != nullptr;
@@ -444,13 +444,16 @@ KB_HD void kb_seed_lane(const KbIndexDev& ix, const KbParams& pm, const KbBatchD
 	bool searching = false, closing = false, tail = false, finished = r < 0, ovf = false, fresh = !finished;
 	int cw = -1; u64 ccode = 0; u32 cn4 = 0;   // the packed word under the cursor
 #if defined(__CUDA_ARCH__)
-	const u32 quorum = KB_SEED_QUORUM; const int min_trips = KB_SEED_TRIPS;
+	const u32 quorum = (u32)qp, squorum = (u32)qs; const int min_trips = min_trips_arg;
 #else
-	const u32 quorum = 1; const int min_trips = 1;
+	const u32 quorum = 1, squorum = 1; const int min_trips = 1; (void)qp; (void)qs; (void)min_trips_arg;
 #endif
 	while (KB_BALLOT(!finished))
 	{
-		if (!finished && !searching)
+		// a pass is worth its ~400 instructions when enough lanes take part (or nobody is walking the index); the same for trips
+		const u32 parked0 = KB_BALLOT(!searching && !finished), active0 = KB_BALLOT(searching);
+		const bool do_pass = (u32)KB_POPCLL((u64)parked0) >= quorum || active0 == 0;
+		if (do_pass && !finished && !searching)
 		{
 			if (fresh)   // a new read
 			{
@@ -517,6 +520,10 @@ KB_HD void kb_seed_lane(const KbIndexDev& ix, const KbParams& pm, const KbBatchD
 		}
 		// extension trips
 		u32 parked, active; int trips = 0;
+		{
+			const u32 a1 = KB_BALLOT(searching), p1 = KB_BALLOT(!searching && !finished);
+			if (a1 == 0 || (do_pass && (u32)KB_POPCLL((u64)a1) < squorum && (u32)KB_POPCLL((u64)p1) >= quorum)) continue;   // let more lanes join the walk first
+		}
 		do
 		{
 			if (searching)
