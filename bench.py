@@ -271,6 +271,9 @@ def main():
            "gpu_launches": int(work["launches"]) * args.steps, "roofline": roof,
            "stage_ms": per, "mapped_fraction": mapped / n,
            "work_per_step": work, "seed_occ_gbs": alg["fm_seed"] / (per["fm_seed"] / 1e3) / 1e9,
+           # work-equivalent rate: the traffic SURVEY 8(d) assigns to the reference's algorithm (64 B per extension step), which the
+           # unique-tail seeding no longer moves
+           "seed_ref_equiv_gbs": 64.0 * work["ext_steps"] / (per["fm_seed"] / 1e3) / 1e9,
            "nw_gcups": work["nw_cells"] / (per["align"] / 1e3) / 1e9}
     # ---- CPU baseline: the unmodified reference on this box's host cores, bounded sample ----
     if os.path.exists(pu.REF_KART):

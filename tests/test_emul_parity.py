@@ -30,8 +30,11 @@ def test_paired_multi_contig(mini, monkeypatch, row64):
     assert m.work()["rescues"] > 0
 
 
-def test_paired_small_est_and_full_sa(mini):
+@pytest.mark.parametrize("row64", [False, True])
+def test_paired_small_est_and_full_sa(mini, monkeypatch, row64):
     idx, g = mini
+    if row64:
+        monkeypatch.setenv("KB_ROW64", "1")
     r1, r2, _ = synth.simulate(g, 600, 150, 0.02, seed=32)
     m = pu.make_mapper(idx, emul=True, expand_sa=True, paired=True)
     assert pu.compare_pairs(m, pu.Oracle(pu.MINI_PREFIX), pu.interleave(r1, r2), est=470) == 0

@@ -41,12 +41,13 @@ def test_paired_vs_oracle(eco, seed, err, kw):
     assert pu.compare_pairs(m, pu.Oracle(prefix), pu.interleave(r1, r2)) == 0
 
 
-def test_paired_64bit_row_kernel(eco, monkeypatch):
-    """k_fm_seed<.., u64> (what a multi-Gbp index runs; E. coli defaults to the 32-bit row kernel) against the oracle."""
+@pytest.mark.parametrize("full_sa", [False, True])
+def test_paired_64bit_row_kernel(eco, monkeypatch, full_sa):
+    """k_fm_seed<.., u64> and k_fm_seed_q<.., u64> (what a multi-Gbp index runs; E. coli defaults to the 32-bit row kernels) against the oracle."""
     idx, g, prefix = eco
     monkeypatch.setenv("KB_ROW64", "1")
     r1, r2, _ = synth.simulate(g, 6000, 150, 0.03, seed=12, indel=0.002, n_rate=0.002)
-    m = pu.make_mapper(idx, paired=True)
+    m = pu.make_mapper(idx, paired=True, expand_sa=full_sa)
     assert pu.compare_pairs(m, pu.Oracle(prefix), pu.interleave(r1, r2)) == 0
 
 
