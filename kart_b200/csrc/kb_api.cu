@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(KB_BLOCK, MINB) k_fm_seed(KbIndexDev ix, KbPar
 struct KbSeedWarpQ { u32* cnt; u32 end; __device__ __forceinline__ int next() { const u32 k = atomicAdd(cnt, 1u); return k < end ? (int)k : -1; } };
 #endif
 template <int MINB, class ROW>
-__global__ void __launch_bounds__(KB_BLOCK, MINB) k_fm_seed_q(KbIndexDev ix, KbParams pm, KbBatchDev bt, int qp, int qs, int trips)
+__global__ void __launch_bounds__(KB_BLOCK, MINB) k_fm_seed_q(KbIndexDev ix, KbParams pm, KbBatchDev bt, int qp, int qs, int trips, int tail_max)
 {
 	u32 steps = 0, blocks = 0;
 #ifndef KB_EMUL
@@ -81,10 +81,9 @@ __global__ void __launch_bounds__(KB_BLOCK, MINB) k_fm_seed_q(KbIndexDev ix, KbP
 	if ((threadIdx.x & 31) == 0) cnt[wib] = lo;
 	__syncwarp();
 	KbSeedWarpQ q; q.cnt = &cnt[wib]; q.end = hi;
-	kb_seed_lane<ROW>(ix, pm, bt, q, &steps, &blocks, qp, qs, trips);
+	kb_seed_lane<ROW>(ix, pm, bt, q, &steps, &blocks, qp, qs, trips, tail_max);
 #else
-	(void)qp; (void)qs; (void)trips;
-	for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < bt.n_reads; r += gridDim.x * blockDim.x) { KbSeedOne q; q.r = r; kb_seed_lane<ROW>(ix, pm, bt, q, &steps, &blocks); }
+	for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < bt.n_reads; r += gridDim.x * blockDim.x) { KbSeedOne q; q.r = r; kb_seed_lane<ROW>(ix, pm, bt, q, &steps, &blocks, qp, qs, trips, tail_max); }
 #endif
 	kb_warp_add64(&bt.work[0], steps); kb_warp_add64(&bt.work[1], blocks);
 }
@@ -94,6 +93,15 @@ __global__ void __launch_bounds__(KB_BLOCK) k_sa_locate(KbIndexDev ix, KbBatchDe
 	long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	u32 lf = 0;
 	if (t < (long long)bt.n_reads * bt.max_hits) kb_locate_hit(ix, bt, (int)(t / bt.max_hits), (int)(t % bt.max_hits), &lf);
+	kb_warp_add64(&bt.work[2], lf);
+}
+// with the full SA a locate is one load: a thread per (read, search) slot mostly finds nothing to do (3.3 seeds per read against
+// 12 slots), so one thread takes all the searches of its read
+__global__ void __launch_bounds__(KB_BLOCK) k_sa_locate_reads(KbIndexDev ix, KbBatchDev bt)
+{
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	u32 lf = 0;
+	if (r < bt.n_reads) { const int nh = bt.n_hits[r]; for (int h = 0; h < nh; h++) kb_locate_hit(ix, bt, r, h, &lf); }
 	kb_warp_add64(&bt.work[2], lf);
 }
 
@@ -419,6 +427,7 @@ struct kb_ctx
 	cudaEvent_t chunk_start = nullptr; int trace = 0;
 	int seed_minb = 10;
 	int seed_qp = 8, seed_qs = 4, seed_trips = 0;   // trips 0 = 8 with 32-bit rows (small index, instruction-bound), 4 otherwise (r15 A/B)   // lane-queue schedule: lanes a pass waits for, lanes a walk waits for, trips per walk (KB_SEED_QP/QS/TRIPS)
+	int seed_tail = 16;          // a search with at most this many rows left is finished against the text (kb_multi_tail; KB_SEED_TAIL)
 	int seed_queue = 1, seed_warps = 148 * 40;   // lane-queue seeding when the full SA is on the device; warps in its grid (KB_SEED_QUEUE, KB_SEED_WARPS)
 	bool row32 = false;          // BWT row numbers fit 32 bits: k_fm_seed<.., u32> (set at index upload; KB_ROW64=1 forces the 64-bit kernel)
 	int nw_streams = 1;          // 1: the size-class kernels of phase B are forked onto the slot's aux streams and joined before the gather
@@ -502,6 +511,7 @@ int kb_init(int device, kb_ctx_t** out)
 	e = getenv("KB_SEED_QP"); if (e && atoi(e) >= 1 && atoi(e) <= 32) ctx->seed_qp = atoi(e);
 	e = getenv("KB_SEED_QS"); if (e && atoi(e) >= 1 && atoi(e) <= 32) ctx->seed_qs = atoi(e);
 	e = getenv("KB_SEED_TRIPS"); if (e && atoi(e) >= 1 && atoi(e) <= 64) ctx->seed_trips = atoi(e);
+	e = getenv("KB_SEED_TAIL"); if (e && atoi(e) >= 1 && atoi(e) <= 50) ctx->seed_tail = atoi(e);
 	e = getenv("KB_SEED_WARPS"); if (e && atoi(e) >= 4 && atoi(e) <= 148 * 64) ctx->seed_warps = atoi(e);
 	e = getenv("KB_NW_WARP_BELOW"); if (e && atoi(e) >= 0) ctx->nw_warp_below = atoi(e);
 	e = getenv("KB_PART_WARPS"); if (e && atoi(e) >= 148 && atoi(e) <= 148 * 64) ctx->part_warps = atoi(e) / 4 * 4;
@@ -787,8 +797,8 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 		// with the full SA most searches finish against the text and reads differ widely in work: lane queue (kb_seed_lane)
 		unsigned warps = (unsigned)((n + 63) / 64); if (warps > (unsigned)ctx->seed_warps) warps = (unsigned)ctx->seed_warps; if (warps < 4) warps = 4;
 		const unsigned gq = (warps + 3) / 4;
-		if (ctx->row32) { if (ctx->seed_minb == 12) { KB_LAUNCH((k_fm_seed_q<12, u32>), gq, KB_BLOCK, s, ix, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 8 : 4)); } else { KB_LAUNCH((k_fm_seed_q<10, u32>), gq, KB_BLOCK, s, ix, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 8 : 4)); } }
-		else { if (ctx->seed_minb == 12) { KB_LAUNCH((k_fm_seed_q<12, u64>), gq, KB_BLOCK, s, ix, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 8 : 4)); } else { KB_LAUNCH((k_fm_seed_q<10, u64>), gq, KB_BLOCK, s, ix, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 8 : 4)); } }
+		if (ctx->row32) { if (ctx->seed_minb == 12) { KB_LAUNCH((k_fm_seed_q<12, u32>), gq, KB_BLOCK, s, ix, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 8 : 4), ctx->seed_tail); } else { KB_LAUNCH((k_fm_seed_q<10, u32>), gq, KB_BLOCK, s, ix, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 8 : 4), ctx->seed_tail); } }
+		else { if (ctx->seed_minb == 12) { KB_LAUNCH((k_fm_seed_q<12, u64>), gq, KB_BLOCK, s, ix, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 8 : 4), ctx->seed_tail); } else { KB_LAUNCH((k_fm_seed_q<10, u64>), gq, KB_BLOCK, s, ix, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 8 : 4), ctx->seed_tail); } }
 	}
 	else
 	if (ctx->row32)
@@ -805,7 +815,8 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 	}
 	sl.launches++;
 	CK(cudaEventRecord(sl.ev[1], s));
-	KB_LAUNCH(k_sa_locate, g_hits, KB_BLOCK, s, ix, bt); sl.launches++;
+	if (ix.sa_full != nullptr && !pm.pacbio) { KB_LAUNCH(k_sa_locate_reads, g_reads, KB_BLOCK, s, ix, bt); } else { KB_LAUNCH(k_sa_locate, g_hits, KB_BLOCK, s, ix, bt); }
+	sl.launches++;
 	CK(cudaEventRecord(sl.ev[2], s));
 	KB_LAUNCH(k_cand_pair, g_items, KB_BLOCK, s, ix, pm, bt); sl.launches++;
 	if (pm.pacbio) { KB_LAUNCH(k_cand_pacbio, g_slow, KB_BLOCK, s, ix, pm, bt); sl.launches++; }

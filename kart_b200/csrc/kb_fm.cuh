@@ -308,6 +308,22 @@ KB_HD int kb_unique_tail(const KbIndexDev& ix, const KbPk* rd, u64 row, int done
 	}
 	return m;
 }
+// The same for a FEW rows (2 .. KB_SEED_TAIL_MAX occurrences: multi-copy genes, insertion sequences, diverged repeat copies):
+// the walk would go on until no occurrence extends, i.e. for max_i LCP_i bases; the rows it ends with are the occurrences that
+// reach that maximum, and they are contiguous in suffix order, so the new x0 is the old one plus the number of rows in front
+// of the first of them (what kb_extend's `gt` and `primary` terms add up to, step by step).
+KB_HD int kb_multi_tail(const KbIndexDev& ix, const KbPk* rd, u64 row, u32 nrows, int done, int cur, int lim, bool* fail, u32* blocks, u32* first, u32* count)
+{
+	int best = -1; bool bfail = false; u32 bfirst = 0, bcount = 0;
+	for (u32 i = 0; i < nrows; i++)
+	{
+		bool f; const int m = kb_unique_tail(ix, rd, row + i, done, cur, lim, &f, blocks);
+		if (m > best) { best = m; bfail = f; bfirst = i; bcount = 1; }
+		else if (m == best) bcount++;
+	}
+	*fail = bfail; *first = bfirst; *count = bcount;
+	return best;
+}
 
 // One read: all searches of IdentifySeedPairs_FastMode (:49) or _SensitiveMode (:132) with BWT_Search (:140-170) inlined.
 // The lanes of a warp each own one read and advance in lock-step, one extension per trip. Everything that is not an
@@ -432,8 +448,9 @@ KB_HD void kb_seed_read(const KbIndexDev& ix, const KbParams& pm, const KbBatchD
 #define KB_SEED_TRIPS 4
 struct KbSeedOne { int r; KB_HD int next() { int v = r; r = -1; return v; } };   // one read per lane: host emulation, and the reference for the queue
 template <class ROW, class Q>
-KB_HD void kb_seed_lane(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, Q& q, u32* w_steps, u32* w_blocks, int qp = KB_SEED_QUORUM, int qs = 1, int min_trips_arg = KB_SEED_TRIPS)
+KB_HD void kb_seed_lane(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, Q& q, u32* w_steps, u32* w_blocks, int qp = KB_SEED_QUORUM, int qs = 1, int min_trips_arg = KB_SEED_TRIPS, int tail_max = 1)
 {
+	const ROW tmax = (ROW)(tail_max < 1 ? 1 : tail_max);
 	const int K = (ix.ktab != nullptr && ix.ktab_k <= pm.min_seed) ? ix.ktab_k : 0;
 	const bool tails = ix.sa_full != nullptr;
 	int r = q.next();
@@ -464,7 +481,9 @@ KB_HD void kb_seed_lane(const KbIndexDev& ix, const KbParams& pm, const KbBatchD
 			if (tail)
 			{
 				tail = false;
-				bool fail; const int m = kb_unique_tail(ix, rd, (u64)x0, cur - pos, cur, lim, &fail, &blocks);
+				bool fail; int m;
+				if (x2 == (ROW)1) m = kb_unique_tail(ix, rd, (u64)x0, cur - pos, cur, lim, &fail, &blocks);
+				else { u32 first, count; m = kb_multi_tail(ix, rd, (u64)x0, (u32)x2, cur - pos, cur, lim, &fail, &blocks, &first, &count); x0 += (ROW)first; x2 = (ROW)count; }
 				cur += m; steps += (u32)m + (fail ? 1u : 0u); len = cur - pos; closing = true;
 			}
 			if (closing)
@@ -515,7 +534,7 @@ KB_HD void kb_seed_lane(const KbIndexDev& ix, const KbParams& pm, const KbBatchD
 					}
 				}
 				if (!seeded) { x0 = (ROW)ix.L2[p] + 1; x1 = (ROW)ix.L2[3 - p] + 1; x2 = (ROW)(ix.L2[p + 1] - ix.L2[p]); cur = pos + 1; searching = true; }
-				if (searching && tails && x2 == (ROW)1 && cur < lim) { searching = false; tail = true; }   // straight to the text
+				if (searching && tails && x2 <= tmax && cur < lim) { searching = false; tail = true; }   // straight to the text
 			}
 		}
 		// extension trips
@@ -531,7 +550,7 @@ KB_HD void kb_seed_lane(const KbIndexDev& ix, const KbParams& pm, const KbBatchD
 				bool ended = true;
 				if (cur < lim)
 				{
-					if (tails && x2 == (ROW)1) { tail = true; }
+					if (tails && x2 <= tmax) { tail = true; }
 					else
 					{
 						if ((cur >> 5) != cw) { cw = cur >> 5; KbPk w = kb_load_pk(rd + cw); ccode = w.code; cn4 = w.n4; }
