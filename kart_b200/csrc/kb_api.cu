@@ -68,20 +68,39 @@ __global__ void __launch_bounds__(KB_BLOCK, MINB) k_fm_seed(KbIndexDev ix, KbPar
 
 // lane-queue seeding (kb_seed_lane): a fixed grid of warps, each with a contiguous range of reads that its lanes draw from
 #ifndef KB_EMUL
-struct KbSeedWarpQ { u32* cnt; u32 end; __device__ __forceinline__ int next() { const u32 k = atomicAdd(cnt, 1u); return k < end ? (int)k : -1; } };
+// reads come from the warp's range through a shared-memory counter; seed slices are handed out from a shared-memory cursor
+// relative to the warp's slab, which gets its place in the arena with ONE global atomic when the warp is done (a global
+// atomic per read, from two or three lanes at a time, was 12 % of the kernel's stall samples: ncu r15)
+struct KbSeedWarpQ
+{
+	u32* cnt; u32 end; u32* seeds; u32 max_ns;
+	__device__ __forceinline__ int next() { const u32 k = atomicAdd(cnt, 1u); return k < end ? (int)k : -1; }
+	__device__ __forceinline__ void store(const KbBatchDev& bt, int rd, int ns) { bt.seed_off[rd] = atomicAdd(seeds, (u32)ns); if ((u32)ns > max_ns) max_ns = (u32)ns; }
+};
 #endif
 template <int MINB, class ROW>
 __global__ void __launch_bounds__(KB_BLOCK, MINB) k_fm_seed_q(KbIndexDev ix, KbParams pm, KbBatchDev bt, int qp, int qs, int trips, int tail_max)
 {
 	u32 steps = 0, blocks = 0;
 #ifndef KB_EMUL
-	__shared__ u32 cnt[KB_BLOCK / 32];
-	const u32 gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5, wib = threadIdx.x >> 5;
+	__shared__ u32 cnt[KB_BLOCK / 32], wseeds[KB_BLOCK / 32];
+	const u32 gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5, wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const u32 lo = (u32)((u64)bt.n_reads * gwarp / nwarps), hi = (u32)((u64)bt.n_reads * (gwarp + 1) / nwarps);
-	if ((threadIdx.x & 31) == 0) cnt[wib] = lo;
+	if (lane == 0) { cnt[wib] = lo; wseeds[wib] = 0; }
 	__syncwarp();
-	KbSeedWarpQ q; q.cnt = &cnt[wib]; q.end = hi;
+	KbSeedWarpQ q; q.cnt = &cnt[wib]; q.end = hi; q.seeds = &wseeds[wib]; q.max_ns = 0;
 	kb_seed_lane<ROW>(ix, pm, bt, q, &steps, &blocks, qp, qs, trips, tail_max);
+	__syncwarp();
+	{
+		const u32 total = wseeds[wib]; u32 base = 0;
+		if (lane == 0 && total) base = atomicAdd(&bt.counters[0], total);
+		base = __shfl_sync(0xFFFFFFFFu, base, 0);
+		if (total) for (u32 r = lo + lane; r < hi; r += 32) bt.seed_off[r] += base;
+		if (lane == 0 && (u64)base + (u64)total > (u64)bt.cap_segs) atomicOr(&bt.counters[3], (u32)KB_OVF_SEEDS);
+		u32 m = q.max_ns;
+		for (int o = 16; o > 0; o >>= 1) { const u32 v = __shfl_xor_sync(0xFFFFFFFFu, m, o); if (v > m) m = v; }
+		if (lane == 0 && m) atomicMax(&bt.counters[5], m);
+	}
 #else
 	for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < bt.n_reads; r += gridDim.x * blockDim.x) { KbSeedOne q; q.r = r; kb_seed_lane<ROW>(ix, pm, bt, q, &steps, &blocks, qp, qs, trips, tail_max); }
 #endif
@@ -427,7 +446,7 @@ struct kb_ctx
 	cudaEvent_t chunk_start = nullptr; int trace = 0;
 	int seed_minb = 10;
 	int seed_qp = 8, seed_qs = 4, seed_trips = 0;   // trips 0 = 8 with 32-bit rows (small index, instruction-bound), 4 otherwise (r15 A/B)   // lane-queue schedule: lanes a pass waits for, lanes a walk waits for, trips per walk (KB_SEED_QP/QS/TRIPS)
-	int seed_tail = 16;          // a search with at most this many rows left is finished against the text (kb_multi_tail; KB_SEED_TAIL)
+	int seed_tail = 1;           // a search with at most this many rows left is finished against the text (1: kb_unique_tail only; >1: kb_multi_tail, measured slower at 4..50 in r16, kept as a knob: KB_SEED_TAIL)
 	int seed_queue = 1, seed_warps = 148 * 40;   // lane-queue seeding when the full SA is on the device; warps in its grid (KB_SEED_QUEUE, KB_SEED_WARPS)
 	bool row32 = false;          // BWT row numbers fit 32 bits: k_fm_seed<.., u32> (set at index upload; KB_ROW64=1 forces the 64-bit kernel)
 	int nw_streams = 1;          // 1: the size-class kernels of phase B are forked onto the slot's aux streams and joined before the gather

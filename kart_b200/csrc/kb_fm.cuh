@@ -446,7 +446,18 @@ KB_HD void kb_seed_read(const KbIndexDev& ix, const KbParams& pm, const KbBatchD
 // extension trips for the lanes that walk the index, at least KB_SEED_TRIPS of them so that a long walk is not throttled to
 // one step per pass. Results per read are identical to kb_seed_read whatever the schedule.
 #define KB_SEED_TRIPS 4
-struct KbSeedOne { int r; KB_HD int next() { int v = r; r = -1; return v; } };   // one read per lane: host emulation, and the reference for the queue
+struct KbSeedOne   // one read per lane: host emulation, and the reference for the queue
+{
+	int r;
+	KB_HD int next() { int v = r; r = -1; return v; }
+	KB_HD void store(const KbBatchDev& bt, int rd, int ns)   // the read's slice of the seed arena, from the grid-wide cursor
+	{
+		u32 off = KB_ALLOC(&bt.counters[0], (u32)ns);
+		bt.seed_off[rd] = off;
+		if ((u64)off + (u64)ns > (u64)bt.cap_segs) KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SEEDS);
+		KB_MAX_U32(&bt.counters[5], (u32)ns);
+	}
+};
 template <class ROW, class Q>
 KB_HD void kb_seed_lane(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, Q& q, u32* w_steps, u32* w_blocks, int qp = KB_SEED_QUORUM, int qs = 1, int min_trips_arg = KB_SEED_TRIPS, int tail_max = 1)
 {
@@ -511,10 +522,7 @@ KB_HD void kb_seed_lane(const KbIndexDev& ix, const KbParams& pm, const KbBatchD
 			{
 				if (ovf) KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_HITS);
 				bt.n_hits[r] = nh; bt.n_seeds[r] = ns;
-				u32 off = KB_ALLOC(&bt.counters[0], (u32)ns);
-				bt.seed_off[r] = off;
-				if ((u64)off + (u64)ns > (u64)bt.cap_segs) KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SEEDS);
-				KB_MAX_U32(&bt.counters[5], (u32)ns);
+				q.store(bt, r, ns);
 				r = q.next();
 				if (r < 0) finished = true; else fresh = true;
 			}
