@@ -445,7 +445,7 @@ struct kb_ctx
 	float stage_ms[9]; uint64_t work_host[8]; u32 counters_host[KB_NCOUNTERS];
 	cudaEvent_t chunk_start = nullptr; int trace = 0;
 	int seed_minb = 10;
-	int seed_qp = 8, seed_qs = 4, seed_trips = 0;   // trips 0 = 8 with 32-bit rows (small index, instruction-bound), 4 otherwise (r15 A/B)   // lane-queue schedule: lanes a pass waits for, lanes a walk waits for, trips per walk (KB_SEED_QP/QS/TRIPS)
+	int seed_qp = 8, seed_qs = 4, seed_trips = 0;   // trips 0 = 6 with 32-bit rows (small index, instruction-bound), 2 otherwise (r16 A/B)   // lane-queue schedule: lanes a pass waits for, lanes a walk waits for, trips per walk (KB_SEED_QP/QS/TRIPS)
 	int seed_tail = 1;           // a search with at most this many rows left is finished against the text (1: kb_unique_tail only; >1: kb_multi_tail, measured slower at 4..50 in r16, kept as a knob: KB_SEED_TAIL)
 	int seed_queue = 1, seed_warps = 148 * 40;   // lane-queue seeding when the full SA is on the device; warps in its grid (KB_SEED_QUEUE, KB_SEED_WARPS)
 	bool row32 = false;          // BWT row numbers fit 32 bits: k_fm_seed<.., u32> (set at index upload; KB_ROW64=1 forces the 64-bit kernel)
@@ -816,8 +816,8 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 		// with the full SA most searches finish against the text and reads differ widely in work: lane queue (kb_seed_lane)
 		unsigned warps = (unsigned)((n + 63) / 64); if (warps > (unsigned)ctx->seed_warps) warps = (unsigned)ctx->seed_warps; if (warps < 4) warps = 4;
 		const unsigned gq = (warps + 3) / 4;
-		if (ctx->row32) { if (ctx->seed_minb == 12) { KB_LAUNCH((k_fm_seed_q<12, u32>), gq, KB_BLOCK, s, ix, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 8 : 4), ctx->seed_tail); } else { KB_LAUNCH((k_fm_seed_q<10, u32>), gq, KB_BLOCK, s, ix, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 8 : 4), ctx->seed_tail); } }
-		else { if (ctx->seed_minb == 12) { KB_LAUNCH((k_fm_seed_q<12, u64>), gq, KB_BLOCK, s, ix, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 8 : 4), ctx->seed_tail); } else { KB_LAUNCH((k_fm_seed_q<10, u64>), gq, KB_BLOCK, s, ix, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 8 : 4), ctx->seed_tail); } }
+		if (ctx->row32) { if (ctx->seed_minb == 12) { KB_LAUNCH((k_fm_seed_q<12, u32>), gq, KB_BLOCK, s, ix, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 6 : 2), ctx->seed_tail); } else { KB_LAUNCH((k_fm_seed_q<10, u32>), gq, KB_BLOCK, s, ix, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 6 : 2), ctx->seed_tail); } }
+		else { if (ctx->seed_minb == 12) { KB_LAUNCH((k_fm_seed_q<12, u64>), gq, KB_BLOCK, s, ix, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 6 : 2), ctx->seed_tail); } else { KB_LAUNCH((k_fm_seed_q<10, u64>), gq, KB_BLOCK, s, ix, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 6 : 2), ctx->seed_tail); } }
 	}
 	else
 	if (ctx->row32)
