@@ -84,11 +84,15 @@ def test_all_nw_size_classes(mini, monkeypatch):
     assert (seen > 0).all(), seen
 
 
-def test_edge_reads(mini):
+@pytest.mark.parametrize("full_sa", [False, True])
+def test_edge_reads(mini, full_sa):
+    """Degenerate reads; with the full SA they go through the lane-queue seeding and its text comparison (kb_unique_tail)."""
     idx, g = mini
-    m = pu.make_mapper(idx, emul=True, paired=False)
+    m = pu.make_mapper(idx, emul=True, paired=False, expand_sa=full_sa)
     reads = [b"A", b"ACGTACGTACGTAC", b"N" * 60, g[0][:150].tobytes(), g[2][-150:].tobytes(), g[1][100:113].tobytes(),
-             (g[0][3000:3075].tobytes() + g[1][500:575].tobytes()), g[0][200:350].tobytes().lower(), b"ACGTRYKM" * 15]
+             (g[0][3000:3075].tobytes() + g[1][500:575].tobytes()), g[0][200:350].tobytes().lower(), b"ACGTRYKM" * 15,
+             g[0][-80:].tobytes() + g[1][:70].tobytes(), synth.revcomp_bytes(g[2][-100:]).tobytes() + b"ACGT" * 5,
+             g[1][1000:1100].tobytes() + b"N" + g[1][1101:1200].tobytes()]   # contig junction, end of the text on the reverse strand, N inside a unique match
     assert pu.compare_singles(m, pu.Oracle(pu.MINI_PREFIX), reads) == 0
     aln, pairs, cig = m.map_chunk(np.zeros(0, np.uint8), np.zeros(1, np.uint64))
     assert len(aln) == 0
