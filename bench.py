@@ -37,10 +37,11 @@ def ncu_traffic(kernel, reads, syn):
     f = max(files, key=lambda p: int(re.findall(r"r(\d+)", os.path.basename(p))[0]))
     d = json.load(open(f))
     norm = {re.sub(r"^void |<.*$", "", name): v for name, v in d["kernels"].items()}   # "void k_fm_seed<10>" -> "k_fm_seed"
-    k = norm.get(kernel)
+    k = norm.get(kernel) or norm.get(kernel + "_q")   # k_fm_seed_q: the lane-queue seeding kernel
     if not k:
         return None, None
-    cap_reads = k["grid"] * k.get("block", 128)
+    per_read = norm.get("k_segments") or k                # one thread per read there; k_fm_seed_q runs a fixed grid
+    cap_reads = per_read["grid"] * per_read.get("block", 128)
     return k["dram_bytes"] * reads / cap_reads, "%s (captured at %d reads/launch, scaled by reads)" % (os.path.basename(f), cap_reads)
 
 
@@ -126,6 +127,30 @@ def time_reference(prefix, r1, r2, pos, sample_pairs, threads, tmp):
     return 2 * sample_pairs / max(total - load, 1e-6), total, load
 
 
+def bind_to_gpu_numa_node(local):
+    """Pins this rank to the cores of the NUMA node its GPU hangs off, BEFORE the pinned host buffers are allocated (first touch
+    places them there): with 8 ranks each moving 0.46 GB per step over PCIe, remote-node buffers halve the end-to-end rate.
+    Best effort: returns a short description, or None when the topology cannot be read."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return "numa node %d (%d cpus) for %s" % (node, len(cpus), bdf)
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -176,7 +201,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; kart_b200 has no CPU path")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     prefix, idx, r1, r2, pos = workload(args.pairs, 1 + rank, args.prefix, args.error)
     reads = pu.interleave(r1, r2)
@@ -264,6 +292,8 @@ def main():
         roof["random_sector_peak"] = rs
         if args.prefix:
             roof["frac_of_random_sector_peak"] = achieved / rs["independent_gbs"]
+    if numa:
+        config["host_binding"] = "each rank bound to its GPU's " + numa.split(" for ")[0]
     out = {"metric": "mapped reads/s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64/int32", "data": "synthetic",
            "config": config, "clocks": sampler.summary(),
