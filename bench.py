@@ -202,9 +202,13 @@ def main():
         raise SystemExit("bench.py: no CUDA device; kart_b200 has no CPU path")
     torch.cuda.set_device(local)
     numa = bind_to_gpu_numa_node(local) if world > 1 else None
+    json_fd = 1
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # NCCL writes its version banner to stdout; rank 0 must print ONE JSON line there: libraries get stderr as their stdout,
+        # the JSON line goes to the saved descriptor
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     prefix, idx, r1, r2, pos = workload(args.pairs, 1 + rank, args.prefix, args.error)
     reads = pu.interleave(r1, r2)
@@ -314,7 +318,8 @@ def main():
                                "sample": "%d reads (first %d pairs of the step's batch), oracle/_ref/kart -t %d, %.2f s map + %.2f s index load (subtracted)" % (2 * sp, sp, ncores, total - load, load)}
     else:
         out["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": ncores, "kind": "reference", "sample": "oracle/_ref/kart not built"}
-    print(json.dumps(out))
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
