@@ -37,13 +37,13 @@ KB_HD int kb_rescue_cluster(const KbParams& pm, const KbBatchDev& bt, i64 left, 
 // enumerated by kb_rescue_plan below). The threads share the work: look every window 8-mer up in a small index of the mate's
 // 8-mers and extend the run starts. The record lives in shared memory; the phases are plain functions of (record, tid, nth)
 // that the host-emulation build can replay.
-struct KbRescueJob
+struct KbRescueJob   // one reference window of one rescue job
 {
-	i32 p, ra, rb, n1, n2, n1o, n2o, l1, l2, est, sc1, sc2, strategy, attempted, mated;
-	i32 side, idx, thr, next_new, done, ovf, clean, mclean, slen, cap_pairs, ml, reindex, hmask;
+	i32 p, ra, rb, l1, l2;           // the pair, its two reads and their lengths
+	i32 side, idx;                   // 0: read 2 is searched around candidate idx of read 1 ; 1: the other way round
+	i32 done, ovf, clean, mclean, slen, cap_pairs, ml, reindex, hmask;
 	u32 npairs;
 	i64 left;
-	u64 arena_used;
 	u32* wm; u8* win; u32* ww; KbSeg* pairs;
 	u32* hkey; i32* hhead; i32* hnext;   // open-addressing index of the mate's 8-mers: id+1 per slot, chain of positions per slot
 	const u8* mate; const KbPk* mate_pk;

@@ -188,6 +188,7 @@ def smoke_check(n_pairs: int = 256):
     genome = genome_of(idx)
     r1, r2, _ = synth.simulate(genome, n_pairs, 150, 0.02, seed=11, indel=0.002)
     reads = interleave(r1, r2)
-    m = make_mapper(idx, paired=True)
     orc = Oracle(default_prefix())
-    return compare_pairs(m, orc, reads), n_pairs
+    bad = compare_pairs(make_mapper(idx, paired=True), orc, reads)                    # sampled SA: k_fm_seed, k_sa_locate
+    bad += compare_pairs(make_mapper(idx, paired=True, expand_sa=True), orc, reads)   # full SA: k_fm_seed_q (what bench.py runs), k_sa_locate_reads
+    return bad, n_pairs
