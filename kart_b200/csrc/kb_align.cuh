@@ -716,6 +716,22 @@ KB_HD void kb_classify_segment(const KbIndexDev& ix, const KbParams& pm, const K
 
 // phase A
 #define KB_SEG_FAST 8   // candidates with at most this many seeds are expanded in local memory instead of the HBM arena
+// Classified-segment slots. Lanes arrive here one or two at a time, so warp aggregation does not help and the grid-wide cursor
+// takes one atomic per candidate (ncu r16: the allocation sites are ~45 % of k_segments' stall samples). With KB_SEG_SLAB the
+// warp reserves a range up front (one global atomic) and its lanes take slots from it through shared memory; a warp that runs
+// out falls back to the cursor. Holes are harmless: every consumer goes through cseg_off / cseg_n. Off by default until it has
+// been measured (next round's A/B).
+KB_HD u32 kb_alloc_segx(const KbBatchDev& bt, u32 n)
+{
+#if defined(__CUDA_ARCH__)
+	if (bt.segx_slab != nullptr)
+	{
+		const u32 at = atomicAdd(&bt.segx_slab[0], n);
+		if (at + n <= bt.segx_slab[1]) return at;
+	}
+#endif
+	return KB_ALLOC(&bt.counters[8], n);
+}
 KB_HD void kb_segments_cand(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int r, const u8* seq, const KbPk* rd, int rlen,
                             u32 ci, const KbCand& c, KbSeg* in, KbSeg* sv, i32* order)
 {
@@ -723,7 +739,7 @@ KB_HD void kb_segments_cand(const KbIndexDev& ix, const KbParams& pm, const KbBa
 	for (int k = 0; k < ns; k++) in[k] = bt.segs[c.seg_start + k];
 	int n = kb_fill_pairs(rlen, -1, in, ns, sv, order);
 	if (!kb_same_chromosome(ix, sv, n)) return;
-	u32 off = KB_ALLOC(&bt.counters[8], (u32)n);
+	u32 off = kb_alloc_segx(bt, (u32)n);
 	if ((u64)off + (u64)n > (u64)bt.cap_segx) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SEGX); return; }
 	bt.cseg_off[ci] = off; bt.cseg_n[ci] = n;
 	for (int j = 0; j < n; j++) kb_classify_segment(ix, pm, bt, r, seq, rd, sv[j], j, n, &bt.segx[off + j]);
@@ -759,7 +775,7 @@ KB_HD bool kb_segments_cand_stream(const KbIndexDev& ix, const KbParams& pm, con
 		int ea = kb_chr_lookup(ix, a), eb = kb_chr_lookup(ix, b);
 		if (!(ea < ix.n_ends && eb < ix.n_ends && ix.end_chr[ea] == ix.end_chr[eb])) return true;
 	}
-	u32 off = KB_ALLOC(&bt.counters[8], (u32)n);
+	u32 off = kb_alloc_segx(bt, (u32)n);
 	if ((u64)off + (u64)n > (u64)bt.cap_segx) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SEGX); return true; }
 	bt.cseg_off[ci] = off; bt.cseg_n[ci] = n;
 	// one loop, one call site of kb_classify_segment: the lanes of a warp then classify their j-th segments together,

@@ -224,7 +224,22 @@ static void k_rescue_win(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulati
 	}
 }
 #endif
-__global__ void __launch_bounds__(KB_BLOCK) k_segments(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_segments(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x); }
+__global__ void __launch_bounds__(KB_BLOCK) k_segments(KbIndexDev ix, KbParams pm, KbBatchDev bt, int slab)
+{
+#ifndef KB_EMUL
+	__shared__ u32 range[KB_BLOCK / 32][2];
+	if (slab > 0)   // kb_alloc_segx
+	{
+		const int wib = threadIdx.x >> 5;
+		if ((threadIdx.x & 31) == 0) { const u32 b = atomicAdd(&bt.counters[8], (u32)slab); range[wib][0] = b; range[wib][1] = b + (u32)slab; }
+		__syncwarp();
+		bt.segx_slab = &range[wib][0];
+	}
+#else
+	(void)slab;
+#endif
+	kb_stage_segments(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x);
+}
 __global__ void __launch_bounds__(KB_BLOCK) k_segments_slow(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_segments_slow(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
 // phase B (kb_align.cuh "phase B"): partition -> nw_alignment problems by size class -> gather
 #ifndef KB_EMUL
@@ -446,6 +461,7 @@ struct kb_ctx
 	cudaEvent_t chunk_start = nullptr; int trace = 0;
 	int seed_minb = 10;
 	int seed_qp = 8, seed_qs = 4, seed_trips = 0;   // trips 0 = 6 with 32-bit rows (small index, instruction-bound), 2 otherwise (r16 A/B)   // lane-queue schedule: lanes a pass waits for, lanes a walk waits for, trips per walk (KB_SEED_QP/QS/TRIPS)
+	int seg_slab = 0;            // segx slots a warp of k_segments reserves up front (0: none; KB_SEG_SLAB, see kb_alloc_segx)
 	int seed_tail = 1;           // a search with at most this many rows left is finished against the text (1: kb_unique_tail only; >1: kb_multi_tail, measured slower at 4..50 in r16, kept as a knob: KB_SEED_TAIL)
 	int seed_queue = 1, seed_warps = 148 * 40;   // lane-queue seeding when the full SA is on the device; warps in its grid (KB_SEED_QUEUE, KB_SEED_WARPS)
 	bool row32 = false;          // BWT row numbers fit 32 bits: k_fm_seed<.., u32> (set at index upload; KB_ROW64=1 forces the 64-bit kernel)
@@ -530,6 +546,7 @@ int kb_init(int device, kb_ctx_t** out)
 	e = getenv("KB_SEED_QP"); if (e && atoi(e) >= 1 && atoi(e) <= 32) ctx->seed_qp = atoi(e);
 	e = getenv("KB_SEED_QS"); if (e && atoi(e) >= 1 && atoi(e) <= 32) ctx->seed_qs = atoi(e);
 	e = getenv("KB_SEED_TRIPS"); if (e && atoi(e) >= 1 && atoi(e) <= 64) ctx->seed_trips = atoi(e);
+	e = getenv("KB_SEG_SLAB"); if (e && atoi(e) >= 0 && atoi(e) <= 4096) ctx->seg_slab = atoi(e);
 	e = getenv("KB_SEED_TAIL"); if (e && atoi(e) >= 1 && atoi(e) <= 50) ctx->seed_tail = atoi(e);
 	e = getenv("KB_SEED_WARPS"); if (e && atoi(e) >= 4 && atoi(e) <= 148 * 64) ctx->seed_warps = atoi(e);
 	e = getenv("KB_NW_WARP_BELOW"); if (e && atoi(e) >= 0) ctx->nw_warp_below = atoi(e);
@@ -721,7 +738,7 @@ static int alloc_batch(kb_ctx* ctx, kb_slot& sl, int shared)
 	sl.cap_cands = 2 * sl.cap_segs + 2 * n + 1024;
 	if (sl.cap_cands > 0xF0000000ull) sl.cap_cands = 0xF0000000ull;
 	sl.cap_cigar = (size_t)(ctx->cigar_factor * (double)n) + (ctx->pm.pacbio ? (size_t)n * (size_t)(L / 2) : 0) + 65536;
-	sl.cap_segx = (size_t)(ctx->segx_factor * (double)n) + (ctx->pm.pacbio ? (size_t)n * (size_t)(L / 16 + 64) : 0) + 65536;
+	sl.cap_segx = (size_t)(ctx->segx_factor * (double)n) + (ctx->pm.pacbio ? (size_t)n * (size_t)(L / 16 + 64) : 0) + 65536 + (size_t)ctx->seg_slab * (n / 32 + 4);
 	sl.cap_jobs = (size_t)(ctx->job_factor * (double)n) + (ctx->pm.pacbio ? (size_t)n * (size_t)(L / 32 + 32) : 0) + 65536;
 	sl.cap_pieces = 2 * sl.cap_jobs;
 	sl.cap_runs = (size_t)(ctx->run_factor * (double)n) + (ctx->pm.pacbio ? (size_t)n * (size_t)(3 * L) : 0) + (1 << 20);
@@ -743,7 +760,7 @@ static int alloc_batch(kb_ctx* ctx, kb_slot& sl, int shared)
 	CK(sl.n_cands.ensure(n)); CK(sl.cand_off.ensure(n)); CK(sl.cand_cap.ensure(n)); CK(sl.rescue.ensure(n / 2 + 1));
 	sl.cap_rtasks = ctx->pm.paired ? (size_t)(ctx->rtask_factor * (double)n) + 65536 : 1;
 	CK(sl.rtasks.ensure(sl.cap_rtasks)); CK(sl.rjob_first.ensure(n / 2 + 1)); CK(sl.rjob_count.ensure(n / 2 + 1));
-	bt.rtasks = sl.rtasks.p; bt.cap_rtasks = (u32)sl.cap_rtasks; bt.rjob_first = sl.rjob_first.p; bt.rjob_count = sl.rjob_count.p;
+	bt.segx_slab = nullptr; bt.rtasks = sl.rtasks.p; bt.cap_rtasks = (u32)sl.cap_rtasks; bt.rjob_first = sl.rjob_first.p; bt.rjob_count = sl.rjob_count.p;
 	CK(sl.res.ensure(n)); CK(sl.pstat.ensure(n / 2 + 1)); CK(sl.aln.ensure(n));
 	if (!shared) CK(sl.cigar.ensure(sl.cap_cigar));
 	sl.cap_extra = ctx->pm.multihit ? (size_t)(ctx->extra_factor * (double)n) + 65536 : 0;
@@ -848,7 +865,7 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 		KB_LAUNCH(k_rescue_commit, 148 * 4, KB_BLOCK, s, ix, pm, bt); sl.launches++;
 	}
 	CK(cudaEventRecord(sl.ev[4], s));
-	KB_LAUNCH(k_segments, g_reads, KB_BLOCK, s, ix, pm, bt); sl.launches++;
+	KB_LAUNCH(k_segments, g_reads, KB_BLOCK, s, ix, pm, bt, ctx->seg_slab); sl.launches++;
 	KB_LAUNCH(k_segments_slow, g_slow, KB_BLOCK, s, ix, pm, bt); sl.launches++;
 	CK(cudaEventRecord(sl.ev[5], s));
 #ifndef KB_EMUL

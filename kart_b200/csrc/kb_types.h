@@ -110,6 +110,7 @@ struct KbBatchDev
 	// stage 2
 	KbCand* cands; u32 cap_cands; i32* n_cands; u32* cand_off; i32* cand_cap;
 	i32* rescue_list;                   // pair ids that need rescue
+	u32* segx_slab;                     // {next, end} of the calling warp's reserved range of segx (shared memory; NULL: none). Set by k_segments
 	KbRTask* rtasks; u32 cap_rtasks;    // rescue windows (cursor: counters[27]); a job's tasks are rtasks[rjob_first[k] .. + rjob_count[k])
 	u32* rjob_first; u32* rjob_count;
 	i32* slow_list; i32* slow_list2;    // reads whose segments / reports need the HBM arena (counters[12], counters[13])
