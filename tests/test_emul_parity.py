@@ -205,6 +205,17 @@ def test_cli_interleaved_and_gz_inputs(kart_emul, tmp_path):
     assert open(out, "rb").read() == open(os.path.join(G, "pe150.sam"), "rb").read()
 
 
+@pytest.mark.parametrize("flag", ["--full-sa", "--sampled-sa"])
+@pytest.mark.parametrize("tag,args", [("pe150", ["-f", "pe150_1.fq", "-f2", "pe150_2.fq"]), ("se100", ["-f", "se100.fq"]), ("pb3k", ["-pacbio", "-f", "pb3k.fq"])])
+def test_cli_sa_modes_give_the_same_sam(kart_emul, tmp_path, tag, args, flag):
+    """--full-sa (lane-queue seeding that finishes one-row searches against the text, one-load locates) and --sampled-sa
+    (every base walked, LF-walk locates) both reproduce the reference's SAM."""
+    a = [os.path.join(G, x) if x.endswith(".fq") else x for x in args]
+    out = str(tmp_path / (tag + ".sam"))
+    subprocess.run([kart_emul, "-silent", "-t", "2", "-i", pu.MINI_PREFIX] + a + ["-o", out, flag], check=True, stdout=subprocess.DEVNULL)
+    assert open(out, "rb").read() == open(os.path.join(G, tag + ".sam"), "rb").read()
+
+
 def test_cli_argument_errors(kart_emul):
     r = subprocess.run([kart_emul, "-i", pu.MINI_PREFIX, "-zzz"], capture_output=True, text=True)
     assert r.returncode == 1 and "Error! Unknown parameter: -zzz" in r.stdout
