@@ -441,10 +441,12 @@ KB_HD void kb_seed_read(const KbIndexDev& ix, const KbParams& pm, const KbBatchD
 // With kb_unique_tail most reads need a dozen extension trips, a read inside a repeat family still needs ~150: one read per
 // lane leaves 31 lanes idle behind the slowest. Here a lane that has finished its read draws the next one from its warp's
 // range (Q::next), so the warp lasts as long as its share of the work, not as long as its slowest read. Per outer iteration:
-// one pass in which every lane without a running search does ONE of {finish a one-row search against the text, close a search,
-// open the next search (table lookup), finish the read and load the next} -- the lanes of a pass run converged -- and then
-// extension trips for the lanes that walk the index, at least KB_SEED_TRIPS of them so that a long walk is not throttled to
-// one step per pass. Results per read are identical to kb_seed_read whatever the schedule.
+// one pass in which every lane without a running search finishes a one-row search against the text, closes it, and opens the
+// next search (table lookup) or finishes the read and draws the next one -- the lanes of a pass run converged; a pass waits
+// for `qp` such lanes unless nobody is walking -- and then extension trips for the lanes that walk the index: they wait for
+// `qs` walkers while passes can still be filled, and run at least `min_trips` trips so that a long walk is not throttled to
+// one step per pass (r15/r16 A/B: qp 8, qs 4, 6 trips on an L2-resident index, 2 on a large one).
+// Results per read are identical to kb_seed_read whatever the schedule.
 #define KB_SEED_TRIPS 4
 struct KbSeedOne   // one read per lane: host emulation, and the reference for the queue
 {
