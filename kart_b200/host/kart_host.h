@@ -20,6 +20,7 @@ struct HostIndex
 	bool load(const std::string& prefix, std::string& err);       // bwa_idx_load + RestoreReferenceInfo
 	void describe(kb_index_host_t* out) const;
 };
+int build_index(const char* fasta, const char* prefix, int threads);   // `kart index`: BWA-format files, byte-identical to the reference builder's (index_build.cpp)
 bool check_index_files(const std::string& prefix);                // CheckBWAIndexFiles, GetData.cpp:222
 
 // Grow-only host array without value-initialisation. `pinned` arrays come from kb_host_alloc (page-locked, so the copies of

@@ -1,7 +1,8 @@
 // Command line of kart_b200: same flags, defaults, messages and exit codes as the reference's src/main.cpp:87-214.
-// `kart index` / `kart update` are not part of the hot path; index files are built with the reference's bwt_index.
+// `kart index` builds the BWA-format files itself (index_build.cpp, genomes up to 2.1 Gbp); `kart update` is not supported.
 #include "kart_host.h"
 #include <thread>
+#include <algorithm>
 #include <ctype.h>
 #include <stdlib.h>
 #include <string.h>
@@ -55,7 +56,12 @@ int main(int argc, char* argv[])
 	RunOptions o;
 	if (argc == 1 || strcmp(argv[1], "-h") == 0) { usage(argv[0]); return 0; }
 	if (strcmp(argv[1], "update") == 0) { fprintf(stderr, "kart_b200: `update` is not supported\n"); return 0; }
-	if (strcmp(argv[1], "index") == 0) { fprintf(stderr, "kart_b200 consumes BWA-format index files; build them with the reference's `bwt_index ref.fa prefix`\n"); return 0; }
+	if (strcmp(argv[1], "index") == 0)   // main.cpp:112-120
+	{
+		if (argc == 4) build_index(argv[2], argv[3], (int)std::max(1u, std::thread::hardware_concurrency()));
+		else fprintf(stderr, "usage: %s index ref.fa prefix\n", argv[0]);
+		return 0;
+	}
 	for (int i = 1; i < argc; i++)
 	{
 		std::string p = argv[i];
