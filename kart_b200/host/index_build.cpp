@@ -7,7 +7,8 @@
 // so here the suffix array of the 2G text (forward strand + reverse complement) is built directly -- suffixes are bucketed
 // by their first 12 bases with a counting sort and every bucket is finished with a comparison sort over the 2-bit packed
 // text, 32 bases per step, buckets spread over threads -- and the BWT, the interleaved Occ blocks and the SA samples are read
-// off it. Text positions are 32-bit here: genomes up to 2.1 Gbp (the reference's own builder remains the tool beyond that).
+// off it. Suffix positions are 32-bit when 2G + 2 < 2^32 (genomes up to 2.1 Gbp) and 64-bit beyond (KART_INDEX_64=1 forces
+// the 64-bit instantiation; the tests run both on the same genomes).
 #include "kart_host.h"
 #include <algorithm>
 #include <atomic>
@@ -110,7 +111,7 @@ struct PackedText
 		return s ? (w[i] << s) | (w[i + 1] >> (64 - s)) : w[i];
 	}
 	// suffix order with the end of the text smaller than every base
-	bool less(uint32_t a, uint32_t b) const
+	template <class IDX> bool less(IDX a, IDX b) const
 	{
 		if (a == b) return false;
 		uint64_t x = a, y = b;
@@ -131,17 +132,11 @@ struct PackedText
 
 }   // namespace
 
-int build_index(const char* fa, const char* prefix_c, int threads)
+template <class IDX>
+static int build_core(const std::string& prefix, const std::vector<uint8_t>& fwd, const std::vector<Ann>& anns, const std::vector<Amb>& ambs, int threads)
 {
-	const std::string prefix = prefix_c;
-	clock_t t0 = clock();
-	fprintf(stdout, "[bwt_index] Pack FASTA... "); fflush(stdout);
-	std::vector<uint8_t> fwd; std::vector<Ann> anns; std::vector<Amb> ambs;
-	if (!read_reference(fa, fwd, anns, ambs)) { fprintf(stdout, "\nError! cannot open %s\n", fa); return 1; }
 	const uint64_t L = fwd.size(), N = 2 * L;
-	fprintf(stdout, "%.2f sec\n", (float)(clock() - t0) / CLOCKS_PER_SEC);
-	if (L == 0) { fprintf(stdout, "Error! %s holds no sequence\n", fa); return 1; }
-	if (N + 2 >= 0xFFFFFFFFull) { fprintf(stdout, "Error! kart_b200's index builder handles genomes up to 2.1 Gbp; use the reference's bwt_index for %s\n", fa); return 1; }
+	clock_t t0 = clock();
 
 	// ---- the 2G text and its suffix array ----
 	fprintf(stdout, "[bwt_index] Construct BWT for the packed sequence...\n"); fflush(stdout);
@@ -153,17 +148,17 @@ int build_index(const char* fa, const char* prefix_c, int threads)
 		for (size_t w = w0_; w < w1_; w++) { uint64_t v = 0; const uint64_t e = std::min<uint64_t>(N, 32ull * w + 32); for (uint64_t i = 32ull * w; i < e; i++) v |= (uint64_t)base(i) << (62 - 2 * (i & 31)); T.w[w] = v; }
 	});
 	const int K = 12; const uint64_t NB = 1ull << (2 * K);
-	std::vector<uint32_t> start(NB + 1, 0);
+	std::vector<IDX> start(NB + 1, 0);
 	auto key = [&](uint64_t p) -> uint32_t { return (uint32_t)(T.win(p) >> (64 - 2 * K)); };
-	std::vector<uint32_t> sa(N);   // rows 1..N of the (N+1)-row matrix; row 0 is the empty suffix
+	std::vector<IDX> sa(N);   // rows 1..N of the (N+1)-row matrix; row 0 is the empty suffix
 	{
 		// counting sort by the first K bases: one histogram per slice of positions, offsets = bucket start + what earlier slices hold
-		std::vector<std::vector<uint32_t>> hist(nt, std::vector<uint32_t>(NB, 0));
-		parallel_for(nt, (size_t)N, [&](int t, size_t lo, size_t hi) { std::vector<uint32_t>& h = hist[t]; for (size_t p = lo; p < hi; p++) h[key(p)]++; });
-		uint32_t run = 0;
-		for (uint64_t b = 0; b < NB; b++) { start[b] = run; for (int t = 0; t < nt; t++) { const uint32_t c = hist[t][b]; hist[t][b] = run; run += c; } }
+		std::vector<std::vector<IDX>> hist(nt, std::vector<IDX>(NB, 0));
+		parallel_for(nt, (size_t)N, [&](int t, size_t lo, size_t hi) { std::vector<IDX>& h = hist[t]; for (size_t p = lo; p < hi; p++) h[key(p)]++; });
+		IDX run = 0;
+		for (uint64_t b = 0; b < NB; b++) { start[b] = run; for (int t = 0; t < nt; t++) { const IDX c = hist[t][b]; hist[t][b] = run; run += c; } }
 		start[NB] = run;
-		parallel_for(nt, (size_t)N, [&](int t, size_t lo, size_t hi) { std::vector<uint32_t>& h = hist[t]; for (size_t p = lo; p < hi; p++) sa[h[key(p)]++] = (uint32_t)p; });
+		parallel_for(nt, (size_t)N, [&](int t, size_t lo, size_t hi) { std::vector<IDX>& h = hist[t]; for (size_t p = lo; p < hi; p++) sa[h[key(p)]++] = (IDX)p; });
 	}
 	{
 		std::atomic<uint64_t> next{0}; const uint64_t chunk = 4096;
@@ -174,10 +169,10 @@ int build_index(const char* fa, const char* prefix_c, int threads)
 				const uint64_t b1 = std::min(NB, b0 + chunk);
 				for (uint64_t b = b0; b < b1; b++)
 				{
-					const uint32_t lo = start[b], hi = start[b + 1];
+					const IDX lo = start[b], hi = start[b + 1];
 					if (hi - lo < 2) continue;
 					// from position 0: a suffix with fewer than K bases left shares its bucket with longer ones through the zero padding
-					std::sort(sa.begin() + lo, sa.begin() + hi, [&](uint32_t a, uint32_t c) { return T.less(a, c); });
+					std::sort(sa.begin() + lo, sa.begin() + hi, [&](IDX a, IDX c) { return T.less<IDX>(a, c); });
 				}
 			}
 		};
@@ -197,7 +192,7 @@ int build_index(const char* fa, const char* prefix_c, int threads)
 		bw[0] = (uint8_t)base(N - 1);   // row 0: the empty suffix, preceded by the last base
 		// matrix row r + 1 holds suffix sa[r]; rows after `primary` move up by one
 		parallel_for(nt, (size_t)N, [&](int, size_t lo, size_t hi) {
-			for (size_t r = lo; r < hi; r++) { const uint32_t p = sa[r]; if (p == 0) continue; const uint64_t row = r + 1; bw[row < primary ? row : row - 1] = (uint8_t)base((uint64_t)p - 1); }
+			for (size_t r = lo; r < hi; r++) { const IDX p = sa[r]; if (p == 0) continue; const uint64_t row = r + 1; bw[row < primary ? row : row - 1] = (uint8_t)base((uint64_t)p - 1); }
 		});
 	}
 	fprintf(stdout, "[bwt_index] %.2f seconds elapse.\n", (float)difftime(time(NULL), w0));
@@ -255,4 +250,18 @@ int build_index(const char* fa, const char* prefix_c, int threads)
 	}
 	fprintf(stdout, "%.2f sec\n", (float)(clock() - t0) / CLOCKS_PER_SEC);
 	return 0;
+}
+
+int build_index(const char* fa, const char* prefix_c, int threads)
+{
+	const std::string prefix = prefix_c;
+	clock_t t0 = clock();
+	fprintf(stdout, "[bwt_index] Pack FASTA... "); fflush(stdout);
+	std::vector<uint8_t> fwd; std::vector<Ann> anns; std::vector<Amb> ambs;
+	if (!read_reference(fa, fwd, anns, ambs)) { fprintf(stdout, "\nError! cannot open %s\n", fa); return 1; }
+	const uint64_t L = fwd.size(), N = 2 * L;
+	fprintf(stdout, "%.2f sec\n", (float)(clock() - t0) / CLOCKS_PER_SEC);
+	if (L == 0) { fprintf(stdout, "Error! %s holds no sequence\n", fa); return 1; }
+	const bool wide = N + 2 >= 0xFFFFFFFFull || (getenv("KART_INDEX_64") && atoi(getenv("KART_INDEX_64")));
+	return wide ? build_core<uint64_t>(prefix, fwd, anns, ambs, threads) : build_core<uint32_t>(prefix, fwd, anns, ambs, threads);
 }

@@ -1,5 +1,5 @@
 // Command line of kart_b200: same flags, defaults, messages and exit codes as the reference's src/main.cpp:87-214.
-// `kart index` builds the BWA-format files itself (index_build.cpp, genomes up to 2.1 Gbp); `kart update` is not supported.
+// `kart index` builds the BWA-format files itself (index_build.cpp); `kart update` is not supported.
 #include "kart_host.h"
 #include <thread>
 #include <algorithm>

@@ -18,7 +18,7 @@ t = time.time()
 ref_tool = os.path.join(ROOT, "oracle", "_ref", "bwt_index")
 if os.path.exists(ref_tool) and os.environ.get("KART_INDEX_BUILDER", "reference") != "ours":
     subprocess.run([ref_tool, prefix + ".fa", prefix], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-else:   # our own builder writes the same bytes (tests/test_index_build.py), an order of magnitude faster, up to 2.1 Gbp
+else:   # our own builder writes the same bytes (tests/test_index_build.py), an order of magnitude faster
     subprocess.run([os.path.join(ROOT, "kart_b200", "bin", "kart"), "index", prefix + ".fa", prefix], check=True, stdout=subprocess.DEVNULL)
 print("index built %.1fs" % (time.time() - t), flush=True)
 os.remove(prefix + ".fa")

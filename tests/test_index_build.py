@@ -25,10 +25,12 @@ def kart_cli(built):
     return exe
 
 
+@pytest.mark.parametrize("wide", ["0", "1"])
 @pytest.mark.parametrize("genome", ["mini", "dup"])
-def test_index_files_equal_the_reference_builders(kart_cli, tmp_path, genome):
+def test_index_files_equal_the_reference_builders(kart_cli, tmp_path, genome, wide):
+    """Both instantiations of the builder: 32-bit suffix positions, and the 64-bit ones a genome above 2.1 Gbp gets."""
     out = str(tmp_path / genome)
-    subprocess.run([kart_cli, "index", os.path.join(G, genome, genome + ".fa"), out], check=True, stdout=subprocess.DEVNULL)
+    subprocess.run([kart_cli, "index", os.path.join(G, genome, genome + ".fa"), out], check=True, stdout=subprocess.DEVNULL, env=dict(os.environ, KART_INDEX_64=wide))
     for e in EXT:
         assert open(out + "." + e, "rb").read() == open(os.path.join(G, genome, genome + "." + e), "rb").read(), e
 
