@@ -310,7 +310,9 @@ def main():
            "seed_ref_equiv_gbs": 64.0 * work["ext_steps"] / (per["fm_seed"] / 1e3) / 1e9,
            "nw_gcups": work["nw_cells"] / (per["align"] / 1e3) / 1e9}
     # ---- CPU baseline: the unmodified reference on this box's host cores, bounded sample ----
-    if os.path.exists(pu.REF_KART):
+    if args.cpu_sample_pairs <= 0:
+        out["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": ncores, "kind": "reference", "sample": "skipped (--cpu-sample-pairs 0)"}
+    elif os.path.exists(pu.REF_KART):
         tmp = tempfile.mkdtemp(prefix="kartbench")
         sp = min(args.cpu_sample_pairs, args.pairs)
         v, total, load = time_reference(prefix, r1, r2, pos, sp, ncores, tmp)
