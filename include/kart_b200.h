@@ -144,9 +144,21 @@ int  kb_work(kb_ctx_t* ctx, uint64_t* w, int n);
 void* kb_cuda_stream(kb_ctx_t* ctx);
 
 /* Test hook: copy an internal device array of the last run to the host. what: 0 n_seeds(i32) 1 seed_off(u32) 2 segs(KbSeg)
- * 3 n_cands(i32) 4 cand_off(u32) 5 cands(KbCand) 6 reports(KbReport) 7 res(KbReadRes) 8 cigar(u32) 9 counters(u32[16]).
+ * 3 n_cands(i32) 4 cand_off(u32) 5 cands(KbCand) 6 reports(KbReport) 7 res(KbReadRes) 8 cigar(u32) 9 counters(u32[32]) 10 jobs(KbJob)
+ * 11 hits(KbHit: the searches that yield seeds, [read][max_hits]) 12 n_hits(i32) 13 max_hits(i32).
  * Returns bytes copied (<= bytes) or a negative error. */
 int64_t kb_debug_fetch(kb_ctx_t* ctx, int what, void* dst, uint64_t bytes);
+
+/* Test hook, stage level: runs caller-chosen fragment pairs of the staged reads (kb_stage_reads) through the device code behind
+ * Process{Normal,Head,Tail}SequencePair (src/tools.cpp:225,292,344): the quick tests, the 8-mer partition
+ * (GenerateNormalPairAlignment, tools.cpp:142; k_align_part), nw_alignment (src/nw_alignment.cpp:18; k_nw_tile<*>, k_nw_warp),
+ * k_align_gather and the per-segment cigar rules of GenMappingReport (src/AlignmentCandidates.cpp:648-723).
+ * mode: 0 middle pair, 1 head, 2 tail (as the reference classifies them), 3 straight to GenerateNormalPairAlignment (no quick
+ * test), 4 straight to ONE nw_alignment call whatever the size. ops receives every fragment's cigar elements (len << 4 | op)
+ * at out[i].ops_off, out[i].n_ops of them; cap_ops must be at least the sum of rlen + glen + 4. */
+typedef struct { uint32_t read; int32_t rpos, rlen, glen, mode, pad; int64_t gpos; } kb_dbg_frag_t;
+typedef struct { int32_t info, aux, score, n_ops; uint32_t ops_off; int32_t nruns, ident, aligned; int64_t g_first, g_end; } kb_dbg_frag_out_t;
+int kb_debug_align(kb_ctx_t* ctx, const kb_dbg_frag_t* specs, int n, kb_dbg_frag_out_t* out, uint32_t* ops, uint32_t cap_ops);
 
 #ifdef __cplusplus
 }

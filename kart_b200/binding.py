@@ -42,11 +42,15 @@ SEG_DTYPE = np.dtype([("gpos", "<i8"), ("rpos", "<i4"), ("rlen", "<i4"), ("glen"
 CAND_DTYPE = np.dtype([("diff", "<i8"), ("score", "<i4"), ("mate", "<i4"), ("seg_start", "<u4"), ("nseg", "<i4")])
 REPORT_DTYPE = np.dtype([("pos", "<i8"), ("aln", "<i4"), ("flag", "<i4"), ("mate", "<i4"), ("chr", "<i4"), ("cig_off", "<u4"),
                          ("cig_len", "<i4"), ("fwd", "<i4"), ("pad", "<i4")])
+HIT_DTYPE = np.dtype([("x0", "<u8"), ("rpos", "<u4"), ("len_freq", "<u4")])   # KbHit: len << 8 | freq
+DBG_FRAG_DTYPE = np.dtype([("read", "<u4"), ("rpos", "<i4"), ("rlen", "<i4"), ("glen", "<i4"), ("mode", "<i4"), ("pad", "<i4"), ("gpos", "<i8")])   # kb_dbg_frag_t
+DBG_OUT_DTYPE = np.dtype([("info", "<i4"), ("aux", "<i4"), ("score", "<i4"), ("n_ops", "<i4"), ("ops_off", "<u4"), ("nruns", "<i4"), ("ident", "<i4"),
+                          ("aligned", "<i4"), ("g_first", "<i8"), ("g_end", "<i8")])   # kb_dbg_frag_out_t
 RES_DTYPE = np.dtype([("score", "<i4"), ("sub", "<i4"), ("mapq", "<i4"), ("ncan", "<i4"), ("best", "<i4"), ("rep_off", "<u4")])
 CIGAR_OPS = "MIDNSHP=X"
 
 EXPORTS = ["kb_init", "kb_destroy", "kb_strerror", "kb_last_error", "kb_upload_index", "kb_set_params", "kb_get_min_seed_len",
-           "kb_map_chunk", "kb_stage_reads", "kb_run", "kb_fetch_results", "kb_fetch_extra", "kb_stage_ms", "kb_work", "kb_cuda_stream", "kb_debug_fetch", "kb_host_alloc", "kb_host_free", "kb_host_register", "kb_host_unregister"]
+           "kb_map_chunk", "kb_stage_reads", "kb_run", "kb_fetch_results", "kb_fetch_extra", "kb_stage_ms", "kb_work", "kb_cuda_stream", "kb_debug_fetch", "kb_debug_align", "kb_host_alloc", "kb_host_free", "kb_host_register", "kb_host_unregister"]
 
 
 class KartB200Error(RuntimeError):
@@ -79,6 +83,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.kb_cuda_stream.argtypes = [C.c_void_p]
     lib.kb_debug_fetch.restype = C.c_int64
     lib.kb_debug_fetch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]
+    lib.kb_debug_align.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32]
     return lib
 
 
@@ -238,6 +243,26 @@ class Mapper:
         if got < 0:
             raise KartB200Error("kb_debug_fetch(%d): %s" % (what, self.lib.kb_strerror(int(got)).decode()))
         return buf[:got // buf.itemsize]
+
+    def debug_align(self, frags):
+        """Stage-level test hook (kb_debug_align): frags = [(read, rpos, rlen, gpos, glen, mode)] on the staged reads. Returns
+        (kb_dbg_frag_out_t array, per-fragment cigar strings)."""
+        spec = np.zeros(len(frags), dtype=DBG_FRAG_DTYPE)
+        for i, (r, rpos, rlen, gpos, glen, mode) in enumerate(frags):
+            spec[i] = (r, rpos, rlen, glen, mode, 0, gpos)
+        out = np.zeros(len(frags), dtype=DBG_OUT_DTYPE)
+        cap = int((spec["rlen"] + spec["glen"] + 4).sum())
+        ops = np.zeros(cap, dtype=np.uint32)
+        self._check(self.lib.kb_debug_align(self.h, spec.ctypes.data, len(frags), out.ctypes.data, ops.ctypes.data, cap), "kb_debug_align")
+        return out, [cigar_string(ops, int(o["ops_off"]), int(o["n_ops"])) if o["n_ops"] >= 0 else None for o in out]
+
+    def hits(self):
+        """The searches of the last run that yield seeds, per read: [(rpos, len, freq, x0)] (BWT_Search results, bwt_search.cpp:171-181)."""
+        n = self.n_reads
+        mh = int(self.debug(13, np.int32, 1)[0])
+        nh = self.debug(12, np.int32, n)
+        h = self.debug(11, HIT_DTYPE, n * mh).reshape(n, mh)
+        return [[(int(x["rpos"]), int(x["len_freq"]) >> 8, int(x["len_freq"]) & 255, int(x["x0"])) for x in h[r, :nh[r]]] for r in range(n)]
 
     # ---- dumps in the oracle's text format (oracle/kart_oracle.h) ----
     def dump_state(self):

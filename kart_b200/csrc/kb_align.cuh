@@ -676,6 +676,24 @@ KB_HD bool kb_quick_match_ref(const KbIndexDev& ix, const KbPk* rd, const u8* f1
 	return *n <= 2 && *n <= (int)(sp.rlen * 0.2);
 }
 
+// registers the fragment pair `sp` of read r as an alignment job (GenerateNormalPairAlignment, tools.cpp:142) and routes it:
+// fragments with both sides > 30 go through the 8-mer partition first (tools.cpp:146), everything else is one nw_alignment
+// problem, registered right away. whole: one nw_alignment problem whatever the size (the stage-level test entry kb_debug_align).
+KB_HD void kb_make_job(const KbIndexDev& ix, const KbBatchDev& bt, int r, const KbSeg& sp, bool whole, KbSegX* out)
+{
+	// one 64-bit atomic reserves the job id (high word = counters[11]) and its slice of the run arena (low word = counters[10])
+	u32 need = (u32)(sp.rlen + sp.glen + 2);
+	unsigned long long old = KB_ALLOC(reinterpret_cast<unsigned long long*>(bt.counters + 10), (unsigned long long)((1ull << 32) | (unsigned long long)need));
+	u32 id = (u32)(old >> 32), ro = (u32)old;
+	if (id >= bt.cap_jobs) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_JOBS); return; }
+	if ((u64)ro + need > (u64)bt.cap_runs) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_RUNS); return; }
+	KbJob jb; jb.gpos = sp.gpos; jb.read = (u32)r; jb.rpos = sp.rpos; jb.rlen = sp.rlen; jb.glen = sp.glen; jb.run_off = ro; jb.nruns = 0; jb.ident = 0; jb.aligned = 0;
+	bt.jobs[id] = jb;
+	if (!whole && sp.rlen > 30 && sp.glen > 30) { const u32 slot = KB_ALLOC(&bt.counters[23], 1u); bt.part_list[slot] = id; }
+	else kb_emit_piece(ix, bt, id, sp.gpos, 0, sp.rlen, 0, sp.glen, ro, 1u);
+	out->info = KB_SEG_JOB; out->aux = id;
+}
+
 KB_HD void kb_classify_segment(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int r, const u8* seq, const KbPk* rd, const KbSeg& sp, int j, int n, KbSegX* out)
 {
 	out->s = sp; out->info = KB_SEG_SKIP; out->aux = 0;
@@ -699,19 +717,7 @@ KB_HD void kb_classify_segment(const KbIndexDev& ix, const KbParams& pm, const K
 		out->info = KB_SEG_ONE; out->aux = f1[0] == kb_ref_char(ix, sp.gpos) ? 1u : 0u;
 		return;
 	}
-	// one 64-bit atomic reserves the job id (high word = counters[11]) and its slice of the run arena (low word = counters[10])
-	u32 need = (u32)(sp.rlen + sp.glen + 2);
-	unsigned long long old = KB_ALLOC(reinterpret_cast<unsigned long long*>(bt.counters + 10), (unsigned long long)((1ull << 32) | (unsigned long long)need));
-	u32 id = (u32)(old >> 32), ro = (u32)old;
-	if (id >= bt.cap_jobs) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_JOBS); return; }
-	if ((u64)ro + need > (u64)bt.cap_runs) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_RUNS); return; }
-	KbJob jb; jb.gpos = sp.gpos; jb.read = (u32)r; jb.rpos = sp.rpos; jb.rlen = sp.rlen; jb.glen = sp.glen; jb.run_off = ro; jb.nruns = 0; jb.ident = 0; jb.aligned = 0;
-	bt.jobs[id] = jb;
-	// route: fragments with both sides > 30 go through the 8-mer partition first (tools.cpp:146); everything else is one
-	// nw_alignment problem, registered right away
-	if (sp.rlen > 30 && sp.glen > 30) { const u32 slot = KB_ALLOC(&bt.counters[23], 1u); bt.part_list[slot] = id; }
-	else kb_emit_piece(ix, bt, id, sp.gpos, 0, sp.rlen, 0, sp.glen, ro, 1u);
-	out->info = KB_SEG_JOB; out->aux = id;
+	kb_make_job(ix, bt, r, sp, false, out);
 }
 
 // phase A

@@ -415,6 +415,43 @@ __global__ void __launch_bounds__(KB_BLOCK) k_finalize(KbIndexDev ix, KbParams p
 	kb_stage_finalize(ix, pm, bt, aln, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
+// ---- stage-level test entry (kb_debug_align): caller-chosen fragment pairs through classification, phase B and the per-segment
+// part of phase C, so that the golden nw_alignment / fragment vectors and the oracle's Process*SequencePair reach
+// k_align_part, k_nw_tile<*>, k_nw_warp and k_align_gather directly
+__global__ void k_debug_classify(KbIndexDev ix, KbParams pm, KbBatchDev bt, const kb_dbg_frag_t* specs, int n)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const kb_dbg_frag_t f = specs[i];
+	const int r = (int)f.read;
+	KbSeg sp; sp.gpos = f.gpos; sp.rpos = f.rpos; sp.rlen = f.rlen; sp.glen = f.glen; sp.simple = 0;
+	const u8* seq = bt.seq + bt.seq_off[r]; const KbPk* rd = kb_pk_read(bt, r);
+	KbSegX* out = &bt.segx[i];
+	if (f.mode >= 3) { out->s = sp; out->info = KB_SEG_SKIP; out->aux = 0; kb_make_job(ix, bt, r, sp, f.mode == 4, out); }
+	else kb_classify_segment(ix, pm, bt, r, seq, rd, sp, f.mode == 1 ? 0 : 1, f.mode == 0 ? 3 : 2, out);
+}
+__global__ void k_debug_assemble(KbIndexDev ix, KbParams pm, KbBatchDev bt, const kb_dbg_frag_t* specs, int n, kb_dbg_frag_out_t* res, u32* ops)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const kb_dbg_frag_t f = specs[i];
+	const KbSegX x = bt.segx[i];
+	// neighbours: one-base simple pairs on either side (heads have none in front, tails none behind)
+	KbSegX sx[3]; int k = 0, at = 0;
+	KbSegX dl; dl.s.simple = 1; dl.s.rlen = 1; dl.s.glen = 1; dl.s.rpos = f.rpos - 1; dl.s.gpos = f.gpos - 1; dl.info = KB_SEG_SIMPLE; dl.aux = 0;
+	KbSegX dr = dl; dr.s.rpos = f.rpos + f.rlen; dr.s.gpos = f.gpos + f.glen;
+	if (f.mode != 1) sx[k++] = dl;
+	at = k; sx[k++] = x;
+	if (f.mode != 2) sx[k++] = dr;
+	kb_dbg_frag_out_t o; memset(&o, 0, sizeof(o));
+	KbCigar cg; cg.e = ops + res[i].ops_off; cg.cap = f.rlen + f.glen + 4; cg.n = 0; cg.ovf = false;
+	int aln; i64 gf, ge;
+	kb_assemble_cigar(pm, bt, sx, k, cg, &aln, &gf, &ge);
+	o.info = (int32_t)x.info; o.aux = (int32_t)x.aux; o.score = aln - (k - 1); o.g_first = gf; o.g_end = ge; o.ops_off = res[i].ops_off + (at ? 1u : 0u); o.n_ops = cg.ovf ? -1 : cg.n - (k - 1);
+	if (x.info == KB_SEG_JOB) { const KbJob& jb = bt.jobs[x.aux]; o.nruns = jb.nruns; o.ident = jb.ident; o.aligned = jb.aligned; }
+	res[i] = o;
+}
+
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
@@ -815,6 +852,36 @@ int kb_stage_reads(kb_ctx_t* ctx, const kb_reads_t* in, const int32_t* est)
 	return KB_OK;
 }
 
+// phase B of a slot's batch: 8-mer partition, the nw_alignment size classes, gather (kb_align.cuh "phase B")
+static int launch_phase_b(kb_ctx* ctx, kb_slot& sl)
+{
+	KbBatchDev& bt = sl.bt; const KbIndexDev& ix = ctx->ix; const KbParams& pm = ctx->pm; cudaStream_t s = sl.stream;
+	unsigned g_warp = (unsigned)(ctx->align_warps * 32 / KB_BLOCK);
+#ifndef KB_EMUL
+	k_align_part<<<(unsigned)(ctx->part_warps * 32 / KB_BLOCK), KB_BLOCK, (size_t)(KB_BLOCK / 32) * (size_t)ctx->part_pool, s>>>(ix, pm, bt, ctx->part_pool);
+#else
+	KB_LAUNCH(k_align_part, g_warp, KB_BLOCK, s, ix, pm, bt, ctx->part_pool);
+#endif
+	sl.launches++;
+	// The size classes are independent and each is latency-bound on its own (one problem per thread: a launch lasts as long as
+	// its longest chain of cells), so they run side by side on the slot's aux streams, heaviest first, and join before the gather.
+	{
+		cudaStream_t q[KB_NW_CLASSES];
+		for (int i = 0; i < KB_NW_CLASSES; i++) q[i] = ctx->nw_streams ? sl.aux[i] : s;
+		if (ctx->nw_streams) { CK(cudaEventRecord(sl.fork, s)); for (int i = 0; i < KB_NW_CLASSES; i++) CK(cudaStreamWaitEvent(q[i], sl.fork, 0)); }
+		KB_LAUNCH((k_nw_tile<5, 32, 128, 4>), 148 * 4, KB_BLOCK, q[5], ix, pm, bt); sl.launches++;
+		KB_LAUNCH((k_nw_tile<4, 32, 64, 2>), 148 * 4, KB_BLOCK, q[4], ix, pm, bt); sl.launches++;
+		KB_LAUNCH(k_nw_warp, g_warp, KB_BLOCK, q[6], ix, pm, bt); sl.launches++;
+		KB_LAUNCH((k_nw_tile<3, 32, 32, 1>), 148 * 8, KB_BLOCK, q[3], ix, pm, bt); sl.launches++;
+		KB_LAUNCH((k_nw_tile<2, 24, 32, 1>), 148 * 8, KB_BLOCK, q[2], ix, pm, bt); sl.launches++;
+		KB_LAUNCH((k_nw_tile<1, 16, 32, 1>), 148 * 8, KB_BLOCK, q[1], ix, pm, bt); sl.launches++;
+		KB_LAUNCH((k_nw_tile<0, 8, 32, 1>), 148 * 8, KB_BLOCK, q[0], ix, pm, bt); sl.launches++;
+		if (ctx->nw_streams) for (int i = 0; i < KB_NW_CLASSES; i++) { CK(cudaEventRecord(sl.join[i], q[i])); CK(cudaStreamWaitEvent(s, sl.join[i], 0)); }
+	}
+	KB_LAUNCH(k_align_gather, 148 * 4, KB_BLOCK, s, bt); sl.launches++;
+	return KB_OK;
+}
+
 static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 {
 	KbBatchDev& bt = sl.bt; const KbIndexDev& ix = ctx->ix; const KbParams& pm = ctx->pm;
@@ -823,7 +890,6 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 	unsigned g_reads = (unsigned)((n + KB_BLOCK - 1) / KB_BLOCK);
 	unsigned g_items = pm.paired ? (unsigned)((n / 2 + KB_BLOCK - 1) / KB_BLOCK) : g_reads;
 	unsigned g_hits = (unsigned)(((long long)n * bt.max_hits + KB_BLOCK - 1) / KB_BLOCK);
-	unsigned g_warp = (unsigned)(ctx->align_warps * 32 / KB_BLOCK);
 	unsigned g_slow = g_reads < 148u * 16u ? g_reads : 148u * 16u;   // arena kernels: one thread per read up to a full machine, slices cut on the device
 	sl.launches = 0;
 	CK(cudaEventRecord(sl.ev[0], s));
@@ -868,28 +934,7 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 	KB_LAUNCH(k_segments, g_reads, KB_BLOCK, s, ix, pm, bt, ctx->seg_slab); sl.launches++;
 	KB_LAUNCH(k_segments_slow, g_slow, KB_BLOCK, s, ix, pm, bt); sl.launches++;
 	CK(cudaEventRecord(sl.ev[5], s));
-#ifndef KB_EMUL
-	k_align_part<<<(unsigned)(ctx->part_warps * 32 / KB_BLOCK), KB_BLOCK, (size_t)(KB_BLOCK / 32) * (size_t)ctx->part_pool, s>>>(ix, pm, bt, ctx->part_pool);
-#else
-	KB_LAUNCH(k_align_part, g_warp, KB_BLOCK, s, ix, pm, bt, ctx->part_pool);
-#endif
-	sl.launches++;
-	// The size classes are independent and each is latency-bound on its own (one problem per thread: a launch lasts as long as
-	// its longest chain of cells), so they run side by side on the slot's aux streams, heaviest first, and join before the gather.
-	{
-		cudaStream_t q[KB_NW_CLASSES];
-		for (int i = 0; i < KB_NW_CLASSES; i++) q[i] = ctx->nw_streams ? sl.aux[i] : s;
-		if (ctx->nw_streams) { CK(cudaEventRecord(sl.fork, s)); for (int i = 0; i < KB_NW_CLASSES; i++) CK(cudaStreamWaitEvent(q[i], sl.fork, 0)); }
-		KB_LAUNCH((k_nw_tile<5, 32, 128, 4>), 148 * 4, KB_BLOCK, q[5], ix, pm, bt); sl.launches++;
-		KB_LAUNCH((k_nw_tile<4, 32, 64, 2>), 148 * 4, KB_BLOCK, q[4], ix, pm, bt); sl.launches++;
-		KB_LAUNCH(k_nw_warp, g_warp, KB_BLOCK, q[6], ix, pm, bt); sl.launches++;
-		KB_LAUNCH((k_nw_tile<3, 32, 32, 1>), 148 * 8, KB_BLOCK, q[3], ix, pm, bt); sl.launches++;
-		KB_LAUNCH((k_nw_tile<2, 24, 32, 1>), 148 * 8, KB_BLOCK, q[2], ix, pm, bt); sl.launches++;
-		KB_LAUNCH((k_nw_tile<1, 16, 32, 1>), 148 * 8, KB_BLOCK, q[1], ix, pm, bt); sl.launches++;
-		KB_LAUNCH((k_nw_tile<0, 8, 32, 1>), 148 * 8, KB_BLOCK, q[0], ix, pm, bt); sl.launches++;
-		if (ctx->nw_streams) for (int i = 0; i < KB_NW_CLASSES; i++) { CK(cudaEventRecord(sl.join[i], q[i])); CK(cudaStreamWaitEvent(s, sl.join[i], 0)); }
-	}
-	KB_LAUNCH(k_align_gather, 148 * 4, KB_BLOCK, s, bt); sl.launches++;
+	{ int rc = launch_phase_b(ctx, sl); if (rc) return rc; }
 	CK(cudaEventRecord(sl.ev[6], s));
 	KB_LAUNCH(k_assemble, g_reads, KB_BLOCK, s, ix, pm, bt); sl.launches++;
 	KB_LAUNCH(k_assemble_slow, g_slow, KB_BLOCK, s, ix, pm, bt); sl.launches++;
@@ -1117,11 +1162,59 @@ int64_t kb_debug_fetch(kb_ctx_t* ctx, int what, void* dst, uint64_t bytes)
 	case 8: src = sl.cigar.p; have = (size_t)ctx->counters_host[2] * 4; break;
 	case 9: src = sl.counters.p; have = KB_NCOUNTERS * 4; break;
 	case 10: src = sl.jobs.p; have = (size_t)ctx->counters_host[11] * sizeof(KbJob); break;
+	case 11: src = sl.hits.p; have = n * (size_t)sl.bt.max_hits * sizeof(KbHit); break;
+	case 12: src = sl.n_hits.p; have = n * 4; break;
+	case 13: { if (bytes < 4) return KB_EINVAL; const int32_t mh = sl.bt.max_hits; memcpy(dst, &mh, 4); return 4; }
 	default: return KB_EINVAL;
 	}
 	if (have > bytes) have = bytes;
 	if (have && cudaMemcpy(dst, src, have, cudaMemcpyDeviceToHost) != cudaSuccess) return KB_ECUDA;
 	return (int64_t)have;
+}
+
+int kb_debug_align(kb_ctx_t* ctx, const kb_dbg_frag_t* specs, int n, kb_dbg_frag_out_t* out, uint32_t* ops, uint32_t cap_ops)
+{
+	if (!ctx || !specs || !out || !ops || n <= 0) return fail(ctx, KB_EINVAL, "kb_debug_align: bad arguments");
+	if (!ctx->staged) return fail(ctx, KB_ESTATE, "kb_debug_align: no staged reads");
+	CK(cudaSetDevice(ctx->device));
+	kb_slot& sl = ctx->slot[0]; cudaStream_t s = sl.stream;
+	int rc = alloc_batch(ctx, sl, 0); if (rc) return rc;
+	KbBatchDev& bt = sl.bt;
+	std::vector<kb_dbg_frag_out_t> res((size_t)n); u64 need_ops = 0, need_runs = 0;
+	for (int i = 0; i < n; i++)
+	{
+		const kb_dbg_frag_t& f = specs[i];
+		if (f.read >= (uint32_t)sl.n_reads || f.rpos < 0 || f.rlen < 0 || f.glen < 0 || f.mode < 0 || f.mode > 4) return fail(ctx, KB_EINVAL, "kb_debug_align: bad fragment");
+		memset(&res[i], 0, sizeof(res[i])); res[i].ops_off = (uint32_t)need_ops;
+		need_ops += (u64)(f.rlen + f.glen + 4); need_runs += (u64)(f.rlen + f.glen + 2);
+	}
+	if (need_ops > cap_ops || need_runs > sl.cap_runs || (size_t)n > sl.cap_jobs || (size_t)n > sl.cap_segx) return fail(ctx, KB_ECAPACITY, "kb_debug_align: too many / too large fragments for this batch's arenas");
+	DevBuf<kb_dbg_frag_t> d_specs; DevBuf<kb_dbg_frag_out_t> d_res; DevBuf<u32> d_ops;
+	CK(d_specs.ensure((size_t)n)); CK(d_res.ensure((size_t)n)); CK(d_ops.ensure((size_t)need_ops));
+	CK(cudaMemcpyAsync(d_specs.p, specs, (size_t)n * sizeof(kb_dbg_frag_t), cudaMemcpyHostToDevice, s));
+	CK(cudaMemcpyAsync(d_res.p, res.data(), (size_t)n * sizeof(kb_dbg_frag_out_t), cudaMemcpyHostToDevice, s));
+	CK(cudaMemsetAsync(sl.counters.p, 0, KB_NCOUNTERS * sizeof(u32), s)); CK(cudaMemsetAsync(sl.work.p, 0, 8 * sizeof(u64), s));
+	sl.launches = 0;
+	KB_LAUNCH(k_pack, (unsigned)(((long long)sl.n_reads * bt.pk_wpr + KB_BLOCK - 1) / KB_BLOCK), KB_BLOCK, s, bt);
+	KB_LAUNCH(k_debug_classify, (unsigned)((n + KB_BLOCK - 1) / KB_BLOCK), KB_BLOCK, s, ctx->ix, ctx->pm, bt, d_specs.p, n);
+	rc = launch_phase_b(ctx, sl);
+	if (rc == KB_OK)
+	{
+		KB_LAUNCH(k_debug_assemble, (unsigned)((n + KB_BLOCK - 1) / KB_BLOCK), KB_BLOCK, s, ctx->ix, ctx->pm, bt, d_specs.p, n, d_res.p, d_ops.p);
+		cudaError_t e = cudaGetLastError();
+		if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_res.p, (size_t)n * sizeof(kb_dbg_frag_out_t), cudaMemcpyDeviceToHost, s);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(ops, d_ops.p, (size_t)need_ops * 4, cudaMemcpyDeviceToHost, s);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(sl.counters_host, sl.counters.p, KB_NCOUNTERS * sizeof(u32), cudaMemcpyDeviceToHost, s);
+		if (e != cudaSuccess) rc = fail(ctx, KB_ECUDA, "kb_debug_align", e);
+	}
+	cudaError_t e2 = cudaStreamSynchronize(s);
+	d_specs.release(); d_res.release(); d_ops.release();
+	if (rc) return rc;
+	if (e2 != cudaSuccess) return fail(ctx, KB_ECUDA, "kb_debug_align: kernels", e2);
+	if (sl.counters_host[3]) return fail(ctx, KB_EOVERFLOW, "kb_debug_align: a device arena overflowed");
+	memcpy(ctx->counters_host, sl.counters_host, sizeof(ctx->counters_host));
+	ctx->ran = true; ctx->ran_pipelined = false;   // kb_debug_fetch may read the arenas (counters, jobs, ...) of this run
+	return KB_OK;
 }
 
 } // extern "C"

@@ -11,6 +11,9 @@ Outputs (all under tests/golden/):
   stage_seeds.txt                     seed lists (fast + sensitive mode) and candidate lists of 60 reads
   nw_vectors.txt                      200 nw_alignment input/output pairs
   frag_vectors.txt                    8-mer partition (+IdentifyNormalPairs) of 60 fragment pairs
+  nw_vectors_large.txt                140 more nw_alignment pairs covering every size class of the CUDA solvers (1..8 up to
+                                      129..400 on the longer side), reference side pure ACGT (`make_golden.py nwlarge`)
+  c1/r1.fq, c1/r2.fq                  the reference's own run_test.sh reads (test/r1.fq, test/r2.fq), for the C1 md5 test on the GPU box
   ecoli_c1.md5                        md5 of the reference SAM for run_test.sh (C1), raw and `LC_ALL=C sort`ed
   dup/dup.* pe150m_{1,2}.fq pe150m.sam pe150m.bam se100m.sam pb3km.sam   -m (multiple alignments) runs, `make_golden.py multihit`
   pe150.bam se100.bam pb3k.bam        the same three runs with `-bo` (reference linked against its vendored htslib 1.5:
@@ -64,7 +67,38 @@ def multihit_goldens():
     kart(pu.MINI_PREFIX, ["-m", "-pacbio", "-f", g + "pb3k.fq"], g + "pb3km.sam")
 
 
+def nw_large_goldens():
+    """nw_alignment on problems of every size class the CUDA path distinguishes; s2 (the reference side) is pure ACGT because the
+    GPU test feeds it as an indexed text; s1 keeps the occasional N and lower-case character."""
+    ref = pu.Oracle(pu.MINI_PREFIX, ref=True)
+    rng = np.random.default_rng(106)
+    acgt = np.frombuffer(b"ACGTNacgt", dtype=np.uint8)
+    with open(os.path.join(HERE, "nw_vectors_large.txt"), "w") as fh:
+        for cls, (lo, hi) in enumerate(((1, 8), (9, 16), (17, 24), (25, 32), (33, 64), (65, 128), (129, 400))):
+            for k in range(20):
+                mx = int(rng.integers(lo, hi + 1)); mn = int(rng.integers(max(1, mx // 3), mx + 1))
+                m, n = (mx, mn) if k % 2 else (mn, mx)
+                b = acgt[rng.integers(0, 4, size=n)]
+                if k % 4 < 3:   # related sequences: substitutions plus a few indels
+                    a = b.copy()
+                    mask = rng.random(len(a)) < 0.12
+                    a[mask] = acgt[rng.integers(0, 4, size=int(mask.sum()))]
+                    a = a[rng.random(len(a)) > 0.04]
+                    ins = rng.integers(0, len(a) + 1, size=int(rng.integers(0, 3)))
+                    for p_ in sorted(ins.tolist(), reverse=True):
+                        a = np.concatenate([a[:p_], acgt[rng.integers(0, 4, size=int(rng.integers(1, 6)))], a[p_:]])
+                    a = a[:m] if len(a) >= m else np.concatenate([a, acgt[rng.integers(0, 4, size=m - len(a))]])
+                else:
+                    a = acgt[rng.integers(0, 4, size=m)]
+                odd = rng.random(len(a)) < 0.02
+                a = a.copy(); a[odd] = acgt[rng.integers(4, 9, size=int(odd.sum()))]
+                o1, o2 = ref.nw(a.tobytes(), b.tobytes())
+                fh.write("%s %s %s %s\n" % (a.tobytes().decode(), b.tobytes().decode(), o1, o2))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "nwlarge":
+        return nw_large_goldens()
     if len(sys.argv) > 1 and sys.argv[1] == "bam":
         return bam_goldens()
     if len(sys.argv) > 1 and sys.argv[1] == "multihit":
