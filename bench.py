@@ -1,5 +1,9 @@
 #!/usr/bin/env python
-"""bench.py -- mapped reads/s of the kart_b200 hot path on BASELINE.json's C2 workload (E. coli, 2x150 bp @ 2 % error).
+"""bench.py -- mapped reads/s of the kart_b200 hot path on BASELINE.json's C3 workload: synthetic 3.1 Gbp reference (random + injected
+repeats, 24 contigs), wgsim-model paired-end reads 2x150 bp @ 1 % error, 10 M pairs sharded over 8 GPUs = 1.25 M pairs per GPU per
+step (weak scaling: every GPU maps one shard). The index (5.4 GB of .bwt/.sa/.pac) cannot travel in a snapshot, so the first run on
+a box builds it with this repo's `kart index` from a seeded genome and caches it under data/_gen/syn/ (--workload c2 selects the
+E. coli config instead; a host without the memory for the 3.1 Gbp build falls back to a smaller genome and says so).
 
 One "step" = one pass of the whole hot path (fm_seed -> sa_locate -> cand_pair -> rescue -> report -> finalize) over one batch
 of synthetic paired reads. Prints ONE JSON line (see the task contract): `value` is device-timed with the batch resident in
@@ -23,26 +27,6 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 STAGES = ["fm_seed", "sa_locate", "cand_pair", "rescue", "segments", "align", "assemble", "finalize"]
-
-
-def ncu_traffic(kernel, reads, syn):
-    """DRAM bytes per launch of `kernel` from the newest committed ncu --set full capture of this kind of workload (C2, or a
-    --prefix index: tags ending in 'syn'), scaled linearly from the captured launch's read count (one thread per read: grid x block)
-    to this launch's."""
-    import glob
-    import re
-    files = [f for f in glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")) if ("syn" in os.path.basename(f)) == bool(syn)]
-    if not files:
-        return None, None
-    f = max(files, key=lambda p: int(re.findall(r"r(\d+)", os.path.basename(p))[0]))
-    d = json.load(open(f))
-    norm = {re.sub(r"^void |<.*$", "", name): v for name, v in d["kernels"].items()}   # "void k_fm_seed<10>" -> "k_fm_seed"
-    k = norm.get(kernel) or norm.get(kernel + "_q")   # k_fm_seed_q: the lane-queue seeding kernel
-    if not k:
-        return None, None
-    per_read = norm.get("k_segments") or k                # one thread per read there; k_fm_seed_q runs a fixed grid
-    cap_reads = per_read["grid"] * per_read.get("block", 128)
-    return k["dram_bytes"] * reads / cap_reads, "%s (captured at %d reads/launch, scaled by reads)" % (os.path.basename(f), cap_reads)
 
 
 def random_sector_peak():
@@ -96,35 +80,80 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None, "reasons": reasons}
 
 
-def workload(pairs, seed, prefix=None, err=0.02):
+C3_MBP, C3_CONTIGS, C3_SEED = 3100, 24, 12345
+
+
+def ensure_index(args, rank):
+    """Index prefix and workload description. C3: rank 0 builds the synthetic genome's index once per box (scripts/make_syn_index.py
+    with this repo's `kart index`: files byte-identical to the reference builder's, minutes instead of hours), the other ranks wait."""
+    import parity_util as pu
+    if args.prefix:
+        return args.prefix, "index %s" % os.path.basename(args.prefix)
+    if args.workload == "c2":
+        return pu.default_prefix(), "C2: E. coli K-12 (4.64 Mbp, index from test/ecoli.fa)"
+    mbp = C3_MBP
+    avail_gb = 0
+    for ln in open("/proc/meminfo"):
+        if ln.startswith("MemAvailable"):
+            avail_gb = int(ln.split()[1]) >> 20
+    prefix = os.path.join(ROOT, "data", "_gen", "syn", "syn%d" % mbp)
+    if not os.path.exists(prefix + ".ok") and avail_gb < mbp * 23 // 1000 + 4:
+        mbp = 2000 if avail_gb >= 52 else 100   # 64-bit suffix positions need ~23 GB per Gbp; 2000 Mbp still builds with 32-bit ones
+        prefix = os.path.join(ROOT, "data", "_gen", "syn", "syn%d" % mbp)
+    if not os.path.exists(prefix + ".ok"):
+        if rank == 0:
+            t = time.time()
+            if not (os.path.exists(prefix + ".bwt") and os.path.exists(prefix + ".sa") and os.path.exists(prefix + ".pac") and os.path.exists(prefix + ".ann")):
+                env = dict(os.environ, KART_INDEX_BUILDER="ours")
+                subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "make_syn_index.py"), str(mbp), str(C3_CONTIGS if mbp >= 1000 else 4), str(C3_SEED)],
+                               check=True, env=env, stdout=sys.stderr)
+            open(prefix + ".ok", "w").write("built in %.0f s\n" % (time.time() - t))
+        else:
+            while not os.path.exists(prefix + ".ok"):
+                time.sleep(2)
+    what = "C3: synthetic %.1f Gbp reference (i.i.d. bases + injected 3-kbp and 300-bp repeat families, %d contigs, seed %d)" % (mbp / 1000.0, C3_CONTIGS if mbp >= 1000 else 4, C3_SEED)
+    if mbp != C3_MBP:
+        what += " -- REDUCED from 3.1 Gbp: this host has %d GB of memory available for the index build" % avail_gb
+    return prefix, what
+
+
+def workload(pairs, seed, prefix, err):
     import parity_util as pu
     from kart_b200 import KartIndex, synth
-    prefix = prefix or pu.default_prefix()
     idx = KartIndex(prefix)
-    genome = pu.genome_of(idx)
-    r1, r2, pos = synth.simulate(genome, pairs, 150, err, seed=seed)
-    return prefix, idx, r1, r2, pos
+    r1, r2, pos = synth.simulate(pu.pac_genome(idx), pairs, 150, err, seed=seed)
+    return idx, r1, r2, pos
 
 
-def time_reference(prefix, r1, r2, pos, sample_pairs, threads, tmp):
-    """Unmodified reference binary on a bounded sample; index-load time (same command, 2 reads) is subtracted."""
-    import parity_util as pu
-    from kart_b200 import synth
-    f1, f2 = os.path.join(tmp, "s_1.fq"), os.path.join(tmp, "s_2.fq")
-    synth.write_fastq(f1, r1[:sample_pairs], pos[:sample_pairs], 1, 0.02)
-    synth.write_fastq(f2, r2[:sample_pairs], pos[:sample_pairs], 2, 0.02)
-    e1, e2 = os.path.join(tmp, "e_1.fq"), os.path.join(tmp, "e_2.fq")
-    synth.write_fastq(e1, r1[:1], pos[:1], 1, 0.02)
-    synth.write_fastq(e2, r2[:1], pos[:1], 2, 0.02)
+class ReferenceRunner:
+    """The unmodified reference binary (oracle/_ref/kart -t <cores>) on FASTQ files of a bounded sample of the step's reads. Its
+    index-load time (the same command on one pair) is measured once and subtracted from every run."""
 
-    def run(a, b):
+    def __init__(self, prefix, r1, r2, pos, sample_pairs, threads, err):
+        import parity_util as pu
+        from kart_b200 import synth
+        self.pu, self.prefix, self.threads, self.n = pu, prefix, threads, sample_pairs
+        self.tmp = tempfile.mkdtemp(prefix="kartbench")
+        self.f = [os.path.join(self.tmp, x) for x in ("s_1.fq", "s_2.fq", "e_1.fq", "e_2.fq")]
+        synth.write_fastq(self.f[0], r1[:sample_pairs], pos[:sample_pairs], 1, err)
+        synth.write_fastq(self.f[1], r2[:sample_pairs], pos[:sample_pairs], 2, err)
+        synth.write_fastq(self.f[2], r1[:1], pos[:1], 1, err)
+        synth.write_fastq(self.f[3], r2[:1], pos[:1], 2, err)
+        self.load = min(self._run(self.f[2], self.f[3]) for _ in range(2))
+
+    def _run(self, a, b):
         t = time.perf_counter()
-        subprocess.run([pu.REF_KART, "-silent", "-t", str(threads), "-i", prefix, "-f", a, "-f2", b, "-o", os.path.join(tmp, "ref.sam")],
+        subprocess.run([self.pu.REF_KART, "-silent", "-t", str(self.threads), "-i", self.prefix, "-f", a, "-f2", b, "-o", os.path.join(self.tmp, "ref.sam")],
                        check=True, stdout=subprocess.DEVNULL)
         return time.perf_counter() - t
-    load = min(run(e1, e2) for _ in range(2))
-    total = run(f1, f2)
-    return 2 * sample_pairs / max(total - load, 1e-6), total, load
+
+    def step(self):
+        """(reads/s net of index load, seconds of mapping)"""
+        total = self._run(self.f[0], self.f[1])
+        return 2 * self.n / max(total - self.load, 1e-6), total - self.load
+
+    def close(self):
+        subprocess.run(["rm", "-rf", self.tmp])
 
 
 def bind_to_gpu_numa_node(local):
@@ -151,44 +180,119 @@ def bind_to_gpu_numa_node(local):
         return None
 
 
+def source_sha():
+    """Hash of the CUDA sources: an ncu traffic capture is only quoted for the build it was taken from."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "kart_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic(kernel, reads, workload_key):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture of THIS workload and THIS build
+    (profiles/*_traffic.json written by scripts/ncu_summary.py on the GPU box, with the hash of the CUDA sources and the workload it
+    profiled), scaled by reads per launch. A capture of another build or workload is not quoted: traffic is then null."""
+    import glob
+    import re
+    best = None
+    for f in glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")):
+        d = json.load(open(f))
+        if d.get("workload") != workload_key:
+            continue
+        if best is None or os.path.getmtime(f) > os.path.getmtime(best[0]):
+            best = (f, d)
+    if best is None:
+        return None, "no ncu capture of workload %s under profiles/" % workload_key
+    f, d = best
+    if d.get("source_sha") != source_sha():
+        return None, "%s was captured from another build (sources changed since): not quoted" % os.path.basename(f)
+    norm = {re.sub(r"^void |<.*$", "", name): v for name, v in d["kernels"].items()}
+    k = norm.get(kernel) or norm.get(kernel + "_q")
+    if not k:
+        return None, "%s has no launch of %s" % (os.path.basename(f), kernel)
+    cap_reads = 2 * d["pairs_per_launch"]
+    return k["dram_bytes"] * reads / cap_reads, "%s (same build, captured at %d reads/launch, scaled by reads)" % (os.path.basename(f), cap_reads)
+
+
+def program_leg(prefix, r1, r2, pos, pairs, err, threads):
+    """Whole program, FASTQ in -> SAM out, same files: kart_b200/bin/kart against oracle/_ref/kart -t <cores>. What a user of the
+    drop-in sees; start-up (index load, CUDA context) is inside both wall times and also reported on its own."""
+    import parity_util as pu
+    from kart_b200 import synth
+    ours = os.path.join(ROOT, "kart_b200", "bin", "kart")
+    if not (os.path.exists(ours) and os.path.exists(pu.REF_KART)):
+        return None
+    tmp = tempfile.mkdtemp(prefix="kartprog")
+    f = [os.path.join(tmp, x) for x in ("p_1.fq", "p_2.fq", "e_1.fq", "e_2.fq")]
+    synth.write_fastq(f[0], r1[:pairs], pos[:pairs], 1, err); synth.write_fastq(f[1], r2[:pairs], pos[:pairs], 2, err)
+    synth.write_fastq(f[2], r1[:1], pos[:1], 1, err); synth.write_fastq(f[3], r2[:1], pos[:1], 2, err)
+
+    def run(binary, a, b, out):
+        t = time.perf_counter()
+        subprocess.run([binary, "-silent", "-t", str(threads), "-i", prefix, "-f", a, "-f2", b, "-o", os.path.join(tmp, out)], check=True, stdout=subprocess.DEVNULL)
+        return time.perf_counter() - t
+    res = {"reads": 2 * pairs, "threads": threads}
+    res["ours_startup_s"] = run(ours, f[2], f[3], "e.sam"); res["ours_total_s"] = run(ours, f[0], f[1], "ours.sam")
+    res["ref_startup_s"] = run(pu.REF_KART, f[2], f[3], "e.sam"); res["ref_total_s"] = run(pu.REF_KART, f[0], f[1], "ref.sam")
+    srt = "LC_ALL=C sort -S 2G --parallel=8 %s | md5sum"
+    a = subprocess.run(srt % os.path.join(tmp, "ours.sam"), shell=True, capture_output=True, text=True).stdout.split()[0]
+    b = subprocess.run(srt % os.path.join(tmp, "ref.sam"), shell=True, capture_output=True, text=True).stdout.split()[0]
+    res["sorted_sam_identical"] = a == b
+    res["ours_reads_per_s"] = 2 * pairs / res["ours_total_s"]; res["ref_reads_per_s"] = 2 * pairs / res["ref_total_s"]
+    net_o, net_r = res["ours_total_s"] - res["ours_startup_s"], res["ref_total_s"] - res["ref_startup_s"]
+    res["ours_reads_per_s_net_of_startup"] = 2 * pairs / net_o if net_o > 0.05 else None
+    res["ref_reads_per_s_net_of_startup"] = 2 * pairs / net_r if net_r > 0.05 else None
+    subprocess.run(["rm", "-rf", tmp])
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="kart_b200", choices=["kart_b200", "reference"])
-    ap.add_argument("--pairs", type=int, default=1_000_000, help="read pairs per step per GPU (C2: 1M pairs)")
-    ap.add_argument("--cpu-sample-pairs", type=int, default=400_000)
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2"], help="BASELINE.json config: c3 = synthetic 3.1 Gbp reference, PE 2x150 @ 1 % (default); c2 = E. coli, PE 2x150 @ 2 %")
+    ap.add_argument("--pairs", type=int, default=0, help="read pairs per step per GPU (default: c3 1.25 M = one of 8 shards of 10 M pairs; c2 1 M)")
+    ap.add_argument("--cpu-sample-pairs", type=int, default=100_000, help="pairs of the step's batch the CPU reference is timed on (0: skip)")
+    ap.add_argument("--program-pairs", type=int, default=500_000, help="pairs for the whole-program leg (FASTQ in -> SAM out, both programs), N = 1 only; 0: skip")
     ap.add_argument("--full-sa", type=int, default=1, help="expand the sampled SA into a full SA in HBM at upload")
-    ap.add_argument("--prefix", default=None, help="index prefix (default: the E. coli index of config C2); e.g. data/_gen/syn/syn400 for the HBM-bound regime")
-    ap.add_argument("--error", type=float, default=0.02)
+    ap.add_argument("--prefix", default=None, help="map against this index instead of the workload's own")
+    ap.add_argument("--error", type=float, default=-1.0)
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     import parity_util as pu
     ncores = os.cpu_count() or 1
-    wl = "C2: E. coli K-12 (4.64 Mbp, index from test/ecoli.fa)" if not args.prefix else "index %s" % os.path.basename(args.prefix)
-    config = {"workload": "%s, %d synthetic paired-end reads 2x150 bp @ %g%% error per GPU per step, seed %d+rank" % (wl, 2 * args.pairs, 100 * args.error, 1),
-              "reads_per_step_per_gpu": 2 * args.pairs, "read_len": 150, "error_rate": args.error, "full_sa_in_hbm": bool(args.full_sa),
+    if args.pairs <= 0:
+        args.pairs = 1_250_000 if args.workload == "c3" else 1_000_000
+    if args.error < 0:
+        args.error = 0.01 if args.workload == "c3" else 0.02
+    if args.impl == "reference" and rank != 0:
+        return
+    prefix, wl = ensure_index(args, rank)
+    big = os.path.getsize(prefix + ".bwt") > 126e6
+    config = {"workload": "%s, %d synthetic paired-end reads 2x150 bp @ %g%% error per GPU per step (wgsim model, seed 1+rank)%s" %
+                          (wl, 2 * args.pairs, 100 * args.error, "; one of 8 shards of C3's 10 M pairs per GPU" if args.workload == "c3" and not args.prefix and args.pairs == 1_250_000 else ""),
+              "index": os.path.basename(prefix), "reads_per_step_per_gpu": 2 * args.pairs, "read_len": 150, "error_rate": args.error, "full_sa_in_hbm": bool(args.full_sa),
               "l2": ("read batch (%.0f MB) exceeds L2; " % (2 * args.pairs * 150 / 1e6)) +
-                    ("the E. coli FM-index (4.6 MB) is L2-resident by construction of this config" if not args.prefix else
-                     "index %s is larger than L2 when its .bwt exceeds 126 MB" % os.path.basename(args.prefix))}
+                    ("the FM-index (%.1f GB of Occ blocks + seeding table + full SA) is far larger than the 126 MB L2" % (os.path.getsize(prefix + ".bwt") / 1e9) if big
+                     else "the E. coli FM-index (4.6 MB) is L2-resident by construction of this config")}
+    workload_key = os.path.basename(prefix)
 
     if args.impl == "reference":
-        if rank != 0:
-            return
         if not os.path.exists(pu.REF_KART):
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/kart was not built (needs /root/reference at build time)"}))
             return
-        prefix, idx, r1, r2, pos = workload(args.cpu_sample_pairs, 1, args.prefix, args.error)
-        tmp = tempfile.mkdtemp(prefix="kartbench")
-        vals = []
-        for it in range(args.warmup + args.steps):
-            v, total, load = time_reference(prefix, r1, r2, pos, args.cpu_sample_pairs, ncores, tmp)
-            if it >= args.warmup:
-                vals.append((v, total - load))
+        sp = min(args.cpu_sample_pairs if args.cpu_sample_pairs > 0 else 100_000, args.pairs)
+        idx, r1, r2, pos = workload(sp, 1, prefix, args.error)
+        ref = ReferenceRunner(prefix, r1, r2, pos, sp, ncores, args.error)
+        vals = [ref.step() for _ in range(args.warmup + args.steps)][args.warmup:]
+        ref.close()
         value = float(np.mean([v for v, _ in vals]))
         ms = float(np.mean([t for _, t in vals]) * 1e3)
-        sample = "%d reads (first %d pairs of the C2 stream), kart -t %d, index-load time subtracted" % (2 * args.cpu_sample_pairs, args.cpu_sample_pairs, ncores)
+        sample = "each step = %d reads (the first %d pairs of the step's batch) through oracle/_ref/kart -t %d, FASTQ in / SAM out; index load (%.1f s, measured once) subtracted" % (2 * sp, sp, ncores, ref.load)
         print(json.dumps({"impl": "reference", "metric": "mapped reads/s", "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64/int32", "data": "synthetic",
                           "config": config, "cpu_baseline": {"value": value, "unit": "reads/s", "cores": ncores, "kind": "reference", "sample": sample},
@@ -210,11 +314,13 @@ def main():
         json_fd = os.dup(1)
         os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    prefix, idx, r1, r2, pos = workload(args.pairs, 1 + rank, args.prefix, args.error)
+    idx, r1, r2, pos = workload(args.pairs, 1 + rank, prefix, args.error)
     reads = pu.interleave(r1, r2)
     n = reads.shape[0]
     m = Mapper(device=local)
+    t_up = time.perf_counter()
     m.upload_index(idx, expand_sa=bool(args.full_sa))
+    upload_s = time.perf_counter() - t_up
     m.set_params(paired=True)
     # pinned host buffers for the end-to-end leg
     seq_pin = torch.empty(reads.size, dtype=torch.uint8).pin_memory()
@@ -244,7 +350,7 @@ def main():
     sampler.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage_sum = {k: 0.0 for k in STAGES + ["total"]}
+    stage_sum = {k: 0.0 for k in STAGES + ["total", "nw"]}
     e0.record(stream)
     for _ in range(args.steps):
         m.run()
@@ -281,45 +387,62 @@ def main():
     e2e = total_reads * args.steps / (e2e_ms / 1e3)
     # ---- roofline of the dominant kernel (algorithmic bytes: DESIGN.md "Kernels") ----
     per = {k: stage_sum[k] / args.steps for k in STAGES}
+    nw_ms = stage_sum["nw"] / args.steps
     dom = max(per, key=per.get)
     alg = {"fm_seed": 32.0 * work["occ_blocks"], "sa_locate": 32.0 * work["lf_steps"] + 8.0 * work["seeds"]}
     peak, which = peaks()
     rk = dom if dom in alg else "fm_seed"
     achieved = alg[rk] / (per[rk] / 1e3) / 1e9
-    traffic, traffic_src = ncu_traffic("k_" + rk, n, args.prefix)
+    traffic, traffic_src = ncu_traffic("k_" + rk, n, workload_key)
     roof = {"kernel": "k_" + rk, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": which, "dominant_kernel": "k_" + dom, "share_of_step": per[rk] / max(sum(per.values()), 1e-9),
-            "note": ("E. coli index is L2-resident: achieved GB/s is L2->SM sector traffic expressed against the HBM copy peak; dram traffic is in profiles/"
-                     if not args.prefix else "random 32-byte sector reads of the Occ blocks and seeding table")}
+            "algorithmic_bytes": "32 B x sectors the algorithm asks for (seeding-table entry, Occ blocks while the interval has > 1 row, SA entry, reference words): %.1f per read" % (work["occ_blocks"] / max(n, 1)),
+            "note": ("random 32-byte sector reads over a %.1f GB index: the ceiling for that access pattern is random_sector_peak, not the copy peak" % (os.path.getsize(prefix + ".bwt") / 1e9) if big
+                     else "E. coli index is L2-resident: achieved GB/s is L2->SM sector traffic expressed against the HBM copy peak")}
     rs = random_sector_peak()
     if rs:
         roof["random_sector_peak"] = rs
-        if args.prefix:
+        if big:
             roof["frac_of_random_sector_peak"] = achieved / rs["independent_gbs"]
     if numa:
         config["host_binding"] = "each rank bound to its GPU's " + numa.split(" for ")[0]
+    # nw_alignment as its own roofline: cell updates over the time of the solver kernels alone; the bound is the INT32 pipe.
+    # One cell = 3 recurrences = ~15 integer instructions in k_nw_tile (SASS count); 148 SMs x 128 INT32 lanes x SM clock.
+    clocks = sampler.summary()
+    int_peak = 148 * 128 * (clocks.get("sm_max_mhz") or 1965) * 1e6
+    nw = {"kernels": "k_nw_tile<0..5>, k_nw_warp (side by side)", "cells_per_step": work["nw_cells"], "calls_per_step": work["nw_calls"], "kernel_ms": nw_ms,
+          "gcups": work["nw_cells"] / max(nw_ms, 1e-9) / 1e6, "bound": "int32 pipe", "int32_ops_per_cell": 15, "peak_gcups": int_peak / 15 / 1e9}
+    nw["frac"] = nw["gcups"] / nw["peak_gcups"]
     out = {"metric": "mapped reads/s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64/int32", "data": "synthetic",
-           "config": config, "clocks": sampler.summary(),
+           "config": config, "clocks": clocks,
            "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
-           "gpu_launches": int(work["launches"]) * args.steps, "roofline": roof,
-           "stage_ms": per, "mapped_fraction": mapped / n,
+           "gpu_launches": int(work["launches"]) * args.steps, "roofline": roof, "nw": nw,
+           "stage_ms": per, "mapped_fraction": mapped / n, "index_upload_s": upload_s,
            "work_per_step": work, "seed_occ_gbs": alg["fm_seed"] / (per["fm_seed"] / 1e3) / 1e9,
            # work-equivalent rate: the traffic SURVEY 8(d) assigns to the reference's algorithm (64 B per extension step), which the
-           # unique-tail seeding no longer moves
+           # unique-tail seeding no longer moves -- a work rate, not a bandwidth
            "seed_ref_equiv_gbs": 64.0 * work["ext_steps"] / (per["fm_seed"] / 1e3) / 1e9,
-           "nw_gcups": work["nw_cells"] / (per["align"] / 1e3) / 1e9}
+           "nw_gcups": nw["gcups"], "align_stage_gcups": work["nw_cells"] / (per["align"] / 1e3) / 1e9}
     # ---- CPU baseline: the unmodified reference on this box's host cores, bounded sample ----
     if args.cpu_sample_pairs <= 0:
         out["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": ncores, "kind": "reference", "sample": "skipped (--cpu-sample-pairs 0)"}
     elif os.path.exists(pu.REF_KART):
-        tmp = tempfile.mkdtemp(prefix="kartbench")
         sp = min(args.cpu_sample_pairs, args.pairs)
-        v, total, load = time_reference(prefix, r1, r2, pos, sp, ncores, tmp)
+        ref = ReferenceRunner(prefix, r1, r2, pos, sp, ncores, args.error)
+        v, secs = ref.step()
+        ref.close()
         out["cpu_baseline"] = {"value": v, "unit": "reads/s", "cores": ncores, "kind": "reference",
-                               "sample": "%d reads (first %d pairs of the step's batch), oracle/_ref/kart -t %d, %.2f s map + %.2f s index load (subtracted)" % (2 * sp, sp, ncores, total - load, load)}
+                               "sample": "%d reads (first %d pairs of the step's batch), oracle/_ref/kart -t %d, %.2f s map + %.2f s index load (subtracted)" % (2 * sp, sp, ncores, secs, ref.load)}
     else:
         out["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": ncores, "kind": "reference", "sample": "oracle/_ref/kart not built"}
+    if world == 1 and args.program_pairs > 0:
+        m.close()   # the CLI brings its own context; free this one's HBM first
+        del m
+        try:
+            out["e2e_program"] = program_leg(prefix, r1, r2, pos, min(args.program_pairs, args.pairs), args.error, ncores)
+        except Exception as e:   # the headline numbers above stand on their own
+            out["e2e_program"] = {"error": str(e)[:200]}
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:

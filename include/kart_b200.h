@@ -135,7 +135,8 @@ int   kb_host_register(void* p, uint64_t bytes);
 void  kb_host_unregister(void* p);
 
 /* Instrumentation. kb_stage_ms: device time (CUDA events on the context's stream) of each kernel of the last kb_run:
- * [0] fm_seed [1] sa_locate [2] cand_pair [3] rescue [4] segments [5] align [6] assemble [7] finalize [8] whole run.
+ * [0] fm_seed [1] sa_locate [2] cand_pair [3] rescue [4] segments [5] align [6] assemble [7] finalize [8] whole run
+ * [9] the nw_alignment solver kernels alone (part of [5]).
  * Returns entries written.
  * kb_work: algorithmic work of the last run: [0] extension steps [1] Occ blocks touched (32-byte sectors)
  * [2] LF steps [3] NW cells [4] seeds [5] NW calls [6] rescue attempts [7] kernels launched. */

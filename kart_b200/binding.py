@@ -228,9 +228,9 @@ class Mapper:
         return ext
 
     def stage_ms(self):
-        a = np.zeros(9, dtype=np.float32)
-        self.lib.kb_stage_ms(self.h, a.ctypes.data, 9)
-        return dict(zip(["fm_seed", "sa_locate", "cand_pair", "rescue", "segments", "align", "assemble", "finalize", "total"], [float(x) for x in a]))
+        a = np.zeros(10, dtype=np.float32)
+        self.lib.kb_stage_ms(self.h, a.ctypes.data, 10)
+        return dict(zip(["fm_seed", "sa_locate", "cand_pair", "rescue", "segments", "align", "assemble", "finalize", "total", "nw"], [float(x) for x in a]))
 
     def work(self):
         a = np.zeros(8, dtype=np.uint64)

@@ -179,19 +179,70 @@ __global__ void __launch_bounds__(KB_BLOCK) k_rescue_commit(KbIndexDev ix, KbPar
 	const int count = (int)bt.counters[4];
 	for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) kb_rescue_commit(pm, bt, k);
 }
+// KB_RESCUE_FAST=0: every window on the slow list
+__global__ void __launch_bounds__(KB_BLOCK) k_rescue_all_slow(KbBatchDev bt)
+{
+	if (bt.counters[3]) return;
+	const u32 count = bt.counters[27];
+	for (u32 q = blockIdx.x * blockDim.x + threadIdx.x; q < count; q += gridDim.x * blockDim.x) bt.rslow[q] = q;
+	if (blockIdx.x == 0 && threadIdx.x == 0) bt.counters[29] = count;
+}
+// warp per rescue window out of shared memory (kb_pair.cuh "warp-per-window fast path"); what it cannot take goes to the slow list
+#ifndef KB_EMUL
+__global__ void __launch_bounds__(KB_BLOCK) k_rescue_fast(KbIndexDev ix, KbParams pm, KbBatchDev bt)
+{
+	extern __shared__ __align__(16) u8 rf_pool[];
+	__shared__ u32 ticket[KB_BLOCK / 32];
+	if (bt.counters[3]) return;
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	KbRescueFast& w = reinterpret_cast<KbRescueFast*>(rf_pool)[wib];
+	const u32 count = bt.counters[27];
+	while (true)
+	{
+		if (lane == 0) ticket[wib] = atomicAdd(&bt.counters[25], 1u);
+		__syncwarp();
+		const u32 q = ticket[wib];
+		__syncwarp();
+		if (q >= count) break;
+		if (lane == 0) kb_rf_begin(ix, bt, w, q);
+		__syncwarp();
+		kb_rf_load(ix, bt, w, lane); __syncwarp();
+		kb_rf_fill(w, lane); __syncwarp();
+		kb_rf_pairs(w, lane); __syncwarp();
+		if (lane == 0) kb_rf_end(pm, bt, w);
+		__syncwarp();
+	}
+}
+#else
+static void k_rescue_fast(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulation: a warp = a loop over 32 lanes per phase
+{
+	if (blockIdx.x != 0 || threadIdx.x != 0) return;
+	if (bt.counters[3]) return;
+	static KbRescueFast w;
+	const u32 count = bt.counters[27];
+	for (u32 q = 0; q < count; q++)
+	{
+		kb_rf_begin(ix, bt, w, q);
+		for (int t = 31; t >= 0; t--) kb_rf_load(ix, bt, w, t);
+		for (int t = 31; t >= 0; t--) kb_rf_fill(w, t);
+		for (int t = 31; t >= 0; t--) kb_rf_pairs(w, t);   // reversed on purpose: the result must not depend on append order
+		kb_rf_end(pm, bt, w);
+	}
+}
+#endif
 #ifndef KB_EMUL
 __global__ void __launch_bounds__(KB_BLOCK) k_rescue_win(KbIndexDev ix, KbParams pm, KbBatchDev bt)
 {
 	__shared__ KbRescueJob sj; __shared__ u32 ticket;
 	if (bt.counters[3]) return;
-	const u32 count = bt.counters[27]; const int tid = threadIdx.x, nth = blockDim.x;
+	const u32 count = bt.counters[29]; const int tid = threadIdx.x, nth = blockDim.x;   // the windows k_rescue_fast handed back
 	KbRescueJob* j = &sj; KbArena ar = kb_job_arena(bt, blockIdx.x, blockDim.x);
 	while (true)
 	{
 		if (tid == 0) ticket = atomicAdd(&bt.counters[28], 1u);
 		__syncthreads();
-		const u32 q = ticket;
-		if (q >= count) break;
+		if (ticket >= count) break;
+		const u32 q = bt.rslow[ticket];
 		if (tid == 0) kb_rt_begin(ix, bt, j, ar, bt.rtasks[q]);
 		__syncthreads();
 		if (!j->ovf)
@@ -209,10 +260,11 @@ static void k_rescue_win(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulati
 {
 	if (blockIdx.x != 0 || threadIdx.x != 0) return;
 	if (bt.counters[3]) return;
-	const u32 count = bt.counters[27]; const int nth = (int)blockDim.x;
+	const u32 count = bt.counters[29]; const int nth = (int)blockDim.x;
 	static KbRescueJob job; KbRescueJob* j = &job; KbArena ar = kb_job_arena(bt, 0, blockDim.x);
-	for (u32 q = 0; q < count; q++)
+	for (u32 qi = 0; qi < count; qi++)
 	{
+		const u32 q = bt.rslow[qi];
 		kb_rt_begin(ix, bt, j, ar, bt.rtasks[q]);
 		if (!j->ovf)
 		{
@@ -468,11 +520,11 @@ struct DevBuf
 // H2D copy of one sub-batch, the kernels of the previous one and the D2H copy of the one before overlap.
 struct kb_slot
 {
-	cudaStream_t stream = nullptr; cudaEvent_t ev[10]; cudaEvent_t done = nullptr;
-	cudaStream_t aux[KB_NW_CLASSES]; cudaEvent_t fork = nullptr, join[KB_NW_CLASSES];   // the nw_alignment size classes run side by side (launch_pipeline)
+	cudaStream_t stream = nullptr; cudaEvent_t ev[10] = {}; cudaEvent_t done = nullptr; cudaEvent_t nw0 = nullptr, nw1 = nullptr;   // nw0..nw1: the nw_alignment solvers alone
+	cudaStream_t aux[KB_NW_CLASSES] = {}; cudaEvent_t fork = nullptr, join[KB_NW_CLASSES] = {};   // the nw_alignment size classes run side by side (launch_pipeline)
 	KbBatchDev bt; int n_reads = 0; size_t seq_bytes = 0; u64 seq_first = 0; int max_rlen = 0; int first_read = 0;
 	DevBuf<u8> seq, scratch, wscratch; DevBuf<u64> seq_off; DevBuf<unsigned long long> work; DevBuf<i32> est, n_hits, n_seeds, n_cands, cand_cap, rescue, slow1, slow2; DevBuf<u32> seed_off, cand_off, cigar, counters, cseg_off, runs; DevBuf<i32> cseg_n; DevBuf<KbSegX> segx; DevBuf<KbJob> jobs; DevBuf<u32> piece_list, part_list; DevBuf<KbPiece> pieces;
-	DevBuf<KbHit> hits; DevBuf<KbSeg> segs; DevBuf<KbCand> cands; DevBuf<KbReport> reports; DevBuf<KbReadRes> res; DevBuf<KbPairStat> pstat; DevBuf<kb_aln_t> aln; DevBuf<KbPk> pk; DevBuf<kb_extra_t> extra; DevBuf<KbRTask> rtasks; DevBuf<u32> rjob_first, rjob_count; size_t cap_rtasks = 0;
+	DevBuf<KbHit> hits; DevBuf<KbSeg> segs; DevBuf<KbCand> cands; DevBuf<KbReport> reports; DevBuf<KbReadRes> res; DevBuf<KbPairStat> pstat; DevBuf<kb_aln_t> aln; DevBuf<KbPk> pk; DevBuf<kb_extra_t> extra; DevBuf<KbRTask> rtasks; DevBuf<u32> rjob_first, rjob_count, rslow; size_t cap_rtasks = 0;
 	size_t cap_segs = 0, cap_cands = 0, cap_cigar = 0, cap_segx = 0, cap_jobs = 0, cap_pieces = 0, cap_runs = 0, cap_extra = 0, scratch_per_thread = 0; int scratch_threads = 0;
 	u32* counters_host = nullptr; unsigned long long* work_dev_host = nullptr;   // pinned: 16 x u32, 8 x u64
 	int launches = 0;
@@ -480,7 +532,7 @@ struct kb_slot
 	{
 		seq.release(); scratch.release(); wscratch.release(); seq_off.release(); work.release(); est.release(); n_hits.release(); n_seeds.release(); n_cands.release(); cand_cap.release();
 		rescue.release(); slow1.release(); slow2.release(); seed_off.release(); cand_off.release(); cigar.release(); counters.release(); cseg_off.release(); runs.release();
-		cseg_n.release(); segx.release(); jobs.release(); piece_list.release(); part_list.release(); pieces.release(); hits.release(); segs.release(); cands.release(); reports.release(); res.release(); pstat.release(); aln.release(); pk.release(); extra.release(); rtasks.release(); rjob_first.release(); rjob_count.release();
+		cseg_n.release(); segx.release(); jobs.release(); piece_list.release(); part_list.release(); pieces.release(); hits.release(); segs.release(); cands.release(); reports.release(); res.release(); pstat.release(); aln.release(); pk.release(); extra.release(); rtasks.release(); rjob_first.release(); rjob_count.release(); rslow.release();
 	}
 };
 
@@ -494,7 +546,7 @@ struct kb_ctx
 	DevBuf<u32> chunk_cigar, chunk_cursor;   // cigar arena and cursor shared by the sub-batches of one pipelined chunk
 	bool staged = false, ran = false, ran_pipelined = false; u32 n_cigar_last = 0;
 	double seg_factor = 32, cigar_factor = 8, scratch_factor = 1, segx_factor = 8, job_factor = 4, run_factor = 96, extra_factor = 0.25, rtask_factor = 0.25;
-	float stage_ms[9]; uint64_t work_host[8]; u32 counters_host[KB_NCOUNTERS];
+	float stage_ms[10]; uint64_t work_host[8]; u32 counters_host[KB_NCOUNTERS];
 	cudaEvent_t chunk_start = nullptr; int trace = 0;
 	int seed_minb = 10;
 	int seed_qp = 8, seed_qs = 4, seed_trips = 0;   // trips 0 = 6 with 32-bit rows (small index, instruction-bound), 2 otherwise (r16 A/B)   // lane-queue schedule: lanes a pass waits for, lanes a walk waits for, trips per walk (KB_SEED_QP/QS/TRIPS)
@@ -508,6 +560,7 @@ struct kb_ctx
 	int nw_tmax = 0;             // largest side one thread solves (0: KB_NW_TMAX); KB_NW_TMAX=32|64 sends more to the wavefront kernel
 	int nw_warp_below = 8192;    // a column-tile class (33..64, 65..128) with fewer problems than this is solved by k_nw_warp instead
 	int rescue_threads = 64;     // block size of k_rescue_win (32, 64 or 128)
+	int rescue_fast = 1;         // warp-per-window fast path first (KB_RESCUE_FAST=0: every window through the block-per-window kernel)
 	int pipe_min_reads = 262144, pipe_sub_reads = 0;   // chunks of at least pipe_min_reads go through the slot pipeline
 	int pipe_first = 0, pipe_grow = 200, pipe_tail = 0;   // sub-batch plan: first size, growth (percent), floor of the halving tail (0: uniform)
 	cudaStream_t copy_stream = nullptr;                   // D2H of each sub-batch's cigar range, in retirement order
@@ -555,16 +608,19 @@ int kb_init(int device, kb_ctx_t** out)
 	memset(&ctx->ix, 0, sizeof(ctx->ix)); memset(ctx->stage_ms, 0, sizeof(ctx->stage_ms)); memset(ctx->work_host, 0, sizeof(ctx->work_host)); memset(ctx->counters_host, 0, sizeof(ctx->counters_host));
 	ctx->pm.min_seed = 0; ctx->pm.max_gaps = 5; ctx->pm.max_insert = 1500; ctx->pm.pacbio = 0; ctx->pm.multihit = 0; ctx->pm.paired = 0;
 	if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return KB_ECUDA; }
+#ifndef KB_EMUL
+	{ const char* g = getenv("KB_L2_FETCH"); if (g && (atoi(g) == 32 || atoi(g) == 64 || atoi(g) == 128)) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g)); }   // A/B knob: bytes the L2 fetches from HBM per miss
+#endif
 	for (int k = 0; k < KB_SLOTS; k++)
 	{
 		kb_slot& sl = ctx->slot[k];
 		memset(&sl.bt, 0, sizeof(sl.bt));
-		if (cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return KB_ECUDA; }
+		if (cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) != cudaSuccess) { kb_destroy(ctx); return KB_ECUDA; }
 		for (int i = 0; i < 10; i++) cudaEventCreate(&sl.ev[i]);
-		cudaEventCreate(&sl.done);
+		cudaEventCreate(&sl.done); cudaEventCreate(&sl.nw0); cudaEventCreate(&sl.nw1);
 		cudaEventCreateWithFlags(&sl.fork, cudaEventDisableTiming);
-		for (int i = 0; i < KB_NW_CLASSES; i++) { if (cudaStreamCreateWithFlags(&sl.aux[i], cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return KB_ECUDA; } cudaEventCreateWithFlags(&sl.join[i], cudaEventDisableTiming); }
-		if (cudaMallocHost((void**)&sl.counters_host, KB_NCOUNTERS * sizeof(u32)) != cudaSuccess || cudaMallocHost((void**)&sl.work_dev_host, 8 * sizeof(unsigned long long)) != cudaSuccess) { delete ctx; return KB_ECUDA; }
+		for (int i = 0; i < KB_NW_CLASSES; i++) { if (cudaStreamCreateWithFlags(&sl.aux[i], cudaStreamNonBlocking) != cudaSuccess) { kb_destroy(ctx); return KB_ECUDA; } cudaEventCreateWithFlags(&sl.join[i], cudaEventDisableTiming); }
+		if (cudaMallocHost((void**)&sl.counters_host, KB_NCOUNTERS * sizeof(u32)) != cudaSuccess || cudaMallocHost((void**)&sl.work_dev_host, 8 * sizeof(unsigned long long)) != cudaSuccess) { kb_destroy(ctx); return KB_ECUDA; }
 		memset(sl.counters_host, 0, KB_NCOUNTERS * sizeof(u32)); memset(sl.work_dev_host, 0, 8 * sizeof(unsigned long long));
 	}
 	cudaEventCreate(&ctx->chunk_start); ctx->trace = getenv("KB_PIPE_TRACE") ? 1 : 0;
@@ -572,10 +628,11 @@ int kb_init(int device, kb_ctx_t** out)
 	e = getenv("KB_SEED_MINB"); if (e && (atoi(e) == 8 || atoi(e) == 12)) ctx->seed_minb = atoi(e);
 	e = getenv("KB_PIPE_SUB_READS"); if (e && atoi(e) > 0) ctx->pipe_sub_reads = atoi(e);
 	e = getenv("KB_RESCUE_THREADS"); if (e && (atoi(e) == 32 || atoi(e) == 64 || atoi(e) == 128)) ctx->rescue_threads = atoi(e);
+	e = getenv("KB_RESCUE_FAST"); if (e) ctx->rescue_fast = atoi(e) ? 1 : 0;
 	e = getenv("KB_PIPE_FIRST"); if (e && atoi(e) >= -1) ctx->pipe_first = atoi(e);
 	e = getenv("KB_PIPE_GROW"); if (e && atoi(e) >= 100) ctx->pipe_grow = atoi(e);
 	e = getenv("KB_PIPE_TAIL"); if (e && atoi(e) >= 0) ctx->pipe_tail = atoi(e);
-	if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return KB_ECUDA; }
+	if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { kb_destroy(ctx); return KB_ECUDA; }
 	e = getenv("KB_NW_STREAMS"); if (e) ctx->nw_streams = atoi(e) ? 1 : 0;
 	e = getenv("KB_ALIGN_WARPS"); if (e && atoi(e) >= 148 && atoi(e) <= 148 * 64) ctx->align_warps = atoi(e) / 4 * 4;
 	e = getenv("KB_NW_TMAX"); if (e && (atoi(e) == 32 || atoi(e) == 64 || atoi(e) == 128)) ctx->nw_tmax = atoi(e);
@@ -602,17 +659,19 @@ void kb_destroy(kb_ctx_t* ctx)
 	if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
 	ctx->occ.release(); ctx->ktab.release(); ctx->ref64.release(); ctx->sa.release(); ctx->sa_full.release(); ctx->pac.release(); ctx->lut.release(); ctx->chr64.release(); ctx->chr32.release();
 	ctx->chunk_cigar.release(); ctx->chunk_cursor.release();
-	for (int k = 0; k < KB_SLOTS; k++)
+	for (int k = 0; k < KB_SLOTS; k++)   // every handle may be null: kb_init calls this on its failure paths
 	{
 		kb_slot& sl = ctx->slot[k];
 		sl.release();
-		for (int i = 0; i < 10; i++) cudaEventDestroy(sl.ev[i]);
-		cudaEventDestroy(sl.done);
-		cudaEventDestroy(sl.fork);
-		for (int i = 0; i < KB_NW_CLASSES; i++) { cudaEventDestroy(sl.join[i]); cudaStreamDestroy(sl.aux[i]); }
+		for (int i = 0; i < 10; i++) if (sl.ev[i]) cudaEventDestroy(sl.ev[i]);
+		if (sl.done) cudaEventDestroy(sl.done);
+		if (sl.nw0) cudaEventDestroy(sl.nw0);
+		if (sl.nw1) cudaEventDestroy(sl.nw1);
+		if (sl.fork) cudaEventDestroy(sl.fork);
+		for (int i = 0; i < KB_NW_CLASSES; i++) { if (sl.join[i]) cudaEventDestroy(sl.join[i]); if (sl.aux[i]) cudaStreamDestroy(sl.aux[i]); }
 		if (sl.counters_host) cudaFreeHost(sl.counters_host);
 		if (sl.work_dev_host) cudaFreeHost(sl.work_dev_host);
-		cudaStreamDestroy(sl.stream);
+		if (sl.stream) cudaStreamDestroy(sl.stream);
 	}
 	delete ctx;
 }
@@ -796,8 +855,8 @@ static int alloc_batch(kb_ctx* ctx, kb_slot& sl, int shared)
 	CK(sl.segs.ensure(sl.cap_segs)); CK(sl.cands.ensure(sl.cap_cands)); CK(sl.reports.ensure(sl.cap_cands));
 	CK(sl.n_cands.ensure(n)); CK(sl.cand_off.ensure(n)); CK(sl.cand_cap.ensure(n)); CK(sl.rescue.ensure(n / 2 + 1));
 	sl.cap_rtasks = ctx->pm.paired ? (size_t)(ctx->rtask_factor * (double)n) + 65536 : 1;
-	CK(sl.rtasks.ensure(sl.cap_rtasks)); CK(sl.rjob_first.ensure(n / 2 + 1)); CK(sl.rjob_count.ensure(n / 2 + 1));
-	bt.segx_slab = nullptr; bt.rtasks = sl.rtasks.p; bt.cap_rtasks = (u32)sl.cap_rtasks; bt.rjob_first = sl.rjob_first.p; bt.rjob_count = sl.rjob_count.p;
+	CK(sl.rtasks.ensure(sl.cap_rtasks)); CK(sl.rslow.ensure(sl.cap_rtasks)); CK(sl.rjob_first.ensure(n / 2 + 1)); CK(sl.rjob_count.ensure(n / 2 + 1));
+	bt.segx_slab = nullptr; bt.rtasks = sl.rtasks.p; bt.cap_rtasks = (u32)sl.cap_rtasks; bt.rjob_first = sl.rjob_first.p; bt.rjob_count = sl.rjob_count.p; bt.rslow = sl.rslow.p;
 	CK(sl.res.ensure(n)); CK(sl.pstat.ensure(n / 2 + 1)); CK(sl.aln.ensure(n));
 	if (!shared) CK(sl.cigar.ensure(sl.cap_cigar));
 	sl.cap_extra = ctx->pm.multihit ? (size_t)(ctx->extra_factor * (double)n) + 65536 : 0;
@@ -863,6 +922,7 @@ static int launch_phase_b(kb_ctx* ctx, kb_slot& sl)
 	KB_LAUNCH(k_align_part, g_warp, KB_BLOCK, s, ix, pm, bt, ctx->part_pool);
 #endif
 	sl.launches++;
+	CK(cudaEventRecord(sl.nw0, s));
 	// The size classes are independent and each is latency-bound on its own (one problem per thread: a launch lasts as long as
 	// its longest chain of cells), so they run side by side on the slot's aux streams, heaviest first, and join before the gather.
 	{
@@ -878,6 +938,7 @@ static int launch_phase_b(kb_ctx* ctx, kb_slot& sl)
 		KB_LAUNCH((k_nw_tile<0, 8, 32, 1>), 148 * 8, KB_BLOCK, q[0], ix, pm, bt); sl.launches++;
 		if (ctx->nw_streams) for (int i = 0; i < KB_NW_CLASSES; i++) { CK(cudaEventRecord(sl.join[i], q[i])); CK(cudaStreamWaitEvent(s, sl.join[i], 0)); }
 	}
+	CK(cudaEventRecord(sl.nw1, s));
 	KB_LAUNCH(k_align_gather, 148 * 4, KB_BLOCK, s, bt); sl.launches++;
 	return KB_OK;
 }
@@ -927,6 +988,16 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 	{
 		unsigned rt = (unsigned)ctx->rescue_threads, g = (unsigned)bt.scratch_threads / rt; if (g > 148u * 32u) g = 148u * 32u;
 		KB_LAUNCH(k_rescue_plan, 148 * 4, KB_BLOCK, s, ix, pm, bt); sl.launches++;
+		if (ctx->rescue_fast)
+		{
+#ifndef KB_EMUL
+			k_rescue_fast<<<148 * 8, KB_BLOCK, (KB_BLOCK / 32) * sizeof(KbRescueFast), s>>>(ix, pm, bt);
+#else
+			KB_LAUNCH(k_rescue_fast, 1, KB_BLOCK, s, ix, pm, bt);
+#endif
+			sl.launches++;
+		}
+		else { KB_LAUNCH(k_rescue_all_slow, 148 * 4, KB_BLOCK, s, bt); sl.launches++; }
 		KB_LAUNCH(k_rescue_win, g, rt, s, ix, pm, bt); sl.launches++;
 		KB_LAUNCH(k_rescue_commit, 148 * 4, KB_BLOCK, s, ix, pm, bt); sl.launches++;
 	}
@@ -964,6 +1035,7 @@ static void account_slot(kb_ctx* ctx, kb_slot& sl)
 {
 	for (int i = 0; i < 8; i++) { float ms = 0; cudaEventElapsedTime(&ms, sl.ev[i], sl.ev[i + 1]); ctx->stage_ms[i] += ms; }
 	{ float ms = 0; cudaEventElapsedTime(&ms, sl.ev[0], sl.ev[8]); ctx->stage_ms[8] += ms; }
+	{ float ms = 0; cudaEventElapsedTime(&ms, sl.nw0, sl.nw1); ctx->stage_ms[9] += ms; }
 	const unsigned long long* w = sl.work_dev_host; const u32* c = sl.counters_host;
 	ctx->work_host[0] += w[0]; ctx->work_host[1] += w[1]; ctx->work_host[2] += w[2]; ctx->work_host[3] += w[3];
 	ctx->work_host[4] += c[0]; ctx->work_host[5] += w[4]; ctx->work_host[6] += c[7]; ctx->work_host[7] += (uint64_t)sl.launches;
@@ -1065,6 +1137,16 @@ static void pipeline_plan(const kb_ctx* ctx, int n, std::vector<int>& first, std
 	}
 }
 
+// an error in the middle of a pipelined chunk must not return while copies into the caller's buffers are still in flight
+static int drain_pipeline(kb_ctx* ctx, int rc)
+{
+	for (int k = 0; k < KB_SLOTS; k++) if (ctx->slot[k].stream) cudaStreamSynchronize(ctx->slot[k].stream);
+	if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+	cudaGetLastError();
+	return rc;
+}
+#define CKP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return drain_pipeline(ctx, fail(ctx, e_ == cudaErrorMemoryAllocation ? KB_ENOMEM : KB_ECUDA, #call, e_)); } while (0)
+
 static int map_chunk_pipelined(kb_ctx* ctx, const kb_reads_t* in, const int32_t* est, kb_results_t* out)
 {
 	const int n = in->n_reads;
@@ -1087,13 +1169,13 @@ static int map_chunk_pipelined(kb_ctx* ctx, const kb_reads_t* in, const int32_t*
 			kb_slot& sl = ctx->slot[k % KB_SLOTS];
 			if (k >= KB_SLOTS)   // retire the sub-batch that used this slot
 			{
-				CK(cudaStreamSynchronize(sl.stream));
+				CKP(cudaStreamSynchronize(sl.stream));
 				status |= sl.counters_host[3];
 				account_slot(ctx, sl);
 				const u32 lo = sl.counters_host[30], hi = sl.counters_host[31];
 				if (hi > n_cigar) n_cigar = hi;
 				if (hi > out->cap_cigar) fits = false;
-				if (!status && fits && hi > lo) CK(cudaMemcpyAsync(out->cigar + lo, ctx->chunk_cigar.p + lo, (size_t)(hi - lo) * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+				if (!status && fits && hi > lo) CKP(cudaMemcpyAsync(out->cigar + lo, ctx->chunk_cigar.p + lo, (size_t)(hi - lo) * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
 				if (ctx->trace)
 				{
 					float a = 0, b = 0, c = 0, d = 0;
@@ -1104,13 +1186,13 @@ static int map_chunk_pipelined(kb_ctx* ctx, const kb_reads_t* in, const int32_t*
 			}
 			if (status || k >= nsub) continue;
 			const int first = p_first[k], count = p_count[k];
-			CK(cudaEventRecord(sl.ev[9], sl.stream));
-			int rc = stage_slot(ctx, sl, in, first, count, est); if (rc) return rc;
-			rc = alloc_batch(ctx, sl, 1); if (rc) return rc;
-			rc = launch_pipeline(ctx, sl); if (rc) return rc;
-			CK(cudaMemcpyAsync(out->aln + first, sl.aln.p, (size_t)count * sizeof(kb_aln_t), cudaMemcpyDeviceToHost, sl.stream));
-			if (ctx->pm.paired && out->pairs) CK(cudaMemcpyAsync(out->pairs + first / 2, sl.pstat.p, (size_t)(count / 2) * sizeof(kb_pair_stat_t), cudaMemcpyDeviceToHost, sl.stream));
-			CK(cudaEventRecord(sl.done, sl.stream));
+			CKP(cudaEventRecord(sl.ev[9], sl.stream));
+			int rc = stage_slot(ctx, sl, in, first, count, est); if (rc) return drain_pipeline(ctx, rc);
+			rc = alloc_batch(ctx, sl, 1); if (rc) return drain_pipeline(ctx, rc);
+			rc = launch_pipeline(ctx, sl); if (rc) return drain_pipeline(ctx, rc);
+			CKP(cudaMemcpyAsync(out->aln + first, sl.aln.p, (size_t)count * sizeof(kb_aln_t), cudaMemcpyDeviceToHost, sl.stream));
+			if (ctx->pm.paired && out->pairs) CKP(cudaMemcpyAsync(out->pairs + first / 2, sl.pstat.p, (size_t)(count / 2) * sizeof(kb_pair_stat_t), cudaMemcpyDeviceToHost, sl.stream));
+			CKP(cudaEventRecord(sl.done, sl.stream));
 		}
 		if (status == 0)
 		{
@@ -1139,7 +1221,7 @@ int kb_map_chunk(kb_ctx_t* ctx, const kb_reads_t* in, const int32_t* est, kb_res
 	return kb_fetch_results(ctx, out);
 }
 
-int kb_stage_ms(kb_ctx_t* ctx, float* ms, int n) { if (!ctx || !ms) return KB_EINVAL; int k = n < 9 ? n : 9; for (int i = 0; i < k; i++) ms[i] = ctx->stage_ms[i]; return k; }
+int kb_stage_ms(kb_ctx_t* ctx, float* ms, int n) { if (!ctx || !ms) return KB_EINVAL; int k = n < 10 ? n : 10; for (int i = 0; i < k; i++) ms[i] = ctx->stage_ms[i]; return k; }
 int kb_work(kb_ctx_t* ctx, uint64_t* w, int n) { if (!ctx || !w) return KB_EINVAL; int k = n < 8 ? n : 8; for (int i = 0; i < k; i++) w[i] = ctx->work_host[i]; return k; }
 
 int64_t kb_debug_fetch(kb_ctx_t* ctx, int what, void* dst, uint64_t bytes)

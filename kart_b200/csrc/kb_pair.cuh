@@ -141,6 +141,120 @@ KB_HD void kb_rj_pairs(const KbIndexDev& ix, KbRescueJob* j, int tid, int nth)
 	}
 }
 
+// ---- warp-per-window fast path ---------------------------------------------------------------------------
+// Nearly every rescue window lies inside the text (pure ACGT) and faces a mate of pure bases. Then the 8-mer ids on both sides
+// are 16 bits of the packed sequences, "the 8-mers at (r,g) and (r-1,g-1) both match" is "base r-1 equals base g-1", and a run of
+// matching 8-mers is an exact base match: the window's runs of >= 10 bases are the left-maximal exact matches between mate and
+// window, each found where a window 8-mer hits the mate's 8-mer index and measured by XOR + count-leading-zeros on 32-base
+// words. One warp does a window out of shared memory: the mate's packed words, the window's packed words (one kb_ref_win per 32
+// positions instead of one per position), a 512-slot open-addressing index of the mate's 8-mers and the run list. ncu r17 (C3, 3.1 Gbp:
+// 244 k windows per million reads) had the block-per-window version at 44 k warp instructions per window, a third of them
+// probing the index in the HBM arena; this one needs about a thousand. Windows it cannot take (outside the text, a mate with
+// other characters or longer than 255, a window of more than 2048 positions, more than KB_RF_PAIRS runs) go to the slow list and
+// through the block-per-window phases above unchanged.
+#define KB_RF_SLOTS 512
+#define KB_RF_WORDS 66      // window words: 2048 positions + the word the last 8-mers reach into + 1
+#define KB_RF_PAIRS 24
+struct KbRescueFast
+{
+	u32 hkey[KB_RF_SLOTS]; u32 hhead[KB_RF_SLOTS];
+	u64 wcode[KB_RF_WORDS]; u64 mcode[10];
+	KbSeg pairs[KB_RF_PAIRS];
+	u8 hnext[256];
+	u32 task, npairs; i32 ok, dirty, ml, slen, mate_read; i64 left;
+};
+KB_HD u64 kb_rf_bits(const u64* w, int p)   // 32 bases starting at base p of a packed word array (one spare word behind the data)
+{
+	const int s = (p & 31) * 2; const u64 a = w[p >> 5];
+	return s ? (a << s) | (w[(p >> 5) + 1] >> (64 - s)) : a;
+}
+// lane 0: the task's window and mate; decides whether the fast path applies
+KB_HD void kb_rf_begin(const KbIndexDev& ix, const KbBatchDev& bt, KbRescueFast& w, u32 task)
+{
+	const KbRTask t = bt.rtasks[task];
+	const int p = bt.rescue_list[t.job], ra = 2 * p, rb = ra + 1;
+	w.task = task; w.npairs = 0; w.dirty = 0;
+	w.mate_read = t.side == 0 ? rb : ra;
+	w.ml = (int)(bt.seq_off[w.mate_read + 1] - bt.seq_off[w.mate_read]);
+	w.left = t.left; w.slen = t.slen;
+	w.ok = (t.left >= 0 && t.left + (i64)t.slen <= ix.G2 && t.slen <= 2048 && w.ml >= 8 && w.ml <= 255) ? 1 : 0;
+}
+// all lanes: clear the index, fetch the packed mate (flagging characters that are no bases) and the packed window
+KB_HD void kb_rf_load(const KbIndexDev& ix, const KbBatchDev& bt, KbRescueFast& w, int lane)
+{
+	if (!w.ok) return;
+	for (int s = lane; s < KB_RF_SLOTS; s += 32) { w.hkey[s] = 0; w.hhead[s] = 0xFFFFFFFFu; }
+	const KbPk* rd = kb_pk_read(bt, w.mate_read);
+	const int mw = (w.ml + 31) >> 5;
+	for (int k = lane; k < 10; k += 32)
+	{
+		u64 code = 0;
+		if (k < mw) { const KbPk v = kb_load_pk(rd + k); code = v.code; u32 n4 = v.n4; const int rem = w.ml - 32 * k; if (rem < 32) n4 &= ~(~0u >> rem); if (n4) w.dirty = 1; }
+		w.mcode[k] = code;
+	}
+	const int ww = ((w.slen + 31) >> 5) + 1;
+	for (int k = lane; k < ww; k += 32) { u32 inv; w.wcode[k] = kb_ref_win(ix, w.left + 32 * (i64)k, &inv); }
+}
+// all lanes: index the mate's 8-mers
+KB_HD void kb_rf_fill(KbRescueFast& w, int lane)
+{
+	if (!w.ok || w.dirty) return;
+	for (int r = lane; r + 8 <= w.ml; r += 32)
+	{
+		const u32 id = (u32)(kb_rf_bits(w.mcode, r) >> 48);
+		u32 s = kb_rj_slot(id, KB_RF_SLOTS - 1);
+		while (true)
+		{
+			const u32 old = KB_ATOMIC_CAS(&w.hkey[s], 0u, id + 1u);
+			if (old == 0u || old == id + 1u) break;
+			s = (s + 1u) & (u32)(KB_RF_SLOTS - 1);
+		}
+		w.hnext[r] = (u8)KB_ATOMIC_EXCH(&w.hhead[s], (u32)r);
+	}
+}
+// all lanes: the left-maximal exact matches of >= 10 bases (kb_rj_pairs on packed words)
+KB_HD void kb_rf_pairs(KbRescueFast& w, int lane)
+{
+	if (!w.ok || w.dirty) return;
+	const u64 M5 = 0x5555555555555555ull;
+	const int ml = w.ml, sl = w.slen, npos = sl - 7;
+	for (int g = lane; g < npos; g += 32)
+	{
+		const u32 id = (u32)(kb_rf_bits(w.wcode, g) >> 48);
+		u32 s = kb_rj_slot(id, KB_RF_SLOTS - 1), key;
+		while ((key = w.hkey[s]) != 0u && key != id + 1u) s = (s + 1u) & (u32)(KB_RF_SLOTS - 1);
+		if (key == 0u) continue;
+		for (u32 r = w.hhead[s]; r < 255u; r = w.hnext[r])
+		{
+			if (r > 0 && g > 0 && ((w.mcode[(r - 1) >> 5] >> (62 - 2 * ((r - 1) & 31))) & 3ull) == ((w.wcode[(g - 1) >> 5] >> (62 - 2 * ((g - 1) & 31))) & 3ull)) continue;   // not the start of its run
+			const int lim = ml - (int)r < sl - g ? ml - (int)r : sl - g;
+			int l = 0;
+			while (l < lim)
+			{
+				u64 x = kb_rf_bits(w.mcode, (int)r + l) ^ kb_rf_bits(w.wcode, g + l); x = (x | (x >> 1)) & M5;
+				const int same = x ? (int)KB_CLZLL(x) >> 1 : 32;
+				l += same;
+				if (same < 32) break;
+			}
+			if (l > lim) l = lim;
+			if (l < 10) continue;
+			const u32 slot = KB_ATOMIC_ADD(&w.npairs, 1u);
+			if (slot < (u32)KB_RF_PAIRS) { KbSeg sg; sg.simple = 1; sg.rpos = (i32)r; sg.gpos = (i64)g; sg.rlen = sg.glen = l; w.pairs[slot] = sg; }
+		}
+	}
+}
+// lane 0: the task's result (kb_rt_end), or the task's place on the slow list
+KB_HD void kb_rf_end(const KbParams& pm, const KbBatchDev& bt, KbRescueFast& w)
+{
+	if (!w.ok || w.dirty || w.npairs > (u32)KB_RF_PAIRS) { const u32 slot = KB_ATOMIC_ADD(&bt.counters[29], 1u); bt.rslow[slot] = w.task; return; }
+	const int np = (int)w.npairs;
+	kb_sort_segs<false>(w.pairs, np);
+	KbCand c;
+	const int score = kb_rescue_cluster(pm, bt, w.left, w.pairs, np, &c);
+	KbRTask* t = &bt.rtasks[w.task];
+	t->score = score; t->diff = c.diff; t->seg_start = c.seg_start; t->nseg = c.nseg;
+}
+
 // ---- task-parallel rescue ----------------------------------------------------------------------------
 // The anchors a rescue job visits, their reference windows and the thresholds all follow from the candidates the pair had
 // BEFORE rescue (scores sc1/sc2, thr, EstDistance): what one window yields never depends on what another window appended.

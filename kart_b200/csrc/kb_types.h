@@ -113,6 +113,7 @@ struct KbBatchDev
 	u32* segx_slab;                     // {next, end} of the calling warp's reserved range of segx (shared memory; NULL: none). Set by k_segments
 	KbRTask* rtasks; u32 cap_rtasks;    // rescue windows (cursor: counters[27]); a job's tasks are rtasks[rjob_first[k] .. + rjob_count[k])
 	u32* rjob_first; u32* rjob_count;
+	u32* rslow;                         // rescue windows the warp-per-window fast path handed back (count: counters[29]); cap_rtasks entries
 	i32* slow_list; i32* slow_list2;    // reads whose segments / reports need the HBM arena (counters[12], counters[13])
 	// stage 3: segments of the surviving candidates, alignment jobs, run arena
 	KbSegX* segx; u32 cap_segx; u32* cseg_off; i32* cseg_n;   // cseg_* indexed like cands (cseg_n < 0: candidate dropped)
@@ -135,7 +136,7 @@ struct KbBatchDev
 	i32 seg_cap, kmer_cap;
 	// counters: [0] seeds cursor [1] cands cursor [2] cigar cursor [3] status bits [4] rescue count [5] max seeds/read
 	//           [6] nw calls [7] rescue attempts [8] segx cursor [10] run cursor + [11] job cursor (one u64) [12],[13] slow lists [14] extra-line cursor (-m)
-	//           [16..22] pieces per size class [23] partition jobs [24] piece cursor [26] k_align_part job tickets [27] rescue task cursor [28] rescue task tickets
+	//           [16..22] pieces per size class [23] partition jobs [24] piece cursor [25] fast rescue tickets [26] k_align_part job tickets [27] rescue task cursor [28] slow rescue tickets [29] slow rescue list
 	//           [30],[31] cigar cursor before / after the assemble kernels (pipelined chunks)
 	//           64-bit: work[0] extension steps, work[1] occ blocks, work[2] LF steps, work[3] NW cells, work[4] NW calls
 	u32* counters;

@@ -74,6 +74,31 @@ def make_genome(total_bp: int, n_contigs: int, seed: int, repeats=((3000, 20, 0.
     return names, seqs
 
 
+class PacText:
+    """The forward strand of a BWA .pac file (2 bit / base, MSB first) addressed like a uint8 array of upper-case bases, decoded
+    on access: read simulation on a multi-Gbp genome then touches only the windows it samples instead of a decoded copy."""
+
+    def __init__(self, pac: np.ndarray, l_pac: int):
+        self.pac, self.l_pac = pac, int(l_pac)
+
+    def __len__(self):
+        return self.l_pac
+
+    def __getitem__(self, key):
+        if isinstance(key, slice):
+            idx = np.arange(*key.indices(self.l_pac), dtype=np.int64)
+        else:
+            idx = np.asarray(key, dtype=np.int64)
+        return _ACGT[(self.pac[idx >> 2] >> ((~idx & 3) << 1).astype(np.uint8)) & 3]
+
+
+class PacGenome:
+    """(contig lengths, PacText): accepted by simulate() in place of the list of decoded contigs"""
+
+    def __init__(self, pac: np.ndarray, l_pac: int, lens):
+        self.text, self.lens = PacText(pac, l_pac), np.asarray(lens, dtype=np.int64)
+
+
 def _apply_errors(reads: np.ndarray, rng, err: float, snp: float) -> None:
     code = np.zeros(256, dtype=np.uint8)
     for i, c in enumerate(b"ACGT"):
@@ -92,8 +117,11 @@ def simulate(genome_seqs, n: int, read_len: int, err: float, seed: int, paired: 
     """Returns (r1, r2, pos) : uint8 arrays [n, read_len] in sequencer orientation (r2 None if not paired)
     and the 0-based forward-strand start of each fragment in the concatenated genome."""
     rng = np.random.default_rng(seed)
-    lens = np.array([len(s) for s in genome_seqs], dtype=np.int64)
-    cat = np.concatenate(genome_seqs)
+    if isinstance(genome_seqs, PacGenome):
+        lens, cat = genome_seqs.lens, genome_seqs.text
+    else:
+        lens = np.array([len(s) for s in genome_seqs], dtype=np.int64)
+        cat = np.concatenate(genome_seqs)
     starts = np.concatenate([[0], np.cumsum(lens)])
     frag = np.maximum(read_len, np.rint(rng.normal(insert_mean, insert_sd, size=n)).astype(np.int64)) if paired \
         else np.full(n, read_len, dtype=np.int64)
@@ -104,10 +132,17 @@ def simulate(genome_seqs, n: int, read_len: int, err: float, seed: int, paired: 
     off = (rng.random(n) * np.maximum(lens[ctg] - frag - slack, 1)).astype(np.int64)
     pos = starts[ctg] + off
     idx = np.arange(read_len, dtype=np.int64)[None, :]
-    left = cat[pos[:, None] + idx].copy()
+
+    def windows(start):   # [n, read_len] bases, gathered in slices so that the index temporaries stay small
+        out = np.empty((n, read_len), dtype=np.uint8)
+        step = max(1, (1 << 24) // max(read_len, 1))
+        for a in range(0, n, step):
+            out[a:a + step] = cat[start[a:a + step, None] + idx]
+        return out
+    left = windows(pos)
     right = None
     if paired:
-        right = cat[(pos + frag - read_len)[:, None] + idx].copy()
+        right = windows(pos + frag - read_len)
     # short indels, applied per read (python loop over the few affected reads)
     if indel > 0:
         for arr, base in ((left, pos), (right, (pos + frag - read_len) if paired else None)):

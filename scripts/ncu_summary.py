@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep (ncu --set full) and an ncu launch list into small tracked files under profiles/.
-Usage: python scripts/ncu_summary.py <tag>   (reads gpurun_out/<tag>_prof.ncu-rep, gpurun_out/<tag>_launches.csv)"""
+Usage: python scripts/ncu_summary.py <tag> [pairs per launch] [index name]   (reads gpurun_out/<tag>_prof.ncu-rep, gpurun_out/<tag>_launches.csv)
+Run it on the box that took the capture (or before touching the CUDA sources): the traffic file records the hash of kart_b200/csrc, and
+bench.py only quotes a capture of the build it is running."""
 import csv
 import io
 import os
@@ -55,7 +57,12 @@ def main():
             if name not in tr or g > tr[name]["grid"]:
                 tr[name] = {"grid": g, "block": int(float(r[hdr.index("launch__block_size")])), "dram_bytes": float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]], "duration_ms": float(r[ti]) * {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(units[ti], 1.0)}
         pairs = int(sys.argv[2]) if len(sys.argv) > 2 else 500000
-        json.dump({"tag": tag, "pairs_per_launch": pairs, "kernels": tr}, open(os.path.join(ROOT, "profiles", tag + "_traffic.json"), "w"), indent=1)
+        import hashlib
+        h = hashlib.sha256()
+        d = os.path.join(ROOT, "kart_b200", "csrc")
+        for f in sorted(os.listdir(d)):
+            h.update(open(os.path.join(d, f), "rb").read())
+        json.dump({"tag": tag, "pairs_per_launch": pairs, "workload": sys.argv[3] if len(sys.argv) > 3 else "EcoliIdx", "source_sha": h.hexdigest()[:16], "kernels": tr}, open(os.path.join(ROOT, "profiles", tag + "_traffic.json"), "w"), indent=1)
     lc = os.path.join(ROOT, "gpurun_out", tag + "_launches.csv")
     if os.path.exists(lc):
         rows = [r for r in csv.reader(open(lc, errors="replace")) if len(r) > 10 and r[0].isdigit()]

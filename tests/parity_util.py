@@ -101,6 +101,35 @@ def genome_of(idx: KartIndex):
     return out
 
 
+def pac_genome(idx: KartIndex):
+    """The same genome for synth.simulate() without decoding it (multi-Gbp indexes)."""
+    return synth.PacGenome(idx.pac, idx.l_pac, idx.chr_len)
+
+
+def ensure_syn_index(mbp: int = 3100, contigs: int = 24, seed: int = 12345):
+    """Prefix of the synthetic <mbp> Mbp index (BASELINE configs 3-5 use 3100), built on first use with this repo's `kart index`
+    (scripts/make_syn_index.py) and cached under data/_gen/syn/ -- the files are too large to travel with a snapshot. Returns None,
+    with the reason printed, when the host cannot build it."""
+    import subprocess
+    prefix = os.path.join(GEN_DIR, "syn", "syn%d" % mbp)
+    if all(os.path.exists(prefix + e) for e in (".bwt", ".sa", ".pac", ".ann")):
+        return prefix
+    avail_gb = 0
+    for ln in open("/proc/meminfo"):
+        if ln.startswith("MemAvailable"):
+            avail_gb = int(ln.split()[1]) >> 20
+    need = mbp * 23 // 1000 + 4
+    if avail_gb < need or (os.cpu_count() or 1) < 8:
+        print("ensure_syn_index: NOT building the %d Mbp index (needs ~%d GB of host memory and >= 8 cores; this host: %d GB, %d cores)" % (mbp, need, avail_gb, os.cpu_count() or 1))
+        return None
+    env = dict(os.environ, KART_INDEX_BUILDER="ours")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "make_syn_index.py"), str(mbp), str(contigs), str(seed)], env=env, capture_output=True, text=True)
+    if r.returncode != 0 or not os.path.exists(prefix + ".sa"):
+        print("ensure_syn_index: build failed: %s" % (r.stderr[-400:] or r.stdout[-400:]))
+        return None
+    return prefix
+
+
 def interleave(r1: np.ndarray, r2: np.ndarray) -> np.ndarray:
     """Pairs in the layout the C ABI expects: read 2i = mate 1, read 2i+1 = reverse-complemented mate 2."""
     n, L = r1.shape

@@ -250,3 +250,22 @@ def test_pipelined_chunk_equals_single_batch(mini, monkeypatch, plan):
     for i in range(len(a0)):
         assert np.array_equal(c0[a0["cig_off"][i]:a0["cig_off"][i] + a0["cig_len"][i]], c1[a1["cig_off"][i]:a1["cig_off"][i] + a1["cig_len"][i]])
     assert m0.work()["ext_steps"] == m1.work()["ext_steps"] and m0.work()["nw_cells"] == m1.work()["nw_cells"]
+
+
+def test_rescue_fast_path_and_fallback(mini, monkeypatch):
+    """Rescue windows go through the warp-per-window fast path (kb_rf_*) unless the window leaves the text or the mate holds a
+    character that is no base; either route gives the oracle's pairs."""
+    idx, g = mini
+    r1, r2, _ = synth.simulate(g, 1200, 150, 0.07, seed=41, indel=0.005)
+    reads = pu.interleave(r1, r2)
+    reads[5::40, 70] = ord("N")   # a few dirty mates: slow list
+    orc = pu.Oracle(pu.MINI_PREFIX)
+    m = pu.make_mapper(idx, emul=True, paired=True)
+    assert pu.compare_pairs(m, orc, reads) == 0
+    c = m.debug(9, np.uint32, 32)
+    assert c[27] > 20 and c[29] < c[27] // 2, (c[27], c[29])
+    monkeypatch.setenv("KB_RESCUE_FAST", "0")
+    m = pu.make_mapper(idx, emul=True, paired=True)
+    assert pu.compare_pairs(m, orc, reads) == 0
+    c = m.debug(9, np.uint32, 32)
+    assert c[29] == c[27]

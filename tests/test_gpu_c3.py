@@ -1,0 +1,54 @@
+"""-m gpu: BASELINE configs 3, 4 and 5 at their real index size -- the synthetic 3.1 Gbp reference (2G = 6.2e9 > 2^32: 33-bit text
+positions, 64-bit BWT rows, MinSeedLength 16, K = 14 seeding table, 50 GB full SA in HBM) -- through the CUDA path, read by read
+against the oracle. The index is built on the box on first use (about three minutes with `kart index` on 16 cores) and cached; the
+tests skip, saying so, only when the host cannot hold the build (~75 GB)."""
+import os
+
+import numpy as np
+import pytest
+
+import parity_util as pu
+from kart_b200 import KartIndex, Mapper, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def c3(built):
+    prefix = pu.ensure_syn_index(3100, 24, 12345)
+    if prefix is None:
+        print("SKIPPED: 3.1 Gbp index not available on this host")
+        pytest.skip("3.1 Gbp index cannot be built on this host (see ensure_syn_index)")
+    idx = KartIndex(prefix)
+    assert idx.seq_len > 1 << 32 and idx.min_seed_len == 16
+    m = Mapper()
+    m.upload_index(idx, expand_sa=True)
+    return prefix, idx, pu.pac_genome(idx), m
+
+
+def test_c3_paired_100k_pairs_vs_oracle(c3):
+    """C3 shape: 100 000 pairs 2x150 @ 1 % over all 24 contigs (a third of them beyond 2^31 / 2^32 in the 2G text)"""
+    prefix, idx, g, m = c3
+    r1, r2, pos = synth.simulate(g, 100000, 150, 0.01, seed=2)
+    assert (pos > (1 << 31)).mean() > 0.2
+    m.set_params(paired=True)
+    assert pu.compare_pairs(m, pu.Oracle(prefix), pu.interleave(r1, r2)) == 0
+    w = m.work()
+    assert w["rescues"] > 500 and w["lf_steps"] == 0
+
+
+def test_c4_single_end_20k_vs_oracle(c3):
+    """C4 shape: 20 000 single-end 100 bp reads @ 8 %"""
+    prefix, idx, g, m = c3
+    r, _, _ = synth.simulate(g, 20000, 100, 0.08, seed=3, paired=False)
+    m.set_params(paired=False)
+    assert pu.compare_singles(m, pu.Oracle(prefix), r) == 0
+
+
+def test_c5_pacbio_500_reads_vs_oracle(c3):
+    """C5 shape: 500 reads of 7 kbp @ 15 % with -pacbio"""
+    prefix, idx, g, m = c3
+    r, _, _ = synth.simulate(g, 500, 7000, 0.15, seed=4, paired=False, indel=0.01)
+    m.set_params(pacbio=True, paired=False)
+    assert pu.compare_singles(m, pu.Oracle(prefix, pacbio=True), r) == 0
+    assert m.work()["nw_calls"] > 50000

@@ -133,6 +133,24 @@ def test_multi_contig_paired_with_rescue(built):
     assert m.work()["rescues"] > 0
 
 
+def test_rescue_fast_path_and_fallback(built, monkeypatch):
+    """k_rescue_fast (warp per window, shared memory) takes the clean windows, k_rescue_win the rest; both against the oracle."""
+    idx = KartIndex(pu.MINI_PREFIX)
+    g = pu.genome_of(idx)
+    r1, r2, _ = synth.simulate(g, 6000, 150, 0.07, seed=41, indel=0.005)
+    reads = pu.interleave(r1, r2)
+    reads[5::40, 70] = ord("N")
+    orc = pu.Oracle(pu.MINI_PREFIX)
+    m = pu.make_mapper(idx, paired=True)
+    assert pu.compare_pairs(m, orc, reads) == 0
+    c = m.debug(9, np.uint32, 32)
+    assert c[27] > 100 and c[29] < c[27] // 2, (c[27], c[29])
+    monkeypatch.setenv("KB_RESCUE_FAST", "0")
+    m = pu.make_mapper(idx, paired=True)
+    assert pu.compare_pairs(m, orc, reads) == 0
+    assert m.debug(9, np.uint32, 32)[29] == m.debug(9, np.uint32, 32)[27]
+
+
 @pytest.mark.parametrize("plan", [{"KB_PIPE_SUB_READS": "65536"}, {"KB_PIPE_SUB_READS": "100000", "KB_PIPE_FIRST": "8192", "KB_PIPE_GROW": "150", "KB_PIPE_TAIL": "8192"}])
 def test_pipelined_chunk_full_size_equals_single_batch(eco, monkeypatch, plan):
     """C2 at size: 400k reads through kb_map_chunk's slot pipeline (uniform sub-batches of 65536, or a ramped plan; cigar ranges
