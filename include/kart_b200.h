@@ -60,6 +60,23 @@ typedef struct {
 	const uint64_t* seq_off;     /* n_reads + 1 offsets into seq */
 } kb_reads_t;
 
+/* The same chunk in the form the device works on, for callers that pack while parsing (FASTQ text is 8 bits per base; over PCIe
+ * that is the longest pole of kb_map_chunk): 2-bit codes (nst_nt4_table, src/BWT_Index/bntseq.c:40: A/a 0, C/c 1, G/g 2, T/t 3), 32
+ * bases per 64-bit word, base i of a word at bits 62-2i, zero where the character is no base and behind the end of a read. Read r
+ * starts at word (seq_off[r] >> 5) + r and takes ceil(len / 32) words; n_words = (seq_off[n_reads] >> 5) + n_reads + 1.
+ * Every character that is not one of the upper-case letters A C G T is listed in exc, ascending:
+ * (read index << 32) | (position in the read << 8) | character -- the device restores the exact characters from it, so results
+ * are identical to kb_map_chunk on the text (N, lower case and IUPAC codes keep their reference semantics). kb_pack_reads() makes
+ * this form from a kb_reads_t. */
+typedef struct {
+	int32_t n_reads;
+	const uint64_t* code;
+	uint64_t n_words;
+	const uint64_t* seq_off;     /* n_reads + 1 character offsets, as in kb_reads_t */
+	const uint64_t* exc;
+	uint64_t n_exc;
+} kb_reads_packed_t;
+
 /* What OutputPairedAlignments / OutputSingledAlignments (src/Mapping.cpp:177-315) need to print one read's primary line. */
 typedef struct {
 	int64_t pos;                 /* 1-based leftmost coordinate (Coordinate_t::gPos)                */
@@ -113,6 +130,15 @@ int  kb_get_min_seed_len(kb_ctx_t* ctx);
 /* The drop-in call: host buffers in, host buffers out (H2D, all kernels, D2H). est holds one EstDistance per pair
  * (n_reads/2 values) when paired, else it may be NULL. */
 int  kb_map_chunk(kb_ctx_t* ctx, const kb_reads_t* in, const int32_t* est, kb_results_t* out);
+
+/* kb_map_chunk / kb_stage_reads on packed reads (48 instead of 160 bytes per 150-bp read over PCIe). */
+int  kb_map_chunk_packed(kb_ctx_t* ctx, const kb_reads_packed_t* in, const int32_t* est, kb_results_t* out);
+int  kb_stage_reads_packed(kb_ctx_t* ctx, const kb_reads_packed_t* in, const int32_t* est);
+/* Host helper: packs `in` into caller-owned buffers (code: kb_packed_words(in) words; exc: cap_exc entries) on `threads` host
+ * threads and fills *out (which borrows in->seq_off, code and exc). KB_ECAPACITY when exc is too small (out->n_exc then holds
+ * the count needed). Needs no device. */
+uint64_t kb_packed_words(const kb_reads_t* in);
+int  kb_pack_reads(const kb_reads_t* in, uint64_t* code, uint64_t* exc, uint64_t cap_exc, int threads, kb_reads_packed_t* out);
 
 /* The same pipeline in three steps, for callers that keep a batch resident in HBM (bench.py's device-timed `value`). */
 int  kb_stage_reads(kb_ctx_t* ctx, const kb_reads_t* in, const int32_t* est);   /* H2D */

@@ -30,6 +30,10 @@ class KbReads(C.Structure):
     _fields_ = [("n_reads", C.c_int32), ("seq", C.c_void_p), ("seq_off", C.c_void_p)]
 
 
+class KbReadsPacked(C.Structure):
+    _fields_ = [("n_reads", C.c_int32), ("code", C.c_void_p), ("n_words", C.c_uint64), ("seq_off", C.c_void_p), ("exc", C.c_void_p), ("n_exc", C.c_uint64)]
+
+
 class KbResults(C.Structure):
     _fields_ = [("aln", C.c_void_p), ("pairs", C.c_void_p), ("cigar", C.c_void_p), ("cap_cigar", C.c_uint32), ("n_cigar", C.c_uint32)]
 
@@ -50,7 +54,7 @@ RES_DTYPE = np.dtype([("score", "<i4"), ("sub", "<i4"), ("mapq", "<i4"), ("ncan"
 CIGAR_OPS = "MIDNSHP=X"
 
 EXPORTS = ["kb_init", "kb_destroy", "kb_strerror", "kb_last_error", "kb_upload_index", "kb_set_params", "kb_get_min_seed_len",
-           "kb_map_chunk", "kb_stage_reads", "kb_run", "kb_fetch_results", "kb_fetch_extra", "kb_stage_ms", "kb_work", "kb_cuda_stream", "kb_debug_fetch", "kb_debug_align", "kb_host_alloc", "kb_host_free", "kb_host_register", "kb_host_unregister"]
+           "kb_map_chunk", "kb_map_chunk_packed", "kb_stage_reads", "kb_stage_reads_packed", "kb_packed_words", "kb_pack_reads", "kb_run", "kb_fetch_results", "kb_fetch_extra", "kb_stage_ms", "kb_work", "kb_cuda_stream", "kb_debug_fetch", "kb_debug_align", "kb_host_alloc", "kb_host_free", "kb_host_register", "kb_host_unregister"]
 
 
 class KartB200Error(RuntimeError):
@@ -74,6 +78,11 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.kb_get_min_seed_len.argtypes = [C.c_void_p]
     lib.kb_map_chunk.argtypes = [C.c_void_p, C.POINTER(KbReads), C.c_void_p, C.POINTER(KbResults)]
     lib.kb_stage_reads.argtypes = [C.c_void_p, C.POINTER(KbReads), C.c_void_p]
+    lib.kb_map_chunk_packed.argtypes = [C.c_void_p, C.POINTER(KbReadsPacked), C.c_void_p, C.POINTER(KbResults)]
+    lib.kb_stage_reads_packed.argtypes = [C.c_void_p, C.POINTER(KbReadsPacked), C.c_void_p]
+    lib.kb_packed_words.restype = C.c_uint64
+    lib.kb_packed_words.argtypes = [C.POINTER(KbReads)]
+    lib.kb_pack_reads.argtypes = [C.POINTER(KbReads), C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(KbReadsPacked)]
     lib.kb_run.argtypes = [C.c_void_p]
     lib.kb_fetch_results.argtypes = [C.c_void_p, C.POINTER(KbResults)]
     lib.kb_fetch_extra.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
@@ -182,25 +191,53 @@ class Mapper:
             return est
         return np.ascontiguousarray(np.broadcast_to(np.asarray(1500 if est is None else est, dtype=np.int32), (n // 2,)))
 
-    def map_chunk(self, flat, off, est=None, out=None):
-        """Host buffers in, host buffers out (the drop-in call). Returns (aln, pairs, cigar)."""
+    def pack(self, flat, off, code=None, threads=8):
+        """kb_pack_reads: (KbReadsPacked, the arrays it borrows). code: optional caller-owned (e.g. pinned) uint64 buffer."""
+        reads = self._reads_struct(flat, off)
+        nw = int(self.lib.kb_packed_words(C.byref(reads)))
+        if code is None:
+            code = np.zeros(nw, dtype=np.uint64)
+        assert len(code) >= nw
+        exc = np.zeros(max(1024, len(flat) // 64), dtype=np.uint64)
+        pk = KbReadsPacked()
+        rc = self.lib.kb_pack_reads(C.byref(reads), code.ctypes.data, exc.ctypes.data, len(exc), threads, C.byref(pk))
+        if rc == -6:
+            exc = np.zeros(int(pk.n_exc), dtype=np.uint64)
+            rc = self.lib.kb_pack_reads(C.byref(reads), code.ctypes.data, exc.ctypes.data, len(exc), threads, C.byref(pk))
+        self._check(rc, "kb_pack_reads")
+        return pk, (code, exc, off, flat)
+
+    def map_chunk(self, flat, off, est=None, out=None, packed=None):
+        """Host buffers in, host buffers out (the drop-in call). Returns (aln, pairs, cigar). packed: a (KbReadsPacked, keep-alive)
+        pair from pack() sends the 2-bit form over PCIe instead of the text (kb_map_chunk_packed); True packs here first."""
         n = len(off) - 1
         self.n_reads = n
         est_arr = self._est(n, est)
+        if packed is None and os.environ.get("KART_TEST_PACKED"):
+            packed = True
+        if packed is True:
+            packed = self.pack(flat, off)
         reads = self._reads_struct(flat, off)
         aln, pairs, cig, res = self._results(n, 4 * n + 1024, out)
-        rc = self.lib.kb_map_chunk(self.h, C.byref(reads), est_arr.ctypes.data if est_arr is not None else None, C.byref(res))
+        if packed:
+            rc = self.lib.kb_map_chunk_packed(self.h, C.byref(packed[0]), est_arr.ctypes.data if est_arr is not None else None, C.byref(res))
+        else:
+            rc = self.lib.kb_map_chunk(self.h, C.byref(reads), est_arr.ctypes.data if est_arr is not None else None, C.byref(res))
         if rc == -6 and out is None:   # KB_ECAPACITY: results are still on the device, fetch again with a big enough cigar buffer
             aln, pairs, cig, res = self._results(n, int(res.n_cigar))
             rc = self.lib.kb_fetch_results(self.h, C.byref(res))
         self._check(rc, "kb_map_chunk")
         return aln, pairs, cig[:res.n_cigar]
 
-    def stage(self, flat, off, est=None):
+    def stage(self, flat, off, est=None, packed=False):
         n = len(off) - 1
         self.n_reads = n
         self._keep = (flat, off)
         est_arr = self._est(n, est)
+        if packed or os.environ.get("KART_TEST_PACKED"):
+            pk, keep = self.pack(flat, off)
+            self._check(self.lib.kb_stage_reads_packed(self.h, C.byref(pk), est_arr.ctypes.data if est_arr is not None else None), "kb_stage_reads_packed")
+            return
         reads = self._reads_struct(flat, off)
         self._check(self.lib.kb_stage_reads(self.h, C.byref(reads), est_arr.ctypes.data if est_arr is not None else None), "kb_stage_reads")
 

@@ -16,6 +16,7 @@
 #include <string>
 #include <algorithm>
 #include <vector>
+#include <thread>
 #include "../../include/kart_b200.h"
 #include "kb_stages.cuh"
 
@@ -42,6 +43,36 @@ __global__ void __launch_bounds__(KB_BLOCK) k_pack(KbBatchDev bt)
 {
 	long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (t < (long long)bt.n_reads * bt.pk_wpr) kb_pack_word(bt, (int)(t / bt.pk_wpr), (int)(t % bt.pk_wpr));
+}
+
+// packed reads (kb_reads_packed_t) -> KbPk words and the read characters; one thread per (read, word). The characters that are
+// not upper-case bases follow in k_unpack_exc.
+__global__ void __launch_bounds__(KB_BLOCK) k_unpack(KbBatchDev bt, const u64* code, u8* seq)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= (long long)bt.n_reads * bt.pk_wpr) return;
+	const int r = (int)(t / bt.pk_wpr), w = (int)(t % bt.pk_wpr);
+	const u64 off = bt.seq_off[r]; const int len = (int)(bt.seq_off[r + 1] - off);
+	if (32 * w >= len) return;
+	const int n = len - 32 * w < 32 ? len - 32 * w : 32;
+	const u64 at = (off >> 5) - (bt.seq_off[0] >> 5) + (u64)r + (u64)w;   // slot-local word index
+	const u64 c = code[at];
+	KbPk k; k.code = c; k.n4 = n == 32 ? 0u : (~0u >> n); k.bad = k.n4;
+	bt.pk[(off >> 5) + (u64)r + (u64)w] = k;
+	u8* s = seq + (off - bt.seq_off[0]) + 32 * w;
+	for (int i = 0; i < n; i++) s[i] = (u8)(0x54474341u >> (8 * (u32)((c >> (62 - 2 * i)) & 3ull)));   // "ACGT"
+}
+__global__ void __launch_bounds__(KB_BLOCK) k_unpack_exc(KbBatchDev bt, const u64* exc, u32 n_exc, u32 first_read, u8* seq)
+{
+	const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n_exc) return;
+	const u64 e = exc[t]; const u32 r = (u32)(e >> 32) - first_read, pos = (u32)(e >> 8) & 0xFFFFFFu; const u8 ch = (u8)e;
+	const u64 off = bt.seq_off[r];
+	seq[(off - bt.seq_off[0]) + pos] = ch;
+	u32* f = reinterpret_cast<u32*>(&bt.pk[(off >> 5) + (u64)r + (u64)(pos >> 5)]) + 2;   // KbPk: {u64 code; u32 n4; u32 bad}
+	const u32 bit = 1u << (31 - (pos & 31));
+	if (kb_nt4(ch) > 3) KB_ATOMIC_OR(f, bit);
+	KB_ATOMIC_OR(f + 1, bit);
 }
 
 // .pac bytes -> big-endian 64-bit words (upload time only)
@@ -523,14 +554,14 @@ struct kb_slot
 	cudaStream_t stream = nullptr; cudaEvent_t ev[10] = {}; cudaEvent_t done = nullptr; cudaEvent_t nw0 = nullptr, nw1 = nullptr;   // nw0..nw1: the nw_alignment solvers alone
 	cudaStream_t aux[KB_NW_CLASSES] = {}; cudaEvent_t fork = nullptr, join[KB_NW_CLASSES] = {};   // the nw_alignment size classes run side by side (launch_pipeline)
 	KbBatchDev bt; int n_reads = 0; size_t seq_bytes = 0; u64 seq_first = 0; int max_rlen = 0; int first_read = 0;
-	DevBuf<u8> seq, scratch, wscratch; DevBuf<u64> seq_off; DevBuf<unsigned long long> work; DevBuf<i32> est, n_hits, n_seeds, n_cands, cand_cap, rescue, slow1, slow2; DevBuf<u32> seed_off, cand_off, cigar, counters, cseg_off, runs; DevBuf<i32> cseg_n; DevBuf<KbSegX> segx; DevBuf<KbJob> jobs; DevBuf<u32> piece_list, part_list; DevBuf<KbPiece> pieces;
+	DevBuf<u8> seq, scratch, wscratch; DevBuf<u64> seq_off, codes, exc; int packed = 0; u32 n_exc = 0; DevBuf<unsigned long long> work; DevBuf<i32> est, n_hits, n_seeds, n_cands, cand_cap, rescue, slow1, slow2; DevBuf<u32> seed_off, cand_off, cigar, counters, cseg_off, runs; DevBuf<i32> cseg_n; DevBuf<KbSegX> segx; DevBuf<KbJob> jobs; DevBuf<u32> piece_list, part_list; DevBuf<KbPiece> pieces;
 	DevBuf<KbHit> hits; DevBuf<KbSeg> segs; DevBuf<KbCand> cands; DevBuf<KbReport> reports; DevBuf<KbReadRes> res; DevBuf<KbPairStat> pstat; DevBuf<kb_aln_t> aln; DevBuf<KbPk> pk; DevBuf<kb_extra_t> extra; DevBuf<KbRTask> rtasks; DevBuf<u32> rjob_first, rjob_count, rslow; size_t cap_rtasks = 0;
 	size_t cap_segs = 0, cap_cands = 0, cap_cigar = 0, cap_segx = 0, cap_jobs = 0, cap_pieces = 0, cap_runs = 0, cap_extra = 0, scratch_per_thread = 0; int scratch_threads = 0;
 	u32* counters_host = nullptr; unsigned long long* work_dev_host = nullptr;   // pinned: 16 x u32, 8 x u64
 	int launches = 0;
 	void release()
 	{
-		seq.release(); scratch.release(); wscratch.release(); seq_off.release(); work.release(); est.release(); n_hits.release(); n_seeds.release(); n_cands.release(); cand_cap.release();
+		seq.release(); scratch.release(); wscratch.release(); seq_off.release(); codes.release(); exc.release(); work.release(); est.release(); n_hits.release(); n_seeds.release(); n_cands.release(); cand_cap.release();
 		rescue.release(); slow1.release(); slow2.release(); seed_off.release(); cand_off.release(); cigar.release(); counters.release(); cseg_off.release(); runs.release();
 		cseg_n.release(); segx.release(); jobs.release(); piece_list.release(); part_list.release(); pieces.release(); hits.release(); segs.release(); cands.release(); reports.release(); res.release(); pstat.release(); aln.release(); pk.release(); extra.release(); rtasks.release(); rjob_first.release(); rjob_count.release(); rslow.release();
 	}
@@ -540,7 +571,7 @@ struct kb_ctx
 {
 	int device = 0; std::string err;
 	bool have_index = false; KbIndexDev ix; KbParams pm;
-	DevBuf<u32> occ; DevBuf<u64> sa, sa_full, ref64; DevBuf<KbKtab> ktab; DevBuf<u8> pac, lut; DevBuf<i64> chr64; DevBuf<i32> chr32;
+	DevBuf<u32> occ; DevBuf<u64> sa, sa_full, ref64; DevBuf<KbKtab> ktab; DevBuf<u8> pac, lut; DevBuf<i64> chr64; DevBuf<i32> chr32; DevBuf<uint16_t> end_tab;
 	int64_t l_pac = 0;
 	kb_slot slot[KB_SLOTS];
 	DevBuf<u32> chunk_cigar, chunk_cursor;   // cigar arena and cursor shared by the sub-batches of one pipelined chunk
@@ -657,7 +688,7 @@ void kb_destroy(kb_ctx_t* ctx)
 	for (int k = 0; k < KB_SLOTS; k++) if (ctx->slot[k].stream) cudaStreamSynchronize(ctx->slot[k].stream);
 	if (ctx->chunk_start) cudaEventDestroy(ctx->chunk_start);
 	if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
-	ctx->occ.release(); ctx->ktab.release(); ctx->ref64.release(); ctx->sa.release(); ctx->sa_full.release(); ctx->pac.release(); ctx->lut.release(); ctx->chr64.release(); ctx->chr32.release();
+	ctx->occ.release(); ctx->ktab.release(); ctx->ref64.release(); ctx->sa.release(); ctx->sa_full.release(); ctx->pac.release(); ctx->lut.release(); ctx->chr64.release(); ctx->chr32.release(); ctx->end_tab.release();
 	ctx->chunk_cigar.release(); ctx->chunk_cursor.release();
 	for (int k = 0; k < KB_SLOTS; k++)   // every handle may be null: kb_init calls this on its failure paths
 	{
@@ -725,6 +756,19 @@ int kb_upload_index(kb_ctx_t* ctx, const kb_index_host_t* h, int expand_sa)
 	CK(ctx->chr64.ensure(t64.size())); CK(ctx->chr32.ensure(t32.size()));
 	CK(cudaMemcpyAsync(ctx->chr64.p, t64.data(), t64.size() * 8, cudaMemcpyHostToDevice, stream));
 	CK(cudaMemcpyAsync(ctx->chr32.p, t32.data(), t32.size() * 4, cudaMemcpyHostToDevice, stream));
+	ix.end_tab = nullptr; ix.end_shift = 0;
+	if (ne <= 65535 && !(getenv("KB_CHR_TAB") && !atoi(getenv("KB_CHR_TAB"))))   // bucket table for kb_chr_lookup
+	{
+		int sh = 10; while (((u64)ix.G2 >> sh) + 2 > 8192) sh++;
+		const size_t nt = (size_t)((u64)ix.G2 >> sh) + 2;
+		std::vector<uint16_t> tab(nt);
+		int at = 0;
+		for (size_t b = 0; b < nt; b++) { const i64 start = (i64)b << sh; while (at < ne && key[at] < start) at++; tab[b] = (uint16_t)at; }
+		CK(ctx->end_tab.ensure(nt));
+		CK(cudaMemcpyAsync(ctx->end_tab.p, tab.data(), nt * sizeof(uint16_t), cudaMemcpyHostToDevice, stream));
+		CK(cudaStreamSynchronize(stream));   // tab is a local
+		ix.end_tab = ctx->end_tab.p; ix.end_shift = sh;
+	}
 	ix.n_chr = nc; ix.n_ends = ne; ix.end_key = ctx->chr64.p; ix.chr_fwd = ctx->chr64.p + ne; ix.chr_rev = ix.chr_fwd + nc; ix.chr_len = ix.chr_rev + nc; ix.end_chr = ctx->chr32.p;
 	// MAPQ table with the reference expression (src/Mapping.cpp:172), evaluated by the host libm exactly like the reference
 	const int lut_scores = 1 << 16;
@@ -880,35 +924,76 @@ static int alloc_batch(kb_ctx* ctx, kb_slot& sl, int shared)
 	return KB_OK;
 }
 
-// H2D of reads [first, first + count) of `in` into a slot (asynchronous on the slot's stream)
-static int stage_slot(kb_ctx* ctx, kb_slot& sl, const kb_reads_t* in, int first, int count, const int32_t* est)
+// the reads of a chunk as either entry point hands them over
+struct KbReadSrc { int n; const u8* seq; const u64* seq_off; const kb_reads_packed_t* pk; };
+static KbReadSrc read_src(const kb_reads_t* in) { KbReadSrc s; s.n = in->n_reads; s.seq = in->seq; s.seq_off = in->seq_off; s.pk = nullptr; return s; }
+static KbReadSrc read_src_packed(const kb_reads_packed_t* in) { KbReadSrc s; s.n = in->n_reads; s.seq = nullptr; s.seq_off = in->seq_off; s.pk = in; return s; }
+
+// H2D of reads [first, first + count) of the chunk into a slot (asynchronous on the slot's stream): the characters, or the packed
+// words and the exception entries of that range (k_unpack rebuilds the characters on the device)
+static int stage_slot(kb_ctx* ctx, kb_slot& sl, const KbReadSrc& in, int first, int count, const int32_t* est)
 {
 	size_t n = (size_t)count;
 	sl.n_reads = count; sl.first_read = first;
-	sl.seq_first = n ? in->seq_off[first] : 0;
-	sl.seq_bytes = n ? (size_t)(in->seq_off[first + n] - sl.seq_first) : 0;
-	int L = 0; for (size_t i = 0; i < n; i++) { u64 l = in->seq_off[first + i + 1] - in->seq_off[first + i]; if (l > 0x7FFFFFF0ull) return fail(ctx, KB_EINVAL, "read too long"); if ((int)l > L) L = (int)l; }
-	sl.max_rlen = L;
+	sl.seq_first = n ? in.seq_off[first] : 0;
+	sl.seq_bytes = n ? (size_t)(in.seq_off[first + n] - sl.seq_first) : 0;
+	int L = 0; for (size_t i = 0; i < n; i++) { u64 l = in.seq_off[first + i + 1] - in.seq_off[first + i]; if (l > (in.pk ? 0xFFFFFFull : 0x7FFFFFF0ull)) return fail(ctx, KB_EINVAL, "read too long"); if ((int)l > L) L = (int)l; }
+	sl.max_rlen = L; sl.packed = in.pk ? 1 : 0; sl.n_exc = 0;
 	CK(sl.seq.ensure(sl.seq_bytes + 64)); CK(sl.seq_off.ensure(n + 1)); CK(sl.est.ensure(n / 2 + 1));
 	if (n)
 	{
-		CK(cudaMemcpyAsync(sl.seq.p, in->seq + sl.seq_first, sl.seq_bytes, cudaMemcpyHostToDevice, sl.stream));
-		CK(cudaMemcpyAsync(sl.seq_off.p, in->seq_off + first, (n + 1) * 8, cudaMemcpyHostToDevice, sl.stream));
+		if (!in.pk) CK(cudaMemcpyAsync(sl.seq.p, in.seq + sl.seq_first, sl.seq_bytes, cudaMemcpyHostToDevice, sl.stream));
+		else
+		{
+			const u64 w0 = (sl.seq_first >> 5) + (u64)first, nw = (in.seq_off[first + n] >> 5) - (sl.seq_first >> 5) + n + 1;
+			if (w0 + nw > in.pk->n_words) return fail(ctx, KB_EINVAL, "packed reads: n_words is smaller than the layout needs");
+			CK(sl.codes.ensure(nw));
+			CK(cudaMemcpyAsync(sl.codes.p, in.pk->code + w0, nw * 8, cudaMemcpyHostToDevice, sl.stream));
+			const u64* e0 = std::lower_bound(in.pk->exc, in.pk->exc + in.pk->n_exc, (u64)first << 32);
+			const u64* e1 = std::lower_bound(e0, in.pk->exc + in.pk->n_exc, (u64)(first + n) << 32);
+			sl.n_exc = (u32)(e1 - e0);
+			if (sl.n_exc) { CK(sl.exc.ensure(sl.n_exc)); CK(cudaMemcpyAsync(sl.exc.p, e0, (size_t)sl.n_exc * 8, cudaMemcpyHostToDevice, sl.stream)); }
+		}
+		CK(cudaMemcpyAsync(sl.seq_off.p, in.seq_off + first, (n + 1) * 8, cudaMemcpyHostToDevice, sl.stream));
 		if (ctx->pm.paired) CK(cudaMemcpyAsync(sl.est.p, est + first / 2, (n / 2) * 4, cudaMemcpyHostToDevice, sl.stream));
 	}
 	return KB_OK;
 }
 
-int kb_stage_reads(kb_ctx_t* ctx, const kb_reads_t* in, const int32_t* est)
+static int stage_reads(kb_ctx* ctx, const KbReadSrc& in, const int32_t* est, const char* who)
 {
-	if (!ctx || !in || in->n_reads < 0 || (in->n_reads > 0 && (!in->seq || !in->seq_off))) return fail(ctx, KB_EINVAL, "kb_stage_reads: bad arguments");
+	if (in.n < 0 || (in.n > 0 && ((!in.seq && !in.pk) || !in.seq_off || (in.pk && (!in.pk->code || (in.pk->n_exc && !in.pk->exc)))))) return fail(ctx, KB_EINVAL, who);
 	if (!ctx->have_index) return fail(ctx, KB_ENOINDEX, "kb_stage_reads: no index");
-	if (ctx->pm.paired && ((in->n_reads & 1) || (in->n_reads > 0 && !est))) return fail(ctx, KB_EINVAL, "kb_stage_reads: paired chunks need an even read count and one EstDistance per pair");
+	if (ctx->pm.paired && ((in.n & 1) || (in.n > 0 && !est))) return fail(ctx, KB_EINVAL, "kb_stage_reads: paired chunks need an even read count and one EstDistance per pair");
 	CK(cudaSetDevice(ctx->device));
 	ctx->staged = false; ctx->ran = false; ctx->ran_pipelined = false;
-	int rc = stage_slot(ctx, ctx->slot[0], in, 0, in->n_reads, est); if (rc) return rc;
+	int rc = stage_slot(ctx, ctx->slot[0], in, 0, in.n, est); if (rc) return rc;
 	ctx->staged = true;
 	return KB_OK;
+}
+
+int kb_stage_reads(kb_ctx_t* ctx, const kb_reads_t* in, const int32_t* est)
+{
+	if (!ctx || !in) return fail(ctx, KB_EINVAL, "kb_stage_reads: bad arguments");
+	return stage_reads(ctx, read_src(in), est, "kb_stage_reads: bad arguments");
+}
+int kb_stage_reads_packed(kb_ctx_t* ctx, const kb_reads_packed_t* in, const int32_t* est)
+{
+	if (!ctx || !in) return fail(ctx, KB_EINVAL, "kb_stage_reads_packed: bad arguments");
+	return stage_reads(ctx, read_src_packed(in), est, "kb_stage_reads_packed: bad arguments");
+}
+
+// the slot's reads in both device forms: characters -> packed words (k_pack), or packed words (+ exceptions) -> characters (k_unpack)
+static void launch_pack(kb_slot& sl)
+{
+	KbBatchDev& bt = sl.bt; cudaStream_t s = sl.stream; const int n = sl.n_reads;
+	const unsigned g = (unsigned)(((long long)n * bt.pk_wpr + KB_BLOCK - 1) / KB_BLOCK);
+	if (sl.packed)
+	{
+		KB_LAUNCH(k_unpack, g, KB_BLOCK, s, bt, sl.codes.p, sl.seq.p); sl.launches++;
+		if (sl.n_exc) { KB_LAUNCH(k_unpack_exc, (unsigned)((sl.n_exc + KB_BLOCK - 1) / KB_BLOCK), KB_BLOCK, s, bt, sl.exc.p, sl.n_exc, (u32)sl.first_read, sl.seq.p); sl.launches++; }
+	}
+	else { KB_LAUNCH(k_pack, g, KB_BLOCK, s, bt); sl.launches++; }
 }
 
 // phase B of a slot's batch: 8-mer partition, the nw_alignment size classes, gather (kb_align.cuh "phase B")
@@ -954,7 +1039,7 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 	unsigned g_slow = g_reads < 148u * 16u ? g_reads : 148u * 16u;   // arena kernels: one thread per read up to a full machine, slices cut on the device
 	sl.launches = 0;
 	CK(cudaEventRecord(sl.ev[0], s));
-	KB_LAUNCH(k_pack, (unsigned)(((long long)n * bt.pk_wpr + KB_BLOCK - 1) / KB_BLOCK), KB_BLOCK, s, bt); sl.launches++;
+	launch_pack(sl);
 	if (ctx->seed_queue && ix.sa_full != nullptr)
 	{
 		// with the full SA most searches finish against the text and reads differ widely in work: lane queue (kb_seed_lane)
@@ -1147,15 +1232,15 @@ static int drain_pipeline(kb_ctx* ctx, int rc)
 }
 #define CKP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return drain_pipeline(ctx, fail(ctx, e_ == cudaErrorMemoryAllocation ? KB_ENOMEM : KB_ECUDA, #call, e_)); } while (0)
 
-static int map_chunk_pipelined(kb_ctx* ctx, const kb_reads_t* in, const int32_t* est, kb_results_t* out)
+static int map_chunk_pipelined(kb_ctx* ctx, const KbReadSrc& in, const int32_t* est, kb_results_t* out)
 {
-	const int n = in->n_reads;
+	const int n = in.n;
 	std::vector<int> p_first, p_count; pipeline_plan(ctx, n, p_first, p_count);
 	const int nsub = (int)p_first.size();
 	memset(ctx->stage_ms, 0, sizeof(ctx->stage_ms)); memset(ctx->work_host, 0, sizeof(ctx->work_host));
 	for (int attempt = 0; attempt < 6; attempt++)
 	{
-		size_t cap = (size_t)(ctx->cigar_factor * (double)n) + (ctx->pm.pacbio ? in->seq_off[n] / 2 : 0) + 65536;
+		size_t cap = (size_t)(ctx->cigar_factor * (double)n) + (ctx->pm.pacbio ? in.seq_off[n] / 2 : 0) + 65536;
 		if (cap > 0xF0000000ull) cap = 0xF0000000ull;
 		CK(cudaStreamSynchronize(ctx->copy_stream));   // copies of an abandoned attempt
 		CK(ctx->chunk_cigar.ensure(cap)); CK(ctx->chunk_cursor.ensure(4));
@@ -1207,18 +1292,63 @@ static int map_chunk_pipelined(kb_ctx* ctx, const kb_reads_t* in, const int32_t*
 	return fail(ctx, KB_EOVERFLOW, "kb_map_chunk: arenas still overflow after regrowth");
 }
 
-int kb_map_chunk(kb_ctx_t* ctx, const kb_reads_t* in, const int32_t* est, kb_results_t* out)
+static int map_chunk(kb_ctx* ctx, const KbReadSrc& in, const int32_t* est, kb_results_t* out, const char* who)
 {
-	if (ctx && in && out && ctx->have_index && !ctx->pm.multihit && in->n_reads >= ctx->pipe_min_reads && in->seq && in->seq_off && out->aln && out->cigar
-	    && !(ctx->pm.paired && ((in->n_reads & 1) || !est)))
+	if (ctx->have_index && !ctx->pm.multihit && in.n >= ctx->pipe_min_reads && (in.seq || (in.pk && in.pk->code && (!in.pk->n_exc || in.pk->exc))) && in.seq_off && out->aln && out->cigar
+	    && !(ctx->pm.paired && ((in.n & 1) || !est)))
 	{
 		CK(cudaSetDevice(ctx->device));
 		ctx->staged = false; ctx->ran = false;
 		return map_chunk_pipelined(ctx, in, est, out);
 	}
-	int rc = kb_stage_reads(ctx, in, est); if (rc) return rc;
+	int rc = stage_reads(ctx, in, est, who); if (rc) return rc;
 	rc = kb_run(ctx); if (rc) return rc;
 	return kb_fetch_results(ctx, out);
+}
+int kb_map_chunk(kb_ctx_t* ctx, const kb_reads_t* in, const int32_t* est, kb_results_t* out)
+{
+	if (!ctx || !in || !out) return fail(ctx, KB_EINVAL, "kb_map_chunk: bad arguments");
+	return map_chunk(ctx, read_src(in), est, out, "kb_map_chunk: bad arguments");
+}
+int kb_map_chunk_packed(kb_ctx_t* ctx, const kb_reads_packed_t* in, const int32_t* est, kb_results_t* out)
+{
+	if (!ctx || !in || !out) return fail(ctx, KB_EINVAL, "kb_map_chunk_packed: bad arguments");
+	return map_chunk(ctx, read_src_packed(in), est, out, "kb_map_chunk_packed: bad arguments");
+}
+
+uint64_t kb_packed_words(const kb_reads_t* in) { return (in && in->n_reads > 0 && in->seq_off) ? (in->seq_off[in->n_reads] >> 5) + (uint64_t)in->n_reads + 1 : 1; }
+int kb_pack_reads(const kb_reads_t* in, uint64_t* code, uint64_t* exc, uint64_t cap_exc, int threads, kb_reads_packed_t* out)
+{
+	if (!in || !out || in->n_reads < 0 || (in->n_reads > 0 && (!in->seq || !in->seq_off || !code))) return KB_EINVAL;
+	const int n = in->n_reads; const int T = threads < 1 ? 1 : (threads > 64 ? 64 : threads);
+	std::vector<std::vector<u64>> ex((size_t)T);
+	auto work = [&](int t) {
+		const int lo = (int)((long long)n * t / T), hi = (int)((long long)n * (t + 1) / T);
+		std::vector<u64>& e = ex[(size_t)t];
+		for (int r = lo; r < hi; r++)
+		{
+			const u64 off = in->seq_off[r]; const u64 len = in->seq_off[r + 1] - off; const u8* s = in->seq + off;
+			u64* w = code + (off >> 5) + (u64)r;
+			for (u64 b = 0; b < len; b += 32)
+			{
+				const int m = len - b < 32 ? (int)(len - b) : 32; u64 v = 0;
+				for (int i = 0; i < m; i++)
+				{
+					const u8 c = s[b + i]; const int k = kb_nt4(c);
+					v |= (u64)(k & 3) << (62 - 2 * i);
+					if (k > 3 || (c & 0x20)) e.push_back(((u64)(u32)r << 32) | ((b + (u64)i) << 8) | c);
+				}
+				w[b >> 5] = v;
+			}
+		}
+	};
+	if (T == 1) work(0);
+	else { std::vector<std::thread> th; for (int t = 1; t < T; t++) th.emplace_back(work, t); work(0); for (auto& x : th) x.join(); }
+	u64 total = 0; for (auto& e : ex) total += e.size();
+	out->n_reads = n; out->code = code; out->n_words = kb_packed_words(in); out->seq_off = in->seq_off; out->exc = exc; out->n_exc = total;
+	if (total > cap_exc || (total && !exc)) return KB_ECAPACITY;
+	u64 at = 0; for (auto& e : ex) { if (!e.empty()) memcpy(exc + at, e.data(), e.size() * 8); at += e.size(); }
+	return KB_OK;
 }
 
 int kb_stage_ms(kb_ctx_t* ctx, float* ms, int n) { if (!ctx || !ms) return KB_EINVAL; int k = n < 10 ? n : 10; for (int i = 0; i < k; i++) ms[i] = ctx->stage_ms[i]; return k; }
@@ -1277,7 +1407,7 @@ int kb_debug_align(kb_ctx_t* ctx, const kb_dbg_frag_t* specs, int n, kb_dbg_frag
 	CK(cudaMemcpyAsync(d_res.p, res.data(), (size_t)n * sizeof(kb_dbg_frag_out_t), cudaMemcpyHostToDevice, s));
 	CK(cudaMemsetAsync(sl.counters.p, 0, KB_NCOUNTERS * sizeof(u32), s)); CK(cudaMemsetAsync(sl.work.p, 0, 8 * sizeof(u64), s));
 	sl.launches = 0;
-	KB_LAUNCH(k_pack, (unsigned)(((long long)sl.n_reads * bt.pk_wpr + KB_BLOCK - 1) / KB_BLOCK), KB_BLOCK, s, bt);
+	launch_pack(sl);
 	KB_LAUNCH(k_debug_classify, (unsigned)((n + KB_BLOCK - 1) / KB_BLOCK), KB_BLOCK, s, ctx->ix, ctx->pm, bt, d_specs.p, n);
 	rc = launch_phase_b(ctx, sl);
 	if (rc == KB_OK)

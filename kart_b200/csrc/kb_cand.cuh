@@ -6,10 +6,20 @@
 #define KB_CAND_CUH
 #include "kb_fm.cuh"
 
-// ChrLocMap.lower_bound(pos): index of the first end key >= pos, or n_ends
+// ChrLocMap.lower_bound(pos): index of the first end key >= pos, or n_ends. The keys are few (two per sequence) but a binary
+// search over them is a chain of dependent global loads per call, and candidate construction, segment validation and
+// coordinate output each call it per candidate (ncu r17, C3: 22 % of k_cand_pair's and 16 % of k_segments' stall samples). A small
+// table of "first key at or behind the start of this 2^end_shift-base bucket" leaves a range of 0..2 keys for typical genomes.
 KB_HD int kb_chr_lookup(const KbIndexDev& ix, i64 pos)
 {
 	int lo = 0, hi = ix.n_ends;
+	if (ix.end_tab != nullptr)
+	{
+		if (pos <= 0) return 0;
+		if (pos >= ix.G2) return ix.n_ends;
+		const i64 b = pos >> ix.end_shift;
+		lo = (int)KB_LDG(ix.end_tab + b); hi = (int)KB_LDG(ix.end_tab + b + 1);
+	}
 	while (lo < hi) { int mid = (lo + hi) >> 1; if (ix.end_key[mid] < pos) lo = mid + 1; else hi = mid; }
 	return lo;
 }

@@ -60,6 +60,8 @@ struct KbIndexDev
 	i32 n_chr, n_ends;
 	const i64* end_key;      // ChrLocMap keys (last coordinate of each chromosome on each strand), ascending
 	const i32* end_chr;      // ChrLocMap values
+	const uint16_t* end_tab; // end_tab[b] = index of the first key >= b << end_shift (NULL: plain binary search); narrows kb_chr_lookup to a bucket
+	i32 end_shift;
 	const i64* chr_fwd;      // Chromosome_t::FowardLocation
 	const i64* chr_rev;      // Chromosome_t::ReverseLocation
 	const i64* chr_len;

@@ -269,3 +269,40 @@ def test_rescue_fast_path_and_fallback(mini, monkeypatch):
     assert pu.compare_pairs(m, orc, reads) == 0
     c = m.debug(9, np.uint32, 32)
     assert c[29] == c[27]
+
+
+def _same_results(a, b, paired=True):
+    (a0, p0, c0), (a1, p1, c1) = a, b
+    for f in ("pos", "mate_pos", "kind", "flag", "chr", "mapq", "score", "sub_score", "tlen", "fwd", "cig_len"):
+        assert np.array_equal(a0[f], a1[f]), f
+    assert not paired or np.array_equal(p0, p1)
+    for x, y in zip(a0, a1):
+        assert np.array_equal(c0[int(x["cig_off"]):int(x["cig_off"]) + int(x["cig_len"])], c1[int(y["cig_off"]):int(y["cig_off"]) + int(y["cig_len"])])
+
+
+def test_packed_entry_point(mini, monkeypatch):
+    """kb_map_chunk_packed (2-bit words + exception list over PCIe, characters rebuilt by k_unpack) == kb_map_chunk on the text,
+    including N, lower case and IUPAC characters and ragged lengths; single batch and through the slot pipeline; vs the oracle."""
+    idx, g = mini
+    r1, r2, _ = synth.simulate(g, 1500, 150, 0.05, seed=51, indel=0.004, n_rate=0.004)
+    reads = pu.interleave(r1, r2)
+    reads[3::17, 20] = ord("a"); reads[4::29, 100] = ord("R"); reads[7::31, 0] = ord("n"); reads[9::37, 149] = ord("t")
+    flat, off = Mapper.pack_reads(reads)
+    est = np.full(1500, 1500, dtype=np.int32)
+    m = pu.make_mapper(idx, emul=True, paired=True)
+    base = m.map_chunk(flat, off, est)
+    pk = m.pack(flat, off, threads=3)
+    assert pk[0].n_exc > 100
+    _same_results(base, m.map_chunk(flat, off, est, packed=pk))
+    monkeypatch.setenv("KART_TEST_PACKED", "1")
+    assert pu.compare_pairs(m, pu.Oracle(pu.MINI_PREFIX), reads) == 0
+    monkeypatch.delenv("KART_TEST_PACKED")
+    monkeypatch.setenv("KB_PIPE_MIN_READS", "500"); monkeypatch.setenv("KB_PIPE_SUB_READS", "700")
+    m2 = pu.make_mapper(idx, emul=True, paired=True)
+    _same_results(base, m2.map_chunk(flat, off, est, packed=pk))
+    assert m2.work()["launches"] > 3 * 19
+    # ragged single-end reads
+    rag = [b"ACGT", b"N" * 40, g[0][1000:1013].tobytes(), g[0][5000:5250].tobytes(), b"acgtn" * 20, g[0][70000:70031].tobytes().lower(), g[1][300:364].tobytes()]
+    m3 = pu.make_mapper(idx, emul=True, paired=False)
+    f3, o3 = Mapper.pack_reads(rag)
+    _same_results(m3.map_chunk(f3, o3), m3.map_chunk(f3, o3, packed=True), paired=False)

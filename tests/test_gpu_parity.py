@@ -133,6 +133,38 @@ def test_multi_contig_paired_with_rescue(built):
     assert m.work()["rescues"] > 0
 
 
+def test_packed_entry_point_gpu(eco, monkeypatch):
+    """kb_map_chunk_packed (2-bit words + exceptions in, k_unpack on the device) against kb_map_chunk on the text and against the
+    oracle: N / lower case / IUPAC characters, single batch and slot pipeline."""
+    idx, g, prefix = eco
+    r1, r2, _ = synth.simulate(g, 20000, 150, 0.03, seed=51, indel=0.004, n_rate=0.004)
+    reads = pu.interleave(r1, r2)
+    reads[3::17, 20] = ord("a"); reads[4::29, 100] = ord("R"); reads[7::31, 0] = ord("n"); reads[9::37, 149] = ord("t")
+    flat, off = Mapper.pack_reads(reads)
+    est = np.full(20000, 1500, dtype=np.int32)
+    m = pu.make_mapper(idx, expand_sa=True, paired=True)
+    a0, p0, c0 = m.map_chunk(flat, off, est)
+    pk = m.pack(flat, off)
+    assert pk[0].n_exc > 1000
+
+    def same(res):
+        a1, p1, c1 = res
+        for f in ("pos", "mate_pos", "kind", "flag", "chr", "mapq", "score", "sub_score", "tlen", "fwd", "cig_len"):
+            assert np.array_equal(a0[f], a1[f]), f
+        assert np.array_equal(p0, p1)
+        i0 = np.repeat(a0["cig_off"].astype(np.int64), a0["cig_len"]) + (np.arange(int(a0["cig_len"].sum())) - np.repeat(np.cumsum(a0["cig_len"]) - a0["cig_len"], a0["cig_len"]))
+        i1 = np.repeat(a1["cig_off"].astype(np.int64), a1["cig_len"]) + (np.arange(int(a1["cig_len"].sum())) - np.repeat(np.cumsum(a1["cig_len"]) - a1["cig_len"], a1["cig_len"]))
+        assert np.array_equal(c0[i0], c1[i1])
+    same(m.map_chunk(flat, off, est, packed=pk))
+    monkeypatch.setenv("KB_PIPE_MIN_READS", "1000"); monkeypatch.setenv("KB_PIPE_SUB_READS", "9000")
+    m2 = pu.make_mapper(idx, expand_sa=True, paired=True)
+    same(m2.map_chunk(flat, off, est, packed=pk))
+    assert m2.work()["launches"] > 3 * 19
+    monkeypatch.delenv("KB_PIPE_MIN_READS"); monkeypatch.delenv("KB_PIPE_SUB_READS")
+    monkeypatch.setenv("KART_TEST_PACKED", "1")
+    assert pu.compare_pairs(pu.make_mapper(idx, paired=True), pu.Oracle(prefix), reads[:8000]) == 0
+
+
 def test_rescue_fast_path_and_fallback(built, monkeypatch):
     """k_rescue_fast (warp per window, shared memory) takes the clean windows, k_rescue_win the rest; both against the oracle."""
     idx = KartIndex(pu.MINI_PREFIX)

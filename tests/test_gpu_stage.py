@@ -78,7 +78,7 @@ def test_pipelined_chunk_vs_oracle_full_size(built):
     reads = pu.interleave(r1, r2)
     flat, off = Mapper.pack_reads(reads)
     m = pu.make_mapper(idx, expand_sa=True, paired=True)
-    aln, pairs, cig = m.map_chunk(flat, off, np.full(140000, 1500, dtype=np.int32))
+    aln, pairs, cig = m.map_chunk(flat, off, np.full(140000, 1500, dtype=np.int32), packed=True)   # the packed entry point: what bench.py's e2e leg calls
     assert m.work()["launches"] > 2 * 19, "the chunk did not go through the slot pipeline"
     exp = _oracle_lines(pu.Oracle(pu.ECOLI_PREFIX), reads, 1500)
     assert len(exp) == len(aln)
