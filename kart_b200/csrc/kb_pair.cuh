@@ -155,9 +155,12 @@ KB_HD void kb_rj_pairs(const KbIndexDev& ix, KbRescueJob* j, int tid, int nth)
 #define KB_RF_SLOTS 512
 #define KB_RF_WORDS 66      // window words: 2048 positions + the word the last 8-mers reach into + 1
 #define KB_RF_PAIRS 24
+#define KB_RF_FILT 16384
+KB_HD u32 kb_rf_fold(u32 id) { return (id ^ (id >> 2)) & (u32)(KB_RF_FILT - 1); }
 struct KbRescueFast
 {
 	u32 hkey[KB_RF_SLOTS]; u32 hhead[KB_RF_SLOTS];
+	u32 filt[KB_RF_FILT / 32];   // one bit per 14-bit fold of an 8-mer id: set where the mate has such an 8-mer (99 % of window positions stop here)
 	u64 wcode[KB_RF_WORDS]; u64 mcode[10];
 	KbSeg pairs[KB_RF_PAIRS];
 	u8 hnext[256];
@@ -183,7 +186,7 @@ KB_HD void kb_rf_begin(const KbIndexDev& ix, const KbBatchDev& bt, KbRescueFast&
 KB_HD void kb_rf_load(const KbIndexDev& ix, const KbBatchDev& bt, KbRescueFast& w, int lane)
 {
 	if (!w.ok) return;
-	for (int s = lane; s < KB_RF_SLOTS; s += 32) { w.hkey[s] = 0; w.hhead[s] = 0xFFFFFFFFu; }
+	for (int s = lane; s < KB_RF_SLOTS; s += 32) { w.hkey[s] = 0; w.hhead[s] = 0xFFFFFFFFu; w.filt[s] = 0; }
 	const KbPk* rd = kb_pk_read(bt, w.mate_read);
 	const int mw = (w.ml + 31) >> 5;
 	for (int k = lane; k < 10; k += 32)
@@ -210,6 +213,8 @@ KB_HD void kb_rf_fill(KbRescueFast& w, int lane)
 			s = (s + 1u) & (u32)(KB_RF_SLOTS - 1);
 		}
 		w.hnext[r] = (u8)KB_ATOMIC_EXCH(&w.hhead[s], (u32)r);
+		const u32 h = kb_rf_fold(id);
+		KB_ATOMIC_OR(&w.filt[h >> 5], 1u << (h & 31));
 	}
 }
 // all lanes: the left-maximal exact matches of >= 10 bases (kb_rj_pairs on packed words)
@@ -218,9 +223,16 @@ KB_HD void kb_rf_pairs(KbRescueFast& w, int lane)
 	if (!w.ok || w.dirty) return;
 	const u64 M5 = 0x5555555555555555ull;
 	const int ml = w.ml, sl = w.slen, npos = sl - 7;
-	for (int g = lane; g < npos; g += 32)
+	// a lane takes a contiguous stretch of window positions: the 8-mer id rolls out of a 32-base register window that is
+	// refilled every 25 positions, and the filter turns nearly every position away after one shared-memory load
+	const int chunk = (npos + 31) >> 5, g0 = lane * chunk, g1 = g0 + chunk < npos ? g0 + chunk : npos;
+	u64 win = 0; int left_in_win = 0;
+	for (int g = g0; g < g1; g++)
 	{
-		const u32 id = (u32)(kb_rf_bits(w.wcode, g) >> 48);
+		if (left_in_win == 0) { win = kb_rf_bits(w.wcode, g); left_in_win = 25; }
+		const u32 id = (u32)(win >> 48); win <<= 2; left_in_win--;
+		const u32 h = kb_rf_fold(id);
+		if (((w.filt[h >> 5] >> (h & 31)) & 1u) == 0u) continue;
 		u32 s = kb_rj_slot(id, KB_RF_SLOTS - 1), key;
 		while ((key = w.hkey[s]) != 0u && key != id + 1u) s = (s + 1u) & (u32)(KB_RF_SLOTS - 1);
 		if (key == 0u) continue;
