@@ -114,6 +114,7 @@ typedef struct {
 	uint32_t n_cigar;            /* out: entries used (also set when KB_ECAPACITY is returned) */
 } kb_results_t;
 
+int  kb_device_count(void);                 /* visible CUDA devices (0 without a driver or a device) */
 int  kb_init(int device, kb_ctx_t** out);
 void kb_destroy(kb_ctx_t* ctx);
 const char* kb_strerror(int code);
@@ -124,6 +125,10 @@ const char* kb_last_error(kb_ctx_t* ctx);
  * untouched): locates become one load, and a search that is down to one row finishes by comparing the read with the text.
  * expand_sa = 2 does so when the device has the memory to spare (the full SA plus 48 GB for batches), 0 never. */
 int  kb_upload_index(kb_ctx_t* ctx, const kb_index_host_t* idx, int expand_sa);
+/* Gives `dst` (another device) the index `src` holds, device to device (NVLink between peers): no host copy, no table build,
+ * no SA expansion. The reference shares one read-only index between its worker threads (Refbwt / RefSequence, src/Mapping.cpp:716);
+ * on several GPUs every device needs its own replica. */
+int  kb_clone_index(kb_ctx_t* dst, kb_ctx_t* src);
 int  kb_set_params(kb_ctx_t* ctx, const kb_params_t* p);
 int  kb_get_min_seed_len(kb_ctx_t* ctx);
 

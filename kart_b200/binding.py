@@ -53,7 +53,7 @@ DBG_OUT_DTYPE = np.dtype([("info", "<i4"), ("aux", "<i4"), ("score", "<i4"), ("n
 RES_DTYPE = np.dtype([("score", "<i4"), ("sub", "<i4"), ("mapq", "<i4"), ("ncan", "<i4"), ("best", "<i4"), ("rep_off", "<u4")])
 CIGAR_OPS = "MIDNSHP=X"
 
-EXPORTS = ["kb_init", "kb_destroy", "kb_strerror", "kb_last_error", "kb_upload_index", "kb_set_params", "kb_get_min_seed_len",
+EXPORTS = ["kb_device_count", "kb_init", "kb_destroy", "kb_strerror", "kb_last_error", "kb_upload_index", "kb_clone_index", "kb_set_params", "kb_get_min_seed_len",
            "kb_map_chunk", "kb_map_chunk_packed", "kb_stage_reads", "kb_stage_reads_packed", "kb_packed_words", "kb_pack_reads", "kb_run", "kb_fetch_results", "kb_fetch_extra", "kb_stage_ms", "kb_work", "kb_cuda_stream", "kb_debug_fetch", "kb_debug_align", "kb_host_alloc", "kb_host_free", "kb_host_register", "kb_host_unregister"]
 
 
@@ -75,6 +75,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.kb_last_error.argtypes = [C.c_void_p]
     lib.kb_upload_index.argtypes = [C.c_void_p, C.POINTER(KbIndexHost), C.c_int]
     lib.kb_set_params.argtypes = [C.c_void_p, C.POINTER(KbParams)]
+    lib.kb_clone_index.argtypes = [C.c_void_p, C.c_void_p]
     lib.kb_get_min_seed_len.argtypes = [C.c_void_p]
     lib.kb_map_chunk.argtypes = [C.c_void_p, C.POINTER(KbReads), C.c_void_p, C.POINTER(KbResults)]
     lib.kb_stage_reads.argtypes = [C.c_void_p, C.POINTER(KbReads), C.c_void_p]
@@ -142,6 +143,12 @@ class Mapper:
         hi.chr_len = idx.chr_len_arr.ctypes.data
         self._check(self.lib.kb_upload_index(self.h, C.byref(hi), 1 if expand_sa else 0), "kb_upload_index")
         self.index = idx
+        self.set_params()
+
+    def clone_index_from(self, other: "Mapper"):
+        """kb_clone_index: this device's replica of the index `other` holds, copied device to device."""
+        self._check(self.lib.kb_clone_index(self.h, other.h), "kb_clone_index")
+        self.index = other.index
         self.set_params()
 
     def set_params(self, pacbio: bool = False, paired: bool = False, max_gaps: int = 5, multihit: bool = False, min_seed_len: int = 0):

@@ -249,7 +249,7 @@ static void k_rescue_fast(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulat
 {
 	if (blockIdx.x != 0 || threadIdx.x != 0) return;
 	if (bt.counters[3]) return;
-	static KbRescueFast w;
+	static thread_local KbRescueFast w;
 	const u32 count = bt.counters[27];
 	for (u32 q = 0; q < count; q++)
 	{
@@ -292,7 +292,7 @@ static void k_rescue_win(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulati
 	if (blockIdx.x != 0 || threadIdx.x != 0) return;
 	if (bt.counters[3]) return;
 	const u32 count = bt.counters[29]; const int nth = (int)blockDim.x;
-	static KbRescueJob job; KbRescueJob* j = &job; KbArena ar = kb_job_arena(bt, 0, blockDim.x);
+	static thread_local KbRescueJob job; KbRescueJob* j = &job; KbArena ar = kb_job_arena(bt, 0, blockDim.x);
 	for (u32 qi = 0; qi < count; qi++)
 	{
 		const u32 q = bt.rslow[qi];
@@ -420,7 +420,7 @@ static void k_align_part(KbIndexDev ix, KbParams pm, KbBatchDev bt, int)   // em
 {
 	if (blockIdx.x != 0 || threadIdx.x != 0) return;
 	if (bt.counters[3]) return;
-	static KbPartWarp w; static u8 pool[KB_ALIGN_POOL];
+	static thread_local KbPartWarp w; static thread_local u8 pool[KB_ALIGN_POOL];
 	w.ar.base = bt.wscratch; w.ar.cap = bt.wscratch_per_warp; w.fast.base = pool; w.fast.cap = KB_ALIGN_POOL; w.fast.ovf = false;
 	const u32 njobs = bt.counters[23];
 	for (u32 q = 0; q < njobs; q++)
@@ -443,7 +443,7 @@ static void k_nw_warp(KbIndexDev ix, KbParams pm, KbBatchDev bt)
 {
 	if (blockIdx.x != 0 || threadIdx.x != 0) return;
 	if (bt.counters[3]) return;
-	static KbPieceWarp w; KbNwLane L[32]; static u8 pool[KB_ALIGN_POOL];
+	static thread_local KbPieceWarp w; KbNwLane L[32]; static thread_local u8 pool[KB_ALIGN_POOL];
 	w.ar.base = bt.wscratch; w.ar.cap = bt.wscratch_per_warp; w.fast.base = pool; w.fast.cap = KB_ALIGN_POOL; w.fast.ovf = false; w.cells = 0; w.calls = 0;
 	for (int cls = 4; cls < KB_NW_CLASSES; cls++)
 	{
@@ -626,6 +626,8 @@ const char* kb_strerror(int code)
 }
 
 const char* kb_last_error(kb_ctx_t* ctx) { return ctx ? ctx->err.c_str() : ""; }
+
+int kb_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
 
 int kb_init(int device, kb_ctx_t** out)
 {
@@ -817,6 +819,47 @@ int kb_upload_index(kb_ctx_t* ctx, const kb_index_host_t* h, int expand_sa)
 	if (ctx->pm.min_seed <= 0) ctx->pm.min_seed = derive_min_seed(h->l_pac);
 	ctx->row32 = (h->seq_len + 2 < 0xFFFFFFFFull) && !(getenv("KB_ROW64") && atoi(getenv("KB_ROW64")));
 	ctx->have_index = true;
+	return KB_OK;
+}
+
+// A second device gets the index from the first one's HBM instead of over PCIe from the host: everything kb_upload_index built
+// (re-blocked Occ, seeding table, full SA, packed reference, tables) is copied device to device -- over NVLink when the two
+// devices are peers -- which also skips the table build and the SA expansion.
+int kb_clone_index(kb_ctx_t* dst, kb_ctx_t* src)
+{
+	kb_ctx* ctx = dst;
+	if (!dst || !src || dst == src) return fail(ctx, KB_EINVAL, "kb_clone_index: bad arguments");
+	if (!src->have_index) return fail(ctx, KB_ENOINDEX, "kb_clone_index: the source context has no index");
+	CK(cudaSetDevice(dst->device));
+#ifndef KB_EMUL
+	if (dst->device != src->device)
+	{
+		int can = 0; cudaDeviceCanAccessPeer(&can, dst->device, src->device);
+		if (can) { cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0); if (e != cudaSuccess) cudaGetLastError(); }   // already enabled is fine
+	}
+#endif
+	cudaStream_t stream = dst->slot[0].stream;
+	auto copy = [&](auto& d, const auto& sbuf) -> int {
+		if (sbuf.n == 0) return KB_OK;
+		CK(d.ensure(sbuf.n));
+#ifndef KB_EMUL
+		CK(cudaMemcpyPeerAsync(d.p, dst->device, sbuf.p, src->device, sbuf.n * sizeof(*sbuf.p), stream));
+#else
+		memcpy(d.p, sbuf.p, sbuf.n * sizeof(*sbuf.p));
+#endif
+		return KB_OK;
+	};
+	int rc;
+	if ((rc = copy(dst->occ, src->occ)) || (rc = copy(dst->sa, src->sa)) || (rc = copy(dst->sa_full, src->sa_full)) || (rc = copy(dst->ktab, src->ktab)) || (rc = copy(dst->ref64, src->ref64))
+	    || (rc = copy(dst->pac, src->pac)) || (rc = copy(dst->lut, src->lut)) || (rc = copy(dst->chr64, src->chr64)) || (rc = copy(dst->chr32, src->chr32)) || (rc = copy(dst->end_tab, src->end_tab))) return rc;
+	CK(cudaStreamSynchronize(stream));
+	KbIndexDev ix = src->ix;
+	ix.occ = dst->occ.p; ix.sa = dst->sa.p; ix.sa_full = src->ix.sa_full ? dst->sa_full.p : nullptr; ix.ktab = src->ix.ktab ? dst->ktab.p : nullptr;
+	ix.pac = dst->pac.p; ix.ref64 = dst->ref64.p; ix.mapq_lut = dst->lut.p; ix.end_tab = src->ix.end_tab ? dst->end_tab.p : nullptr;
+	const int nc = ix.n_chr, ne = ix.n_ends;
+	ix.end_key = dst->chr64.p; ix.chr_fwd = dst->chr64.p + ne; ix.chr_rev = ix.chr_fwd + nc; ix.chr_len = ix.chr_rev + nc; ix.end_chr = dst->chr32.p;
+	dst->ix = ix; dst->l_pac = src->l_pac; dst->row32 = src->row32; dst->have_index = true;
+	if (dst->pm.min_seed <= 0) dst->pm.min_seed = derive_min_seed(dst->l_pac);
 	return KB_OK;
 }
 

@@ -101,8 +101,8 @@ struct RunOptions
 {
 	std::string index_prefix, out_name = "output.sam";
 	std::vector<std::string> files1, files2;
-	int threads = 4, max_gaps = 5, out_format = 0, n_gpus = 1; bool pair_flag = false, pacbio = false, multihit = false, silent = false, debug = false;
-	int batch_reads = 1 << 18; int expand_sa = 2;   // 0 sampled SA, 1 full SA in HBM, 2 full SA when the device has room (kb_upload_index)
+	int threads = 4, max_gaps = 5, out_format = 0, n_gpus = 0 /* 0: all visible devices (--gpus N) */; bool pair_flag = false, pacbio = false, multihit = false, silent = false, debug = false;
+	int batch_reads = 1 << 20 /* large enough for kb_map_chunk's slot pipeline (>= 262 144 reads) to overlap copies and kernels */; int expand_sa = 2;   // 0 sampled SA, 1 full SA in HBM, 2 full SA when the device has room (kb_upload_index)
 };
 
 int run_mapping(const RunOptions& opt, const HostIndex& idx);     // Mapping(), src/Mapping.cpp:639

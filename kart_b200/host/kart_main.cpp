@@ -79,6 +79,7 @@ int main(int argc, char* argv[])
 		else if (p == "-d" || p == "-debug") o.debug = true;
 		else if (p == "-v" || p == "--version") { fprintf(stdout, "kart v%s\n\n", kVersion); exit(0); }
 		else if (p == "--batch" && i + 1 < argc) o.batch_reads = atoi(argv[++i]);        // kart_b200 extension: reads per GPU batch
+		else if (p == "--gpus" && i + 1 < argc) o.n_gpus = atoi(argv[++i]);              // kart_b200 extension: devices to use (default: all visible)
 		else if (p == "--full-sa") o.expand_sa = 1;                                      // kart_b200 extension: expand the SA in HBM (default: when it fits)
 		else if (p == "--sampled-sa") o.expand_sa = 0;                                   // kart_b200 extension: keep the .sa sampling on the device
 		else { fprintf(stdout, "Error! Unknown parameter: %s\n", argv[i]); usage(argv[0]); exit(1); }

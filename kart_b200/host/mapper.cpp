@@ -5,6 +5,13 @@
 // the interval of EstDistance values for which its result cannot change (kb_pair_stat_t::est_lo/est_hi), and this file
 // replays the per-chunk recurrence in input order, re-mapping only the pairs whose interval excludes the true value, until
 // the batch is self-consistent. The output is therefore identical to `kart -t 1`.
+//
+// Several GPUs (the reference's worker pool, pthread_create x iThreadNum over one chunk source, Mapping.cpp:716-717,504-512): one
+// host thread and one kb_ctx_t per device take batches from the same queue in input order. Mapping a batch needs nothing from the
+// other devices; the recurrence does, so a worker settles its batch only when every earlier batch has been settled (a turnstile
+// on the batch number) and hands it to the writer in that order. The first device gets the index from the host, the others copy
+// it from the first one's HBM (kb_clone_index: NVLink between peers). Devices beyond the first are only brought up when the
+// input is long enough to need them (a CUDA context costs most of a second).
 #include "kart_host.h"
 #include <algorithm>
 #include <atomic>
@@ -25,13 +32,22 @@ struct BatchResult
 };
 static bool g_multihit = false;
 
-static int map_batch(kb_ctx_t* ctx, const uint8_t* seq, const uint64_t* off, int n, const int32_t* est, BatchResult& out)
+// Packs the reads on the host threads (2 bits per base + the list of characters that are no upper-case bases) and maps them
+// through kb_map_chunk_packed: a third of the bytes of the text over PCIe. `pk` holds the page-locked staging of one worker.
+struct PackBuf { HBuf<uint64_t> code{true}; HBuf<uint64_t> exc{true}; };
+static int g_pack_threads = 4;
+static int map_batch(kb_ctx_t* ctx, const uint8_t* seq, const uint64_t* off, int n, const int32_t* est, BatchResult& out, PackBuf& pk)
 {
 	kb_reads_t in; in.n_reads = n; in.seq = seq; in.seq_off = off;
 	out.aln.resize(n); out.pairs.resize(n / 2 + 1);
 	if (out.cigar.cap < (size_t)n * 4 + 1024) { out.cigar.clear(); out.cigar.reserve((size_t)n * 4 + 1024); }
 	kb_results_t res; res.aln = out.aln.data(); res.pairs = out.pairs.data(); res.cigar = out.cigar.data(); res.cap_cigar = (uint32_t)out.cigar.cap; res.n_cigar = 0;
-	int rc = kb_map_chunk(ctx, &in, est, &res);
+	kb_reads_packed_t pr;
+	pk.code.resize((size_t)kb_packed_words(&in));
+	if (pk.exc.cap < 4096) pk.exc.reserve(4096);
+	int rc = kb_pack_reads(&in, pk.code.data(), pk.exc.data(), pk.exc.cap, g_pack_threads, &pr);
+	if (rc == KB_ECAPACITY) { pk.exc.clear(); pk.exc.reserve((size_t)pr.n_exc + 4096); rc = kb_pack_reads(&in, pk.code.data(), pk.exc.data(), pk.exc.cap, g_pack_threads, &pr); }
+	if (rc == KB_OK) rc = kb_map_chunk_packed(ctx, &pr, est, &res);
 	if (rc == KB_ECAPACITY)
 	{
 		out.cigar.clear(); out.cigar.reserve((size_t)res.n_cigar + 1024); res.cigar = out.cigar.data(); res.cap_cigar = (uint32_t)out.cigar.cap;
@@ -57,7 +73,7 @@ static inline int est_of(const PairState& s) { if (s.iPaired >= 1000) { int e = 
 
 // Replays the chunk recurrence over one mapped batch; re-maps the pairs whose result depends on the difference between the
 // predicted and the true EstDistance. Returns 0 or a kb error code.
-static int settle_est(kb_ctx_t* ctx, const ReadBatch& b, BatchResult& br, PairState& st, int chunk_reads, int n, long long* remapped)
+static int settle_est(kb_ctx_t* ctx, const ReadBatch& b, BatchResult& br, PairState& st, int chunk_reads, int n, long long* remapped, PackBuf& pk)
 {
 	while (true)
 	{
@@ -78,7 +94,7 @@ static int settle_est(kb_ctx_t* ctx, const ReadBatch& b, BatchResult& br, PairSt
 		std::vector<uint8_t> seq; std::vector<uint64_t> off(1, 0);
 		for (int p : viol) for (int r = 2 * p; r < 2 * p + 2; r++) { seq.insert(seq.end(), b.seq.data() + b.seq_off[r], b.seq.data() + b.seq_off[r + 1]); off.push_back(seq.size()); }
 		BatchResult fix;
-		int rc = map_batch(ctx, seq.data(), off.data(), (int)off.size() - 1, viol_est.data(), fix); if (rc) return rc;
+		int rc = map_batch(ctx, seq.data(), off.data(), (int)off.size() - 1, viol_est.data(), fix, pk); if (rc) return rc;
 		const uint32_t base = (uint32_t)br.cigar.size();   // the re-mapped pairs' cigar elements go behind the batch's, offsets shift by base
 		br.cigar.append(fix.cigar.data(), fix.cigar.size());
 		for (size_t k = 0; k < viol.size(); k++)
@@ -102,7 +118,7 @@ static int settle_est(kb_ctx_t* ctx, const ReadBatch& b, BatchResult& br, PairSt
 // One batch travelling through the three stages (reader thread -> GPU on the main thread -> writer thread).
 struct Job
 {
-	ReadBatch rb; BatchResult br, tail; int n_pe = 0; bool last_of_run = false;
+	ReadBatch rb; BatchResult br, tail; int n_pe = 0; bool last_of_run = false; long long seq_no = 0;
 };
 template <class T> class Channel   // small blocking queue
 {
@@ -143,10 +159,11 @@ int run_mapping(const RunOptions& opt, const HostIndex& idx)
 {
 	const int chunk_reads = opt.pacbio ? 10 : 4000;
 	const int io_threads = std::max(1, opt.threads);
-	const int batch_reads = std::max(chunk_reads, opt.batch_reads / chunk_reads * chunk_reads);
+	const int batch_reads = std::max(chunk_reads, std::min(opt.batch_reads, opt.pacbio ? (1 << 16) : (1 << 30)) / chunk_reads * chunk_reads);   // long reads: bound the bases per batch
 
 	// stage 1 starts before the device is ready: the first batch is parsed while the index is uploaded
-	const int n_jobs = 3;
+	const int n_dev_max = opt.n_gpus > 0 ? opt.n_gpus : std::max(1, kb_device_count());   // default: every visible device
+	const int n_jobs = 2 * n_dev_max + 2;
 	g_t0 = now_s();
 	std::vector<Job> jobs(n_jobs);
 	Channel<Job*> free_q, ready_q, done_q;
@@ -261,40 +278,97 @@ int run_mapping(const RunOptions& opt, const HostIndex& idx)
 		}
 	});
 
-	// stage 2: the GPU
-	kb_params_t pm; pm.min_seed_len = 0; pm.max_gaps = opt.max_gaps; pm.max_insert = 1500; pm.pacbio = opt.pacbio; pm.multihit = opt.multihit; pm.paired = 0;
-	bool pair_end_seen = opt.pair_flag; g_multihit = opt.multihit;
-	while (Job* j = ready_q.take())
+	// stage 2: the GPUs
+	g_multihit = opt.multihit; g_pack_threads = std::max(1, std::min(io_threads, 16));
+	bool pair_end_seen = opt.pair_flag;
+	std::mutex turn_m; std::condition_variable turn_cv; long long turn = 0;     // number of the batch that may settle next
+	std::atomic<int> err{0}; std::atomic<int> est_pred{1500};
+	Channel<Job*> work_q;
+	auto gpu_worker = [&](int dev, kb_ctx_t* wctx) {
+		PackBuf pk;
+		kb_params_t pm; pm.min_seed_len = 0; pm.max_gaps = opt.max_gaps; pm.max_insert = 1500; pm.pacbio = opt.pacbio; pm.multihit = opt.multihit; pm.paired = 0;
+		while (Job* j = work_q.take())
+		{
+			int wrc = err.load();
+			ReadBatch& cur = j->rb; const bool pair_end = cur.pair_end;
+			int n = cur.n(); double ta = now_s(), tb = ta;
+			// a batch with an odd number of reads can only be the last one of its library: the reference sends a whole chunk through the
+			// single-end branch when its read count is odd (Mapping.cpp:531,598), i.e. the final short chunk
+			int n_pe = (!opt.pacbio && pair_end) ? ((n & 1) ? (n / chunk_reads) * chunk_reads : n) : 0;
+			j->n_pe = n_pe;
+			if (!wrc)
+			{
+				cur.seq.pin_now(); cur.seq_off.pin_now();
+				if (n_pe > 0)
+				{
+					pm.paired = 1; kb_set_params(wctx, &pm);
+					j->br.est_used.assign(n_pe / 2, est_pred.load());
+					wrc = map_batch(wctx, cur.seq.data(), cur.seq_off.data(), n_pe, j->br.est_used.data(), j->br, pk);
+				}
+				if (!wrc && n > n_pe)
+				{
+					pm.paired = 0; kb_set_params(wctx, &pm);
+					std::vector<uint64_t> off(cur.seq_off.data() + n_pe, cur.seq_off.data() + n + 1);
+					uint64_t base = off[0]; for (auto& o : off) o -= base;
+					wrc = map_batch(wctx, cur.seq.data() + base, off.data(), n - n_pe, nullptr, j->tail, pk);
+				}
+				tb = now_s();
+			}
+			// the recurrence, the counters and the hand-over to the writer happen in batch order
+			{ std::unique_lock<std::mutex> g(turn_m); turn_cv.wait(g, [&]() { return turn == j->seq_no; }); }
+			if (!wrc && !err.load() && n_pe > 0)
+			{
+				pm.paired = 1; kb_set_params(wctx, &pm);
+				wrc = settle_est(wctx, cur, j->br, st, chunk_reads, n_pe, &remapped, pk);
+				est_pred.store(est_of(st));
+			}
+			if (wrc && !err.load())
+			{
+				err.store(wrc);
+				fprintf(stderr, "\nError! GPU mapping failed on device %d: %s (%s)\n", dev, kb_strerror(wrc), kb_last_error(wctx));
+			}
+			if (!err.load())
+			{
+				pair_end_seen = pair_end;
+				if (!opt.silent) { fprintf(stdout, "\r%lld %s reads have been processed in %ld seconds...", total, pair_end ? "paired-end" : "singled-end", (long)(time(NULL) - t0)); fflush(stdout); }
+				total += n;
+				if (g_trace) fprintf(stderr, "[kart trace] gpu%d   %8d reads  %.3f..%.3f s  settle ..%.3f s (remapped %lld)\n", dev, n, ta - g_t0, tb - g_t0, now_s() - g_t0, remapped);
+				done_q.put(j);
+			}
+			else free_q.put(j);
+			{ std::lock_guard<std::mutex> g(turn_m); turn++; }
+			turn_cv.notify_all();
+		}
+		work_q.put(nullptr);   // pass the end marker on to the next worker
+	};
+	std::vector<std::thread> extra_workers;
+	std::thread worker0(gpu_worker, 0, ctx);
 	{
-		if (rc) { free_q.put(j); continue; }      // after an error: let the reader run out
-		ReadBatch& cur = j->rb; const bool pair_end = cur.pair_end; pair_end_seen = pair_end;
-		if (!opt.silent) { fprintf(stdout, "\r%lld %s reads have been processed in %ld seconds...", total, pair_end ? "paired-end" : "singled-end", (long)(time(NULL) - t0)); fflush(stdout); }
-		cur.seq.pin_now(); cur.seq_off.pin_now();
-		int n = cur.n(); double ta = now_s(), tb = ta;
-		// a batch with an odd number of reads can only be the last one of its library: the reference sends a whole chunk through the
-		// single-end branch when its read count is odd (Mapping.cpp:531,598), i.e. the final short chunk
-		int n_pe = (!opt.pacbio && pair_end) ? ((n & 1) ? (n / chunk_reads) * chunk_reads : n) : 0;
-		j->n_pe = n_pe;
-		if (n_pe > 0)
+		// dispatcher: numbers the batches; a further device is brought up for every two batches beyond what the running ones took
+		long long seq_no = 0; int n_dev = 1, n_visible = 1;
+		if (n_dev_max > 1) n_visible = std::min(n_dev_max, kb_device_count());
+		while (Job* j = ready_q.take())
 		{
-			pm.paired = 1; kb_set_params(ctx, &pm);
-			j->br.est_used.assign(n_pe / 2, est_of(st));
-			rc = map_batch(ctx, cur.seq.data(), cur.seq_off.data(), n_pe, j->br.est_used.data(), j->br);
-			tb = now_s();
-			if (!rc) rc = settle_est(ctx, cur, j->br, st, chunk_reads, n_pe, &remapped);
+			j->seq_no = seq_no++;
+			work_q.put(j);
+			if (n_dev < n_visible && seq_no >= 2 * (long long)n_dev && !err.load())
+			{
+				const int dev = n_dev++;
+				extra_workers.emplace_back([&, dev]() {
+					kb_ctx_t* c2 = nullptr; double ta = now_s();
+					int r2 = kb_init(dev, &c2);
+					if (!r2) r2 = kb_clone_index(c2, ctx);
+					if (r2) { fprintf(stderr, "Warning! device %d is not used: %s (%s)\n", dev, kb_strerror(r2), c2 ? kb_last_error(c2) : ""); if (c2) kb_destroy(c2); return; }
+					if (g_trace) fprintf(stderr, "[kart trace] device %d up (context + index clone) %.3f..%.3f s\n", dev, ta - g_t0, now_s() - g_t0);
+					gpu_worker(dev, c2);
+				});
+			}
 		}
-		if (!rc && n > n_pe)
-		{
-			pm.paired = 0; kb_set_params(ctx, &pm);
-			std::vector<uint64_t> off(cur.seq_off.data() + n_pe, cur.seq_off.data() + n + 1);
-			uint64_t base = off[0]; for (auto& o : off) o -= base;
-			rc = map_batch(ctx, cur.seq.data() + base, off.data(), n - n_pe, nullptr, j->tail);
-		}
-		if (rc) { fprintf(stderr, "\nError! GPU mapping failed: %s (%s)\n", kb_strerror(rc), kb_last_error(ctx)); free_q.put(j); continue; }
-		total += n;
-		if (g_trace) fprintf(stderr, "[kart trace] gpu    %8d reads  %.3f..%.3f s  settle ..%.3f s (remapped %lld)\n", n, ta - g_t0, tb - g_t0, now_s() - g_t0, remapped);
-		done_q.put(j);
+		work_q.put(nullptr);
 	}
+	worker0.join();
+	for (auto& t : extra_workers) t.join();
+	rc = err.load();
 	reader.join();
 	done_q.put(nullptr); writer.join();
 	const bool pair_end = opt.files1.empty() ? pair_end_seen : pair_end_final;

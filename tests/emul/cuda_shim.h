@@ -20,7 +20,7 @@ struct kb_emul_event { std::chrono::steady_clock::time_point t; };
 typedef kb_emul_event* cudaEvent_t;
 enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2 };
 enum { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaStreamNonBlocking = 1 };
-static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceCount(int* n) { const char* e = getenv("KB_EMUL_DEVICES"); *n = e && atoi(e) > 0 ? atoi(e) : 1; return cudaSuccess; }   // KB_EMUL_DEVICES=N: the host's multi-device worker pool over N emulated devices
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }

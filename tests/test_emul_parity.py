@@ -306,3 +306,32 @@ def test_packed_entry_point(mini, monkeypatch):
     m3 = pu.make_mapper(idx, emul=True, paired=False)
     f3, o3 = Mapper.pack_reads(rag)
     _same_results(m3.map_chunk(f3, o3), m3.map_chunk(f3, o3, packed=True), paired=False)
+
+
+def test_cli_multi_device_worker_pool(kart_emul, mini, tmp_path):
+    """The host's device worker pool (one thread + context per device, batches settled in input order, index cloned from device 0)
+    over three emulated devices: 6 batches of 4000 reads, byte-identical to the oracle's `kart -t 1` replay whatever the interleaving,
+    and all three devices took part."""
+    import ctypes as C
+    idx, g = mini
+    f1, f2 = synth.make_reads(g, str(tmp_path / "md"), 11000, 150, 0.02, seed=71, indel=0.002)
+    out, exp = str(tmp_path / "md.sam"), str(tmp_path / "exp.sam")
+    o = pu.Oracle(pu.MINI_PREFIX)
+    o.lib.kor_map_files.restype = C.c_long
+    assert o.lib.kor_map_files(f1.encode(), f2.encode(), 1, exp.encode(), 4) == 22000
+    env = dict(os.environ, KB_EMUL_DEVICES="3", KART_B200_TRACE="1")
+    r = subprocess.run([kart_emul, "-silent", "-t", "2", "--gpus", "3", "-i", pu.MINI_PREFIX, "-f", f1, "-f2", f2, "-o", out, "--batch", "4000"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, env=env)
+    assert open(out, "rb").read() == open(exp, "rb").read()
+    assert "device 1 up" in r.stderr and "device 2 up" in r.stderr
+    assert len({ln.split()[2] for ln in r.stderr.splitlines() if ln.startswith("[kart trace] gpu")}) >= 2
+
+
+def test_clone_index(mini):
+    """kb_clone_index: a second context mapped from the first one's device arrays gives the same records"""
+    idx, g = mini
+    r1, r2, _ = synth.simulate(g, 400, 150, 0.03, seed=61)
+    m1 = pu.make_mapper(idx, emul=True, expand_sa=True, paired=True)
+    m2 = Mapper(lib_path=pu.EMUL_LIB)
+    m2.clone_index_from(m1)
+    m2.set_params(paired=True)
+    assert pu.compare_pairs(m2, pu.Oracle(pu.MINI_PREFIX), pu.interleave(r1, r2)) == 0

@@ -295,3 +295,41 @@ def test_c3_c4_shaped_on_100mbp_vs_oracle(built):
     r, _, _ = synth.simulate(g, 6000, 100, 0.08, seed=3, paired=False)
     m = pu.make_mapper(idx, paired=False)
     assert pu.compare_singles(m, orc, r) == 0
+
+
+def _n_gpus():
+    try:
+        import ctypes
+        from kart_b200.binding import load_library
+        return int(load_library().kb_device_count())
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(not (os.path.exists(pu.REF_KART) and pu.have_ecoli()), reason="needs oracle/_ref/kart and the E. coli index")
+def test_cli_multi_gpu_identical_to_reference_t1(built, tmp_path):
+    """The CLI's device worker pool on every visible GPU (batches of 40 000 reads, so that a box with 2+ GPUs brings them all up):
+    byte-identical to `kart -t 1` including the EstDistance recurrence across devices. With one GPU this is the single-device path."""
+    idx = KartIndex(pu.ECOLI_PREFIX)
+    g = pu.genome_of(idx)
+    f1, f2 = synth.make_reads(g, str(tmp_path / "r"), 160000, 150, 0.02, seed=3)
+    ours, ref = str(tmp_path / "ours.sam"), str(tmp_path / "ref.sam")
+    r = subprocess.run([KART, "-silent", "-t", "8", "-i", pu.ECOLI_PREFIX, "-f", f1, "-f2", f2, "-o", ours, "--batch", "40000"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True,
+                       env=dict(os.environ, KART_B200_TRACE="1"))
+    subprocess.run([pu.REF_KART, "-silent", "-t", "1", "-i", pu.ECOLI_PREFIX, "-f", f1, "-f2", f2, "-o", ref], check=True, stdout=subprocess.DEVNULL)
+    assert open(ours, "rb").read() == open(ref, "rb").read()
+    if _n_gpus() >= 2:
+        assert "device 1 up" in r.stderr
+    else:
+        print("one visible GPU: the multi-device pool ran with a single worker")
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="kb_clone_index between devices needs two GPUs (run with gpurun --gpus 2)")
+def test_clone_index_between_devices(eco):
+    idx, g, prefix = eco
+    r1, r2, _ = synth.simulate(g, 20000, 150, 0.02, seed=62)
+    m1 = pu.make_mapper(idx, expand_sa=True, paired=True)
+    m2 = Mapper(device=1)
+    m2.clone_index_from(m1)
+    m2.set_params(paired=True)
+    assert pu.compare_pairs(m2, pu.Oracle(prefix), pu.interleave(r1[:6000], r2[:6000])) == 0
