@@ -14,7 +14,11 @@
 
 struct HostIndex
 {
-	std::vector<uint32_t> bwt; std::vector<uint64_t> sa; std::vector<uint8_t> pac;
+	struct Mapping { uint8_t* p = nullptr; size_t n = 0; };
+	Mapping map_bwt, map_sa, map_pac;                              // private file mappings (index_load.cpp)
+	const uint32_t* bwt = nullptr; uint64_t bwt_words = 0; const uint64_t* sa = nullptr; uint64_t n_sa = 0; const uint8_t* pac = nullptr;
+	std::vector<uint8_t> pac_copy;                                 // only when the .pac file is shorter than l_pac / 4 + 1 bytes
+	HostIndex() = default; HostIndex(const HostIndex&) = delete; HostIndex& operator=(const HostIndex&) = delete; ~HostIndex();
 	std::vector<std::string> chr_name; std::vector<int64_t> chr_len;
 	uint64_t primary = 0, L2[5] = {0, 0, 0, 0, 0}, seq_len = 0; int sa_intv = 32; int64_t l_pac = 0;
 	bool load(const std::string& prefix, std::string& err);       // bwa_idx_load + RestoreReferenceInfo

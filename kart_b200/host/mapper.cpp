@@ -205,7 +205,19 @@ int run_mapping(const RunOptions& opt, const HostIndex& idx)
 	if (rc) { fprintf(stderr, "Error! kart_b200 needs a CUDA device: %s\n", kb_strerror(rc)); drain_reader(); return 1; }
 	host_cuda_ready();   // from here on the batch buffers are page-locked at allocation; the ones filled meanwhile are pinned in place below
 	kb_index_host_t hi; idx.describe(&hi);
-	if ((rc = kb_upload_index(ctx, &hi, opt.expand_sa)) != 0) { fprintf(stderr, "Error! index upload failed: %s (%s)\n", kb_strerror(rc), kb_last_error(ctx)); drain_reader(); kb_destroy(ctx); return 1; }
+	// The full SA in HBM (8 bytes per BWT row, expanded on the device from the .sa samples) makes seeding several times cheaper per
+	// read but costs seconds to expand on a multi-Gbp index (3.4 s at 3.1 Gbp) -- and this program is bound by parsing and SAM
+	// text, not by the kernels. So by default the samples are expanded when that is cheap (up to 2^30 rows: under a second) or
+	// when the input is long enough to pay for it; --full-sa / --sampled-sa decide explicitly.
+	int expand = opt.expand_sa;
+	if (expand == 2)
+	{
+		unsigned long long in_bytes = 0; struct stat fs;
+		for (const auto& f : opt.files1) if (stat(f.c_str(), &fs) == 0) in_bytes += (unsigned long long)fs.st_size * (f.size() > 3 && f.compare(f.size() - 3, 3, ".gz") == 0 ? 4 : 1);
+		for (const auto& f : opt.files2) if (stat(f.c_str(), &fs) == 0) in_bytes += (unsigned long long)fs.st_size * (f.size() > 3 && f.compare(f.size() - 3, 3, ".gz") == 0 ? 4 : 1);
+		expand = (hi.seq_len <= (1ull << 30) || in_bytes >= (64ull << 30)) ? 2 : 0;
+	}
+	if ((rc = kb_upload_index(ctx, &hi, expand)) != 0) { fprintf(stderr, "Error! index upload failed: %s (%s)\n", kb_strerror(rc), kb_last_error(ctx)); drain_reader(); kb_destroy(ctx); return 1; }
 
 	if (g_trace) fprintf(stderr, "[kart trace] index uploaded %.3f s\n", now_s() - g_t0);
 	SamSink out; BamWriter bam; const bool to_bam = opt.out_format == 1 && !opt.debug;

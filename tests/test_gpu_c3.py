@@ -52,3 +52,22 @@ def test_c5_pacbio_500_reads_vs_oracle(c3):
     m.set_params(pacbio=True, paired=False)
     assert pu.compare_singles(m, pu.Oracle(prefix, pacbio=True), r) == 0
     assert m.work()["nw_calls"] > 50000
+
+
+def test_c3_sampled_sa_kernels_vs_oracle(c3):
+    """The same index without the full SA in HBM (what the CLI uses for short inputs: k_fm_seed<.., u64> walking every base,
+    k_sa_locate through the .sa samples): C3 / C4 / C5 shapes against the oracle."""
+    prefix, idx, g, _ = c3
+    m = Mapper()
+    m.upload_index(idx, expand_sa=False)
+    r1, r2, _ = synth.simulate(g, 20000, 150, 0.01, seed=5)
+    m.set_params(paired=True)
+    assert pu.compare_pairs(m, pu.Oracle(prefix), pu.interleave(r1, r2)) == 0
+    assert m.work()["lf_steps"] > 0
+    r, _, _ = synth.simulate(g, 5000, 100, 0.08, seed=6, paired=False)
+    m.set_params(paired=False)
+    assert pu.compare_singles(m, pu.Oracle(prefix), r) == 0
+    r, _, _ = synth.simulate(g, 60, 7000, 0.15, seed=7, paired=False, indel=0.01)
+    m.set_params(pacbio=True, paired=False)
+    assert pu.compare_singles(m, pu.Oracle(prefix, pacbio=True), r) == 0
+    m.close()
