@@ -192,6 +192,17 @@ typedef struct { uint32_t read; int32_t rpos, rlen, glen, mode, pad; int64_t gpo
 typedef struct { int32_t info, aux, score, n_ops; uint32_t ops_off; int32_t nruns, ident, aligned; int64_t g_first, g_end; } kb_dbg_frag_out_t;
 int kb_debug_align(kb_ctx_t* ctx, const kb_dbg_frag_t* specs, int n, kb_dbg_frag_out_t* out, uint32_t* ops, uint32_t cap_ops);
 
+/* Index construction on the device (`kart index -gpu`): the contents of the .bwt and .sa files of the 2G text (forward strand +
+ * reverse complement) from the packed forward strand, i.e. the BWT / Occ / SA part of the reference's bwa_idx_build
+ * (src/BWT_Index/bwtindex.c:107-142: bwt_pac2bwt -> bwt_gen.c:1601, bwt_bwtupdate_core :53-75, bwt_cal_sa bwt.c:101-123); byte-identical
+ * output. pac: l_pac/4 + 1 bytes, 2 bit per base, MSB first (ambiguous bases already replaced, bntseq.c:144).
+ * out->bwt: the .bwt payload behind its 40-byte header (bwt_words 32-bit words); out->sa: the n_sa - 1 samples sa[1..] (the .sa payload
+ * behind its 56-byte header). Both are page-locked host arrays owned by the library until kb_index_free(). */
+typedef struct { uint64_t primary; uint64_t L2[5]; uint64_t seq_len; uint32_t* bwt; uint64_t bwt_words; uint64_t* sa; uint64_t n_sa; } kb_built_index_t;
+int  kb_index_build(int device, const uint8_t* pac, int64_t l_pac, kb_built_index_t* out);
+void kb_index_free(kb_built_index_t* b);
+const char* kb_index_build_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,7 +54,8 @@ RES_DTYPE = np.dtype([("score", "<i4"), ("sub", "<i4"), ("mapq", "<i4"), ("ncan"
 CIGAR_OPS = "MIDNSHP=X"
 
 EXPORTS = ["kb_device_count", "kb_init", "kb_destroy", "kb_strerror", "kb_last_error", "kb_upload_index", "kb_clone_index", "kb_set_params", "kb_get_min_seed_len",
-           "kb_map_chunk", "kb_map_chunk_packed", "kb_stage_reads", "kb_stage_reads_packed", "kb_packed_words", "kb_pack_reads", "kb_run", "kb_fetch_results", "kb_fetch_extra", "kb_stage_ms", "kb_work", "kb_cuda_stream", "kb_debug_fetch", "kb_debug_align", "kb_host_alloc", "kb_host_free", "kb_host_register", "kb_host_unregister"]
+           "kb_map_chunk", "kb_map_chunk_packed", "kb_stage_reads", "kb_stage_reads_packed", "kb_packed_words", "kb_pack_reads", "kb_run", "kb_fetch_results", "kb_fetch_extra", "kb_stage_ms", "kb_work", "kb_cuda_stream", "kb_debug_fetch", "kb_debug_align", "kb_host_alloc", "kb_host_free", "kb_host_register", "kb_host_unregister",
+           "kb_index_build", "kb_index_free", "kb_index_build_error"]
 
 
 class KartB200Error(RuntimeError):

@@ -1365,6 +1365,8 @@ int kb_pack_reads(const kb_reads_t* in, uint64_t* code, uint64_t* exc, uint64_t 
 	if (!in || !out || in->n_reads < 0 || (in->n_reads > 0 && (!in->seq || !in->seq_off || !code))) return KB_EINVAL;
 	const int n = in->n_reads; const int T = threads < 1 ? 1 : (threads > 64 ? 64 : threads);
 	std::vector<std::vector<u64>> ex((size_t)T);
+	u8 lut[256];   // nt4 code in the low two bits (0 for no base), bit 2 = "not one of the upper-case letters ACGT"
+	for (int c = 0; c < 256; c++) { const int k = kb_nt4((u8)c); lut[c] = (u8)((k & 3) | ((k > 3 || (c & 0x20)) ? 4 : 0)); if (k > 3) lut[c] = 4; }
 	auto work = [&](int t) {
 		const int lo = (int)((long long)n * t / T), hi = (int)((long long)n * (t + 1) / T);
 		std::vector<u64>& e = ex[(size_t)t];
@@ -1374,14 +1376,11 @@ int kb_pack_reads(const kb_reads_t* in, uint64_t* code, uint64_t* exc, uint64_t 
 			u64* w = code + (off >> 5) + (u64)r;
 			for (u64 b = 0; b < len; b += 32)
 			{
-				const int m = len - b < 32 ? (int)(len - b) : 32; u64 v = 0;
-				for (int i = 0; i < m; i++)
-				{
-					const u8 c = s[b + i]; const int k = kb_nt4(c);
-					v |= (u64)(k & 3) << (62 - 2 * i);
-					if (k > 3 || (c & 0x20)) e.push_back(((u64)(u32)r << 32) | ((b + (u64)i) << 8) | c);
-				}
+				// table-driven and branch-free over the 32 characters; a word that holds anything but upper-case bases is walked again for the list
+				const int m = len - b < 32 ? (int)(len - b) : 32; u64 v = 0; unsigned odd = 0;
+				for (int i = 0; i < m; i++) { const unsigned q = lut[s[b + i]]; v |= (u64)(q & 3u) << (62 - 2 * i); odd |= q; }
 				w[b >> 5] = v;
+				if (odd & 4u) for (int i = 0; i < m; i++) { const u8 c = s[b + i]; if (lut[c] & 4u) e.push_back(((u64)(u32)r << 32) | ((b + (u64)i) << 8) | c); }
 			}
 		}
 	};
@@ -1471,5 +1470,11 @@ int kb_debug_align(kb_ctx_t* ctx, const kb_dbg_frag_t* specs, int n, kb_dbg_frag
 	ctx->ran = true; ctx->ran_pipelined = false;   // kb_debug_fetch may read the arenas (counters, jobs, ...) of this run
 	return KB_OK;
 }
+
+#ifdef KB_EMUL   // the device index builder (kb_index_build.cu) has no host emulation: the emulated library reports that there is no device
+int kb_index_build(int, const uint8_t*, int64_t, kb_built_index_t* out) { if (out) memset(out, 0, sizeof(*out)); return KB_ENODEV; }
+void kb_index_free(kb_built_index_t*) {}
+const char* kb_index_build_error(void) { return "no CUDA device (emulation build)"; }
+#endif
 
 } // extern "C"

@@ -223,14 +223,13 @@ KB_HD void kb_rf_pairs(KbRescueFast& w, int lane)
 	if (!w.ok || w.dirty) return;
 	const u64 M5 = 0x5555555555555555ull;
 	const int ml = w.ml, sl = w.slen, npos = sl - 7;
-	// a lane takes a contiguous stretch of window positions: the 8-mer id rolls out of a 32-base register window that is
-	// refilled every 25 positions, and the filter turns nearly every position away after one shared-memory load
-	const int chunk = (npos + 31) >> 5, g0 = lane * chunk, g1 = g0 + chunk < npos ? g0 + chunk : npos;
-	u64 win = 0; int left_in_win = 0;
-	for (int g = g0; g < g1; g++)
+	// Positions are dealt to the lanes round-robin, not in stretches: where the window does hold a copy of the mate (or of the
+	// repeat element the mate comes from) ~150 consecutive positions pass the filter, and almost all of them only to find that
+	// they continue a run; in stretches three or four lanes would do that one after the other while the rest idle (ncu r19:
+	// 30 % of the kernel at 2-4 lanes). The filter turns every other position away after one shared-memory load.
+	for (int g = lane; g < npos; g += 32)
 	{
-		if (left_in_win == 0) { win = kb_rf_bits(w.wcode, g); left_in_win = 25; }
-		const u32 id = (u32)(win >> 48); win <<= 2; left_in_win--;
+		const u32 id = (u32)(kb_rf_bits(w.wcode, g) >> 48);
 		const u32 h = kb_rf_fold(id);
 		if (((w.filt[h >> 5] >> (h & 31)) & 1u) == 0u) continue;
 		u32 s = kb_rj_slot(id, KB_RF_SLOTS - 1), key;

@@ -132,6 +132,8 @@ struct PackedText
 
 }   // namespace
 
+static int write_pac_ann_amb(const std::string& prefix, const std::vector<uint8_t>& fwd, const std::vector<Ann>& anns, const std::vector<Amb>& ambs, std::vector<uint8_t>* pac_out);
+
 template <class IDX>
 static int build_core(const std::string& prefix, const std::vector<uint8_t>& fwd, const std::vector<Ann>& anns, const std::vector<Amb>& ambs, int threads)
 {
@@ -216,27 +218,7 @@ static int build_core(const std::string& prefix, const std::vector<uint8_t>& fwd
 	fprintf(stdout, "%.2f sec\n", (float)(clock() - t0) / CLOCKS_PER_SEC);
 	// ---- forward-only .pac, .ann, .amb (second bns_fasta2bntseq pass, for_only = 1) ----
 	fprintf(stdout, "[bwt_index] Pack forward-only FASTA... "); fflush(stdout); t0 = clock();
-	{
-		std::vector<uint8_t> pac((size_t)(L >> 2) + ((L & 3) ? 1 : 0), 0);
-		for (uint64_t i = 0; i < L; i++) pac[i >> 2] |= (uint8_t)(fwd[i] << ((~i & 3) << 1));
-		FILE* fp = fopen((prefix + ".pac").c_str(), "wb"); if (!fp) { fprintf(stdout, "\nError! cannot write %s.pac\n", prefix.c_str()); return 1; }
-		write_or_die(fp, pac.data(), pac.size());
-		uint8_t ct = 0; if (L % 4 == 0) write_or_die(fp, &ct, 1);
-		ct = (uint8_t)(L % 4); write_or_die(fp, &ct, 1); fclose(fp);
-		fp = fopen((prefix + ".ann").c_str(), "w"); if (!fp) return 1;
-		fprintf(fp, "%lld %d %u\n", (long long)L, (int)anns.size(), 11u);
-		for (const Ann& a : anns)
-		{
-			fprintf(fp, "%d %s", 0, a.name.c_str());
-			if (!a.anno.empty()) fprintf(fp, " %s\n", a.anno.c_str()); else fprintf(fp, "\n");
-			fprintf(fp, "%lld %d %d\n", a.offset, a.len, a.n_ambs);
-		}
-		fclose(fp);
-		fp = fopen((prefix + ".amb").c_str(), "w"); if (!fp) return 1;
-		fprintf(fp, "%lld %d %u\n", (long long)L, (int)anns.size(), (unsigned)ambs.size());
-		for (const Amb& h : ambs) fprintf(fp, "%lld %d %c\n", h.offset, h.len, h.amb);
-		fclose(fp);
-	}
+	if (write_pac_ann_amb(prefix, fwd, anns, ambs, nullptr)) return 1;
 	fprintf(stdout, "%.2f sec\n", (float)(clock() - t0) / CLOCKS_PER_SEC);
 	// ---- .sa: every 32nd row of the (N+1)-row matrix (bwt_cal_sa; sa[0] is not stored) ----
 	fprintf(stdout, "[bwt_index] Construct SA from BWT and Occ... "); fflush(stdout); t0 = clock();
@@ -250,6 +232,84 @@ static int build_core(const std::string& prefix, const std::vector<uint8_t>& fwd
 	}
 	fprintf(stdout, "%.2f sec\n", (float)(clock() - t0) / CLOCKS_PER_SEC);
 	return 0;
+}
+
+// .pac / .ann / .amb (second bns_fasta2bntseq pass, for_only = 1) -- shared by the host and the device builder
+static int write_pac_ann_amb(const std::string& prefix, const std::vector<uint8_t>& fwd, const std::vector<Ann>& anns, const std::vector<Amb>& ambs, std::vector<uint8_t>* pac_out)
+{
+	const uint64_t L = fwd.size();
+	std::vector<uint8_t> pac((size_t)(L >> 2) + ((L & 3) ? 1 : 0) + 1, 0);
+	for (uint64_t i = 0; i < L; i++) pac[i >> 2] |= (uint8_t)(fwd[i] << ((~i & 3) << 1));
+	FILE* fp = fopen((prefix + ".pac").c_str(), "wb"); if (!fp) { fprintf(stdout, "\nError! cannot write %s.pac\n", prefix.c_str()); return 1; }
+	write_or_die(fp, pac.data(), (size_t)(L >> 2) + ((L & 3) ? 1 : 0));
+	uint8_t ct = 0; if (L % 4 == 0) write_or_die(fp, &ct, 1);
+	ct = (uint8_t)(L % 4); write_or_die(fp, &ct, 1); fclose(fp);
+	fp = fopen((prefix + ".ann").c_str(), "w"); if (!fp) return 1;
+	fprintf(fp, "%lld %d %u\n", (long long)L, (int)anns.size(), 11u);
+	for (const Ann& a : anns)
+	{
+		fprintf(fp, "%d %s", 0, a.name.c_str());
+		if (!a.anno.empty()) fprintf(fp, " %s\n", a.anno.c_str()); else fprintf(fp, "\n");
+		fprintf(fp, "%lld %d %d\n", a.offset, a.len, a.n_ambs);
+	}
+	fclose(fp);
+	fp = fopen((prefix + ".amb").c_str(), "w"); if (!fp) return 1;
+	fprintf(fp, "%lld %d %u\n", (long long)L, (int)anns.size(), (unsigned)ambs.size());
+	for (const Amb& h : ambs) fprintf(fp, "%lld %d %c\n", h.offset, h.len, h.amb);
+	fclose(fp);
+	if (pac_out) pac_out->swap(pac);
+	return 0;
+}
+
+// .bwt and .sa from what the device built (kb_index_build): the same headers as bwt_dump_bwt / bwt_dump_sa (bwt.c:174-196)
+static int write_bwt_sa(const std::string& prefix, const kb_built_index_t& b)
+{
+	FILE* fp = fopen((prefix + ".bwt").c_str(), "wb"); if (!fp) { fprintf(stdout, "\nError! cannot write %s.bwt\n", prefix.c_str()); return 1; }
+	write_or_die(fp, &b.primary, 8); write_or_die(fp, b.L2 + 1, 32); write_or_die(fp, b.bwt, (size_t)b.bwt_words * 4); fclose(fp);
+	const uint64_t intv = 32;
+	fp = fopen((prefix + ".sa").c_str(), "wb"); if (!fp) { fprintf(stdout, "\nError! cannot write %s.sa\n", prefix.c_str()); return 1; }
+	write_or_die(fp, &b.primary, 8); write_or_die(fp, b.L2 + 1, 32); write_or_die(fp, &intv, 8); write_or_die(fp, &b.seq_len, 8);
+	write_or_die(fp, b.sa, (size_t)(b.n_sa - 1) * 8); fclose(fp);
+	return 0;
+}
+
+// `kart index -gpu ref.fa prefix`: the text is packed on the host, the suffix array, BWT, Occ counts and SA samples are built on the
+// device (csrc/kb_index_build.cu). `kart index -gpu -pac prefix`: the same from an existing prefix.pac / prefix.ann (l_pac is the
+// first number of the .ann file), e.g. a genome that was never a FASTA file.
+int build_index_gpu(const char* fa, const char* prefix_c, bool from_pac)
+{
+	const std::string prefix = prefix_c;
+	std::vector<uint8_t> pac; long long L = 0;
+	time_t w0 = time(NULL);
+	if (from_pac)
+	{
+		FILE* fp = fopen((prefix + ".ann").c_str(), "r"); if (!fp) { fprintf(stdout, "Error! cannot open %s.ann\n", prefix.c_str()); return 1; }
+		if (fscanf(fp, "%lld", &L) != 1 || L <= 0) { fclose(fp); fprintf(stdout, "Error! bad %s.ann\n", prefix.c_str()); return 1; }
+		fclose(fp);
+		fp = fopen((prefix + ".pac").c_str(), "rb"); if (!fp) { fprintf(stdout, "Error! cannot open %s.pac\n", prefix.c_str()); return 1; }
+		pac.assign((size_t)(L / 4 + 1), 0);
+		size_t got = fread(pac.data(), 1, pac.size(), fp); fclose(fp);
+		if (got < (size_t)((L + 3) / 4)) { fprintf(stdout, "Error! %s.pac is too short\n", prefix.c_str()); return 1; }
+		if (L % 4 == 0) pac[(size_t)(L / 4)] = 0;   // the byte behind the bases is the file's own trailer
+	}
+	else
+	{
+		fprintf(stdout, "[bwt_index] Pack FASTA... "); fflush(stdout);
+		std::vector<uint8_t> fwd; std::vector<Ann> anns; std::vector<Amb> ambs;
+		if (!read_reference(fa, fwd, anns, ambs)) { fprintf(stdout, "\nError! cannot open %s\n", fa); return 1; }
+		if (fwd.empty()) { fprintf(stdout, "Error! %s holds no sequence\n", fa); return 1; }
+		L = (long long)fwd.size();
+		if (write_pac_ann_amb(prefix, fwd, anns, ambs, &pac)) return 1;
+		fprintf(stdout, "%.2f sec\n", (float)difftime(time(NULL), w0));
+	}
+	fprintf(stdout, "[bwt_index] Construct BWT, Occ and SA on the GPU...\n"); fflush(stdout);
+	kb_built_index_t b;
+	int rc = kb_index_build(0, pac.data(), L, &b);
+	if (rc) { fprintf(stdout, "Error! GPU index construction failed: %s (%s)\n", kb_strerror(rc), kb_index_build_error()); return 1; }
+	rc = write_bwt_sa(prefix, b);
+	kb_index_free(&b);
+	fprintf(stdout, "[bwt_index] %.2f seconds elapse.\n", (float)difftime(time(NULL), w0));
+	return rc;
 }
 
 int build_index(const char* fa, const char* prefix_c, int threads)

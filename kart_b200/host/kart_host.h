@@ -14,8 +14,8 @@
 
 struct HostIndex
 {
-	struct Mapping { uint8_t* p = nullptr; size_t n = 0; };
-	Mapping map_bwt, map_sa, map_pac;                              // private file mappings (index_load.cpp)
+	struct Mapping { uint8_t* p = nullptr; size_t n = 0, cap = 0; };
+	Mapping map_bwt, map_sa, map_pac;                              // the files' bytes in huge-page backed memory (index_load.cpp)
 	const uint32_t* bwt = nullptr; uint64_t bwt_words = 0; const uint64_t* sa = nullptr; uint64_t n_sa = 0; const uint8_t* pac = nullptr;
 	std::vector<uint8_t> pac_copy;                                 // only when the .pac file is shorter than l_pac / 4 + 1 bytes
 	HostIndex() = default; HostIndex(const HostIndex&) = delete; HostIndex& operator=(const HostIndex&) = delete; ~HostIndex();
@@ -24,7 +24,8 @@ struct HostIndex
 	bool load(const std::string& prefix, std::string& err);       // bwa_idx_load + RestoreReferenceInfo
 	void describe(kb_index_host_t* out) const;
 };
-int build_index(const char* fasta, const char* prefix, int threads);   // `kart index`: BWA-format files, byte-identical to the reference builder's (index_build.cpp)
+int build_index(const char* fasta, const char* prefix, int threads);
+int build_index_gpu(const char* fasta, const char* prefix, bool from_pac);   // `kart index -gpu [-pac]`: BWT / Occ / SA built on the device (csrc/kb_index_build.cu), same bytes   // `kart index`: BWA-format files, byte-identical to the reference builder's (index_build.cpp)
 bool check_index_files(const std::string& prefix);                // CheckBWAIndexFiles, GetData.cpp:222
 
 // Grow-only host array without value-initialisation. `pinned` arrays come from kb_host_alloc (page-locked, so the copies of

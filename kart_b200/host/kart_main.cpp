@@ -58,8 +58,10 @@ int main(int argc, char* argv[])
 	if (strcmp(argv[1], "update") == 0) { fprintf(stderr, "kart_b200: `update` is not supported\n"); return 0; }
 	if (strcmp(argv[1], "index") == 0)   // main.cpp:112-120
 	{
-		if (argc == 4) build_index(argv[2], argv[3], (int)std::max(1u, std::thread::hardware_concurrency()));
-		else fprintf(stderr, "usage: %s index ref.fa prefix\n", argv[0]);
+		if (argc == 4) return build_index(argv[2], argv[3], (int)std::max(1u, std::thread::hardware_concurrency()));
+		if (argc == 5 && strcmp(argv[2], "-gpu") == 0 && strcmp(argv[3], "-pac") == 0) return build_index_gpu(nullptr, argv[4], true);
+		if (argc == 5 && strcmp(argv[2], "-gpu") == 0) return build_index_gpu(argv[3], argv[4], false);
+		fprintf(stderr, "usage: %s index ref.fa prefix\n       %s index -gpu ref.fa prefix    (BWT, Occ and SA built on the GPU; same files)\n       %s index -gpu -pac prefix      (the same from an existing prefix.pac + prefix.ann)\n", argv[0], argv[0], argv[0]);
 		return 0;
 	}
 	for (int i = 1; i < argc; i++)
