@@ -366,15 +366,37 @@ def main():
     t0 = time.perf_counter()
     pk = m.pack(flat, off, code=code_pin.numpy().view(np.uint64), threads=min(ncores, 16))
     pack_ms = (time.perf_counter() - t0) * 1e3
-    for _ in range(max(1, args.warmup // 2)):
-        aln, pairs, cig = m.map_chunk(flat, off, est, out=out_bufs, packed=pk)
+    # (a) chunks in flight (kb_map_chunk_begin_packed / kb_map_chunk_end): what a mapper streaming a read file does -- chunk k+1 is
+    # handed over while chunk k is being mapped, so its H2D copy and chunk k-1's D2H copy run under chunk k's kernels. Every step still
+    # copies its reads in from pinned memory and its records out; the timed region holds all K steps' copies.
+    aln_pin2 = torch.empty(n * ALN_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    pair_pin2 = torch.empty((n // 2) * PAIR_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    cig_pin2 = torch.empty(4 * n + 1024, dtype=torch.int32).pin_memory()
+    outs = [out_bufs, (aln_pin2.numpy().view(ALN_DTYPE), pair_pin2.numpy().view(PAIR_DTYPE), cig_pin2.numpy().view(np.uint32))]
+
+    def in_flight(steps):
+        h = m.map_chunk_begin(flat, off, est, out=outs[0], packed=pk)
+        for k in range(1, steps):
+            h2 = m.map_chunk_begin(flat, off, est, out=outs[k & 1], packed=pk)
+            res_ = m.map_chunk_end(h)
+            h = h2
+        return m.map_chunk_end(h)
+    in_flight(max(2, args.warmup))
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        aln, pairs, cig = m.map_chunk(flat, off, est, out=out_bufs, packed=pk)
+    aln, pairs, cig = in_flight(args.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
     aln_packed = aln.copy()
+    # (b) one synchronous call per step (kb_map_chunk_packed: the chunk is cut into sub-batches that overlap inside the call)
+    for _ in range(max(1, args.warmup // 2)):
+        m.map_chunk(flat, off, est, out=out_bufs, packed=pk)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        m.map_chunk(flat, off, est, out=out_bufs, packed=pk)
+    barrier()
+    e2e_sync_s = time.perf_counter() - t0
     m.map_chunk(flat, off, est, out=out_bufs)
     barrier()
     t0 = time.perf_counter()
@@ -389,10 +411,10 @@ def main():
     h2d_text = int(flat.nbytes + off.nbytes + (n // 2) * 4)
     d2h = int(aln.nbytes + cig.nbytes + pairs[:n // 2].nbytes)
     mapped = int((aln["score"] > 0).sum())
-    t = torch.tensor([dev_ms, e2e_s * 1e3, e2e_text_s * 1e3], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, e2e_s * 1e3, e2e_text_s * 1e3, e2e_sync_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, e2e_text_ms = float(t[0]), float(t[1]), float(t[2])
+    dev_ms, e2e_ms, e2e_text_ms, e2e_sync_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -432,10 +454,12 @@ def main():
            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64/int32", "data": "synthetic",
            "config": config, "clocks": clocks,
            "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
-                   "entry": "kb_map_chunk_packed: pinned 2-bit words + exception list in, pinned kb_aln_t / cigar / pair statistics out",
+                   "entry": "kb_map_chunk_begin_packed / kb_map_chunk_end, two chunks in flight: pinned 2-bit words + exception list in, pinned kb_aln_t / cigar / pair statistics out, every step",
                    "host_pack_ms_outside_timed_region": pack_ms, "records_equal_text_entry": same_records},
+           "e2e_sync": {"value": total_reads * args.steps / (e2e_sync_ms / 1e3), "unit": "reads/s", "ms_per_step": e2e_sync_ms / args.steps,
+                        "entry": "kb_map_chunk_packed, one synchronous call per step (sub-batches overlap inside the call)"},
            "e2e_text": {"value": total_reads * args.steps / (e2e_text_ms / 1e3), "unit": "reads/s", "h2d_bytes_per_step": h2d_text, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_text_ms / args.steps, "entry": "kb_map_chunk: pinned read characters in"},
+                        "ms_per_step": e2e_text_ms / args.steps, "entry": "kb_map_chunk, synchronous: pinned read characters in"},
            "gpu_launches": int(work["launches"]) * args.steps, "roofline": roof, "nw": nw,
            "stage_ms": per, "mapped_fraction": mapped / n, "index_upload_s": upload_s,
            "work_per_step": work, "seed_occ_gbs": alg["fm_seed"] / (per["fm_seed"] / 1e3) / 1e9,

@@ -139,6 +139,14 @@ int  kb_map_chunk(kb_ctx_t* ctx, const kb_reads_t* in, const int32_t* est, kb_re
 /* kb_map_chunk / kb_stage_reads on packed reads (48 instead of 160 bytes per 150-bp read over PCIe). */
 int  kb_map_chunk_packed(kb_ctx_t* ctx, const kb_reads_packed_t* in, const int32_t* est, kb_results_t* out);
 int  kb_stage_reads_packed(kb_ctx_t* ctx, const kb_reads_packed_t* in, const int32_t* est);
+/* Chunks in flight: the same call split in two, for callers that have the next chunk ready while one is being mapped (a mapper
+ * streaming a read file). Every chunk runs as one batch on a stream of its own, so the H2D copy of chunk k+1 and the D2H copy of
+ * chunk k-1 run under the kernels of chunk k; at most 3 chunks may be in flight. begin returns immediately with a ticket; the read
+ * and result buffers must stay valid and untouched until end(ticket) returns, which delivers out->n_cigar and the cigar elements.
+ * Chunks may be ended in any order. Not available with -m. */
+int  kb_map_chunk_begin(kb_ctx_t* ctx, const kb_reads_t* in, const int32_t* est, kb_results_t* out, int* ticket);
+int  kb_map_chunk_begin_packed(kb_ctx_t* ctx, const kb_reads_packed_t* in, const int32_t* est, kb_results_t* out, int* ticket);
+int  kb_map_chunk_end(kb_ctx_t* ctx, int ticket);
 /* Host helper: packs `in` into caller-owned buffers (code: kb_packed_words(in) words; exc: cap_exc entries) on `threads` host
  * threads and fills *out (which borrows in->seq_off, code and exc). KB_ECAPACITY when exc is too small (out->n_exc then holds
  * the count needed). Needs no device. */

@@ -54,7 +54,7 @@ RES_DTYPE = np.dtype([("score", "<i4"), ("sub", "<i4"), ("mapq", "<i4"), ("ncan"
 CIGAR_OPS = "MIDNSHP=X"
 
 EXPORTS = ["kb_device_count", "kb_init", "kb_destroy", "kb_strerror", "kb_last_error", "kb_upload_index", "kb_clone_index", "kb_set_params", "kb_get_min_seed_len",
-           "kb_map_chunk", "kb_map_chunk_packed", "kb_stage_reads", "kb_stage_reads_packed", "kb_packed_words", "kb_pack_reads", "kb_run", "kb_fetch_results", "kb_fetch_extra", "kb_stage_ms", "kb_work", "kb_cuda_stream", "kb_debug_fetch", "kb_debug_align", "kb_host_alloc", "kb_host_free", "kb_host_register", "kb_host_unregister",
+           "kb_map_chunk", "kb_map_chunk_packed", "kb_map_chunk_begin", "kb_map_chunk_begin_packed", "kb_map_chunk_end", "kb_stage_reads", "kb_stage_reads_packed", "kb_packed_words", "kb_pack_reads", "kb_run", "kb_fetch_results", "kb_fetch_extra", "kb_stage_ms", "kb_work", "kb_cuda_stream", "kb_debug_fetch", "kb_debug_align", "kb_host_alloc", "kb_host_free", "kb_host_register", "kb_host_unregister",
            "kb_index_build", "kb_index_free", "kb_index_build_error"]
 
 
@@ -82,6 +82,9 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.kb_stage_reads.argtypes = [C.c_void_p, C.POINTER(KbReads), C.c_void_p]
     lib.kb_map_chunk_packed.argtypes = [C.c_void_p, C.POINTER(KbReadsPacked), C.c_void_p, C.POINTER(KbResults)]
     lib.kb_stage_reads_packed.argtypes = [C.c_void_p, C.POINTER(KbReadsPacked), C.c_void_p]
+    lib.kb_map_chunk_begin.argtypes = [C.c_void_p, C.POINTER(KbReads), C.c_void_p, C.POINTER(KbResults), C.POINTER(C.c_int)]
+    lib.kb_map_chunk_begin_packed.argtypes = [C.c_void_p, C.POINTER(KbReadsPacked), C.c_void_p, C.POINTER(KbResults), C.POINTER(C.c_int)]
+    lib.kb_map_chunk_end.argtypes = [C.c_void_p, C.c_int]
     lib.kb_packed_words.restype = C.c_uint64
     lib.kb_packed_words.argtypes = [C.POINTER(KbReads)]
     lib.kb_pack_reads.argtypes = [C.POINTER(KbReads), C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(KbReadsPacked)]
@@ -235,6 +238,28 @@ class Mapper:
             aln, pairs, cig, res = self._results(n, int(res.n_cigar))
             rc = self.lib.kb_fetch_results(self.h, C.byref(res))
         self._check(rc, "kb_map_chunk")
+        return aln, pairs, cig[:res.n_cigar]
+
+    def map_chunk_begin(self, flat, off, est=None, out=None, packed=None):
+        """kb_map_chunk_begin[_packed]: returns a handle for map_chunk_end(). The buffers are kept alive by the handle."""
+        n = len(off) - 1
+        est_arr = self._est(n, est)
+        if packed is True:
+            packed = self.pack(flat, off)
+        reads = self._reads_struct(flat, off)
+        aln, pairs, cig, res = self._results(n, 4 * n + 1024, out)
+        ticket = C.c_int(-1)
+        if packed:
+            rc = self.lib.kb_map_chunk_begin_packed(self.h, C.byref(packed[0]), est_arr.ctypes.data if est_arr is not None else None, C.byref(res), C.byref(ticket))
+        else:
+            rc = self.lib.kb_map_chunk_begin(self.h, C.byref(reads), est_arr.ctypes.data if est_arr is not None else None, C.byref(res), C.byref(ticket))
+        self._check(rc, "kb_map_chunk_begin")
+        return (ticket.value, aln, pairs, cig, res, (flat, off, est_arr, packed, reads))
+
+    def map_chunk_end(self, handle):
+        ticket, aln, pairs, cig, res, _keep = handle
+        self._check(self.lib.kb_map_chunk_end(self.h, ticket), "kb_map_chunk_end")
+        self.n_reads = len(aln)
         return aln, pairs, cig[:res.n_cigar]
 
     def stage(self, flat, off, est=None, packed=False):

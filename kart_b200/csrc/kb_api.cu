@@ -559,6 +559,8 @@ struct kb_slot
 	size_t cap_segs = 0, cap_cands = 0, cap_cigar = 0, cap_segx = 0, cap_jobs = 0, cap_pieces = 0, cap_runs = 0, cap_extra = 0, scratch_per_thread = 0; int scratch_threads = 0;
 	u32* counters_host = nullptr; unsigned long long* work_dev_host = nullptr;   // pinned: 16 x u32, 8 x u64
 	int launches = 0;
+	// a chunk in flight through kb_map_chunk_begin / _end: the caller's result buffers and the reads it came from (for a rerun after an arena overflow)
+	bool busy = false; kb_results_t* user_out = nullptr; const int32_t* user_est = nullptr; bool user_packed = false; kb_reads_t user_text; kb_reads_packed_t user_pk;
 	void release()
 	{
 		seq.release(); scratch.release(); wscratch.release(); seq_off.release(); codes.release(); exc.release(); work.release(); est.release(); n_hits.release(); n_seeds.release(); n_cands.release(); cand_cap.release();
@@ -595,6 +597,7 @@ struct kb_ctx
 	int pipe_min_reads = 262144, pipe_sub_reads = 0;   // chunks of at least pipe_min_reads go through the slot pipeline
 	int pipe_first = 0, pipe_grow = 200, pipe_tail = 0;   // sub-batch plan: first size, growth (percent), floor of the halving tail (0: uniform)
 	cudaStream_t copy_stream = nullptr;                   // D2H of each sub-batch's cigar range, in retirement order
+	int next_slot = 0;                                    // kb_map_chunk_begin: where the search for a free slot starts
 };
 
 static int fail(kb_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess)
@@ -1008,6 +1011,7 @@ static int stage_reads(kb_ctx* ctx, const KbReadSrc& in, const int32_t* est, con
 	if (in.n < 0 || (in.n > 0 && ((!in.seq && !in.pk) || !in.seq_off || (in.pk && (!in.pk->code || (in.pk->n_exc && !in.pk->exc)))))) return fail(ctx, KB_EINVAL, who);
 	if (!ctx->have_index) return fail(ctx, KB_ENOINDEX, "kb_stage_reads: no index");
 	if (ctx->pm.paired && ((in.n & 1) || (in.n > 0 && !est))) return fail(ctx, KB_EINVAL, "kb_stage_reads: paired chunks need an even read count and one EstDistance per pair");
+	for (int k = 0; k < KB_SLOTS; k++) if (ctx->slot[k].busy) return fail(ctx, KB_ESTATE, "a chunk is in flight (kb_map_chunk_end it first)");
 	CK(cudaSetDevice(ctx->device));
 	ctx->staged = false; ctx->ran = false; ctx->ran_pipelined = false;
 	int rc = stage_slot(ctx, ctx->slot[0], in, 0, in.n, est); if (rc) return rc;
@@ -1337,6 +1341,7 @@ static int map_chunk_pipelined(kb_ctx* ctx, const KbReadSrc& in, const int32_t* 
 
 static int map_chunk(kb_ctx* ctx, const KbReadSrc& in, const int32_t* est, kb_results_t* out, const char* who)
 {
+	for (int k = 0; k < KB_SLOTS; k++) if (ctx->slot[k].busy) return fail(ctx, KB_ESTATE, "a chunk is in flight (kb_map_chunk_end it first)");
 	if (ctx->have_index && !ctx->pm.multihit && in.n >= ctx->pipe_min_reads && (in.seq || (in.pk && in.pk->code && (!in.pk->n_exc || in.pk->exc))) && in.seq_off && out->aln && out->cigar
 	    && !(ctx->pm.paired && ((in.n & 1) || !est)))
 	{
@@ -1357,6 +1362,81 @@ int kb_map_chunk_packed(kb_ctx_t* ctx, const kb_reads_packed_t* in, const int32_
 {
 	if (!ctx || !in || !out) return fail(ctx, KB_EINVAL, "kb_map_chunk_packed: bad arguments");
 	return map_chunk(ctx, read_src_packed(in), est, out, "kb_map_chunk_packed: bad arguments");
+}
+
+// ---- chunks in flight -------------------------------------------------------------------------------------------------
+// kb_map_chunk overlaps copies and kernels INSIDE one chunk by cutting it into sub-batches; the price is kernel efficiency (a
+// sub-batch's 22-kernel chain has a latency floor of ~1.5 ms, and small grids leave SMs idle: r19, C3, 2.5 M reads: 21.6 ms per chunk
+// against 13.9 ms of kernels for the same reads as one batch). A caller that has the next chunk ready -- a mapper streaming a
+// FASTQ file does -- gets the overlap ACROSS chunks instead: every chunk runs as one batch on its own slot and stream, the
+// H2D copy of chunk k+1 and the D2H copy of chunk k-1 run under the kernels of chunk k. Up to KB_SLOTS chunks may be in flight.
+// begin: returns at once with a ticket; end: waits for that chunk, delivers n_cigar and the cigar elements.
+static int begin_slot(kb_ctx* ctx, kb_slot& sl, const KbReadSrc& in, const int32_t* est, kb_results_t* out)
+{
+	int rc = stage_slot(ctx, sl, in, 0, in.n, est); if (rc) return rc;
+	if (in.n == 0) return KB_OK;
+	rc = alloc_batch(ctx, sl, 0); if (rc) return rc;
+	rc = launch_pipeline(ctx, sl); if (rc) return rc;
+	CK(cudaMemcpyAsync(out->aln, sl.aln.p, (size_t)in.n * sizeof(kb_aln_t), cudaMemcpyDeviceToHost, sl.stream));
+	if (ctx->pm.paired && out->pairs) CK(cudaMemcpyAsync(out->pairs, sl.pstat.p, (size_t)(in.n / 2) * sizeof(kb_pair_stat_t), cudaMemcpyDeviceToHost, sl.stream));
+	return KB_OK;
+}
+static int map_chunk_begin(kb_ctx* ctx, const KbReadSrc& in, const int32_t* est, kb_results_t* out, int* ticket, const char* who)
+{
+	if (!ticket || in.n < 0 || (in.n > 0 && ((!in.seq && !in.pk) || !in.seq_off || !out->aln || !out->cigar))) return fail(ctx, KB_EINVAL, who);
+	if (!ctx->have_index) return fail(ctx, KB_ENOINDEX, "kb_map_chunk_begin: no index");
+	if (ctx->pm.multihit) return fail(ctx, KB_EINVAL, "kb_map_chunk_begin: not available with -m (use kb_map_chunk)");
+	if (ctx->pm.paired && ((in.n & 1) || (in.n > 0 && !est))) return fail(ctx, KB_EINVAL, "kb_map_chunk_begin: paired chunks need an even read count and one EstDistance per pair");
+	CK(cudaSetDevice(ctx->device));
+	int k = -1;
+	for (int i = 0; i < KB_SLOTS; i++) { const int c = (ctx->next_slot + i) % KB_SLOTS; if (!ctx->slot[c].busy) { k = c; break; } }
+	if (k < 0) return fail(ctx, KB_ESTATE, "kb_map_chunk_begin: every slot holds a chunk in flight (call kb_map_chunk_end first)");
+	kb_slot& sl = ctx->slot[k];
+	ctx->staged = false; ctx->ran = false; ctx->ran_pipelined = false;
+	int rc = begin_slot(ctx, sl, in, est, out);
+	if (rc) { cudaStreamSynchronize(sl.stream); cudaGetLastError(); return rc; }
+	sl.busy = true; sl.user_out = out; sl.user_est = est; sl.user_packed = in.pk != nullptr;
+	if (in.pk) sl.user_pk = *in.pk; else { sl.user_text.n_reads = in.n; sl.user_text.seq = in.seq; sl.user_text.seq_off = in.seq_off; }
+	ctx->next_slot = (k + 1) % KB_SLOTS;
+	*ticket = k;
+	return KB_OK;
+}
+int kb_map_chunk_begin(kb_ctx_t* ctx, const kb_reads_t* in, const int32_t* est, kb_results_t* out, int* ticket)
+{
+	if (!ctx || !in || !out) return fail(ctx, KB_EINVAL, "kb_map_chunk_begin: bad arguments");
+	return map_chunk_begin(ctx, read_src(in), est, out, ticket, "kb_map_chunk_begin: bad arguments");
+}
+int kb_map_chunk_begin_packed(kb_ctx_t* ctx, const kb_reads_packed_t* in, const int32_t* est, kb_results_t* out, int* ticket)
+{
+	if (!ctx || !in || !out) return fail(ctx, KB_EINVAL, "kb_map_chunk_begin_packed: bad arguments");
+	return map_chunk_begin(ctx, read_src_packed(in), est, out, ticket, "kb_map_chunk_begin_packed: bad arguments");
+}
+int kb_map_chunk_end(kb_ctx_t* ctx, int ticket)
+{
+	if (!ctx || ticket < 0 || ticket >= KB_SLOTS || !ctx->slot[ticket].busy) return fail(ctx, KB_ESTATE, "kb_map_chunk_end: no such chunk in flight");
+	CK(cudaSetDevice(ctx->device));
+	kb_slot& sl = ctx->slot[ticket]; kb_results_t* out = sl.user_out;
+	sl.busy = false;
+	memset(ctx->stage_ms, 0, sizeof(ctx->stage_ms)); memset(ctx->work_host, 0, sizeof(ctx->work_host));
+	if (sl.n_reads == 0) { out->n_cigar = 0; return KB_OK; }
+	for (int attempt = 0; attempt < 6; attempt++)
+	{
+		CK(cudaStreamSynchronize(sl.stream));
+		const u32 st = sl.counters_host[3];
+		if (st == 0)
+		{
+			account_slot(ctx, sl);
+			memcpy(ctx->counters_host, sl.counters_host, sizeof(ctx->counters_host));
+			out->n_cigar = sl.counters_host[2]; ctx->n_cigar_last = out->n_cigar;
+			if (out->n_cigar > out->cap_cigar) return fail(ctx, KB_ECAPACITY, "kb_map_chunk_end: cigar buffer too small");
+			if (out->n_cigar) { CK(cudaMemcpyAsync(out->cigar, sl.cigar.p, (size_t)out->n_cigar * 4, cudaMemcpyDeviceToHost, sl.stream)); CK(cudaStreamSynchronize(sl.stream)); }
+			return KB_OK;
+		}
+		grow_factors(ctx, st);   // something overflowed: grow what was flagged and run this chunk again on its slot
+		const KbReadSrc in = sl.user_packed ? read_src_packed(&sl.user_pk) : read_src(&sl.user_text);
+		int rc = begin_slot(ctx, sl, in, sl.user_est, out); if (rc) return rc;
+	}
+	return fail(ctx, KB_EOVERFLOW, "kb_map_chunk_end: arenas still overflow after regrowth");
 }
 
 uint64_t kb_packed_words(const kb_reads_t* in) { return (in && in->n_reads > 0 && in->seq_off) ? (in->seq_off[in->n_reads] >> 5) + (uint64_t)in->n_reads + 1 : 1; }

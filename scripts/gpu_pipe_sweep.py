@@ -7,8 +7,9 @@ import parity_util as pu
 from kart_b200 import KartIndex, Mapper, synth
 from kart_b200.binding import ALN_DTYPE, PAIR_DTYPE
 pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
-idx = KartIndex(pu.default_prefix()); g = pu.genome_of(idx)
-r1, r2, _ = synth.simulate(g, pairs, 150, 0.02, seed=1)
+PREFIX = os.environ.get("SWEEP_PREFIX") or pu.default_prefix()      # SWEEP_PREFIX=data/_gen/syn/syn3100 SWEEP_ERR=0.01 SWEEP_PACKED=1 for the C3 workload
+idx = KartIndex(PREFIX); g = pu.pac_genome(idx)
+r1, r2, _ = synth.simulate(g, pairs, 150, float(os.environ.get("SWEEP_ERR", "0.02")), seed=1)
 reads = pu.interleave(r1, r2); n = reads.shape[0]
 seq_pin = torch.empty(reads.size, dtype=torch.uint8).pin_memory(); seq_pin.numpy()[:] = reads.reshape(-1)
 off_pin = torch.empty(n + 1, dtype=torch.int64).pin_memory(); off_pin.numpy()[:] = np.arange(n + 1, dtype=np.int64) * 150
@@ -31,9 +32,10 @@ for pl in plans:
     os.environ["KB_PIPE_FIRST"] = str(pl.get("first", -1)); os.environ["KB_PIPE_GROW"] = str(pl.get("grow", 200)); os.environ["KB_PIPE_TAIL"] = str(pl.get("tail", 0))
     os.environ["KB_PIPE_MIN_READS"] = "1000" if sub != 2 * pairs + 2 else "2000000000"
     m = Mapper(device=0); m.upload_index(idx, expand_sa=True); m.set_params(paired=True)
-    for _ in range(2): m.map_chunk(flat, off, est, out=out)
+    pk = m.pack(flat, off, threads=16) if os.environ.get("SWEEP_PACKED") else None
+    for _ in range(2): m.map_chunk(flat, off, est, out=out, packed=pk)
     torch.cuda.synchronize(); t = time.perf_counter()
-    for _ in range(5): m.map_chunk(flat, off, est, out=out)
+    for _ in range(5): m.map_chunk(flat, off, est, out=out, packed=pk)
     torch.cuda.synchronize(); dt = (time.perf_counter() - t) / 5
     print("plan %-60s e2e %.2f ms  (%.1f M reads/s)  launches %d" % (pl, dt * 1e3, n / dt / 1e6, m.work()["launches"]), flush=True)
     del m

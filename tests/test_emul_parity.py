@@ -335,3 +335,24 @@ def test_clone_index(mini):
     m2.clone_index_from(m1)
     m2.set_params(paired=True)
     assert pu.compare_pairs(m2, pu.Oracle(pu.MINI_PREFIX), pu.interleave(r1, r2)) == 0
+
+
+def test_chunks_in_flight(mini):
+    """kb_map_chunk_begin / _end: three chunks in flight (text and packed), ended out of order, equal the synchronous call"""
+    idx, g = mini
+    m = pu.make_mapper(idx, emul=True, paired=True)
+    chunks = []
+    for k in range(3):
+        r1, r2, _ = synth.simulate(g, 300 + 50 * k, 150, 0.04, seed=80 + k, indel=0.003)
+        flat, off = Mapper.pack_reads(pu.interleave(r1, r2))
+        chunks.append((flat, off, np.full(300 + 50 * k, 1500 - 400 * k, dtype=np.int32)))
+    want = [m.map_chunk(*c) for c in chunks]
+    hs = [m.map_chunk_begin(c[0], c[1], c[2], packed=(True if k == 1 else None)) for k, c in enumerate(chunks)]
+    with pytest.raises(Exception):
+        m.map_chunk_begin(*chunks[0])          # a fourth chunk: every slot is taken
+    with pytest.raises(Exception):
+        m.map_chunk(*chunks[0])                # the synchronous call is refused while chunks are in flight
+    got = {k: m.map_chunk_end(hs[k]) for k in (2, 0, 1)}
+    for k in range(3):
+        _same_results(want[k], got[k])
+    _same_results(want[0], m.map_chunk(*chunks[0]))
