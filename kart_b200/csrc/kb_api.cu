@@ -195,7 +195,64 @@ __global__ void k_reblock(const u32* bwt, u64 bwt_words, u64 n_new, u32* occ)
 	o[4] = (u32)lo; o[5] = (u32)(lo >> 32); o[6] = (u32)hi; o[7] = (u32)(hi >> 32);
 }
 
-__global__ void __launch_bounds__(KB_BLOCK) k_cand_pair(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_cand_pair(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x); }
+__global__ void __launch_bounds__(KB_BLOCK) k_cand_pair(KbIndexDev ix, KbParams pm, KbBatchDev bt, int split_heavy) { kb_stage_cand_pair(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, split_heavy != 0); }
+// the items k_cand_pair put on the heavy list (a read with more than KB_CAND_HEAVY seeds): one warp each
+#ifndef KB_EMUL
+__global__ void __launch_bounds__(KB_BLOCK) k_cand_heavy(KbIndexDev ix, KbParams pm, KbBatchDev bt)
+{
+	__shared__ KbWarpSort sw[KB_BLOCK / 32];
+	if (bt.counters[3]) return;
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const u32 gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+	KbWarpSort& w = sw[wib];
+	const u32 count = bt.counters[15];
+	for (u32 q = gwarp; q < count; q += nwarps)
+	{
+		const int t = bt.slow_list2[q];
+		for (int which = 0; which < 2; which++)
+		{
+			KbSeg* v; KbSeg* tmp; int n;
+			if (!kb_cand_heavy_list(pm, bt, t, which, &v, &n, &tmp)) break;
+			if (n < 2) continue;
+			if (n > KB_WSORT_MAX) { if (lane == 0) kb_sort_segs<false>(v, n); __syncwarp(); continue; }
+			if (lane == 0) kb_wsort_begin(w, v, n, tmp);
+			__syncwarp();
+			kb_wsort_load(w, lane); __syncwarp();
+			for (int k = 2; k <= w.p; k <<= 1) for (int j = k >> 1; j > 0; j >>= 1) { kb_wsort_step(w, k, j, lane); __syncwarp(); }
+			kb_wsort_gather(w, lane); __syncwarp();
+			kb_wsort_scatter(w, lane); __syncwarp();
+		}
+		__threadfence_block();
+		if (lane == 0) kb_cand_finish(ix, pm, bt, t);
+		__syncwarp();
+	}
+}
+#else
+static void k_cand_heavy(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulation: a warp = a loop over 32 lanes per phase
+{
+	if (blockIdx.x != 0 || threadIdx.x != 0) return;
+	if (bt.counters[3]) return;
+	static thread_local KbWarpSort w;
+	const u32 count = bt.counters[15];
+	for (u32 q = 0; q < count; q++)
+	{
+		const int t = bt.slow_list2[q];
+		for (int which = 0; which < 2; which++)
+		{
+			KbSeg* v; KbSeg* tmp; int n;
+			if (!kb_cand_heavy_list(pm, bt, t, which, &v, &n, &tmp)) break;
+			if (n < 2) continue;
+			if (n > KB_WSORT_MAX) { kb_sort_segs<false>(v, n); continue; }
+			kb_wsort_begin(w, v, n, tmp);
+			for (int l = 31; l >= 0; l--) kb_wsort_load(w, l);
+			for (int k = 2; k <= w.p; k <<= 1) for (int j = k >> 1; j > 0; j >>= 1) for (int l = 31; l >= 0; l--) kb_wsort_step(w, k, j, l);
+			for (int l = 31; l >= 0; l--) kb_wsort_gather(w, l);
+			for (int l = 31; l >= 0; l--) kb_wsort_scatter(w, l);
+		}
+		kb_cand_finish(ix, pm, bt, t);
+	}
+}
+#endif
 __global__ void __launch_bounds__(KB_BLOCK) k_cand_pacbio(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_cand_pacbio(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
 // rescue: plan (thread per job) -> windows (block per task) -> commit (thread per job); see kb_pair.cuh "task-parallel rescue"
 __global__ void __launch_bounds__(KB_BLOCK) k_rescue_plan(KbIndexDev ix, KbParams pm, KbBatchDev bt)
@@ -593,6 +650,7 @@ struct kb_ctx
 	int nw_tmax = 0;             // largest side one thread solves (0: KB_NW_TMAX); KB_NW_TMAX=32|64 sends more to the wavefront kernel
 	int nw_warp_below = 8192;    // a column-tile class (33..64, 65..128) with fewer problems than this is solved by k_nw_warp instead
 	int rescue_threads = 64;     // block size of k_rescue_win (32, 64 or 128)
+	int cand_heavy = 1;          // items with a long seed list get a warp of their own in k_cand_heavy (KB_CAND_HEAVY=0: everything in k_cand_pair)
 	int rescue_fast = 1;         // warp-per-window fast path first (KB_RESCUE_FAST=0: every window through the block-per-window kernel)
 	int pipe_min_reads = 262144, pipe_sub_reads = 0;   // chunks of at least pipe_min_reads go through the slot pipeline
 	int pipe_first = 0, pipe_grow = 200, pipe_tail = 0;   // sub-batch plan: first size, growth (percent), floor of the halving tail (0: uniform)
@@ -665,6 +723,7 @@ int kb_init(int device, kb_ctx_t** out)
 	e = getenv("KB_PIPE_SUB_READS"); if (e && atoi(e) > 0) ctx->pipe_sub_reads = atoi(e);
 	e = getenv("KB_RESCUE_THREADS"); if (e && (atoi(e) == 32 || atoi(e) == 64 || atoi(e) == 128)) ctx->rescue_threads = atoi(e);
 	e = getenv("KB_RESCUE_FAST"); if (e) ctx->rescue_fast = atoi(e) ? 1 : 0;
+	e = getenv("KB_CAND_HEAVY"); if (e) ctx->cand_heavy = atoi(e) ? 1 : 0;
 	e = getenv("KB_PIPE_FIRST"); if (e && atoi(e) >= -1) ctx->pipe_first = atoi(e);
 	e = getenv("KB_PIPE_GROW"); if (e && atoi(e) >= 100) ctx->pipe_grow = atoi(e);
 	e = getenv("KB_PIPE_TAIL"); if (e && atoi(e) >= 0) ctx->pipe_tail = atoi(e);
@@ -1113,7 +1172,8 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 	if (ix.sa_full != nullptr && !pm.pacbio) { KB_LAUNCH(k_sa_locate_reads, g_reads, KB_BLOCK, s, ix, bt); } else { KB_LAUNCH(k_sa_locate, g_hits, KB_BLOCK, s, ix, bt); }
 	sl.launches++;
 	CK(cudaEventRecord(sl.ev[2], s));
-	KB_LAUNCH(k_cand_pair, g_items, KB_BLOCK, s, ix, pm, bt); sl.launches++;
+	KB_LAUNCH(k_cand_pair, g_items, KB_BLOCK, s, ix, pm, bt, ctx->cand_heavy); sl.launches++;
+	if (ctx->cand_heavy && !pm.pacbio) { KB_LAUNCH(k_cand_heavy, 148 * 8, KB_BLOCK, s, ix, pm, bt); sl.launches++; }
 	if (pm.pacbio) { KB_LAUNCH(k_cand_pacbio, g_slow, KB_BLOCK, s, ix, pm, bt); sl.launches++; }
 	CK(cudaEventRecord(sl.ev[3], s));
 	if (pm.paired)

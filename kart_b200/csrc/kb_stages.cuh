@@ -5,12 +5,17 @@
 #include "../../include/kart_b200.h"
 #include "kb_pair.cuh"
 
-// seeds -> sorted seeds -> candidates -> pairing (one thread per pair, or per read when not paired)
-KB_HD void kb_stage_cand_pair(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int t)
+// seeds -> sorted seeds -> candidates -> pairing (one thread per pair, or per read when not paired).
+// A read inside a repeat family brings dozens to hundreds of seeds (up to 50 per search); sorting those in one thread while the
+// other 31 pairs of the warp wait was 36 % of k_cand_pair's samples at 1.6 lanes (ncu r17, C3). Such items (more than
+// KB_CAND_HEAVY seeds on either read) are therefore only set up here and put on the heavy list; k_cand_heavy gives each of them
+// a warp that sorts cooperatively (kb_wsort_*) and finishes the rest on one lane without holding anybody up.
+#define KB_CAND_HEAVY 24
+// part 1: candidate slots and the pair's statistics record. False: nothing more to do (overflow, or pacbio's own kernel follows).
+KB_HD bool kb_cand_setup(const KbParams& pm, const KbBatchDev& bt, int t)
 {
 	if (pm.paired)
 	{
-		int np = bt.n_reads >> 1; if (t >= np) return;
 		int ra = 2 * t, rb = ra + 1;
 		int s1 = bt.n_seeds[ra], s2 = bt.n_seeds[rb];
 		int cap = s1 + s2 + 1;
@@ -18,16 +23,37 @@ KB_HD void kb_stage_cand_pair(const KbIndexDev& ix, const KbParams& pm, const Kb
 		bt.cand_off[ra] = off; bt.cand_off[rb] = off + cap; bt.cand_cap[ra] = cap; bt.cand_cap[rb] = cap;
 		bt.n_cands[ra] = 0; bt.n_cands[rb] = 0;
 		KbPairStat st; st.counted = 0; st.absdist = 0; st.est_lo = -2147483647 - 1; st.est_hi = 2147483647; bt.pstat[t] = st;
-		if ((u64)off + 2ull * cap > (u64)bt.cap_cands) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_CANDS); bt.cand_off[ra] = 0; bt.cand_off[rb] = 0; return; }
-		if (bt.counters[3] & (KB_OVF_SEEDS | KB_OVF_HITS)) return;
+		if ((u64)off + 2ull * cap > (u64)bt.cap_cands) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_CANDS); bt.cand_off[ra] = 0; bt.cand_off[rb] = 0; return false; }
+		if (bt.counters[3] & (KB_OVF_SEEDS | KB_OVF_HITS)) return false;
+		return true;
+	}
+	int s1 = bt.n_seeds[t], cap = s1 + 1;
+	u32 off = KB_ALLOC(&bt.counters[1], (u32)cap);
+	bt.cand_off[t] = off; bt.cand_cap[t] = cap; bt.n_cands[t] = 0;
+	if ((u64)off + (u64)cap > (u64)bt.cap_cands) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_CANDS); bt.cand_off[t] = 0; return false; }
+	if (bt.counters[3] & (KB_OVF_SEEDS | KB_OVF_HITS)) return false;
+	if (pm.pacbio) return false;   // pacbio chaining needs scratch: done by k_cand_pacbio
+	return true;
+}
+KB_HD bool kb_cand_is_heavy(const KbParams& pm, const KbBatchDev& bt, int t)
+{
+	if (pm.paired) return bt.n_seeds[2 * t] > KB_CAND_HEAVY || bt.n_seeds[2 * t + 1] > KB_CAND_HEAVY;
+	return bt.n_seeds[t] > KB_CAND_HEAVY;
+}
+// part 3 (the seeds are (PosDiff,rPos)-sorted): candidates, pairing, pruning, rescue list
+KB_HD void kb_cand_finish(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int t)
+{
+	if (pm.paired)
+	{
+		int ra = 2 * t, rb = ra + 1;
+		int s1 = bt.n_seeds[ra], s2 = bt.n_seeds[rb], cap = bt.cand_cap[ra];
 		KbSeg* v1 = bt.segs + bt.seed_off[ra]; KbSeg* v2 = bt.segs + bt.seed_off[rb];
-		kb_sort_segs<false>(v1, s1); kb_sort_segs<false>(v2, s2);
 		int l1 = (int)(bt.seq_off[ra + 1] - bt.seq_off[ra]), l2 = (int)(bt.seq_off[rb + 1] - bt.seq_off[rb]);
-		KbCand* a = bt.cands + off; KbCand* b = a + cap;
+		KbCand* a = bt.cands + bt.cand_off[ra]; KbCand* b = a + cap;
 		int n1 = kb_cands_illumina(ix, pm, l1, v1, s1, bt.seed_off[ra], a, cap);
 		int n2 = kb_cands_illumina(ix, pm, l2, v2, s2, bt.seed_off[rb], b, cap);
 		bt.n_cands[ra] = n1; bt.n_cands[rb] = n2;
-		i32 lo = st.est_lo, hi = st.est_hi;
+		i32 lo = bt.pstat[t].est_lo, hi = bt.pstat[t].est_hi;
 		bool paired = kb_pair(pm, (i64)bt.est[t], a, n1, b, n2, &lo, &hi);
 		bt.pstat[t].est_lo = lo; bt.pstat[t].est_hi = hi;
 		if (paired) { kb_keep_mated(a, n1, b, n2); kb_prune(pm, a, n1); kb_prune(pm, b, n2); }
@@ -36,21 +62,61 @@ KB_HD void kb_stage_cand_pair(const KbIndexDev& ix, const KbParams& pm, const Kb
 	}
 	else
 	{
-		if (t >= bt.n_reads) return;
-		int s1 = bt.n_seeds[t], cap = s1 + 1;
-		u32 off = KB_ALLOC(&bt.counters[1], (u32)cap);
-		bt.cand_off[t] = off; bt.cand_cap[t] = cap; bt.n_cands[t] = 0;
-		if ((u64)off + (u64)cap > (u64)bt.cap_cands) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_CANDS); bt.cand_off[t] = 0; return; }
-		if (bt.counters[3] & (KB_OVF_SEEDS | KB_OVF_HITS)) return;
-		if (pm.pacbio) return;   // pacbio chaining needs scratch: done by k_cand_pacbio
+		int s1 = bt.n_seeds[t];
 		KbSeg* v = bt.segs + bt.seed_off[t];
-		kb_sort_segs<false>(v, s1);
 		int l = (int)(bt.seq_off[t + 1] - bt.seq_off[t]);
-		KbCand* a = bt.cands + off;
-		int n = kb_cands_illumina(ix, pm, l, v, s1, bt.seed_off[t], a, cap);
+		KbCand* a = bt.cands + bt.cand_off[t];
+		int n = kb_cands_illumina(ix, pm, l, v, s1, bt.seed_off[t], a, bt.cand_cap[t]);
 		bt.n_cands[t] = n;
 		kb_prune(pm, a, n);
 	}
+}
+KB_HD void kb_stage_cand_pair(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int t, bool split_heavy)
+{
+	if (t >= (pm.paired ? (bt.n_reads >> 1) : bt.n_reads)) return;
+	if (!kb_cand_setup(pm, bt, t)) return;
+	if (split_heavy && kb_cand_is_heavy(pm, bt, t)) { const u32 slot = KB_ALLOC(&bt.counters[15], 1u); bt.slow_list2[slot] = t; return; }
+	if (pm.paired) { kb_sort_segs<false>(bt.segs + bt.seed_off[2 * t], bt.n_seeds[2 * t]); kb_sort_segs<false>(bt.segs + bt.seed_off[2 * t + 1], bt.n_seeds[2 * t + 1]); }
+	else kb_sort_segs<false>(bt.segs + bt.seed_off[t], bt.n_seeds[t]);
+	kb_cand_finish(ix, pm, bt, t);
+}
+
+// ---- warp-cooperative (PosDiff,rPos) sort of one read's seeds (k_cand_heavy) ----
+// Keys are packed into 64 bits (PosDiff biased into 43 bits, rPos in 20) and sorted with their index by a bitonic network in the
+// warp's shared memory; the seeds are then permuted through `tmp`, a region of at least n entries nobody uses yet (the pair's
+// candidate slots: a KbCand is as large as a KbSeg). Both orders are total on distinct seeds, so the result equals kb_sort_segs'.
+#define KB_WSORT_MAX 1024
+struct KbWarpSort { u64 key[KB_WSORT_MAX]; unsigned short idx[KB_WSORT_MAX]; KbSeg* v; KbSeg* tmp; int n, p; };
+KB_HD void kb_wsort_begin(KbWarpSort& w, KbSeg* v, int n, KbSeg* tmp) { w.v = v; w.tmp = tmp; w.n = n; int p = 32; while (p < n) p <<= 1; w.p = p; }
+KB_HD void kb_wsort_load(KbWarpSort& w, int lane)
+{
+	for (int i = lane; i < w.p; i += 32)
+	{
+		u64 k = ~0ull;
+		if (i < w.n) { const KbSeg s = w.v[i]; k = ((u64)((s.gpos - (i64)s.rpos) + ((i64)1 << 42)) << 20) | (u64)(u32)s.rpos; }
+		w.key[i] = k; w.idx[i] = (unsigned short)i;
+	}
+}
+KB_HD void kb_wsort_step(KbWarpSort& w, int k, int j, int lane)
+{
+	for (int i = lane; i < w.p; i += 32)
+	{
+		const int o = i ^ j;
+		if (o <= i) continue;
+		const u64 a = w.key[i], b = w.key[o];
+		if ((a > b) == ((i & k) == 0)) { w.key[i] = b; w.key[o] = a; const unsigned short t = w.idx[i]; w.idx[i] = w.idx[o]; w.idx[o] = t; }
+	}
+}
+KB_HD void kb_wsort_gather(KbWarpSort& w, int lane) { for (int i = lane; i < w.n; i += 32) w.tmp[i] = w.v[w.idx[i]]; }
+KB_HD void kb_wsort_scatter(KbWarpSort& w, int lane) { for (int i = lane; i < w.n; i += 32) w.v[i] = w.tmp[i]; }
+// which seed lists of heavy item t the warp sorts: list 0 / 1, the list and its length; false when there is no such list
+KB_HD bool kb_cand_heavy_list(const KbParams& pm, const KbBatchDev& bt, int t, int which, KbSeg** v, int* n, KbSeg** tmp)
+{
+	if (which > (pm.paired ? 1 : 0)) return false;
+	const int r = pm.paired ? 2 * t + which : t;
+	*v = bt.segs + bt.seed_off[r]; *n = bt.n_seeds[r];
+	*tmp = reinterpret_cast<KbSeg*>(bt.cands + bt.cand_off[pm.paired ? 2 * t : t]);   // 2 x (s1 + s2 + 1) (or s1 + 1) unused candidate slots
+	return true;
 }
 
 // Private arena of thread `tid` of an arena kernel launched with `nth` threads. The scratch buffer is sized for the worst

@@ -137,7 +137,7 @@ struct KbBatchDev
 	i32 nw_warp_below;                  // a column-tile class with fewer problems than this goes to the warp wavefront kernel as well
 	i32 seg_cap, kmer_cap;
 	// counters: [0] seeds cursor [1] cands cursor [2] cigar cursor [3] status bits [4] rescue count [5] max seeds/read
-	//           [6] nw calls [7] rescue attempts [8] segx cursor [10] run cursor + [11] job cursor (one u64) [12],[13] slow lists [14] extra-line cursor (-m)
+	//           [6] nw calls [7] rescue attempts [8] segx cursor [10] run cursor + [11] job cursor (one u64) [12],[13] slow lists [14] extra-line cursor (-m) [15] heavy candidate items (k_cand_heavy; listed in slow_list2 until the assemble stage reuses it)
 	//           [16..22] pieces per size class [23] partition jobs [24] piece cursor [25] fast rescue tickets [26] k_align_part job tickets [27] rescue task cursor [28] slow rescue tickets [29] slow rescue list
 	//           [30],[31] cigar cursor before / after the assemble kernels (pipelined chunks)
 	//           64-bit: work[0] extension steps, work[1] occ blocks, work[2] LF steps, work[3] NW cells, work[4] NW calls

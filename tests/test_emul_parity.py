@@ -356,3 +356,20 @@ def test_chunks_in_flight(mini):
     for k in range(3):
         _same_results(want[k], got[k])
     _same_results(want[0], m.map_chunk(*chunks[0]))
+
+
+def test_heavy_candidate_items(mini, monkeypatch):
+    """Reads with more than KB_CAND_HEAVY seeds (repeat copies) are sorted by a warp in k_cand_heavy; with KB_CAND_HEAVY=0 every item stays
+    in k_cand_pair. Both against the oracle, paired and single-end."""
+    idx, g = mini
+    r1, r2, _ = synth.simulate(g, 1500, 150, 0.02, seed=31, indel=0.002)
+    r, _, _ = synth.simulate(g, 1500, 100, 0.05, seed=32, paired=False)
+    orc = pu.Oracle(pu.MINI_PREFIX)
+    for split in ("1", "0"):
+        monkeypatch.setenv("KB_CAND_HEAVY", split)
+        m = pu.make_mapper(idx, emul=True, paired=True)
+        assert pu.compare_pairs(m, orc, pu.interleave(r1, r2)) == 0
+        assert (m.debug(9, np.uint32, 32)[15] > 10) == (split == "1")
+        m = pu.make_mapper(idx, emul=True, paired=False)
+        assert pu.compare_singles(m, orc, r) == 0
+        assert (m.debug(9, np.uint32, 32)[15] > 10) == (split == "1")

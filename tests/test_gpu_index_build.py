@@ -63,10 +63,18 @@ def test_gpu_index_awkward_texts_equal_host_builder(built, tmp_path, monkeypatch
     cases = {"one": ["A"], "five": ["ACGTT"], "l33": [rnd(33)], "l127": [rnd(127)], "l128": [rnd(64), rnd(64)], "l129": [rnd(129)], "l4099": [rnd(4099)],
              "allA": ["A" * 3001], "allT": ["T" * 2000], "AT": ["AT" * 1500], "tandem": [unit * 90 + rnd(100)], "dups": [rnd(300) + dup + rnd(200) + dup + rnd(111), dup],
              "withN": [rnd(500) + "NNNNNNNNNN" + rnd(300) + "RY" + rnd(77)], "palin": ["ACGT" * 300 + "GAATTC" * 100]}
+    bad = []
     for name, seqs in cases.items():
         fa = str(tmp_path / (name + ".fa"))
         _write_fa(fa, seqs)
         host, dev = str(tmp_path / (name + "_h")), str(tmp_path / (name + "_d"))
         subprocess.run([KART, "index", fa, host], check=True, stdout=subprocess.DEVNULL)
-        subprocess.run([KART, "index", "-gpu", fa, dev], check=True, stdout=subprocess.DEVNULL)
-        _same(dev, host, [".bwt", ".sa", ".pac", ".ann", ".amb"])
+        r = subprocess.run([KART, "index", "-gpu", fa, dev], capture_output=True, text=True, env=dict(os.environ, KB_INDEX_TRACE="1"))
+        if r.returncode != 0:
+            bad.append((name, "exit %d: %s %s" % (r.returncode, r.stdout[-300:], r.stderr[-600:])))
+            continue
+        try:
+            _same(dev, host, [".bwt", ".sa", ".pac", ".ann", ".amb"])
+        except AssertionError as e:
+            bad.append((name, str(e)))
+    assert not bad, bad

@@ -165,6 +165,47 @@ def test_packed_entry_point_gpu(eco, monkeypatch):
     assert pu.compare_pairs(pu.make_mapper(idx, paired=True), pu.Oracle(prefix), reads[:8000]) == 0
 
 
+def test_heavy_candidate_items_gpu(built, monkeypatch):
+    """k_cand_heavy (warp per item with a long seed list, cooperative sort) and the single-kernel path (KB_CAND_HEAVY=0) against the oracle"""
+    idx = KartIndex(pu.MINI_PREFIX)
+    g = pu.genome_of(idx)
+    r1, r2, _ = synth.simulate(g, 6000, 150, 0.02, seed=31, indel=0.002)
+    r, _, _ = synth.simulate(g, 6000, 100, 0.05, seed=32, paired=False)
+    orc = pu.Oracle(pu.MINI_PREFIX)
+    for split in ("1", "0"):
+        monkeypatch.setenv("KB_CAND_HEAVY", split)
+        m = pu.make_mapper(idx, paired=True)
+        assert pu.compare_pairs(m, orc, pu.interleave(r1, r2)) == 0
+        assert (m.debug(9, np.uint32, 32)[15] > 50) == (split == "1")
+        m = pu.make_mapper(idx, paired=False)
+        assert pu.compare_singles(m, orc, r) == 0
+        assert (m.debug(9, np.uint32, 32)[15] > 50) == (split == "1")
+
+
+def test_chunks_in_flight_gpu(eco):
+    """kb_map_chunk_begin / _end on the device: three chunks in flight (text and packed), ended out of order, equal the synchronous call"""
+    idx, g, prefix = eco
+    m = pu.make_mapper(idx, expand_sa=True, paired=True)
+    chunks = []
+    for k in range(3):
+        r1, r2, _ = synth.simulate(g, 30000 + 5000 * k, 150, 0.03, seed=80 + k, indel=0.003)
+        flat, off = Mapper.pack_reads(pu.interleave(r1, r2))
+        chunks.append((flat, off, np.full(30000 + 5000 * k, 1500 - 400 * k, dtype=np.int32)))
+    want = [m.map_chunk(*c) for c in chunks]
+    hs = [m.map_chunk_begin(c[0], c[1], c[2], packed=(True if k == 1 else None)) for k, c in enumerate(chunks)]
+    with pytest.raises(Exception):
+        m.map_chunk_begin(*chunks[0])
+    got = {k: m.map_chunk_end(hs[k]) for k in (2, 0, 1)}
+    for k in range(3):
+        a0, p0, c0 = want[k]; a1, p1, c1 = got[k]
+        for f in ("pos", "mate_pos", "kind", "flag", "chr", "mapq", "score", "sub_score", "tlen", "fwd", "cig_len"):
+            assert np.array_equal(a0[f], a1[f]), (k, f)
+        assert np.array_equal(p0, p1) and len(c0) == len(c1)
+        i0 = np.repeat(a0["cig_off"].astype(np.int64), a0["cig_len"]) + (np.arange(int(a0["cig_len"].sum())) - np.repeat(np.cumsum(a0["cig_len"]) - a0["cig_len"], a0["cig_len"]))
+        i1 = np.repeat(a1["cig_off"].astype(np.int64), a1["cig_len"]) + (np.arange(int(a1["cig_len"].sum())) - np.repeat(np.cumsum(a1["cig_len"]) - a1["cig_len"], a1["cig_len"]))
+        assert np.array_equal(c0[i0], c1[i1])
+
+
 def test_rescue_fast_path_and_fallback(built, monkeypatch):
     """k_rescue_fast (warp per window, shared memory) takes the clean windows, k_rescue_win the rest; both against the oracle."""
     idx = KartIndex(pu.MINI_PREFIX)
