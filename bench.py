@@ -85,7 +85,8 @@ C3_MBP, C3_CONTIGS, C3_SEED = 3100, 24, 12345
 
 def ensure_index(args, rank):
     """Index prefix and workload description. C3: rank 0 builds the synthetic genome's index once per box (scripts/make_syn_index.py
-    with this repo's `kart index`: files byte-identical to the reference builder's, minutes instead of hours), the other ranks wait."""
+    with this repo's `kart index -gpu`: files byte-identical to the reference builder's, seconds instead of hours; the host builder when
+    the device builder cannot run), the other ranks wait."""
     import parity_util as pu
     if args.prefix:
         return args.prefix, "index %s" % os.path.basename(args.prefix)
@@ -97,16 +98,15 @@ def ensure_index(args, rank):
         if ln.startswith("MemAvailable"):
             avail_gb = int(ln.split()[1]) >> 20
     prefix = os.path.join(ROOT, "data", "_gen", "syn", "syn%d" % mbp)
-    if not os.path.exists(prefix + ".ok") and avail_gb < mbp * 23 // 1000 + 4:
-        mbp = 2000 if avail_gb >= 52 else 100   # 64-bit suffix positions need ~23 GB per Gbp; 2000 Mbp still builds with 32-bit ones
+    if not os.path.exists(prefix + ".ok") and avail_gb < mbp * 6 // 1000 + 4:
+        mbp = 100   # the generator, the .pac and what the GPU builder hands back need ~6 GB per Gbp of host memory
         prefix = os.path.join(ROOT, "data", "_gen", "syn", "syn%d" % mbp)
     if not os.path.exists(prefix + ".ok"):
         if rank == 0:
             t = time.time()
             if not (os.path.exists(prefix + ".bwt") and os.path.exists(prefix + ".sa") and os.path.exists(prefix + ".pac") and os.path.exists(prefix + ".ann")):
-                env = dict(os.environ, KART_INDEX_BUILDER="ours")
                 subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "make_syn_index.py"), str(mbp), str(C3_CONTIGS if mbp >= 1000 else 4), str(C3_SEED)],
-                               check=True, env=env, stdout=sys.stderr)
+                               check=True, stdout=sys.stderr)
             open(prefix + ".ok", "w").write("built in %.0f s\n" % (time.time() - t))
         else:
             while not os.path.exists(prefix + ".ok"):

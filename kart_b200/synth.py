@@ -49,20 +49,19 @@ def write_fasta(path: str, names, seqs, width: int = 70) -> None:
             fh.write(b"\n".join(b[i:i + width] for i in range(0, len(b), width)) + b"\n")
 
 
-def make_genome(total_bp: int, n_contigs: int, seed: int, repeats=((3000, 20, 0.02), (300, 200, 0.05))):
-    """i.i.d. uniform ACGT contigs with injected repeat families (len, copies, per-copy divergence).
-
-    Mirrors the pilot genome of SURVEY.md Appendix B at any scale."""
+def make_genome_codes(total_bp: int, n_contigs: int, seed: int, repeats=((3000, 20, 0.02), (300, 200, 0.05))):
+    """i.i.d. uniform contigs with injected repeat families (len, copies, per-copy divergence) as 2-bit codes (A 0, C 1, G 2, T 3):
+    (names, contig lengths, codes of the concatenated genome). Mirrors the pilot genome of SURVEY.md Appendix B at any scale."""
     rng = np.random.default_rng(seed)
-    g = _ACGT[rng.integers(0, 4, size=total_bp, dtype=np.uint8)].copy()
+    g = rng.integers(0, 4, size=total_bp, dtype=np.uint8)
     for rep_len, copies, div in repeats:
         if rep_len * 2 >= total_bp:
             continue
-        elem = _ACGT[rng.integers(0, 4, size=rep_len, dtype=np.uint8)]
+        elem = rng.integers(0, 4, size=rep_len, dtype=np.uint8)
         for p in rng.integers(0, total_bp - rep_len, size=copies):
             c = elem.copy()
             m = rng.random(rep_len) < div
-            c[m] = _ACGT[rng.integers(0, 4, size=int(m.sum()), dtype=np.uint8)]
+            c[m] = rng.integers(0, 4, size=int(m.sum()), dtype=np.uint8)
             g[p:p + rep_len] = c
     cuts = np.linspace(0, total_bp, n_contigs + 1).astype(np.int64)
     # uneven contigs so that "longer chromosome wins" ties are exercised
@@ -70,8 +69,37 @@ def make_genome(total_bp: int, n_contigs: int, seed: int, repeats=((3000, 20, 0.
         jitter = rng.integers(-total_bp // (8 * n_contigs), total_bp // (8 * n_contigs) + 1, size=n_contigs - 1)
         cuts[1:-1] += jitter
     names = ["chr%d" % (i + 1) for i in range(n_contigs)]
-    seqs = [g[cuts[i]:cuts[i + 1]] for i in range(n_contigs)]
-    return names, seqs
+    return names, np.diff(cuts), g
+
+
+def make_genome(total_bp: int, n_contigs: int, seed: int, repeats=((3000, 20, 0.02), (300, 200, 0.05))):
+    """The same genome as upper-case characters: (names, list of contigs)."""
+    names, lens, g = make_genome_codes(total_bp, n_contigs, seed, repeats)
+    g = _ACGT[g]
+    cuts = np.concatenate([[0], np.cumsum(lens)])
+    return names, [g[cuts[i]:cuts[i + 1]] for i in range(n_contigs)]
+
+
+def write_pac_ann(prefix: str, names, lens, codes: np.ndarray) -> None:
+    """prefix.pac / .ann / .amb exactly as the index builders write them for an ACGT-only FASTA without header comments
+    (BWT_Index/bntseq.c:59-89,192-205): the input of `kart index -gpu -pac prefix`, without a FASTA detour."""
+    L = int(len(codes))
+    pad = (-L) % 4
+    c = np.concatenate([codes, np.zeros(pad, dtype=np.uint8)]) if pad else codes
+    pac = (c[0::4] << 6) | (c[1::4] << 4) | (c[2::4] << 2) | c[3::4]
+    with open(prefix + ".pac", "wb") as fh:
+        pac.astype(np.uint8).tofile(fh)
+        if L % 4 == 0:
+            fh.write(b"\x00")
+        fh.write(bytes([L % 4]))
+    with open(prefix + ".ann", "w") as fh:
+        fh.write("%d %d %u\n" % (L, len(names), 11))
+        off = 0
+        for n, ln in zip(names, lens):
+            fh.write("0 %s (null)\n%d %d 0\n" % (n, off, int(ln)))
+            off += int(ln)
+    with open(prefix + ".amb", "w") as fh:
+        fh.write("%d %d 0\n" % (L, len(names)))
 
 
 class PacText:
