@@ -173,8 +173,10 @@ __global__ void k_put_counts(const u64* cA, const u64* cC, const u64* cG, const 
 {
 	const u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x;
 	if (b > nblk) return;
-	u64* o = reinterpret_cast<u64*>(out + (b < nblk ? b * 16 : tail_at));
-	o[0] = cA[b]; o[1] = cC[b]; o[2] = cG[b]; o[3] = cT[b];
+	// 32-bit halves: the totals behind a partial last block start at an odd word when that block holds an odd number of symbol words
+	u32* o = out + (b < nblk ? b * 16 : tail_at);
+	const u64 v[4] = {cA[b], cC[b], cG[b], cT[b]};
+	for (int c = 0; c < 4; c++) { o[2 * c] = (u32)v[c]; o[2 * c + 1] = (u32)(v[c] >> 32); }
 }
 __global__ void k_samples(const u64* sa, u64 n_sa, u64* smp) { const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; if (j >= 1 && j < n_sa) smp[j - 1] = sa[j * 32 - 1]; }
 

@@ -77,4 +77,6 @@ def test_gpu_index_awkward_texts_equal_host_builder(built, tmp_path, monkeypatch
             _same(dev, host, [".bwt", ".sa", ".pac", ".ann", ".amb"])
         except AssertionError as e:
             bad.append((name, str(e)))
-    assert not bad, bad
+    for name, why in bad:   # in full: pytest abbreviates a long assertion message
+        print("== %s: %s" % (name, why))
+    assert not bad, "%d of %d texts differ or failed: %s" % (len(bad), len(cases), [b[0] for b in bad])
