@@ -47,6 +47,66 @@ __global__ void __launch_bounds__(KB_BLOCK) k_pack(KbBatchDev bt)
 
 // packed reads (kb_reads_packed_t) -> KbPk words and the read characters; one thread per (read, word). The characters that are
 // not upper-case bases follow in k_unpack_exc.
+#ifndef KB_EMUL
+// The characters of a warp's 32 (read, word) pieces are one contiguous stretch of `seq` (reads lie back to back, pieces in order), but
+// every piece starts 32 (or fewer) bytes after its neighbour at whatever alignment the read lengths give: written piece by piece that is
+// 32 one-byte stores per thread, each touching 32 sectors per warp (ncu r21, C3: 0.82 ms per million reads, as long as k_segments; it is
+// the difference between the end-to-end and the device-resident step). So the warp stages its stretch in shared memory at the same
+// alignment modulo 16 and writes it out with 16-byte stores, lane after lane.
+__global__ void __launch_bounds__(KB_BLOCK) k_unpack(KbBatchDev bt, const u64* code, u8* seq)
+{
+	__shared__ __align__(16) u8 stage[KB_BLOCK / 32][32 * 32 + 32];
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const int lane = threadIdx.x & 31; u8* st = stage[threadIdx.x >> 5];
+	int n = 0; u64 dst = 0, c = 0;
+	if (t < (long long)bt.n_reads * bt.pk_wpr)
+	{
+		const int r = (int)(t / bt.pk_wpr), w = (int)(t % bt.pk_wpr);
+		const u64 off = bt.seq_off[r]; const int len = (int)(bt.seq_off[r + 1] - off);
+		if (32 * w < len)
+		{
+			n = len - 32 * w < 32 ? len - 32 * w : 32;
+			const u64 at = (off >> 5) - (bt.seq_off[0] >> 5) + (u64)r + (u64)w;   // slot-local word index
+			c = code[at];
+			KbPk k; k.code = c; k.n4 = n == 32 ? 0u : (~0u >> n); k.bad = k.n4;
+			bt.pk[(off >> 5) + (u64)r + (u64)w] = k;
+			dst = (off - bt.seq_off[0]) + 32 * (u64)w;
+		}
+	}
+	const u32 have = __ballot_sync(0xFFFFFFFFu, n > 0);
+	if (have == 0) return;
+	const int first = __ffs(have) - 1, last = 31 - __clz(have);
+	const u64 start = __shfl_sync(0xFFFFFFFFu, dst, first);
+	const u64 end = __shfl_sync(0xFFFFFFFFu, dst + (u64)n, last);
+	const u32 a0 = (u32)(start & 15u);                       // the stretch keeps its alignment modulo 16 in shared memory
+	if (n > 0)
+	{
+		const u32 rel = a0 + (u32)(dst - start);
+		u32 wd[8];
+		for (int q = 0; q < 8; q++)
+		{
+			u32 v = 0;
+			for (int i = 0; i < 4; i++) v |= ((0x54474341u >> (8 * (u32)((c >> (62 - 2 * (4 * q + i))) & 3ull))) & 0xFFu) << (8 * i);   // "ACGT"
+			wd[q] = v;
+		}
+		if (n == 32 && (rel & 3u) == 0u) { u32* p = reinterpret_cast<u32*>(st + rel); for (int q = 0; q < 8; q++) p[q] = wd[q]; }
+		else if (n == 32 && (rel & 1u) == 0u) { unsigned short* p = reinterpret_cast<unsigned short*>(st + rel); for (int q = 0; q < 8; q++) { p[2 * q] = (unsigned short)wd[q]; p[2 * q + 1] = (unsigned short)(wd[q] >> 16); } }
+		else for (int i = 0; i < n; i++) st[rel + i] = (u8)(wd[i >> 2] >> (8 * (i & 3)));
+	}
+	__syncwarp();
+	const u32 total = (u32)(end - start);
+	u8* out = seq + start - a0;                              // 16-byte aligned (the slot's buffer is)
+	const u32 lo = a0, hi = a0 + total;                      // the bytes of `st` that hold characters
+	const u32 body_lo = (lo + 15u) & ~15u, body_hi = hi & ~15u;
+	if (body_lo < body_hi)
+	{
+		for (u32 b = body_lo + 16u * (u32)lane; b < body_hi; b += 16u * 32u) *reinterpret_cast<uint4*>(out + b) = *reinterpret_cast<const uint4*>(st + b);
+		for (u32 b = lo + (u32)lane; b < body_lo; b += 32u) out[b] = st[b];
+		for (u32 b = body_hi + (u32)lane; b < hi; b += 32u) out[b] = st[b];
+	}
+	else for (u32 b = lo + (u32)lane; b < hi; b += 32u) out[b] = st[b];
+}
+#else
 __global__ void __launch_bounds__(KB_BLOCK) k_unpack(KbBatchDev bt, const u64* code, u8* seq)
 {
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -62,6 +122,7 @@ __global__ void __launch_bounds__(KB_BLOCK) k_unpack(KbBatchDev bt, const u64* c
 	u8* s = seq + (off - bt.seq_off[0]) + 32 * w;
 	for (int i = 0; i < n; i++) s[i] = (u8)(0x54474341u >> (8 * (u32)((c >> (62 - 2 * i)) & 3ull)));   // "ACGT"
 }
+#endif
 __global__ void __launch_bounds__(KB_BLOCK) k_unpack_exc(KbBatchDev bt, const u64* exc, u32 n_exc, u32 first_read, u8* seq)
 {
 	const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -167,7 +228,7 @@ __global__ void k_expand_sa(KbIndexDev ix, u64* full)
 __global__ void k_build_ktab(KbIndexDev ix, int K, KbKtab* out)
 {
 	u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-	if (t < (1ull << (2 * K))) out[t] = kb_ktab_entry(ix, (u32)t, K);
+	if (t < (1ull << (2 * K))) out[t] = kb_ktab_entry(ix, t, K);
 }
 
 // re-blocks the BWA Occ/BWT interleave (16 words / 128 rows, u64 counts) into 8 words / 64 rows: u32 counts + two bit planes
@@ -222,9 +283,6 @@ __global__ void __launch_bounds__(KB_BLOCK) k_cand_heavy(KbIndexDev ix, KbParams
 			kb_wsort_gather(w, lane); __syncwarp();
 			kb_wsort_scatter(w, lane); __syncwarp();
 		}
-		__threadfence_block();
-		if (lane == 0) kb_cand_finish(ix, pm, bt, t);
-		__syncwarp();
 	}
 }
 #else
@@ -249,10 +307,18 @@ static void k_cand_heavy(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulati
 			for (int l = 31; l >= 0; l--) kb_wsort_gather(w, l);
 			for (int l = 31; l >= 0; l--) kb_wsort_scatter(w, l);
 		}
-		kb_cand_finish(ix, pm, bt, t);
 	}
 }
 #endif
+// ... and then a thread each for the scan over the sorted seeds, the pairing and the pruning. On the sorting warp's lane 0 that part
+// ran one item after the other (80 % of k_cand_heavy's samples at one lane: ncu r21, C3); here every heavy item of the batch is in
+// flight at once, and a warp lasts as long as its longest item instead of as long as the sum of thirteen.
+__global__ void __launch_bounds__(KB_BLOCK) k_cand_heavy_finish(KbIndexDev ix, KbParams pm, KbBatchDev bt)
+{
+	if (bt.counters[3]) return;
+	const u32 count = bt.counters[15];
+	for (u32 q = blockIdx.x * blockDim.x + threadIdx.x; q < count; q += gridDim.x * blockDim.x) kb_cand_finish(ix, pm, bt, bt.slow_list2[q]);
+}
 __global__ void __launch_bounds__(KB_BLOCK) k_cand_pacbio(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_cand_pacbio(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
 // rescue: plan (thread per job) -> windows (block per task) -> commit (thread per job); see kb_pair.cuh "task-parallel rescue"
 __global__ void __launch_bounds__(KB_BLOCK) k_rescue_plan(KbIndexDev ix, KbParams pm, KbBatchDev bt)
@@ -784,6 +850,7 @@ int kb_upload_index(kb_ctx_t* ctx, const kb_index_host_t* h, int expand_sa)
 	CK(cudaSetDevice(ctx->device));
 	cudaStream_t stream = ctx->slot[0].stream;
 	for (int c = 1; c <= 4; c++) if (h->L2[c] - h->L2[c - 1] >= 0xFFFFFFFFull) return fail(ctx, KB_EINVAL, "kb_upload_index: a base count exceeds 2^32-1 (u32 Occ layout)");
+	if (h->seq_len + 2 >= (1ull << 40)) return fail(ctx, KB_EINVAL, "kb_upload_index: text longer than 2^40 (row numbers are packed into 40 bits)");
 	KbIndexDev& ix = ctx->ix; memset(&ix, 0, sizeof(ix));
 	ix.primary = h->primary; for (int i = 0; i < 5; i++) ix.L2[i] = h->L2[i]; ix.seq_len = h->seq_len;
 	// Occ re-blocking on the device
@@ -848,11 +915,11 @@ int kb_upload_index(kb_ctx_t* ctx, const kb_index_host_t* h, int expand_sa)
 	ix.mapq_lut = ctx->lut.p; ix.mapq_lut_scores = lut_scores;
 	CK(cudaStreamSynchronize(stream));
 	{
-		// seeding table: the smallest K with 4^K >= 2G, at most 14 (8.6 GB of the 180 GB): past it intervals are narrow, so
+		// seeding table: the smallest K with 4^K >= 2G, at most 14 (4.3 GB of the 180 GB): past it intervals are narrow, so
 		// nearly every remaining extension step is the one-block case of kb_extend. Never longer than MinSeedLength.
 		int K = 1; while (K < 14 && (1ull << (2 * K)) < h->seq_len) K++;
-		{ int ms = derive_min_seed(h->l_pac); if (K > ms) K = ms; }
-		{ const char* e = getenv("KB_KTAB_K"); if (e && atoi(e) >= 0 && atoi(e) <= 14) K = atoi(e); }
+		const int ms = derive_min_seed(h->l_pac); if (K > ms) K = ms;
+		{ const char* e = getenv("KB_KTAB_K"); if (e && atoi(e) >= 0 && atoi(e) <= 16) K = atoi(e) < ms ? atoi(e) : ms; }   // 16 bytes x 4^K: 4.3 GB at 14, 17 GB at 15, 69 GB at 16
 		if (K >= 4)
 		{
 			u64 ne2 = 1ull << (2 * K);
@@ -1173,7 +1240,7 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 	sl.launches++;
 	CK(cudaEventRecord(sl.ev[2], s));
 	KB_LAUNCH(k_cand_pair, g_items, KB_BLOCK, s, ix, pm, bt, ctx->cand_heavy); sl.launches++;
-	if (ctx->cand_heavy && !pm.pacbio) { KB_LAUNCH(k_cand_heavy, 148 * 8, KB_BLOCK, s, ix, pm, bt); sl.launches++; }
+	if (ctx->cand_heavy && !pm.pacbio) { KB_LAUNCH(k_cand_heavy, 148 * 8, KB_BLOCK, s, ix, pm, bt); KB_LAUNCH(k_cand_heavy_finish, 148 * 8, KB_BLOCK, s, ix, pm, bt); sl.launches += 2; }
 	if (pm.pacbio) { KB_LAUNCH(k_cand_pacbio, g_slow, KB_BLOCK, s, ix, pm, bt); sl.launches++; }
 	CK(cudaEventRecord(sl.ev[3], s));
 	if (pm.paired)

@@ -126,11 +126,21 @@ KB_HD bool kb_pair(const KbParams& pm, i64 est, KbCand* a, int n1, KbCand* b, in
 {
 	bool any = false;
 	if (n1 * n2 > 1000) { kb_prune(pm, a, n1); kb_prune(pm, b, n2); }
+	// Both lists come out of a (PosDiff,rPos)-sorted seed scan, so their PosDiff ascends: the mates of a[i] that the reference's
+	// inner loop does anything with (PosDiff >= a[i]'s, distance < Est) are one window of b, followed by at most one candidate that
+	// narrows *hi; every later one is further away still. The window's start only moves forward with i. A pair inside a repeat
+	// family has dozens of candidates on either side, all but a few of them a genome away from each other: n1 + n2 steps instead of
+	// n1 x n2 (ncu r21, C3: the quadratic loop was a quarter of k_cand_heavy). The order is checked, not assumed.
+	bool ascending = n1 * n2 > 16;
+	for (int i = 1; ascending && i < n1; i++) if (a[i].diff < a[i - 1].diff) ascending = false;
+	for (int j = 1; ascending && j < n2; j++) if (b[j].diff < b[j - 1].diff) ascending = false;
+	int j0 = 0;
 	for (int i = 0; i < n1; i++)
 	{
 		if (a[i].score == 0) continue;
 		int best = -1, s = 0;
-		for (int j = 0; j < n2; j++)
+		if (ascending) while (j0 < n2 && b[j0].diff < a[i].diff) j0++;
+		for (int j = j0; j < n2; j++)
 		{
 			if (b[j].score == 0 || b[j].diff < a[i].diff) continue;
 			i64 dist = b[j].diff - a[i].diff;
@@ -139,7 +149,7 @@ KB_HD bool kb_pair(const KbParams& pm, i64 est, KbCand* a, int n1, KbCand* b, in
 				if (dist + 1 > *lo) *lo = (i32)(dist + 1);
 				if (b[j].score > s) { best = j; s = b[j].score; } else if (b[j].score == s) best = -1;
 			}
-			else if (dist < *hi) *hi = (i32)dist;
+			else { if (dist < *hi) *hi = (i32)dist; if (ascending) break; }
 		}
 		if (s > 0 && best != -1)
 		{

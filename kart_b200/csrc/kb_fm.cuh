@@ -231,30 +231,42 @@ KB_HD bool kb_extend(const KbIndexDev& ix, ROW& x0, ROW& x1, ROW& x2, int c, u32
 }
 
 // one entry of the seeding table: BWT_Search over the K bases spelled by `kmer` (first base most significant)
-KB_HD KbKtab kb_ktab_entry(const KbIndexDev& ix, u32 kmer, int K)
+KB_HD KbKtab kb_ktab_pack(u64 x0, u64 x1, u64 x2, u32 flen)
 {
-	KbKtab e; e.pad = 0; e.flen = 0;
+	KbKtab e;
+	if (x2 == 0) { e.a = 0; e.b = flen; return e; }
+	e.a = x0 | ((x2 & 0xFFFFFFull) << 40); e.b = x1 | ((x2 >> 24) << 40);
+	return e;
+}
+KB_HD KbKtabE kb_ktab_unpack(u64 a, u64 b)
+{
+	KbKtabE e; const u64 M40 = (1ull << 40) - 1;
+	e.x2 = (a >> 40) | ((b >> 40) << 24);
+	if (e.x2 == 0) { e.x0 = 0; e.x1 = 0; e.flen = (u32)b; return e; }
+	e.x0 = a & M40; e.x1 = b & M40; e.flen = 0;
+	return e;
+}
+KB_HD KbKtab kb_ktab_entry(const KbIndexDev& ix, u64 kmer, int K)
+{
 	int p = (int)((kmer >> (2 * (K - 1))) & 3u);
 	u64 x0 = ix.L2[p] + 1, x1 = ix.L2[3 - p] + 1, x2 = ix.L2[p + 1] - ix.L2[p];
 	u32 blocks = 0;
 	for (int i = 1; i < K; i++)
 	{
 		int c = (int)((kmer >> (2 * (K - 1 - i))) & 3u);
-		if (!kb_extend(ix, x0, x1, x2, c, &blocks)) { e.x0 = 0; e.x1 = 0; e.x2 = 0; e.flen = (u32)i; return e; }
+		if (!kb_extend(ix, x0, x1, x2, c, &blocks)) return kb_ktab_pack(0, 0, 0, (u32)i);
 	}
-	e.x0 = x0; e.x1 = x1; e.x2 = (u32)x2;
-	if (x2 == 0) { e.x0 = 0; e.x1 = 0; e.flen = (u32)K; }   // a base that does not occur (K == 1 only)
-	return e;
+	if (x2 == 0) return kb_ktab_pack(0, 0, 0, (u32)K);   // a base that does not occur (K == 1 only)
+	return kb_ktab_pack(x0, x1, x2, 0);
 }
-KB_HD KbKtab kb_load_ktab(const KbKtab* p)
+KB_HD KbKtabE kb_load_ktab(const KbKtab* p)
 {
 #if defined(__CUDA_ARCH__)
-	u32 r[8];
-	asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-	             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
-	KbKtab e; e.x0 = ((u64)r[1] << 32) | r[0]; e.x1 = ((u64)r[3] << 32) | r[2]; e.x2 = r[4]; e.flen = r[5]; e.pad = 0; return e;
+	u32 r[4];
+	asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "l"(p));
+	return kb_ktab_unpack(((u64)r[1] << 32) | r[0], ((u64)r[3] << 32) | r[2]);
 #else
-	return *p;
+	return kb_ktab_unpack(p->a, p->b);
 #endif
 }
 
@@ -390,7 +402,7 @@ KB_HD void kb_seed_read(const KbIndexDev& ix, const KbParams& pm, const KbBatchD
 				const KbPk w = kb_read_win(rd, pos);
 				if ((w.n4 >> (32 - K)) == 0)
 				{
-					const KbKtab e = kb_load_ktab(ix.ktab + (u32)(w.code >> (64 - 2 * K))); blocks++;
+					const KbKtabE e = kb_load_ktab(ix.ktab + (u32)(w.code >> (64 - 2 * K))); blocks++;
 					seeded = true;
 					if (e.x2 != 0) { x0 = (ROW)e.x0; x1 = (ROW)e.x1; x2 = (ROW)e.x2; cur = pos + K; steps += (u32)(K - 1); searching = true; }
 					else { closing = true; len = (int)e.flen; steps += e.flen; x2 = 0; }
@@ -537,7 +549,7 @@ KB_HD void kb_seed_lane(const KbIndexDev& ix, const KbParams& pm, const KbBatchD
 					const KbPk w = kb_read_win(rd, pos);
 					if ((w.n4 >> (32 - K)) == 0)
 					{
-						const KbKtab e = kb_load_ktab(ix.ktab + (u32)(w.code >> (64 - 2 * K))); blocks++;
+						const KbKtabE e = kb_load_ktab(ix.ktab + (u32)(w.code >> (64 - 2 * K))); blocks++;
 						seeded = true;
 						if (e.x2 != 0) { x0 = (ROW)e.x0; x1 = (ROW)e.x1; x2 = (ROW)e.x2; cur = pos + K; steps += (u32)(K - 1); searching = true; }
 						else { closing = true; len = (int)e.flen; steps += e.flen; x2 = 0; }

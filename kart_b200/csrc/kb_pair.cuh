@@ -223,13 +223,21 @@ KB_HD void kb_rf_pairs(KbRescueFast& w, int lane)
 	if (!w.ok || w.dirty) return;
 	const u64 M5 = 0x5555555555555555ull;
 	const int ml = w.ml, sl = w.slen, npos = sl - 7;
-	// Positions are dealt to the lanes round-robin, not in stretches: where the window does hold a copy of the mate (or of the
-	// repeat element the mate comes from) ~150 consecutive positions pass the filter, and almost all of them only to find that
-	// they continue a run; in stretches three or four lanes would do that one after the other while the rest idle (ncu r19:
+	// Positions are dealt to the lanes in small groups, not in long stretches: where the window does hold a copy of the mate (or of
+	// the repeat element the mate comes from) ~150 consecutive positions pass the filter, and almost all of them only to find that
+	// they continue a run; in stretches of 64 three or four lanes would do that one after the other while the rest idle (ncu r19:
 	// 30 % of the kernel at 2-4 lanes). The filter turns every other position away after one shared-memory load.
-	for (int g = lane; g < npos; g += 32)
+	// r21: dealt position by position, fetching the 8-mer (two shared-memory loads and a funnel shift) was half of the kernel's
+	// instructions. Positions are now dealt in groups of 8: one 32-base fetch serves the group's eight 8-mers out of a register, and a
+	// 150-position copy still spreads over 19 lanes.
+	const int ngroups = (npos + 7) >> 3;
+	for (int grp = lane; grp < ngroups; grp += 32)
 	{
-		const u32 id = (u32)(kb_rf_bits(w.wcode, g) >> 48);
+	u64 bits = kb_rf_bits(w.wcode, grp << 3);
+	const int gend = (grp << 3) + 8 < npos ? (grp << 3) + 8 : npos;
+	for (int g = grp << 3; g < gend; g++, bits <<= 2)
+	{
+		const u32 id = (u32)(bits >> 48);
 		const u32 h = kb_rf_fold(id);
 		if (((w.filt[h >> 5] >> (h & 31)) & 1u) == 0u) continue;
 		u32 s = kb_rj_slot(id, KB_RF_SLOTS - 1), key;
@@ -252,6 +260,7 @@ KB_HD void kb_rf_pairs(KbRescueFast& w, int lane)
 			const u32 slot = KB_ATOMIC_ADD(&w.npairs, 1u);
 			if (slot < (u32)KB_RF_PAIRS) { KbSeg sg; sg.simple = 1; sg.rpos = (i32)r; sg.gpos = (i64)g; sg.rlen = sg.glen = l; w.pairs[slot] = sg; }
 		}
+	}
 	}
 }
 // lane 0: the task's result (kb_rt_end), or the task's place on the slow list

@@ -40,8 +40,11 @@ struct KbParams
 	i32 paired;        // reads come as (mate1, revcomp(mate2)) pairs
 };
 
-// seeding table: state of BWT_Search after the first K bases (x2 > 0), or the length at which the search died (x2 == 0)
-struct __attribute__((aligned(32))) KbKtab { u64 x0, x1; u32 x2, flen; u64 pad; };
+// seeding table: state of BWT_Search after the first K bases (x2 > 0), or the length at which the search died (x2 == 0).
+// 16 bytes per entry, two entries per DRAM sector: a = x0 | (x2 & 0xFFFFFF) << 40, b = x1 | (x2 >> 24) << 40 (row numbers below 2^40);
+// a dead search has a = 0 and the length in b. KbKtabE is the unpacked form.
+struct __attribute__((aligned(16))) KbKtab { u64 a, b; };
+struct KbKtabE { u64 x0, x1, x2; u32 flen; };
 
 struct KbIndexDev
 {

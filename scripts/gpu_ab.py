@@ -16,10 +16,11 @@ ap.add_argument("--prefix", default=None)
 ap.add_argument("--error", type=float, default=0.02)
 ap.add_argument("--lib", default=None)
 ap.add_argument("--reps", type=int, default=4)
+ap.add_argument("--no-e2e", action="store_true")
 ap.add_argument("configs", nargs="+")
 a = ap.parse_args()
 prefix = a.prefix or pu.default_prefix()
-idx = KartIndex(prefix); g = pu.genome_of(idx)
+idx = KartIndex(prefix); g = pu.pac_genome(idx) if idx.l_pac > 500_000_000 else pu.genome_of(idx)
 r1, r2, _ = synth.simulate(g, a.pairs, 150, a.error, seed=1)
 reads = pu.interleave(r1, r2); n = reads.shape[0]
 seq_pin = torch.empty(reads.size, dtype=torch.uint8).pin_memory(); seq_pin.numpy()[:] = reads.reshape(-1)
@@ -45,9 +46,9 @@ for spec in a.configs:
         m.run()
         for k, v in m.stage_ms().items(): st[k] = st.get(k, 0.0) + v / a.reps
     torch.cuda.synchronize(); dev = (time.perf_counter() - t) / a.reps
-    for _ in range(2): aln, pr, cig = m.map_chunk(flat, off, est, out=out)
+    for _ in range(1 if a.no_e2e else 2): aln, pr, cig = m.map_chunk(flat, off, est, out=out)
     torch.cuda.synchronize(); t = time.perf_counter()
-    for _ in range(a.reps): aln, pr, cig = m.map_chunk(flat, off, est, out=out)
+    for _ in range(0 if a.no_e2e else a.reps): aln, pr, cig = m.map_chunk(flat, off, est, out=out)
     torch.cuda.synchronize(); e2e = (time.perf_counter() - t) / a.reps
     sig = (int(aln["pos"].sum()), int(aln["score"].sum()), int(aln["flag"].sum()), int(aln["cig_len"].sum()), int(aln["mapq"].sum()))
     if ref_sig is None: ref_sig = sig
