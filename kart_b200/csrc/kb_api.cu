@@ -331,7 +331,13 @@ __global__ void __launch_bounds__(KB_BLOCK) k_rescue_commit(KbIndexDev ix, KbPar
 {
 	if (bt.counters[3]) return;
 	const int count = (int)bt.counters[4];
-	for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) kb_rescue_commit(pm, bt, k);
+	u32 attempted = 0;
+	for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) kb_rescue_commit(pm, bt, k, &attempted);
+#ifndef KB_EMUL
+	for (int o = 16; o > 0; o >>= 1) attempted += __shfl_down_sync(0xFFFFFFFFu, attempted, o);
+	if ((threadIdx.x & 31) != 0) attempted = 0;
+#endif
+	if (attempted) KB_ATOMIC_ADD(&bt.counters[7], attempted);
 }
 // KB_RESCUE_FAST=0: every window on the slow list
 __global__ void __launch_bounds__(KB_BLOCK) k_rescue_all_slow(KbBatchDev bt)
@@ -615,10 +621,29 @@ __global__ void __launch_bounds__(KB_BLOCK) k_align_gather(KbBatchDev bt)
 }
 __global__ void __launch_bounds__(KB_BLOCK) k_assemble(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_assemble(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x); }
 __global__ void __launch_bounds__(KB_BLOCK) k_assemble_slow(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_assemble_slow(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
+// The records of a block's items are one contiguous stretch of `aln` (56 bytes each, what one SAM line needs). Written field by field from
+// a thread per pair that is 12 four- and eight-byte stores per record, every one of them touching 32 different sectors per warp; the block
+// therefore assembles its records in shared memory and copies the stretch out with 16-byte stores.
 __global__ void __launch_bounds__(KB_BLOCK) k_finalize(KbIndexDev ix, KbParams pm, KbBatchDev bt, kb_aln_t* aln)
 {
 	if (blockIdx.x == 0 && threadIdx.x == 0) bt.counters[31] = KB_ATOMIC_ADD(bt.cig_cursor, 0u);
-	kb_stage_finalize(ix, pm, bt, aln, blockIdx.x * blockDim.x + threadIdx.x);
+	const int t = blockIdx.x * blockDim.x + threadIdx.x, per = pm.paired ? 2 : 1, items = pm.paired ? (bt.n_reads >> 1) : bt.n_reads;
+#ifndef KB_EMUL
+	__shared__ __align__(16) kb_aln_t st[2 * KB_BLOCK];
+	// (a batch that overflowed an arena is rerun as a whole: kb_stage_finalize then leaves the records alone and what is copied out is never looked at)
+	if (t < items) kb_stage_finalize(ix, pm, bt, st + per * (int)threadIdx.x, t);
+	__syncthreads();
+	const int t0 = blockIdx.x * blockDim.x, nrec = per * (items - t0 < (int)blockDim.x ? items - t0 : (int)blockDim.x);
+	if (nrec <= 0) return;
+	static_assert(sizeof(kb_aln_t) % 8 == 0, "kb_aln_t is copied in 8-byte words");
+	const size_t base = (size_t)per * (size_t)t0 * sizeof(kb_aln_t);   // a multiple of 16: the block size is even
+	const int nbytes = nrec * (int)sizeof(kb_aln_t), n16 = nbytes >> 4;
+	const uint4* src = reinterpret_cast<const uint4*>(st); uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<u8*>(aln) + base);
+	for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
+	if ((nbytes & 15) && threadIdx.x == 0) reinterpret_cast<u64*>(reinterpret_cast<u8*>(aln) + base)[2 * n16] = reinterpret_cast<const u64*>(st)[2 * n16];
+#else
+	if (t < items) kb_stage_finalize(ix, pm, bt, aln + (size_t)per * (size_t)t, t);
+#endif
 }
 
 // ---- stage-level test entry (kb_debug_align): caller-chosen fragment pairs through classification, phase B and the per-segment
@@ -1246,7 +1271,8 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 	if (pm.paired)
 	{
 		unsigned rt = (unsigned)ctx->rescue_threads, g = (unsigned)bt.scratch_threads / rt; if (g > 148u * 32u) g = 148u * 32u;
-		KB_LAUNCH(k_rescue_plan, 148 * 4, KB_BLOCK, s, ix, pm, bt); sl.launches++;
+		const unsigned g_jobs = g_items < 148u * 16u ? g_items : 148u * 16u;   // thread per rescue job, each a chain of dependent loads: as many in flight as there may be jobs
+		KB_LAUNCH(k_rescue_plan, g_jobs, KB_BLOCK, s, ix, pm, bt); sl.launches++;
 		if (ctx->rescue_fast)
 		{
 #ifndef KB_EMUL
@@ -1258,7 +1284,7 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 		}
 		else { KB_LAUNCH(k_rescue_all_slow, 148 * 4, KB_BLOCK, s, bt); sl.launches++; }
 		KB_LAUNCH(k_rescue_win, g, rt, s, ix, pm, bt); sl.launches++;
-		KB_LAUNCH(k_rescue_commit, 148 * 4, KB_BLOCK, s, ix, pm, bt); sl.launches++;
+		KB_LAUNCH(k_rescue_commit, g_jobs, KB_BLOCK, s, ix, pm, bt); sl.launches++;
 	}
 	CK(cudaEventRecord(sl.ev[4], s));
 	KB_LAUNCH(k_segments, g_reads, KB_BLOCK, s, ix, pm, bt, ctx->seg_slab); sl.launches++;

@@ -395,7 +395,7 @@ KB_HD void kb_rt_end(const KbParams& pm, const KbBatchDev& bt, KbRescueJob* j, K
 	t->score = score; t->diff = c.diff; t->seg_start = c.seg_start; t->nseg = c.nseg;
 }
 // thread per rescue job: AlignmentRescue.cpp:125-130 / :160-165 over the job's tasks, then what follows in ReadMapping (Mapping.cpp:561-563)
-KB_HD void kb_rescue_commit(const KbParams& pm, const KbBatchDev& bt, int k)
+KB_HD void kb_rescue_commit(const KbParams& pm, const KbBatchDev& bt, int k, u32* n_attempted)
 {
 	const int p = bt.rescue_list[k], ra = 2 * p, rb = ra + 1;
 	const int n1o = bt.n_cands[ra], n2o = bt.n_cands[rb];
@@ -416,7 +416,7 @@ KB_HD void kb_rescue_commit(const KbParams& pm, const KbBatchDev& bt, int k)
 	bt.n_cands[ra] = n1; bt.n_cands[rb] = n2;
 	if (attempted)
 	{
-		KB_ATOMIC_ADD(&bt.counters[7], 1u);
+		*n_attempted += 1;   // counters[7], added up per warp by the kernel (one same-address atomic per job was most of k_rescue_commit)
 		KbPairStat& st = bt.pstat[p]; int est = bt.est[p];
 		if (est >= pm.max_insert) { if (st.est_lo < pm.max_insert) st.est_lo = pm.max_insert; }
 		else { st.est_lo = est; st.est_hi = est; }

@@ -235,6 +235,7 @@ KB_HD void kb_emit_extra(const KbBatchDev& bt, int r, const KbReadRes& rd, const
 	}
 }
 
+// aln: where this item's records go -- aln[0] and aln[1] for a pair, aln[0] for a single read (the kernel stages them in shared memory)
 KB_HD void kb_stage_finalize(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, kb_aln_t* aln, int t)
 {
 	if (bt.counters[3]) return;
@@ -249,12 +250,12 @@ KB_HD void kb_stage_finalize(const KbIndexDev& ix, const KbParams& pm, const KbB
 		{   // read 1 line (:194-221)
 			const KbReport& a = p1[r1.best]; int j = a.mate; bool ok = r1.score > 0 && a.aln > 0 && j != -1 && p2[j].aln > 0;
 			int dist = ok ? (int)(p2[j].pos - a.pos + (a.fwd ? l2 : 0 - l1)) : 0;
-			kb_fill_aln(aln[ra], r1, p1, ok ? &p2[j] : nullptr, ok, dist);
+			kb_fill_aln(aln[0], r1, p1, ok ? &p2[j] : nullptr, ok, dist);
 		}
 		{   // read 2 line (:242-261)
 			const KbReport& b = p2[r2.best]; int i = b.mate; bool ok = r2.score > 0 && b.aln > 0 && i != -1 && p1[i].aln > 0;
 			int dist = ok ? 0 - (int)(b.pos - p1[i].pos + (p1[i].fwd ? l2 : 0 - l1)) : 0;
-			kb_fill_aln(aln[rb], r2, p2, ok ? &p1[i] : nullptr, ok, dist);
+			kb_fill_aln(aln[1], r2, p2, ok ? &p1[i] : nullptr, ok, dist);
 		}
 		if (pm.multihit) { kb_emit_extra(bt, ra, r1, p1, p2, l1, l2, 1); kb_emit_extra(bt, rb, r2, p2, p1, l1, l2, 2); }
 	}
@@ -263,8 +264,8 @@ KB_HD void kb_stage_finalize(const KbIndexDev& ix, const KbParams& pm, const KbB
 		if (t >= bt.n_reads) return;
 		kb_finalize_single(ix, pm, bt, t);
 		const KbReadRes& rd = bt.res[t]; const KbReport* rep = bt.reports + rd.rep_off;
-		kb_fill_aln(aln[t], rd, rep, nullptr, false, 0);
-		if (rd.score > 0 && rep[rd.best].aln != rd.score) aln[t].kind = 2;   // OutputSingledAlignments prints reports with AlnScore == score (:293)
+		kb_fill_aln(aln[0], rd, rep, nullptr, false, 0);
+		if (rd.score > 0 && rep[rd.best].aln != rd.score) aln[0].kind = 2;   // OutputSingledAlignments prints reports with AlnScore == score (:293)
 		if (pm.multihit) kb_emit_extra(bt, t, rd, rep, nullptr, 0, 0, 0);
 	}
 }
