@@ -16,22 +16,24 @@ ap.add_argument("--prefixes", default=",".join([pu.ECOLI_PREFIX, os.path.join(RO
 ap.add_argument("--ref-se", type=int, default=200000)
 ap.add_argument("--ref-pb", type=int, default=2000)
 ap.add_argument("--check", type=int, default=200, help="reads compared with the oracle per mode")
+ap.add_argument("--modes", default="se100,pacbio")
+ap.add_argument("--reps", type=int, default=3)
 a = ap.parse_args()
 ncores = os.cpu_count() or 1
 for prefix in a.prefixes.split(","):
     if not os.path.exists(prefix + ".bwt"):
         continue
-    idx = KartIndex(prefix); g = pu.genome_of(idx)
+    idx = KartIndex(prefix); g = pu.pac_genome(idx) if idx.l_pac > 500_000_000 else pu.genome_of(idx)
     m = Mapper(); m.upload_index(idx, expand_sa=True)
     for mode, n, L, err, kw, nref in (("se100", a.se, 100, 0.08, {}, a.ref_se), ("pacbio", a.pb, a.pblen, 0.15, dict(indel=0.01), a.ref_pb)):
-        if n <= 0:
+        if n <= 0 or mode not in a.modes.split(","):
             continue
         r, _, pos = synth.simulate(g, n, L, err, seed=3, paired=False, **kw)
         flat, off = Mapper.pack_reads(r)
         m.set_params(pacbio=(mode == "pacbio"), paired=False)
         m.stage(flat, off)
         m.run()
-        t = time.perf_counter(); reps = 3
+        t = time.perf_counter(); reps = a.reps
         st = {}
         for _ in range(reps):
             m.run()
