@@ -74,6 +74,20 @@ struct ReadBatch
 	void clear() { seq.clear(); seq_off.assign(1, 0); qual.clear(); names.clear(); name_off.assign(1, 0); }
 };
 
+// One input file behind a gzread-like call. Plain and ordinary gzip files go through zlib's gzFile (one inflate stream: a gzip
+// stream has no block boundaries to split at). A file that is a chain of BGZF blocks (bgzip / htslib: self-contained deflate members
+// of at most 64 KB, each announcing its compressed size in a "BC" extra field) is mapped, and read() inflates as many whole blocks as
+// fit the request on `threads` workers, checking every block's CRC-32 and length like gzread does (the reference reads .gz input through
+// gzgets on one thread, src/GetData.cpp:184-219).
+struct GzInput
+{
+	gzFile fp = nullptr;
+	const uint8_t* map = nullptr; size_t map_len = 0, at = 0; std::vector<char> carry; size_t carry_pos = 0; int threads = 1; bool bgzf = false, failed = false;
+	bool open(const char* path, int n_threads);
+	int read(char* dst, unsigned n);      // bytes delivered (possibly fewer than n), 0 at the end of the input, < 0 on a damaged file
+	void close();
+};
+
 // FASTA / FASTQ (plain or .gz) input with the reference's parsing rules. FASTQ goes through a block reader: every stream
 // buffers a large piece of (decompressed) text, newline positions are indexed by `threads` workers, and the records are
 // parsed and copied into the batch by the same workers (read_input.cpp). FASTA keeps the entry-at-a-time path.
@@ -88,7 +102,7 @@ public:
 	int fill_serial(ReadBatch& b, int max_reads, bool pair_end);       // entry-at-a-time path (FASTA; and the cross-check of the block path in tests)
 	struct Stream
 	{
-		gzFile fp = nullptr; std::vector<char> buf; size_t pos = 0, end = 0; bool eof = false; std::string pending; bool has_pending = false;
+		GzInput in; std::vector<char> buf; size_t pos = 0, end = 0; bool eof = false; std::string pending; bool has_pending = false;
 		// block path: text[lo, hi) is buffered, nl[] holds the offsets of the newlines in it, rec = lines already consumed
 		HBuf<char> text; size_t lo = 0, hi = 0; HBuf<uint32_t> nl; size_t nl_used = 0; bool drained = false;
 	};

@@ -7,6 +7,9 @@
 #include <thread>
 #include <stdlib.h>
 #include <sys/mman.h>
+#include <sys/stat.h>
+#include <fcntl.h>
+#include <unistd.h>
 
 static size_t KB_IO_CHUNK = 32u << 20;             // bytes per gzread (KART_B200_IO_CHUNK overrides it: the tests use tiny chunks to exercise refills)
 
@@ -15,18 +18,133 @@ static inline char comp_base(char c)   // GetComplementaryBase, src/tools.cpp:3
 	switch (c) { case 'A': case 'a': return 'T'; case 'C': case 'c': return 'G'; case 'G': case 'g': return 'C'; case 'T': case 't': return 'A'; default: return 'N'; }
 }
 
+// ---- GzInput ---------------------------------------------------------------------------------------------------------
+// BGZF block at `o`: gzip member header with FEXTRA whose extra field holds the subfield 'B','C',2,<block size - 1>. Returns the
+// block's size (0: not a BGZF block) and where its deflate data starts.
+static size_t bgzf_block(const uint8_t* m, size_t len, size_t o, size_t* data_off)
+{
+	if (o + 18 > len || m[o] != 0x1f || m[o + 1] != 0x8b || m[o + 2] != 8 || !(m[o + 3] & 4)) return 0;
+	const size_t xlen = (size_t)m[o + 10] | ((size_t)m[o + 11] << 8);
+	if (o + 12 + xlen > len) return 0;
+	size_t bsize = 0;
+	for (size_t p = o + 12; p + 4 <= o + 12 + xlen;)
+	{
+		const size_t slen = (size_t)m[p + 2] | ((size_t)m[p + 3] << 8);
+		if (m[p] == 'B' && m[p + 1] == 'C' && slen == 2 && p + 6 <= o + 12 + xlen) bsize = ((size_t)m[p + 4] | ((size_t)m[p + 5] << 8)) + 1;
+		p += 4 + slen;
+	}
+	if ((m[o + 3] & ~4) != 0) return 0;   // a name / comment / header CRC in front of the data: not what bgzip writes, leave it to zlib
+	if (bsize < 12 + xlen + 8 || o + bsize > len) return 0;
+	*data_off = o + 12 + xlen;
+	return bsize;
+}
+bool GzInput::open(const char* path, int n_threads)
+{
+	close();
+	threads = n_threads < 1 ? 1 : n_threads;
+	int fd = ::open(path, O_RDONLY);
+	if (fd >= 0)
+	{
+		struct stat st;
+		if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size >= 28 && !getenv("KART_B200_NO_BGZF"))
+		{
+			void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+			if (m != MAP_FAILED)
+			{
+				// the whole file must be one chain of BGZF blocks; anything else (plain text, ordinary gzip, trailing bytes) is zlib's
+				const uint8_t* mm = (const uint8_t*)m; size_t o = 0, d;
+				while (o < (size_t)st.st_size) { const size_t b = bgzf_block(mm, (size_t)st.st_size, o, &d); if (!b) break; o += b; }
+				if (o == (size_t)st.st_size) { map = mm; map_len = o; at = 0; bgzf = true; madvise(m, map_len, MADV_SEQUENTIAL); }
+				else munmap(m, (size_t)st.st_size);
+			}
+		}
+		::close(fd);
+	}
+	if (bgzf) return true;
+	fp = gzopen(path, "rb");
+	if (!fp) return false;
+	gzbuffer(fp, 1 << 20);
+	return true;
+}
+void GzInput::close()
+{
+	if (fp) gzclose(fp);
+	if (map) munmap((void*)map, map_len);
+	fp = nullptr; map = nullptr; map_len = at = 0; carry.clear(); carry_pos = 0; bgzf = false; failed = false;
+}
+static bool bgzf_inflate(const uint8_t* m, size_t data_off, size_t block_end, char* dst, size_t isize)
+{
+	const uint8_t* tail = m + block_end - 8;
+	const uint32_t crc = (uint32_t)tail[0] | ((uint32_t)tail[1] << 8) | ((uint32_t)tail[2] << 16) | ((uint32_t)tail[3] << 24);
+	z_stream zs; memset(&zs, 0, sizeof(zs));
+	if (inflateInit2(&zs, -15) != Z_OK) return false;
+	zs.next_in = (Bytef*)(m + data_off); zs.avail_in = (uInt)(block_end - 8 - data_off);
+	zs.next_out = (Bytef*)dst; zs.avail_out = (uInt)isize;
+	const int rc = inflate(&zs, Z_FINISH);
+	const bool ok = rc == Z_STREAM_END && zs.avail_out == 0;
+	inflateEnd(&zs);
+	return ok && (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const Bytef*)dst, (uInt)isize) == crc;
+}
+int GzInput::read(char* dst, unsigned n)
+{
+	if (!bgzf) return fp ? gzread(fp, dst, n) : -1;
+	if (failed) return -1;
+	if (carry_pos < carry.size())
+	{
+		const size_t k = std::min((size_t)n, carry.size() - carry_pos);
+		memcpy(dst, carry.data() + carry_pos, k); carry_pos += k;
+		return (int)k;
+	}
+	// as many whole blocks as fit into n bytes
+	struct Blk { size_t data, end, out, isize; };
+	std::vector<Blk> blk; size_t total = 0;
+	while (at < map_len && blk.size() < 65536)
+	{
+		size_t d; const size_t b = bgzf_block(map, map_len, at, &d);
+		const uint8_t* t = map + at + b - 4;
+		const size_t isize = (size_t)t[0] | ((size_t)t[1] << 8) | ((size_t)t[2] << 16) | ((size_t)t[3] << 24);
+		if (isize == 0) { at += b; continue; }                 // empty blocks (the end-of-file marker) hold nothing
+		if (total + isize > (size_t)n) break;
+		blk.push_back({d, at + b, total, isize}); total += isize; at += b;
+	}
+	if (blk.empty())
+	{
+		if (at >= map_len) return 0;
+		// the next block is larger than the request: through the carry buffer
+		size_t d; const size_t b = bgzf_block(map, map_len, at, &d);
+		const uint8_t* t = map + at + b - 4;
+		const size_t isize = (size_t)t[0] | ((size_t)t[1] << 8) | ((size_t)t[2] << 16) | ((size_t)t[3] << 24);
+		carry.resize(isize); carry_pos = 0;
+		if (!bgzf_inflate(map, d, at + b, carry.data(), isize)) { carry.clear(); failed = true; return -1; }
+		at += b;
+		return read(dst, n);
+	}
+	std::atomic<size_t> first_bad{blk.size()};
+	parallel_for(threads, blk.size(), [&](int, size_t lo, size_t hi) {
+		for (size_t i = lo; i < hi; i++)
+			if (!bgzf_inflate(map, blk[i].data, blk[i].end, dst + blk[i].out, blk[i].isize)) { size_t cur = first_bad.load(); while (i < cur && !first_bad.compare_exchange_weak(cur, i)) {} }
+	});
+	if (first_bad.load() == blk.size()) return (int)total;
+	// a damaged block: what lies in front of it is delivered (gzread does the same), then the input has ended in an error
+	at = map_len; failed = true;
+	const size_t good = blk[first_bad.load()].out;
+	return good ? (int)good : -1;
+}
+
 bool ReadSource::open(const char* f1, const char* f2)
 {
 	{ gzFile t = gzopen(f1, "rb"); if (!t) return false; char c = 0; gzread(t, &c, 1); gzclose(t); fastq = (c == '@'); }   // CheckReadFormat :8
-	for (Stream* s : {&s1, &s2}) { s->fp = nullptr; s->pos = s->end = 0; s->eof = false; s->pending.clear(); s->has_pending = false; s->lo = s->hi = 0; s->nl.clear(); s->nl_used = 0; s->drained = false; }
+	for (Stream* s : {&s1, &s2}) { s->in.close(); s->pos = s->end = 0; s->eof = false; s->pending.clear(); s->has_pending = false; s->lo = s->hi = 0; s->nl.clear(); s->nl_used = 0; s->drained = false; }
 	two = f2 != nullptr;
 	{ const char* e = getenv("KART_B200_IO_CHUNK"); if (e && atol(e) >= 16) KB_IO_CHUNK = (size_t)atol(e); }
-	s1.fp = gzopen(f1, "rb"); if (!s1.fp) return false; gzbuffer(s1.fp, 1 << 20); s1.buf.resize(1 << 22);
-	if (two) { s2.fp = gzopen(f2, "rb"); if (!s2.fp) { gzclose(s1.fp); s1.fp = nullptr; return false; } gzbuffer(s2.fp, 1 << 20); s2.buf.resize(1 << 22); }
+	const int per = threads > 1 && two ? (threads + 1) / 2 : threads;
+	if (!s1.in.open(f1, per)) return false;
+	s1.buf.resize(1 << 22);
+	if (two) { if (!s2.in.open(f2, per)) { s1.in.close(); return false; } s2.buf.resize(1 << 22); }
 	return true;
 }
 
-void ReadSource::close() { if (s1.fp) gzclose(s1.fp); if (s2.fp) gzclose(s2.fp); s1.fp = s2.fp = nullptr; }
+void ReadSource::close() { s1.in.close(); s2.in.close(); }
 
 bool ReadSource::line(Stream& s, std::string& out)   // one line including its '\n' (getline semantics)
 {
@@ -37,7 +155,7 @@ bool ReadSource::line(Stream& s, std::string& out)   // one line including its '
 		if (s.pos == s.end)
 		{
 			if (s.eof) return !out.empty();
-			int got = gzread(s.fp, s.buf.data(), (unsigned)s.buf.size());
+			int got = s.in.read(s.buf.data(), (unsigned)s.buf.size());
 			if (got <= 0) { s.eof = true; return !out.empty(); }
 			s.pos = 0; s.end = (size_t)got;
 		}
@@ -164,7 +282,7 @@ size_t ReadSource::buffer_records(Stream& s, size_t want)
 		}
 		if (s.hi + KB_IO_CHUNK > 0xFFFFFF00u) { s.drained = true; continue; }      // an "entry" beyond 4 GB: give up on the stream like a read error
 		s.text.n = s.hi; if (s.text.cap < s.hi + KB_IO_CHUNK) s.text.reserve(std::max(s.hi + KB_IO_CHUNK, std::min((size_t)KB_IO_MAX_TEXT, want * 512) + 2 * KB_IO_CHUNK));
-		int got = gzread(s.fp, s.text.data() + s.hi, (unsigned)KB_IO_CHUNK);
+		int got = s.in.read(s.text.data() + s.hi, (unsigned)KB_IO_CHUNK);
 		if (got <= 0) { s.drained = true; continue; }
 		index_newlines(s, s.hi, s.hi + (size_t)got, threads > 1 && two ? (threads + 1) / 2 : threads);
 		s.hi += (size_t)got;

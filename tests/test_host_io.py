@@ -83,3 +83,44 @@ def test_block_reader_gz_and_many_refills(io_check, tmp_path):
     assert want.count(b"\n") == 6000 + 12
     for threads, chunk in ((4, 4096), (8, 333), (2, None)):
         assert run(io_check, "blocks", threads, 512, 1, [f1, f2], chunk) == want
+
+
+def bgzf_bytes(data: bytes, block: int = 60000, level: int = 6) -> bytes:
+    """The container bgzip / htslib write: self-contained gzip members of at most 64 KB with a 'BC' extra field, then the empty end marker."""
+    import struct
+    import zlib
+    out = []
+    for at in list(range(0, len(data), block)) + [None]:
+        piece = b"" if at is None else data[at:at + block]
+        c = zlib.compressobj(level, zlib.DEFLATED, -15)
+        body = c.compress(piece) + c.flush()
+        bsize = 18 + len(body) + 8
+        out.append(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", bsize - 1) + body + struct.pack("<II", zlib.crc32(piece) & 0xFFFFFFFF, len(piece)))
+    return b"".join(out)
+
+
+def test_bgzf_input_is_inflated_in_parallel_and_equals_plain(io_check, tmp_path):
+    """A chain of BGZF blocks goes through GzInput's parallel inflate; the batches must equal the ones of the same text read plainly, whatever
+    the request size (requests smaller than a block use the carry buffer) and the worker count; a damaged block ends the input like gzread."""
+    a, b = fq(4000, 41, L=(30, 200)), fq(4000, 42, L=(30, 200))
+    p1, p2 = str(tmp_path / "a.fq"), str(tmp_path / "b.fq")
+    z1, z2 = str(tmp_path / "a.fq.gz"), str(tmp_path / "b.fq.gz")
+    for f, d in ((p1, a), (p2, b)):
+        open(f, "wb").write(d)
+    for f, d, blk in ((z1, a, 60000), (z2, b, 777)):
+        open(f, "wb").write(bgzf_bytes(d, blk))
+    assert gzip.open(z1, "rb").read() == a and gzip.open(z2, "rb").read() == b   # valid gzip for everybody else
+    want = run(io_check, "serial", 1, 512, 1, [p1, p2])
+    assert want.count(b"\n") == 8000 + 16
+    for threads, chunk in ((4, 4096), (8, 333), (2, None), (1, 100000)):
+        assert run(io_check, "blocks", threads, 512, 1, [z1, z2], chunk) == want
+    assert run(io_check, "serial", 3, 512, 1, [z1, z2]) == want
+    env = dict(os.environ, KART_B200_NO_BGZF="1")   # the same files through zlib's gzread
+    assert subprocess.run([io_check, "blocks", "4", "512", "1", z1, z2], capture_output=True, env=env, check=True).stdout == want
+    # damage one block's payload: the reader must stop there (CRC / inflate error), not deliver garbage
+    raw = bytearray(open(z1, "rb").read()); raw[len(raw) // 2] ^= 0x55
+    bad = str(tmp_path / "bad.fq.gz"); open(bad, "wb").write(bytes(raw))
+    good = run(io_check, "blocks", 4, 512, 0, [z1]).split(b"\n")
+    got = run(io_check, "blocks", 4, 512, 0, [bad]).split(b"\n")
+    reads = lambda lines: [ln for ln in lines if ln.startswith(b"[")]
+    assert 100 < len(reads(got)) < len(reads(good)) and reads(got)[:-1] == reads(good)[:len(reads(got)) - 1]   # everything in front of the damage, nothing made up behind it
