@@ -491,18 +491,24 @@ struct KbSink
 struct KbFragIter
 {
 	const KbParams* pm; KbArena* ar; KbArena* fast; const u8* f1; const u8* f2; KbSink* sink;
-	KbWorkP* st; int sp, scap;
+	// Work stack: worst case rl0 + gl0 + 4 entries, in practice a handful. The first `sfast` entries are tried in the warp's shared-memory
+	// pool, the rest lives in the HBM arena (r23: with the whole stack in front of them, the 8-mer id arrays of every fragment beyond
+	// ~100 x 100 ended up in HBM, where part_pairs reads them n1 x (2 shift + 1) times).
+	KbWorkP* st; KbWorkP* st2; int sp, scap, sfast;
+	KB_HD KbWorkP& slot(int i) { return i < sfast ? st[i] : st2[i - sfast]; }
 	// the fragment being partitioned (between next() == 2 and part_finish())
-	KbWork cur; u32* w1; u32* w2; KbSeg* raw; int shift, cap, dirty; u32 np; u64 pmark, fmark;
+	KbWork cur; u32* w1; u32* w2; KbSeg* raw; int shift, cap, cap_full, dirty; u32 np; u64 pmark, fmark;
 
 	// fast_: the warp's shared-memory pool, used for whatever fits; ar_: its arena in HBM
 	KB_HD bool init(const KbParams* pm_, KbArena* fast_, KbArena* ar_, const u8* f1_, int rl0, const u8* f2_, int gl0, KbSink* sink_)
 	{
 		pm = pm_; ar = ar_; fast = fast_; f1 = f1_; f2 = f2_; sink = sink_; sp = 0;
 		scap = rl0 + gl0 + 4;
-		st = (KbWorkP*)kb_alloc2(*fast, *ar, (u64)scap * sizeof(KbWorkP));
-		if (st == nullptr) return false;
-		KbWork w; w.r0 = 0; w.rl = rl0; w.g0 = 0; w.gl = gl0; w.kind = KB_W_FRAG; w.pad = 0; st[sp++] = kb_work_pack(w);
+		sfast = sink_->bt->part_stack > 0 && sink_->bt->part_stack < scap ? sink_->bt->part_stack : scap;
+		st = (KbWorkP*)kb_alloc2(*fast, *ar, (u64)sfast * sizeof(KbWorkP));
+		st2 = scap > sfast ? (KbWorkP*)ar->alloc((u64)(scap - sfast) * sizeof(KbWorkP)) : nullptr;
+		if (st == nullptr || (scap > sfast && st2 == nullptr)) return false;
+		KbWork w; w.r0 = 0; w.rl = rl0; w.g0 = 0; w.gl = gl0; w.kind = KB_W_FRAG; w.pad = 0; slot(sp++) = kb_work_pack(w);
 		return true;
 	}
 
@@ -512,7 +518,7 @@ struct KbFragIter
 	{
 		while (sp > 0 && !ar->ovf && !sink->ovf)
 		{
-			const KbWork e = kb_work_unpack(st[--sp]);
+			const KbWork e = kb_work_unpack(slot(--sp));
 			const u8* a = f1 + e.r0; const u8* b = f2 + e.g0;
 			if (e.kind == KB_W_INS) { sink->lit(KB_RUN_I, e.rl, e.rl); continue; }
 			if (e.kind == KB_W_DEL) { sink->lit(KB_RUN_D, e.gl, e.gl); continue; }
@@ -529,8 +535,11 @@ struct KbFragIter
 				else shift = pm->max_gaps;
 				pmark = ar->used; fmark = fast->used;
 				w1 = (u32*)kb_alloc2(*fast, *ar, (u64)rl * 4); w2 = (u32*)kb_alloc2(*fast, *ar, (u64)gl * 4);
-				cap = ((rl < gl ? rl : gl) / 9 + 2) * (2 * shift + 1);   // exact-match runs on one diagonal start >= 9 apart
-				if (cap > rl + gl) cap = rl + gl;
+				cap_full = ((rl < gl ? rl : gl) / 9 + 2) * (2 * shift + 1);   // exact-match runs on one diagonal start >= 9 apart
+				if (cap_full > rl + gl) cap_full = rl + gl;
+				// that bound is hundreds of entries, a fragment usually has a handful of runs: a short list (in the pool when it fits) first,
+				// part_grow() switches to the full one in HBM when the runs did not fit
+				cap = sink->bt->part_raw > 0 && sink->bt->part_raw < cap_full ? sink->bt->part_raw : cap_full;
 				raw = (KbSeg*)kb_alloc2(*fast, *ar, (u64)cap * sizeof(KbSeg));
 				if (ar->ovf) return 0;
 				cur = e; np = 0; dirty = 0;
@@ -581,6 +590,16 @@ struct KbFragIter
 			if ((int)slot < cap) { KbSeg sg; sg.simple = 1; sg.rpos = r; sg.gpos = (i64)g; sg.rlen = sg.glen = 8 + run - 1; raw[slot] = sg; }
 		}
 	}
+	// one lane, after part_pairs: true when the runs did not fit the short list -- the full-size list is then in place (HBM arena) and
+	// part_pairs has to run again
+	KB_HD bool part_grow()
+	{
+		if ((int)np <= cap || cap >= cap_full) return false;
+		raw = (KbSeg*)ar->alloc((u64)cap_full * sizeof(KbSeg));
+		if (ar->ovf) return false;
+		cap = cap_full; np = 0;
+		return true;
+	}
 	// one lane: IdentifyNormalPairs on the runs; pushes the pieces, or registers the whole fragment as one nw_alignment problem
 	KB_HD void part_finish()
 	{
@@ -608,7 +627,7 @@ struct KbFragIter
 				else if ((p.rlen == 1 && p.glen == 1) || p.simple) w.kind = KB_W_COPY;
 				else if (pm->pacbio && (p.rlen > 300 || p.glen > 300)) w.kind = KB_W_FRAG;
 				else w.kind = KB_W_NW;
-				st[sp++] = kb_work_pack(w);
+				slot(sp++) = kb_work_pack(w);
 			}
 			ar->used = pmark; fast->used = fmark;
 			return;

@@ -491,6 +491,9 @@ __global__ void __launch_bounds__(KB_BLOCK) k_align_part(KbIndexDev ix, KbParams
 			w.it.part_scan(lane); __syncwarp();
 			w.it.part_ids(lane); __syncwarp();
 			w.it.part_pairs(lane); __syncwarp();
+			if (lane == 0) w.state = w.it.part_grow() ? 3 : 2;
+			__syncwarp();
+			if (w.state == 3) { w.it.part_pairs(lane); __syncwarp(); }
 			if (lane == 0) w.it.part_finish();
 			__syncwarp();
 		}
@@ -563,6 +566,7 @@ static void k_align_part(KbIndexDev ix, KbParams pm, KbBatchDev bt, int)   // em
 			for (int t = 0; t < 32; t++) w.it.part_scan(t);
 			for (int t = 31; t >= 0; t--) w.it.part_ids(t);
 			for (int t = 31; t >= 0; t--) w.it.part_pairs(t);
+			if (w.it.part_grow()) for (int t = 31; t >= 0; t--) w.it.part_pairs(t);
 			w.it.part_finish();
 		}
 		kb_pt_end(bt, w);
@@ -621,29 +625,14 @@ __global__ void __launch_bounds__(KB_BLOCK) k_align_gather(KbBatchDev bt)
 }
 __global__ void __launch_bounds__(KB_BLOCK) k_assemble(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_assemble(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x); }
 __global__ void __launch_bounds__(KB_BLOCK) k_assemble_slow(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_assemble_slow(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
-// The records of a block's items are one contiguous stretch of `aln` (56 bytes each, what one SAM line needs). Written field by field from
-// a thread per pair that is 12 four- and eight-byte stores per record, every one of them touching 32 different sectors per warp; the block
-// therefore assembles its records in shared memory and copies the stretch out with 16-byte stores.
+// (r23: assembling a block's records in shared memory and copying them out in 16-byte words made this kernel slower, 0.98 -> 1.27 ms per
+// 2.5 M reads: it is bound by the latency of its scattered report reads, and the barrier in front of the copy-out makes every warp wait
+// for the block's slowest thread. The records are written straight from the thread again.)
 __global__ void __launch_bounds__(KB_BLOCK) k_finalize(KbIndexDev ix, KbParams pm, KbBatchDev bt, kb_aln_t* aln)
 {
 	if (blockIdx.x == 0 && threadIdx.x == 0) bt.counters[31] = KB_ATOMIC_ADD(bt.cig_cursor, 0u);
 	const int t = blockIdx.x * blockDim.x + threadIdx.x, per = pm.paired ? 2 : 1, items = pm.paired ? (bt.n_reads >> 1) : bt.n_reads;
-#ifndef KB_EMUL
-	__shared__ __align__(16) kb_aln_t st[2 * KB_BLOCK];
-	// (a batch that overflowed an arena is rerun as a whole: kb_stage_finalize then leaves the records alone and what is copied out is never looked at)
-	if (t < items) kb_stage_finalize(ix, pm, bt, st + per * (int)threadIdx.x, t);
-	__syncthreads();
-	const int t0 = blockIdx.x * blockDim.x, nrec = per * (items - t0 < (int)blockDim.x ? items - t0 : (int)blockDim.x);
-	if (nrec <= 0) return;
-	static_assert(sizeof(kb_aln_t) % 8 == 0, "kb_aln_t is copied in 8-byte words");
-	const size_t base = (size_t)per * (size_t)t0 * sizeof(kb_aln_t);   // a multiple of 16: the block size is even
-	const int nbytes = nrec * (int)sizeof(kb_aln_t), n16 = nbytes >> 4;
-	const uint4* src = reinterpret_cast<const uint4*>(st); uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<u8*>(aln) + base);
-	for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
-	if ((nbytes & 15) && threadIdx.x == 0) reinterpret_cast<u64*>(reinterpret_cast<u8*>(aln) + base)[2 * n16] = reinterpret_cast<const u64*>(st)[2 * n16];
-#else
 	if (t < items) kb_stage_finalize(ix, pm, bt, aln + (size_t)per * (size_t)t, t);
-#endif
 }
 
 // ---- stage-level test entry (kb_debug_align): caller-chosen fragment pairs through classification, phase B and the per-segment
@@ -739,6 +728,7 @@ struct kb_ctx
 	int align_warps = KB_ALIGN_WARPS;   // k_nw_warp
 	int part_warps = 148 * 40, part_pool = 4096;   // k_align_part: warps in the grid (each with an HBM arena) and shared-memory pool bytes per warp (r14 A/B: 8 warps/SM + 10 KB pool 2.34 ms -> 40 warps/SM + 4 KB 1.34 ms for the align stage at C2)
 	int nw_tmax = 0;             // largest side one thread solves (0: KB_NW_TMAX); KB_NW_TMAX=32|64 sends more to the wavefront kernel
+	int part_stack = 24, part_raw = 40;   // KB_PART_STACK / KB_PART_RAW: see KbBatchDev
 	int nw_warp_below = 8192;    // a column-tile class (33..64, 65..128) with fewer problems than this is solved by k_nw_warp instead
 	int rescue_threads = 64;     // block size of k_rescue_win (32, 64 or 128)
 	int cand_heavy = 1;          // items with a long seed list get a warp of their own in k_cand_heavy (KB_CAND_HEAVY=0: everything in k_cand_pair)
@@ -830,6 +820,8 @@ int kb_init(int device, kb_ctx_t** out)
 	e = getenv("KB_SEED_TAIL"); if (e && atoi(e) >= 1 && atoi(e) <= 50) ctx->seed_tail = atoi(e);
 	e = getenv("KB_SEED_WARPS"); if (e && atoi(e) >= 4 && atoi(e) <= 148 * 64) ctx->seed_warps = atoi(e);
 	e = getenv("KB_NW_WARP_BELOW"); if (e && atoi(e) >= 0) ctx->nw_warp_below = atoi(e);
+	e = getenv("KB_PART_STACK"); if (e && atoi(e) >= 1) ctx->part_stack = atoi(e);
+	e = getenv("KB_PART_RAW"); if (e && atoi(e) >= 1) ctx->part_raw = atoi(e);
 	e = getenv("KB_PART_WARPS"); if (e && atoi(e) >= 148 && atoi(e) <= 148 * 64) ctx->part_warps = atoi(e) / 4 * 4;
 	e = getenv("KB_PART_POOL"); if (e && atoi(e) >= 1024 && atoi(e) <= 11264) ctx->part_pool = atoi(e) / 16 * 16;
 	*out = ctx;
@@ -1117,7 +1109,7 @@ static int alloc_batch(kb_ctx* ctx, kb_slot& sl, int shared)
 	else { bt.cigar = sl.cigar.p; bt.cap_cigar = (u32)sl.cap_cigar; bt.cig_cursor = sl.counters.p + 2; }
 	bt.scratch = sl.scratch.p; bt.scratch_per_thread = per; bt.scratch_threads = (int)threads;
 	bt.wscratch = sl.wscratch.p; bt.wscratch_per_warp = per; bt.wscratch_warps = wwarps;
-	bt.max_rlen = L; bt.nw_tmax = ctx->nw_tmax > 0 ? ctx->nw_tmax : KB_NW_TMAX; bt.nw_warp_below = ctx->nw_warp_below; bt.seg_cap = 0; bt.kmer_cap = 0; bt.counters = sl.counters.p; bt.work = sl.work.p;
+	bt.max_rlen = L; bt.nw_tmax = ctx->nw_tmax > 0 ? ctx->nw_tmax : KB_NW_TMAX; bt.nw_warp_below = ctx->nw_warp_below; bt.part_stack = ctx->part_stack; bt.part_raw = ctx->part_raw; bt.seg_cap = 0; bt.kmer_cap = 0; bt.counters = sl.counters.p; bt.work = sl.work.p;
 	return KB_OK;
 }
 
