@@ -59,6 +59,18 @@ def test_pacbio_long_reads(mini):
     assert pu.compare_singles(m, pu.Oracle(pu.MINI_PREFIX, pacbio=True), r) == 0
 
 
+@pytest.mark.parametrize("stack,raw", [("1", "1"), ("3", "4")])
+def test_partition_buffers_spill(mini, monkeypatch, stack, raw):
+    """k_align_part keeps the first entries of a job's work stack and a short exact-match run list in the warp's pool; with tiny limits every
+    partition goes through the HBM part of the stack and through part_grow()'s second pass over the full-size list. Same reads, same answers."""
+    idx, g = mini
+    monkeypatch.setenv("KB_PART_STACK", stack); monkeypatch.setenv("KB_PART_RAW", raw)
+    r, _, _ = synth.simulate(g, 12, 3000, 0.15, seed=36, paired=False, indel=0.01)
+    assert pu.compare_singles(pu.make_mapper(idx, emul=True, pacbio=True), pu.Oracle(pu.MINI_PREFIX, pacbio=True), r) == 0
+    reads = pu.big_gap_reads(g)
+    assert pu.compare_singles(pu.make_mapper(idx, emul=True), pu.Oracle(pu.MINI_PREFIX), reads) == 0
+
+
 def test_all_nw_size_classes(mini, monkeypatch):
     """Every nw_alignment size class (register tiles <= 8/16/24/32, column tiles <= 64/128, warp wavefront) against the oracle."""
     idx, g = mini

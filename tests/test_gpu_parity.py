@@ -98,6 +98,17 @@ def test_pacbio_vs_oracle(built):
     assert pu.compare_singles(m, pu.Oracle(pu.MINI_PREFIX, pacbio=True), r) == 0
 
 
+@pytest.mark.parametrize("stack,raw", [("1", "1"), ("3", "4")])
+def test_partition_buffers_spill_gpu(built, monkeypatch, stack, raw):
+    """The CUDA k_align_part with tiny shared-memory limits for the work stack and the run list (HBM part of the stack, part_grow's second pass)."""
+    idx = KartIndex(pu.MINI_PREFIX)
+    g = pu.genome_of(idx)
+    monkeypatch.setenv("KB_PART_STACK", stack); monkeypatch.setenv("KB_PART_RAW", raw)
+    r, _, _ = synth.simulate(g, 48, 3000, 0.15, seed=36, paired=False, indel=0.01)
+    assert pu.compare_singles(pu.make_mapper(idx, pacbio=True), pu.Oracle(pu.MINI_PREFIX, pacbio=True), r) == 0
+    assert pu.compare_singles(pu.make_mapper(idx), pu.Oracle(pu.MINI_PREFIX), pu.big_gap_reads(g)) == 0
+
+
 def test_all_nw_size_classes(built, monkeypatch):
     """Every nw_alignment size class of the CUDA path (thread-per-problem register tiles, column tiles, warp wavefront) against the oracle."""
     idx = KartIndex(pu.MINI_PREFIX)
