@@ -566,28 +566,29 @@ struct KbFragIter
 		for (int p = lane; p < cur.rl; p += 32) { u32 id = KB_NOKMER; if (p + 8 <= cur.rl) { id = 0; for (int i = 0; i < 8; i++) id = (id << 2) | (u32)kb_nt4(a[p + i]); } w1[p] = id; }
 		for (int p = lane; p < cur.gl; p += 32) { u32 id = KB_NOKMER; if (p + 8 <= cur.gl) { id = 0; for (int i = 0; i < 8; i++) id = (id << 2) | (u32)kb_nt4(b[p + i]); } w2[p] = id; }
 	}
-	// all lanes: the exact-match runs of kb_kmer_pairs (min_len 8), one (position, diagonal) cell per lane and step, appended in
-	// arbitrary order (part_finish sorts them by a total order)
+	// all lanes: the exact-match runs of kb_kmer_pairs (min_len 8), appended in arbitrary order (part_finish sorts them by a total
+	// order). A lane takes read positions r = lane, lane + 32, ... and walks the diagonals |g - r| < shift of each: the id of r stays in
+	// a register, the ids of g are consecutive loads (r24, C5: dealing (position, diagonal) cells to the lanes through idx / nd and
+	// idx % nd spent 37 % of the kernel's instructions on the division and reloaded w1[r] for every cell).
 	KB_HD void part_pairs(int lane)
 	{
 		const int n1 = cur.rl - 7, n2 = cur.gl - 7;
 		if (n1 <= 0 || n2 <= 0) return;
-		int dlo = -(n1 - 1), dhi = n2 - 1;
-		if (dlo < -(shift - 1)) dlo = -(shift - 1);
-		if (dhi > shift - 1) dhi = shift - 1;
-		const int nd = dhi - dlo + 1; if (nd <= 0) return;
-		const int total = n1 * nd;
-		for (int idx = lane; idx < total; idx += 32)
+		for (int r = lane; r < n1; r += 32)
 		{
-			const int r = idx / nd, d = dlo + idx % nd, g = r + d;
-			if (g < 0 || g >= n2) continue;
 			const u32 id = w1[r];
-			if (id == KB_NOKMER || id != w2[g]) continue;
-			if (r > 0 && g > 0 && w1[r - 1] != KB_NOKMER && w1[r - 1] == w2[g - 1]) continue;   // not the start of its run
-			int run = 1;
-			while (r + run < n1 && g + run < n2 && w1[r + run] != KB_NOKMER && w1[r + run] == w2[g + run]) run++;
-			u32 slot = KB_ATOMIC_ADD(&np, 1u);
-			if ((int)slot < cap) { KbSeg sg; sg.simple = 1; sg.rpos = r; sg.gpos = (i64)g; sg.rlen = sg.glen = 8 + run - 1; raw[slot] = sg; }
+			if (id == KB_NOKMER) continue;
+			const int glo = r - (shift - 1) > 0 ? r - (shift - 1) : 0, ghi = r + (shift - 1) < n2 - 1 ? r + (shift - 1) : n2 - 1;
+			const u32 before = r > 0 ? w1[r - 1] : KB_NOKMER;
+			for (int g = glo; g <= ghi; g++)
+			{
+				if (w2[g] != id) continue;
+				if (g > 0 && before != KB_NOKMER && before == w2[g - 1]) continue;   // not the start of its run
+				int run = 1;
+				while (r + run < n1 && g + run < n2 && w1[r + run] != KB_NOKMER && w1[r + run] == w2[g + run]) run++;
+				u32 slot = KB_ATOMIC_ADD(&np, 1u);
+				if ((int)slot < cap) { KbSeg sg; sg.simple = 1; sg.rpos = r; sg.gpos = (i64)g; sg.rlen = sg.glen = 8 + run - 1; raw[slot] = sg; }
+			}
 		}
 	}
 	// one lane, after part_pairs: true when the runs did not fit the short list -- the full-size list is then in place (HBM arena) and

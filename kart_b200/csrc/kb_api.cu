@@ -319,7 +319,53 @@ __global__ void __launch_bounds__(KB_BLOCK) k_cand_heavy_finish(KbIndexDev ix, K
 	const u32 count = bt.counters[15];
 	for (u32 q = blockIdx.x * blockDim.x + threadIdx.x; q < count; q += gridDim.x * blockDim.x) kb_cand_finish(ix, pm, bt, bt.slow_list2[q]);
 }
-__global__ void __launch_bounds__(KB_BLOCK) k_cand_pacbio(KbIndexDev ix, KbParams pm, KbBatchDev bt) { kb_stage_cand_pacbio(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
+__global__ void __launch_bounds__(KB_BLOCK) k_cand_pacbio(KbIndexDev ix, KbParams pm, KbBatchDev bt, int sorted) { kb_stage_cand_pacbio(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, sorted != 0); }
+// A 7-kbp read brings ~600 seeds; sorted by the read's own thread (Shell sort over 24-byte records in HBM) that was 79 % of k_cand_pacbio's
+// samples (ncu r24, C5). A warp per read sorts them first, with the same bitonic network on packed keys as k_cand_heavy; the read's
+// unused candidate slots (n_seeds + 1 of them, as large as a seed) are the permutation buffer. Lists beyond KB_WSORT_MAX seeds, and reads of
+// a megabase or more (rPos would not fit the key), are sorted by one lane as before.
+#ifndef KB_EMUL
+__global__ void __launch_bounds__(KB_BLOCK) k_cand_pacbio_sort(KbBatchDev bt)
+{
+	__shared__ KbWarpSort sw[KB_BLOCK / 32];
+	if (bt.counters[3]) return;
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const u32 gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+	KbWarpSort& w = sw[wib];
+	for (u32 r = gwarp; r < (u32)bt.n_reads; r += nwarps)
+	{
+		const int n = bt.n_seeds[r];
+		if (n < 2) continue;
+		KbSeg* v = bt.segs + bt.seed_off[r];
+		if (n > KB_WSORT_MAX || bt.seq_off[r + 1] - bt.seq_off[r] >= (1ull << 20)) { if (lane == 0) kb_sort_segs<true>(v, n); __syncwarp(); continue; }
+		if (lane == 0) kb_wsort_begin(w, v, n, reinterpret_cast<KbSeg*>(bt.cands + bt.cand_off[r]), true);
+		__syncwarp();
+		kb_wsort_load(w, lane); __syncwarp();
+		for (int k = 2; k <= w.p; k <<= 1) for (int j = k >> 1; j > 0; j >>= 1) { kb_wsort_step(w, k, j, lane); __syncwarp(); }
+		kb_wsort_gather(w, lane); __syncwarp();
+		kb_wsort_scatter(w, lane); __syncwarp();
+	}
+}
+#else
+static void k_cand_pacbio_sort(KbBatchDev bt)   // emulation: a warp = a loop over 32 lanes per phase
+{
+	if (blockIdx.x != 0 || threadIdx.x != 0) return;
+	if (bt.counters[3]) return;
+	static thread_local KbWarpSort w;
+	for (int r = 0; r < bt.n_reads; r++)
+	{
+		const int n = bt.n_seeds[r];
+		if (n < 2) continue;
+		KbSeg* v = bt.segs + bt.seed_off[r];
+		if (n > KB_WSORT_MAX || bt.seq_off[r + 1] - bt.seq_off[r] >= (1ull << 20)) { kb_sort_segs<true>(v, n); continue; }
+		kb_wsort_begin(w, v, n, reinterpret_cast<KbSeg*>(bt.cands + bt.cand_off[r]), true);
+		for (int l = 31; l >= 0; l--) kb_wsort_load(w, l);
+		for (int k = 2; k <= w.p; k <<= 1) for (int j = k >> 1; j > 0; j >>= 1) for (int l = 31; l >= 0; l--) kb_wsort_step(w, k, j, l);
+		for (int l = 31; l >= 0; l--) kb_wsort_gather(w, l);
+		for (int l = 31; l >= 0; l--) kb_wsort_scatter(w, l);
+	}
+}
+#endif
 // rescue: plan (thread per job) -> windows (block per task) -> commit (thread per job); see kb_pair.cuh "task-parallel rescue"
 __global__ void __launch_bounds__(KB_BLOCK) k_rescue_plan(KbIndexDev ix, KbParams pm, KbBatchDev bt)
 {
@@ -368,6 +414,7 @@ __global__ void __launch_bounds__(KB_BLOCK) k_rescue_fast(KbIndexDev ix, KbParam
 		__syncwarp();
 		kb_rf_load(ix, bt, w, lane); __syncwarp();
 		kb_rf_fill(w, lane); __syncwarp();
+		kb_rf_scan(w, lane); __syncwarp();
 		kb_rf_pairs(w, lane); __syncwarp();
 		if (lane == 0) kb_rf_end(pm, bt, w);
 		__syncwarp();
@@ -385,6 +432,7 @@ static void k_rescue_fast(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulat
 		kb_rf_begin(ix, bt, w, q);
 		for (int t = 31; t >= 0; t--) kb_rf_load(ix, bt, w, t);
 		for (int t = 31; t >= 0; t--) kb_rf_fill(w, t);
+		for (int t = 31; t >= 0; t--) kb_rf_scan(w, t);
 		for (int t = 31; t >= 0; t--) kb_rf_pairs(w, t);   // reversed on purpose: the result must not depend on append order
 		kb_rf_end(pm, bt, w);
 	}
@@ -728,6 +776,7 @@ struct kb_ctx
 	int align_warps = KB_ALIGN_WARPS;   // k_nw_warp
 	int part_warps = 148 * 40, part_pool = 4096;   // k_align_part: warps in the grid (each with an HBM arena) and shared-memory pool bytes per warp (r14 A/B: 8 warps/SM + 10 KB pool 2.34 ms -> 40 warps/SM + 4 KB 1.34 ms for the align stage at C2)
 	int nw_tmax = 0;             // largest side one thread solves (0: KB_NW_TMAX); KB_NW_TMAX=32|64 sends more to the wavefront kernel
+	int rf_cand = 256;           // KB_RF_CAND (<= 256)
 	int part_stack = 24, part_raw = 40;   // KB_PART_STACK / KB_PART_RAW: see KbBatchDev
 	int nw_warp_below = 8192;    // a column-tile class (33..64, 65..128) with fewer problems than this is solved by k_nw_warp instead
 	int rescue_threads = 64;     // block size of k_rescue_win (32, 64 or 128)
@@ -820,6 +869,7 @@ int kb_init(int device, kb_ctx_t** out)
 	e = getenv("KB_SEED_TAIL"); if (e && atoi(e) >= 1 && atoi(e) <= 50) ctx->seed_tail = atoi(e);
 	e = getenv("KB_SEED_WARPS"); if (e && atoi(e) >= 4 && atoi(e) <= 148 * 64) ctx->seed_warps = atoi(e);
 	e = getenv("KB_NW_WARP_BELOW"); if (e && atoi(e) >= 0) ctx->nw_warp_below = atoi(e);
+	e = getenv("KB_RF_CAND"); if (e && atoi(e) >= 0 && atoi(e) <= 256) ctx->rf_cand = atoi(e);
 	e = getenv("KB_PART_STACK"); if (e && atoi(e) >= 1) ctx->part_stack = atoi(e);
 	e = getenv("KB_PART_RAW"); if (e && atoi(e) >= 1) ctx->part_raw = atoi(e);
 	e = getenv("KB_PART_WARPS"); if (e && atoi(e) >= 148 && atoi(e) <= 148 * 64) ctx->part_warps = atoi(e) / 4 * 4;
@@ -1109,7 +1159,7 @@ static int alloc_batch(kb_ctx* ctx, kb_slot& sl, int shared)
 	else { bt.cigar = sl.cigar.p; bt.cap_cigar = (u32)sl.cap_cigar; bt.cig_cursor = sl.counters.p + 2; }
 	bt.scratch = sl.scratch.p; bt.scratch_per_thread = per; bt.scratch_threads = (int)threads;
 	bt.wscratch = sl.wscratch.p; bt.wscratch_per_warp = per; bt.wscratch_warps = wwarps;
-	bt.max_rlen = L; bt.nw_tmax = ctx->nw_tmax > 0 ? ctx->nw_tmax : KB_NW_TMAX; bt.nw_warp_below = ctx->nw_warp_below; bt.part_stack = ctx->part_stack; bt.part_raw = ctx->part_raw; bt.seg_cap = 0; bt.kmer_cap = 0; bt.counters = sl.counters.p; bt.work = sl.work.p;
+	bt.max_rlen = L; bt.nw_tmax = ctx->nw_tmax > 0 ? ctx->nw_tmax : KB_NW_TMAX; bt.nw_warp_below = ctx->nw_warp_below; bt.rf_cand = ctx->rf_cand; bt.part_stack = ctx->part_stack; bt.part_raw = ctx->part_raw; bt.seg_cap = 0; bt.kmer_cap = 0; bt.counters = sl.counters.p; bt.work = sl.work.p;
 	return KB_OK;
 }
 
@@ -1258,7 +1308,11 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 	CK(cudaEventRecord(sl.ev[2], s));
 	KB_LAUNCH(k_cand_pair, g_items, KB_BLOCK, s, ix, pm, bt, ctx->cand_heavy); sl.launches++;
 	if (ctx->cand_heavy && !pm.pacbio) { KB_LAUNCH(k_cand_heavy, 148 * 8, KB_BLOCK, s, ix, pm, bt); KB_LAUNCH(k_cand_heavy_finish, 148 * 8, KB_BLOCK, s, ix, pm, bt); sl.launches += 2; }
-	if (pm.pacbio) { KB_LAUNCH(k_cand_pacbio, g_slow, KB_BLOCK, s, ix, pm, bt); sl.launches++; }
+	if (pm.pacbio)
+	{
+		if (ctx->cand_heavy) { KB_LAUNCH(k_cand_pacbio_sort, 148 * 8, KB_BLOCK, s, bt); sl.launches++; }
+		KB_LAUNCH(k_cand_pacbio, g_slow, KB_BLOCK, s, ix, pm, bt, ctx->cand_heavy); sl.launches++;
+	}
 	CK(cudaEventRecord(sl.ev[3], s));
 	if (pm.paired)
 	{

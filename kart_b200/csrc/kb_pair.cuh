@@ -156,6 +156,7 @@ KB_HD void kb_rj_pairs(const KbIndexDev& ix, KbRescueJob* j, int tid, int nth)
 #define KB_RF_WORDS 66      // window words: 2048 positions + the word the last 8-mers reach into + 1
 #define KB_RF_PAIRS 24
 #define KB_RF_FILT 16384
+#define KB_RF_CAND 256
 KB_HD u32 kb_rf_fold(u32 id) { return (id ^ (id >> 2)) & (u32)(KB_RF_FILT - 1); }
 struct KbRescueFast
 {
@@ -164,7 +165,8 @@ struct KbRescueFast
 	u64 wcode[KB_RF_WORDS]; u64 mcode[10];
 	KbSeg pairs[KB_RF_PAIRS];
 	u8 hnext[256];
-	u32 task, npairs; i32 ok, dirty, ml, slen, mate_read; i64 left;
+	unsigned short cand[KB_RF_CAND];   // window positions that passed the filter (kb_rf_scan -> kb_rf_pairs)
+	u32 task, npairs, ncand, cand_cap; i32 ok, dirty, ml, slen, mate_read; i64 left;
 };
 KB_HD u64 kb_rf_bits(const u64* w, int p)   // 32 bases starting at base p of a packed word array (one spare word behind the data)
 {
@@ -176,7 +178,7 @@ KB_HD void kb_rf_begin(const KbIndexDev& ix, const KbBatchDev& bt, KbRescueFast&
 {
 	const KbRTask t = bt.rtasks[task];
 	const int p = bt.rescue_list[t.job], ra = 2 * p, rb = ra + 1;
-	w.task = task; w.npairs = 0; w.dirty = 0;
+	w.task = task; w.npairs = 0; w.ncand = 0; w.cand_cap = (u32)(bt.rf_cand < KB_RF_CAND ? (bt.rf_cand > 0 ? bt.rf_cand : 0) : KB_RF_CAND); w.dirty = 0;
 	w.mate_read = t.side == 0 ? rb : ra;
 	w.ml = (int)(bt.seq_off[w.mate_read + 1] - bt.seq_off[w.mate_read]);
 	w.left = t.left; w.slen = t.slen;
@@ -217,51 +219,61 @@ KB_HD void kb_rf_fill(KbRescueFast& w, int lane)
 		KB_ATOMIC_OR(&w.filt[h >> 5], 1u << (h & 31));
 	}
 }
-// all lanes: the left-maximal exact matches of >= 10 bases (kb_rj_pairs on packed words)
+// one lane: window position g passed the filter: look its 8-mer up in the mate's index and measure the runs that start here
+KB_HD void kb_rf_probe(KbRescueFast& w, int g, u32 id)
+{
+	const u64 M5 = 0x5555555555555555ull;
+	const int ml = w.ml, sl = w.slen;
+	u32 s = kb_rj_slot(id, KB_RF_SLOTS - 1), key;
+	while ((key = w.hkey[s]) != 0u && key != id + 1u) s = (s + 1u) & (u32)(KB_RF_SLOTS - 1);
+	if (key == 0u) return;
+	for (u32 r = w.hhead[s]; r < 255u; r = w.hnext[r])
+	{
+		if (r > 0 && g > 0 && ((w.mcode[(r - 1) >> 5] >> (62 - 2 * ((r - 1) & 31))) & 3ull) == ((w.wcode[(g - 1) >> 5] >> (62 - 2 * ((g - 1) & 31))) & 3ull)) continue;   // not the start of its run
+		const int lim = ml - (int)r < sl - g ? ml - (int)r : sl - g;
+		int l = 0;
+		while (l < lim)
+		{
+			u64 x = kb_rf_bits(w.mcode, (int)r + l) ^ kb_rf_bits(w.wcode, g + l); x = (x | (x >> 1)) & M5;
+			const int same = x ? (int)KB_CLZLL(x) >> 1 : 32;
+			l += same;
+			if (same < 32) break;
+		}
+		if (l > lim) l = lim;
+		if (l < 10) continue;
+		const u32 slot = KB_ATOMIC_ADD(&w.npairs, 1u);
+		if (slot < (u32)KB_RF_PAIRS) { KbSeg sg; sg.simple = 1; sg.rpos = (i32)r; sg.gpos = (i64)g; sg.rlen = sg.glen = l; w.pairs[slot] = sg; }
+	}
+}
+// all lanes: the left-maximal exact matches of >= 10 bases (kb_rj_pairs on packed words), in two phases.
+// Scan: positions are dealt to the lanes in groups of 8 (one 32-base fetch serves the group's eight 8-mers out of a register); the
+// 16 K-bit filter turns ~99 % of them away after one shared-memory load, the others are only noted in a short list. A lane that
+// probed right away held the other 31 up for ~100 instructions whenever any lane passed (ncu r24: the scan ran at 16 of 32 lanes).
+// Probe: the noted positions are dealt round-robin, so the ~150 consecutive positions of a real copy of the mate spread over all
+// lanes. Positions beyond the list's capacity are probed on the spot.
+KB_HD void kb_rf_scan(KbRescueFast& w, int lane)
+{
+	if (!w.ok || w.dirty) return;
+	const int npos = w.slen - 7, ngroups = (npos + 7) >> 3;
+	for (int grp = lane; grp < ngroups; grp += 32)
+	{
+		u64 bits = kb_rf_bits(w.wcode, grp << 3);
+		const int gend = (grp << 3) + 8 < npos ? (grp << 3) + 8 : npos;
+		for (int g = grp << 3; g < gend; g++, bits <<= 2)
+		{
+			const u32 id = (u32)(bits >> 48);
+			const u32 h = kb_rf_fold(id);
+			if (((w.filt[h >> 5] >> (h & 31)) & 1u) == 0u) continue;
+			const u32 at = KB_ATOMIC_ADD(&w.ncand, 1u);
+			if (at < w.cand_cap) w.cand[at] = (unsigned short)g; else kb_rf_probe(w, g, id);
+		}
+	}
+}
 KB_HD void kb_rf_pairs(KbRescueFast& w, int lane)
 {
 	if (!w.ok || w.dirty) return;
-	const u64 M5 = 0x5555555555555555ull;
-	const int ml = w.ml, sl = w.slen, npos = sl - 7;
-	// Positions are dealt to the lanes in small groups, not in long stretches: where the window does hold a copy of the mate (or of
-	// the repeat element the mate comes from) ~150 consecutive positions pass the filter, and almost all of them only to find that
-	// they continue a run; in stretches of 64 three or four lanes would do that one after the other while the rest idle (ncu r19:
-	// 30 % of the kernel at 2-4 lanes). The filter turns every other position away after one shared-memory load.
-	// r21: dealt position by position, fetching the 8-mer (two shared-memory loads and a funnel shift) was half of the kernel's
-	// instructions. Positions are now dealt in groups of 8: one 32-base fetch serves the group's eight 8-mers out of a register, and a
-	// 150-position copy still spreads over 19 lanes.
-	const int ngroups = (npos + 7) >> 3;
-	for (int grp = lane; grp < ngroups; grp += 32)
-	{
-	u64 bits = kb_rf_bits(w.wcode, grp << 3);
-	const int gend = (grp << 3) + 8 < npos ? (grp << 3) + 8 : npos;
-	for (int g = grp << 3; g < gend; g++, bits <<= 2)
-	{
-		const u32 id = (u32)(bits >> 48);
-		const u32 h = kb_rf_fold(id);
-		if (((w.filt[h >> 5] >> (h & 31)) & 1u) == 0u) continue;
-		u32 s = kb_rj_slot(id, KB_RF_SLOTS - 1), key;
-		while ((key = w.hkey[s]) != 0u && key != id + 1u) s = (s + 1u) & (u32)(KB_RF_SLOTS - 1);
-		if (key == 0u) continue;
-		for (u32 r = w.hhead[s]; r < 255u; r = w.hnext[r])
-		{
-			if (r > 0 && g > 0 && ((w.mcode[(r - 1) >> 5] >> (62 - 2 * ((r - 1) & 31))) & 3ull) == ((w.wcode[(g - 1) >> 5] >> (62 - 2 * ((g - 1) & 31))) & 3ull)) continue;   // not the start of its run
-			const int lim = ml - (int)r < sl - g ? ml - (int)r : sl - g;
-			int l = 0;
-			while (l < lim)
-			{
-				u64 x = kb_rf_bits(w.mcode, (int)r + l) ^ kb_rf_bits(w.wcode, g + l); x = (x | (x >> 1)) & M5;
-				const int same = x ? (int)KB_CLZLL(x) >> 1 : 32;
-				l += same;
-				if (same < 32) break;
-			}
-			if (l > lim) l = lim;
-			if (l < 10) continue;
-			const u32 slot = KB_ATOMIC_ADD(&w.npairs, 1u);
-			if (slot < (u32)KB_RF_PAIRS) { KbSeg sg; sg.simple = 1; sg.rpos = (i32)r; sg.gpos = (i64)g; sg.rlen = sg.glen = l; w.pairs[slot] = sg; }
-		}
-	}
-	}
+	const int n = (int)(w.ncand < w.cand_cap ? w.ncand : w.cand_cap);
+	for (int i = lane; i < n; i += 32) { const int g = (int)w.cand[i]; kb_rf_probe(w, g, (u32)(kb_rf_bits(w.wcode, g) >> 48)); }
 }
 // lane 0: the task's result (kb_rt_end), or the task's place on the slow list
 KB_HD void kb_rf_end(const KbParams& pm, const KbBatchDev& bt, KbRescueFast& w)

@@ -86,14 +86,19 @@ KB_HD void kb_stage_cand_pair(const KbIndexDev& ix, const KbParams& pm, const Kb
 // warp's shared memory; the seeds are then permuted through `tmp`, a region of at least n entries nobody uses yet (the pair's
 // candidate slots: a KbCand is as large as a KbSeg). Both orders are total on distinct seeds, so the result equals kb_sort_segs'.
 #define KB_WSORT_MAX 1024
-struct KbWarpSort { u64 key[KB_WSORT_MAX]; unsigned short idx[KB_WSORT_MAX]; KbSeg* v; KbSeg* tmp; int n, p; };
-KB_HD void kb_wsort_begin(KbWarpSort& w, KbSeg* v, int n, KbSeg* tmp) { w.v = v; w.tmp = tmp; w.n = n; int p = 32; while (p < n) p <<= 1; w.p = p; }
+struct KbWarpSort { u64 key[KB_WSORT_MAX]; unsigned short idx[KB_WSORT_MAX]; KbSeg* v; KbSeg* tmp; int n, p, by_gpos; };
+KB_HD void kb_wsort_begin(KbWarpSort& w, KbSeg* v, int n, KbSeg* tmp, bool by_gpos = false) { w.v = v; w.tmp = tmp; w.n = n; w.by_gpos = by_gpos ? 1 : 0; int p = 32; while (p < n) p <<= 1; w.p = p; }
+// by_gpos: the (gPos,rPos) order of the pacbio path (AlignmentCandidates.cpp:17-21): gPos in the upper 44 bits, rPos (< 2^20) below
 KB_HD void kb_wsort_load(KbWarpSort& w, int lane)
 {
 	for (int i = lane; i < w.p; i += 32)
 	{
 		u64 k = ~0ull;
-		if (i < w.n) { const KbSeg s = w.v[i]; k = ((u64)((s.gpos - (i64)s.rpos) + ((i64)1 << 42)) << 20) | (u64)(u32)s.rpos; }
+		if (i < w.n)
+		{
+			const KbSeg s = w.v[i];
+			k = w.by_gpos ? (((u64)s.gpos << 20) | (u64)(u32)s.rpos) : (((u64)((s.gpos - (i64)s.rpos) + ((i64)1 << 42)) << 20) | (u64)(u32)s.rpos);
+		}
 		w.key[i] = k; w.idx[i] = (unsigned short)i;
 	}
 }
@@ -132,7 +137,8 @@ KB_HD int kb_thread_arena(const KbBatchDev& bt, int tid, int nth, u64 need, KbAr
 	return (int)fit;
 }
 
-KB_HD void kb_stage_cand_pacbio(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int tid, int nth)
+// sorted: k_cand_pacbio_sort has put every read's seeds into (gPos,rPos) order already
+KB_HD void kb_stage_cand_pacbio(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int tid, int nth, bool sorted)
 {
 	if (bt.counters[3]) return;
 	KbArena ar; nth = kb_thread_arena(bt, tid, nth, ((u64)bt.counters[5] + 2) * 32ull + 256ull, &ar);   // taken[] + a copy of the read's seeds
@@ -141,7 +147,7 @@ KB_HD void kb_stage_cand_pacbio(const KbIndexDev& ix, const KbParams& pm, const 
 	{
 		int n = bt.n_seeds[r];
 		KbSeg* v = bt.segs + bt.seed_off[r];
-		kb_sort_segs<true>(v, n);
+		if (!sorted) kb_sort_segs<true>(v, n);
 		ar.used = 0;
 		u8* taken = (u8*)ar.alloc((u64)n + 1); KbSeg* tmp = (KbSeg*)ar.alloc((u64)(n + 1) * sizeof(KbSeg));
 		if (ar.ovf) { KB_ATOMIC_OR(&bt.counters[3], (u32)KB_OVF_SCRATCH); return; }

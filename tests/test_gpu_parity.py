@@ -229,6 +229,10 @@ def test_rescue_fast_path_and_fallback(built, monkeypatch):
     assert pu.compare_pairs(m, orc, reads) == 0
     c = m.debug(9, np.uint32, 32)
     assert c[27] > 100 and c[29] < c[27] // 2, (c[27], c[29])
+    for cap in ("0", "3"):   # the probe list of kb_rf_scan too short: positions beyond it are probed on the spot
+        monkeypatch.setenv("KB_RF_CAND", cap)
+        assert pu.compare_pairs(pu.make_mapper(idx, paired=True), orc, reads) == 0
+    monkeypatch.delenv("KB_RF_CAND")
     monkeypatch.setenv("KB_RESCUE_FAST", "0")
     m = pu.make_mapper(idx, paired=True)
     assert pu.compare_pairs(m, orc, reads) == 0
