@@ -21,7 +21,7 @@ ap.add_argument("--diff-out", default=None, help="write the first differing line
 ap.add_argument("--threads", type=int, default=os.cpu_count() or 1)
 a = ap.parse_args()
 prefix = a.prefix or pu.default_prefix()
-idx = KartIndex(prefix); genome = pu.genome_of(idx)
+idx = KartIndex(prefix); genome = pu.pac_genome(idx) if idx.l_pac > 500_000_000 else pu.genome_of(idx)
 L = a.len or {"pe": 150, "se": 100, "pacbio": 7000}[a.mode]
 tmp = tempfile.mkdtemp(prefix="kartcli")
 t = time.time()
