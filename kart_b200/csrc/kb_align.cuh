@@ -488,9 +488,29 @@ struct KbSink
 	}
 };
 
+KB_HD int kb_mismatch_packed(const KbIndexDev& ix, const KbPk* rd, const u8* f1, int rpos, i64 gpos, int n, int limit);
+KB_HD u8 kb_ref_char(const KbIndexDev& ix, i64 p);
+// 32 bases of a packed read from position pos on (codes only)
+KB_HD u64 kb_read_code(const KbPk* rd, int pos)
+{
+	const u64 a = rd[pos >> 5].code; const int s = (pos & 31) * 2;
+	return s ? (a << s) | (rd[(pos >> 5) + 1].code >> (64 - s)) : a;
+}
+// Where do eight equal bases in a row start? a, b: 32 bases each (base i at bits 63-2i, 62-2i); bit 62-2i of the result is set iff
+// bases i .. i+7 are pairwise equal (so only for i <= 24): exactly "the 8-mer ids at the two positions are equal" for pure-base text.
+KB_HD u64 kb_match8(u64 a, u64 b)
+{
+	const u64 x = a ^ b; u64 e = ~(x | (x >> 1)) & 0x5555555555555555ull;
+	e &= e << 2; e &= e << 4; e &= e << 8;
+	return e;
+}
 struct KbFragIter
 {
 	const KbParams* pm; KbArena* ar; KbArena* fast; const u8* f1; const u8* f2; KbSink* sink;
+	// the job's place in the packed read and in the text (set by kb_pt_begin): fragments of pure bases are partitioned on the packed
+	// words (part_pairs_packed), nothing of them is copied; f1 points at the read's characters in HBM, f2 (reference characters) is
+	// only materialised for a fragment that holds a character which is no base
+	const KbIndexDev* ix; const KbPk* rd; int rbase, gl0; i64 gbase; u8* f2w;
 	// Work stack: worst case rl0 + gl0 + 4 entries, in practice a handful. The first `sfast` entries are tried in the warp's shared-memory
 	// pool, the rest lives in the HBM arena (r23: with the whole stack in front of them, the 8-mer id arrays of every fragment beyond
 	// ~100 x 100 ended up in HBM, where part_pairs reads them n1 x (2 shift + 1) times).
@@ -500,9 +520,9 @@ struct KbFragIter
 	KbWork cur; u32* w1; u32* w2; KbSeg* raw; int shift, cap, cap_full, dirty; u32 np; u64 pmark, fmark;
 
 	// fast_: the warp's shared-memory pool, used for whatever fits; ar_: its arena in HBM
-	KB_HD bool init(const KbParams* pm_, KbArena* fast_, KbArena* ar_, const u8* f1_, int rl0, const u8* f2_, int gl0, KbSink* sink_)
+	KB_HD bool init(const KbParams* pm_, KbArena* fast_, KbArena* ar_, const u8* f1_, int rl0, const u8* f2_, int gl0_, KbSink* sink_)
 	{
-		pm = pm_; ar = ar_; fast = fast_; f1 = f1_; f2 = f2_; sink = sink_; sp = 0;
+		pm = pm_; ar = ar_; fast = fast_; f1 = f1_; f2 = f2_; sink = sink_; sp = 0; gl0 = gl0_; f2w = nullptr;
 		scap = rl0 + gl0 + 4;
 		sfast = sink_->bt->part_stack > 0 && sink_->bt->part_stack < scap ? sink_->bt->part_stack : scap;
 		st = (KbWorkP*)kb_alloc2(*fast, *ar, (u64)sfast * sizeof(KbWorkP));
@@ -519,12 +539,12 @@ struct KbFragIter
 		while (sp > 0 && !ar->ovf && !sink->ovf)
 		{
 			const KbWork e = kb_work_unpack(slot(--sp));
-			const u8* a = f1 + e.r0; const u8* b = f2 + e.g0;
 			if (e.kind == KB_W_INS) { sink->lit(KB_RUN_I, e.rl, e.rl); continue; }
 			if (e.kind == KB_W_DEL) { sink->lit(KB_RUN_D, e.gl, e.gl); continue; }
 			if (e.kind == KB_W_COPY)
 			{
-				int id = 0; for (int t = 0; t < e.rl; t++) if (a[t] == b[t]) id++;
+				// identical characters (raw equality against the upper-case reference, tools.cpp:84): 32 per step on the packed words
+				const int id = e.rl - kb_mismatch_packed(*ix, rd, f1 + e.r0, rbase + e.r0, gbase + e.g0, e.rl, 0x3FFFFFFF);
 				sink->lit(KB_RUN_M, e.rl, e.rl + e.gl); sink->ident += id; sink->aligned += e.rl;
 				continue;
 			}
@@ -534,7 +554,7 @@ struct KbFragIter
 				if (pm->pacbio) { shift = rl > gl ? (int)(rl * 0.2) : (int)(gl * 0.2); if (shift > 50) shift = 50; }
 				else shift = pm->max_gaps;
 				pmark = ar->used; fmark = fast->used;
-				w1 = (u32*)kb_alloc2(*fast, *ar, (u64)rl * 4); w2 = (u32*)kb_alloc2(*fast, *ar, (u64)gl * 4);
+				w1 = nullptr; w2 = nullptr;   // only a fragment with a character that is no base needs the id arrays (part_ids)
 				cap_full = ((rl < gl ? rl : gl) / 9 + 2) * (2 * shift + 1);   // exact-match runs on one diagonal start >= 9 apart
 				if (cap_full > rl + gl) cap_full = rl + gl;
 				// that bound is hundreds of entries, a fragment usually has a handful of runs: a short list (in the pool when it fits) first,
@@ -550,21 +570,91 @@ struct KbFragIter
 		return 0;
 	}
 
-	// all lanes: does either side hold a character that is no base? (then the literal scan of kb_kmer_ids is replayed)
+	// all lanes: does either side hold a character that is no base? (then the literal scan of kb_kmer_ids is replayed on characters)
 	KB_HD void part_scan(int lane)
 	{
-		const u8* a = f1 + cur.r0; const u8* b = f2 + cur.g0; int bad = 0;
-		for (int i = lane; i < cur.rl; i += 32) if (kb_nt4(a[i]) > 3) bad = 1;
-		for (int i = lane; i < cur.gl; i += 32) if (kb_nt4(b[i]) > 3) bad = 1;
+		int bad = 0;
+		for (int o = 32 * lane; o < cur.rl; o += 32 * 32)
+		{
+			const int m = cur.rl - o < 32 ? cur.rl - o : 32;
+			if (kb_read_win(rd, rbase + cur.r0 + o).n4 & ~((~0u >> (m - 1)) >> 1)) bad = 1;
+		}
+		for (int o = 32 * lane; o < cur.gl; o += 32 * 32)
+		{
+			const int m = cur.gl - o < 32 ? cur.gl - o : 32; u32 inv;
+			kb_ref_win(*ix, gbase + cur.g0 + o, &inv);
+			if (inv & ~((~0u >> (m - 1)) >> 1)) bad = 1;
+		}
 		if (bad) dirty = 1;
 	}
-	// all lanes: 8-mer ids of both sides. Pure-base strings: id(p) is the 16-bit value of the 8 characters at p, for p <= len-8.
+	// one lane, dirty fragments only: 8-mer ids of both sides by the reference's literal scan (the reference characters are fetched now)
 	KB_HD void part_ids(int lane)
 	{
-		const u8* a = f1 + cur.r0; const u8* b = f2 + cur.g0;
-		if (dirty) { if (lane == 0) { kb_kmer_ids(cur.rl, a, w1); kb_kmer_ids(cur.gl, b, w2); } return; }
-		for (int p = lane; p < cur.rl; p += 32) { u32 id = KB_NOKMER; if (p + 8 <= cur.rl) { id = 0; for (int i = 0; i < 8; i++) id = (id << 2) | (u32)kb_nt4(a[p + i]); } w1[p] = id; }
-		for (int p = lane; p < cur.gl; p += 32) { u32 id = KB_NOKMER; if (p + 8 <= cur.gl) { id = 0; for (int i = 0; i < 8; i++) id = (id << 2) | (u32)kb_nt4(b[p + i]); } w2[p] = id; }
+		if (!dirty || lane != 0) return;
+		w1 = (u32*)kb_alloc2(*fast, *ar, (u64)cur.rl * 4); w2 = (u32*)kb_alloc2(*fast, *ar, (u64)cur.gl * 4);
+		u8* b = (u8*)ar->alloc((u64)cur.gl);
+		if (ar->ovf) return;
+		for (int i = 0; i < cur.gl; i++) b[i] = kb_ref_char(*ix, gbase + cur.g0 + i);
+		kb_kmer_ids(cur.rl, f1 + cur.r0, w1); kb_kmer_ids(cur.gl, b, w2);
+	}
+	// one exact-match run found: rpos / gpos relative to the fragment, l bases
+	KB_HD void part_emit(int r, int g, int l)
+	{
+		const u32 slot = KB_ATOMIC_ADD(&np, 1u);
+		if ((int)slot < cap) { KbSeg sg; sg.simple = 1; sg.rpos = r; sg.gpos = (i64)g; sg.rlen = sg.glen = l; raw[slot] = sg; }
+	}
+	// all lanes, pure-base fragments: the same runs from the packed words. A run of equal 8-mer ids along a diagonal is a maximal run
+	// of L >= 8 equal bases (L - 7 consecutive id pairs, reported length 8 + (L - 7) - 1 = L). The id pairs of a diagonal are cut into
+	// cells of 25 positions: kb_match8 marks where eight equal bases start; a cell reports the runs that START in it (its first
+	// position starts one unless the base in front is equal too) and measures them forward with XOR + count-leading-zeros, across
+	// cell borders. Cells are independent, so lanes take them in any order: P (a power of two) lanes per diagonal, 32 / P diagonals
+	// per round. r24/r26 (C5): comparing ids cell by cell was a third of k_align_part -- 46 G (position, diagonal) cells per 50 k reads.
+	KB_HD void part_pairs_packed(int lane)
+	{
+		const u64 M5 = 0x5555555555555555ull;
+		const int rl = cur.rl, gl = cur.gl, n1 = rl - 7, n2 = gl - 7;
+		if (n1 <= 0 || n2 <= 0) return;
+		int dlo = -(n1 - 1), dhi = n2 - 1;
+		if (dlo < -(shift - 1)) dlo = -(shift - 1);
+		if (dhi > shift - 1) dhi = shift - 1;
+		const int rp0 = rbase + cur.r0; const i64 gp0 = gbase + cur.g0;
+		const int longest = n1 < n2 ? n1 : n2, ncell_max = (longest + 24) / 25;
+		int lg = 0; while ((1 << lg) < ncell_max && lg < 5) lg++;
+		const int P = 1 << lg, dper = 32 >> lg;
+		for (int dbase = dlo; dbase <= dhi; dbase += dper)
+		{
+			const int d = dbase + (lane >> lg);
+			if (d > dhi) continue;
+			const int r_lo = d < 0 ? -d : 0, r_end = n1 < n2 - d ? n1 : n2 - d;   // id pairs (r, r + d) exist for r in [r_lo, r_end)
+			for (int rs = r_lo + 25 * (lane & (P - 1)); rs < r_end; rs += 25 * P)
+			{
+				u32 inv;
+				u64 S = kb_match8(kb_read_code(rd, rp0 + rs), kb_ref_win(*ix, gp0 + rs + d, &inv));
+				const int cnt = r_end - rs < 25 ? r_end - rs : 25;
+				S &= ~(~0ull >> (2 * cnt));                                         // the cell's own positions
+				if (S == 0) continue;
+				u64 st = S & ~(S >> 2);                                             // a position whose predecessor is no match
+				if ((st >> 62) & 1ull)                                              // the cell's first position: is the base in front equal as well?
+				{
+					if (rs > r_lo && (((kb_read_code(rd, rp0 + rs - 1) ^ kb_ref_win(*ix, gp0 + rs - 1 + d, &inv)) >> 62) & 3ull) == 0ull) st &= ~(1ull << 62);
+				}
+				while (st)
+				{
+					const int i = (int)KB_CLZLL(st) >> 1; st &= ~(1ull << (62 - 2 * i));
+					const int r = rs + i, g = r + d, lim = rl - r < gl - g ? rl - r : gl - g;
+					int l = 0;
+					while (l < lim)
+					{
+						u64 x = kb_read_code(rd, rp0 + r + l) ^ kb_ref_win(*ix, gp0 + g + l, &inv); x = (x | (x >> 1)) & M5;
+						const int same = x ? (int)KB_CLZLL(x) >> 1 : 32;
+						l += same;
+						if (same < 32) break;
+					}
+					if (l > lim) l = lim;
+					part_emit(r, g, l);
+				}
+			}
+		}
 	}
 	// all lanes: the exact-match runs of kb_kmer_pairs (min_len 8), appended in arbitrary order (part_finish sorts them by a total
 	// order). A lane takes read positions r = lane, lane + 32, ... and walks the diagonals |g - r| < shift of each: the id of r stays in
@@ -572,8 +662,9 @@ struct KbFragIter
 	// idx % nd spent 37 % of the kernel's instructions on the division and reloaded w1[r] for every cell).
 	KB_HD void part_pairs(int lane)
 	{
+		if (!dirty) { part_pairs_packed(lane); return; }
 		const int n1 = cur.rl - 7, n2 = cur.gl - 7;
-		if (n1 <= 0 || n2 <= 0) return;
+		if (n1 <= 0 || n2 <= 0 || w1 == nullptr || w2 == nullptr) return;
 		for (int r = lane; r < n1; r += 32)
 		{
 			const u32 id = w1[r];
@@ -586,8 +677,7 @@ struct KbFragIter
 				if (g > 0 && before != KB_NOKMER && before == w2[g - 1]) continue;   // not the start of its run
 				int run = 1;
 				while (r + run < n1 && g + run < n2 && w1[r + run] != KB_NOKMER && w1[r + run] == w2[g + run]) run++;
-				u32 slot = KB_ATOMIC_ADD(&np, 1u);
-				if ((int)slot < cap) { KbSeg sg; sg.simple = 1; sg.rpos = r; sg.gpos = (i64)g; sg.rlen = sg.glen = 8 + run - 1; raw[slot] = sg; }
+				part_emit(r, g, 8 + run - 1);
 			}
 		}
 	}
@@ -1013,21 +1103,17 @@ KB_HD void kb_pt_begin(const KbIndexDev& ix, const KbParams& pm, const KbBatchDe
 {
 	const KbJob& jb = bt.jobs[id];
 	w.job = id; w.ar.used = 0; w.ar.ovf = false; w.fast.used = 0; w.rlen = jb.rlen; w.glen = jb.glen;
-	w.f1 = (u8*)kb_alloc2(w.fast, w.ar, (u64)jb.rlen);
-	w.f2 = (u8*)kb_alloc2(w.fast, w.ar, (u64)jb.glen);
 	w.f1g = bt.seq + bt.seq_off[jb.read] + jb.rpos;
+	w.f1 = const_cast<u8*>(w.f1g); w.f2 = nullptr;   // the partition works on the packed read and text (KbFragIter); characters stay where they are
 	w.sink.ix = &ix; w.sink.bt = &bt; w.sink.job = id; w.sink.gpos = jb.gpos; w.sink.base = jb.run_off; w.sink.cap = (u32)(jb.rlen + jb.glen + 2); w.sink.cur = 0;
 	w.sink.ident = 0; w.sink.aligned = 0; w.sink.ovf = false;
-	w.ok = (w.f1 != nullptr && w.f2 != nullptr) ? 1 : 0;
-	if (w.ok) w.ok = w.it.init(&pm, &w.fast, &w.ar, w.f1, jb.rlen, w.f2, jb.glen, &w.sink) ? 1 : 0;
+	w.ok = w.it.init(&pm, &w.fast, &w.ar, w.f1, jb.rlen, w.f2, jb.glen, &w.sink) ? 1 : 0;
+	w.it.ix = &ix; w.it.rd = kb_pk_read(bt, (int)jb.read); w.it.rbase = jb.rpos; w.it.gbase = jb.gpos;
 }
-// all lanes: characters of the fragment into the warp's pool, and the job's slice of the run arena zeroed
+// all lanes: the job's slice of the run arena zeroed
 KB_HD void kb_pt_fetch(const KbIndexDev& ix, const KbBatchDev& bt, KbPartWarp& w, int t)
 {
 	if (!w.ok) return;
-	const i64 g = bt.jobs[w.job].gpos;
-	for (int i = t; i < w.glen; i += 32) w.f2[i] = kb_ref_char(ix, g + i);
-	for (int i = t; i < w.rlen; i += 32) w.f1[i] = w.f1g[i];
 	for (u32 i = (u32)t; i < w.sink.cap; i += 32) bt.runs[w.sink.base + i] = 0;
 }
 // lane 0: close the job (identities of the literal pieces; the nw_alignment pieces add theirs later)

@@ -192,6 +192,45 @@ def big_gap_reads(g):
     return reads
 
 
+def partition_stress_reads(g, n=24, seed=5, dirty=True):
+    """Reads whose middle stretches carry a substitution every 9..12 bases plus a few small indels: no seed survives there, so the stretch
+    becomes one fragment pair > 30 x 30 full of exact runs of 8..12 bases on neighbouring diagonals -- the 8-mer partition's food (runs that
+    cross the 25-position cells of part_pairs_packed, runs at the fragment ends, both strands). With `dirty`, every third read also gets an N
+    and a lower-case base inside the stretch: those fragments go through the literal id scan instead."""
+    rng = np.random.default_rng(seed)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    comp = np.zeros(256, dtype=np.uint8); comp[list(b"ACGT")] = list(b"TGCA")
+    reads = []
+    for k in range(n):
+        c = g[k % len(g)]
+        L = int(rng.integers(500, 2600))
+        at = int(rng.integers(0, len(c) - L - 1))
+        s = c[at:at + L].copy()
+        a, w = int(rng.integers(60, 150)), int(rng.integers(90, L - 200))
+        out, p = [s[:a]], a
+        while p < a + w:
+            step = int(rng.integers(9, 13))   # below MinSeedLength (13 on the small genomes): no seed inside the stretch
+            out.append(s[p:min(p + step, a + w)])
+            p += step
+            if p >= a + w:
+                break
+            u = rng.random()
+            if u < 0.75:
+                out.append(acgt[(np.searchsorted(acgt, s[p]) + 1 + rng.integers(0, 3)) % 4][None]); p += 1     # substitution
+            elif u < 0.88:
+                out.append(acgt[rng.integers(0, 4, size=int(rng.integers(1, 4)))])                              # insertion
+            else:
+                p += int(rng.integers(1, 4))                                                                     # deletion
+        out.append(s[a + w:])
+        r = np.concatenate(out)
+        if dirty and k % 3 == 2:
+            r[a + w // 2] = ord("N"); r[a + w // 3] = r[a + w // 3] + 32
+        if k % 2:
+            r = comp[r[::-1]] if not (dirty and k % 3 == 2) else r
+        reads.append(r.tobytes())
+    return reads
+
+
 def bam_equal(path, golden):
     """Byte-identical when the zlib in this process matches the one the golden was deflated with; always identical in the BGZF
     block structure (ISIZE sequence) and in the inflated BAM payload."""

@@ -98,6 +98,19 @@ def test_pacbio_vs_oracle(built):
     assert pu.compare_singles(m, pu.Oracle(pu.MINI_PREFIX, pacbio=True), r) == 0
 
 
+@pytest.mark.parametrize("pacbio", [False, True])
+def test_partition_on_packed_words_gpu(built, pacbio):
+    """The 8-mer partition of k_align_part on fragments full of short exact runs (part_pairs_packed: kb_match8 cells, run starts, runs across
+    cell borders, both strands) and on fragments with an N / a lower-case base (literal id scan), against the oracle."""
+    idx = KartIndex(pu.MINI_PREFIX)
+    g = pu.genome_of(idx)
+    reads = pu.partition_stress_reads(g, n=30 if pacbio else 24, seed=7 if pacbio else 5)
+    m = pu.make_mapper(idx, pacbio=pacbio)
+    assert pu.compare_singles(m, pu.Oracle(pu.MINI_PREFIX, pacbio=pacbio), reads) == 0
+    c = m.debug(9, np.uint32, 32)
+    assert c[23] >= len(reads) // 3, c[23]   # the partition did run
+
+
 @pytest.mark.parametrize("stack,raw", [("1", "1"), ("3", "4")])
 def test_partition_buffers_spill_gpu(built, monkeypatch, stack, raw):
     """The CUDA k_align_part with tiny shared-memory limits for the work stack and the run list (HBM part of the stack, part_grow's second pass)."""
