@@ -1283,7 +1283,10 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 	if (ctx->seed_queue && ix.sa_full != nullptr)
 	{
 		// with the full SA most searches finish against the text and reads differ widely in work: lane queue (kb_seed_lane)
-		unsigned warps = (unsigned)((n + 63) / 64); if (warps > (unsigned)ctx->seed_warps) warps = (unsigned)ctx->seed_warps; if (warps < 4) warps = 4;
+		// two reads per lane at least, so that the queue has something to balance -- but a long read is thousands of dependent steps on its
+		// own: those get a lane each, as many warps resident as there are reads (C5: 50 k reads were 782 warps = 5 per SM)
+		unsigned warps = sl.max_rlen >= 1000 ? (unsigned)((n + 31) / 32) : (unsigned)((n + 63) / 64);
+		if (warps > (unsigned)ctx->seed_warps) warps = (unsigned)ctx->seed_warps; if (warps < 4) warps = 4;
 		const unsigned gq = (warps + 3) / 4;
 		if (ctx->row32) { if (ctx->seed_minb == 12) { KB_LAUNCH((k_fm_seed_q<12, u32>), gq, KB_BLOCK, s, ix, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 6 : 2), ctx->seed_tail); } else { KB_LAUNCH((k_fm_seed_q<10, u32>), gq, KB_BLOCK, s, ix, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 6 : 2), ctx->seed_tail); } }
 		else { if (ctx->seed_minb == 12) { KB_LAUNCH((k_fm_seed_q<12, u64>), gq, KB_BLOCK, s, ix, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 6 : 2), ctx->seed_tail); } else { KB_LAUNCH((k_fm_seed_q<10, u64>), gq, KB_BLOCK, s, ix, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 6 : 2), ctx->seed_tail); } }

@@ -486,14 +486,18 @@ KB_HD void kb_seed_lane(const KbIndexDev& ix, const KbParams& pm, const KbBatchD
 	bool searching = false, closing = false, tail = false, finished = r < 0, ovf = false, fresh = !finished;
 	int cw = -1; u64 ccode = 0; u32 cn4 = 0;   // the packed word under the cursor
 #if defined(__CUDA_ARCH__)
-	const u32 quorum = (u32)qp, squorum = (u32)qs; const int min_trips = min_trips_arg;
+	const u32 quorum_max = (u32)qp, squorum_max = (u32)qs; const int min_trips = min_trips_arg;
 #else
-	const u32 quorum = 1, squorum = 1; const int min_trips = 1; (void)qp; (void)qs; (void)min_trips_arg;
+	const u32 quorum_max = 1, squorum_max = 1; const int min_trips = 1; (void)qp; (void)qs; (void)min_trips_arg;
 #endif
 	while (KB_BALLOT(!finished))
 	{
-		// a pass is worth its ~400 instructions when enough lanes take part (or nobody is walking the index); the same for trips
+		// a pass is worth its ~400 instructions when enough lanes take part (or nobody is walking the index); the same for trips.
+		// "Enough" is relative to the lanes that still have a read: a warp with 8 live lanes (long reads: 50 k x 7 kbp are 8 reads per warp;
+		// or the tail of any warp's range) must not wait for 8 parked ones -- r26, C5: the seeding kernel lasted 15 ms at one wave.
 		const u32 parked0 = KB_BALLOT(!searching && !finished), active0 = KB_BALLOT(searching);
+		const u32 live = (u32)KB_POPCLL((u64)(parked0 | active0));
+		const u32 quorum = quorum_max < (live + 1) / 2 ? quorum_max : (live + 1) / 2, squorum = squorum_max < (live + 1) / 2 ? squorum_max : (live + 1) / 2;
 		const bool do_pass = (u32)KB_POPCLL((u64)parked0) >= quorum || active0 == 0;
 		if (do_pass && !finished && !searching)
 		{
