@@ -72,12 +72,13 @@ def main():
             a = agg.setdefault(name, [0, 0.0, r[8], r[7]])
             a[0] += 1
             a[1] += float(r[-1]) / 1e3
-        tot = sum(v[1] for k, v in agg.items() if k not in ("k_reblock", "k_expand_sa"))
+        UPLOAD = ("k_reblock", "k_expand_sa", "k_build_ktab", "k_ref64")   # index upload, once per context: not part of a step
+        tot = sum(v[1] for k, v in agg.items() if k not in UPLOAD)
         o = ["# ncu launch list (%s): gpu__time_duration.sum per kernel, --clock-control none" % tag, "",
              "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py --steps 2 --warmup 1 --pairs 500000` (per-launch times are cold-cache and serialised; shares are what matter).", "",
              "| kernel | launches | total us | mean us | share of step (excl. upload kernels) | grid | block |", "|---|---|---|---|---|---|---|"]
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-            share = "" if k in ("k_reblock", "k_expand_sa") else "%.1f %%" % (100 * v[1] / tot)
+            share = "" if k in UPLOAD else "%.1f %%" % (100 * v[1] / tot)
             o.append("| %s | %d | %.1f | %.1f | %s | %s | %s |" % (k, v[0], v[1], v[1] / v[0], share, v[2], v[3]))
         open(os.path.join(ROOT, "profiles", tag + "_launches.md"), "w").write("\n".join(o) + "\n")
         import shutil
