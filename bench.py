@@ -197,11 +197,12 @@ def ncu_traffic(kernel, reads, workload_key):
     import glob
     import re
     best = None
-    for f in glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")):
+    sha = source_sha()
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json"))):   # file times do not survive a checkout: the capture of this build wins, else the last tag
         d = json.load(open(f))
         if d.get("workload") != workload_key:
             continue
-        if best is None or os.path.getmtime(f) > os.path.getmtime(best[0]):
+        if best is None or best[1].get("source_sha") != sha:
             best = (f, d)
     if best is None:
         return None, "no ncu capture of workload %s under profiles/" % workload_key
