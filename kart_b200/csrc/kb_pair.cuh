@@ -166,7 +166,7 @@ struct KbRescueFast
 	KbSeg pairs[KB_RF_PAIRS];
 	u8 hnext[256];
 	unsigned short cand[KB_RF_CAND];   // window positions that passed the filter (kb_rf_scan -> kb_rf_pairs)
-	u32 task, npairs, ncand, cand_cap; i32 ok, dirty, ml, slen, mate_read; i64 left;
+	u32 task, npairs, ncand, cand_cap; i32 ok, dirty, ml, slen, mate_read, stride; i64 left;
 };
 KB_HD u64 kb_rf_bits(const u64* w, int p)   // 32 bases starting at base p of a packed word array (one spare word behind the data)
 {
@@ -178,7 +178,7 @@ KB_HD void kb_rf_begin(const KbIndexDev& ix, const KbBatchDev& bt, KbRescueFast&
 {
 	const KbRTask t = bt.rtasks[task];
 	const int p = bt.rescue_list[t.job], ra = 2 * p, rb = ra + 1;
-	w.task = task; w.npairs = 0; w.ncand = 0; w.cand_cap = (u32)(bt.rf_cand < KB_RF_CAND ? (bt.rf_cand > 0 ? bt.rf_cand : 0) : KB_RF_CAND); w.dirty = 0;
+	w.task = task; w.npairs = 0; w.ncand = 0; w.cand_cap = (u32)(bt.rf_cand < KB_RF_CAND ? (bt.rf_cand > 0 ? bt.rf_cand : 0) : KB_RF_CAND); w.dirty = 0; w.stride = bt.rf_stride == 1 ? 1 : 3;
 	w.mate_read = t.side == 0 ? rb : ra;
 	w.ml = (int)(bt.seq_off[w.mate_read + 1] - bt.seq_off[w.mate_read]);
 	w.left = t.left; w.slen = t.slen;
@@ -219,22 +219,32 @@ KB_HD void kb_rf_fill(KbRescueFast& w, int lane)
 		KB_ATOMIC_OR(&w.filt[h >> 5], 1u << (h & 31));
 	}
 }
-// one lane: window position g passed the filter: look its 8-mer up in the mate's index and measure the runs that start here
-KB_HD void kb_rf_probe(KbRescueFast& w, int g, u32 id)
+// one lane: window position g passed the filter: look its 8-mer up in the mate's index and measure the runs that start here.
+// SAMPLED (every third window position is scanned, see kb_rf_scan): the 8-mer at (r, g) may lie up to two bases inside its run, so
+// the run is followed to the left first; three matching bases to the left mean that the sampled position g - 3 is inside the same
+// run and reports it.
+template <bool SAMPLED>
+KB_HD void kb_rf_probe(KbRescueFast& w, int g0, u32 id)
 {
 	const u64 M5 = 0x5555555555555555ull;
 	const int ml = w.ml, sl = w.slen;
 	u32 s = kb_rj_slot(id, KB_RF_SLOTS - 1), key;
 	while ((key = w.hkey[s]) != 0u && key != id + 1u) s = (s + 1u) & (u32)(KB_RF_SLOTS - 1);
 	if (key == 0u) return;
-	for (u32 r = w.hhead[s]; r < 255u; r = w.hnext[r])
+	for (u32 r0 = w.hhead[s]; r0 < 255u; r0 = w.hnext[r0])
 	{
-		if (r > 0 && g > 0 && ((w.mcode[(r - 1) >> 5] >> (62 - 2 * ((r - 1) & 31))) & 3ull) == ((w.wcode[(g - 1) >> 5] >> (62 - 2 * ((g - 1) & 31))) & 3ull)) continue;   // not the start of its run
-		const int lim = ml - (int)r < sl - g ? ml - (int)r : sl - g;
+		int r = (int)r0, g = g0, back = 0;
+		while (r > 0 && g > 0 && ((w.mcode[(r - 1) >> 5] >> (62 - 2 * ((r - 1) & 31))) & 3ull) == ((w.wcode[(g - 1) >> 5] >> (62 - 2 * ((g - 1) & 31))) & 3ull))
+		{
+			if (!SAMPLED || back == 2) { back = 3; break; }   // not the start of its run / the run reaches back to the previous sampled position
+			r--; g--; back++;
+		}
+		if (back == 3) continue;
+		const int lim = ml - r < sl - g ? ml - r : sl - g;
 		int l = 0;
 		while (l < lim)
 		{
-			u64 x = kb_rf_bits(w.mcode, (int)r + l) ^ kb_rf_bits(w.wcode, g + l); x = (x | (x >> 1)) & M5;
+			u64 x = kb_rf_bits(w.mcode, r + l) ^ kb_rf_bits(w.wcode, g + l); x = (x | (x >> 1)) & M5;
 			const int same = x ? (int)KB_CLZLL(x) >> 1 : 32;
 			l += same;
 			if (same < 32) break;
@@ -251,10 +261,33 @@ KB_HD void kb_rf_probe(KbRescueFast& w, int g, u32 id)
 // probed right away held the other 31 up for ~100 instructions whenever any lane passed (ncu r24: the scan ran at 16 of 32 lanes).
 // Probe: the noted positions are dealt round-robin, so the ~150 consecutive positions of a real copy of the mate spread over all
 // lanes. Positions beyond the list's capacity are probed on the spot.
+// Sampling (r32): a run of >= 10 bases holds the 8-mers at >= 3 consecutive window positions, so every third position (g = 0, 3, 6 ...)
+// meets each such run at least once, at most two bases behind its start: a third of the filter tests, the same set of runs
+// (kb_rf_probe<true> walks back to the start and leaves the run to the earlier sampled position when there is one). One 32-base fetch
+// serves nine sampled positions. KB_RF_STRIDE=1 scans every position (the r24 schedule) for the A/B.
 KB_HD void kb_rf_scan(KbRescueFast& w, int lane)
 {
 	if (!w.ok || w.dirty) return;
-	const int npos = w.slen - 7, ngroups = (npos + 7) >> 3;
+	const int npos = w.slen - 7;
+	if (w.stride == 3)
+	{
+		const int ngroups = (npos + 26) / 27;
+		for (int grp = lane; grp < ngroups; grp += 32)
+		{
+			u64 bits = kb_rf_bits(w.wcode, grp * 27);
+			const int gend = grp * 27 + 27 < npos ? grp * 27 + 27 : npos;
+			for (int g = grp * 27; g < gend; g += 3, bits <<= 6)
+			{
+				const u32 id = (u32)(bits >> 48);
+				const u32 h = kb_rf_fold(id);
+				if (((w.filt[h >> 5] >> (h & 31)) & 1u) == 0u) continue;
+				const u32 at = KB_ATOMIC_ADD(&w.ncand, 1u);
+				if (at < w.cand_cap) w.cand[at] = (unsigned short)g; else kb_rf_probe<true>(w, g, id);
+			}
+		}
+		return;
+	}
+	const int ngroups = (npos + 7) >> 3;
 	for (int grp = lane; grp < ngroups; grp += 32)
 	{
 		u64 bits = kb_rf_bits(w.wcode, grp << 3);
@@ -265,7 +298,7 @@ KB_HD void kb_rf_scan(KbRescueFast& w, int lane)
 			const u32 h = kb_rf_fold(id);
 			if (((w.filt[h >> 5] >> (h & 31)) & 1u) == 0u) continue;
 			const u32 at = KB_ATOMIC_ADD(&w.ncand, 1u);
-			if (at < w.cand_cap) w.cand[at] = (unsigned short)g; else kb_rf_probe(w, g, id);
+			if (at < w.cand_cap) w.cand[at] = (unsigned short)g; else kb_rf_probe<false>(w, g, id);
 		}
 	}
 }
@@ -273,7 +306,11 @@ KB_HD void kb_rf_pairs(KbRescueFast& w, int lane)
 {
 	if (!w.ok || w.dirty) return;
 	const int n = (int)(w.ncand < w.cand_cap ? w.ncand : w.cand_cap);
-	for (int i = lane; i < n; i += 32) { const int g = (int)w.cand[i]; kb_rf_probe(w, g, (u32)(kb_rf_bits(w.wcode, g) >> 48)); }
+	for (int i = lane; i < n; i += 32)
+	{
+		const int g = (int)w.cand[i]; const u32 id = (u32)(kb_rf_bits(w.wcode, g) >> 48);
+		if (w.stride == 3) kb_rf_probe<true>(w, g, id); else kb_rf_probe<false>(w, g, id);
+	}
 }
 // lane 0: the task's result (kb_rt_end), or the task's place on the slow list
 KB_HD void kb_rf_end(const KbParams& pm, const KbBatchDev& bt, KbRescueFast& w)

@@ -139,6 +139,7 @@ struct KbBatchDev
 	i32 nw_tmax;                        // largest side one thread solves (<= KB_NW_TMAX); larger problems go to the warp wavefront kernel
 	i32 nw_warp_below;                  // a column-tile class with fewer problems than this goes to the warp wavefront kernel as well
 	i32 rf_cand;                        // k_rescue_fast: filter-passing window positions noted for the probe phase (the rest is probed on the spot)
+	i32 rf_stride;                      // k_rescue_fast: 3 = every third window position is scanned (kb_rf_scan), 1 = every position
 	i32 part_stack, part_raw;           // k_align_part: entries of a job's work stack / of its exact-match run list that are tried in the warp's shared-memory pool first (the rest, and an overflowing run list, live in the HBM arena)
 	i32 seg_cap, kmer_cap;
 	// counters: [0] seeds cursor [1] cands cursor [2] cigar cursor [3] status bits [4] rescue count [5] max seeds/read

@@ -231,6 +231,21 @@ def partition_stress_reads(g, n=24, seed=5, dirty=True):
     return reads
 
 
+def repeat_rich_text(length=120000, seed=3):
+    """A genome for the rescue stress tests: random bases with 150 micro-satellites / homopolymers (units of 1..6 bases, 20..200 bases
+    long: mates whose 8-mers repeat, long chains in the mate index) and 60 copies of a 300-bp family at 4 % divergence."""
+    rng = np.random.default_rng(seed)
+    g = rng.integers(0, 4, length)
+    for _ in range(150):
+        p = rng.integers(0, length - 400); unit = rng.integers(0, 4, rng.integers(1, 7)); n = rng.integers(20, 200)
+        g[p:p + n] = np.resize(unit, n)
+    fam = rng.integers(0, 4, 300)
+    for _ in range(60):
+        p = rng.integers(0, length - 400); c = fam.copy(); m = rng.random(300) < 0.04
+        c[m] = rng.integers(0, 4, int(m.sum())); g[p:p + 300] = c
+    return "".join("ACGT"[c] for c in g)
+
+
 def bam_equal(path, golden):
     """Byte-identical when the zlib in this process matches the one the golden was deflated with; always identical in the BGZF
     block structure (ISIZE sequence) and in the inflated BAM payload."""

@@ -246,10 +246,31 @@ def test_rescue_fast_path_and_fallback(built, monkeypatch):
         monkeypatch.setenv("KB_RF_CAND", cap)
         assert pu.compare_pairs(pu.make_mapper(idx, paired=True), orc, reads) == 0
     monkeypatch.delenv("KB_RF_CAND")
+    monkeypatch.setenv("KB_RF_STRIDE", "1")   # every window position scanned instead of every third
+    assert pu.compare_pairs(pu.make_mapper(idx, paired=True), orc, reads) == 0
+    monkeypatch.delenv("KB_RF_STRIDE")
     monkeypatch.setenv("KB_RESCUE_FAST", "0")
     m = pu.make_mapper(idx, paired=True)
     assert pu.compare_pairs(m, orc, reads) == 0
     assert m.debug(9, np.uint32, 32)[29] == m.debug(9, np.uint32, 32)[27]
+
+
+def test_rescue_sampled_scan_repeat_rich(built, tmp_path, monkeypatch):
+    """k_rescue_fast scans every third window position (a run of >= 10 bases holds three consecutive 8-mers) and walks back to the
+    run's start: same pairs as the oracle on a genome of micro-satellites and a diverged repeat family at 10 % read error, where
+    thousands of windows are rescued and the mate's 8-mer chains are long; the every-position scan next to it."""
+    import stage_util as su
+    prefix, _ = su.text_index(str(tmp_path), [pu.repeat_rich_text()])
+    idx = KartIndex(prefix)
+    r1, r2, _ = synth.simulate(pu.genome_of(idx), 20000, 150, 0.10, seed=11, indel=0.01)
+    reads = pu.interleave(r1, r2)
+    orc = pu.Oracle(prefix)
+    for stride in ("3", "1"):
+        monkeypatch.setenv("KB_RF_STRIDE", stride)
+        m = pu.make_mapper(idx, paired=True)
+        assert pu.compare_pairs(m, orc, reads) == 0
+        c = m.debug(9, np.uint32, 32)
+        assert m.work()["rescues"] > 4000 and c[27] - c[29] > 1500, (m.work()["rescues"], c[27], c[29])
 
 
 @pytest.mark.parametrize("plan", [{"KB_PIPE_SUB_READS": "65536"}, {"KB_PIPE_SUB_READS": "100000", "KB_PIPE_FIRST": "8192", "KB_PIPE_GROW": "150", "KB_PIPE_TAIL": "8192"}])
