@@ -402,22 +402,28 @@ __global__ void __launch_bounds__(KB_BLOCK) k_rescue_fast(KbIndexDev ix, KbParam
 	if (bt.counters[3]) return;
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	KbRescueFast& w = reinterpret_cast<KbRescueFast*>(rf_pool)[wib];
-	const u32 count = bt.counters[27];
+	const u32 count = bt.counters[27], batch = (u32)(bt.rf_batch > 0 ? bt.rf_batch : 1);
+	if (lane == 0) w.have_mate = -1;
 	while (true)
 	{
-		if (lane == 0) ticket[wib] = atomicAdd(&bt.counters[25], 1u);
+		// a warp draws `batch` consecutive windows: a job's windows follow each other, so most of them face the mate whose index is in place
+		if (lane == 0) ticket[wib] = atomicAdd(&bt.counters[25], batch);
 		__syncwarp();
-		const u32 q = ticket[wib];
+		const u32 q0 = ticket[wib];
 		__syncwarp();
-		if (q >= count) break;
-		if (lane == 0) kb_rf_begin(ix, bt, w, q);
-		__syncwarp();
-		kb_rf_load(ix, bt, w, lane); __syncwarp();
-		kb_rf_fill(w, lane); __syncwarp();
-		kb_rf_scan(w, lane); __syncwarp();
-		kb_rf_pairs(w, lane); __syncwarp();
-		if (lane == 0) kb_rf_end(pm, bt, w);
-		__syncwarp();
+		if (q0 >= count) break;
+		const u32 q1 = q0 + batch < count ? q0 + batch : count;
+		for (u32 q = q0; q < q1; q++)
+		{
+			if (lane == 0) kb_rf_begin(ix, bt, w, q);
+			__syncwarp();
+			kb_rf_load(ix, bt, w, lane); __syncwarp();
+			kb_rf_fill(w, lane); __syncwarp();
+			kb_rf_scan(w, lane); __syncwarp();
+			kb_rf_pairs(w, lane); __syncwarp();
+			if (lane == 0) kb_rf_end(pm, bt, w);
+			__syncwarp();
+		}
 	}
 }
 #else
@@ -427,6 +433,7 @@ static void k_rescue_fast(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulat
 	if (bt.counters[3]) return;
 	static thread_local KbRescueFast w;
 	const u32 count = bt.counters[27];
+	w.have_mate = -1;
 	for (u32 q = 0; q < count; q++)
 	{
 		kb_rf_begin(ix, bt, w, q);
@@ -777,6 +784,8 @@ struct kb_ctx
 	int part_warps = 148 * 40, part_pool = 4096;   // k_align_part: warps in the grid (each with an HBM arena) and shared-memory pool bytes per warp (r14 A/B: 8 warps/SM + 10 KB pool 2.34 ms -> 40 warps/SM + 4 KB 1.34 ms for the align stage at C2)
 	int nw_tmax = 0;             // largest side one thread solves (0: KB_NW_TMAX); KB_NW_TMAX=32|64 sends more to the wavefront kernel
 	int rf_cand = 256;           // KB_RF_CAND (<= 256)
+	int seed_ld_hint = 0;        // KB_SEED_LD_HINT=1: Occ blocks, seeding-table and SA entries are loaded with L1::no_allocate in the seeding kernels
+	int rf_reuse = 1, rf_batch = 4;   // k_rescue_fast: the mate's 8-mer index is kept while consecutive windows face the same mate; windows a warp draws per ticket (KB_RF_REUSE, KB_RF_BATCH)
 	int rf_stride = 3;           // KB_RF_STRIDE: 3 = k_rescue_fast scans every third window position, 1 = every position
 	int part_stack = 24, part_raw = 40;   // KB_PART_STACK / KB_PART_RAW: see KbBatchDev
 	int nw_warp_below = 8192;    // a column-tile class (33..64, 65..128) with fewer problems than this is solved by k_nw_warp instead
@@ -871,6 +880,9 @@ int kb_init(int device, kb_ctx_t** out)
 	e = getenv("KB_SEED_WARPS"); if (e && atoi(e) >= 4 && atoi(e) <= 148 * 64) ctx->seed_warps = atoi(e);
 	e = getenv("KB_NW_WARP_BELOW"); if (e && atoi(e) >= 0) ctx->nw_warp_below = atoi(e);
 	e = getenv("KB_RF_CAND"); if (e && atoi(e) >= 0 && atoi(e) <= 256) ctx->rf_cand = atoi(e);
+	e = getenv("KB_SEED_LD_HINT"); if (e) ctx->seed_ld_hint = atoi(e) ? 1 : 0;
+	e = getenv("KB_RF_REUSE"); if (e) ctx->rf_reuse = atoi(e) ? 1 : 0;
+	e = getenv("KB_RF_BATCH"); if (e && atoi(e) >= 1 && atoi(e) <= 64) ctx->rf_batch = atoi(e);
 	e = getenv("KB_RF_STRIDE"); if (e && (atoi(e) == 1 || atoi(e) == 3)) ctx->rf_stride = atoi(e);
 	e = getenv("KB_PART_STACK"); if (e && atoi(e) >= 1) ctx->part_stack = atoi(e);
 	e = getenv("KB_PART_RAW"); if (e && atoi(e) >= 1) ctx->part_raw = atoi(e);
@@ -1161,7 +1173,7 @@ static int alloc_batch(kb_ctx* ctx, kb_slot& sl, int shared)
 	else { bt.cigar = sl.cigar.p; bt.cap_cigar = (u32)sl.cap_cigar; bt.cig_cursor = sl.counters.p + 2; }
 	bt.scratch = sl.scratch.p; bt.scratch_per_thread = per; bt.scratch_threads = (int)threads;
 	bt.wscratch = sl.wscratch.p; bt.wscratch_per_warp = per; bt.wscratch_warps = wwarps;
-	bt.max_rlen = L; bt.nw_tmax = ctx->nw_tmax > 0 ? ctx->nw_tmax : KB_NW_TMAX; bt.nw_warp_below = ctx->nw_warp_below; bt.rf_cand = ctx->rf_cand; bt.rf_stride = ctx->rf_stride; bt.part_stack = ctx->part_stack; bt.part_raw = ctx->part_raw; bt.seg_cap = 0; bt.kmer_cap = 0; bt.counters = sl.counters.p; bt.work = sl.work.p;
+	bt.max_rlen = L; bt.nw_tmax = ctx->nw_tmax > 0 ? ctx->nw_tmax : KB_NW_TMAX; bt.nw_warp_below = ctx->nw_warp_below; bt.rf_cand = ctx->rf_cand; bt.rf_stride = ctx->rf_stride; bt.rf_reuse = ctx->rf_reuse; bt.rf_batch = ctx->rf_batch; bt.part_stack = ctx->part_stack; bt.part_raw = ctx->part_raw; bt.seg_cap = 0; bt.kmer_cap = 0; bt.counters = sl.counters.p; bt.work = sl.work.p;
 	return KB_OK;
 }
 
@@ -1282,6 +1294,7 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 	sl.launches = 0;
 	CK(cudaEventRecord(sl.ev[0], s));
 	launch_pack(sl);
+	KbIndexDev ixs = ix; ixs.ld_hint = ctx->seed_ld_hint;   // the seeding kernels' loads of Occ blocks, table and SA entries (kb_load_blk)
 	if (ctx->seed_queue && ix.sa_full != nullptr)
 	{
 		// with the full SA most searches finish against the text and reads differ widely in work: lane queue (kb_seed_lane)
@@ -1290,21 +1303,21 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 		unsigned warps = sl.max_rlen >= 1000 ? (unsigned)((n + 31) / 32) : (unsigned)((n + 63) / 64);
 		if (warps > (unsigned)ctx->seed_warps) warps = (unsigned)ctx->seed_warps; if (warps < 4) warps = 4;
 		const unsigned gq = (warps + 3) / 4;
-		if (ctx->row32) { if (ctx->seed_minb == 12) { KB_LAUNCH((k_fm_seed_q<12, u32>), gq, KB_BLOCK, s, ix, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 6 : 2), ctx->seed_tail); } else { KB_LAUNCH((k_fm_seed_q<10, u32>), gq, KB_BLOCK, s, ix, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 6 : 2), ctx->seed_tail); } }
-		else { if (ctx->seed_minb == 12) { KB_LAUNCH((k_fm_seed_q<12, u64>), gq, KB_BLOCK, s, ix, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 6 : 2), ctx->seed_tail); } else { KB_LAUNCH((k_fm_seed_q<10, u64>), gq, KB_BLOCK, s, ix, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 6 : 2), ctx->seed_tail); } }
+		if (ctx->row32) { if (ctx->seed_minb == 12) { KB_LAUNCH((k_fm_seed_q<12, u32>), gq, KB_BLOCK, s, ixs, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 6 : 2), ctx->seed_tail); } else { KB_LAUNCH((k_fm_seed_q<10, u32>), gq, KB_BLOCK, s, ixs, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 6 : 2), ctx->seed_tail); } }
+		else { if (ctx->seed_minb == 12) { KB_LAUNCH((k_fm_seed_q<12, u64>), gq, KB_BLOCK, s, ixs, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 6 : 2), ctx->seed_tail); } else { KB_LAUNCH((k_fm_seed_q<10, u64>), gq, KB_BLOCK, s, ixs, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 6 : 2), ctx->seed_tail); } }
 	}
 	else
 	if (ctx->row32)
 	{
-		if (ctx->seed_minb == 8) { KB_LAUNCH((k_fm_seed<8, u32>), g_reads, KB_BLOCK, s, ix, pm, bt); }
-		else if (ctx->seed_minb == 12) { KB_LAUNCH((k_fm_seed<12, u32>), g_reads, KB_BLOCK, s, ix, pm, bt); }
-		else { KB_LAUNCH((k_fm_seed<10, u32>), g_reads, KB_BLOCK, s, ix, pm, bt); }
+		if (ctx->seed_minb == 8) { KB_LAUNCH((k_fm_seed<8, u32>), g_reads, KB_BLOCK, s, ixs, pm, bt); }
+		else if (ctx->seed_minb == 12) { KB_LAUNCH((k_fm_seed<12, u32>), g_reads, KB_BLOCK, s, ixs, pm, bt); }
+		else { KB_LAUNCH((k_fm_seed<10, u32>), g_reads, KB_BLOCK, s, ixs, pm, bt); }
 	}
 	else
 	{
-		if (ctx->seed_minb == 8) { KB_LAUNCH((k_fm_seed<8, u64>), g_reads, KB_BLOCK, s, ix, pm, bt); }
-		else if (ctx->seed_minb == 12) { KB_LAUNCH((k_fm_seed<12, u64>), g_reads, KB_BLOCK, s, ix, pm, bt); }
-		else { KB_LAUNCH((k_fm_seed<10, u64>), g_reads, KB_BLOCK, s, ix, pm, bt); }
+		if (ctx->seed_minb == 8) { KB_LAUNCH((k_fm_seed<8, u64>), g_reads, KB_BLOCK, s, ixs, pm, bt); }
+		else if (ctx->seed_minb == 12) { KB_LAUNCH((k_fm_seed<12, u64>), g_reads, KB_BLOCK, s, ixs, pm, bt); }
+		else { KB_LAUNCH((k_fm_seed<10, u64>), g_reads, KB_BLOCK, s, ixs, pm, bt); }
 	}
 	sl.launches++;
 	CK(cudaEventRecord(sl.ev[1], s));

@@ -158,18 +158,34 @@ KB_HD void kb_count32(u64 W, int n, u32 cnt[4])
 // [u32 cntA,cntC,cntG,cntT : occurrences before the block][u64 lo][u64 hi]: the 64 BWT symbols of the block as two bit
 // planes (low and high bit of the 2-bit code), row i of the block at bit 63-i. Rank queries are then one mask per plane.
 struct KbBlk { u32 c0, c1, c2, c3; u64 lo, hi; };
-KB_HD KbBlk kb_load_blk(const uint32_t* occ, u64 blk)
+// hint (KbIndexDev::ld_hint, seeding only): 1 = the sector is not kept in L1 (ld.global.nc.L1::no_allocate). Occ blocks, seeding-table
+// entries and SA entries are visited once, at random; allocating them evicts the packed read words the same lanes come back to.
+KB_HD KbBlk kb_load_blk(const uint32_t* occ, u64 blk, int hint = 0)
 {
 	KbBlk b; const uint32_t* p = occ + (blk << 3);
 #if defined(__CUDA_ARCH__)
 	u32 l0, l1, h0, h1;
-	asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-	             : "=r"(b.c0), "=r"(b.c1), "=r"(b.c2), "=r"(b.c3), "=r"(l0), "=r"(l1), "=r"(h0), "=r"(h1) : "l"(p));
+	if (hint)
+		asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		             : "=r"(b.c0), "=r"(b.c1), "=r"(b.c2), "=r"(b.c3), "=r"(l0), "=r"(l1), "=r"(h0), "=r"(h1) : "l"(p));
+	else
+		asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		             : "=r"(b.c0), "=r"(b.c1), "=r"(b.c2), "=r"(b.c3), "=r"(l0), "=r"(l1), "=r"(h0), "=r"(h1) : "l"(p));
 	b.lo = ((u64)l1 << 32) | l0; b.hi = ((u64)h1 << 32) | h0;
 #else
+	(void)hint;
 	b.c0 = p[0]; b.c1 = p[1]; b.c2 = p[2]; b.c3 = p[3]; b.lo = ((u64)p[5] << 32) | p[4]; b.hi = ((u64)p[7] << 32) | p[6];
 #endif
 	return b;
+}
+KB_HD u64 kb_load_u64_once(const u64* p, int hint)
+{
+#if defined(__CUDA_ARCH__)
+	if (hint) { u64 v; asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p)); return v; }
+#else
+	(void)hint;
+#endif
+	return KB_LDG(p);
 }
 KB_HD u64 kb_top_bits(u32 n) { return n == 0 ? 0ull : (~0ull << (64u - n)); }   // the first n (0..64) rows of a block
 KB_HD u32 kb_sel4(int b, u32 v0, u32 v1, u32 v2, u32 v3) { u32 lo = (b & 1) ? v1 : v0, hi = (b & 1) ? v3 : v2; return (b & 2) ? hi : lo; }
@@ -203,7 +219,7 @@ KB_HD bool kb_extend(const KbIndexDev& ix, ROW& x0, ROW& x1, ROW& x2, int c, u32
 	u32 ek, n2, gt;
 	if (((rk + 1) >> 6) == (rl >> 6))
 	{
-		const KbBlk B = kb_load_blk(ix.occ, (u64)(rl >> 6)); *blocks += 1;
+		const KbBlk B = kb_load_blk(ix.occ, (u64)(rl >> 6), ix.ld_hint); *blocks += 1;
 		const u64 pk = kb_top_bits((u32)((rk + 1) & 63)), rg = kb_top_bits((u32)(rl & 63) + 1u) & ~pk;   // rows (k', l']
 		const u64 e = (B.lo ^ nBL) & (B.hi ^ nBH);
 		n2 = (u32)KB_POPCLL(e & rg);
@@ -218,7 +234,7 @@ KB_HD bool kb_extend(const KbIndexDev& ix, ROW& x0, ROW& x1, ROW& x2, int c, u32
 	}
 	else
 	{
-		const KbBlk bk = kb_load_blk(ix.occ, (u64)(rk >> 6)), bl = kb_load_blk(ix.occ, (u64)(rl >> 6)); *blocks += 2;
+		const KbBlk bk = kb_load_blk(ix.occ, (u64)(rk >> 6), ix.ld_hint), bl = kb_load_blk(ix.occ, (u64)(rl >> 6), ix.ld_hint); *blocks += 2;
 		u32 gk, el, gl;
 		kb_rank_eq_gt(bk, (int)(rk & 63), b, &ek, &gk);
 		kb_rank_eq_gt(bl, (int)(rl & 63), b, &el, &gl);
@@ -259,13 +275,15 @@ KB_HD KbKtab kb_ktab_entry(const KbIndexDev& ix, u64 kmer, int K)
 	if (x2 == 0) return kb_ktab_pack(0, 0, 0, (u32)K);   // a base that does not occur (K == 1 only)
 	return kb_ktab_pack(x0, x1, x2, 0);
 }
-KB_HD KbKtabE kb_load_ktab(const KbKtab* p)
+KB_HD KbKtabE kb_load_ktab(const KbKtab* p, int hint = 0)
 {
 #if defined(__CUDA_ARCH__)
 	u32 r[4];
-	asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "l"(p));
+	if (hint) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "l"(p));
+	else asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "l"(p));
 	return kb_ktab_unpack(((u64)r[1] << 32) | r[0], ((u64)r[3] << 32) | r[2]);
 #else
+	(void)hint;
 	return kb_ktab_unpack(p->a, p->b);
 #endif
 }
@@ -304,7 +322,7 @@ KB_HD u64 kb_ref_win(const KbIndexDev& ix, i64 p, u32* inval);   // kb_align.cuh
 KB_HD int kb_unique_tail(const KbIndexDev& ix, const KbPk* rd, u64 row, int done, int cur, int lim, bool* fail, u32* blocks)
 {
 	const u64 M5 = 0x5555555555555555ull;
-	const i64 tp = (i64)KB_LDG(ix.sa_full + row) + (i64)done;   // text position facing read position cur
+	const i64 tp = (i64)kb_load_u64_once(ix.sa_full + row, ix.ld_hint) + (i64)done;   // text position facing read position cur
 	*blocks += 1; *fail = false;
 	int m = 0;
 	while (cur + m < lim)
@@ -402,7 +420,7 @@ KB_HD void kb_seed_read(const KbIndexDev& ix, const KbParams& pm, const KbBatchD
 				const KbPk w = kb_read_win(rd, pos);
 				if ((w.n4 >> (32 - K)) == 0)
 				{
-					const KbKtabE e = kb_load_ktab(ix.ktab + (u32)(w.code >> (64 - 2 * K))); blocks++;
+					const KbKtabE e = kb_load_ktab(ix.ktab + (u32)(w.code >> (64 - 2 * K)), ix.ld_hint); blocks++;
 					seeded = true;
 					if (e.x2 != 0) { x0 = (ROW)e.x0; x1 = (ROW)e.x1; x2 = (ROW)e.x2; cur = pos + K; steps += (u32)(K - 1); searching = true; }
 					else { closing = true; len = (int)e.flen; steps += e.flen; x2 = 0; }
@@ -553,7 +571,7 @@ KB_HD void kb_seed_lane(const KbIndexDev& ix, const KbParams& pm, const KbBatchD
 					const KbPk w = kb_read_win(rd, pos);
 					if ((w.n4 >> (32 - K)) == 0)
 					{
-						const KbKtabE e = kb_load_ktab(ix.ktab + (u32)(w.code >> (64 - 2 * K))); blocks++;
+						const KbKtabE e = kb_load_ktab(ix.ktab + (u32)(w.code >> (64 - 2 * K)), ix.ld_hint); blocks++;
 						seeded = true;
 						if (e.x2 != 0) { x0 = (ROW)e.x0; x1 = (ROW)e.x1; x2 = (ROW)e.x2; cur = pos + K; steps += (u32)(K - 1); searching = true; }
 						else { closing = true; len = (int)e.flen; steps += e.flen; x2 = 0; }

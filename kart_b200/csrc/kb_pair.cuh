@@ -167,6 +167,7 @@ struct KbRescueFast
 	u8 hnext[256];
 	unsigned short cand[KB_RF_CAND];   // window positions that passed the filter (kb_rf_scan -> kb_rf_pairs)
 	u32 task, npairs, ncand, cand_cap; i32 ok, dirty, ml, slen, mate_read, stride; i64 left;
+	i32 have_mate, same;   // the mate whose index is in place (-1: none) ; this task faces the same mate: index, filter and packed mate are kept
 };
 KB_HD u64 kb_rf_bits(const u64* w, int p)   // 32 bases starting at base p of a packed word array (one spare word behind the data)
 {
@@ -178,24 +179,30 @@ KB_HD void kb_rf_begin(const KbIndexDev& ix, const KbBatchDev& bt, KbRescueFast&
 {
 	const KbRTask t = bt.rtasks[task];
 	const int p = bt.rescue_list[t.job], ra = 2 * p, rb = ra + 1;
-	w.task = task; w.npairs = 0; w.ncand = 0; w.cand_cap = (u32)(bt.rf_cand < KB_RF_CAND ? (bt.rf_cand > 0 ? bt.rf_cand : 0) : KB_RF_CAND); w.dirty = 0; w.stride = bt.rf_stride == 1 ? 1 : 3;
+	w.task = task; w.npairs = 0; w.ncand = 0; w.cand_cap = (u32)(bt.rf_cand < KB_RF_CAND ? (bt.rf_cand > 0 ? bt.rf_cand : 0) : KB_RF_CAND); w.stride = bt.rf_stride == 1 ? 1 : 3;
 	w.mate_read = t.side == 0 ? rb : ra;
-	w.ml = (int)(bt.seq_off[w.mate_read + 1] - bt.seq_off[w.mate_read]);
 	w.left = t.left; w.slen = t.slen;
+	// a job's windows of one side follow each other and face the same mate: its 8-mer index is built once per run of such tasks
+	w.same = (w.have_mate == w.mate_read) ? 1 : 0;
+	if (!w.same) { w.ml = (int)(bt.seq_off[w.mate_read + 1] - bt.seq_off[w.mate_read]); w.dirty = 0; }
 	w.ok = (t.left >= 0 && t.left + (i64)t.slen <= ix.G2 && t.slen <= 2048 && w.ml >= 8 && w.ml <= 255) ? 1 : 0;
+	if (!w.same) w.have_mate = (w.ok && bt.rf_reuse) ? w.mate_read : -1;   // set before the lanes fill it: a task that is not ok leaves the old index untouched but unusable
 }
 // all lanes: clear the index, fetch the packed mate (flagging characters that are no bases) and the packed window
 KB_HD void kb_rf_load(const KbIndexDev& ix, const KbBatchDev& bt, KbRescueFast& w, int lane)
 {
 	if (!w.ok) return;
-	for (int s = lane; s < KB_RF_SLOTS; s += 32) { w.hkey[s] = 0; w.hhead[s] = 0xFFFFFFFFu; w.filt[s] = 0; }
-	const KbPk* rd = kb_pk_read(bt, w.mate_read);
-	const int mw = (w.ml + 31) >> 5;
-	for (int k = lane; k < 10; k += 32)
+	if (!w.same)
 	{
-		u64 code = 0;
-		if (k < mw) { const KbPk v = kb_load_pk(rd + k); code = v.code; u32 n4 = v.n4; const int rem = w.ml - 32 * k; if (rem < 32) n4 &= ~(~0u >> rem); if (n4) w.dirty = 1; }
-		w.mcode[k] = code;
+		for (int s = lane; s < KB_RF_SLOTS; s += 32) { w.hkey[s] = 0; w.hhead[s] = 0xFFFFFFFFu; w.filt[s] = 0; }
+		const KbPk* rd = kb_pk_read(bt, w.mate_read);
+		const int mw = (w.ml + 31) >> 5;
+		for (int k = lane; k < 10; k += 32)
+		{
+			u64 code = 0;
+			if (k < mw) { const KbPk v = kb_load_pk(rd + k); code = v.code; u32 n4 = v.n4; const int rem = w.ml - 32 * k; if (rem < 32) n4 &= ~(~0u >> rem); if (n4) w.dirty = 1; }
+			w.mcode[k] = code;
+		}
 	}
 	const int ww = ((w.slen + 31) >> 5) + 1;
 	for (int k = lane; k < ww; k += 32) { u32 inv; w.wcode[k] = kb_ref_win(ix, w.left + 32 * (i64)k, &inv); }
@@ -203,7 +210,7 @@ KB_HD void kb_rf_load(const KbIndexDev& ix, const KbBatchDev& bt, KbRescueFast& 
 // all lanes: index the mate's 8-mers
 KB_HD void kb_rf_fill(KbRescueFast& w, int lane)
 {
-	if (!w.ok || w.dirty) return;
+	if (!w.ok || w.dirty || w.same) return;
 	for (int r = lane; r + 8 <= w.ml; r += 32)
 	{
 		const u32 id = (u32)(kb_rf_bits(w.mcode, r) >> 48);

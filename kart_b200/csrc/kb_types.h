@@ -70,6 +70,7 @@ struct KbIndexDev
 	const i64* chr_len;
 	const u8* mapq_lut;      // [score][diff-1], diff = 1..5 ; built on the host with the reference expression
 	i32 mapq_lut_scores;
+	i32 ld_hint;             // seeding kernels: 1 = Occ blocks, table and SA entries bypass L1 allocation (kb_load_blk)
 };
 
 // 32 read characters: nt4 codes (2 bit, MSB first, 0 where the character is no base), n4 = "nt4 code is 4" and
@@ -139,6 +140,7 @@ struct KbBatchDev
 	i32 nw_tmax;                        // largest side one thread solves (<= KB_NW_TMAX); larger problems go to the warp wavefront kernel
 	i32 nw_warp_below;                  // a column-tile class with fewer problems than this goes to the warp wavefront kernel as well
 	i32 rf_cand;                        // k_rescue_fast: filter-passing window positions noted for the probe phase (the rest is probed on the spot)
+	i32 rf_reuse, rf_batch;             // k_rescue_fast: keep the mate's 8-mer index across consecutive windows of one mate ; windows per ticket
 	i32 rf_stride;                      // k_rescue_fast: 3 = every third window position is scanned (kb_rf_scan), 1 = every position
 	i32 part_stack, part_raw;           // k_align_part: entries of a job's work stack / of its exact-match run list that are tried in the warp's shared-memory pool first (the rest, and an overflowing run list, live in the HBM arena)
 	i32 seg_cap, kmer_cap;

@@ -265,8 +265,9 @@ def test_rescue_sampled_scan_repeat_rich(built, tmp_path, monkeypatch):
     r1, r2, _ = synth.simulate(pu.genome_of(idx), 20000, 150, 0.10, seed=11, indel=0.01)
     reads = pu.interleave(r1, r2)
     orc = pu.Oracle(prefix)
-    for stride in ("3", "1"):
+    for stride, reuse in (("3", "1"), ("1", "1"), ("3", "0")):   # reuse: the mate's 8-mer index kept across consecutive windows of one mate
         monkeypatch.setenv("KB_RF_STRIDE", stride)
+        monkeypatch.setenv("KB_RF_REUSE", reuse)
         m = pu.make_mapper(idx, paired=True)
         assert pu.compare_pairs(m, orc, reads) == 0
         c = m.debug(9, np.uint32, 32)
