@@ -259,6 +259,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=0, help="read pairs per step per GPU (default: c3 1.25 M = one of 8 shards of 10 M pairs; c2 1 M)")
     ap.add_argument("--cpu-sample-pairs", type=int, default=1_250_000, help="pairs of the step's batch the CPU reference is timed on (default: the whole step, ~10 s on 16 cores; 0: skip)")
     ap.add_argument("--program-pairs", type=int, default=500_000, help="pairs for the whole-program leg (FASTQ in -> SAM out, both programs), N = 1 only; 0: skip")
+    ap.add_argument("--in-flight", type=int, default=2, help="chunks in flight in the end-to-end leg (2 or 3)")
     ap.add_argument("--full-sa", type=int, default=1, help="expand the sampled SA into a full SA in HBM at upload")
     ap.add_argument("--prefix", default=None, help="map against this index instead of the workload's own")
     ap.add_argument("--error", type=float, default=-1.0)
@@ -375,14 +376,21 @@ def main():
     pair_pin2 = torch.empty((n // 2) * PAIR_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
     cig_pin2 = torch.empty(4 * n + 1024, dtype=torch.int32).pin_memory()
     outs = [out_bufs, (aln_pin2.numpy().view(ALN_DTYPE), pair_pin2.numpy().view(PAIR_DTYPE), cig_pin2.numpy().view(np.uint32))]
+    depth = max(2, min(3, args.in_flight))
+    for _ in range(depth - 2):
+        outs.append((torch.empty(n * ALN_DTYPE.itemsize, dtype=torch.uint8).pin_memory().numpy().view(ALN_DTYPE),
+                     torch.empty((n // 2) * PAIR_DTYPE.itemsize, dtype=torch.uint8).pin_memory().numpy().view(PAIR_DTYPE),
+                     torch.empty(4 * n + 1024, dtype=torch.int32).pin_memory().numpy().view(np.uint32)))
 
     def in_flight(steps):
-        h = m.map_chunk_begin(flat, off, est, out=outs[0], packed=pk)
-        for k in range(1, steps):
-            h2 = m.map_chunk_begin(flat, off, est, out=outs[k & 1], packed=pk)
-            res_ = m.map_chunk_end(h)
-            h = h2
-        return m.map_chunk_end(h)
+        pending, res_ = [], None
+        for k in range(steps):
+            pending.append(m.map_chunk_begin(flat, off, est, out=outs[k % depth], packed=pk))
+            if len(pending) == depth:
+                res_ = m.map_chunk_end(pending.pop(0))
+        while pending:
+            res_ = m.map_chunk_end(pending.pop(0))
+        return res_
     in_flight(max(2, args.warmup))
     barrier()
     t0 = time.perf_counter()
@@ -456,7 +464,7 @@ def main():
            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64/int32", "data": "synthetic",
            "config": config, "clocks": clocks,
            "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
-                   "entry": "kb_map_chunk_begin_packed / kb_map_chunk_end, two chunks in flight: pinned 2-bit words + exception list in, pinned kb_aln_t / cigar / pair statistics out, every step",
+                   "entry": "kb_map_chunk_begin_packed / kb_map_chunk_end, %d chunks in flight: pinned 2-bit words + exception list in, pinned kb_aln_t / cigar / pair statistics out, every step" % depth,
                    "host_pack_ms_outside_timed_region": pack_ms, "records_equal_text_entry": same_records},
            "e2e_sync": {"value": total_reads * args.steps / (e2e_sync_ms / 1e3), "unit": "reads/s", "ms_per_step": e2e_sync_ms / args.steps,
                         "entry": "kb_map_chunk_packed, one synchronous call per step (sub-batches overlap inside the call)"},

@@ -31,6 +31,10 @@ struct BatchResult
 	std::vector<kb_extra_t> extra;   // -m: further lines, sorted by (read, rank)
 };
 static bool g_multihit = false;
+// KART_B200_TRACE=1: wall time of every pipeline stage per batch on stderr (reader fill, GPU map, EstDistance settle, format, write)
+static double now_s() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec; }
+static const bool g_trace = getenv("KART_B200_TRACE") != nullptr;
+static double g_t0 = 0;
 
 // Packs the reads on the host threads (2 bits per base + the list of characters that are no upper-case bases) and maps them
 // through kb_map_chunk_packed: a third of the bytes of the text over PCIe. `pk` holds the page-locked staging of one worker.
@@ -38,6 +42,7 @@ struct PackBuf { HBuf<uint64_t> code{true}; HBuf<uint64_t> exc{true}; };
 static int g_pack_threads = 4;
 static int map_batch(kb_ctx_t* ctx, const uint8_t* seq, const uint64_t* off, int n, const int32_t* est, BatchResult& out, PackBuf& pk)
 {
+	const double t_in = g_trace ? now_s() : 0;
 	kb_reads_t in; in.n_reads = n; in.seq = seq; in.seq_off = off;
 	out.aln.resize(n); out.pairs.resize(n / 2 + 1);
 	if (out.cigar.cap < (size_t)n * 4 + 1024) { out.cigar.clear(); out.cigar.reserve((size_t)n * 4 + 1024); }
@@ -45,9 +50,12 @@ static int map_batch(kb_ctx_t* ctx, const uint8_t* seq, const uint64_t* off, int
 	kb_reads_packed_t pr;
 	pk.code.resize((size_t)kb_packed_words(&in));
 	if (pk.exc.cap < 4096) pk.exc.reserve(4096);
+	const double t_a = g_trace ? now_s() : 0;
 	int rc = kb_pack_reads(&in, pk.code.data(), pk.exc.data(), pk.exc.cap, g_pack_threads, &pr);
 	if (rc == KB_ECAPACITY) { pk.exc.clear(); pk.exc.reserve((size_t)pr.n_exc + 4096); rc = kb_pack_reads(&in, pk.code.data(), pk.exc.data(), pk.exc.cap, g_pack_threads, &pr); }
+	const double t_b = g_trace ? now_s() : 0;
 	if (rc == KB_OK) rc = kb_map_chunk_packed(ctx, &pr, est, &res);
+	if (g_trace && n > 100000) fprintf(stderr, "[kart trace]   map_batch %8d reads: buffers %.1f ms, pack %.1f ms, kb_map_chunk_packed %.1f ms\n", n, (t_a - t_in) * 1e3, (t_b - t_a) * 1e3, (now_s() - t_b) * 1e3);
 	if (rc == KB_ECAPACITY)
 	{
 		out.cigar.clear(); out.cigar.reserve((size_t)res.n_cigar + 1024); res.cigar = out.cigar.data(); res.cap_cigar = (uint32_t)out.cigar.cap;
@@ -63,10 +71,6 @@ static int map_batch(kb_ctx_t* ctx, const uint8_t* seq, const uint64_t* off, int
 	return rc;
 }
 
-// KART_B200_TRACE=1: wall time of every pipeline stage per batch on stderr (reader fill, GPU map, EstDistance settle, format, write)
-static double now_s() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec; }
-static const bool g_trace = getenv("KART_B200_TRACE") != nullptr;
-static double g_t0 = 0;
 
 struct PairState { long long iPaired = 0, iDistance = 0; };
 static inline int est_of(const PairState& s) { if (s.iPaired >= 1000) { int e = (int)(s.iDistance / (s.iPaired >> 2)); return e + (e >> 1); } return 1500; }
@@ -311,6 +315,7 @@ int run_mapping(const RunOptions& opt, const HostIndex& idx)
 			if (!wrc)
 			{
 				cur.seq.pin_now(); cur.seq_off.pin_now();
+				if (g_trace && n > 100000) fprintf(stderr, "[kart trace]   pin %.1f ms\n", (now_s() - ta) * 1e3);
 				if (n_pe > 0)
 				{
 					pm.paired = 1; kb_set_params(wctx, &pm);
