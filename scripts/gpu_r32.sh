@@ -24,6 +24,11 @@ print("in flight $f: device %.3f ms (%.1f M/s)  e2e %.3f ms (%.1f M/s)  e2e_sync
 print({k: round(v, 3) for k, v in d["stage_ms"].items()}, d["e2e"]["records_equal_text_entry"], d["roofline"]["frac"])
 PY
 done
+for h in 0 1; do
+  KB_SEED_LD_HINT=$h ncu --set full --clock-control none -k regex:'k_fm_seed' -s 2 -c 1 -o /tmp/${TAG}seed$h -f python bench.py --steps 1 --warmup 1 --pairs 500000 --cpu-sample-pairs 0 --program-pairs 0 > gpurun_out/${TAG}_ncu_seed$h.log 2>&1
+  ncu -i /tmp/${TAG}seed$h.ncu-rep --page raw --csv > gpurun_out/${TAG}_seed_raw_hint$h.csv 2>/dev/null
+done
+ls -la gpurun_out/${TAG}_seed_raw_hint*.csv
 for v in "KB_SEED_LD_HINT=0" "KB_SEED_LD_HINT=1"; do
   echo "== $v" >> gpurun_out/${TAG}_modes.jsonl
   env $v python scripts/gpu_modes.py --prefixes $PREFIX --se 200000 --pb 50000 --ref-se 0 --ref-pb 0 --check 100 >> gpurun_out/${TAG}_modes.jsonl 2>> gpurun_out/${TAG}_bench.err
