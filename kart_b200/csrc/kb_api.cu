@@ -6,8 +6,10 @@
 #ifndef KB_EMUL
 #include <cuda_runtime.h>
 #define KB_LAUNCH(kern, grid, block, stream, ...) kern<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#define KB_LAUNCH_SMEM(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #else   // host emulation build for the CPU-only test container (tests/emul/cuda_shim.h); never part of the product library
 #define KB_LAUNCH(kern, grid, block, stream, ...) kb_emul_launch((grid), (block), [&]() { kern(__VA_ARGS__); })
+#define KB_LAUNCH_SMEM(kern, grid, block, smem, stream, ...) do { (void)(smem); kb_emul_launch((grid), (block), [&]() { kern(__VA_ARGS__); }); } while (0)
 #endif
 #include <math.h>
 #include <stdio.h>
@@ -165,22 +167,25 @@ __global__ void __launch_bounds__(KB_BLOCK, MINB) k_fm_seed(KbIndexDev ix, KbPar
 // atomic per read, from two or three lanes at a time, was 12 % of the kernel's stall samples: ncu r15)
 struct KbSeedWarpQ
 {
-	u32* cnt; u32 end; u32* seeds; u32 max_ns;
+	u32* cnt; u32 end; u32* seeds; u32 max_ns; KbPk* stg;
+	__device__ __forceinline__ KbPk* stage() { return stg; }
 	__device__ __forceinline__ int next() { const u32 k = atomicAdd(cnt, 1u); return k < end ? (int)k : -1; }
 	__device__ __forceinline__ void store(const KbBatchDev& bt, int rd, int ns) { bt.seed_off[rd] = atomicAdd(seeds, (u32)ns); if ((u32)ns > max_ns) max_ns = (u32)ns; }
 };
 #endif
 template <int MINB, class ROW>
-__global__ void __launch_bounds__(KB_BLOCK, MINB) k_fm_seed_q(KbIndexDev ix, KbParams pm, KbBatchDev bt, int qp, int qs, int trips, int tail_max)
+__global__ void __launch_bounds__(KB_BLOCK, MINB) k_fm_seed_q(KbIndexDev ix, KbParams pm, KbBatchDev bt, int qp, int qs, int trips, int tail_max, int staged)
 {
 	u32 steps = 0, blocks = 0;
 #ifndef KB_EMUL
+	extern __shared__ __align__(16) u8 seed_stage[];   // KB_SEED_STAGE packed words per lane when `staged` (see kb_fm.cuh)
 	__shared__ u32 cnt[KB_BLOCK / 32], wseeds[KB_BLOCK / 32];
 	const u32 gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5, wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const u32 lo = (u32)((u64)bt.n_reads * gwarp / nwarps), hi = (u32)((u64)bt.n_reads * (gwarp + 1) / nwarps);
 	if (lane == 0) { cnt[wib] = lo; wseeds[wib] = 0; }
 	__syncwarp();
 	KbSeedWarpQ q; q.cnt = &cnt[wib]; q.end = hi; q.seeds = &wseeds[wib]; q.max_ns = 0;
+	q.stg = staged ? reinterpret_cast<KbPk*>(seed_stage) + (size_t)threadIdx.x * KB_SEED_STAGE : nullptr;
 	kb_seed_lane<ROW>(ix, pm, bt, q, &steps, &blocks, qp, qs, trips, tail_max);
 	__syncwarp();
 	{
@@ -194,7 +199,7 @@ __global__ void __launch_bounds__(KB_BLOCK, MINB) k_fm_seed_q(KbIndexDev ix, KbP
 		if (lane == 0 && m) atomicMax(&bt.counters[5], m);
 	}
 #else
-	for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < bt.n_reads; r += gridDim.x * blockDim.x) { KbSeedOne q; q.r = r; kb_seed_lane<ROW>(ix, pm, bt, q, &steps, &blocks, qp, qs, trips, tail_max); }
+	for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < bt.n_reads; r += gridDim.x * blockDim.x) { KbSeedOne q; q.r = r; q.staged = staged != 0; kb_seed_lane<ROW>(ix, pm, bt, q, &steps, &blocks, qp, qs, trips, tail_max); }
 #endif
 	kb_warp_add64(&bt.work[0], steps); kb_warp_add64(&bt.work[1], blocks);
 }
@@ -784,7 +789,8 @@ struct kb_ctx
 	int part_warps = 148 * 40, part_pool = 4096;   // k_align_part: warps in the grid (each with an HBM arena) and shared-memory pool bytes per warp (r14 A/B: 8 warps/SM + 10 KB pool 2.34 ms -> 40 warps/SM + 4 KB 1.34 ms for the align stage at C2)
 	int nw_tmax = 0;             // largest side one thread solves (0: KB_NW_TMAX); KB_NW_TMAX=32|64 sends more to the wavefront kernel
 	int rf_cand = 256;           // KB_RF_CAND (<= 256)
-	int seed_ld_hint = 0;        // KB_SEED_LD_HINT=1: Occ blocks, seeding-table and SA entries are loaded with L1::no_allocate in the seeding kernels
+	int seed_stage = 1;          // KB_SEED_STAGE=0: the lane-queue seeding kernel walks a read's packed words in HBM instead of copying them to shared memory first
+	int seed_ld_hint = 1;        // Occ blocks, seeding-table and SA entries are loaded with L1::no_allocate in the seeding kernels (r32, C3: seeding 3.47 -> 3.38 ms, L1 hit rate 41 -> 49 %; KB_SEED_LD_HINT=0: plain loads)
 	int rf_reuse = 1, rf_batch = 4;   // k_rescue_fast: the mate's 8-mer index is kept while consecutive windows face the same mate; windows a warp draws per ticket (KB_RF_REUSE, KB_RF_BATCH)
 	int rf_stride = 3;           // KB_RF_STRIDE: 3 = k_rescue_fast scans every third window position, 1 = every position
 	int part_stack = 24, part_raw = 40;   // KB_PART_STACK / KB_PART_RAW: see KbBatchDev
@@ -880,6 +886,7 @@ int kb_init(int device, kb_ctx_t** out)
 	e = getenv("KB_SEED_WARPS"); if (e && atoi(e) >= 4 && atoi(e) <= 148 * 64) ctx->seed_warps = atoi(e);
 	e = getenv("KB_NW_WARP_BELOW"); if (e && atoi(e) >= 0) ctx->nw_warp_below = atoi(e);
 	e = getenv("KB_RF_CAND"); if (e && atoi(e) >= 0 && atoi(e) <= 256) ctx->rf_cand = atoi(e);
+	e = getenv("KB_SEED_STAGE"); if (e) ctx->seed_stage = atoi(e) ? 1 : 0;
 	e = getenv("KB_SEED_LD_HINT"); if (e) ctx->seed_ld_hint = atoi(e) ? 1 : 0;
 	e = getenv("KB_RF_REUSE"); if (e) ctx->rf_reuse = atoi(e) ? 1 : 0;
 	e = getenv("KB_RF_BATCH"); if (e && atoi(e) >= 1 && atoi(e) <= 64) ctx->rf_batch = atoi(e);
@@ -1303,8 +1310,9 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 		unsigned warps = sl.max_rlen >= 1000 ? (unsigned)((n + 31) / 32) : (unsigned)((n + 63) / 64);
 		if (warps > (unsigned)ctx->seed_warps) warps = (unsigned)ctx->seed_warps; if (warps < 4) warps = 4;
 		const unsigned gq = (warps + 3) / 4;
-		if (ctx->row32) { if (ctx->seed_minb == 12) { KB_LAUNCH((k_fm_seed_q<12, u32>), gq, KB_BLOCK, s, ixs, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 6 : 2), ctx->seed_tail); } else { KB_LAUNCH((k_fm_seed_q<10, u32>), gq, KB_BLOCK, s, ixs, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 6 : 2), ctx->seed_tail); } }
-		else { if (ctx->seed_minb == 12) { KB_LAUNCH((k_fm_seed_q<12, u64>), gq, KB_BLOCK, s, ixs, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 6 : 2), ctx->seed_tail); } else { KB_LAUNCH((k_fm_seed_q<10, u64>), gq, KB_BLOCK, s, ixs, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 6 : 2), ctx->seed_tail); } }
+		const size_t seed_smem = ctx->seed_stage ? (size_t)KB_BLOCK * KB_SEED_STAGE * sizeof(KbPk) : 0;
+		if (ctx->row32) { if (ctx->seed_minb == 12) { KB_LAUNCH_SMEM((k_fm_seed_q<12, u32>), gq, KB_BLOCK, seed_smem, s, ixs, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 6 : 2), ctx->seed_tail, ctx->seed_stage); } else { KB_LAUNCH_SMEM((k_fm_seed_q<10, u32>), gq, KB_BLOCK, seed_smem, s, ixs, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 6 : 2), ctx->seed_tail, ctx->seed_stage); } }
+		else { if (ctx->seed_minb == 12) { KB_LAUNCH_SMEM((k_fm_seed_q<12, u64>), gq, KB_BLOCK, seed_smem, s, ixs, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 6 : 2), ctx->seed_tail, ctx->seed_stage); } else { KB_LAUNCH_SMEM((k_fm_seed_q<10, u64>), gq, KB_BLOCK, seed_smem, s, ixs, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 6 : 2), ctx->seed_tail, ctx->seed_stage); } }
 	}
 	else
 	if (ctx->row32)

@@ -116,6 +116,17 @@ KB_HD KbPk kb_load_pk(const KbPk* p)
 	return *p;
 #endif
 }
+// the same word, streamed: not kept in L1 (the seeding kernel copies a read's words to shared memory once)
+KB_HD KbPk kb_load_pk_once(const KbPk* p)
+{
+#if defined(__CUDA_ARCH__)
+	u32 a, b, c, d;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p));
+	KbPk k; k.code = ((u64)b << 32) | a; k.n4 = c; k.bad = d; return k;
+#else
+	return *p;
+#endif
+}
 // one thread per (read, word): 32 characters -> KbPk
 KB_HD void kb_pack_word(const KbBatchDev& bt, int r, int w)
 {
@@ -478,9 +489,16 @@ KB_HD void kb_seed_read(const KbIndexDev& ix, const KbParams& pm, const KbBatchD
 // one step per pass (r15/r16 A/B: qp 8, qs 4, 6 trips on an L2-resident index, 2 on a large one).
 // Results per read are identical to kb_seed_read whatever the schedule.
 #define KB_SEED_TRIPS 4
+// A lane comes back to the packed words of its read for every search (cursor word, table window, the windows of kb_unique_tail): ~50
+// 16-byte loads per 150-bp read, which the random index traffic keeps evicting from L1 and L2 -- ncu r32 (C3): the loads that are NOT
+// Occ blocks, table or SA entries were four fifths of the L2 read misses of the kernel. A read of up to 32 * (KB_SEED_STAGE - 1)
+// bases is therefore copied once into the lane's KB_SEED_STAGE words of shared memory (Q::stage(), streamed past L1) and walked there;
+// longer reads (C5) stay where they are. The stride of 7 words = 28 banks keeps the lanes' 16-byte accesses free of bank conflicts.
+#define KB_SEED_STAGE 7
 struct KbSeedOne   // one read per lane: host emulation, and the reference for the queue
 {
-	int r;
+	int r; KbPk buf[KB_SEED_STAGE]; bool staged = true;
+	KB_HD KbPk* stage() { return staged ? buf : nullptr; }
 	KB_HD int next() { int v = r; r = -1; return v; }
 	KB_HD void store(const KbBatchDev& bt, int rd, int ns)   // the read's slice of the seed arena, from the grid-wide cursor
 	{
@@ -523,6 +541,13 @@ KB_HD void kb_seed_lane(const KbIndexDev& ix, const KbParams& pm, const KbBatchD
 			{
 				fresh = false;
 				rd = kb_pk_read(bt, r); rlen = (int)(bt.seq_off[r + 1] - bt.seq_off[r]); hits = bt.hits + (size_t)r * bt.max_hits;
+				KbPk* const st = q.stage();
+				if (st != nullptr && rlen <= 32 * (KB_SEED_STAGE - 1))
+				{
+					const int nw = ((rlen > 0 ? rlen - 1 : 0) >> 5) + 2;   // every word a 32-base window starting inside the read can reach
+					for (int k = 0; k < nw; k++) st[k] = kb_load_pk_once(rd + k);
+					rd = st;
+				}
 				end = rlen - pm.min_seed; nh = 0; ns = 0; pos = 0; stop = 30; cw = -1; ovf = false; closing = false; tail = false;
 			}
 			if (tail)

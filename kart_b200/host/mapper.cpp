@@ -251,14 +251,25 @@ int run_mapping(const RunOptions& opt, const HostIndex& idx)
 	time_t t0 = time(NULL);
 	long long total = 0, unmapped = 0, unique = 0, remapped = 0; PairState st;
 
-	// stage 3: SAM/BAM text of batch k is formatted in slices and written while batch k+1 is on the GPU
+	// stage 3: SAM/BAM text of batch k is formatted in slices while batch k+1 is on the GPU, and written (stage 4, its own thread) while
+	// batch k+1 is being formatted: the batch's read and result buffers go back to the reader as soon as the text exists, and the
+	// page-cache copy of ~390 MB per million reads (the long pole: 3-4 GB/s on ext4 whatever the number of writers, scripts/host_write_bench.cpp)
+	// no longer waits for the formatter.
+	struct OutBatch
+	{
+		std::vector<HBuf<char>> parts; std::vector<std::string> bparts; std::vector<std::vector<uint32_t>> rec_ends; int n = 0; double ta = 0, tb = 0;
+		explicit OutBatch(int t) : parts(t), bparts(t), rec_ends(t) {}
+	};
+	OutBatch obuf0(io_threads), obuf1(io_threads); Channel<OutBatch*> ob_free, ob_ready;
+	ob_free.put(&obuf0); ob_free.put(&obuf1);
 	std::thread writer([&]() {
-		std::vector<HBuf<char>> parts(io_threads); std::vector<std::string> bparts(io_threads); std::vector<std::vector<uint32_t>> rec_ends(io_threads);
 		while (Job* j = done_q.take())
 		{
+			OutBatch* ob = ob_free.take();
+			std::vector<HBuf<char>>& parts = ob->parts; std::vector<std::string>& bparts = ob->bparts; std::vector<std::vector<uint32_t>>& rec_ends = ob->rec_ends;
 			const ReadBatch& cur = j->rb; const int n = cur.n(), n_pe = j->n_pe; const bool fastq = cur.fastq;
 			std::vector<long long> um(io_threads, 0), uq(io_threads, 0);
-			double ta = now_s();
+			ob->n = n; ob->ta = now_s();
 			parallel_for(io_threads, (size_t)io_threads, [&](int, size_t t0_, size_t t1_) {
 				for (size_t t = t0_; t < t1_; t++)
 				{
@@ -285,12 +296,21 @@ int run_mapping(const RunOptions& opt, const HostIndex& idx)
 					}
 				}
 			});
-			double tb = now_s();
-			if (to_bam) for (int t = 0; t < io_threads; t++) bam.append(bparts[t], rec_ends[t], true);
-			else if (!opt.debug) out.write_parts(parts);
-			if (g_trace) fprintf(stderr, "[kart trace] format %8d reads  %.3f..%.3f s  write ..%.3f s\n", n, ta - g_t0, tb - g_t0, now_s() - g_t0);
+			ob->tb = now_s();
 			for (int t = 0; t < io_threads; t++) { unmapped += um[t]; unique += uq[t]; }
 			free_q.put(j);
+			ob_ready.put(ob);
+		}
+		ob_ready.put(nullptr);
+	});
+	std::thread sink([&]() {
+		while (OutBatch* ob = ob_ready.take())
+		{
+			const double tc = now_s();
+			if (to_bam) for (int t = 0; t < io_threads; t++) bam.append(ob->bparts[t], ob->rec_ends[t], true);
+			else if (!opt.debug) out.write_parts(ob->parts);
+			if (g_trace) fprintf(stderr, "[kart trace] format %8d reads  %.3f..%.3f s  write %.3f..%.3f s\n", ob->n, ob->ta - g_t0, ob->tb - g_t0, tc - g_t0, now_s() - g_t0);
+			ob_free.put(ob);
 		}
 	});
 
@@ -387,7 +407,7 @@ int run_mapping(const RunOptions& opt, const HostIndex& idx)
 	for (auto& t : extra_workers) t.join();
 	rc = err.load();
 	reader.join();
-	done_q.put(nullptr); writer.join();
+	done_q.put(nullptr); writer.join(); sink.join();
 	const bool pair_end = opt.files1.empty() ? pair_end_seen : pair_end_final;
 	fprintf(stdout, "\rAll the %lld %s reads have been processed in %lld seconds.\n", total, pair_end ? "paired-end" : "single-end", (long long)(time(NULL) - t0));
 	out.close();

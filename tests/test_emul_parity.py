@@ -321,6 +321,27 @@ def test_rescue_sampled_scan_repeat_rich(mini, tmp_path, monkeypatch):
         assert m.work()["rescues"] > 500 and c[27] - c[29] > 200, (m.work()["rescues"], c[27], c[29])
 
 
+def test_seeding_load_paths(mini, monkeypatch):
+    """The lane-queue seeding kernel with a read's packed words staged in shared memory or walked in HBM, and with or without the
+    L1 no-allocate loads of Occ blocks / table / SA entries: the oracle's pairs every time (reads of 150 and of 250 bases: the
+    latter are too long for the stage)."""
+    idx = KartIndex(pu.MINI_PREFIX)
+    g = pu.genome_of(idx)
+    orc = pu.Oracle(pu.MINI_PREFIX)
+    sets = []
+    for L, seed in ((150, 5), (250, 6)):
+        r1, r2, _ = synth.simulate(g, 300, L, 0.03, seed=seed, indel=0.002)
+        reads = pu.interleave(r1, r2)
+        reads[3::50, 40] = ord("N")
+        sets.append(reads)
+    for stage, hint in (("1", "1"), ("0", "1"), ("1", "0"), ("0", "0")):
+        monkeypatch.setenv("KB_SEED_STAGE", stage)
+        monkeypatch.setenv("KB_SEED_LD_HINT", hint)
+        m = pu.make_mapper(idx, emul=True, expand_sa=True, paired=True)
+        for reads in sets:
+            assert pu.compare_pairs(m, orc, reads) == 0
+
+
 def _same_results(a, b, paired=True):
     (a0, p0, c0), (a1, p1, c1) = a, b
     for f in ("pos", "mate_pos", "kind", "flag", "chr", "mapq", "score", "sub_score", "tlen", "fwd", "cig_len"):

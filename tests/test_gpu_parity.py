@@ -274,6 +274,27 @@ def test_rescue_sampled_scan_repeat_rich(built, tmp_path, monkeypatch):
         assert m.work()["rescues"] > 4000 and c[27] - c[29] > 1500, (m.work()["rescues"], c[27], c[29])
 
 
+def test_seeding_load_paths(built, monkeypatch):
+    """The lane-queue seeding kernel with a read's packed words staged in shared memory or walked in HBM, and with or without the
+    L1 no-allocate loads of Occ blocks / table / SA entries: the oracle's pairs every time (reads of 150 and of 250 bases: the
+    latter are too long for the stage)."""
+    idx = KartIndex(pu.MINI_PREFIX)
+    g = pu.genome_of(idx)
+    orc = pu.Oracle(pu.MINI_PREFIX)
+    sets = []
+    for L, seed in ((150, 5), (250, 6)):
+        r1, r2, _ = synth.simulate(g, 4000, L, 0.03, seed=seed, indel=0.002)
+        reads = pu.interleave(r1, r2)
+        reads[3::50, 40] = ord("N")
+        sets.append(reads)
+    for stage, hint in (("1", "1"), ("0", "1"), ("1", "0"), ("0", "0")):
+        monkeypatch.setenv("KB_SEED_STAGE", stage)
+        monkeypatch.setenv("KB_SEED_LD_HINT", hint)
+        m = pu.make_mapper(idx, expand_sa=True, paired=True)
+        for reads in sets:
+            assert pu.compare_pairs(m, orc, reads) == 0
+
+
 @pytest.mark.parametrize("plan", [{"KB_PIPE_SUB_READS": "65536"}, {"KB_PIPE_SUB_READS": "100000", "KB_PIPE_FIRST": "8192", "KB_PIPE_GROW": "150", "KB_PIPE_TAIL": "8192"}])
 def test_pipelined_chunk_full_size_equals_single_batch(eco, monkeypatch, plan):
     """C2 at size: 400k reads through kb_map_chunk's slot pipeline (uniform sub-batches of 65536, or a ramped plan; cigar ranges
