@@ -221,7 +221,18 @@ int run_mapping(const RunOptions& opt, const HostIndex& idx)
 		for (const auto& f : opt.files2) if (stat(f.c_str(), &fs) == 0) in_bytes += (unsigned long long)fs.st_size * (f.size() > 3 && f.compare(f.size() - 3, 3, ".gz") == 0 ? 4 : 1);
 		expand = (hi.seq_len <= (1ull << 30) || in_bytes >= (64ull << 30)) ? 2 : 0;
 	}
-	if ((rc = kb_upload_index(ctx, &hi, expand)) != 0) { fprintf(stderr, "Error! index upload failed: %s (%s)\n", kb_strerror(rc), kb_last_error(ctx)); drain_reader(); kb_destroy(ctx); return 1; }
+	// page-locked result buffers of every rotating batch are allocated while the index goes to the device (r32 trace: 40-100 ms per
+	// batch when the first pass through the rotation had to do it in the GPU worker)
+	std::thread prealloc([&]() {
+		for (size_t k = 0; k < jobs.size() && k < 4; k++)   // the first batches of the rotation; the others allocate on first use, under the running pipeline
+		{
+			Job& j = jobs[k];
+			j.br.aln.reserve((size_t)batch_reads); j.br.pairs.reserve((size_t)batch_reads / 2 + 1); j.br.cigar.reserve((size_t)batch_reads * 4 + 1024);
+		}
+	});
+	rc = kb_upload_index(ctx, &hi, expand);
+	prealloc.join();
+	if (rc != 0) { fprintf(stderr, "Error! index upload failed: %s (%s)\n", kb_strerror(rc), kb_last_error(ctx)); drain_reader(); kb_destroy(ctx); return 1; }
 
 	if (g_trace) fprintf(stderr, "[kart trace] index uploaded %.3f s\n", now_s() - g_t0);
 	SamSink out; BamWriter bam; const bool to_bam = opt.out_format == 1 && !opt.debug;
