@@ -791,6 +791,7 @@ struct kb_ctx
 	int rf_cand = 256;           // KB_RF_CAND (<= 256)
 	int seed_stage = 1;          // KB_SEED_STAGE=0: the lane-queue seeding kernel walks a read's packed words in HBM instead of copying them to shared memory first
 	int seed_ld_hint = 1;        // Occ blocks, seeding-table and SA entries are loaded with L1::no_allocate in the seeding kernels (r32, C3: seeding 3.47 -> 3.38 ms, L1 hit rate 41 -> 49 %; KB_SEED_LD_HINT=0: plain loads)
+	int fin_local = 1;           // KB_FIN_LOCAL=0: k_finalize works on the reports where they lie
 	int rf_reuse = 1, rf_batch = 4;   // k_rescue_fast: the mate's 8-mer index is kept while consecutive windows face the same mate; windows a warp draws per ticket (KB_RF_REUSE, KB_RF_BATCH)
 	int rf_stride = 3;           // KB_RF_STRIDE: 3 = k_rescue_fast scans every third window position, 1 = every position
 	int part_stack = 24, part_raw = 40;   // KB_PART_STACK / KB_PART_RAW: see KbBatchDev
@@ -888,6 +889,7 @@ int kb_init(int device, kb_ctx_t** out)
 	e = getenv("KB_RF_CAND"); if (e && atoi(e) >= 0 && atoi(e) <= 256) ctx->rf_cand = atoi(e);
 	e = getenv("KB_SEED_STAGE"); if (e) ctx->seed_stage = atoi(e) ? 1 : 0;
 	e = getenv("KB_SEED_LD_HINT"); if (e) ctx->seed_ld_hint = atoi(e) ? 1 : 0;
+	e = getenv("KB_FIN_LOCAL"); if (e) ctx->fin_local = atoi(e) ? 1 : 0;
 	e = getenv("KB_RF_REUSE"); if (e) ctx->rf_reuse = atoi(e) ? 1 : 0;
 	e = getenv("KB_RF_BATCH"); if (e && atoi(e) >= 1 && atoi(e) <= 64) ctx->rf_batch = atoi(e);
 	e = getenv("KB_RF_STRIDE"); if (e && (atoi(e) == 1 || atoi(e) == 3)) ctx->rf_stride = atoi(e);
@@ -1180,7 +1182,7 @@ static int alloc_batch(kb_ctx* ctx, kb_slot& sl, int shared)
 	else { bt.cigar = sl.cigar.p; bt.cap_cigar = (u32)sl.cap_cigar; bt.cig_cursor = sl.counters.p + 2; }
 	bt.scratch = sl.scratch.p; bt.scratch_per_thread = per; bt.scratch_threads = (int)threads;
 	bt.wscratch = sl.wscratch.p; bt.wscratch_per_warp = per; bt.wscratch_warps = wwarps;
-	bt.max_rlen = L; bt.nw_tmax = ctx->nw_tmax > 0 ? ctx->nw_tmax : KB_NW_TMAX; bt.nw_warp_below = ctx->nw_warp_below; bt.rf_cand = ctx->rf_cand; bt.rf_stride = ctx->rf_stride; bt.rf_reuse = ctx->rf_reuse; bt.rf_batch = ctx->rf_batch; bt.part_stack = ctx->part_stack; bt.part_raw = ctx->part_raw; bt.seg_cap = 0; bt.kmer_cap = 0; bt.counters = sl.counters.p; bt.work = sl.work.p;
+	bt.max_rlen = L; bt.nw_tmax = ctx->nw_tmax > 0 ? ctx->nw_tmax : KB_NW_TMAX; bt.nw_warp_below = ctx->nw_warp_below; bt.rf_cand = ctx->rf_cand; bt.rf_stride = ctx->rf_stride; bt.fin_local = ctx->fin_local; bt.rf_reuse = ctx->rf_reuse; bt.rf_batch = ctx->rf_batch; bt.part_stack = ctx->part_stack; bt.part_raw = ctx->part_raw; bt.seg_cap = 0; bt.kmer_cap = 0; bt.counters = sl.counters.p; bt.work = sl.work.p;
 	return KB_OK;
 }
 

@@ -573,12 +573,9 @@ KB_HD void kb_mapq(const KbIndexDev& ix, const KbParams& pm, KbReadRes& r, int r
 	if (r.mapq > 60) r.mapq = 60;
 }
 
-KB_HD void kb_finalize_pair(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int p)
+// r1 / r2 and p1 / p2 are the pair's results and reports where the caller holds them: in the arenas, or copies in the thread's local memory
+KB_HD void kb_finalize_pair_on(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int p, KbReadRes& r1, KbReport* p1, KbReadRes& r2, KbReport* p2, int l1, int l2)
 {
-	int ra = 2 * p, rb = ra + 1;
-	KbReadRes& r1 = bt.res[ra]; KbReadRes& r2 = bt.res[rb];
-	KbReport* p1 = bt.reports + r1.rep_off; KbReport* p2 = bt.reports + r2.rep_off;
-	int l1 = (int)(bt.seq_off[ra + 1] - bt.seq_off[ra]), l2 = (int)(bt.seq_off[rb + 1] - bt.seq_off[rb]);
 	kb_settle_pair(pm, r1, p1, r2, p2);
 	kb_flag_pair(r1, p1, r2, p2);
 	kb_mapq(ix, pm, r1, l1); kb_mapq(ix, pm, r2, l2);
@@ -592,6 +589,14 @@ KB_HD void kb_finalize_pair(const KbIndexDev& ix, const KbParams& pm, const KbBa
 			st.counted = 1; st.absdist = dist < 0 ? -dist : dist;
 		}
 	}
+}
+KB_HD void kb_finalize_pair(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int p)
+{
+	int ra = 2 * p, rb = ra + 1;
+	KbReadRes& r1 = bt.res[ra]; KbReadRes& r2 = bt.res[rb];
+	KbReport* p1 = bt.reports + r1.rep_off; KbReport* p2 = bt.reports + r2.rep_off;
+	int l1 = (int)(bt.seq_off[ra + 1] - bt.seq_off[ra]), l2 = (int)(bt.seq_off[rb + 1] - bt.seq_off[rb]);
+	kb_finalize_pair_on(ix, pm, bt, p, r1, p1, r2, p2, l1, l2);
 }
 
 KB_HD void kb_finalize_single(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int r)

@@ -140,6 +140,7 @@ struct KbBatchDev
 	i32 nw_tmax;                        // largest side one thread solves (<= KB_NW_TMAX); larger problems go to the warp wavefront kernel
 	i32 nw_warp_below;                  // a column-tile class with fewer problems than this goes to the warp wavefront kernel as well
 	i32 rf_cand;                        // k_rescue_fast: filter-passing window positions noted for the probe phase (the rest is probed on the spot)
+	i32 fin_local;                      // k_finalize: pairs with few reports are finished on copies in local memory (kb_stage_finalize)
 	i32 rf_reuse, rf_batch;             // k_rescue_fast: keep the mate's 8-mer index across consecutive windows of one mate ; windows per ticket
 	i32 rf_stride;                      // k_rescue_fast: 3 = every third window position is scanned (kb_rf_scan), 1 = every position
 	i32 part_stack, part_raw;           // k_align_part: entries of a job's work stack / of its exact-match run list that are tried in the warp's shared-memory pool first (the rest, and an overflowing run list, live in the HBM arena)
