@@ -779,8 +779,8 @@ struct kb_ctx
 	float stage_ms[10]; uint64_t work_host[8]; u32 counters_host[KB_NCOUNTERS];
 	cudaEvent_t chunk_start = nullptr; int trace = 0;
 	int seed_minb = 10;
-	int seed_qp = 8, seed_qs = 4, seed_trips = 0;   // trips 0 = 6 with 32-bit rows (small index, instruction-bound), 4 otherwise (r33 A/B at C3: 2 trips 3.33 ms, 4 trips 3.27 ms)   // lane-queue schedule: lanes a pass waits for, lanes a walk waits for, trips per walk (KB_SEED_QP/QS/TRIPS)
-	int seg_slab = 0;            // segx slots a warp of k_segments reserves up front (0: none; KB_SEG_SLAB, see kb_alloc_segx)
+	int seed_qp = 8, seed_qs = 4, seed_trips = 0;   // trips 0 = 6 (r33 / r35 A/B at C3: 2 trips 3.33 ms, 4 trips 3.27 ms, 6 trips 3.21 ms; 6 on an L2-resident index since r16)   // lane-queue schedule: lanes a pass waits for, lanes a walk waits for, trips per walk (KB_SEED_QP/QS/TRIPS)
+	int seg_slab = 256;          // segx slots a warp of k_segments reserves up front (0: none; KB_SEG_SLAB, see kb_alloc_segx; r35 A/B at C3: segments 1.64 -> 1.41 ms)
 	int seed_tail = 1;           // a search with at most this many rows left is finished against the text (1: kb_unique_tail only; >1: kb_multi_tail, measured slower at 4..50 in r16, kept as a knob: KB_SEED_TAIL)
 	int seed_queue = 1, seed_warps = 148 * 40;   // lane-queue seeding when the full SA is on the device; warps in its grid (KB_SEED_QUEUE, KB_SEED_WARPS)
 	bool row32 = false;          // BWT row numbers fit 32 bits: k_fm_seed<.., u32> (set at index upload; KB_ROW64=1 forces the 64-bit kernel)
@@ -1313,8 +1313,8 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 		if (warps > (unsigned)ctx->seed_warps) warps = (unsigned)ctx->seed_warps; if (warps < 4) warps = 4;
 		const unsigned gq = (warps + 3) / 4;
 		const size_t seed_smem = ctx->seed_stage ? (size_t)KB_BLOCK * KB_SEED_STAGE * sizeof(KbPk) : 0;
-		if (ctx->row32) { if (ctx->seed_minb == 12) { KB_LAUNCH_SMEM((k_fm_seed_q<12, u32>), gq, KB_BLOCK, seed_smem, s, ixs, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 6 : 4), ctx->seed_tail, ctx->seed_stage); } else { KB_LAUNCH_SMEM((k_fm_seed_q<10, u32>), gq, KB_BLOCK, seed_smem, s, ixs, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 6 : 4), ctx->seed_tail, ctx->seed_stage); } }
-		else { if (ctx->seed_minb == 12) { KB_LAUNCH_SMEM((k_fm_seed_q<12, u64>), gq, KB_BLOCK, seed_smem, s, ixs, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 6 : 4), ctx->seed_tail, ctx->seed_stage); } else { KB_LAUNCH_SMEM((k_fm_seed_q<10, u64>), gq, KB_BLOCK, seed_smem, s, ixs, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : (ctx->row32 ? 6 : 4), ctx->seed_tail, ctx->seed_stage); } }
+		if (ctx->row32) { if (ctx->seed_minb == 12) { KB_LAUNCH_SMEM((k_fm_seed_q<12, u32>), gq, KB_BLOCK, seed_smem, s, ixs, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : 6, ctx->seed_tail, ctx->seed_stage); } else { KB_LAUNCH_SMEM((k_fm_seed_q<10, u32>), gq, KB_BLOCK, seed_smem, s, ixs, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : 6, ctx->seed_tail, ctx->seed_stage); } }
+		else { if (ctx->seed_minb == 12) { KB_LAUNCH_SMEM((k_fm_seed_q<12, u64>), gq, KB_BLOCK, seed_smem, s, ixs, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : 6, ctx->seed_tail, ctx->seed_stage); } else { KB_LAUNCH_SMEM((k_fm_seed_q<10, u64>), gq, KB_BLOCK, seed_smem, s, ixs, pm, bt, ctx->seed_qp, ctx->seed_qs, ctx->seed_trips > 0 ? ctx->seed_trips : 6, ctx->seed_tail, ctx->seed_stage); } }
 	}
 	else
 	if (ctx->row32)

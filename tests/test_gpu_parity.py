@@ -295,6 +295,19 @@ def test_seeding_load_paths(built, monkeypatch):
             assert pu.compare_pairs(m, orc, reads) == 0
 
 
+def test_segx_slab_sizes(built, monkeypatch):
+    """k_segments hands out segment slots from a per-warp slab (KB_SEG_SLAB, 256 by default), falling back to the arena cursor when a warp
+    runs out: no slab, a slab that is always too small and the default give the oracle's pairs."""
+    idx = KartIndex(pu.MINI_PREFIX)
+    g = pu.genome_of(idx)
+    r1, r2, _ = synth.simulate(g, 6000, 150, 0.05, seed=23, indel=0.004)
+    reads = pu.interleave(r1, r2)
+    orc = pu.Oracle(pu.MINI_PREFIX)
+    for slab in ("0", "8", "256"):
+        monkeypatch.setenv("KB_SEG_SLAB", slab)
+        assert pu.compare_pairs(pu.make_mapper(idx, paired=True), orc, reads) == 0
+
+
 @pytest.mark.parametrize("plan", [{"KB_PIPE_SUB_READS": "65536"}, {"KB_PIPE_SUB_READS": "100000", "KB_PIPE_FIRST": "8192", "KB_PIPE_GROW": "150", "KB_PIPE_TAIL": "8192"}])
 def test_pipelined_chunk_full_size_equals_single_batch(eco, monkeypatch, plan):
     """C2 at size: 400k reads through kb_map_chunk's slot pipeline (uniform sub-batches of 65536, or a ramped plan; cigar ranges
