@@ -318,11 +318,12 @@ static void k_cand_heavy(KbIndexDev ix, KbParams pm, KbBatchDev bt)   // emulati
 // ... and then a thread each for the scan over the sorted seeds, the pairing and the pruning. On the sorting warp's lane 0 that part
 // ran one item after the other (80 % of k_cand_heavy's samples at one lane: ncu r21, C3); here every heavy item of the batch is in
 // flight at once, and a warp lasts as long as its longest item instead of as long as the sum of thirteen.
-__global__ void __launch_bounds__(KB_BLOCK) k_cand_heavy_finish(KbIndexDev ix, KbParams pm, KbBatchDev bt)
+__global__ void __launch_bounds__(KB_BLOCK) k_cand_heavy_finish(KbIndexDev ix, KbParams pm, KbBatchDev bt, int wide)
 {
 	if (bt.counters[3]) return;
 	const u32 count = bt.counters[15];
-	for (u32 q = blockIdx.x * blockDim.x + threadIdx.x; q < count; q += gridDim.x * blockDim.x) kb_cand_finish(ix, pm, bt, bt.slow_list2[q]);
+	if (wide) { for (u32 q = blockIdx.x * blockDim.x + threadIdx.x; q < count; q += gridDim.x * blockDim.x) kb_cand_finish<true>(ix, pm, bt, bt.slow_list2[q]); }
+	else for (u32 q = blockIdx.x * blockDim.x + threadIdx.x; q < count; q += gridDim.x * blockDim.x) kb_cand_finish<false>(ix, pm, bt, bt.slow_list2[q]);
 }
 __global__ void __launch_bounds__(KB_BLOCK) k_cand_pacbio(KbIndexDev ix, KbParams pm, KbBatchDev bt, int sorted) { kb_stage_cand_pacbio(ix, pm, bt, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, sorted != 0); }
 // A 7-kbp read brings ~600 seeds; sorted by the read's own thread (Shell sort over 24-byte records in HBM) that was 79 % of k_cand_pacbio's
@@ -791,6 +792,7 @@ struct kb_ctx
 	int rf_cand = 256;           // KB_RF_CAND (<= 256)
 	int seed_stage = 1;          // KB_SEED_STAGE=0: the lane-queue seeding kernel walks a read's packed words in HBM instead of copying them to shared memory first
 	int seed_ld_hint = 1;        // Occ blocks, seeding-table and SA entries are loaded with L1::no_allocate in the seeding kernels (r32, C3: seeding 3.47 -> 3.38 ms, L1 hit rate 41 -> 49 %; KB_SEED_LD_HINT=0: plain loads)
+	int cand_wide = 1;           // k_cand_heavy_finish: the candidate scan fetches four seeds per round of loads (KB_CAND_WIDE=0: one)
 	int fin_local = 1;           // KB_FIN_LOCAL=0: k_finalize works on the reports where they lie
 	int rf_reuse = 1, rf_batch = 4;   // k_rescue_fast: the mate's 8-mer index is kept while consecutive windows face the same mate; windows a warp draws per ticket (KB_RF_REUSE, KB_RF_BATCH)
 	int rf_stride = 3;           // KB_RF_STRIDE: 3 = k_rescue_fast scans every third window position, 1 = every position
@@ -889,6 +891,7 @@ int kb_init(int device, kb_ctx_t** out)
 	e = getenv("KB_RF_CAND"); if (e && atoi(e) >= 0 && atoi(e) <= 256) ctx->rf_cand = atoi(e);
 	e = getenv("KB_SEED_STAGE"); if (e) ctx->seed_stage = atoi(e) ? 1 : 0;
 	e = getenv("KB_SEED_LD_HINT"); if (e) ctx->seed_ld_hint = atoi(e) ? 1 : 0;
+	e = getenv("KB_CAND_WIDE"); if (e) ctx->cand_wide = atoi(e) ? 1 : 0;
 	e = getenv("KB_FIN_LOCAL"); if (e) ctx->fin_local = atoi(e) ? 1 : 0;
 	e = getenv("KB_RF_REUSE"); if (e) ctx->rf_reuse = atoi(e) ? 1 : 0;
 	e = getenv("KB_RF_BATCH"); if (e && atoi(e) >= 1 && atoi(e) <= 64) ctx->rf_batch = atoi(e);
@@ -1335,7 +1338,7 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 	sl.launches++;
 	CK(cudaEventRecord(sl.ev[2], s));
 	KB_LAUNCH(k_cand_pair, g_items, KB_BLOCK, s, ix, pm, bt, ctx->cand_heavy); sl.launches++;
-	if (ctx->cand_heavy && !pm.pacbio) { KB_LAUNCH(k_cand_heavy, 148 * 8, KB_BLOCK, s, ix, pm, bt); KB_LAUNCH(k_cand_heavy_finish, 148 * 8, KB_BLOCK, s, ix, pm, bt); sl.launches += 2; }
+	if (ctx->cand_heavy && !pm.pacbio) { KB_LAUNCH(k_cand_heavy, 148 * 8, KB_BLOCK, s, ix, pm, bt); KB_LAUNCH(k_cand_heavy_finish, 148 * 8, KB_BLOCK, s, ix, pm, bt, ctx->cand_wide); sl.launches += 2; }
 	if (pm.pacbio)
 	{
 		if (ctx->cand_heavy) { KB_LAUNCH(k_cand_pacbio_sort, 148 * 8, KB_BLOCK, s, bt); sl.launches++; }

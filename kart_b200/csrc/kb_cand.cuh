@@ -48,6 +48,8 @@ KB_HD void kb_sort_segs(KbSeg* v, int n)
 
 // Illumina candidates: runs of (PosDiff,rPos)-sorted seeds whose neighbours differ by <= MaxGaps on the diagonal
 // and stay on the first seed's chromosome; kept when the summed seed length beats a ratcheting threshold.
+// WIDE: the seed list is long and in HBM (k_cand_heavy_finish): the scan fetches four seeds per round of loads.
+template <bool WIDE>
 KB_HD int kb_cands_illumina(const KbIndexDev& ix, const KbParams& pm, int rlen, KbSeg* sv, int n, u32 seg_base, KbCand* out, int cap)
 {
 	int thr = (int)(rlen * 0.2); if (thr > 50) thr = 50;
@@ -55,12 +57,32 @@ KB_HD int kb_cands_illumina(const KbIndexDev& ix, const KbParams& pm, int rlen, 
 	while (i < n && sv[i].gpos - sv[i].rpos < 0) i++;
 	while (i < n)
 	{
-		int score = sv[i].rlen, j = i, k;
+		int score = sv[i].rlen, k;
 		i64 bound = ix.end_key[kb_chr_lookup(ix, sv[i].gpos)];
-		for (k = i + 1; k < n; k++)
+		// four seeds per round of loads: a heavy item (hundreds of seeds, one thread: k_cand_heavy_finish) otherwise pays one memory round trip
+		// per seed, the break test standing between consecutive loads (ncu r29: 30 % of that kernel's samples on this line, at 6 % warps active)
+		i64 dprev = sv[i].gpos - sv[i].rpos; bool open = true;
+		if (!WIDE)
 		{
-			if (sv[k].gpos > bound || (sv[k].gpos - sv[k].rpos) - (sv[j].gpos - sv[j].rpos) > pm.max_gaps) break;
-			score += sv[k].rlen; j = k;
+			for (k = i + 1; k < n; k++)
+			{
+				const i64 d = sv[k].gpos - sv[k].rpos;
+				if (sv[k].gpos > bound || d - dprev > pm.max_gaps) break;
+				score += sv[k].rlen; dprev = d;
+			}
+		}
+		else for (k = i + 1; k < n && open;)
+		{
+			const int m = n - k < 4 ? n - k : 4;
+			i64 g[4]; int rp[4], rl[4];
+			for (int u = 0; u < 4; u++) if (u < m) { g[u] = sv[k + u].gpos; rp[u] = sv[k + u].rpos; rl[u] = sv[k + u].rlen; }
+			for (int u = 0; u < 4; u++)
+			{
+				if (u >= m) break;
+				const i64 d = g[u] - rp[u];
+				if (g[u] > bound || d - dprev > pm.max_gaps) { open = false; break; }
+				score += rl[u]; dprev = d; k++;
+			}
 		}
 		if (score > thr)
 		{
@@ -132,8 +154,13 @@ KB_HD bool kb_pair(const KbParams& pm, i64 est, KbCand* a, int n1, KbCand* b, in
 	// family has dozens of candidates on either side, all but a few of them a genome away from each other: n1 + n2 steps instead of
 	// n1 x n2 (ncu r21, C3: the quadratic loop was a quarter of k_cand_heavy). The order is checked, not assumed.
 	bool ascending = n1 * n2 > 16;
-	for (int i = 1; ascending && i < n1; i++) if (a[i].diff < a[i - 1].diff) ascending = false;
-	for (int j = 1; ascending && j < n2; j++) if (b[j].diff < b[j - 1].diff) ascending = false;
+	if (ascending)   // no early exit: the loads of consecutive candidates then overlap instead of waiting for each other's test
+	{
+		bool asc = true;
+		for (int i = 1; i < n1; i++) asc &= !(a[i].diff < a[i - 1].diff);
+		for (int j = 1; j < n2; j++) asc &= !(b[j].diff < b[j - 1].diff);
+		ascending = asc;
+	}
 	int j0 = 0;
 	for (int i = 0; i < n1; i++)
 	{

@@ -41,6 +41,7 @@ KB_HD bool kb_cand_is_heavy(const KbParams& pm, const KbBatchDev& bt, int t)
 	return bt.n_seeds[t] > KB_CAND_HEAVY;
 }
 // part 3 (the seeds are (PosDiff,rPos)-sorted): candidates, pairing, pruning, rescue list
+template <bool WIDE>
 KB_HD void kb_cand_finish(const KbIndexDev& ix, const KbParams& pm, const KbBatchDev& bt, int t)
 {
 	if (pm.paired)
@@ -50,8 +51,8 @@ KB_HD void kb_cand_finish(const KbIndexDev& ix, const KbParams& pm, const KbBatc
 		KbSeg* v1 = bt.segs + bt.seed_off[ra]; KbSeg* v2 = bt.segs + bt.seed_off[rb];
 		int l1 = (int)(bt.seq_off[ra + 1] - bt.seq_off[ra]), l2 = (int)(bt.seq_off[rb + 1] - bt.seq_off[rb]);
 		KbCand* a = bt.cands + bt.cand_off[ra]; KbCand* b = a + cap;
-		int n1 = kb_cands_illumina(ix, pm, l1, v1, s1, bt.seed_off[ra], a, cap);
-		int n2 = kb_cands_illumina(ix, pm, l2, v2, s2, bt.seed_off[rb], b, cap);
+		int n1 = kb_cands_illumina<WIDE>(ix, pm, l1, v1, s1, bt.seed_off[ra], a, cap);
+		int n2 = kb_cands_illumina<WIDE>(ix, pm, l2, v2, s2, bt.seed_off[rb], b, cap);
 		bt.n_cands[ra] = n1; bt.n_cands[rb] = n2;
 		i32 lo = bt.pstat[t].est_lo, hi = bt.pstat[t].est_hi;
 		bool paired = kb_pair(pm, (i64)bt.est[t], a, n1, b, n2, &lo, &hi);
@@ -66,7 +67,7 @@ KB_HD void kb_cand_finish(const KbIndexDev& ix, const KbParams& pm, const KbBatc
 		KbSeg* v = bt.segs + bt.seed_off[t];
 		int l = (int)(bt.seq_off[t + 1] - bt.seq_off[t]);
 		KbCand* a = bt.cands + bt.cand_off[t];
-		int n = kb_cands_illumina(ix, pm, l, v, s1, bt.seed_off[t], a, bt.cand_cap[t]);
+		int n = kb_cands_illumina<WIDE>(ix, pm, l, v, s1, bt.seed_off[t], a, bt.cand_cap[t]);
 		bt.n_cands[t] = n;
 		kb_prune(pm, a, n);
 	}
@@ -78,7 +79,7 @@ KB_HD void kb_stage_cand_pair(const KbIndexDev& ix, const KbParams& pm, const Kb
 	if (split_heavy && kb_cand_is_heavy(pm, bt, t)) { const u32 slot = KB_ALLOC(&bt.counters[15], 1u); bt.slow_list2[slot] = t; return; }
 	if (pm.paired) { kb_sort_segs<false>(bt.segs + bt.seed_off[2 * t], bt.n_seeds[2 * t]); kb_sort_segs<false>(bt.segs + bt.seed_off[2 * t + 1], bt.n_seeds[2 * t + 1]); }
 	else kb_sort_segs<false>(bt.segs + bt.seed_off[t], bt.n_seeds[t]);
-	kb_cand_finish(ix, pm, bt, t);
+	kb_cand_finish<false>(ix, pm, bt, t);
 }
 
 // ---- warp-cooperative (PosDiff,rPos) sort of one read's seeds (k_cand_heavy) ----
