@@ -790,6 +790,7 @@ struct kb_ctx
 	int part_warps = 148 * 40, part_pool = 4096;   // k_align_part: warps in the grid (each with an HBM arena) and shared-memory pool bytes per warp (r14 A/B: 8 warps/SM + 10 KB pool 2.34 ms -> 40 warps/SM + 4 KB 1.34 ms for the align stage at C2)
 	int nw_tmax = 0;             // largest side one thread solves (0: KB_NW_TMAX); KB_NW_TMAX=32|64 sends more to the wavefront kernel
 	int rf_cand = 256;           // KB_RF_CAND (<= 256)
+	int seed_tail_fast = 1;      // kb_unique_tail compares on the read's word boundaries with the strand decided once (KB_SEED_TAIL_FAST=0: the general window loop)
 	int seed_stage = 1;          // KB_SEED_STAGE=0: the lane-queue seeding kernel walks a read's packed words in HBM instead of copying them to shared memory first
 	int seed_ld_hint = 1;        // Occ blocks, seeding-table and SA entries are loaded with L1::no_allocate in the seeding kernels (r32, C3: seeding 3.47 -> 3.38 ms, L1 hit rate 41 -> 49 %; KB_SEED_LD_HINT=0: plain loads)
 	int cand_wide = 1;           // k_cand_heavy_finish: the candidate scan fetches four seeds per round of loads (KB_CAND_WIDE=0: one)
@@ -889,6 +890,7 @@ int kb_init(int device, kb_ctx_t** out)
 	e = getenv("KB_SEED_WARPS"); if (e && atoi(e) >= 4 && atoi(e) <= 148 * 64) ctx->seed_warps = atoi(e);
 	e = getenv("KB_NW_WARP_BELOW"); if (e && atoi(e) >= 0) ctx->nw_warp_below = atoi(e);
 	e = getenv("KB_RF_CAND"); if (e && atoi(e) >= 0 && atoi(e) <= 256) ctx->rf_cand = atoi(e);
+	e = getenv("KB_SEED_TAIL_FAST"); if (e) ctx->seed_tail_fast = atoi(e) ? 1 : 0;
 	e = getenv("KB_SEED_STAGE"); if (e) ctx->seed_stage = atoi(e) ? 1 : 0;
 	e = getenv("KB_SEED_LD_HINT"); if (e) ctx->seed_ld_hint = atoi(e) ? 1 : 0;
 	e = getenv("KB_CAND_WIDE"); if (e) ctx->cand_wide = atoi(e) ? 1 : 0;
@@ -1306,7 +1308,7 @@ static int launch_pipeline(kb_ctx* ctx, kb_slot& sl)
 	sl.launches = 0;
 	CK(cudaEventRecord(sl.ev[0], s));
 	launch_pack(sl);
-	KbIndexDev ixs = ix; ixs.ld_hint = ctx->seed_ld_hint;   // the seeding kernels' loads of Occ blocks, table and SA entries (kb_load_blk)
+	KbIndexDev ixs = ix; ixs.ld_hint = ctx->seed_ld_hint | (ctx->seed_tail_fast ? 0 : 2);   // the seeding kernels' loads of Occ blocks, table and SA entries (kb_load_blk)
 	if (ctx->seed_queue && ix.sa_full != nullptr)
 	{
 		// with the full SA most searches finish against the text and reads differ widely in work: lane queue (kb_seed_lane)

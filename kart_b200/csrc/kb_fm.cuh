@@ -176,7 +176,7 @@ KB_HD KbBlk kb_load_blk(const uint32_t* occ, u64 blk, int hint = 0)
 	KbBlk b; const uint32_t* p = occ + (blk << 3);
 #if defined(__CUDA_ARCH__)
 	u32 l0, l1, h0, h1;
-	if (hint)
+	if (hint & 1)
 		asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
 		             : "=r"(b.c0), "=r"(b.c1), "=r"(b.c2), "=r"(b.c3), "=r"(l0), "=r"(l1), "=r"(h0), "=r"(h1) : "l"(p));
 	else
@@ -192,7 +192,7 @@ KB_HD KbBlk kb_load_blk(const uint32_t* occ, u64 blk, int hint = 0)
 KB_HD u64 kb_load_u64_once(const u64* p, int hint)
 {
 #if defined(__CUDA_ARCH__)
-	if (hint) { u64 v; asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p)); return v; }
+	if (hint & 1) { u64 v; asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p)); return v; }
 #else
 	(void)hint;
 #endif
@@ -290,7 +290,7 @@ KB_HD KbKtabE kb_load_ktab(const KbKtab* p, int hint = 0)
 {
 #if defined(__CUDA_ARCH__)
 	u32 r[4];
-	if (hint) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "l"(p));
+	if (hint & 1) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "l"(p));
 	else asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "l"(p));
 	return kb_ktab_unpack(((u64)r[1] << 32) | r[0], ((u64)r[3] << 32) | r[2]);
 #else
@@ -335,6 +335,54 @@ KB_HD int kb_unique_tail(const KbIndexDev& ix, const KbPk* rd, u64 row, int done
 	const u64 M5 = 0x5555555555555555ull;
 	const i64 tp = (i64)kb_load_u64_once(ix.sa_full + row, ix.ld_hint) + (i64)done;   // text position facing read position cur
 	*blocks += 1; *fail = false;
+	const int total = lim - cur;
+	if (total <= 0) return 0;
+	// Nearly every comparison lies inside one strand of the 2G text. Then the windows are cut at the READ's word boundaries (no funnel
+	// shift of code / n4 on the read side, one 16-byte load per window), the strand is decided once, and the reference side is the
+	// two-word funnel shift alone (reverse strand: of the mirrored forward window, bit-reversed and complemented). ~25 instructions per
+	// 32 bases instead of ~70 (r33: the pass around this function was the bulk of the kernel's 4750 instructions per read at 8 lanes).
+	// The result does not depend on how the stretch is cut into windows; `blocks` counts 32-base windows from `cur` as before.
+	const bool fwd = tp >= 0 && tp + (i64)total + 32 <= ix.G, rev = tp >= ix.G && tp + (i64)total + 32 <= ix.G2;
+	if ((fwd || rev) && !(ix.ld_hint & 2))   // bit 1 of ld_hint: KB_SEED_TAIL_FAST=0, the general loop below for everything (A/B)
+	{
+		int pos = cur; bool stopped = false;
+		while (pos < lim)
+		{
+			const int o = pos & 31;
+			const KbPk rw = kb_load_pk(rd + (pos >> 5));
+			const int room = 32 - o, left = lim - pos, want = left < room ? left : room;
+			const u64 rc = rw.code << (2 * o); const u32 rn = rw.n4 << o;   // read bases pos.. at the top; what is shifted in lies beyond `want`
+			const i64 q = tp + (i64)(pos - cur);
+			u64 gw;
+			if (fwd)
+			{
+				const u64* w = ix.ref64 + (q >> 5); const int sh = (int)(q & 31) * 2;
+				gw = KB_LDG(w); if (sh) gw = (gw << sh) | (KB_LDG(w + 1) >> (64 - sh));
+			}
+			else
+			{
+				const i64 f = ix.G2 - 32 - q;
+				const u64* w = ix.ref64 + (f >> 5); const int sh = (int)(f & 31) * 2;
+				u64 v = KB_LDG(w); if (sh) v = (v << sh) | (KB_LDG(w + 1) >> (64 - sh));
+#if defined(__CUDA_ARCH__)
+				v = __brevll(v);
+#else
+				{ u64 x = v; x = ((x >> 1) & M5) | ((x & M5) << 1); x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+				  x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4); v = __builtin_bswap64(x); }
+#endif
+				gw = ~(((v >> 1) & M5) | ((v & M5) << 1));
+			}
+			u64 x = rc ^ gw; x = (x | (x >> 1)) & M5;
+			const int i_mis = x ? (int)KB_CLZLL(x) >> 1 : 32, i_n = rn ? (int)KB_CLZ(rn) : 32;
+			const int st = i_mis < i_n ? i_mis : i_n;
+			if (st >= want) { pos += want; continue; }
+			pos += st; *fail = i_n != st; stopped = true;   // a non-ACGT read character ends the search without a step (it is looked at first)
+			break;
+		}
+		const int m = pos - cur;
+		*blocks += stopped ? (u32)(m >> 5) + 1u : (u32)((total + 31) >> 5);
+		return m;
+	}
 	int m = 0;
 	while (cur + m < lim)
 	{

@@ -70,7 +70,7 @@ struct KbIndexDev
 	const i64* chr_len;
 	const u8* mapq_lut;      // [score][diff-1], diff = 1..5 ; built on the host with the reference expression
 	i32 mapq_lut_scores;
-	i32 ld_hint;             // seeding kernels: 1 = Occ blocks, table and SA entries bypass L1 allocation (kb_load_blk)
+	i32 ld_hint;             // seeding kernels: bit 0 = Occ blocks, table and SA entries bypass L1 allocation (kb_load_blk); bit 1 = kb_unique_tail without its fast path
 };
 
 // 32 read characters: nt4 codes (2 bit, MSB first, 0 where the character is no base), n4 = "nt4 code is 4" and

@@ -287,12 +287,16 @@ def test_seeding_load_paths(built, monkeypatch):
         reads = pu.interleave(r1, r2)
         reads[3::50, 40] = ord("N")
         sets.append(reads)
-    for stage, hint in (("1", "1"), ("0", "1"), ("1", "0"), ("0", "0")):
+    counts = {}
+    for stage, hint, fast in (("1", "1", "1"), ("0", "1", "1"), ("1", "0", "0"), ("0", "0", "1"), ("1", "1", "0")):   # fast: kb_unique_tail's one-strand path
         monkeypatch.setenv("KB_SEED_STAGE", stage)
         monkeypatch.setenv("KB_SEED_LD_HINT", hint)
+        monkeypatch.setenv("KB_SEED_TAIL_FAST", fast)
         m = pu.make_mapper(idx, expand_sa=True, paired=True)
-        for reads in sets:
+        for k, reads in enumerate(sets):
             assert pu.compare_pairs(m, orc, reads) == 0
+            w = m.work()
+            assert counts.setdefault(k, (w["ext_steps"], w["occ_blocks"])) == (w["ext_steps"], w["occ_blocks"])   # the work counters do not depend on the path
 
 
 def test_segx_slab_sizes(built, monkeypatch):
